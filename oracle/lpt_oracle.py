@@ -1,0 +1,590 @@
+"""CPU oracle for the monofonIC LPT field pipeline  --  TEST INFRASTRUCTURE ONLY.
+
+This is a numpy (pocketfft, FP64) restatement of the reference algorithm for the hot path
+named in BASELINE.json.  It is the *checker* used by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product path (monofonic_b200/) never
+imports it; if the CUDA library is missing the product fails loudly instead.
+
+Parity status: PINNED.  tests/test_oracle_golden.py checks this module against all five
+golden regression files of the reference (tests/references/*.hdf5, converted to
+tests/golden/*.npz by tests/golden/make_golden.py) at the reference's own tolerance
+np.allclose(rtol=1e-9, atol=1e-14) (tests/scripts/compare_hdf5.py:66-75).
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+
+Conventions (include/grid_fft.hh, src/grid_fft.cc):
+  * real grid  [n0][n1][n2]           (the two pad reals per z-row are not modelled)
+  * k grid     [kx][ky][kz], kz = 0..n2/2   (non-transposed layout; the reference's
+    MPI build stores [ky][kx][kz] - a pure storage permutation, src/grid_fft.cc:125-128)
+  * symmetric normalisation: fwd = rfftn/sqrt(N^3), bwd = irfftn*sqrt(N^3)
+    (src/grid_fft.cc:69,199-205,222-224,256-257)
+  * Orszag pad/unpad follow the MPI-build semantics (Nyquist planes are never copied),
+    because the goldens were produced by an MPI-enabled build.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # multi-threaded pocketfft if scipy is around (same algorithm as numpy.fft)
+    import scipy.fft as _sfft
+except Exception:  # pragma: no cover
+    _sfft = None
+
+
+# --------------------------------------------------------------------------------------
+# FFT backend (pluggable so that bench.py can time the same algorithm with MKL via torch)
+# --------------------------------------------------------------------------------------
+class FFTBackend:
+    """numpy/scipy pocketfft.  workers>1 uses scipy's threaded pocketfft."""
+
+    def __init__(self, workers: int = 1):
+        self.workers = int(workers)
+
+    def rfftn(self, x):
+        if _sfft is not None:
+            return _sfft.rfftn(x, workers=self.workers)
+        return np.fft.rfftn(x)
+
+    def irfftn(self, X, s):
+        if _sfft is not None:
+            return _sfft.irfftn(X, s=s, workers=self.workers)
+        return np.fft.irfftn(X, s=s)
+
+    def fftn(self, x):
+        if _sfft is not None:
+            return _sfft.fftn(x, workers=self.workers)
+        return np.fft.fftn(x)
+
+    def ifftn(self, x):
+        if _sfft is not None:
+            return _sfft.ifftn(x, workers=self.workers)
+        return np.fft.ifftn(x)
+
+
+class TorchFFTBackend(FFTBackend):
+    """torch CPU (MKL) FFT with all host threads - only used as a *timed CPU baseline*."""
+
+    def __init__(self, threads: int | None = None):
+        import torch
+
+        self.torch = torch
+        if threads:
+            torch.set_num_threads(int(threads))
+        self.workers = torch.get_num_threads()
+
+    def rfftn(self, x):
+        t = self.torch
+        return t.fft.rfftn(t.from_numpy(np.ascontiguousarray(x))).numpy()
+
+    def irfftn(self, X, s):
+        t = self.torch
+        return t.fft.irfftn(t.from_numpy(np.ascontiguousarray(X)), s=tuple(s)).numpy()
+
+    def fftn(self, x):
+        t = self.torch
+        return t.fft.fftn(t.from_numpy(np.ascontiguousarray(x))).numpy()
+
+    def ifftn(self, x):
+        t = self.torch
+        return t.fft.ifftn(t.from_numpy(np.ascontiguousarray(x))).numpy()
+
+
+_DEFAULT_FFT = FFTBackend(1)
+
+
+# --------------------------------------------------------------------------------------
+# Grid helpers  (include/grid_fft.hh)
+# --------------------------------------------------------------------------------------
+class GridSpec:
+    """Geometry of an N^3 grid in a box of side L  (src/grid_fft.cc:82-91)."""
+
+    def __init__(self, n: int, boxlen: float, fft: FFTBackend | None = None):
+        self.n = int(n)
+        self.L = float(boxlen)
+        self.nh = self.n // 2
+        self.nzc = self.n // 2 + 1
+        self.kfac = 2.0 * np.pi / self.L
+        self.dx = self.L / self.n
+        self.norm = 1.0 / np.sqrt(float(self.n) ** 3)
+        self.fft = fft or _DEFAULT_FFT
+        i = np.arange(self.n)
+        # signed integer wavenumber: n - N*[n > N/2]   (include/grid_fft.hh:287-293; note '>')
+        self.nsigned = (i - self.n * (i > self.nh)).astype(np.float64)
+        self.k1d = self.nsigned * self.kfac
+        # gradient wavenumber: zero at the Nyquist index (include/grid_fft.hh:376-385,
+        # include/operators.hh:50-55)
+        self.g1d = np.where(i == self.nh, 0.0, self.k1d)
+
+    # -- FFTs with the reference's symmetric normalisation (src/grid_fft.cc:199-270)
+    def fwd(self, x):
+        return self.fft.rfftn(x) * self.norm
+
+    def bwd(self, X):
+        n = self.n
+        return self.fft.irfftn(X, (n, n, n)) * (float(n) ** 3 * self.norm)
+
+    # -- broadcastable k vectors on the half-spectrum [kx][ky][kz]
+    def kvec(self):
+        kx = self.k1d[:, None, None]
+        ky = self.k1d[None, :, None]
+        kz = self.k1d[None, None, : self.nzc]
+        return kx, ky, kz
+
+    def k2(self):
+        kx, ky, kz = self.kvec()
+        return kx * kx + ky * ky + kz * kz
+
+    def grad(self, d):
+        """i*k_d with k_d := 0 at that axis' Nyquist index  (include/grid_fft.hh:376-385)."""
+        shape = [1, 1, 1]
+        if d == 2:
+            g = self.g1d[: self.nzc]
+        else:
+            g = self.g1d
+        shape[d] = g.shape[0]
+        return 1j * g.reshape(shape)
+
+    def zeros_k(self):
+        return np.zeros((self.n, self.n, self.nzc), dtype=np.complex128)
+
+
+def zero_dc(X):
+    """Grid_FFT::zero_DC_mode in k-space  (include/grid_fft.hh:844-850)."""
+    X[0, 0, 0] = 0.0
+    return X
+
+
+def inverse_laplacian(g: GridSpec, X):
+    """Grid_FFT::apply_InverseLaplacian: x <- -x/|k|^2, then DC = 0
+    (include/grid_fft.hh:440-449).  The reference divides by zero at DC and then overwrites."""
+    k2 = g.k2()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = -X / k2
+    out[0, 0, 0] = 0.0
+    return out
+
+
+def shift_field_k(g: GridSpec, X, s):
+    """k-space part of Grid_FFT::shift_field (include/grid_fft.hh:832-842):
+    x <- x * exp(i (s.x kx dx + s.y ky dy + s.z kz dz)) for every stored mode (get_k, so the
+    Nyquist index carries +N/2)."""
+    kx, ky, kz = g.kvec()
+    ph = (s[0] * kx + s[1] * ky + s[2] * kz) * g.dx
+    return X * np.exp(1j * ph)
+
+
+def shift_field_r(g: GridSpec, x, s):
+    """Grid_FFT::shift_field on a real-space field: fwd, phase, bwd."""
+    return g.bwd(shift_field_k(g, g.fwd(x), s))
+
+
+# --------------------------------------------------------------------------------------
+# Fourier-space resampling == Grid_FFT::FourierInterpolateCopyTo, MPI branch
+# (src/grid_fft.cc:382-394, 432-463): only modes strictly inside both Nyquist limits are
+# copied, the target is zeroed first.
+# --------------------------------------------------------------------------------------
+def fourier_interpolate_copy(src: GridSpec, dst: GridSpec, X):
+    nf, nt = src.n, dst.n
+    out = dst.zeros_k()
+    if nf == nt:
+        out[...] = X
+        return out
+    fny_left = min(nf // 2, nt // 2)
+    fny_right = max(nf - nt // 2, nf // 2)
+    isend = np.array([i for i in range(nf) if (i < fny_left or i > fny_right)], dtype=np.int64)
+    irecv = np.where(isend < fny_left, isend, isend + nt - nf)
+    kz = fny_left  # k < fny2_left
+    out[np.ix_(irecv, irecv, np.arange(kz))] = X[np.ix_(isend, isend, np.arange(kz))]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Orszag 3/2 convolver  (include/convolution.hh:429-669, MPI-build semantics)
+# --------------------------------------------------------------------------------------
+class OrszagConvolver:
+    def __init__(self, g: GridSpec):
+        self.g = g
+        self.gp = GridSpec(3 * g.n // 2, g.L, g.fft)  # include/convolution.hh:464
+        self.nfft = 0
+
+    def pad_insert(self, A):
+        """pad_insert, MPI branch (include/convolution.hh:594-608): multiply by 1.5^1.5 and
+        FourierInterpolateCopyTo the padded grid (Nyquist planes dropped)."""
+        rfac = 1.5 ** 1.5
+        return fourier_interpolate_copy(self.g, self.gp, A * rfac)
+
+    def unpad(self, P):
+        """unpad, MPI branch (include/convolution.hh:657-665): FourierInterpolateCopyTo(fbuf),
+        then divide by rfac = sqrt(Np^3)/sqrt(N^3)."""
+        rfac = np.sqrt(float(self.gp.n) ** 3) / np.sqrt(float(self.g.n) ** 3)
+        return fourier_interpolate_copy(self.gp, self.g, P) / rfac
+
+    def convolve2(self, A, B):
+        """OrszagConvolver::convolve2 (include/convolution.hh:512-535)."""
+        a = self.gp.bwd(self.pad_insert(A))
+        b = self.gp.bwd(self.pad_insert(B))
+        self.nfft += 3
+        return self.unpad(self.gp.fwd(a * b))
+
+    def convolve3(self, A, B, C):
+        """convolve3 = convolve2(convolve2(A,B) truncated to the N grid, C)
+        (include/convolution.hh:542-549)."""
+        return self.convolve2(self.convolve2(A, B), C)
+
+    # ---- named products of BaseConvolver (include/convolution.hh:75-292)
+    def hess(self, F, a, b):
+        g = self.g
+        return g.grad(a) * g.grad(b) * F  # :147-151
+
+    def convolve_Hessians(self, F, d2l, G, d2r):
+        return self.convolve2(self.hess(F, *d2l), self.hess(G, *d2r))  # :137-160
+
+    def convolve_Hessians3(self, F, d2l, G, d2m, H, d2r):
+        return self.convolve3(self.hess(F, *d2l), self.hess(G, *d2m), self.hess(H, *d2r))  # :172-203
+
+    def convolve_SumOfHessians(self, F, d2l, G, d2r1, d2r2):
+        g = self.g
+        fac = g.grad(d2r1[0]) * g.grad(d2r1[1]) + g.grad(d2r2[0]) * g.grad(d2r2[1])
+        return self.convolve2(self.hess(F, *d2l), fac * G)  # :214-239
+
+    def convolve_DifferenceOfHessians(self, F, d2l, G, d2r1, d2r2):
+        g = self.g
+        fac = g.grad(d2r1[0]) * g.grad(d2r1[1]) - g.grad(d2r2[0]) * g.grad(d2r2[1])
+        return self.convolve2(self.hess(F, *d2l), fac * G)  # :250-274
+
+    def convolve_Gradients(self, F, d1l, G, d1r):
+        g = self.g
+        return self.convolve2(g.grad(d1l) * F, g.grad(d1r) * G)  # :75-96
+
+    def convolve_Gradient_and_Hessian(self, F, d1l, G, d2r):
+        """uses get_k (no Nyquist zeroing) and sign -i k  (include/convolution.hh:106-127)."""
+        kv = self.g.kvec()
+        return self.convolve2((-1j * kv[d1l]) * F, (-kv[d2r[0]] * kv[d2r[1]]) * G)
+
+    def multiply_field(self, F, G):
+        return self.convolve2(F, G)  # :282-292
+
+
+class NaiveConvolver(OrszagConvolver):
+    """NaiveConvolver (include/convolution.hh:296-426): same API, no padding."""
+
+    def __init__(self, g: GridSpec):
+        self.g = g
+        self.gp = g
+        self.nfft = 0
+
+    def convolve2(self, A, B):
+        self.nfft += 3
+        return self.g.fwd(self.g.bwd(A) * self.g.bwd(B))
+
+    def convolve3(self, A, B, C):
+        self.nfft += 4
+        return self.g.fwd(self.g.bwd(A) * self.g.bwd(B) * self.g.bwd(C))
+
+
+# --------------------------------------------------------------------------------------
+# Noise conditioning and first-order potential  (src/ic_generator.cc:341-358, 461-468)
+# --------------------------------------------------------------------------------------
+def condition_noise(g: GridSpec, W, fix=False, invert=False, remove_corners=False):
+    volfac = (g.L / g.n / 2.0 / np.pi) ** 1.5  # :210
+    W = W.copy()
+    if fix:
+        a = np.abs(W)
+        W = np.where(a != 0.0, W / np.where(a != 0.0, a, 1.0), W)  # :342-344
+    W = (-1.0 if invert else 1.0) * W / volfac  # :345
+    if remove_corners:
+        kny = g.kfac * g.n / 2
+        W = np.where(np.sqrt(g.k2()) > kny, 0.0, W)  # :352-358
+    return W
+
+
+def phi1_from_noise(g: GridSpec, W, amplitude):
+    """phi = -W*A(|k|)/|k|^2, DC=0  (src/ic_generator.cc:461-468).
+    `amplitude` is a vectorised callable A(|k|) (cosmology_calculator.hh:405-408)."""
+    k2 = g.k2()
+    kmod = np.sqrt(k2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        amp = amplitude(kmod)
+        phi = -(W * amp) / (kmod * kmod)
+    phi[0, 0, 0] = 0.0
+    return phi
+
+
+def radial_table(g: GridSpec, amplitude):
+    """Tabulate A(|k|) on the distinct integer |n|^2 values of the grid:
+    table[m] = A(kfac*sqrt(m)), m = 0..3(N/2)^2.  Host-side helper shared by tests."""
+    m = np.arange(3 * g.nh * g.nh + 1, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.asarray(amplitude(g.kfac * np.sqrt(m)), dtype=np.float64)
+    t = np.where(np.isfinite(t), t, 0.0)
+    return t
+
+
+# --------------------------------------------------------------------------------------
+# LPT source terms  (src/ic_generator.cc:475-574)
+# --------------------------------------------------------------------------------------
+def lpt_potentials(g: GridSpec, phi, order, Dplus0=1.0, convolver=None, tides=None):
+    """Returns dict(phi, phi2, phi3, A3=[..]) *after* growth-factor scaling (:561-574).
+    phi is the unscaled first-order potential in k-space."""
+    conv = convolver or OrszagConvolver(g)
+    g1 = -Dplus0
+    g2 = -3.0 / 7.0 * Dplus0 * Dplus0 if order > 1 else 0.0
+    g3 = 1.0 / 3.0 * Dplus0 ** 3 if order > 2 else 0.0
+    g3c = 1.0 / 7.0 * Dplus0 ** 3 if order > 2 else 0.0
+    out = {"phi": None, "phi2": None, "phi3": None, "A3": None}
+    phi2 = phi3 = None
+    A3 = None
+    if order > 1:
+        # :482-486
+        phi2 = conv.convolve_SumOfHessians(phi, (0, 0), phi, (1, 1), (2, 2))
+        phi2 = phi2 + conv.convolve_Hessians(phi, (1, 1), phi, (2, 2))
+        phi2 = phi2 - conv.convolve_Hessians(phi, (0, 1), phi, (0, 1))
+        phi2 = phi2 - conv.convolve_Hessians(phi, (0, 2), phi, (0, 2))
+        phi2 = phi2 - conv.convolve_Hessians(phi, (1, 2), phi, (1, 2))
+        if tides is not None:  # :488-497
+            lam = np.asarray(tides, dtype=np.float64)
+            kx, ky, kz = g.kvec()
+            fac_aniso = kx * kx * lam[0] + ky * ky * lam[1] + kz * kz * lam[2]
+            phi2 = phi2 - (lam.sum() * g.k2() + 4.0 / 3.0 * fac_aniso) * phi
+        phi2 = inverse_laplacian(g, phi2)  # :499
+    if order > 2:
+        # 3a  :522-526
+        phi3 = conv.convolve_Hessians3(phi, (0, 0), phi, (1, 1), phi, (2, 2))
+        phi3 = phi3 + 2.0 * conv.convolve_Hessians3(phi, (0, 1), phi, (0, 2), phi, (1, 2))
+        phi3 = phi3 - conv.convolve_Hessians3(phi, (1, 2), phi, (1, 2), phi, (0, 0))
+        phi3 = phi3 - conv.convolve_Hessians3(phi, (0, 2), phi, (0, 2), phi, (1, 1))
+        phi3 = phi3 - conv.convolve_Hessians3(phi, (0, 1), phi, (0, 1), phi, (2, 2))
+        # 3b  :533-538  (un-scaled phi2)
+        phi3 = phi3 + (-5.0 / 7.0) * conv.convolve_SumOfHessians(phi, (0, 0), phi2, (1, 1), (2, 2))
+        phi3 = phi3 + (-5.0 / 7.0) * conv.convolve_SumOfHessians(phi, (1, 1), phi2, (2, 2), (0, 0))
+        phi3 = phi3 + (-5.0 / 7.0) * conv.convolve_SumOfHessians(phi, (2, 2), phi2, (0, 0), (1, 1))
+        phi3 = phi3 + (10.0 / 7.0) * conv.convolve_Hessians(phi, (0, 1), phi2, (0, 1))
+        phi3 = phi3 + (10.0 / 7.0) * conv.convolve_Hessians(phi, (0, 2), phi2, (0, 2))
+        phi3 = phi3 + (10.0 / 7.0) * conv.convolve_Hessians(phi, (1, 2), phi2, (1, 2))
+        phi3 = inverse_laplacian(g, phi3)  # :539
+        # transverse term  :545-556
+        A3 = []
+        for d in range(3):
+            p, q = (d + 1) % 3, (d + 2) % 3
+            a = conv.convolve_Hessians(phi2, (d, p), phi, (d, q))
+            a = a - conv.convolve_Hessians(phi2, (d, q), phi, (d, p))
+            a = a + conv.convolve_DifferenceOfHessians(phi, (p, q), phi2, (p, p), (q, q))
+            a = a - conv.convolve_DifferenceOfHessians(phi2, (p, q), phi, (p, p), (q, q))
+            A3.append(inverse_laplacian(g, a))
+    out["phi"] = phi * g1
+    if order > 1:
+        out["phi2"] = phi2 * g2
+    if order > 2:
+        out["phi3"] = phi3 * g3
+        out["A3"] = [a * g3c for a in A3]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Displacement / velocity assembly  (src/ic_generator.cc:832-871, 888-942)
+# --------------------------------------------------------------------------------------
+def displacement_k(g: GridSpec, pots, order, d, scale=1.0):
+    """k-space Psi_d * scale; scale = lunit/boxlen (:866)."""
+    p, q = (d + 1) % 3, (d + 2) % 3
+    tot = pots["phi"].copy()
+    if order > 1:
+        tot = tot + pots["phi2"]
+    if order > 2:
+        tot = tot + pots["phi3"]
+    tmp = g.grad(d) * tot
+    if order > 2:
+        tmp = tmp + g.grad(p) * pots["A3"][q] - g.grad(q) * pots["A3"][p]
+    tmp = tmp * scale
+    return zero_dc(tmp)
+
+
+def velocity_k(g: GridSpec, pots, order, d, vfac, scale=1.0, vbc=None):
+    """k-space v_d * scale; scale = vunit/boxlen (:937).
+    vbc = (C_species, theta_bc_amplitude(|k|) callable, W) adds the relative-velocity term (:918-921)."""
+    p, q = (d + 1) % 3, (d + 2) % 3
+    tot = vfac * pots["phi"]
+    if order > 1:
+        tot = tot + (2 * vfac) * pots["phi2"]
+    if order > 2:
+        tot = tot + (3 * vfac) * pots["phi3"]
+    tmp = g.grad(d) * tot
+    if order > 2:
+        tmp = tmp + (3 * vfac) * (g.grad(p) * pots["A3"][q] - g.grad(q) * pots["A3"][p])
+    if vbc is not None:
+        C, amp, W = vbc
+        k2 = g.k2()
+        kn = np.sqrt(k2)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            term = vfac * C * amp(kn) * W * g.grad(d) / (kn * kn)
+        term[0, 0, 0] = 0.0
+        tmp = tmp - term
+    tmp = tmp * scale
+    return zero_dc(tmp)
+
+
+def density_k(g: GridSpec, pots):
+    """first-order SPT density delta = k^2 phi  (src/ic_generator.cc:962-973)."""
+    return g.k2() * pots["phi"]
+
+
+def fields(g: GridSpec, pots, order, vfac, lunit=1.0, vunit=1.0):
+    """all six real-space component fields + density; defaults = generic output plugin
+    (lunit=vunit=1, output_generic.cc:74-76); fields are in box units * unit (:866,:937)."""
+    out = {}
+    for d, nm in enumerate("xyz"):
+        out["d" + nm] = g.bwd(displacement_k(g, pots, order, d, lunit / g.L))
+        out["v" + nm] = g.bwd(velocity_k(g, pots, order, d, vfac, vunit / g.L))
+    out["delta"] = g.bwd(density_k(g, pots))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Particle lattice  (include/particle_generator.hh)
+# --------------------------------------------------------------------------------------
+LATTICE_SHIFTS = {  # :48-56
+    0: [(0.0, 0.0, 0.0)],
+    1: [(0.0, 0.0, 0.0), (0.5, 0.5, 0.5)],
+    2: [(0.0, 0.0, 0.0), (0.0, 0.5, 0.5), (0.5, 0.0, 0.5), (0.5, 0.5, 0.0)],
+    3: [(0.0, 0.0, 0.0), (0.0, 0.0, 0.5), (0.0, 0.5, 0.0), (0.0, 0.5, 0.5),
+        (0.5, 0.0, 0.0), (0.5, 0.0, 0.5), (0.5, 0.5, 0.0), (0.5, 0.5, 0.5)],
+}
+SECOND_LATTICE_SHIFT = {0: (0.5, 0.5, 0.5), 1: (0.5, 0.5, 0.0), 2: (0.5, 0.5, 0.5), 3: (0.25, 0.25, 0.25)}  # :58-64
+LATTICE_TYPES = {"sc": 0, "bcc": 1, "fcc": 2, "rsc": 3}
+
+
+def particle_ids(n, lattice_type, id_offset=0, ids64=False):
+    """lattice_generator ctor (include/particle_generator.hh:129-170):
+    id = IDoffset*ov*N^3 + ov*cell + iload stored at ipcount + iload*N^3."""
+    ov = 1 << max(0, lattice_type)
+    ncell = n ** 3
+    cell = np.arange(ncell, dtype=np.uint64)
+    off = np.uint64(id_offset * ov * ncell)
+    ids = np.empty(ov * ncell, dtype=np.uint64)
+    for iload in range(ov):
+        ids[iload * ncell:(iload + 1) * ncell] = off + np.uint64(ov) * cell + np.uint64(iload)
+    return ids if ids64 else ids.astype(np.uint32)
+
+
+def _shift_sequence(lattice_type, lattice_index):
+    """absolute shift of each sub-lattice and the *relative* shift applied to the field
+    before reading it out (set_positions :433-445)."""
+    shifts = LATTICE_SHIFTS[lattice_type]
+    sec = SECOND_LATTICE_SHIFT[lattice_type] if lattice_index == 1 else (0.0, 0.0, 0.0)
+    seq = []
+    for ish, s in enumerate(shifts):
+        rel = []
+        if ish == 0 and lattice_index == 1:
+            rel.append(SECOND_LATTICE_SHIFT[lattice_type])
+        if ish > 0:
+            rel.append(tuple(a - b for a, b in zip(s, shifts[ish - 1])))
+        absolute = tuple(a + b for a, b in zip(s, sec))
+        seq.append((absolute, rel))
+    return seq
+
+
+def set_positions(g: GridSpec, field_r, d, lattice_type, lattice_index, lunit, real64=True):
+    """lattice_generator::set_positions for Bravais lattices (:422-467).  Returns the d-th
+    coordinate of all particles (sub-lattices concatenated) in the storage dtype."""
+    n = g.n
+    f = field_r
+    outs = []
+    idx = np.arange(n, dtype=np.float64)
+    for absolute, rel in _shift_sequence(lattice_type, lattice_index):
+        for s in rel:
+            f = shift_field_r(g, f, s)
+        shape = [1, 1, 1]
+        shape[d] = n
+        q = ((idx + absolute[d]) / float(n)).reshape(shape)  # get_unit_r_shifted, grid_fft.hh:243-252
+        pos = q * lunit + f
+        outs.append(pos.reshape(-1))
+    res = np.concatenate(outs)
+    return res if real64 else res.astype(np.float32)
+
+
+def set_velocities(g: GridSpec, field_r, lattice_type, lattice_index, real64=True):
+    """lattice_generator::set_velocities (:520-562)."""
+    f = field_r
+    outs = []
+    for _, rel in _shift_sequence(lattice_type, lattice_index):
+        for s in rel:
+            f = shift_field_r(g, f, s)
+        outs.append(f.reshape(-1).copy())
+    res = np.concatenate(outs)
+    return res if real64 else res.astype(np.float32)
+
+
+def set_masses(g: GridSpec, field_r, lattice_type, lattice_index, munit, real64=True):
+    """lattice_generator::set_masses, Bravais branch (:292-350)."""
+    ov = 1 << max(0, lattice_type)
+    pmean = munit / float(g.n ** 3 * ov)
+    f = field_r
+    outs = []
+    for _, rel in _shift_sequence(lattice_type, lattice_index):
+        for s in rel:
+            f = shift_field_r(g, f, s)
+        outs.append((pmean * f).reshape(-1))
+    res = np.concatenate(outs)
+    return res if real64 else res.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# Whole pipeline (one species) - used by tests, smoke() and the CPU baseline
+# --------------------------------------------------------------------------------------
+def run_pipeline(n, boxlen, W, amplitude, order, Dplus0, vfac, lattice="sc", lunit=1.0, vunit=1.0,
+                 real64=True, ids64=False, fft=None, particles=True):
+    """noise (k-space, already conditioned) -> potentials -> Psi, v (-> particles)."""
+    g = GridSpec(n, boxlen, fft)
+    phi = phi1_from_noise(g, W, amplitude)
+    pots = lpt_potentials(g, phi, order, Dplus0)
+    res = {"pots": pots}
+    lt = LATTICE_TYPES[lattice]
+    pos, vel = [], []
+    flds = {}
+    for d, nm in enumerate("xyz"):
+        dr = g.bwd(displacement_k(g, pots, order, d, lunit / boxlen))
+        flds["d" + nm] = dr
+        if particles:
+            pos.append(set_positions(g, dr, d, lt, 0, lunit, real64))
+    for d, nm in enumerate("xyz"):
+        vr = g.bwd(velocity_k(g, pots, order, d, vfac, vunit / boxlen))
+        flds["v" + nm] = vr
+        if particles:
+            vel.append(set_velocities(g, vr, lt, 0, real64))
+    res["fields"] = flds
+    if particles:
+        res["pos"] = np.stack(pos, axis=1)
+        res["vel"] = np.stack(vel, axis=1)
+        res["ids"] = particle_ids(n, lt, 0, ids64)
+    return res
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic inputs shared by tests / bench (NGenIC-like Hermitian white noise)
+# --------------------------------------------------------------------------------------
+def make_white_noise_k(n, seed, nyquist_zero=True):
+    """Unit-variance complex Gaussian white noise on the half spectrum [kx][ky][kz] that is the
+    transform of a real field.  With nyquist_zero (NGenIC behaviour, random_ngenic.cc:117) all
+    Nyquist planes and DC are zero."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, n, n))
+    W = np.fft.rfftn(x) / np.sqrt(float(n) ** 3)
+    if nyquist_zero:
+        W[n // 2, :, :] = 0.0
+        W[:, n // 2, :] = 0.0
+        W[:, :, n // 2] = 0.0
+        W[0, 0, 0] = 0.0
+    return np.ascontiguousarray(W)
+
+
+def power_law_amplitude(ns=0.9649, kcut=0.5, norm=1.0):
+    """A smooth stand-in for k^{ns/2} T(k) sqrt(pnorm) (BBKS-like roll-off)."""
+
+    def amp(k):
+        k = np.asarray(k, dtype=np.float64)
+        q = k / kcut
+        T = np.log1p(2.34 * q) / np.where(q > 0, 2.34 * q, 1.0) * (
+            1 + 3.89 * q + (16.1 * q) ** 2 + (5.46 * q) ** 3 + (6.71 * q) ** 4) ** -0.25
+        T = np.where(q > 0, T, 1.0)
+        return norm * np.power(k, 0.5 * ns) * T
+
+    return amp

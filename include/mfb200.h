@@ -1,0 +1,135 @@
+/* mfb200.h - C ABI of libmfb200: the B200-native LPT field pipeline of monofonIC (MUSIC2).
+ *
+ * This is the drop-in boundary (SURVEY.md section 8b / DESIGN.md section 2).  The reference has no
+ * FFI around this path (header templates in one executable), so every entry point names the
+ * reference member function / loop it replaces (paths relative to the reference repo).  The host
+ * classes in include/mfb/ (C++) and monofonic_b200/ (Python, ctypes) are thin mirrors of the
+ * reference's Grid_FFT / OrszagConvolver / op:: / particle::lattice_generator on top of this ABI.
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; mfb_last_error() gives the message
+ *     (the reference throws std::runtime_error / aborts; the C++ shim re-throws).
+ *   - FP64 only (CODE_PRECISION=DOUBLE, the reference default, CMakeLists.txt:89-96).
+ *   - a grid is stored on the device exactly like the reference's non-distributed Grid_FFT
+ *     (src/grid_fft.cc:45-54,73-74): real view [n0][n1][n2+2], complex view [n0][n1][n2/2+1],
+ *     in place.  Multi-GPU slabs (mfb_dist_*) use the reference's MPI layout: real slab along
+ *     axis 0, k-space slab along axis 1, transposed [ky_loc][kx][kz] (src/grid_fft.cc:120-128).
+ *   - FFTs carry the symmetric 1/sqrt(n0 n1 n2) normalisation (src/grid_fft.cc:199-205).
+ *   - no CPU fallback: without a CUDA device mfb_init fails.
+ */
+#ifndef MFB200_H
+#define MFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfb_grid mfb_grid; /* opaque: replaces Grid_FFT<real_t> (include/grid_fft.hh:40-914) */
+typedef struct mfb_conv mfb_conv; /* opaque: replaces OrszagConvolver<real_t> (include/convolution.hh:429-669) */
+typedef struct mfb_particles mfb_particles; /* opaque: replaces particle::container (include/particle_container.hh:30-189) */
+
+enum { MFB_RSPACE = 1, MFB_KSPACE = 0 };                           /* space_t, include/grid_fft.hh:29 */
+enum { MFB_OP_ASSIGN = 0, MFB_OP_ADD = 1, MFB_OP_SUB = 2, MFB_OP_MULADD = 3 }; /* include/operators.hh:25-35 */
+enum { MFB_LATTICE_SC = 0, MFB_LATTICE_BCC = 1, MFB_LATTICE_FCC = 2, MFB_LATTICE_RSC = 3 }; /* particle_generator.hh:31-39 */
+
+/* ---- library / device ------------------------------------------------------------------ */
+int mfb_init(int device);            /* selects the CUDA device, creates the stream; fails without a GPU */
+int mfb_finalize(void);
+const char* mfb_last_error(void);
+const char* mfb_build_info(void);    /* "cuda sm_100a" for the product build */
+int mfb_synchronize(void);
+void* mfb_stream(void);              /* the cudaStream_t all work is issued on */
+long long mfb_kernel_launches(void); /* number of kernels launched so far (bench.py gpu_launches) */
+int mfb_supported_fft_size(int n);   /* 1 if an FFT plan exists for line length n */
+
+/* ---- Grid_FFT ---------------------------------------------------------------------------- */
+/* Grid_FFT(N, L, allocate=true, initialspace) + allocate()        include/grid_fft.hh:77-83, src/grid_fft.cc:40-197 */
+int mfb_grid_create(mfb_grid** g, const int n[3], const double L[3], int space);
+int mfb_grid_destroy(mfb_grid* g);                                 /* reset(), include/grid_fft.hh:95-101 */
+int mfb_grid_space(const mfb_grid* g);
+size_t mfb_grid_ntot(const mfb_grid* g);                           /* ntot_ in doubles, src/grid_fft.cc:45 */
+void* mfb_grid_device_ptr(mfb_grid* g);
+/* host<->device copies of the whole buffer (ntot doubles) - the coherence primitive under relem/kelem/data_ */
+int mfb_grid_upload(mfb_grid* g, const double* host);
+int mfb_grid_download(const mfb_grid* g, double* host);
+/* FourierTransformForward/Backward(do_transform)                  src/grid_fft.cc:208-270 */
+int mfb_fft_forward(mfb_grid* g, int do_transform);
+int mfb_fft_backward(mfb_grid* g, int do_transform);
+int mfb_grid_zero(mfb_grid* g);                                    /* zero(), include/grid_fft.hh:150-155 */
+int mfb_grid_copy(mfb_grid* dst, const mfb_grid* src);             /* copy_from(), :157-177 */
+int mfb_grid_scale(mfb_grid* g, double a);                         /* operator*=, :392-403 */
+int mfb_grid_axpy(mfb_grid* y, double a, const mfb_grid* x, double b); /* y = a*y + b*x (same space) */
+int mfb_grid_affine(mfb_grid* g, double a, double b);              /* x <- a + b*x in real space (src/ic_generator.cc:673-675) */
+int mfb_grid_zero_dc(mfb_grid* g);                                 /* zero_DC_mode(), :844-887 (both spaces) */
+int mfb_grid_inverse_laplacian(mfb_grid* g);                       /* apply_InverseLaplacian(), :440-449 */
+int mfb_grid_laplacian(mfb_grid* g, int negative);                 /* apply_Laplacian / apply_negative_Laplacian, :418-438 */
+int mfb_grid_shift_field(mfb_grid* g, const double s[3], int transform_back); /* shift_field(), :832-842 */
+int mfb_grid_mean(mfb_grid* g, double* out);                       /* mean(), :555-595 */
+int mfb_grid_std(mfb_grid* g, double* out);                        /* std(), :507-553 */
+int mfb_grid_2norm(mfb_grid* g, double* out);                      /* compute_2norm(), :485-505 (real space) */
+int mfb_grid_max_neighbour_diff(mfb_grid* g, double* out);         /* src/ic_generator.cc:713-735 */
+int mfb_fourier_resample(mfb_grid* src, mfb_grid* dst);            /* FourierInterpolateCopyTo(), src/grid_fft.cc:273-492 */
+
+/* ---- pipeline k-space operators (src/ic_generator.cc) ------------------------------------- */
+/* wnoise <- (+-1) wnoise/volfac [, w/|w| fixing][, corner-mode cut]            :341-358 */
+int mfb_noise_condition(mfb_grid* w, double volfac, int fix, int invert, int remove_corners);
+/* out = in * A(|k|) * (inv_k2 ? -1/k^2 : 1), DC=0.  table[m] = A(kfac*sqrt(m)), m = |n|^2 = 0..3(N/2)^2:
+   the transfer plugin is evaluated on the host once per distinct |k|           :461-468, :667-670 */
+int mfb_apply_radial_table(mfb_grid* out, const mfb_grid* in, const double* table, size_t ntable, int inv_k2);
+/* phi2 -= (sum(lambda) k^2 + 4/3 sum lambda_d k_d^2) phi                        :492-496 */
+int mfb_add_tides(mfb_grid* phi2, const mfb_grid* phi, const double lambda[3]);
+/* out = G_d (w1 phi + w2 phi2 + w3 phi3) + wc (G_p A_q - G_q A_p), * scale, DC=0 (k-space)
+   displacement: w=(1,1,1,1), scale=lunit/L  :841-870;  velocity: w=vfac*(1,2,3,3), scale=vunit/L  :896-941.
+   phi2/phi3/A3 may be NULL (lower LPT order).  vbc_* add  - cvbc*T(|k|)*W*G_d/k^2  (:918-921) when non-NULL. */
+int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* phi2, const mfb_grid* phi3,
+                     mfb_grid* const A3[3], double w1, double w2, double w3, double wc, double scale,
+                     const mfb_grid* wnoise, const double* vbc_table, size_t ntable, double cvbc);
+/* delta = k^2 phi  (first-order SPT density, :962-973) */
+int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi);
+
+/* ---- OrszagConvolver ------------------------------------------------------------------------ */
+int mfb_conv_create(mfb_conv** c, const int n[3], const double L[3]);      /* include/convolution.hh:463-495 */
+int mfb_conv_destroy(mfb_conv* c);
+size_t mfb_conv_workspace_bytes(const mfb_conv* c);
+/* All products: inputs are k-space N-grids, `out` is a k-space N-grid updated with `op` (alpha for MULADD).
+   dims are axis pairs {a,b}: the operand is (i k_a)(i k_b) f^ with the gradient zeroed at Nyquist. */
+int mfb_conv_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r[2],
+                      mfb_grid* out, int op, double alpha);                 /* convolve_Hessians 2-field :137-160 */
+int mfb_conv_hessians3(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* m, const int d2m[2], mfb_grid* r,
+                       const int d2r[2], mfb_grid* out, int op, double alpha); /* 3-field :172-203 (= two convolve2, :542-549) */
+int mfb_conv_sum_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r1[2],
+                          const int d2r2[2], mfb_grid* out, int op, double alpha); /* convolve_SumOfHessians :214-239 */
+int mfb_conv_diff_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r1[2],
+                           const int d2r2[2], mfb_grid* out, int op, double alpha); /* convolve_DifferenceOfHessians :250-274 */
+int mfb_conv_gradients(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, int d1r, mfb_grid* out, int op,
+                       double alpha);                                       /* convolve_Gradients :75-96 */
+int mfb_conv_gradient_hessian(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, const int d2r[2], mfb_grid* out,
+                              int op, double alpha);                        /* convolve_Gradient_and_Hessian :106-127 */
+int mfb_conv_multiply(mfb_conv* c, mfb_grid* l, mfb_grid* r, mfb_grid* out, int op, double alpha); /* multiply_field :282-292 */
+/* The whole source stage of ic_generator::run (:475-574): phi2, phi3, A3 from phi (un-scaled, k-space), then the
+   growth-factor scaling g1,g2,g3,g3c.  phi2/phi3/A3 may be NULL below the requested order. */
+int mfb_lpt_sources(mfb_conv* c, int order, double Dplus0, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3,
+                    mfb_grid* const A3[3], const double* tides_lambda);
+
+/* ---- particle::lattice_generator -------------------------------------------------------------- */
+/* container::allocate (particle_container.hh:60-80): device AoS buffers pos[3*np], vel[3*np], ids[np], mass[np] */
+int mfb_particles_create(mfb_particles** p, const int n[3], int lattice_type, int real64, int ids64, int with_masses);
+int mfb_particles_destroy(mfb_particles* p);
+size_t mfb_particles_count(const mfb_particles* p);
+/* lattice_generator ctor, Bravais branch (particle_generator.hh:129-170) */
+int mfb_particles_set_ids(mfb_particles* p, unsigned long long id_offset_species);
+/* set_positions / set_velocities / set_masses, Bravais branch (:422-467, :520-562, :292-350).
+   `field` is a real-space grid; it is phase-shifted in place exactly like the reference. */
+int mfb_particles_set_positions(mfb_particles* p, int lattice_index, int idim, double lunit, mfb_grid* field);
+int mfb_particles_set_velocities(mfb_particles* p, int lattice_index, int idim, mfb_grid* field);
+int mfb_particles_set_masses(mfb_particles* p, int lattice_index, double munit, mfb_grid* field);
+/* device -> host copies into the container vectors the output plugins read (get_*_ptr, particle_container.hh:110-148) */
+int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* ids, void* mass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB200_H */

@@ -1,0 +1,288 @@
+// fft_kernels.cuh - the FFT pass kernels of the LPT pipeline (FP64, sm_100a).
+//
+//   strided_pass_kernel : complex FFT along a strided axis (x or y) for a tile of T adjacent-k_z
+//                         lines; optional spectral zero-padding of the input (N -> 3N/2), spectral
+//                         truncation of the output (3N/2 -> N), k-space operand factor at load
+//                         (Hessian / gradient of the potential), scale + output operator
+//                         (=, +=, -=, += alpha*) at store.          [replaces fftw_execute x/y sweeps,
+//                         OrszagConvolver::pad_insert/unpad, op::assign_to & friends]
+//   z_c2r_kernel/z_r2c_kernel : the contiguous-axis real<->half-complex pass, two real rows per
+//                         complex FFT, in place in the reference's padded-row layout
+//                         (src/grid_fft.cc:45-54,73-74).
+//   z_conv_kernel       : fused  c2r(A) , c2r(B) , A*B , r2c  along z for the padded grid -
+//                         the padded real-space fields never touch HBM
+//                         (include/convolution.hh:524-532 collapsed into one pass).
+#pragma once
+#include "fft_core.cuh"
+
+namespace mfb {
+
+enum OutOp { OP_ASSIGN = 0, OP_ADD = 1, OP_SUB = 2, OP_MULADD = 3 };
+
+// k-space factor applied to an operand element at integer wave index (ix,iy,iz):
+//   f = c1*K[a1]*K[b1] + c2*K[a2]*K[b2],   K[d] = kf[d] * (i_d - n[d]*[i_d > n[d]/2]), 0 at i_d == n[d]/2
+// axis index -1 means "1".  imag: multiply by i on top (single gradient).
+struct OperandFactor {
+    int enabled;
+    int a1, b1, a2, b2;
+    double c1, c2;
+    int imag;
+    int n[3];      // grid size per axis (wave-number folding)
+    double kf[3];  // 2 pi / L per axis
+};
+
+struct StridedArgs {
+    const double2* in;
+    double2* out;
+    ptrdiff_t in_ps, in_as;    // element strides of the position axis / the "a" (other) axis
+    ptrdiff_t out_ps, out_as;
+    int na;                    // number of a-indices
+    int nz;                    // number of contiguous lines per a (tiles cover [0,nz))
+    int nz_fft;                // lines >= nz_fft are not transformed (only zero-filled on assign)
+    int n_in, n_out;           // logical input / output lengths (<= n): spectral pad / truncate
+    int inverse;               // backward transform (conj at load and store)
+    double scale;              // applied at store
+    OperandFactor f;
+    int pos_axis, a_axis;      // which grid axis (0=x,1=y) the position / a index is (for f)
+    int op;                    // OutOp
+    double alpha;
+    int a_skip;                // a-index whose lines are identically zero (Nyquist), -1: none
+    int zero_fill;             // on OP_ASSIGN also write zeros to skipped lines / Nyquist outputs
+};
+
+MFB_HD double wave_k(int i, int n, double kfac) {
+    return (i == n / 2) ? 0.0 : kfac * double(i - ((i > n / 2) ? n : 0));
+}
+
+template <class P>
+__global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N;
+    constexpr int T = P::T;
+    const int tid = threadIdx.x;
+    const int line = tid % T;
+    const int q = tid / T;
+    const int tiles_per_a = (A.nz + T - 1) / T;
+    const int a = blockIdx.x / tiles_per_a;
+    const int z0 = (blockIdx.x - a * tiles_per_a) * T;
+    const int iz = z0 + line;
+    const bool line_valid = iz < A.nz;
+    double2* obase = A.out + ptrdiff_t(a) * A.out_as + iz;
+
+    // ---- lines that carry no data: optional zero fill, no transform
+    const bool skip_tile = (a == A.a_skip) || (z0 >= A.nz_fft);
+    if (skip_tile) {
+        if (A.zero_fill && A.op == OP_ASSIGN && line_valid) {
+            for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(obase + ptrdiff_t(k) * A.out_ps, make_double2(0.0, 0.0));
+        }
+        return;
+    }
+    const bool fft_line = line_valid && iz < A.nz_fft;
+
+    // ---- per-thread operand factor polynomial in K_pos:  f = q0 + q1*Kp + q2*Kp^2
+    double q0 = 1.0, q1 = 0.0, q2 = 0.0;
+    if (A.f.enabled) {
+        const double Ka = wave_k(a, A.f.n[A.a_axis], A.f.kf[A.a_axis]);
+        const double Kz = wave_k(iz, A.f.n[2], A.f.kf[2]);
+        q0 = 0.0;
+        auto term = [&](int d1, int d2, double c) {
+            if (c == 0.0) return;
+            int np = 0;
+            double rest = c;
+            int dd[2] = {d1, d2};
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int d = dd[t];
+                if (d < 0) continue;
+                if (d == A.pos_axis) ++np;
+                else if (d == A.a_axis) rest *= Ka;
+                else rest *= Kz;
+            }
+            if (np == 0) q0 += rest;
+            else if (np == 1) q1 += rest;
+            else q2 += rest;
+        };
+        term(A.f.a1, A.f.b1, A.f.c1);
+        term(A.f.a2, A.f.b2, A.f.c2);
+    }
+
+    const double2* ibase = A.in + ptrdiff_t(a) * A.in_as + iz;
+    const int hin = A.n_in / 2;
+    const int hout = A.n_out / 2;
+
+    auto loader = [&](int pos, int /*line*/) -> double2 {
+        if (!fft_line) return make_double2(0.0, 0.0);
+        int src = pos;
+        if (A.n_in != N) {
+            if (pos < hin) src = pos;
+            else if (pos > N - hin) src = pos - (N - A.n_in);
+            else return make_double2(0.0, 0.0);
+        }
+        double2 v = mfb_ld_stream(ibase + ptrdiff_t(src) * A.in_ps);
+        if (A.f.enabled) {
+            const double Kp = wave_k(src, A.f.n[A.pos_axis], A.f.kf[A.pos_axis]);
+            const double fac = fma(fma(q2, Kp, q1), Kp, q0);
+            v = A.f.imag ? make_double2(-v.y * fac, v.x * fac) : make_double2(v.x * fac, v.y * fac);
+        }
+        if (A.inverse) v.y = -v.y;
+        return v;
+    };
+    auto storer = [&](int k, int /*line*/, double2 v) {
+        if (!fft_line) return;
+        int dst = k;
+        if (A.n_out != N) {
+            if (k < hout) dst = k;
+            else if (k > N - hout) dst = k - (N - A.n_out);
+            else return;
+        }
+        v = make_double2(v.x * A.scale, (A.inverse ? -v.y : v.y) * A.scale);
+        double2* p = obase + ptrdiff_t(dst) * A.out_ps;
+        if (A.op != OP_ASSIGN) {
+            const double2 o = mfb_ld_stream(p);
+            const double al = (A.op == OP_ADD) ? 1.0 : ((A.op == OP_SUB) ? -1.0 : A.alpha);
+            v = make_double2(fma(al, v.x, o.x), fma(al, v.y, o.y));
+        }
+        mfb_st_stream(p, v);
+    };
+
+    fft_tile<P, false, true, true>(sm, tw, line, q, true, loader, storer);
+
+    // Nyquist output of a truncated transform is defined to be zero (include/convolution.hh:641-643)
+    if (A.zero_fill && A.op == OP_ASSIGN && A.n_out != N && q == 0 && line_valid) {
+        mfb_st_stream(obase + ptrdiff_t(hout) * A.out_ps, make_double2(0.0, 0.0));
+    }
+    // lines of a partially transformed tile beyond nz_fft
+    if (A.zero_fill && A.op == OP_ASSIGN && line_valid && !fft_line) {
+        for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(obase + ptrdiff_t(k) * A.out_ps, make_double2(0.0, 0.0));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// z pass, half-complex -> real, in place.  rows: nrows rows of `pitch` doubles, each holding
+// n/2+1 complex on input and n reals (+2 pad) on output.  One complex FFT serves two rows.
+template <class P>
+__global__ void __launch_bounds__(P::NTHREADS) z_c2r_kernel(double* __restrict__ data, ptrdiff_t pitch, long nrows,
+                                                            double scale, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N, T = P::T, NC = N / 2 + 1;
+    const int tid = threadIdx.x;
+    const long row0 = long(blockIdx.x) * (2 * T);
+    // pack: Z[k] = X1[k] + i X2[k], Z[n-k] = conj(X1[k]) + i conj(X2[k]); store conj(Z) (inverse trick)
+    for (int idx = tid; idx < T * NC; idx += P::NTHREADS) {
+        const int l = idx / NC, k = idx - l * NC;
+        const long r1 = row0 + 2 * l;
+        double2 x1 = make_double2(0.0, 0.0), x2 = x1;
+        if (r1 < nrows) x1 = mfb_ld_stream(reinterpret_cast<const double2*>(data + r1 * pitch) + k);
+        if (r1 + 1 < nrows) x2 = mfb_ld_stream(reinterpret_cast<const double2*>(data + (r1 + 1) * pitch) + k);
+        if (k == 0 || k == N / 2) { x1.y = 0.0; x2.y = 0.0; }  // c2r ignores these imaginary parts
+        sm[P::smem_addr(k, l)] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
+        if (k > 0 && k < N / 2) sm[P::smem_addr(N - k, l)] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
+    }
+    __syncthreads();
+    NoLoader nl; NoStorer ns;
+    fft_tile<P, false, false, false>(sm, tw, tid % T, tid / T, true, nl, ns);
+    __syncthreads();
+    for (int idx = tid; idx < T * N; idx += P::NTHREADS) {
+        const int l = idx / N, j = idx - l * N;
+        const long r1 = row0 + 2 * l;
+        const double2 z = sm[P::smem_addr(P::pos_of_freq(j), l)];
+        if (r1 < nrows) data[r1 * pitch + j] = z.x * scale;
+        if (r1 + 1 < nrows) data[(r1 + 1) * pitch + j] = -z.y * scale;
+    }
+}
+
+// z pass, real -> half-complex, in place.
+template <class P>
+__global__ void __launch_bounds__(P::NTHREADS) z_r2c_kernel(double* __restrict__ data, ptrdiff_t pitch, long nrows,
+                                                            double scale, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N, T = P::T, NC = N / 2 + 1;
+    const int tid = threadIdx.x;
+    const long row0 = long(blockIdx.x) * (2 * T);
+    for (int idx = tid; idx < T * N; idx += P::NTHREADS) {
+        const int l = idx / N, j = idx - l * N;
+        const long r1 = row0 + 2 * l;
+        double2 z = make_double2(0.0, 0.0);
+        if (r1 < nrows) z.x = mfb_ld_stream1(data + r1 * pitch + j);
+        if (r1 + 1 < nrows) z.y = mfb_ld_stream1(data + (r1 + 1) * pitch + j);
+        sm[P::smem_addr(j, l)] = z;
+    }
+    __syncthreads();
+    NoLoader nl; NoStorer ns;
+    fft_tile<P, false, false, false>(sm, tw, tid % T, tid / T, true, nl, ns);
+    __syncthreads();
+    for (int idx = tid; idx < T * NC; idx += P::NTHREADS) {
+        const int l = idx / NC, k = idx - l * NC;
+        const long r1 = row0 + 2 * l;
+        const double2 zk = sm[P::smem_addr(P::pos_of_freq(k), l)];
+        const double2 zm = sm[P::smem_addr(P::pos_of_freq((N - k) % N), l)];
+        const double h = 0.5 * scale;
+        const double2 x1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+        const double2 x2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
+        if (r1 < nrows) mfb_st_stream(reinterpret_cast<double2*>(data + r1 * pitch) + k, x1);
+        if (r1 + 1 < nrows) mfb_st_stream(reinterpret_cast<double2*>(data + (r1 + 1) * pitch) + k, x2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused z pass of a dealiased product on the padded grid (n = 3N/2):
+//   rows of A and B hold the nzin = N/2 retained k_z modes; per row
+//     a + i b = IFFT_n( A^ + i B^ ) (Hermitian extension, zero padded), p = a*b,
+//   two rows' products are packed into one complex line, FFT_n, unpacked, and the first nzin
+//   modes are written to `out`.  DIF backward + DIT forward => no permutation in between.
+template <class P>
+__global__ void __launch_bounds__(P::NTHREADS) z_conv_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin,
+                                                             double2* __restrict__ out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
+                                                             long nrows, int nzin, double scale, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N, T = P::T, H = T / 2;
+    static_assert(T >= 2, "need at least two lines per tile");
+    const int tid = threadIdx.x;
+    const int line = tid % T, q = tid / T;
+    const long row0 = long(blockIdx.x) * T;
+    // zero the padded band [nzin, N - nzin]
+    const int nzero = N - 2 * nzin + 1;
+    for (int idx = tid; idx < T * nzero; idx += P::NTHREADS) {
+        const int l = idx / nzero, k = nzin + (idx - l * nzero);
+        sm[P::smem_addr(k, l)] = make_double2(0.0, 0.0);
+    }
+    for (int idx = tid; idx < T * nzin; idx += P::NTHREADS) {
+        const int l = idx / nzin, k = idx - l * nzin;
+        const long r = row0 + l;
+        double2 x1 = make_double2(0.0, 0.0), x2 = x1;
+        if (r < nrows) {
+            x1 = mfb_ld_stream(Ain + r * in_pitch + k);
+            x2 = mfb_ld_stream(Bin + r * in_pitch + k);
+        }
+        if (k == 0) { x1.y = 0.0; x2.y = 0.0; }
+        sm[P::smem_addr(k, l)] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
+        if (k > 0) sm[P::smem_addr(N - k, l)] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
+    }
+    __syncthreads();
+    NoLoader nl; NoStorer ns;
+    fft_tile<P, false, false, false>(sm, tw, line, q, true, nl, ns);   // DIF: result digit-reversed
+    __syncthreads();
+    // product, in digit-reversed order: a = Re, b = -Im (conj trick); pack lines l and l+H
+    for (int idx = tid; idx < H * N; idx += P::NTHREADS) {
+        const int p = idx / H, l = idx - p * H;
+        const double2 u = sm[P::smem_addr(p, l)];
+        const double2 w = sm[P::smem_addr(p, l + H)];
+        sm[P::smem_addr(p, l)] = make_double2(-u.x * u.y, -w.x * w.y);
+    }
+    __syncthreads();
+    fft_tile<P, true, false, false>(sm, tw, line, q, line < H, nl, ns);  // DIT: natural order out
+    __syncthreads();
+    for (int idx = tid; idx < H * nzin; idx += P::NTHREADS) {
+        const int l = idx / nzin, k = idx - l * nzin;
+        const long r1 = row0 + l, r2 = row0 + l + H;
+        const double2 zk = sm[P::smem_addr(k, l)];
+        const double2 zm = sm[P::smem_addr((N - k) % N, l)];
+        const double h = 0.5 * scale;
+        const double2 x1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+        const double2 x2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
+        if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, x1);
+        if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, x2);
+    }
+}
+
+}  // namespace mfb

@@ -1,0 +1,320 @@
+// grid_ops.cuh - element-wise k-space / real-space operators, reductions and the lattice
+// read-out of the LPT pipeline (FP64, bandwidth-bound streaming kernels).
+// Each kernel names the reference loop it replaces (paths relative to /root/reference).
+#pragma once
+#include "fft_core.cuh"
+
+namespace mfb {
+
+// geometry of a cubic-or-not grid in k-space, layout [kx][ky][kz] (kz = 0..n2/2)
+struct KGeom {
+    int n0, n1, n2, nzc;
+    double kf0, kf1, kf2;  // 2 pi / L_d
+};
+
+MFB_HD int signed_idx(int i, int n) { return i - ((i > n / 2) ? n : 0); }
+// get_k (include/grid_fft.hh:281-296): Nyquist index carries +n/2
+MFB_HD double getk(int i, int n, double kf) { return double(signed_idx(i, n)) * kf; }
+// gradient wavenumber (include/grid_fft.hh:376-385, include/operators.hh:50-55): 0 at Nyquist
+MFB_HD double gradk(int i, int n, double kf) { return (i == n / 2) ? 0.0 : double(signed_idx(i, n)) * kf; }
+
+constexpr int EW_THREADS = 256;
+constexpr int EW_ROWS = 4;  // k-space rows (fixed kx,ky) per block
+
+// iterate over the k-space elements of EW_ROWS rows; opens ONE brace (closed by the caller) and
+// defines i, j, k, idx
+#define MFB_K_LOOP_BEGIN(G)                                                   \
+    for (int t_ = threadIdx.x; t_ < EW_ROWS * (G).nzc; t_ += EW_THREADS) {    \
+        const long r_ = long(blockIdx.x) * EW_ROWS + t_ / (G).nzc;            \
+        if (r_ >= long((G).n0) * (G).n1) break;                               \
+        const int k = t_ % (G).nzc;                                           \
+        const int i = int(r_ / (G).n1);                                       \
+        const int j = int(r_ - long(i) * (G).n1);                             \
+        const long idx = r_ * (G).nzc + k;                                    \
+        (void)i; (void)j; (void)k;
+
+inline unsigned kgrid_blocks(const KGeom& g) { return unsigned((long(g.n0) * g.n1 + EW_ROWS - 1) / EW_ROWS); }
+
+// ---------------------------------------------------------------- plain streaming ops
+__global__ void __launch_bounds__(EW_THREADS) scale_kernel(double* __restrict__ d, size_t n, double a) {
+    for (size_t i = size_t(blockIdx.x) * EW_THREADS + threadIdx.x; i < n; i += size_t(gridDim.x) * EW_THREADS) d[i] *= a;
+}
+__global__ void __launch_bounds__(EW_THREADS) affine_kernel(double* __restrict__ d, size_t n, double a, double b) {
+    // x <- a + b*x  (src/ic_generator.cc:673-675 mass field)
+    for (size_t i = size_t(blockIdx.x) * EW_THREADS + threadIdx.x; i < n; i += size_t(gridDim.x) * EW_THREADS)
+        d[i] = a + b * d[i];
+}
+__global__ void __launch_bounds__(EW_THREADS) axpy_kernel(double* __restrict__ y, const double* __restrict__ x, size_t n, double a, double b) {
+    // y <- a*y + b*x
+    for (size_t i = size_t(blockIdx.x) * EW_THREADS + threadIdx.x; i < n; i += size_t(gridDim.x) * EW_THREADS)
+        y[i] = a * y[i] + b * x[i];
+}
+
+// ---------------------------------------------------------------- k-space operators
+// wnoise conditioning (src/ic_generator.cc:341-358)
+__global__ void __launch_bounds__(EW_THREADS) noise_condition_kernel(double2* __restrict__ w, KGeom g, double inv_volfac,
+                                                                      int fix, int remove_corners, double kny) {
+    MFB_K_LOOP_BEGIN(g)
+        double2 v = w[idx];
+        if (fix) {
+            const double a = sqrt(v.x * v.x + v.y * v.y);
+            if (a != 0.0) { v.x /= a; v.y /= a; }
+        }
+        v.x *= inv_volfac; v.y *= inv_volfac;
+        if (remove_corners) {
+            const double kx = getk(i, g.n0, g.kf0), ky = getk(j, g.n1, g.kf1), kz = getk(k, g.n2, g.kf2);
+            if (sqrt(kx * kx + ky * ky + kz * kz) > kny) v = make_double2(0.0, 0.0);
+        }
+        w[idx] = v;
+    }
+}
+
+// out = in * T(|n|^2) * (mode==1 ? -1/|k|^2 : 1), DC = 0.   T = tabulated A(|k|) on integer |n|^2
+// mode 1: phi(1) = -W A / k^2 (src/ic_generator.cc:461-468); mode 0: rho = W A (:667-670)
+__global__ void __launch_bounds__(EW_THREADS) radial_table_kernel(double2* __restrict__ out, const double2* __restrict__ in,
+                                                                   const double* __restrict__ table, KGeom g, int mode) {
+    MFB_K_LOOP_BEGIN(g)
+        const int a = signed_idx(i, g.n0), b = signed_idx(j, g.n1), c = signed_idx(k, g.n2);
+        const long m = long(a) * a + long(b) * b + long(c) * c;
+        double f = __ldg(&table[m]);
+        if (mode == 1) {
+            const double kk = g.kf0 * g.kf0 * double(m);
+            f = -f / kk;
+        }
+        double2 v = in[idx];
+        v = (m == 0) ? make_double2(0.0, 0.0) : make_double2(v.x * f, v.y * f);
+        out[idx] = v;
+    }
+}
+
+// x <- x * s * |k|^(2p), p = -1,0,+1, DC = 0
+// p=-1,s=-1: apply_InverseLaplacian (include/grid_fft.hh:440-449); p=+1: (negative) Laplacian (:418-438)
+__global__ void __launch_bounds__(EW_THREADS) laplacian_pow_kernel(double2* __restrict__ out, const double2* __restrict__ in,
+                                                                    KGeom g, int p, double s) {
+    MFB_K_LOOP_BEGIN(g)
+        const double kx = getk(i, g.n0, g.kf0), ky = getk(j, g.n1, g.kf1), kz = getk(k, g.n2, g.kf2);
+        const double k2 = kx * kx + ky * ky + kz * kz;
+        double f = s;
+        if (p > 0) f *= k2;
+        else if (p < 0) f /= k2;
+        double2 v = in[idx];
+        v = (idx == 0) ? make_double2(0.0, 0.0) : make_double2(v.x * f, v.y * f);
+        out[idx] = v;
+    }
+}
+
+// external-tide correction of phi2 source (src/ic_generator.cc:492-496)
+__global__ void __launch_bounds__(EW_THREADS) tides_kernel(double2* __restrict__ phi2, const double2* __restrict__ phi,
+                                                            KGeom g, double l0, double l1, double l2) {
+    MFB_K_LOOP_BEGIN(g)
+        const double kx = getk(i, g.n0, g.kf0), ky = getk(j, g.n1, g.kf1), kz = getk(k, g.n2, g.kf2);
+        const double k2 = kx * kx + ky * ky + kz * kz;
+        const double fa = kx * kx * l0 + ky * ky * l1 + kz * kz * l2;
+        const double f = (l0 + l1 + l2) * k2 + (4.0 / 3.0) * fa;
+        const double2 p = phi[idx];
+        double2 v = phi2[idx];
+        v.x -= f * p.x; v.y -= f * p.y;
+        phi2[idx] = v;
+    }
+}
+
+// sub-cell shift (include/grid_fft.hh:832-842): x <- x * exp(i (s.k) dx)
+__global__ void __launch_bounds__(EW_THREADS) shift_phase_kernel(double2* __restrict__ d, KGeom g, double sx, double sy, double sz) {
+    MFB_K_LOOP_BEGIN(g)
+        // k_d * dx_d = 2 pi n_d / N_d  -> use sincospi for accuracy
+        const double ph = 2.0 * (sx * double(signed_idx(i, g.n0)) / g.n0 + sy * double(signed_idx(j, g.n1)) / g.n1 +
+                                 sz * double(signed_idx(k, g.n2)) / g.n2);
+        double sn, cs;
+        sincospi(ph, &sn, &cs);
+        const double2 v = d[idx];
+        d[idx] = make_double2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+    }
+}
+
+// Psi / v assembly (src/ic_generator.cc:841-869, 896-940):
+//   out = G_d (w1 phi + w2 phi2 + w3 phi3) + wc (G_p A_q - G_q A_p) [- cvbc * T(|k|) W G_d / k^2], * scale, DC=0
+struct AssembleArgs {
+    const double2 *phi, *phi2, *phi3, *Ap, *Aq, *wnoise;
+    const double* vbc_table;
+    double w1, w2, w3, wc, cvbc, scale;
+    int d, p, q;
+};
+__global__ void __launch_bounds__(EW_THREADS) assemble_kernel(double2* __restrict__ out, AssembleArgs A, KGeom g) {
+    MFB_K_LOOP_BEGIN(g)
+        double G[3] = {gradk(i, g.n0, g.kf0), gradk(j, g.n1, g.kf1), gradk(k, g.n2, g.kf2)};
+        const double Gd = (A.d == 0) ? G[0] : ((A.d == 1) ? G[1] : G[2]);
+        double2 t = A.phi[idx];
+        t.x *= A.w1; t.y *= A.w1;
+        if (A.phi2) { const double2 v = A.phi2[idx]; t.x = fma(A.w2, v.x, t.x); t.y = fma(A.w2, v.y, t.y); }
+        if (A.phi3) { const double2 v = A.phi3[idx]; t.x = fma(A.w3, v.x, t.x); t.y = fma(A.w3, v.y, t.y); }
+        // multiply by i*Gd
+        double2 r = make_double2(-Gd * t.y, Gd * t.x);
+        if (A.Ap) {
+            const double Gp = (A.p == 0) ? G[0] : ((A.p == 1) ? G[1] : G[2]);
+            const double Gq = (A.q == 0) ? G[0] : ((A.q == 1) ? G[1] : G[2]);
+            const double2 aq = A.Aq[idx], ap = A.Ap[idx];
+            // i*(Gp*Aq - Gq*Ap) * wc
+            const double cx = Gp * aq.x - Gq * ap.x, cy = Gp * aq.y - Gq * ap.y;
+            r.x -= A.wc * cy; r.y += A.wc * cx;
+        }
+        if (A.vbc_table) {
+            const int a = signed_idx(i, g.n0), b = signed_idx(j, g.n1), c = signed_idx(k, g.n2);
+            const long m = long(a) * a + long(b) * b + long(c) * c;
+            if (m > 0) {
+                const double f = A.cvbc * __ldg(&A.vbc_table[m]) * Gd / (g.kf0 * g.kf0 * double(m));
+                const double2 w = A.wnoise[idx];
+                r.x -= -f * w.y; r.y -= f * w.x;
+            }
+        }
+        r.x *= A.scale; r.y *= A.scale;
+        if (idx == 0) r = make_double2(0.0, 0.0);
+        out[idx] = r;
+    }
+}
+
+// Fourier-space resample == Grid_FFT::FourierInterpolateCopyTo (src/grid_fft.cc:382-394,432-463):
+// target pre-zeroed by the caller; copy modes strictly inside both Nyquist limits.
+__global__ void __launch_bounds__(EW_THREADS) resample_kernel(double2* __restrict__ dst, KGeom gd, const double2* __restrict__ src, KGeom gs) {
+    MFB_K_LOOP_BEGIN(gd)
+        const int h0 = min(gs.n0, gd.n0) / 2, h1 = min(gs.n1, gd.n1) / 2, h2 = min(gs.n2, gd.n2) / 2;
+        const int a = signed_idx(i, gd.n0), b = signed_idx(j, gd.n1);
+        double2 v = make_double2(0.0, 0.0);
+        if (abs(a) < h0 && abs(b) < h1 && k < h2) {
+            const int is = (a < 0) ? a + gs.n0 : a, js = (b < 0) ? b + gs.n1 : b;
+            v = src[(long(is) * gs.n1 + js) * gs.nzc + k];
+        }
+        dst[idx] = v;
+    }
+}
+
+// ---------------------------------------------------------------- reductions (deterministic two-stage)
+constexpr int RED_THREADS = 256;
+// real view: rows of `pitch` doubles, first n2 valid.  partial[2*b] = sum, partial[2*b+1] = sum of squares
+__global__ void __launch_bounds__(RED_THREADS) reduce_real_kernel(const double* __restrict__ d, long nrows, int n2, ptrdiff_t pitch,
+                                                                   double* __restrict__ partial) {
+    __shared__ double s1[RED_THREADS], s2[RED_THREADS];
+    double a = 0.0, b = 0.0;
+    const long total = nrows * n2;
+    for (long t = long(blockIdx.x) * RED_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * RED_THREADS) {
+        const long r = t / n2;
+        const double v = d[r * pitch + (t - r * n2)];
+        a += v; b += v * v;
+    }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
+        if (int(threadIdx.x) < s) { s1[threadIdx.x] += s1[threadIdx.x + s]; s2[threadIdx.x] += s2[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s1[0]; partial[2 * blockIdx.x + 1] = s2[0]; }
+}
+// complex view (k-space std, include/grid_fft.hh:507-553): sum of real parts, sum of |z|^2
+__global__ void __launch_bounds__(RED_THREADS) reduce_cplx_kernel(const double2* __restrict__ d, long n, double* __restrict__ partial) {
+    __shared__ double s1[RED_THREADS], s2[RED_THREADS];
+    double a = 0.0, b = 0.0;
+    for (long t = long(blockIdx.x) * RED_THREADS + threadIdx.x; t < n; t += long(gridDim.x) * RED_THREADS) {
+        const double2 v = d[t];
+        a += v.x; b += v.x * v.x + v.y * v.y;
+    }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
+        if (int(threadIdx.x) < s) { s1[threadIdx.x] += s1[threadIdx.x + s]; s2[threadIdx.x] += s2[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s1[0]; partial[2 * blockIdx.x + 1] = s2[0]; }
+}
+// max |phi(x+1)-phi(x)| over the three axes (src/ic_generator.cc:713-731; note i < size(0)-1)
+__global__ void __launch_bounds__(RED_THREADS) max_neighbour_diff_kernel(const double* __restrict__ d, int n0, int n1, int n2,
+                                                                          ptrdiff_t pitch, double* __restrict__ partial) {
+    __shared__ double s1[RED_THREADS];
+    double m = -1.0;
+    const long total = long(n0 - 1) * n1 * n2;
+    for (long t = long(blockIdx.x) * RED_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * RED_THREADS) {
+        const int k = int(t % n2);
+        const long r = t / n2;
+        const int j = int(r % n1), i = int(r / n1);
+        const int ir = (i + 1) % n0, jr = (j + 1) % n1, kr = (k + 1) % n2;
+        const double c = d[(long(i) * n1 + j) * pitch + k];
+        m = fmax(m, fabs(d[(long(ir) * n1 + j) * pitch + k] - c));
+        m = fmax(m, fabs(d[(long(i) * n1 + jr) * pitch + k] - c));
+        m = fmax(m, fabs(d[(long(i) * n1 + j) * pitch + kr] - c));
+    }
+    s1[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
+        if (int(threadIdx.x) < s) s1[threadIdx.x] = fmax(s1[threadIdx.x], s1[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s1[0];
+}
+// final stage: one block folds `nb` partial pairs. mode 0: sum pairs; mode 1: max singles
+__global__ void __launch_bounds__(RED_THREADS) reduce_final_kernel(const double* __restrict__ partial, int nb, int mode, double* __restrict__ out) {
+    __shared__ double s1[RED_THREADS], s2[RED_THREADS];
+    double a = (mode == 1) ? -1.0 : 0.0, b = 0.0;
+    for (int t = threadIdx.x; t < nb; t += RED_THREADS) {
+        if (mode == 1) a = fmax(a, partial[t]);
+        else { a += partial[2 * t]; b += partial[2 * t + 1]; }
+    }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
+        if (int(threadIdx.x) < s) {
+            if (mode == 1) s1[threadIdx.x] = fmax(s1[threadIdx.x], s1[threadIdx.x + s]);
+            else { s1[threadIdx.x] += s1[threadIdx.x + s]; s2[threadIdx.x] += s2[threadIdx.x + s]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = s1[0]; out[1] = s2[0]; }
+}
+// real-space DC removal (include/grid_fft.hh:851-886)
+__global__ void __launch_bounds__(EW_THREADS) subtract_real_kernel(double* __restrict__ d, long nrows, int n2, ptrdiff_t pitch, double m) {
+    const long total = nrows * n2;
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * EW_THREADS) {
+        const long r = t / n2;
+        d[r * pitch + (t - r * n2)] -= m;
+    }
+}
+
+// ---------------------------------------------------------------- particles (include/particle_generator.hh)
+// IDs (:150-169): id = idoffset + ov*cell + iload at slot iload*ncell + cell
+template <typename id_t>
+__global__ void __launch_bounds__(EW_THREADS) particle_ids_kernel(id_t* __restrict__ ids, long ncell, int ov, unsigned long long idoffset,
+                                                                   long cell0) {
+    const long total = ncell * ov;
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * EW_THREADS) {
+        const long iload = t / ncell, c = t - iload * ncell;
+        ids[t] = id_t(idoffset + (unsigned long long)ov * (unsigned long long)(cell0 + c) + (unsigned long long)iload);
+    }
+}
+// lattice read-out (:448-465 positions, :544-560 velocities, :327-344 masses):
+//   dst[stride*(slot0 + cell) + comp] = real_t( add_lattice ? ((idx_d + shift)/n_d)*lunit + f : mul*f )
+template <typename real_out>
+__global__ void __launch_bounds__(EW_THREADS) lattice_readout_kernel(real_out* __restrict__ dst, const double* __restrict__ f,
+                                                                      int n0, int n1, int n2, ptrdiff_t pitch, int i0,
+                                                                      long slot0, int stride, int comp, int add_lattice, int d,
+                                                                      double shift, double lunit, double mul) {
+    const long total = long(n0) * n1 * n2;
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * EW_THREADS) {
+        const int k = int(t % n2);
+        const long r = t / n2;
+        const int j = int(r % n1), i = int(r / n1);
+        const double v = f[r * pitch + k];
+        double o;
+        if (add_lattice) {
+            const int id = (d == 0) ? (i + i0) : ((d == 1) ? j : k);
+            const int nd = (d == 0) ? n0 : ((d == 1) ? n1 : n2);  // n0 here is the *global* size for d==0 (single slab: equal)
+            const double qpos = (double(id) + shift) / double(nd);
+#ifdef MFB_EMU
+            o = qpos * lunit + v;
+#else
+            o = __dadd_rn(__dmul_rn(qpos, lunit), v);  // no FMA contraction: bit-identical to the CPU expression
+#endif
+        } else {
+            o = mul * v;
+        }
+        dst[size_t(stride) * size_t(slot0 + t) + comp] = real_out(o);
+    }
+}
+
+}  // namespace mfb

@@ -1,0 +1,967 @@
+// mfb_api.cu - libmfb200: context, grids, FFT orchestration, Orszag convolver, LPT source stage,
+// lattice read-out and the extern "C" boundary declared in include/mfb200.h.
+//
+// Single-GPU part.  (The multi-GPU slab layer lives in mfb_dist.cu.)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fft_kernels.cuh"
+#include "grid_ops.cuh"
+#include "mfb_internal.h"
+#include "../../include/mfb200.h"
+
+#ifdef MFB_EMU
+using std::abs;
+using std::max;
+using std::min;
+#endif
+
+namespace mfb {
+
+// ------------------------------------------------------------------------------------------
+// plan table: n, threads-per-line, lines-per-tile, radix sequence
+// ------------------------------------------------------------------------------------------
+#define MFB_FOR_EACH_PLAN(X)      \
+    X(32, 4, 16, 8, 4)            \
+    X(48, 2, 16, 8, 6)            \
+    X(64, 8, 16, 8, 8)            \
+    X(96, 4, 16, 12, 8)           \
+    X(128, 8, 16, 16, 8)          \
+    X(192, 4, 16, 16, 12)         \
+    X(256, 16, 8, 16, 16)         \
+    X(384, 16, 8, 8, 8, 6)        \
+    X(512, 32, 8, 8, 8, 8)        \
+    X(768, 32, 8, 12, 8, 8)       \
+    X(1024, 32, 8, 16, 8, 8)      \
+    X(1536, 32, 8, 16, 12, 8)     \
+    X(2048, 64, 4, 16, 16, 8)     \
+    X(3072, 64, 4, 16, 16, 12)
+
+Context g_ctx;
+thread_local std::string g_err;
+
+void set_error(const std::string& s) { g_err = s; }
+
+#define MFB_TRY try {
+#define MFB_CATCH                              \
+    }                                          \
+    catch (const std::exception& e) {          \
+        mfb::set_error(e.what());              \
+        return 1;                              \
+    }                                          \
+    catch (...) {                              \
+        mfb::set_error("unknown error");       \
+        return 1;                              \
+    }                                          \
+    return 0;
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+void require(bool c, const char* msg) {
+    if (!c) throw std::runtime_error(msg);
+}
+void check_launch(const char* what) {
+    ++g_ctx.launches;
+    cuda_check(cudaGetLastError(), what);
+}
+
+void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    cuda_check(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc");
+    return p;
+}
+
+const double2* twiddles(int n) {
+    auto it = g_ctx.tw.find(n);
+    if (it != g_ctx.tw.end()) return it->second;
+    std::vector<double2> h(n);
+    for (int m = 0; m < n; ++m) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)n;
+        h[m].x = (double)cosl(a);
+        h[m].y = (double)sinl(a);
+    }
+    double2* d = (double2*)dev_alloc(sizeof(double2) * n);
+    cuda_check(cudaMemcpy(d, h.data(), sizeof(double2) * n, cudaMemcpyHostToDevice), "twiddle upload");
+    g_ctx.tw[n] = d;
+    return d;
+}
+
+bool supported_size(int n) {
+    switch (n) {
+#define X(N_, TPL_, T_, ...) case N_:
+        MFB_FOR_EACH_PLAN(X)
+#undef X
+        return true;
+        default: return false;
+    }
+}
+
+template <class K> void optin_smem(K kernel, size_t bytes, bool& done) {
+    if (!done) {
+        if (bytes > 48 * 1024) cuda_check(MFB_KERNEL_SMEM_OPTIN(kernel, bytes), "cudaFuncSetAttribute(smem)");
+        done = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launchers
+// ------------------------------------------------------------------------------------------
+template <class P> void launch_strided_t(const StridedArgs& a) {
+    static bool done = false;
+    optin_smem(strided_pass_kernel<P>, P::SMEM_BYTES, done);
+    const int tiles = (a.nz + P::T - 1) / P::T;
+    const unsigned grid = unsigned(a.na) * unsigned(tiles);
+    if (grid == 0) return;
+    const double2* tw = twiddles(P::N);
+    MFB_LAUNCH(strided_pass_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, a, tw);
+    check_launch("strided_pass_kernel");
+}
+void launch_strided(int n, const StridedArgs& a) {
+    switch (n) {
+#define X(N_, TPL_, T_, ...)                              \
+    case N_: {                                            \
+        using P = Plan<N_, TPL_, T_, __VA_ARGS__>;        \
+        launch_strided_t<P>(a);                           \
+        break;                                            \
+    }
+        MFB_FOR_EACH_PLAN(X)
+#undef X
+        default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
+    }
+}
+
+template <class P> void launch_z_t(int kind, double* data, ptrdiff_t pitch, long nrows, double scale) {
+    static bool done_c2r = false, done_r2c = false;
+    const unsigned grid = unsigned((nrows + 2 * P::T - 1) / (2 * P::T));
+    const double2* tw = twiddles(P::N);
+    if (kind == 0) {
+        optin_smem(z_c2r_kernel<P>, P::SMEM_BYTES, done_c2r);
+        MFB_LAUNCH(z_c2r_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, pitch, nrows, scale, tw);
+        check_launch("z_c2r_kernel");
+    } else {
+        optin_smem(z_r2c_kernel<P>, P::SMEM_BYTES, done_r2c);
+        MFB_LAUNCH(z_r2c_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, pitch, nrows, scale, tw);
+        check_launch("z_r2c_kernel");
+    }
+}
+void launch_z(int n, int kind, double* data, ptrdiff_t pitch, long nrows, double scale) {
+    switch (n) {
+#define X(N_, TPL_, T_, ...)                                  \
+    case N_: {                                                \
+        using P = Plan<N_, TPL_, T_, __VA_ARGS__>;            \
+        launch_z_t<P>(kind, data, pitch, nrows, scale);       \
+        break;                                                \
+    }
+        MFB_FOR_EACH_PLAN(X)
+#undef X
+        default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
+    }
+}
+
+template <class P>
+void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
+                    int nzin, double scale) {
+    static bool done = false;
+    optin_smem(z_conv_kernel<P>, P::SMEM_BYTES, done);
+    const unsigned grid = unsigned((nrows + P::T - 1) / P::T);
+    const double2* tw = twiddles(P::N);
+    MFB_LAUNCH(z_conv_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, nzin,
+               scale, tw);
+    check_launch("z_conv_kernel");
+}
+void launch_zconv(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
+                  int nzin, double scale) {
+    switch (n) {
+#define X(N_, TPL_, T_, ...)                                                   \
+    case N_: {                                                                 \
+        using P = Plan<N_, TPL_, T_, __VA_ARGS__>;                             \
+        launch_zconv_t<P>(A, B, out, in_pitch, out_pitch, nrows, nzin, scale); \
+        break;                                                                 \
+    }
+        MFB_FOR_EACH_PLAN(X)
+#undef X
+        default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
+    }
+}
+
+static StridedArgs plain_strided(const double2* in, double2* out, ptrdiff_t ps, ptrdiff_t as, int na, int nz, int n,
+                                 int inverse) {
+    StridedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.out = out;
+    a.in_ps = a.out_ps = ps;
+    a.in_as = a.out_as = as;
+    a.na = na; a.nz = nz; a.nz_fft = nz;
+    a.n_in = a.n_out = n;
+    a.inverse = inverse;
+    a.scale = 1.0;
+    a.op = OP_ASSIGN;
+    a.a_skip = -1;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// Grid
+// ------------------------------------------------------------------------------------------
+KGeom kgeom(const mfb_grid* g) {
+    KGeom k;
+    k.n0 = g->n[0]; k.n1 = g->n[1]; k.n2 = g->n[2]; k.nzc = g->nzc;
+    k.kf0 = 2.0 * M_PI / g->L[0]; k.kf1 = 2.0 * M_PI / g->L[1]; k.kf2 = 2.0 * M_PI / g->L[2];
+    return k;
+}
+static unsigned stream_blocks(size_t n) {
+    size_t b = (n + EW_THREADS - 1) / EW_THREADS;
+    const size_t cap = size_t(148) * 16;
+    return unsigned(b < cap ? (b ? b : 1) : cap);
+}
+
+void grid_fft_forward(mfb_grid* g) {
+    const double norm = 1.0 / std::sqrt(double(g->n[0]) * double(g->n[1]) * double(g->n[2]));
+    double2* c = reinterpret_cast<double2*>(g->d);
+    const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
+    launch_z(g->n[2], 1, g->d, g->pitch, long(n0) * n1, norm);
+    launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 0));
+    launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 0));
+}
+void grid_fft_backward(mfb_grid* g) {
+    const double norm = 1.0 / std::sqrt(double(g->n[0]) * double(g->n[1]) * double(g->n[2]));
+    double2* c = reinterpret_cast<double2*>(g->d);
+    const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
+    launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 1));
+    launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 1));
+    launch_z(g->n[2], 0, g->d, g->pitch, long(n0) * n1, norm);
+}
+void to_kspace(mfb_grid* g) {
+    if (g->space != MFB_KSPACE) { grid_fft_forward(g); g->space = MFB_KSPACE; }
+}
+void to_rspace(mfb_grid* g) {
+    if (g->space != MFB_RSPACE) { grid_fft_backward(g); g->space = MFB_RSPACE; }
+}
+
+double* partial_buffer(size_t ndoubles) {
+    if (g_ctx.partial_cap < ndoubles) {
+        if (g_ctx.partial) cudaFree(g_ctx.partial);
+        g_ctx.partial = (double*)dev_alloc(ndoubles * sizeof(double));
+        g_ctx.partial_cap = ndoubles;
+    }
+    return g_ctx.partial;
+}
+
+// returns (sum, sumsq) over the logical elements of the grid in its current space
+static void grid_sums(mfb_grid* g, double out[2]) {
+    const int nb = 148 * 4;
+    double* part = partial_buffer(2 * nb + 2);
+    if (g->space == MFB_RSPACE) {
+        MFB_LAUNCH(reduce_real_kernel, nb, RED_THREADS, 0, g_ctx.stream, g->d, long(g->n[0]) * g->n[1], g->n[2], g->pitch, part);
+    } else {
+        MFB_LAUNCH(reduce_cplx_kernel, nb, RED_THREADS, 0, g_ctx.stream, reinterpret_cast<const double2*>(g->d),
+                   long(g->n[0]) * g->n[1] * g->nzc, part);
+    }
+    check_launch("reduce");
+    MFB_LAUNCH(reduce_final_kernel, 1, RED_THREADS, 0, g_ctx.stream, part, nb, 0, part + 2 * nb);
+    check_launch("reduce_final");
+    cuda_check(cudaMemcpyAsync(out, part + 2 * nb, 2 * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "reduce D2H");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+}
+
+void grid_zero_dc(mfb_grid* g) {
+    if (g->space == MFB_KSPACE) {
+        cuda_check(cudaMemsetAsync(g->d, 0, sizeof(double2), g_ctx.stream), "zero DC");
+    } else {
+        double s[2];
+        grid_sums(g, s);
+        const double mean = s[0] / (double(g->n[0]) * g->n[1] * g->n[2]);
+        const long nrows = long(g->n[0]) * g->n[1];
+        MFB_LAUNCH(subtract_real_kernel, stream_blocks(size_t(nrows) * g->n[2]), EW_THREADS, 0, g_ctx.stream, g->d, nrows, g->n[2],
+                   g->pitch, mean);
+        check_launch("subtract_real");
+    }
+}
+
+void grid_laplacian_pow(mfb_grid* g, int p, double s) {
+    to_kspace(g);
+    KGeom k = kgeom(g);
+    double2* c = reinterpret_cast<double2*>(g->d);
+    MFB_LAUNCH(laplacian_pow_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, c, c, k, p, s);
+    check_launch("laplacian_pow");
+}
+
+void grid_scale(mfb_grid* g, double a) {
+    MFB_LAUNCH(scale_kernel, stream_blocks(g->ntot), EW_THREADS, 0, g_ctx.stream, g->d, g->ntot, a);
+    check_launch("scale");
+}
+
+void grid_shift_field(mfb_grid* g, const double s[3], bool back) {
+    to_kspace(g);
+    KGeom k = kgeom(g);
+    MFB_LAUNCH(shift_phase_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(g->d), k, s[0], s[1], s[2]);
+    check_launch("shift_phase");
+    if (back) to_rspace(g);
+}
+
+// ------------------------------------------------------------------------------------------
+// Orszag convolver
+// ------------------------------------------------------------------------------------------
+struct Operand {
+    mfb_grid* g;
+    int a1, b1, a2, b2;
+    double c1, c2;
+    int imag;
+};
+
+static void conv_backward_operand(mfb_conv* c, const Operand& o, double2* W2) {
+    const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
+    const int P0 = c->np[0], P1 = c->np[1];
+    const int nzc = N2 / 2 + 1, nzin = N2 / 2;
+    const double ptot = double(c->np[0]) * c->np[1] * c->np[2];
+    const double s1 = std::pow(1.5, 1.5) / std::sqrt(ptot);  // pad factor (convolution.hh:572) * bwd norm
+    // pass 1: x axis, N0 -> P0, operand factor fused into the load
+    StridedArgs a = plain_strided(reinterpret_cast<const double2*>(o.g->d), c->W1, 0, 0, N1, nzin, P0, 1);
+    a.in_ps = ptrdiff_t(N1) * nzc; a.in_as = nzc;
+    a.out_ps = ptrdiff_t(N1) * nzin; a.out_as = nzin;
+    a.n_in = N0;
+    a.a_skip = N1 / 2;
+    a.f.enabled = 1;
+    a.f.a1 = o.a1; a.f.b1 = o.b1; a.f.a2 = o.a2; a.f.b2 = o.b2;
+    a.f.c1 = o.c1 * s1; a.f.c2 = o.c2 * s1;
+    a.f.imag = o.imag;
+    for (int d = 0; d < 3; ++d) { a.f.n[d] = c->n[d]; a.f.kf[d] = 2.0 * M_PI / c->L[d]; }
+    a.pos_axis = 0; a.a_axis = 1;
+    launch_strided(P0, a);
+    // pass 2: y axis, N1 -> P1
+    StridedArgs b = plain_strided(c->W1, W2, nzin, 0, P0, nzin, P1, 1);
+    b.in_as = ptrdiff_t(N1) * nzin;
+    b.out_as = ptrdiff_t(P1) * nzin;
+    b.n_in = N1;
+    launch_strided(P1, b);
+}
+
+void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
+    require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+    to_kspace(A.g);
+    to_kspace(B.g);
+    const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
+    const int P0 = c->np[0], P1 = c->np[1], P2 = c->np[2];
+    const int nzc = N2 / 2 + 1, nzin = N2 / 2;
+    const double ptot = double(P0) * P1 * P2, ntot = double(N0) * N1 * N2;
+    conv_backward_operand(c, A, c->W2a);
+    conv_backward_operand(c, B, c->W2b);
+    // pass 3: fused z  c2r x2, product, r2c (in place on W2a)
+    launch_zconv(P2, c->W2a, c->W2b, c->W2a, nzin, nzin, long(P0) * P1, nzin, 1.0);
+    // pass 4: y axis forward, P1 -> N1
+    StridedArgs d = plain_strided(c->W2a, c->W1, nzin, 0, P0, nzin, P1, 0);
+    d.in_as = ptrdiff_t(P1) * nzin;
+    d.out_as = ptrdiff_t(N1) * nzin;
+    d.n_out = N1;
+    launch_strided(P1, d);
+    // pass 5: x axis forward, P0 -> N0, unpad scale + Nyquist zero + output operator
+    StridedArgs e = plain_strided(c->W1, reinterpret_cast<double2*>(out->d), 0, 0, N1, (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
+    e.in_ps = ptrdiff_t(N1) * nzin; e.in_as = nzin;
+    e.out_ps = ptrdiff_t(N1) * nzc; e.out_as = nzc;
+    e.nz_fft = nzin;
+    e.n_out = N0;
+    e.scale = (1.0 / std::sqrt(ptot)) / (std::sqrt(ptot) / std::sqrt(ntot));  // fwd norm / rfac (convolution.hh:620,664)
+    e.op = op; e.alpha = alpha;
+    e.a_skip = N1 / 2;
+    e.zero_fill = 1;
+    launch_strided(P0, e);
+    ++c->nconv;
+}
+
+static Operand hessian_operand(mfb_grid* g, const int d[2]) { return Operand{g, d[0], d[1], -1, -1, -1.0, 0.0, 0}; }
+
+void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3, mfb_grid* const A3[3],
+                 const double* lam) {
+    require(phi->space == MFB_KSPACE, "phi must be in k-space");
+    const double g1 = -D;
+    const double g2 = (order > 1) ? -3.0 / 7.0 * D * D : 0.0;
+    const double g3 = (order > 2) ? 1.0 / 3.0 * D * D * D : 0.0;
+    const double g3c = (order > 2) ? 1.0 / 7.0 * D * D * D : 0.0;
+    auto H = [](mfb_grid* g, int a, int b) { int d[2] = {a, b}; return hessian_operand(g, d); };
+    auto HS = [](mfb_grid* g, int a, int b, int cc, int d, double sgn) { return Operand{g, a, b, cc, d, -1.0, -sgn, 0}; };
+    if (order > 1) {
+        require(phi2 != nullptr, "phi2 grid required for LPT order > 1");
+        phi2->space = MFB_KSPACE;
+        // src/ic_generator.cc:482-486
+        conv2(c, H(phi, 0, 0), HS(phi, 1, 1, 2, 2, +1.0), phi2, OP_ASSIGN, 0.0);
+        conv2(c, H(phi, 1, 1), H(phi, 2, 2), phi2, OP_ADD, 0.0);
+        conv2(c, H(phi, 0, 1), H(phi, 0, 1), phi2, OP_SUB, 0.0);
+        conv2(c, H(phi, 0, 2), H(phi, 0, 2), phi2, OP_SUB, 0.0);
+        conv2(c, H(phi, 1, 2), H(phi, 1, 2), phi2, OP_SUB, 0.0);
+        if (lam) {
+            KGeom k = kgeom(phi2);
+            MFB_LAUNCH(tides_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(phi2->d),
+                       reinterpret_cast<const double2*>(phi->d), k, lam[0], lam[1], lam[2]);
+            check_launch("tides");
+        }
+        grid_laplacian_pow(phi2, -1, -1.0);  // :499
+    }
+    if (order > 2) {
+        require(phi3 && A3 && A3[0] && A3[1] && A3[2], "phi3 and A3 grids required for LPT order > 2");
+        phi3->space = MFB_KSPACE;
+        mfb_grid* fb = c->fbuf;
+        fb->space = MFB_KSPACE;
+        Operand FB{fb, -1, -1, -1, -1, 1.0, 0.0, 0};
+        auto conv3 = [&](Operand a, Operand b, Operand cc, int op, double alpha) {
+            conv2(c, a, b, fb, OP_ASSIGN, 0.0);  // include/convolution.hh:542-549
+            conv2(c, FB, cc, phi3, op, alpha);
+        };
+        // 3a  :522-526
+        conv3(H(phi, 0, 0), H(phi, 1, 1), H(phi, 2, 2), OP_ASSIGN, 0.0);
+        conv3(H(phi, 0, 1), H(phi, 0, 2), H(phi, 1, 2), OP_MULADD, 2.0);
+        conv3(H(phi, 1, 2), H(phi, 1, 2), H(phi, 0, 0), OP_SUB, 0.0);
+        conv3(H(phi, 0, 2), H(phi, 0, 2), H(phi, 1, 1), OP_SUB, 0.0);
+        conv3(H(phi, 0, 1), H(phi, 0, 1), H(phi, 2, 2), OP_SUB, 0.0);
+        // 3b  :533-538
+        conv2(c, H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), phi3, OP_MULADD, -5.0 / 7.0);
+        conv2(c, H(phi, 1, 1), HS(phi2, 2, 2, 0, 0, +1.0), phi3, OP_MULADD, -5.0 / 7.0);
+        conv2(c, H(phi, 2, 2), HS(phi2, 0, 0, 1, 1, +1.0), phi3, OP_MULADD, -5.0 / 7.0);
+        conv2(c, H(phi, 0, 1), H(phi2, 0, 1), phi3, OP_MULADD, 10.0 / 7.0);
+        conv2(c, H(phi, 0, 2), H(phi2, 0, 2), phi3, OP_MULADD, 10.0 / 7.0);
+        conv2(c, H(phi, 1, 2), H(phi2, 1, 2), phi3, OP_MULADD, 10.0 / 7.0);
+        grid_laplacian_pow(phi3, -1, -1.0);  // :539
+        // transverse term  :545-556
+        for (int d = 0; d < 3; ++d) {
+            const int p = (d + 1) % 3, q = (d + 2) % 3;
+            mfb_grid* A = A3[d];
+            A->space = MFB_KSPACE;
+            conv2(c, H(phi2, d, p), H(phi, d, q), A, OP_ASSIGN, 0.0);
+            conv2(c, H(phi2, d, q), H(phi, d, p), A, OP_SUB, 0.0);
+            conv2(c, H(phi, p, q), HS(phi2, p, p, q, q, -1.0), A, OP_ADD, 0.0);
+            conv2(c, H(phi2, p, q), HS(phi, p, p, q, q, -1.0), A, OP_SUB, 0.0);
+            grid_laplacian_pow(A, -1, -1.0);
+        }
+    }
+    // :561-574
+    grid_scale(phi, g1);
+    if (order > 1) grid_scale(phi2, g2);
+    if (order > 2) {
+        grid_scale(phi3, g3);
+        for (int d = 0; d < 3; ++d) grid_scale(A3[d], g3c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// particles
+// ------------------------------------------------------------------------------------------
+static const double LATTICE_SHIFTS[4][8][3] = {
+    {{0, 0, 0}},
+    {{0, 0, 0}, {0.5, 0.5, 0.5}},
+    {{0, 0, 0}, {0, 0.5, 0.5}, {0.5, 0, 0.5}, {0.5, 0.5, 0}},
+    {{0, 0, 0}, {0, 0, 0.5}, {0, 0.5, 0}, {0, 0.5, 0.5}, {0.5, 0, 0}, {0.5, 0, 0.5}, {0.5, 0.5, 0}, {0.5, 0.5, 0.5}},
+};
+static const double SECOND_LATTICE_SHIFT[4][3] = {{0.5, 0.5, 0.5}, {0.5, 0.5, 0}, {0.5, 0.5, 0.5}, {0.25, 0.25, 0.25}};
+
+// kind 0: positions, 1: velocities, 2: masses
+static void particles_readout(mfb_particles* p, int kind, int lattice_index, int idim, double unit, mfb_grid* f) {
+    require(lattice_index == 0 || lattice_index == 1, "For Bravais lattice type, lattice index must be 0 or 1.");
+    require(f->n[0] == p->n[0] && f->n[1] == p->n[1] && f->n[2] == p->n[2], "field/particle grid size mismatch");
+    const int lt = p->lattice_type;
+    const int nshift = 1 << lt;
+    const long ncell = long(p->n[0]) * p->n[1] * p->n[2];
+    const double pmean = unit / double(ncell * nshift);
+    to_rspace(f);
+    for (int is = 0; is < nshift; ++is) {
+        if (is == 0 && lattice_index == 1) grid_shift_field(f, SECOND_LATTICE_SHIFT[lt], true);
+        if (is > 0) {
+            double rel[3];
+            for (int d = 0; d < 3; ++d) rel[d] = LATTICE_SHIFTS[lt][is][d] - LATTICE_SHIFTS[lt][is - 1][d];
+            grid_shift_field(f, rel, true);
+        }
+        const unsigned nb = stream_blocks(size_t(ncell));
+        const long slot0 = long(is) * ncell;
+        double shift = 0.0;
+        if (kind == 0) shift = LATTICE_SHIFTS[lt][is][idim] + (lattice_index == 1 ? SECOND_LATTICE_SHIFT[lt][idim] : 0.0);
+        void* dst = (kind == 0) ? p->pos : ((kind == 1) ? p->vel : p->mass);
+        require(dst != nullptr, "particle buffer not allocated");
+        const int stride = (kind == 2) ? 1 : 3;
+        const int comp = (kind == 2) ? 0 : idim;
+        const int addl = (kind == 0) ? 1 : 0;
+        const double mul = (kind == 2) ? pmean : 1.0;
+        if (p->real64) {
+            MFB_LAUNCH(lattice_readout_kernel<double>, nb, EW_THREADS, 0, g_ctx.stream, (double*)dst, f->d, f->n[0], f->n[1],
+                       f->n[2], f->pitch, 0, slot0, stride, comp, addl, idim, shift, unit, mul);
+        } else {
+            MFB_LAUNCH(lattice_readout_kernel<float>, nb, EW_THREADS, 0, g_ctx.stream, (float*)dst, f->d, f->n[0], f->n[1],
+                       f->n[2], f->pitch, 0, slot0, stride, comp, addl, idim, shift, unit, mul);
+        }
+        check_launch("lattice_readout");
+    }
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+extern "C" {
+
+const char* mfb_last_error(void) { return g_err.c_str(); }
+const char* mfb_build_info(void) {
+#ifdef MFB_EMU
+    return "cpu-emulation (TEST ONLY)";
+#else
+    return "cuda sm_100a";
+#endif
+}
+
+int mfb_init(int device) {
+    MFB_TRY
+    if (g_ctx.initialised) return 0;
+    int ndev = 0;
+    cuda_check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+    require(ndev > 0, "libmfb200: no CUDA device visible - there is no CPU fallback");
+    require(device >= 0 && device < ndev, "libmfb200: invalid device index");
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    cuda_check(cudaStreamCreate(&g_ctx.stream), "cudaStreamCreate");
+    g_ctx.device = device;
+    g_ctx.initialised = true;
+    MFB_CATCH
+}
+int mfb_finalize(void) {
+    MFB_TRY
+    if (!g_ctx.initialised) return 0;
+    cudaStreamSynchronize(g_ctx.stream);
+    for (auto& kv : g_ctx.tw) cudaFree(kv.second);
+    g_ctx.tw.clear();
+    if (g_ctx.partial) cudaFree(g_ctx.partial);
+    g_ctx.partial = nullptr; g_ctx.partial_cap = 0;
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx.initialised = false;
+    MFB_CATCH
+}
+int mfb_synchronize(void) {
+    MFB_TRY
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "cudaStreamSynchronize");
+    MFB_CATCH
+}
+void* mfb_stream(void) { return (void*)g_ctx.stream; }
+long long mfb_kernel_launches(void) { return g_ctx.launches; }
+int mfb_supported_fft_size(int n) { return supported_size(n) ? 1 : 0; }
+
+// ---------------------------------------------------------------- grids
+int mfb_grid_create(mfb_grid** out, const int n[3], const double L[3], int space) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    for (int d = 0; d < 3; ++d) {
+        require(supported_size(n[d]), "unsupported grid size (supported: 32..2048 powers of two and 3*2^k up to 3072)");
+        require(L[d] > 0.0, "box length must be positive");
+    }
+    mfb_grid* g = new mfb_grid();
+    for (int d = 0; d < 3; ++d) { g->n[d] = n[d]; g->L[d] = L[d]; }
+    g->nzc = n[2] / 2 + 1;
+    g->pitch = n[2] + 2;
+    g->ntot = size_t(n[0]) * n[1] * (n[2] + 2);
+    g->space = space;
+    g->d = (double*)dev_alloc(g->ntot * sizeof(double));
+    *out = g;
+    MFB_CATCH
+}
+int mfb_grid_destroy(mfb_grid* g) {
+    MFB_TRY
+    if (g) { if (g->d) cudaFree(g->d); delete g; }
+    MFB_CATCH
+}
+int mfb_grid_space(const mfb_grid* g) { return g->space; }
+size_t mfb_grid_ntot(const mfb_grid* g) { return g->ntot; }
+void* mfb_grid_device_ptr(mfb_grid* g) { return g->d; }
+int mfb_grid_upload(mfb_grid* g, const double* host) {
+    MFB_TRY
+    cuda_check(cudaMemcpyAsync(g->d, host, g->ntot * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream), "upload");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+int mfb_grid_download(const mfb_grid* g, double* host) {
+    MFB_TRY
+    cuda_check(cudaMemcpyAsync(host, g->d, g->ntot * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "download");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+int mfb_fft_forward(mfb_grid* g, int do_transform) {
+    MFB_TRY
+    if (g->space != MFB_KSPACE) {
+        if (do_transform) grid_fft_forward(g);
+        g->space = MFB_KSPACE;
+    }
+    MFB_CATCH
+}
+int mfb_fft_backward(mfb_grid* g, int do_transform) {
+    MFB_TRY
+    if (g->space != MFB_RSPACE) {
+        if (do_transform) grid_fft_backward(g);
+        g->space = MFB_RSPACE;
+    }
+    MFB_CATCH
+}
+int mfb_grid_zero(mfb_grid* g) {
+    MFB_TRY
+    cuda_check(cudaMemsetAsync(g->d, 0, g->ntot * sizeof(double), g_ctx.stream), "zero");
+    MFB_CATCH
+}
+int mfb_grid_copy(mfb_grid* dst, const mfb_grid* src) {
+    MFB_TRY
+    require(dst->n[0] == src->n[0] && dst->n[1] == src->n[1] && dst->n[2] == src->n[2], "copy_from: grid size mismatch");
+    dst->space = src->space;  // copy_from flips the flag without transforming (grid_fft.hh:160-166)
+    cuda_check(cudaMemcpyAsync(dst->d, src->d, src->ntot * sizeof(double), cudaMemcpyDeviceToDevice, g_ctx.stream), "copy");
+    MFB_CATCH
+}
+int mfb_grid_scale(mfb_grid* g, double a) {
+    MFB_TRY
+    grid_scale(g, a);
+    MFB_CATCH
+}
+int mfb_grid_axpy(mfb_grid* y, double a, const mfb_grid* x, double b) {
+    MFB_TRY
+    require(y->ntot == x->ntot && y->space == x->space, "axpy: grids must have equal size and space");
+    MFB_LAUNCH(axpy_kernel, stream_blocks(y->ntot), EW_THREADS, 0, g_ctx.stream, y->d, x->d, y->ntot, a, b);
+    check_launch("axpy");
+    MFB_CATCH
+}
+int mfb_grid_affine(mfb_grid* g, double a, double b) {
+    MFB_TRY
+    MFB_LAUNCH(affine_kernel, stream_blocks(g->ntot), EW_THREADS, 0, g_ctx.stream, g->d, g->ntot, a, b);
+    check_launch("affine");
+    MFB_CATCH
+}
+int mfb_grid_zero_dc(mfb_grid* g) {
+    MFB_TRY
+    grid_zero_dc(g);
+    MFB_CATCH
+}
+int mfb_grid_inverse_laplacian(mfb_grid* g) {
+    MFB_TRY
+    grid_laplacian_pow(g, -1, -1.0);
+    MFB_CATCH
+}
+int mfb_grid_laplacian(mfb_grid* g, int negative) {
+    MFB_TRY
+    grid_laplacian_pow(g, +1, negative ? 1.0 : -1.0);
+    MFB_CATCH
+}
+int mfb_grid_shift_field(mfb_grid* g, const double s[3], int transform_back) {
+    MFB_TRY
+    grid_shift_field(g, s, transform_back != 0);
+    MFB_CATCH
+}
+int mfb_grid_mean(mfb_grid* g, double* out) {
+    MFB_TRY
+    require(g->space == MFB_RSPACE, "mean(): grid must be in real space");
+    double s[2];
+    grid_sums(g, s);
+    *out = s[0] / (double(g->n[0]) * g->n[1] * g->n[2]);
+    MFB_CATCH
+}
+int mfb_grid_std(mfb_grid* g, double* out) {
+    MFB_TRY
+    double s[2];
+    grid_sums(g, s);
+    const double cnt = (g->space == MFB_RSPACE) ? double(g->n[0]) * g->n[1] * g->n[2] : double(g->n[0]) * g->n[1] * g->nzc;
+    const double m1 = s[0] / cnt, m2 = s[1] / cnt;
+    *out = std::sqrt(m2 - m1 * m1);
+    MFB_CATCH
+}
+int mfb_grid_2norm(mfb_grid* g, double* out) {
+    MFB_TRY
+    require(g->space == MFB_RSPACE, "compute_2norm(): grid must be in real space");
+    double s[2];
+    grid_sums(g, s);
+    *out = s[1] / (double(g->n[0]) * g->n[1] * g->n[2]);
+    MFB_CATCH
+}
+int mfb_grid_max_neighbour_diff(mfb_grid* g, double* out) {
+    MFB_TRY
+    require(g->space == MFB_RSPACE, "max_neighbour_diff: grid must be in real space");
+    const int nb = 148 * 4;
+    double* part = partial_buffer(2 * nb + 2);
+    MFB_LAUNCH(max_neighbour_diff_kernel, nb, RED_THREADS, 0, g_ctx.stream, g->d, g->n[0], g->n[1], g->n[2], g->pitch, part);
+    check_launch("max_neighbour_diff");
+    MFB_LAUNCH(reduce_final_kernel, 1, RED_THREADS, 0, g_ctx.stream, part, nb, 1, part + 2 * nb);
+    check_launch("reduce_final");
+    cuda_check(cudaMemcpyAsync(out, part + 2 * nb, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "D2H");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+int mfb_fourier_resample(mfb_grid* src, mfb_grid* dst) {
+    MFB_TRY
+    to_kspace(src);
+    dst->space = MFB_KSPACE;
+    if (src->n[0] == dst->n[0] && src->n[1] == dst->n[1] && src->n[2] == dst->n[2]) {
+        cuda_check(cudaMemcpyAsync(dst->d, src->d, src->ntot * sizeof(double), cudaMemcpyDeviceToDevice, g_ctx.stream), "copy");
+    } else {
+        KGeom kd = kgeom(dst), ks = kgeom(src);
+        MFB_LAUNCH(resample_kernel, kgrid_blocks(kd), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(dst->d), kd,
+                   reinterpret_cast<const double2*>(src->d), ks);
+        check_launch("resample");
+    }
+    MFB_CATCH
+}
+
+// ---------------------------------------------------------------- pipeline operators
+int mfb_noise_condition(mfb_grid* w, double volfac, int fix, int invert, int remove_corners) {
+    MFB_TRY
+    require(w->space == MFB_KSPACE, "noise_condition: grid must be in k-space");
+    KGeom k = kgeom(w);
+    const double kny = k.kf0 * w->n[0] / 2;
+    MFB_LAUNCH(noise_condition_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(w->d), k,
+               (invert ? -1.0 : 1.0) / volfac, fix, remove_corners, kny);
+    check_launch("noise_condition");
+    MFB_CATCH
+}
+static const double* upload_table(const double* table, size_t ntable, size_t need, int slot) {
+    require(table != nullptr && ntable >= need, "radial table too short: need 3*(N/2)^2+1 entries");
+    if (g_ctx.table_cap[slot] < ntable) {
+        if (g_ctx.table[slot]) cudaFree(g_ctx.table[slot]);
+        g_ctx.table[slot] = (double*)dev_alloc(ntable * sizeof(double));
+        g_ctx.table_cap[slot] = ntable;
+    }
+    cuda_check(cudaMemcpyAsync(g_ctx.table[slot], table, ntable * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream), "table upload");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    return g_ctx.table[slot];
+}
+int mfb_apply_radial_table(mfb_grid* out, const mfb_grid* in, const double* table, size_t ntable, int inv_k2) {
+    MFB_TRY
+    require(in->space == MFB_KSPACE, "apply_radial_table: input must be in k-space");
+    require(in->n[0] == in->n[1] && in->n[1] == in->n[2] && in->L[0] == in->L[1] && in->L[1] == in->L[2],
+            "apply_radial_table: cubic grid required");
+    require(out->ntot == in->ntot, "apply_radial_table: grid size mismatch");
+    const int h = in->n[0] / 2;
+    const double* dt = upload_table(table, ntable, size_t(3) * h * h + 1, 0);
+    out->space = MFB_KSPACE;
+    KGeom k = kgeom(in);
+    MFB_LAUNCH(radial_table_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(out->d),
+               reinterpret_cast<const double2*>(in->d), dt, k, inv_k2 ? 1 : 0);
+    check_launch("radial_table");
+    MFB_CATCH
+}
+int mfb_add_tides(mfb_grid* phi2, const mfb_grid* phi, const double lam[3]) {
+    MFB_TRY
+    require(phi2->space == MFB_KSPACE && phi->space == MFB_KSPACE, "add_tides: k-space grids required");
+    KGeom k = kgeom(phi2);
+    MFB_LAUNCH(tides_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(phi2->d),
+               reinterpret_cast<const double2*>(phi->d), k, lam[0], lam[1], lam[2]);
+    check_launch("tides");
+    MFB_CATCH
+}
+int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* phi2, const mfb_grid* phi3,
+                     mfb_grid* const A3[3], double w1, double w2, double w3, double wc, double scale, const mfb_grid* wnoise,
+                     const double* vbc_table, size_t ntable, double cvbc) {
+    MFB_TRY
+    require(d >= 0 && d < 3, "assemble: bad dimension");
+    require(phi->space == MFB_KSPACE, "assemble: phi must be in k-space");
+    require(!phi2 || phi2->space == MFB_KSPACE, "assemble: phi2 must be in k-space");
+    require(!phi3 || phi3->space == MFB_KSPACE, "assemble: phi3 must be in k-space");
+    AssembleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = d; a.p = (d + 1) % 3; a.q = (d + 2) % 3;
+    a.phi = reinterpret_cast<const double2*>(phi->d);
+    a.phi2 = phi2 ? reinterpret_cast<const double2*>(phi2->d) : nullptr;
+    a.phi3 = phi3 ? reinterpret_cast<const double2*>(phi3->d) : nullptr;
+    if (A3 && A3[0] && A3[1] && A3[2]) {
+        require(A3[a.p]->space == MFB_KSPACE && A3[a.q]->space == MFB_KSPACE, "assemble: A3 must be in k-space");
+        a.Ap = reinterpret_cast<const double2*>(A3[a.p]->d);
+        a.Aq = reinterpret_cast<const double2*>(A3[a.q]->d);
+    }
+    a.w1 = w1; a.w2 = w2; a.w3 = w3; a.wc = wc; a.scale = scale;
+    if (vbc_table) {
+        require(wnoise && wnoise->space == MFB_KSPACE, "assemble: wnoise (k-space) needed for the vbc term");
+        const int h = phi->n[0] / 2;
+        a.vbc_table = upload_table(vbc_table, ntable, size_t(3) * h * h + 1, 1);
+        a.wnoise = reinterpret_cast<const double2*>(wnoise->d);
+        a.cvbc = cvbc;
+    }
+    out->space = MFB_KSPACE;
+    KGeom k = kgeom(phi);
+    MFB_LAUNCH(assemble_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(out->d), a, k);
+    check_launch("assemble");
+    MFB_CATCH
+}
+int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi) {
+    MFB_TRY
+    require(phi->space == MFB_KSPACE, "density_from_phi: phi must be in k-space");
+    out->space = MFB_KSPACE;
+    KGeom k = kgeom(phi);
+    MFB_LAUNCH(laplacian_pow_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(out->d),
+               reinterpret_cast<const double2*>(phi->d), k, 1, 1.0);
+    check_launch("density");
+    MFB_CATCH
+}
+
+// ---------------------------------------------------------------- convolver
+int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    mfb_conv* c = new mfb_conv();
+    for (int d = 0; d < 3; ++d) {
+        require(n[d] % 2 == 0, "Orszag convolver for LPTorder>1 requires even grid size!");  // src/ic_generator.cc:118-121
+        c->n[d] = n[d]; c->L[d] = L[d]; c->np[d] = 3 * n[d] / 2;
+        require(supported_size(n[d]) && supported_size(c->np[d]), "unsupported grid size for the Orszag convolver");
+    }
+    const size_t nzin = n[2] / 2;
+    c->w1_elems = size_t(c->np[0]) * n[1] * nzin;
+    c->w2_elems = size_t(c->np[0]) * c->np[1] * nzin;
+    c->W1 = (double2*)dev_alloc(c->w1_elems * sizeof(double2));
+    c->W2a = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
+    c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
+    if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
+    *out = c;
+    MFB_CATCH
+}
+int mfb_conv_destroy(mfb_conv* c) {
+    MFB_TRY
+    if (c) {
+        cudaFree(c->W1); cudaFree(c->W2a); cudaFree(c->W2b);
+        mfb_grid_destroy(c->fbuf);
+        delete c;
+    }
+    MFB_CATCH
+}
+size_t mfb_conv_workspace_bytes(const mfb_conv* c) {
+    return (c->w1_elems + 2 * c->w2_elems) * sizeof(double2) + c->fbuf->ntot * sizeof(double);
+}
+static void check_conv_grids(mfb_conv* c, mfb_grid* a, mfb_grid* b, mfb_grid* o) {
+    for (mfb_grid* g : {a, b, o})
+        require(g && g->n[0] == c->n[0] && g->n[1] == c->n[1] && g->n[2] == c->n[2], "convolver: grid size mismatch");
+}
+static void check_dims(const int* d, int cnt) {
+    for (int i = 0; i < cnt; ++i) require(d[i] >= 0 && d[i] < 3, "convolver: axis index must be 0,1,2");
+}
+int mfb_conv_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r[2], mfb_grid* out, int op,
+                      double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, r, out); check_dims(d2l, 2); check_dims(d2r, 2);
+    conv2(c, hessian_operand(l, d2l), hessian_operand(r, d2r), out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_hessians3(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* m, const int d2m[2], mfb_grid* r,
+                       const int d2r[2], mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, m, out); check_conv_grids(c, r, r, out);
+    check_dims(d2l, 2); check_dims(d2m, 2); check_dims(d2r, 2);
+    to_kspace(r);
+    c->fbuf->space = MFB_KSPACE;
+    conv2(c, hessian_operand(l, d2l), hessian_operand(m, d2m), c->fbuf, OP_ASSIGN, 0.0);
+    conv2(c, Operand{c->fbuf, -1, -1, -1, -1, 1.0, 0.0, 0}, hessian_operand(r, d2r), out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_sum_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r1[2], const int d2r2[2],
+                          mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, r, out); check_dims(d2l, 2); check_dims(d2r1, 2); check_dims(d2r2, 2);
+    conv2(c, hessian_operand(l, d2l), Operand{r, d2r1[0], d2r1[1], d2r2[0], d2r2[1], -1.0, -1.0, 0}, out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_diff_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r1[2], const int d2r2[2],
+                           mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, r, out); check_dims(d2l, 2); check_dims(d2r1, 2); check_dims(d2r2, 2);
+    conv2(c, hessian_operand(l, d2l), Operand{r, d2r1[0], d2r1[1], d2r2[0], d2r2[1], -1.0, +1.0, 0}, out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_gradients(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, int d1r, mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, r, out); check_dims(&d1l, 1); check_dims(&d1r, 1);
+    conv2(c, Operand{l, d1l, -1, -1, -1, 1.0, 0.0, 1}, Operand{r, d1r, -1, -1, -1, 1.0, 0.0, 1}, out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_gradient_hessian(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, const int d2r[2], mfb_grid* out, int op,
+                              double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, r, out); check_dims(&d1l, 1); check_dims(d2r, 2);
+    // (-i k_a) f  and  -k_a k_b g   (include/convolution.hh:116-124); Nyquist never enters the padded grid
+    conv2(c, Operand{l, d1l, -1, -1, -1, -1.0, 0.0, 1}, Operand{r, d2r[0], d2r[1], -1, -1, -1.0, 0.0, 0}, out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_multiply(mfb_conv* c, mfb_grid* l, mfb_grid* r, mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, l, r, out);
+    conv2(c, Operand{l, -1, -1, -1, -1, 1.0, 0.0, 0}, Operand{r, -1, -1, -1, -1, 1.0, 0.0, 0}, out, op, alpha);
+    MFB_CATCH
+}
+int mfb_lpt_sources(mfb_conv* c, int order, double Dplus0, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3, mfb_grid* const A3[3],
+                    const double* tides_lambda) {
+    MFB_TRY
+    lpt_sources(c, order, Dplus0, phi, phi2, phi3, A3, tides_lambda);
+    MFB_CATCH
+}
+
+// ---------------------------------------------------------------- particles
+int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, int real64, int ids64, int with_masses) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(lattice_type >= 0 && lattice_type <= 3, "only Bravais lattices (sc,bcc,fcc,rsc) are supported on the device path");
+    mfb_particles* p = new mfb_particles();
+    for (int d = 0; d < 3; ++d) p->n[d] = n[d];
+    p->lattice_type = lattice_type; p->real64 = real64; p->ids64 = ids64;
+    const size_t ov = size_t(1) << lattice_type;
+    p->np = ov * size_t(n[0]) * n[1] * n[2];
+    const size_t rs = real64 ? 8 : 4, is = ids64 ? 8 : 4;
+    p->pos = dev_alloc(3 * p->np * rs);
+    p->vel = dev_alloc(3 * p->np * rs);
+    p->ids = dev_alloc(p->np * is);
+    p->mass = with_masses ? dev_alloc(p->np * rs) : nullptr;
+    *out = p;
+    MFB_CATCH
+}
+int mfb_particles_destroy(mfb_particles* p) {
+    MFB_TRY
+    if (p) {
+        cudaFree(p->pos); cudaFree(p->vel); cudaFree(p->ids);
+        if (p->mass) cudaFree(p->mass);
+        delete p;
+    }
+    MFB_CATCH
+}
+size_t mfb_particles_count(const mfb_particles* p) { return p->np; }
+int mfb_particles_set_ids(mfb_particles* p, unsigned long long id_offset_species) {
+    MFB_TRY
+    const long ncell = long(p->n[0]) * p->n[1] * p->n[2];
+    const int ov = 1 << p->lattice_type;
+    const unsigned long long off = id_offset_species * (unsigned long long)ov * (unsigned long long)ncell;
+    const unsigned nb = stream_blocks(p->np);
+    if (p->ids64) {
+        MFB_LAUNCH(particle_ids_kernel<unsigned long long>, nb, EW_THREADS, 0, g_ctx.stream, (unsigned long long*)p->ids, ncell, ov, off, 0L);
+    } else {
+        MFB_LAUNCH(particle_ids_kernel<unsigned int>, nb, EW_THREADS, 0, g_ctx.stream, (unsigned int*)p->ids, ncell, ov, off, 0L);
+    }
+    check_launch("particle_ids");
+    MFB_CATCH
+}
+int mfb_particles_set_positions(mfb_particles* p, int lattice_index, int idim, double lunit, mfb_grid* field) {
+    MFB_TRY
+    require(idim >= 0 && idim < 3, "bad dimension");
+    particles_readout(p, 0, lattice_index, idim, lunit, field);
+    MFB_CATCH
+}
+int mfb_particles_set_velocities(mfb_particles* p, int lattice_index, int idim, mfb_grid* field) {
+    MFB_TRY
+    require(idim >= 0 && idim < 3, "bad dimension");
+    particles_readout(p, 1, lattice_index, idim, 1.0, field);
+    MFB_CATCH
+}
+int mfb_particles_set_masses(mfb_particles* p, int lattice_index, double munit, mfb_grid* field) {
+    MFB_TRY
+    require(p->mass != nullptr, "particles were created without masses");
+    particles_readout(p, 2, lattice_index, 0, munit, field);
+    MFB_CATCH
+}
+int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* ids, void* mass) {
+    MFB_TRY
+    const size_t rs = p->real64 ? 8 : 4, is = p->ids64 ? 8 : 4;
+    if (pos) cuda_check(cudaMemcpyAsync(pos, p->pos, 3 * p->np * rs, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H pos");
+    if (vel) cuda_check(cudaMemcpyAsync(vel, p->vel, 3 * p->np * rs, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H vel");
+    if (ids) cuda_check(cudaMemcpyAsync(ids, p->ids, p->np * is, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H ids");
+    if (mass && p->mass) cuda_check(cudaMemcpyAsync(mass, p->mass, p->np * rs, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H mass");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// mfb_platform.h - build-mode switch for the monofonIC-B200 kernels.
+//
+// Product build: nvcc, sm_100a.  All kernels are plain CUDA.
+//
+// Test-only build (-DMFB_EMU, g++): the very same kernel sources are compiled against
+// tests/emu/cuda_emu.h, which runs every CUDA thread of a block as an OS thread with a
+// real barrier for __syncthreads().  It exists so that the index arithmetic of the kernels
+// can be checked against the oracle in the GPU-less build container (`pytest -m "not gpu"`).
+// It is NOT a fallback: the Python package and the C++ host shims only ever load
+// libmfb200.so (the nvcc build) and fail loudly when it is missing.
+#pragma once
+
+#ifdef MFB_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define MFB_DYN_SMEM(type, name)                                     \
+    extern __shared__ __align__(16) unsigned char name##_raw_[];     \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#define MFB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MFB_KERNEL_SMEM_OPTIN(kernel, bytes) \
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
+#include <cstddef>
+#include <cstdint>
+
+#define MFB_HD __host__ __device__ __forceinline__
+#define MFB_D __device__ __forceinline__
+
+// streaming (read-once / write-once) global accesses: keep them out of L1 so that the
+// twiddle table stays cached there.
+#if !defined(MFB_EMU)
+MFB_D double2 mfb_ld_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+MFB_D void mfb_st_stream(double2* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+MFB_D double mfb_ld_stream1(const double* p) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+#else
+inline double2 mfb_ld_stream(const double2* p) { return *p; }
+inline void mfb_st_stream(double2* p, double2 v) { *p = v; }
+inline double mfb_ld_stream1(const double* p) { return *p; }
+#endif

@@ -1,0 +1,351 @@
+"""Host-side mirrors of the reference classes on the hot path.
+
+Names, argument meaning and error behaviour follow the reference:
+  Grid_FFT            include/grid_fft.hh:40-914, src/grid_fft.cc
+  OrszagConvolver     include/convolution.hh:28-293 (named products), :429-669
+  op.*                include/operators.hh:25-35
+  Particles           particle::lattice_generator / particle::container
+                      (include/particle_generator.hh, include/particle_container.hh)
+Every method is a thin call into the C ABI (include/mfb200.h); numpy is only used to move
+host buffers in and out.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+kspace_id, rspace_id = 0, 1  # enum space_t, include/grid_fft.hh:29
+_state = {"lib": None}
+
+
+def _lib():
+    if _state["lib"] is None:
+        raise L.MfbError("monofonic_b200.init() has not been called")
+    return _state["lib"]
+
+
+def init(device: int = 0, lib_path: str | None = None):
+    """Load libmfb200.so and bind it to CUDA device `device`.  Fails loudly without a GPU."""
+    lib = L.load(lib_path)
+    L.check(lib.mfb_init(int(device)), lib)
+    _state["lib"] = lib
+    return lib
+
+
+def finalize():
+    if _state["lib"] is not None:
+        _state["lib"].mfb_finalize()
+        _state["lib"] = None
+
+
+def synchronize():
+    L.check(_lib().mfb_synchronize(), _lib())
+
+
+def kernel_launches() -> int:
+    return int(_lib().mfb_kernel_launches())
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _i2(v):
+    return (C.c_int * 2)(*[int(x) for x in v])
+
+
+class _OutOp:
+    """op::assign_to / add_to / subtract_from / multiply_add_to  (include/operators.hh:25-35)"""
+
+    def __init__(self, grid, code, alpha=0.0):
+        self.grid, self.code, self.alpha = grid, code, float(alpha)
+
+
+class op:
+    @staticmethod
+    def assign_to(g):
+        return _OutOp(g, 0)
+
+    @staticmethod
+    def add_to(g):
+        return _OutOp(g, 1)
+
+    @staticmethod
+    def subtract_from(g):
+        return _OutOp(g, 2)
+
+    @staticmethod
+    def multiply_add_to(g, x):
+        return _OutOp(g, 3, x)
+
+
+class Grid_FFT:
+    """Device-resident FFT-able grid (Grid_FFT<real_t>, non-distributed layout)."""
+
+    def __init__(self, N, Lbox, allocate=True, initialspace=rspace_id):
+        self.n_ = tuple(int(x) for x in N)
+        self.length_ = tuple(float(x) for x in Lbox)
+        self._h = C.c_void_p()
+        self._initialspace = initialspace
+        self._lib = _lib()
+        if allocate:
+            self.allocate()
+
+    # -- allocation ---------------------------------------------------------------------
+    def allocate(self):
+        if self._h:
+            return
+        L.check(self._lib.mfb_grid_create(C.byref(self._h), _i3(self.n_), _d3(self.length_), self._initialspace), self._lib)
+
+    def is_allocated(self):
+        return bool(self._h)
+
+    def reset(self):
+        if self._h:
+            self._lib.mfb_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.reset()
+        except Exception:
+            pass
+
+    # -- geometry -----------------------------------------------------------------------
+    @property
+    def space_(self):
+        return self._lib.mfb_grid_space(self._h)
+
+    @property
+    def ntot_(self):
+        return int(self._lib.mfb_grid_ntot(self._h))
+
+    def size(self, i):
+        n0, n1, n2 = self.n_
+        if self.space_ == rspace_id:
+            return (n0, n1, n2, n2 + 2)[i]
+        return (n0, n1, n2 // 2 + 1, n2 // 2 + 1)[i]
+
+    def global_size(self):
+        return self.n_[0] * self.n_[1] * self.n_[2]
+
+    # -- host <-> device ----------------------------------------------------------------
+    def upload_raw(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.float64).reshape(-1)
+        assert buf.size == self.ntot_, (buf.size, self.ntot_)
+        L.check(self._lib.mfb_grid_upload(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)
+
+    def download_raw(self) -> np.ndarray:
+        buf = np.empty(self.ntot_, dtype=np.float64)
+        L.check(self._lib.mfb_grid_download(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)
+        return buf
+
+    def set_real(self, x: np.ndarray):
+        """fill from a [n0][n1][n2] real array (relem view); grid is declared real-space"""
+        n0, n1, n2 = self.n_
+        buf = np.zeros((n0, n1, n2 + 2))
+        buf[:, :, :n2] = x
+        self.FourierTransformBackward(False)
+        self.upload_raw(buf)
+
+    def get_real(self) -> np.ndarray:
+        n0, n1, n2 = self.n_
+        assert self.space_ == rspace_id
+        return self.download_raw().reshape(n0, n1, n2 + 2)[:, :, :n2].copy()
+
+    def set_kspace(self, X: np.ndarray):
+        """fill from a [kx][ky][kz] half-spectrum (kelem view); grid is declared k-space"""
+        n0, n1, n2 = self.n_
+        X = np.ascontiguousarray(X, dtype=np.complex128)
+        assert X.shape == (n0, n1, n2 // 2 + 1)
+        self.FourierTransformForward(False)
+        self.upload_raw(X.view(np.float64))
+
+    def get_kspace(self) -> np.ndarray:
+        n0, n1, n2 = self.n_
+        assert self.space_ == kspace_id
+        return self.download_raw().view(np.complex128).reshape(n0, n1, n2 // 2 + 1).copy()
+
+    # -- transforms ---------------------------------------------------------------------
+    def FourierTransformForward(self, do_transform=True):
+        L.check(self._lib.mfb_fft_forward(self._h, int(bool(do_transform))), self._lib)
+
+    def FourierTransformBackward(self, do_transform=True):
+        L.check(self._lib.mfb_fft_backward(self._h, int(bool(do_transform))), self._lib)
+
+    def FourierInterpolateCopyTo(self, grid_to: "Grid_FFT"):
+        L.check(self._lib.mfb_fourier_resample(self._h, grid_to._h), self._lib)
+
+    # -- element-wise -------------------------------------------------------------------
+    def zero(self):
+        L.check(self._lib.mfb_grid_zero(self._h), self._lib)
+
+    def copy_from(self, g: "Grid_FFT"):
+        L.check(self._lib.mfb_grid_copy(self._h, g._h), self._lib)
+
+    def __imul__(self, x):
+        L.check(self._lib.mfb_grid_scale(self._h, float(x)), self._lib)
+        return self
+
+    def __itruediv__(self, x):
+        L.check(self._lib.mfb_grid_scale(self._h, 1.0 / float(x)), self._lib)
+        return self
+
+    def axpy(self, a, x: "Grid_FFT", b):
+        L.check(self._lib.mfb_grid_axpy(self._h, float(a), x._h, float(b)), self._lib)
+
+    def affine(self, a, b):
+        L.check(self._lib.mfb_grid_affine(self._h, float(a), float(b)), self._lib)
+
+    def zero_DC_mode(self):
+        L.check(self._lib.mfb_grid_zero_dc(self._h), self._lib)
+
+    def apply_InverseLaplacian(self):
+        L.check(self._lib.mfb_grid_inverse_laplacian(self._h), self._lib)
+        return self
+
+    def apply_Laplacian(self):
+        L.check(self._lib.mfb_grid_laplacian(self._h, 0), self._lib)
+        return self
+
+    def apply_negative_Laplacian(self):
+        L.check(self._lib.mfb_grid_laplacian(self._h, 1), self._lib)
+        return self
+
+    def shift_field(self, s, transform_back=True):
+        L.check(self._lib.mfb_grid_shift_field(self._h, _d3(s), int(bool(transform_back))), self._lib)
+
+    # -- reductions ---------------------------------------------------------------------
+    def _red(self, fn):
+        out = C.c_double()
+        L.check(fn(self._h, C.byref(out)), self._lib)
+        return out.value
+
+    def mean(self):
+        return self._red(self._lib.mfb_grid_mean)
+
+    def std(self):
+        return self._red(self._lib.mfb_grid_std)
+
+    def compute_2norm(self):
+        return self._red(self._lib.mfb_grid_2norm)
+
+    def max_neighbour_diff(self):
+        return self._red(self._lib.mfb_grid_max_neighbour_diff)
+
+
+class OrszagConvolver:
+    """OrszagConvolver<real_t> with the named products of BaseConvolver."""
+
+    def __init__(self, N, Lbox):
+        self._lib = _lib()
+        self._h = C.c_void_p()
+        self.n_ = tuple(int(x) for x in N)
+        L.check(self._lib.mfb_conv_create(C.byref(self._h), _i3(N), _d3(Lbox)), self._lib)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.mfb_conv_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def workspace_bytes(self):
+        return int(self._lib.mfb_conv_workspace_bytes(self._h))
+
+    def convolve_Hessians(self, *args):
+        """(inl, d2l, inr, d2r, output_op)  or  (inl, d2l, inm, d2m, inr, d2r, output_op)"""
+        if len(args) == 5:
+            inl, d2l, inr, d2r, o = args
+            rc = self._lib.mfb_conv_hessians(self._h, inl._h, _i2(d2l), inr._h, _i2(d2r), o.grid._h, o.code, o.alpha)
+        elif len(args) == 7:
+            inl, d2l, inm, d2m, inr, d2r, o = args
+            rc = self._lib.mfb_conv_hessians3(self._h, inl._h, _i2(d2l), inm._h, _i2(d2m), inr._h, _i2(d2r), o.grid._h,
+                                              o.code, o.alpha)
+        else:
+            raise TypeError("convolve_Hessians takes 5 or 7 arguments")
+        L.check(rc, self._lib)
+
+    def convolve_SumOfHessians(self, inl, d2l, inr, d2r1, d2r2, o):
+        L.check(self._lib.mfb_conv_sum_hessians(self._h, inl._h, _i2(d2l), inr._h, _i2(d2r1), _i2(d2r2), o.grid._h,
+                                                o.code, o.alpha), self._lib)
+
+    def convolve_DifferenceOfHessians(self, inl, d2l, inr, d2r1, d2r2, o):
+        L.check(self._lib.mfb_conv_diff_hessians(self._h, inl._h, _i2(d2l), inr._h, _i2(d2r1), _i2(d2r2), o.grid._h,
+                                                 o.code, o.alpha), self._lib)
+
+    def convolve_Gradients(self, inl, d1l, inr, d1r, o):
+        L.check(self._lib.mfb_conv_gradients(self._h, inl._h, int(d1l[0]), inr._h, int(d1r[0]), o.grid._h, o.code, o.alpha),
+                self._lib)
+
+    def convolve_Gradient_and_Hessian(self, inl, d1l, inr, d2r, o):
+        L.check(self._lib.mfb_conv_gradient_hessian(self._h, inl._h, int(d1l[0]), inr._h, _i2(d2r), o.grid._h, o.code,
+                                                    o.alpha), self._lib)
+
+    def multiply_field(self, inl, inr, o):
+        L.check(self._lib.mfb_conv_multiply(self._h, inl._h, inr._h, o.grid._h, o.code, o.alpha), self._lib)
+
+
+LATTICE = {"sc": 0, "bcc": 1, "fcc": 2, "rsc": 3}
+
+
+class Particles:
+    """particle::lattice_generator + particle::container for the Bravais lattices."""
+
+    def __init__(self, lattice_type, lattice_index, b64reals, b64ids, bwithmasses, IDoffset, field: Grid_FFT):
+        self._lib = _lib()
+        self._h = C.c_void_p()
+        lt = LATTICE[lattice_type] if isinstance(lattice_type, str) else int(lattice_type)
+        self.lattice_type, self.lattice_index = lt, int(lattice_index)
+        self.b64reals, self.b64ids, self.bwithmasses = bool(b64reals), bool(b64ids), bool(bwithmasses)
+        L.check(self._lib.mfb_particles_create(C.byref(self._h), _i3(field.n_), lt, int(self.b64reals), int(self.b64ids),
+                                               int(self.bwithmasses)), self._lib)
+        L.check(self._lib.mfb_particles_set_ids(self._h, int(IDoffset)), self._lib)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.mfb_particles_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def get_local_num_particles(self):
+        return int(self._lib.mfb_particles_count(self._h))
+
+    def set_positions(self, idim, lunit, field: Grid_FFT):
+        L.check(self._lib.mfb_particles_set_positions(self._h, self.lattice_index, int(idim), float(lunit), field._h), self._lib)
+
+    def set_velocities(self, idim, field: Grid_FFT):
+        L.check(self._lib.mfb_particles_set_velocities(self._h, self.lattice_index, int(idim), field._h), self._lib)
+
+    def set_masses(self, munit, field: Grid_FFT):
+        L.check(self._lib.mfb_particles_set_masses(self._h, self.lattice_index, float(munit), field._h), self._lib)
+
+    def download(self, pos=True, vel=True, ids=True, mass=True, out=None):
+        """-> dict of host arrays (positions/velocities [np,3], ids [np], masses [np]).
+        `out` may hold preallocated (e.g. pinned) arrays under the same keys."""
+        n = self.get_local_num_particles()
+        rt = np.float64 if self.b64reals else np.float32
+        it = np.uint64 if self.b64ids else np.uint32
+        out = out if out is not None else {}
+        res = {}
+        if pos:
+            res["pos"] = out.get("pos") if "pos" in out else np.empty((n, 3), rt)
+        if vel:
+            res["vel"] = out.get("vel") if "vel" in out else np.empty((n, 3), rt)
+        if ids:
+            res["ids"] = out.get("ids") if "ids" in out else np.empty(n, it)
+        if mass and self.bwithmasses:
+            res["mass"] = out.get("mass") if "mass" in out else np.empty(n, rt)
+        p = lambda k: res[k].ctypes.data_as(C.c_void_p) if k in res else None
+        L.check(self._lib.mfb_particles_download(self._h, p("pos"), p("vel"), p("ids"), p("mass")), self._lib)
+        return res

@@ -1,0 +1,159 @@
+"""Host driver of the LPT field pipeline - the numerical spine of ic_generator::run
+(src/ic_generator.cc:90-982) expressed as calls into the C ABI.
+
+What stays on the host (and keeps the reference's plugin APIs): the white-noise plugin fills a
+grid, the transfer-function plugin is evaluated once per distinct |k| into a radial table
+(SURVEY.md 0.7), the output plugin receives host arrays.  Everything between
+"conditioned white noise in k-space" and "particle arrays / component fields" runs on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+from .grid import Grid_FFT, OrszagConvolver, Particles, kspace_id, rspace_id, _lib, LATTICE
+
+
+@dataclass
+class lpt_config:
+    """the [setup]/[output] keys that reach the hot path"""
+    GridRes: int = 32
+    BoxLength: float = 100.0
+    LPTorder: int = 3
+    ParticleLoad: str = "sc"
+    DoFixing: bool = False
+    DoInversion: bool = False
+    DoRemoveCornerModes: bool = False
+    Dplus0: float = 1.0          # cosmology::calculator::get_growth_factor(astart)
+    vfac: float = 1.0            # cosmology::calculator::get_vfact(astart)
+    lunit: float = 1.0           # output_plugin::position_unit()
+    vunit: float = 1.0           # output_plugin::velocity_unit()
+    real64: bool = True          # output_plugin::has_64bit_reals()
+    ids64: bool = False          # output_plugin::has_64bit_ids()
+    tides: tuple | None = None   # LSS_aniso_l{x,y,z}
+
+
+def radial_table(n: int, boxlen: float, amplitude) -> np.ndarray:
+    """table[m] = A(kfac*sqrt(m)), m = |n|^2 = 0..3(N/2)^2: one host call of the transfer-function
+    plugin per distinct |k| instead of one per mode (include/cosmology_calculator.hh:405-408)."""
+    h = n // 2
+    m = np.arange(3 * h * h + 1, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.asarray(amplitude(2.0 * np.pi / boxlen * np.sqrt(m)), dtype=np.float64)
+    return np.ascontiguousarray(np.where(np.isfinite(t), t, 0.0))
+
+
+class LPTPipeline:
+    """Device-resident state of one IC run: wnoise, phi, phi2, phi3, A3[3], tmp + the convolver."""
+
+    def __init__(self, cfg: lpt_config):
+        self.cfg = cfg
+        n, Lb = cfg.GridRes, cfg.BoxLength
+        if cfg.LPTorder > 1 and n % 2:
+            # src/ic_generator.cc:118-121
+            raise RuntimeError("Orszag convolver for LPTorder>1 requires even grid size!")
+        self.N, self.Lbox = (n, n, n), (Lb, Lb, Lb)
+        self._lib = _lib()
+        mk = lambda alloc=True, sp=rspace_id: Grid_FFT(self.N, self.Lbox, alloc, sp)
+        order = min(cfg.LPTorder, 3)
+        self.order = order
+        self.wnoise = mk()
+        self.phi = mk()
+        self.phi2 = mk(order > 1)
+        self.phi3 = mk(order > 2)
+        self.A3 = [mk(order > 2) for _ in range(3)]
+        self.tmp = mk()
+        self.conv = OrszagConvolver(self.N, self.Lbox) if order > 1 else None
+        self.particles = None
+
+    # -- stages -------------------------------------------------------------------------
+    def set_noise_k(self, W: np.ndarray):
+        """white noise in k-space [kx][ky][kz] as left by RNG_plugin::Fill_Grid + forward FFT"""
+        self.wnoise.set_kspace(W)
+
+    def condition_noise(self):
+        c = self.cfg
+        volfac = (c.BoxLength / c.GridRes / 2.0 / np.pi) ** 1.5  # src/ic_generator.cc:210
+        L.check(self._lib.mfb_noise_condition(self.wnoise._h, volfac, int(c.DoFixing), int(c.DoInversion),
+                                              int(c.DoRemoveCornerModes)), self._lib)
+
+    def compute_phi1(self, table: np.ndarray):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        L.check(self._lib.mfb_apply_radial_table(self.phi._h, self.wnoise._h, t.ctypes.data_as(C.c_void_p), t.size, 1),
+                self._lib)
+
+    def compute_sources(self):
+        """phi2, phi3, A3 and the growth-factor scaling (src/ic_generator.cc:475-574)"""
+        c = self.cfg
+        if self.order == 1:
+            self.phi *= -c.Dplus0
+            return
+        A3 = (C.c_void_p * 3)(*[(g._h if g.is_allocated() else None) for g in self.A3])
+        lam = (C.c_double * 3)(*c.tides) if c.tides is not None else None
+        L.check(self._lib.mfb_lpt_sources(self.conv._h, self.order, float(c.Dplus0), self.phi._h,
+                                          self.phi2._h if self.order > 1 else None,
+                                          self.phi3._h if self.order > 2 else None, A3, lam), self._lib)
+
+    def _assemble(self, d, w, wc, scale, vbc=None):
+        A3 = (C.c_void_p * 3)(*[(g._h if g.is_allocated() else None) for g in self.A3])
+        o = self.order
+        tab, ntab, cv, wn = None, 0, 0.0, None
+        if vbc is not None:
+            t = np.ascontiguousarray(vbc[0], dtype=np.float64)
+            tab, ntab, cv, wn = t.ctypes.data_as(C.c_void_p), t.size, float(vbc[1]), self.wnoise._h
+        L.check(self._lib.mfb_lpt_assemble(self.tmp._h, d, self.phi._h, self.phi2._h if o > 1 else None,
+                                           self.phi3._h if o > 2 else None, A3 if o > 2 else None,
+                                           w[0], w[1], w[2], wc, scale, wn, tab, ntab, cv), self._lib)
+
+    def displacement_field(self, d):
+        """tmp <- Psi_d in real space (src/ic_generator.cc:832-871)"""
+        c = self.cfg
+        self._assemble(d, (1.0, 1.0, 1.0), 1.0, c.lunit / c.BoxLength)
+        self.tmp.FourierTransformBackward()
+        return self.tmp
+
+    def velocity_field(self, d, vbc=None):
+        """tmp <- v_d in real space (src/ic_generator.cc:888-942)"""
+        c = self.cfg
+        v = c.vfac
+        self._assemble(d, (v, 2 * v, 3 * v), 3 * v, c.vunit / c.BoxLength, vbc)
+        self.tmp.FourierTransformBackward()
+        return self.tmp
+
+    def density_field(self):
+        """tmp <- delta = k^2 phi in real space (src/ic_generator.cc:962-973)"""
+        L.check(self._lib.mfb_density_from_phi(self.tmp._h, self.phi._h), self._lib)
+        self.tmp.FourierTransformBackward()
+        return self.tmp
+
+    def make_particles(self, lattice_index=0, with_masses=False, id_offset=0):
+        c = self.cfg
+        self.particles = Particles(c.ParticleLoad, lattice_index, c.real64, c.ids64, with_masses, id_offset, self.tmp)
+        return self.particles
+
+    def fill_particles(self, lattice_index=0):
+        """the species output loop for particle output (src/ic_generator.cc:832-955)"""
+        c = self.cfg
+        if self.particles is None:
+            self.make_particles(lattice_index)
+        for d in range(3):
+            self.particles.set_positions(d, c.lunit, self.displacement_field(d))
+        for d in range(3):
+            self.particles.set_velocities(d, self.velocity_field(d))
+        return self.particles
+
+    def run_device(self, table: np.ndarray, particles=True):
+        """conditioned noise resident in k-space -> all LPT terms -> Psi, v (-> particle AoS), all on device"""
+        self.compute_phi1(table)
+        self.compute_sources()
+        if particles:
+            return self.fill_particles()
+        out = {}
+        for d, nm in enumerate("xyz"):
+            out["d" + nm] = self.displacement_field(d).get_real()
+        for d, nm in enumerate("xyz"):
+            out["v" + nm] = self.velocity_field(d).get_real()
+        return out

@@ -1,0 +1,276 @@
+"""Backend-agnostic parity checks: the CUDA path (through the C ABI host mirror `M`) against the
+CPU oracle.  Used twice: tests/test_emu_parity.py runs them on the thread-emulation build at tiny
+sizes (no GPU needed), tests/test_gpu_parity.py on the real sm_100a build on a B200.
+
+Tolerances: FP64 fields  max|err| <= 1e-12 * max|ref|  (far inside north_star's 1e-9*max|Psi|);
+goldens at the reference's own np.allclose(rtol=1e-9, atol=1e-14); integer IDs exact."""
+import numpy as np
+
+import golden_util as G
+import lpt_oracle as O
+
+TOL = 1e-12
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def noise_and_phi(n, L=100.0, seed=7, nyquist_zero=True):
+    g = O.GridSpec(n, L)
+    W = O.make_white_noise_k(n, seed, nyquist_zero)
+    Wc = O.condition_noise(g, W)
+    phi = O.phi1_from_noise(g, Wc, O.power_law_amplitude())
+    return g, W, Wc, phi
+
+
+# ------------------------------------------------------------------ FFT
+def check_fft(M, n, n1=None, n2=None):
+    n1, n2 = n1 or n, n2 or n
+    rng = np.random.default_rng(n + 3 * n1 + 7 * n2)
+    x = rng.standard_normal((n, n1, n2))
+    G_ = M.Grid_FFT((n, n1, n2), (100.0, 100.0, 100.0))
+    G_.set_real(x)
+    G_.FourierTransformForward()
+    ref = np.fft.rfftn(x) / np.sqrt(float(n * n1 * n2))
+    assert relerr(G_.get_kspace(), ref) < TOL
+    G_.FourierTransformBackward()
+    assert relerr(G_.get_real(), x) < TOL
+    # do_transform=False only flips the flag (src/grid_fft.cc:218,230-235)
+    G_.FourierTransformForward(False)
+    assert G_.space_ == M.kspace_id
+    G_.FourierTransformBackward(False)
+    assert relerr(G_.get_real(), x) < TOL
+
+
+def check_c2r_nonhermitian(M, n):
+    """FFTW c2r ignores Im of the self-conjugate kz=0 / kz=n/2 entries: same here."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((n, n, n // 2 + 1)) + 1j * rng.standard_normal((n, n, n // 2 + 1))
+    G_ = M.Grid_FFT((n,) * 3, (1.0,) * 3)
+    G_.set_kspace(X)
+    G_.FourierTransformBackward()
+    ref = np.fft.irfftn(X, s=(n, n, n), axes=(0, 1, 2)) * np.sqrt(float(n) ** 3)
+    assert relerr(G_.get_real(), ref) < TOL
+
+
+# ------------------------------------------------------------------ k-space operators
+def check_kops(M, n):
+    L = 100.0
+    g, W, Wc, phi = noise_and_phi(n, L)
+    Gw = M.Grid_FFT((n,) * 3, (L,) * 3)
+    Gw.set_kspace(W)
+    lib = M.grid._lib()
+    import ctypes as C
+    volfac = (L / n / 2.0 / np.pi) ** 1.5
+    assert lib.mfb_noise_condition(Gw._h, volfac, 0, 0, 0) == 0
+    assert relerr(Gw.get_kspace(), Wc) < TOL
+    # fixing + inversion + corner removal
+    Gw.set_kspace(W)
+    assert lib.mfb_noise_condition(Gw._h, volfac, 1, 1, 1) == 0
+    assert relerr(Gw.get_kspace(), O.condition_noise(g, W, True, True, True)) < TOL
+    # phi1 through the radial table
+    Gw.set_kspace(Wc)
+    Gp = M.Grid_FFT((n,) * 3, (L,) * 3)
+    tab = O.radial_table(g, O.power_law_amplitude())
+    assert lib.mfb_apply_radial_table(Gp._h, Gw._h, tab.ctypes.data_as(C.c_void_p), tab.size, 1) == 0
+    assert relerr(Gp.get_kspace(), phi) < TOL
+    # Poisson / Laplacians / DC
+    Gp.apply_InverseLaplacian()
+    assert relerr(Gp.get_kspace(), O.inverse_laplacian(g, phi)) < TOL
+    Gp.set_kspace(phi)
+    Gp.apply_Laplacian()
+    ref = -g.k2() * phi
+    ref[0, 0, 0] = 0
+    assert relerr(Gp.get_kspace(), ref) < TOL
+    # scale, copy, axpy
+    Gp.set_kspace(phi)
+    Gp *= 2.5
+    Gq = M.Grid_FFT((n,) * 3, (L,) * 3)
+    Gq.copy_from(Gp)
+    assert Gq.space_ == M.kspace_id
+    Gq.axpy(2.0, Gp, -1.0)
+    assert relerr(Gq.get_kspace(), 2.5 * phi) < TOL
+    # shift_field incl. Nyquist planes (include/grid_fft.hh:832-842)
+    _, _, _, phin = noise_and_phi(n, L, 11, nyquist_zero=False)
+    x = g.bwd(phin)
+    Gq.set_real(x)
+    Gq.shift_field((0.5, 0.25, 0.5))
+    assert relerr(Gq.get_real(), O.shift_field_r(g, x, (0.5, 0.25, 0.5))) < TOL
+    # reductions
+    assert abs(Gq.mean() - Gq.get_real().mean()) < 1e-13 * max(1.0, np.abs(x).max())
+    assert abs(Gq.std() - Gq.get_real().std()) < 1e-12 * x.std()
+    xr = Gq.get_real()
+    d = max(np.abs(np.roll(xr, -1, a) - xr)[: n - 1].max() for a in range(3))
+    assert abs(Gq.max_neighbour_diff() - d) <= 1e-15 * d
+    Gq.zero_DC_mode()
+    assert abs(Gq.get_real().mean()) < 1e-14 * np.abs(x).max()
+    # resample N -> 3N/2 -> N (FourierInterpolateCopyTo, Nyquist dropped)
+    n15 = 3 * n // 2
+    Gb = M.Grid_FFT((n15,) * 3, (L,) * 3)
+    Gp.set_kspace(phin)
+    Gp.FourierInterpolateCopyTo(Gb)
+    assert relerr(Gb.get_kspace(), O.fourier_interpolate_copy(g, O.GridSpec(n15, L), phin)) < TOL
+    Gb.FourierInterpolateCopyTo(Gq)
+    ref = phin.copy()
+    ref[n // 2], ref[:, n // 2], ref[:, :, n // 2] = 0, 0, 0
+    assert relerr(Gq.get_kspace(), ref) < TOL
+
+
+# ------------------------------------------------------------------ convolver
+def check_convolver(M, n, nyquist_zero=True):
+    L = 100.0
+    g, W, Wc, phi = noise_and_phi(n, L, 9, nyquist_zero)
+    _, _, _, psi = noise_and_phi(n, L, 10, nyquist_zero)
+    cv = O.OrszagConvolver(g)
+    P = M.Grid_FFT((n,) * 3, (L,) * 3)
+    Q = M.Grid_FFT((n,) * 3, (L,) * 3)
+    out = M.Grid_FFT((n,) * 3, (L,) * 3, True, M.kspace_id)
+    P.set_kspace(phi)
+    Q.set_kspace(psi)
+    C = M.OrszagConvolver((n,) * 3, (L,) * 3)
+    op = M.op
+    ref = cv.convolve_Hessians(phi, (0, 1), psi, (1, 2))
+    C.convolve_Hessians(P, (0, 1), Q, (1, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    got = out.get_kspace()
+    h = n // 2
+    assert not got[h].any() and not got[:, h].any() and not got[:, :, h].any()  # Nyquist planes are exactly 0
+    ref = ref + cv.convolve_SumOfHessians(phi, (0, 0), psi, (1, 1), (2, 2))
+    C.convolve_SumOfHessians(P, (0, 0), Q, (1, 1), (2, 2), op.add_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = ref - cv.convolve_DifferenceOfHessians(phi, (1, 2), psi, (1, 1), (2, 2))
+    C.convolve_DifferenceOfHessians(P, (1, 2), Q, (1, 1), (2, 2), op.subtract_from(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = ref + (-5.0 / 7.0) * cv.convolve_Hessians3(phi, (0, 0), psi, (0, 2), phi, (2, 2))
+    C.convolve_Hessians(P, (0, 0), Q, (0, 2), P, (2, 2), op.multiply_add_to(out, -5.0 / 7.0))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = cv.convolve_Gradients(phi, 0, psi, 2)
+    C.convolve_Gradients(P, (0,), Q, (2,), op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = cv.convolve_Gradient_and_Hessian(phi, 1, psi, (0, 2))
+    C.convolve_Gradient_and_Hessian(P, (1,), Q, (0, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = cv.multiply_field(phi, psi)
+    C.multiply_field(P, Q, op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    # operands handed over in real space are transformed first (convolution.hh:142-143)
+    P.FourierTransformBackward()
+    C.multiply_field(P, Q, op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < 10 * TOL
+
+
+# ------------------------------------------------------------------ whole pipeline vs oracle
+def check_pipeline(M, n, order, lattice="sc", real64=True, seed=21):
+    L = 100.0
+    Dp, vfac = 0.0257, 396.69
+    lunit, vunit = L, L / np.sqrt(1 / 51.0)
+    g, W, Wc, phi = noise_and_phi(n, L, seed)
+    amp = O.power_law_amplitude()
+    ref = O.run_pipeline(n, L, Wc, amp, order, Dp, vfac, lattice, lunit, vunit, real64, ids64=True)
+    cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad=lattice, Dplus0=Dp, vfac=vfac,
+                       lunit=lunit, vunit=vunit, real64=real64, ids64=True)
+    pl = M.LPTPipeline(cfg)
+    pl.set_noise_k(W)
+    pl.condition_noise()
+    parts = pl.run_device(O.radial_table(g, amp), particles=True)
+    # potentials
+    scale = np.abs(ref["pots"]["phi"]).max()
+    assert relerr(pl.phi.get_kspace(), ref["pots"]["phi"]) < TOL
+    if order > 1:
+        assert relerr(pl.phi2.get_kspace(), ref["pots"]["phi2"]) < TOL
+    if order > 2:
+        assert relerr(pl.phi3.get_kspace(), ref["pots"]["phi3"]) < 10 * TOL
+        for d in range(3):
+            assert relerr(pl.A3[d].get_kspace(), ref["pots"]["A3"][d]) < 10 * TOL
+    host = parts.download()
+    assert np.array_equal(host["ids"], ref["ids"])
+    maxpsi = max(np.abs(ref["fields"]["d" + c]).max() for c in "xyz")
+    maxv = max(np.abs(ref["fields"]["v" + c]).max() for c in "xyz")
+    if real64:
+        # north_star: max|err| <= 1e-9 * max|Psi|; we hold 1e-11
+        assert np.abs(host["pos"] - ref["pos"]).max() < 1e-11 * maxpsi
+        assert np.abs(host["vel"] - ref["vel"]).max() < 1e-11 * maxv
+    else:
+        assert host["pos"].dtype == np.float32
+        assert (host["pos"] == ref["pos"]).mean() > 0.999
+        assert np.allclose(host["pos"], ref["pos"], rtol=1e-6, atol=1e-6 * maxpsi)
+        assert np.allclose(host["vel"], ref["vel"], rtol=1e-6, atol=1e-6 * maxv)
+    return pl
+
+
+def check_lattice_positions_bitexact(M, n, lattice):
+    """zero displacement: positions are the bare lattice coordinates, bit-for-bit"""
+    L = 100.0
+    g = O.GridSpec(n, L)
+    F = M.Grid_FFT((n,) * 3, (L,) * 3)
+    lt = O.LATTICE_TYPES[lattice]
+    for lattice_index in (0, 1):
+        P = M.Particles(lattice, lattice_index, True, True, False, lattice_index, F)
+        for d in range(3):
+            F.set_real(np.zeros((n,) * 3))
+            P.set_positions(d, 7.3, F)
+        host = P.download(vel=False)
+        for d in range(3):
+            ref = O.set_positions(g, np.zeros((n,) * 3), d, lt, lattice_index, 7.3, True)
+            # shift_field of an all-zero field stays all-zero -> exact lattice
+            assert np.array_equal(host["pos"][:, d], ref)
+        assert np.array_equal(host["ids"], O.particle_ids(n, lt, lattice_index, True))
+
+
+# ------------------------------------------------------------------ goldens through the CUDA path
+def _golden_pipeline(M, order, lattice, fmt):
+    g, phi_s, vfac = G.bootstrap()
+    lunit, vunit, r64 = G.units(fmt)
+    cfg = M.lpt_config(GridRes=G.N, BoxLength=G.L, LPTorder=order, ParticleLoad=lattice, Dplus0=-1.0, vfac=vfac,
+                       lunit=lunit, vunit=vunit, real64=r64, ids64=False)
+    pl = M.LPTPipeline(cfg)
+    pl.phi.set_kspace(phi_s)
+    pl.compute_sources()
+    return pl
+
+
+def close(a, b):
+    return np.allclose(a, b, rtol=G.RTOL, atol=G.ATOL)
+
+
+def check_golden_generic(M, name, order):
+    gold = G.load(name)
+    pl = _golden_pipeline(M, order, "sc", "generic")
+    for d, c in enumerate("xyz"):
+        assert close(pl.displacement_field(d).get_real(), gold["DM_d" + c]), c
+    for d, c in enumerate("xyz"):
+        assert close(pl.velocity_field(d).get_real(), gold["DM_v" + c]), c
+    assert close(pl.density_field().get_real(), gold["DM_delta"])
+
+
+def check_golden_gadget(M):
+    gold = G.load("test_2lpt_baryons_vrel_gadget")
+    gold_dm = G.load("test_2lpt_sc_gadget")
+    pl = _golden_pipeline(M, 2, "sc", "gadget")
+    p = pl.fill_particles(0).download()
+    assert close(p["pos"], gold_dm["PartType1__Coordinates"]) and close(p["vel"], gold_dm["PartType1__Velocities"])
+    assert close(p["pos"], gold["PartType1__Coordinates"]) and close(p["vel"], gold["PartType1__Velocities"])
+    assert np.array_equal(p["ids"], gold_dm["PartType1__ParticleIDs"])
+    # baryons: secondary lattice (index 1), IDs offset by N^3, uniform masses through set_masses
+    pl.particles = None
+    pl.make_particles(lattice_index=1, with_masses=True, id_offset=1)
+    pb = pl.fill_particles(1)
+    munit = 27.7519737 * G.L ** 3
+    rho = M.Grid_FFT(pl.N, pl.Lbox)
+    rho.set_real(np.zeros((G.N,) * 3))
+    rho.affine(0.048891054 * munit, 0.048891054 * munit * 0.5)  # (1 + C*rho)*Omega*munit with rho == 0
+    pb.set_masses(1.0, rho)
+    b = pb.download()
+    assert close(b["pos"], gold["PartType0__Coordinates"]) and close(b["vel"], gold["PartType0__Velocities"])
+    assert np.array_equal(b["ids"], gold["PartType0__ParticleIDs"])
+    assert close(b["mass"], gold["PartType0__Masses"])
+
+
+def check_golden_swift(M):
+    gold = G.load("test_3lpt_bcc_swift")
+    pl = _golden_pipeline(M, 3, "bcc", "swift")
+    p = pl.fill_particles(0).download()
+    assert p["pos"].shape == (65536, 3)
+    assert close(p["pos"], gold["PartType1__Coordinates"])
+    assert close(p["vel"], gold["PartType1__Velocities"])

@@ -1,0 +1,68 @@
+"""CPU-only: the kernel sources, compiled for the thread emulator (tests/emu), against the oracle
+and the reference goldens at 32^3 (padded 48^3).  This validates index arithmetic, pad/unpad,
+Nyquist handling, operand factors and the host logic without a GPU; it is NOT a product path."""
+import pytest
+
+import emu_util
+import parity_cases as PC
+
+
+@pytest.fixture(scope="module")
+def M():
+    return emu_util.emu_backend()
+
+
+@pytest.mark.parametrize("n", [32, 48, 64, 96])
+def test_fft_roundtrip(M, n):
+    PC.check_fft(M, n)
+
+
+def test_fft_noncubic(M):
+    PC.check_fft(M, 32, 48, 64)
+
+
+def test_c2r_nonhermitian(M):
+    PC.check_c2r_nonhermitian(M, 32)
+
+
+def test_kspace_operators(M):
+    PC.check_kops(M, 32)
+
+
+@pytest.mark.parametrize("nyq0", [True, False])
+def test_convolver(M, nyq0):
+    PC.check_convolver(M, 32, nyq0)
+
+
+@pytest.mark.parametrize("order,lattice,real64", [(1, "sc", True), (2, "sc", False), (3, "bcc", True)])
+def test_pipeline_vs_oracle(M, order, lattice, real64):
+    PC.check_pipeline(M, 32, order, lattice, real64)
+
+
+@pytest.mark.parametrize("lattice", ["sc", "bcc", "fcc", "rsc"])
+def test_lattice_bitexact(M, lattice):
+    PC.check_lattice_positions_bitexact(M, 32, lattice)
+
+
+def test_golden_1lpt_generic(M):
+    PC.check_golden_generic(M, "test_1lpt_sc_generic", 1)
+
+
+def test_golden_2lpt_generic(M):
+    PC.check_golden_generic(M, "test_2lpt_baryons_generic", 2)
+
+
+def test_golden_gadget(M):
+    PC.check_golden_gadget(M)
+
+
+def test_golden_swift(M):
+    PC.check_golden_swift(M)
+
+
+def test_error_behaviour(M):
+    import monofonic_b200 as MM
+    with pytest.raises(MM.MfbError):
+        MM.Grid_FFT((33, 33, 33), (1.0,) * 3)           # no plan for this size
+    with pytest.raises(RuntimeError):
+        MM.LPTPipeline(MM.lpt_config(GridRes=33, LPTorder=2))  # Orszag needs an even grid (ic_generator.cc:118)

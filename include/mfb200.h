@@ -45,6 +45,14 @@ void* mfb_stream(void);              /* the cudaStream_t all work is issued on *
 long long mfb_kernel_launches(void); /* number of kernels launched so far (bench.py gpu_launches) */
 int mfb_supported_fft_size(int n);   /* 1 if an FFT plan exists for line length n */
 
+/* per-role device timing (CUDA events on the library stream around every kernel launch); the reference's
+   analogue are the "took : ...s" stage timers (src/ic_generator.cc:470,500,528,540,557) */
+int mfb_profile_enable(int on);
+int mfb_profile_reset(void);
+int mfb_profile_num_roles(void);
+const char* mfb_profile_role_name(int role);
+int mfb_profile_get(int role, double* ms, long long* count, double* algorithmic_bytes);
+
 /* ---- Grid_FFT ---------------------------------------------------------------------------- */
 /* Grid_FFT(N, L, allocate=true, initialspace) + allocate()        include/grid_fft.hh:77-83, src/grid_fft.cc:40-197 */
 int mfb_grid_create(mfb_grid** g, const int n[3], const double L[3], int space);

@@ -27,6 +27,11 @@ def _declare(lib):
         "mfb_stream": (vp, []),
         "mfb_kernel_launches": (C.c_longlong, []),
         "mfb_supported_fft_size": (i, [i]),
+        "mfb_profile_enable": (i, [i]),
+        "mfb_profile_reset": (i, []),
+        "mfb_profile_num_roles": (i, []),
+        "mfb_profile_role_name": (C.c_char_p, [i]),
+        "mfb_profile_get": (i, [i, dp, C.POINTER(C.c_longlong), dp]),
         "mfb_grid_create": (i, [vpp, ip, dp, i]),
         "mfb_grid_destroy": (i, [vp]),
         "mfb_grid_space": (i, [vp]),

@@ -67,10 +67,66 @@ void cuda_check(cudaError_t e, const char* what) {
 void require(bool c, const char* msg) {
     if (!c) throw std::runtime_error(msg);
 }
+#ifndef MFB_EMU
+static cudaEvent_t prof_event() {
+    if (!g_ctx.event_pool.empty()) { cudaEvent_t e = g_ctx.event_pool.back(); g_ctx.event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    return e;
+}
+#endif
+// every launch goes through RoleScope (begin event) and check_launch (end event)
+RoleScope::RoleScope(int role, double bytes) : prev_role(g_ctx.cur_role), prev_bytes(g_ctx.cur_bytes), armed(false) {
+    g_ctx.cur_role = role;
+    g_ctx.cur_bytes = bytes;
+#ifndef MFB_EMU
+    if (g_ctx.profiling) {
+        ProfEvent pe;
+        pe.a = prof_event(); pe.b = nullptr; pe.role = role; pe.bytes = bytes;
+        cudaEventRecord(pe.a, g_ctx.stream);
+        g_ctx.pending.push_back(pe);
+        armed = true;
+    }
+#endif
+}
+RoleScope::~RoleScope() {
+#ifndef MFB_EMU
+    if (armed) {
+        ProfEvent& pe = g_ctx.pending.back();
+        pe.b = prof_event();
+        cudaEventRecord(pe.b, g_ctx.stream);
+    }
+#endif
+    g_ctx.cur_role = prev_role;
+    g_ctx.cur_bytes = prev_bytes;
+}
+void prof_collect() {
+#ifndef MFB_EMU
+    if (g_ctx.pending.empty()) return;
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    for (auto& pe : g_ctx.pending) {
+        float ms = 0.f;
+        if (pe.b && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+            g_ctx.role_ms[pe.role] += ms;
+            g_ctx.role_bytes[pe.role] += pe.bytes;
+            g_ctx.role_count[pe.role] += 1;
+        }
+        g_ctx.event_pool.push_back(pe.a);
+        if (pe.b) g_ctx.event_pool.push_back(pe.b);
+    }
+    g_ctx.pending.clear();
+#endif
+}
 void check_launch(const char* what) {
     ++g_ctx.launches;
     cuda_check(cudaGetLastError(), what);
 }
+
+#define MFB_LAUNCH_ROLE(role, kernel, grid, block, ...)                           \
+    do {                                                                          \
+        RoleScope rs_(role, 0.0);                                                 \
+        MFB_LAUNCH(kernel, grid, block, 0, g_ctx.stream, __VA_ARGS__);            \
+    } while (0)
 
 void* dev_alloc(size_t bytes) {
     void* p = nullptr;
@@ -113,22 +169,26 @@ template <class K> void optin_smem(K kernel, size_t bytes, bool& done) {
 // ------------------------------------------------------------------------------------------
 // kernel launchers
 // ------------------------------------------------------------------------------------------
-template <class P> void launch_strided_t(const StridedArgs& a) {
+template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     static bool done = false;
     optin_smem(strided_pass_kernel<P>, P::SMEM_BYTES, done);
     const int tiles = (a.nz + P::T - 1) / P::T;
     const unsigned grid = unsigned(a.na) * unsigned(tiles);
     if (grid == 0) return;
     const double2* tw = twiddles(P::N);
+    // algorithmic bytes: every transformed line reads n_in and writes n_out complex (+ RMW read)
+    const double lines = double(a.na - (a.a_skip >= 0 ? 1 : 0)) * double(a.nz_fft);
+    const double bytes = lines * 16.0 * (double(a.n_in) + double(a.n_out) * (a.op == OP_ASSIGN ? 1.0 : 2.0));
+    RoleScope rs(role, bytes);
     MFB_LAUNCH(strided_pass_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, a, tw);
     check_launch("strided_pass_kernel");
 }
-void launch_strided(int n, const StridedArgs& a) {
+void launch_strided(int n, const StridedArgs& a, int role) {
     switch (n) {
 #define X(N_, TPL_, T_, ...)                              \
     case N_: {                                            \
         using P = Plan<N_, TPL_, T_, __VA_ARGS__>;        \
-        launch_strided_t<P>(a);                           \
+        launch_strided_t<P>(a, role);                     \
         break;                                            \
     }
         MFB_FOR_EACH_PLAN(X)
@@ -141,6 +201,7 @@ template <class P> void launch_z_t(int kind, double* data, ptrdiff_t pitch, long
     static bool done_c2r = false, done_r2c = false;
     const unsigned grid = unsigned((nrows + 2 * P::T - 1) / (2 * P::T));
     const double2* tw = twiddles(P::N);
+    RoleScope rs(kind == 0 ? ROLE_FFT_Z_C2R : ROLE_FFT_Z_R2C, double(nrows) * (16.0 * P::N + 16.0));
     if (kind == 0) {
         optin_smem(z_c2r_kernel<P>, P::SMEM_BYTES, done_c2r);
         MFB_LAUNCH(z_c2r_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, pitch, nrows, scale, tw);
@@ -172,6 +233,7 @@ void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t 
     optin_smem(z_conv_kernel<P>, P::SMEM_BYTES, done);
     const unsigned grid = unsigned((nrows + P::T - 1) / P::T);
     const double2* tw = twiddles(P::N);
+    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(nzin) * 16.0 * 3.0);
     MFB_LAUNCH(z_conv_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, nzin,
                scale, tw);
     check_launch("z_conv_kernel");
@@ -227,15 +289,15 @@ void grid_fft_forward(mfb_grid* g) {
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
     launch_z(g->n[2], 1, g->d, g->pitch, long(n0) * n1, norm);
-    launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 0));
-    launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 0));
+    launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 0), ROLE_FFT_Y);
+    launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 0), ROLE_FFT_X);
 }
 void grid_fft_backward(mfb_grid* g) {
     const double norm = 1.0 / std::sqrt(double(g->n[0]) * double(g->n[1]) * double(g->n[2]));
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
-    launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 1));
-    launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 1));
+    launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 1), ROLE_FFT_X);
+    launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 1), ROLE_FFT_Y);
     launch_z(g->n[2], 0, g->d, g->pitch, long(n0) * n1, norm);
 }
 void to_kspace(mfb_grid* g) {
@@ -259,13 +321,13 @@ static void grid_sums(mfb_grid* g, double out[2]) {
     const int nb = 148 * 4;
     double* part = partial_buffer(2 * nb + 2);
     if (g->space == MFB_RSPACE) {
-        MFB_LAUNCH(reduce_real_kernel, nb, RED_THREADS, 0, g_ctx.stream, g->d, long(g->n[0]) * g->n[1], g->n[2], g->pitch, part);
+        MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_real_kernel, nb, RED_THREADS, g->d, long(g->n[0]) * g->n[1], g->n[2], g->pitch, part);
     } else {
-        MFB_LAUNCH(reduce_cplx_kernel, nb, RED_THREADS, 0, g_ctx.stream, reinterpret_cast<const double2*>(g->d),
+        MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_cplx_kernel, nb, RED_THREADS, reinterpret_cast<const double2*>(g->d),
                    long(g->n[0]) * g->n[1] * g->nzc, part);
     }
     check_launch("reduce");
-    MFB_LAUNCH(reduce_final_kernel, 1, RED_THREADS, 0, g_ctx.stream, part, nb, 0, part + 2 * nb);
+    MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_final_kernel, 1, RED_THREADS, part, nb, 0, part + 2 * nb);
     check_launch("reduce_final");
     cuda_check(cudaMemcpyAsync(out, part + 2 * nb, 2 * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "reduce D2H");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
@@ -279,7 +341,7 @@ void grid_zero_dc(mfb_grid* g) {
         grid_sums(g, s);
         const double mean = s[0] / (double(g->n[0]) * g->n[1] * g->n[2]);
         const long nrows = long(g->n[0]) * g->n[1];
-        MFB_LAUNCH(subtract_real_kernel, stream_blocks(size_t(nrows) * g->n[2]), EW_THREADS, 0, g_ctx.stream, g->d, nrows, g->n[2],
+        MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, subtract_real_kernel, stream_blocks(size_t(nrows) * g->n[2]), EW_THREADS, g->d, nrows, g->n[2],
                    g->pitch, mean);
         check_launch("subtract_real");
     }
@@ -289,19 +351,19 @@ void grid_laplacian_pow(mfb_grid* g, int p, double s) {
     to_kspace(g);
     KGeom k = kgeom(g);
     double2* c = reinterpret_cast<double2*>(g->d);
-    MFB_LAUNCH(laplacian_pow_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, c, c, k, p, s);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, laplacian_pow_kernel, kgrid_blocks(k), EW_THREADS, c, c, k, p, s);
     check_launch("laplacian_pow");
 }
 
 void grid_scale(mfb_grid* g, double a) {
-    MFB_LAUNCH(scale_kernel, stream_blocks(g->ntot), EW_THREADS, 0, g_ctx.stream, g->d, g->ntot, a);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, scale_kernel, stream_blocks(g->ntot), EW_THREADS, g->d, g->ntot, a);
     check_launch("scale");
 }
 
 void grid_shift_field(mfb_grid* g, const double s[3], bool back) {
     to_kspace(g);
     KGeom k = kgeom(g);
-    MFB_LAUNCH(shift_phase_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(g->d), k, s[0], s[1], s[2]);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, shift_phase_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(g->d), k, s[0], s[1], s[2]);
     check_launch("shift_phase");
     if (back) to_rspace(g);
 }
@@ -334,13 +396,13 @@ static void conv_backward_operand(mfb_conv* c, const Operand& o, double2* W2) {
     a.f.imag = o.imag;
     for (int d = 0; d < 3; ++d) { a.f.n[d] = c->n[d]; a.f.kf[d] = 2.0 * M_PI / c->L[d]; }
     a.pos_axis = 0; a.a_axis = 1;
-    launch_strided(P0, a);
+    launch_strided(P0, a, ROLE_CONV_X_BWD);
     // pass 2: y axis, N1 -> P1
     StridedArgs b = plain_strided(c->W1, W2, nzin, 0, P0, nzin, P1, 1);
     b.in_as = ptrdiff_t(N1) * nzin;
     b.out_as = ptrdiff_t(P1) * nzin;
     b.n_in = N1;
-    launch_strided(P1, b);
+    launch_strided(P1, b, ROLE_CONV_Y_BWD);
 }
 
 void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
@@ -360,7 +422,7 @@ void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int o
     d.in_as = ptrdiff_t(P1) * nzin;
     d.out_as = ptrdiff_t(N1) * nzin;
     d.n_out = N1;
-    launch_strided(P1, d);
+    launch_strided(P1, d, ROLE_CONV_Y_FWD);
     // pass 5: x axis forward, P0 -> N0, unpad scale + Nyquist zero + output operator
     StridedArgs e = plain_strided(c->W1, reinterpret_cast<double2*>(out->d), 0, 0, N1, (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
     e.in_ps = ptrdiff_t(N1) * nzin; e.in_as = nzin;
@@ -371,7 +433,7 @@ void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int o
     e.op = op; e.alpha = alpha;
     e.a_skip = N1 / 2;
     e.zero_fill = 1;
-    launch_strided(P0, e);
+    launch_strided(P0, e, ROLE_CONV_X_FWD);
     ++c->nconv;
 }
 
@@ -397,7 +459,7 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
         conv2(c, H(phi, 1, 2), H(phi, 1, 2), phi2, OP_SUB, 0.0);
         if (lam) {
             KGeom k = kgeom(phi2);
-            MFB_LAUNCH(tides_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(phi2->d),
+            MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, tides_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(phi2->d),
                        reinterpret_cast<const double2*>(phi->d), k, lam[0], lam[1], lam[2]);
             check_launch("tides");
         }
@@ -486,10 +548,10 @@ static void particles_readout(mfb_particles* p, int kind, int lattice_index, int
         const int addl = (kind == 0) ? 1 : 0;
         const double mul = (kind == 2) ? pmean : 1.0;
         if (p->real64) {
-            MFB_LAUNCH(lattice_readout_kernel<double>, nb, EW_THREADS, 0, g_ctx.stream, (double*)dst, f->d, f->n[0], f->n[1],
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, lattice_readout_kernel<double>, nb, EW_THREADS, (double*)dst, f->d, f->n[0], f->n[1],
                        f->n[2], f->pitch, 0, slot0, stride, comp, addl, idim, shift, unit, mul);
         } else {
-            MFB_LAUNCH(lattice_readout_kernel<float>, nb, EW_THREADS, 0, g_ctx.stream, (float*)dst, f->d, f->n[0], f->n[1],
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, lattice_readout_kernel<float>, nb, EW_THREADS, (float*)dst, f->d, f->n[0], f->n[1],
                        f->n[2], f->pitch, 0, slot0, stride, comp, addl, idim, shift, unit, mul);
         }
         check_launch("lattice_readout");
@@ -547,6 +609,33 @@ int mfb_synchronize(void) {
 void* mfb_stream(void) { return (void*)g_ctx.stream; }
 long long mfb_kernel_launches(void) { return g_ctx.launches; }
 int mfb_supported_fft_size(int n) { return supported_size(n) ? 1 : 0; }
+
+// ---------------------------------------------------------------- profiling
+int mfb_profile_enable(int on) {
+    MFB_TRY
+    prof_collect();
+    g_ctx.profiling = on != 0;
+    MFB_CATCH
+}
+int mfb_profile_reset(void) {
+    MFB_TRY
+    prof_collect();
+    for (int r = 0; r < ROLE_COUNT; ++r) { g_ctx.role_ms[r] = 0; g_ctx.role_bytes[r] = 0; g_ctx.role_count[r] = 0; }
+    MFB_CATCH
+}
+int mfb_profile_num_roles(void) { return ROLE_COUNT; }
+const char* mfb_profile_role_name(int role) {
+    static const char* names[ROLE_COUNT] = {"conv_x_bwd", "conv_y_bwd", "conv_z_fused", "conv_y_fwd", "conv_x_fwd", "fft_x",
+                                            "fft_y", "fft_z_r2c", "fft_z_c2r", "elementwise", "reduce", "particles"};
+    return (role >= 0 && role < ROLE_COUNT) ? names[role] : "?";
+}
+int mfb_profile_get(int role, double* ms, long long* count, double* bytes) {
+    MFB_TRY
+    require(role >= 0 && role < ROLE_COUNT, "bad role");
+    prof_collect();
+    *ms = g_ctx.role_ms[role]; *count = g_ctx.role_count[role]; *bytes = g_ctx.role_bytes[role];
+    MFB_CATCH
+}
 
 // ---------------------------------------------------------------- grids
 int mfb_grid_create(mfb_grid** out, const int n[3], const double L[3], int space) {
@@ -622,13 +711,13 @@ int mfb_grid_scale(mfb_grid* g, double a) {
 int mfb_grid_axpy(mfb_grid* y, double a, const mfb_grid* x, double b) {
     MFB_TRY
     require(y->ntot == x->ntot && y->space == x->space, "axpy: grids must have equal size and space");
-    MFB_LAUNCH(axpy_kernel, stream_blocks(y->ntot), EW_THREADS, 0, g_ctx.stream, y->d, x->d, y->ntot, a, b);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, axpy_kernel, stream_blocks(y->ntot), EW_THREADS, y->d, x->d, y->ntot, a, b);
     check_launch("axpy");
     MFB_CATCH
 }
 int mfb_grid_affine(mfb_grid* g, double a, double b) {
     MFB_TRY
-    MFB_LAUNCH(affine_kernel, stream_blocks(g->ntot), EW_THREADS, 0, g_ctx.stream, g->d, g->ntot, a, b);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, affine_kernel, stream_blocks(g->ntot), EW_THREADS, g->d, g->ntot, a, b);
     check_launch("affine");
     MFB_CATCH
 }
@@ -682,9 +771,9 @@ int mfb_grid_max_neighbour_diff(mfb_grid* g, double* out) {
     require(g->space == MFB_RSPACE, "max_neighbour_diff: grid must be in real space");
     const int nb = 148 * 4;
     double* part = partial_buffer(2 * nb + 2);
-    MFB_LAUNCH(max_neighbour_diff_kernel, nb, RED_THREADS, 0, g_ctx.stream, g->d, g->n[0], g->n[1], g->n[2], g->pitch, part);
+    MFB_LAUNCH_ROLE(ROLE_REDUCE, max_neighbour_diff_kernel, nb, RED_THREADS, g->d, g->n[0], g->n[1], g->n[2], g->pitch, part);
     check_launch("max_neighbour_diff");
-    MFB_LAUNCH(reduce_final_kernel, 1, RED_THREADS, 0, g_ctx.stream, part, nb, 1, part + 2 * nb);
+    MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_final_kernel, 1, RED_THREADS, part, nb, 1, part + 2 * nb);
     check_launch("reduce_final");
     cuda_check(cudaMemcpyAsync(out, part + 2 * nb, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "D2H");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
@@ -698,7 +787,7 @@ int mfb_fourier_resample(mfb_grid* src, mfb_grid* dst) {
         cuda_check(cudaMemcpyAsync(dst->d, src->d, src->ntot * sizeof(double), cudaMemcpyDeviceToDevice, g_ctx.stream), "copy");
     } else {
         KGeom kd = kgeom(dst), ks = kgeom(src);
-        MFB_LAUNCH(resample_kernel, kgrid_blocks(kd), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(dst->d), kd,
+        MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, resample_kernel, kgrid_blocks(kd), EW_THREADS, reinterpret_cast<double2*>(dst->d), kd,
                    reinterpret_cast<const double2*>(src->d), ks);
         check_launch("resample");
     }
@@ -711,7 +800,7 @@ int mfb_noise_condition(mfb_grid* w, double volfac, int fix, int invert, int rem
     require(w->space == MFB_KSPACE, "noise_condition: grid must be in k-space");
     KGeom k = kgeom(w);
     const double kny = k.kf0 * w->n[0] / 2;
-    MFB_LAUNCH(noise_condition_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(w->d), k,
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, noise_condition_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(w->d), k,
                (invert ? -1.0 : 1.0) / volfac, fix, remove_corners, kny);
     check_launch("noise_condition");
     MFB_CATCH
@@ -737,7 +826,7 @@ int mfb_apply_radial_table(mfb_grid* out, const mfb_grid* in, const double* tabl
     const double* dt = upload_table(table, ntable, size_t(3) * h * h + 1, 0);
     out->space = MFB_KSPACE;
     KGeom k = kgeom(in);
-    MFB_LAUNCH(radial_table_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(out->d),
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, radial_table_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(out->d),
                reinterpret_cast<const double2*>(in->d), dt, k, inv_k2 ? 1 : 0);
     check_launch("radial_table");
     MFB_CATCH
@@ -746,7 +835,7 @@ int mfb_add_tides(mfb_grid* phi2, const mfb_grid* phi, const double lam[3]) {
     MFB_TRY
     require(phi2->space == MFB_KSPACE && phi->space == MFB_KSPACE, "add_tides: k-space grids required");
     KGeom k = kgeom(phi2);
-    MFB_LAUNCH(tides_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(phi2->d),
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, tides_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(phi2->d),
                reinterpret_cast<const double2*>(phi->d), k, lam[0], lam[1], lam[2]);
     check_launch("tides");
     MFB_CATCH
@@ -780,7 +869,7 @@ int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* 
     }
     out->space = MFB_KSPACE;
     KGeom k = kgeom(phi);
-    MFB_LAUNCH(assemble_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(out->d), a, k);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, assemble_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(out->d), a, k);
     check_launch("assemble");
     MFB_CATCH
 }
@@ -789,7 +878,7 @@ int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi) {
     require(phi->space == MFB_KSPACE, "density_from_phi: phi must be in k-space");
     out->space = MFB_KSPACE;
     KGeom k = kgeom(phi);
-    MFB_LAUNCH(laplacian_pow_kernel, kgrid_blocks(k), EW_THREADS, 0, g_ctx.stream, reinterpret_cast<double2*>(out->d),
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, laplacian_pow_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(out->d),
                reinterpret_cast<const double2*>(phi->d), k, 1, 1.0);
     check_launch("density");
     MFB_CATCH
@@ -928,9 +1017,9 @@ int mfb_particles_set_ids(mfb_particles* p, unsigned long long id_offset_species
     const unsigned long long off = id_offset_species * (unsigned long long)ov * (unsigned long long)ncell;
     const unsigned nb = stream_blocks(p->np);
     if (p->ids64) {
-        MFB_LAUNCH(particle_ids_kernel<unsigned long long>, nb, EW_THREADS, 0, g_ctx.stream, (unsigned long long*)p->ids, ncell, ov, off, 0L);
+        MFB_LAUNCH_ROLE(ROLE_PARTICLES, particle_ids_kernel<unsigned long long>, nb, EW_THREADS, (unsigned long long*)p->ids, ncell, ov, off, 0L);
     } else {
-        MFB_LAUNCH(particle_ids_kernel<unsigned int>, nb, EW_THREADS, 0, g_ctx.stream, (unsigned int*)p->ids, ncell, ov, off, 0L);
+        MFB_LAUNCH_ROLE(ROLE_PARTICLES, particle_ids_kernel<unsigned int>, nb, EW_THREADS, (unsigned int*)p->ids, ncell, ov, off, 0L);
     }
     check_launch("particle_ids");
     MFB_CATCH

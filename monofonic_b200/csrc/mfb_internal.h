@@ -2,6 +2,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <vector>
 
 #include "mfb_platform.h"
 
@@ -32,6 +33,13 @@ struct mfb_particles {
 };
 
 namespace mfb {
+// profiling roles: one per kernel use in the pipeline (bench.py reports time and algorithmic bytes per role)
+enum Role {
+    ROLE_CONV_X_BWD = 0, ROLE_CONV_Y_BWD, ROLE_CONV_Z, ROLE_CONV_Y_FWD, ROLE_CONV_X_FWD,
+    ROLE_FFT_X, ROLE_FFT_Y, ROLE_FFT_Z_R2C, ROLE_FFT_Z_C2R, ROLE_ELEMENTWISE, ROLE_REDUCE, ROLE_PARTICLES,
+    ROLE_COUNT
+};
+struct ProfEvent { cudaEvent_t a, b; int role; double bytes; };
 struct Context {
     bool initialised = false;
     int device = -1;
@@ -42,6 +50,21 @@ struct Context {
     double* table[2] = {nullptr, nullptr};  // radial tables (amplitude, vbc)
     size_t table_cap[2] = {0, 0};
     long long launches = 0;
+    // optional per-role device timing (cudaEvents on `stream` around every launch)
+    bool profiling = false;
+    int cur_role = ROLE_ELEMENTWISE;
+    double cur_bytes = 0.0;
+    std::vector<ProfEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    double role_ms[ROLE_COUNT] = {0};
+    double role_bytes[ROLE_COUNT] = {0};
+    long long role_count[ROLE_COUNT] = {0};
+};
+// RAII: tags the launches issued in its scope with a role and their algorithmic HBM bytes
+struct RoleScope {
+    int prev_role; double prev_bytes; bool armed;
+    RoleScope(int role, double bytes);
+    ~RoleScope();
 };
 extern Context g_ctx;
 void set_error(const std::string& s);

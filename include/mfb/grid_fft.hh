@@ -1,0 +1,224 @@
+// include/mfb/grid_fft.hh - GPU-backed drop-in for the reference's Grid_FFT<real_t>
+// (include/grid_fft.hh:40-914, src/grid_fft.cc:40-492) on top of the C ABI (include/mfb200.h).
+//
+// Same public data members and member functions as the reference class, so that the RNG, transfer and
+// output plugins - which touch a grid only through n_, ntot_, sizes_, local_*_, data_, relem/kelem,
+// size/rsize/global_size, zero/reset/allocate, FourierTransform*, FourierInterpolateCopyTo, mean/std -
+// compile against it untouched.  The numerics run on the device; `data_` is a host mirror kept coherent
+// lazily: host accessors pull the device copy when it is newer and mark the host copy dirty (non-const
+// access), device operations push a dirty host copy first.
+//
+// Differences to the reference, all outside the plugin contract:
+//  * the arbitrary-lambda functor family (apply_function_k/_r/_k_dep/_r_dep, assign_function_of_grids_*)
+//    runs on the HOST mirror (it takes a host lambda); the pipeline itself uses the named device operators
+//    of mfb200.h instead (mfb_noise_condition, mfb_apply_radial_table, mfb_lpt_assemble, ...).
+//  * bdistributed == false layout ([kx][ky][kz]); the multi-GPU slab layer is separate.
+#pragma once
+#include <array>
+#include <cassert>
+#include <cmath>
+#include <complex>
+#include <cstddef>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#include "../mfb200.h"
+
+#ifndef MFB_HAVE_REFERENCE_GENERAL_HH
+using real_t = double;                   // CODE_PRECISION=DOUBLE (include/general.hh:50-53)
+using ccomplex_t = std::complex<double>;
+#endif
+
+enum space_t { kspace_id, rspace_id };  // include/grid_fft.hh:29  (kspace_id == MFB_KSPACE == 0)
+
+namespace mfb_detail {
+inline void check(int rc) {
+    if (rc != 0) throw std::runtime_error(mfb_last_error());
+}
+}  // namespace mfb_detail
+
+template <typename data_t_, bool bdistributed = false>
+class Grid_FFT {
+    static_assert(std::is_same<data_t_, double>::value, "the device path is FP64 real grids (PPT c2c: DESIGN.md section 8)");
+    static_assert(!bdistributed, "non-distributed host view; multi-GPU slabs are handled below the ABI");
+
+public:
+    using data_t = data_t_;
+    static constexpr bool is_distributed_trait{bdistributed};
+
+    std::array<size_t, 3> n_, nhalf_;
+    std::array<size_t, 4> sizes_;
+    size_t npr_, npc_;
+    size_t ntot_;
+    std::array<real_t, 3> length_, kfac_, kny_, dx_;
+    space_t space_;
+    data_t* data_;        // host mirror
+    ccomplex_t* cdata_;
+    real_t fft_norm_fac_;
+    bool ballocated_;
+    ptrdiff_t local_0_start_, local_1_start_;
+    ptrdiff_t local_0_size_, local_1_size_;
+
+    Grid_FFT(const std::array<size_t, 3>& N, const std::array<real_t, 3>& L, bool allocate = true,
+             space_t initialspace = rspace_id)
+        : n_(N), length_(L), space_(initialspace), data_(nullptr), cdata_(nullptr), ballocated_(false), h_(nullptr),
+          host_dirty_(false), dev_newer_(false) {
+        if (allocate) this->allocate();
+    }
+    Grid_FFT(const Grid_FFT&) = delete;
+    Grid_FFT& operator=(const Grid_FFT&) = delete;
+    ~Grid_FFT() { reset(); }
+
+    void reset() {
+        if (h_) { mfb_grid_destroy(h_); h_ = nullptr; }
+        if (data_) { std::free(data_); data_ = nullptr; cdata_ = nullptr; }
+        ballocated_ = false;
+    }
+
+    void allocate() {  // src/grid_fft.cc:40-112 (non-distributed branch)
+        if (ballocated_) return;
+        int n[3] = {int(n_[0]), int(n_[1]), int(n_[2])};
+        double L[3] = {length_[0], length_[1], length_[2]};
+        mfb_detail::check(mfb_grid_create(&h_, n, L, space_ == kspace_id ? MFB_KSPACE : MFB_RSPACE));
+        ntot_ = (n_[2] + 2) * n_[1] * n_[0];
+        data_ = static_cast<data_t*>(std::calloc(ntot_, sizeof(data_t)));
+        if (!data_) throw std::runtime_error("Grid_FFT: host mirror allocation failed");
+        cdata_ = reinterpret_cast<ccomplex_t*>(data_);
+        fft_norm_fac_ = 1.0 / std::sqrt(real_t(n_[0]) * real_t(n_[1]) * real_t(n_[2]));
+        npr_ = n_[2] + 2;
+        npc_ = n_[2] / 2 + 1;
+        for (int i = 0; i < 3; ++i) {
+            nhalf_[i] = n_[i] / 2;
+            kfac_[i] = 2.0 * M_PI / length_[i];
+            kny_[i] = kfac_[i] * n_[i] / 2;
+            dx_[i] = length_[i] / n_[i];
+        }
+        local_0_size_ = n_[0]; local_1_size_ = n_[1];
+        local_0_start_ = 0; local_1_start_ = 0;
+        set_sizes();
+        ballocated_ = true;
+        host_dirty_ = true;  // calloc'ed zeros are the truth until a device op runs
+        dev_newer_ = false;
+    }
+
+    // ---- geometry (include/grid_fft.hh:104-138, 213-318)
+    const Grid_FFT* get_grid(size_t) const { return this; }
+    bool is_distributed() const noexcept { return bdistributed; }
+    bool is_allocated() const noexcept { return ballocated_; }
+    size_t memsize() const noexcept { return ntot_; }
+    size_t size(size_t i) const noexcept { return sizes_[i]; }
+    size_t local_size() const noexcept { return local_0_size_ * n_[1] * n_[2]; }
+    size_t global_size() const noexcept { return n_[0] * n_[1] * n_[2]; }
+    size_t global_size(size_t i) const noexcept { return n_[i]; }
+    size_t rsize(size_t i) const noexcept { return (i == 0) ? local_0_size_ : n_[i]; }
+    size_t get_idx(size_t i, size_t j, size_t k) const noexcept { return (i * sizes_[1] + j) * sizes_[3] + k; }
+    size_t get_cell_idx_1d(size_t i, size_t j, size_t k) const noexcept { return ((i + local_0_start_) * n_[1] + j) * n_[2] + k; }
+    real_t get_dx(int idim) const noexcept { return dx_[idim]; }
+    const std::array<real_t, 3>& get_dx() const noexcept { return dx_; }
+    bool is_nyquist_mode(size_t i, size_t j, size_t k) const { return i == n_[0] / 2 || j == n_[1] / 2 || k == n_[2] / 2; }
+    template <typename ft> std::array<ft, 3> get_k(size_t i, size_t j, size_t k) const noexcept {
+        return {ft((real_t(i) - real_t(i > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(j) - real_t(j > nhalf_[1]) * n_[1]) * kfac_[1]),
+                ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2])};
+    }
+    std::array<size_t, 3> get_k3(size_t i, size_t j, size_t k) const noexcept { return {i, j, k}; }
+    ccomplex_t gradient(int idim, std::array<size_t, 3> ijk) const {
+        real_t rgrad = (ijk[idim] != nhalf_[idim]) ? (real_t(ijk[idim]) - real_t(ijk[idim] > nhalf_[idim]) * n_[idim]) * kfac_[idim] : 0.0;
+        return ccomplex_t(0.0, rgrad);
+    }
+
+    // ---- host element access: lazily synchronised mirror (include/grid_fft.hh:179-211)
+    data_t& operator[](size_t i) { to_host(true); return data_[i]; }
+    data_t& relem(size_t i, size_t j, size_t k) { to_host(true); return data_[get_idx(i, j, k)]; }
+    const data_t& relem(size_t i, size_t j, size_t k) const { to_host(false); return data_[get_idx(i, j, k)]; }
+    ccomplex_t& kelem(size_t i, size_t j, size_t k) { to_host(true); return cdata_[get_idx(i, j, k)]; }
+    const ccomplex_t& kelem(size_t i, size_t j, size_t k) const { to_host(false); return cdata_[get_idx(i, j, k)]; }
+    ccomplex_t& kelem(size_t idx) { to_host(true); return cdata_[idx]; }
+    const ccomplex_t& kelem(size_t idx) const { to_host(false); return cdata_[idx]; }
+    data_t& relem(size_t idx) { to_host(true); return data_[idx]; }
+    const data_t& relem(size_t idx) const { to_host(false); return data_[idx]; }
+    //! plugins that hand data_ to C code (random_panphasia.cc:177) call this around the raw access
+    data_t* host_data(bool will_write = true) { to_host(will_write); return data_; }
+
+    // ---- device operations
+    mfb_grid* device_handle() { to_device(); dev_newer_ = true; return h_; }
+    void FourierTransformForward(bool do_transform = true) {
+        if (space_ != kspace_id) {
+            if (do_transform) { to_device(); mfb_detail::check(mfb_fft_forward(h_, 1)); dev_newer_ = true; }
+            else mfb_detail::check(mfb_fft_forward(h_, 0));
+            space_ = kspace_id;
+            set_sizes();
+        }
+    }
+    void FourierTransformBackward(bool do_transform = true) {
+        if (space_ != rspace_id) {
+            if (do_transform) { to_device(); mfb_detail::check(mfb_fft_backward(h_, 1)); dev_newer_ = true; }
+            else mfb_detail::check(mfb_fft_backward(h_, 0));
+            space_ = rspace_id;
+            set_sizes();
+        }
+    }
+    void FourierInterpolateCopyTo(Grid_FFT& grid_to) {
+        to_device();
+        grid_to.to_device();
+        mfb_detail::check(mfb_fourier_resample(h_, grid_to.h_));
+        space_ = kspace_id; set_sizes(); dev_newer_ = true;
+        grid_to.space_ = kspace_id; grid_to.set_sizes(); grid_to.dev_newer_ = true;
+    }
+    void zero() noexcept { mfb_grid_zero(h_); host_dirty_ = false; dev_newer_ = true; }
+    void copy_from(const Grid_FFT& g) {
+        const_cast<Grid_FFT&>(g).to_device();
+        mfb_detail::check(mfb_grid_copy(h_, g.h_));
+        space_ = g.space_; set_sizes(); host_dirty_ = false; dev_newer_ = true;
+    }
+    Grid_FFT& operator*=(data_t x) { dev_op(mfb_grid_scale(prep(), x)); return *this; }
+    Grid_FFT& operator/=(data_t x) { dev_op(mfb_grid_scale(prep(), 1.0 / x)); return *this; }
+    Grid_FFT& apply_InverseLaplacian() { dev_op(mfb_grid_inverse_laplacian(prep())); after_k(); return *this; }
+    Grid_FFT& apply_Laplacian() { dev_op(mfb_grid_laplacian(prep(), 0)); after_k(); return *this; }
+    Grid_FFT& apply_negative_Laplacian() { dev_op(mfb_grid_laplacian(prep(), 1)); after_k(); return *this; }
+    void zero_DC_mode() { dev_op(mfb_grid_zero_dc(prep())); }
+    template <class vec3> void shift_field(const vec3& s, bool transform_back = true) {
+        double ss[3] = {double(s[0]), double(s[1]), double(s[2])};
+        dev_op(mfb_grid_shift_field(prep(), ss, transform_back ? 1 : 0));
+        space_ = transform_back ? rspace_id : kspace_id;
+        set_sizes();
+    }
+    real_t mean() const { double v; auto* s = const_cast<Grid_FFT*>(this); mfb_detail::check(mfb_grid_mean(s->prep(), &v)); return v; }
+    real_t std() const { double v; auto* s = const_cast<Grid_FFT*>(this); mfb_detail::check(mfb_grid_std(s->prep(), &v)); return v; }
+    real_t compute_2norm() const { double v; auto* s = const_cast<Grid_FFT*>(this); mfb_detail::check(mfb_grid_2norm(s->prep(), &v)); return v; }
+
+    // ---- host-lambda functor family (runs on the mirror; include/grid_fft.hh:451-483, 698-808)
+    template <typename F> void apply_function_k(const F& f) {
+        to_host(true);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
+            auto& e = cdata_[get_idx(i, j, k)]; e = f(e);
+        }
+    }
+    template <typename F> void apply_function_r(const F& f) {
+        to_host(true);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
+            auto& e = data_[get_idx(i, j, k)]; e = f(e);
+        }
+    }
+
+private:
+    mfb_grid* h_;
+    mutable bool host_dirty_, dev_newer_;
+    void set_sizes() {  // src/grid_fft.cc:98-111, 230-233, 262-265
+        if (space_ == rspace_id) { sizes_ = {n_[0], n_[1], n_[2], npr_}; }
+        else { sizes_ = {n_[1], n_[0], npc_, npc_}; }
+    }
+    void to_host(bool will_write) const {
+        if (dev_newer_) { mfb_detail::check(mfb_grid_download(h_, data_)); dev_newer_ = false; }
+        if (will_write) host_dirty_ = true;
+    }
+    void to_device() {
+        if (host_dirty_) { mfb_detail::check(mfb_grid_upload(h_, data_)); host_dirty_ = false; }
+    }
+    mfb_grid* prep() { to_device(); return h_; }
+    void dev_op(int rc) { mfb_detail::check(rc); dev_newer_ = true; }
+    void after_k() { space_ = kspace_id; set_sizes(); }
+    template <typename, typename> friend class BaseConvolver;
+    template <typename> friend class OrszagConvolver;
+    template <typename> friend class mfb_lattice_access;
+};

@@ -1,0 +1,88 @@
+// include/mfb/particle_generator.hh - particle::container + particle::lattice_generator (Bravais branch)
+// (include/particle_container.hh:30-189, include/particle_generator.hh:129-170, 292-350, 422-467, 520-562).
+// The AoS arrays are filled on the device and copied once into the std::vectors the output plugins read
+// (get_particles()), instead of a serial host triple loop per component.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "grid_fft.hh"
+
+namespace particle {
+enum lattice { lattice_masked = -2, lattice_glass = -1, lattice_sc = 0, lattice_bcc = 1, lattice_fcc = 2, lattice_rsc = 3 };
+
+class container {
+public:
+    std::vector<float> positions32_, velocities32_, mass32_;
+    std::vector<double> positions64_, velocities64_, mass64_;
+    std::vector<uint32_t> ids32_;
+    std::vector<uint64_t> ids64_;
+    bool bhas_individual_masses_ = false;
+    container() = default;
+    container(const container&) = delete;
+    void allocate(size_t nump, bool b64reals, bool b64ids, bool bindividualmasses) {
+        bhas_individual_masses_ = bindividualmasses;
+        if (b64reals) { positions64_.resize(3 * nump); velocities64_.resize(3 * nump); if (bindividualmasses) mass64_.resize(nump); }
+        else { positions32_.resize(3 * nump); velocities32_.resize(3 * nump); if (bindividualmasses) mass32_.resize(nump); }
+        if (b64ids) ids64_.resize(nump); else ids32_.resize(nump);
+    }
+    const void* get_pos32_ptr() const { return positions32_.data(); }
+    const void* get_pos64_ptr() const { return positions64_.data(); }
+    const void* get_vel32_ptr() const { return velocities32_.data(); }
+    const void* get_vel64_ptr() const { return velocities64_.data(); }
+    const void* get_ids32_ptr() const { return ids32_.data(); }
+    const void* get_ids64_ptr() const { return ids64_.data(); }
+    const void* get_mass32_ptr() const { return mass32_.data(); }
+    const void* get_mass64_ptr() const { return mass64_.data(); }
+    size_t get_local_num_particles() const { return ids32_.empty() ? ids64_.size() : ids32_.size(); }
+    size_t get_global_num_particles() const { return get_local_num_particles(); }
+};
+
+template <typename field_t>
+class lattice_generator {
+    mfb_particles* p_ = nullptr;
+    container particles_;
+    bool b64reals_, b64ids_, bmass_, downloaded_ = false;
+    size_t global_num_particles_ = 0;
+
+public:
+    template <class config_t>
+    lattice_generator(lattice lattice_type, int /*lattice_index*/, const bool b64reals, const bool b64ids, const bool bwithmasses,
+                      size_t IDoffset, const field_t& field, config_t&)
+        : b64reals_(b64reals), b64ids_(b64ids), bmass_(bwithmasses) {
+        if (lattice_type < 0) throw std::runtime_error("glass / masked particle loads are not on the device path (DESIGN.md section 8)");
+        int n[3] = {int(field.n_[0]), int(field.n_[1]), int(field.n_[2])};
+        mfb_detail::check(mfb_particles_create(&p_, n, int(lattice_type), b64reals, b64ids, bwithmasses));
+        mfb_detail::check(mfb_particles_set_ids(p_, (unsigned long long)IDoffset));
+        global_num_particles_ = mfb_particles_count(p_);
+    }
+    ~lattice_generator() { if (p_) mfb_particles_destroy(p_); }
+    template <class config_t>
+    void set_masses(const lattice, int lattice_index, const real_t munit, const bool, field_t& field, config_t&) {
+        mfb_detail::check(mfb_particles_set_masses(p_, lattice_index, munit, field.device_handle()));
+        downloaded_ = false;
+    }
+    template <class config_t>
+    void set_positions(const lattice, int lattice_index, int idim, real_t lunit, const bool, field_t& field, config_t&) {
+        mfb_detail::check(mfb_particles_set_positions(p_, lattice_index, idim, lunit, field.device_handle()));
+        downloaded_ = false;
+    }
+    template <class config_t>
+    void set_velocities(lattice, int lattice_index, int idim, const bool, field_t& field, config_t&) {
+        mfb_detail::check(mfb_particles_set_velocities(p_, lattice_index, idim, field.device_handle()));
+        downloaded_ = false;
+    }
+    const container& get_particles() {
+        if (!downloaded_) {
+            particles_.allocate(global_num_particles_, b64reals_, b64ids_, bmass_);
+            void* pos = b64reals_ ? (void*)particles_.positions64_.data() : (void*)particles_.positions32_.data();
+            void* vel = b64reals_ ? (void*)particles_.velocities64_.data() : (void*)particles_.velocities32_.data();
+            void* ids = b64ids_ ? (void*)particles_.ids64_.data() : (void*)particles_.ids32_.data();
+            void* mas = bmass_ ? (b64reals_ ? (void*)particles_.mass64_.data() : (void*)particles_.mass32_.data()) : nullptr;
+            mfb_detail::check(mfb_particles_download(p_, pos, vel, ids, mas));
+            downloaded_ = true;
+        }
+        return particles_;
+    }
+};
+}  // namespace particle

@@ -1,0 +1,88 @@
+// C++ host-mirror test: a mock RNG "plugin" fills a Grid_FFT through kelem/relem exactly like the reference's
+// plugins do, then the reference-style call sequence of ic_generator::run (phi2 source) runs on the device.
+// Checks: relem/kelem coherence, FFT round trip, Parseval, convolve_Hessians bilinearity & symmetry, IDs.
+#include <cstdio>
+#include <random>
+
+#include "../../include/mfb/convolution.hh"
+#include "../../include/mfb/particle_generator.hh"
+
+struct mock_config {};
+
+// mirrors RNG_plugin::Fill_Grid(Grid_FFT<real_t>&) (include/random_plugin.hh:26-38)
+static void Fill_Grid(Grid_FFT<real_t>& g, unsigned seed) {
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd;
+    g.zero();
+    g.FourierTransformBackward(false);
+    for (size_t i = 0; i < g.size(0); ++i)
+        for (size_t j = 0; j < g.size(1); ++j)
+            for (size_t k = 0; k < g.size(2); ++k) g.relem(i, j, k) = nd(rng);
+}
+
+#define CHECK(c)                                                      \
+    do {                                                              \
+        if (!(c)) { std::printf("FAILED: %s (line %d)\n", #c, __LINE__); return 1; } \
+    } while (0)
+
+int main() {
+    if (mfb_init(0) != 0) { std::printf("mfb_init: %s\n", mfb_last_error()); return 2; }
+    const size_t n = 32;
+    std::array<size_t, 3> N{n, n, n};
+    std::array<real_t, 3> L{100.0, 100.0, 100.0};
+    Grid_FFT<real_t> w(N, L), phi(N, L), phi2(N, L, true, kspace_id), tmp(N, L, true, kspace_id);
+    Fill_Grid(w, 42);
+    double s2 = 0;
+    for (size_t i = 0; i < w.ntot_; ++i) if (i % (n + 2) < n) s2 += w.data_[i] * w.data_[i];
+    const double x0 = w.relem(3, 4, 5);
+    w.FourierTransformForward();
+    CHECK(w.space_ == kspace_id && w.size(2) == n / 2 + 1 && w.size(3) == n / 2 + 1);
+    double p2 = 0;
+    for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k <= n / 2; ++k)
+        p2 += std::norm(w.kelem(i, j, k)) * ((k == 0 || k == n / 2) ? 1.0 : 2.0);
+    CHECK(std::fabs(p2 - s2) < 1e-11 * s2);  // Parseval with the symmetric normalisation
+    // phi = -w/k^2 on the host mirror with a lambda (reference style), Nyquist planes zeroed like NGenIC
+    phi.FourierTransformForward(false);
+    for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k <= n / 2; ++k) {
+        auto kk = phi.get_k<real_t>(i, j, k);
+        const double k2 = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2];
+        phi.kelem(i, j, k) = (k2 > 0 && !phi.is_nyquist_mode(i, j, k)) ? -w.kelem(i, j, k) / k2 : 0.0;
+    }
+    w.FourierTransformBackward();
+    CHECK(std::fabs(w.relem(3, 4, 5) - x0) < 1e-13);
+    // phi2 source exactly as written in src/ic_generator.cc:482-486
+    OrszagConvolver<real_t> Conv(N, L);
+    Conv.convolve_SumOfHessians(phi, {0, 0}, phi, {1, 1}, {2, 2}, op::assign_to(phi2));
+    Conv.convolve_Hessians(phi, {1, 1}, phi, {2, 2}, op::add_to(phi2));
+    Conv.convolve_Hessians(phi, {0, 1}, phi, {0, 1}, op::subtract_from(phi2));
+    Conv.convolve_Hessians(phi, {0, 2}, phi, {0, 2}, op::subtract_from(phi2));
+    Conv.convolve_Hessians(phi, {1, 2}, phi, {1, 2}, op::subtract_from(phi2));
+    phi2.apply_InverseLaplacian();
+    CHECK(phi2.kelem(0, 0, 0) == ccomplex_t(0.0, 0.0));
+    CHECK(phi2.kelem(n / 2, 3, 4) == ccomplex_t(0.0, 0.0));  // Nyquist planes are zero after a product
+    double nrm = 0;
+    for (size_t i = 0; i < phi2.ntot_ / 2; ++i) nrm += std::norm(phi2.kelem(i));
+    CHECK(nrm > 0);
+    // symmetry of the product: conv(a,b) - conv(b,a) == 0
+    Conv.convolve_Hessians(phi, {0, 1}, phi, {1, 2}, op::assign_to(tmp));
+    Conv.convolve_Hessians(phi, {1, 2}, phi, {0, 1}, op::subtract_from(tmp));
+    double asym = 0, ref = 0;
+    for (size_t i = 0; i < tmp.ntot_ / 2; ++i) asym = std::max(asym, std::abs(tmp.kelem(i)));
+    Conv.convolve_Hessians(phi, {0, 1}, phi, {1, 2}, op::assign_to(tmp));
+    for (size_t i = 0; i < tmp.ntot_ / 2; ++i) ref = std::max(ref, std::abs(tmp.kelem(i)));
+    CHECK(asym < 1e-13 * ref);
+    // particles: ids of a bcc load (include/particle_generator.hh:150-169)
+    mock_config cf;
+    tmp.FourierTransformBackward(false);
+    tmp.zero();
+    particle::lattice_generator<Grid_FFT<real_t>> lg(particle::lattice_bcc, 0, true, true, false, 1, tmp, cf);
+    for (int d = 0; d < 3; ++d) { lg.set_positions(particle::lattice_bcc, 0, d, 2.0, true, tmp, cf); lg.set_velocities(particle::lattice_bcc, 0, d, true, tmp, cf); }
+    const auto& pc = lg.get_particles();
+    const size_t nc = n * n * n;
+    CHECK(pc.ids64_.size() == 2 * nc);
+    CHECK(pc.ids64_[0] == 2 * nc && pc.ids64_[5] == 2 * nc + 10 && pc.ids64_[nc + 5] == 2 * nc + 11);
+    CHECK(pc.positions64_[3 * 5 + 2] == 5.0 / 32 * 2.0 && pc.positions64_[3 * (nc + 5) + 2] == 5.5 / 32 * 2.0);
+    std::printf("host mirror ok (%s)\n", mfb_build_info());
+    mfb_finalize();
+    return 0;
+}

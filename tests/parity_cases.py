@@ -274,3 +274,40 @@ def check_golden_swift(M):
     assert p["pos"].shape == (65536, 3)
     assert close(p["pos"], gold["PartType1__Coordinates"])
     assert close(p["vel"], gold["PartType1__Velocities"])
+
+
+# ------------------------------------------------------------------ non-cubic product (exercises every z_conv / strided plan)
+def _pad_idx(n, p):
+    i = np.array([k for k in range(n) if k != n // 2])
+    return i, np.where(i < n // 2, i, i + p - n)
+
+
+def check_multiply_noncubic(M, shape):
+    """multiply_field on an (n0,n1,n2) grid against a direct numpy statement of
+    unpad(fwd_P(bwd_P(pad a) * bwd_P(pad b))) with Nyquist planes dropped (MPI semantics)."""
+    n = np.array(shape)
+    p = 3 * n // 2
+    rng = np.random.default_rng(int(n.sum()))
+    def spec():
+        return np.fft.rfftn(rng.standard_normal(shape)) / np.sqrt(float(n.prod()))
+    A, B = spec(), spec()
+    (s0, d0), (s1, d1) = _pad_idx(n[0], p[0]), _pad_idx(n[1], p[1])
+    kz = np.arange(n[2] // 2)
+    def pad(X):
+        Y = np.zeros((p[0], p[1], p[2] // 2 + 1), complex)
+        Y[np.ix_(d0, d1, kz)] = X[np.ix_(s0, s1, kz)] * 1.5 ** 1.5
+        return Y
+    sp = np.sqrt(float(p.prod()))
+    a = np.fft.irfftn(pad(A), s=tuple(p), axes=(0, 1, 2)) * sp
+    b = np.fft.irfftn(pad(B), s=tuple(p), axes=(0, 1, 2)) * sp
+    Cp = np.fft.rfftn(a * b) / sp
+    ref = np.zeros_like(A)
+    ref[np.ix_(s0, s1, kz)] = Cp[np.ix_(d0, d1, kz)] / (sp / np.sqrt(float(n.prod())))
+    L = (100.0, 100.0, 100.0)
+    P, Q = M.Grid_FFT(shape, L), M.Grid_FFT(shape, L)
+    out = M.Grid_FFT(shape, L, True, M.kspace_id)
+    P.set_kspace(A)
+    Q.set_kspace(B)
+    C = M.OrszagConvolver(shape, L)
+    C.multiply_field(P, Q, M.op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL

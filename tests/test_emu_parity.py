@@ -21,6 +21,19 @@ def test_fft_noncubic(M):
     PC.check_fft(M, 32, 48, 64)
 
 
+@pytest.mark.parametrize("shape", [(128, 32, 32), (32, 192, 32), (32, 32, 256), (384, 32, 32), (32, 512, 32),
+                                   (32, 32, 768), (1024, 32, 32), (32, 1536, 32), (32, 32, 2048), (3072, 32, 32),
+                                   (32, 32, 1536), (32, 32, 3072), (32, 2048, 32)])
+def test_fft_every_plan(M, shape):
+    """each of the 14 radix plans as a strided pass and as a z pass"""
+    PC.check_fft(M, *shape)
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 128), (256, 32, 32), (32, 32, 512), (32, 32, 1024), (32, 32, 2048)])
+def test_multiply_noncubic_every_conv_plan(M, shape):
+    PC.check_multiply_noncubic(M, shape)
+
+
 def test_c2r_nonhermitian(M):
     PC.check_c2r_nonhermitian(M, 32)
 

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-grid", type=int, default=0, help="GridRes of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--staged-exchange", action="store_true",
+                    help="N>1: do the slab exchange with NCCL all_to_all instead of peer stores fused into the FFT passes")
     return ap.parse_args()
 
 
@@ -158,16 +160,31 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        from monofonic_b200 import dist_bench
-
-        return dist_bench.run(args, world, rank, local_rank)
-
     n = args.grid or 1024
     order = args.order
     Lbox = 100.0
     torch.cuda.set_device(local_rank)
-    lib = M.init(local_rank)
+    dist = None
+    if world > 1:
+        # one process per GPU (torchrun); slabs of the same global grid on every N => strong scaling
+        import torch.distributed as dist
+        from monofonic_b200 import dist as MD
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        lib = MD.init(local_rank, n, order > 1, staged=args.staged_exchange)
+    else:
+        lib = M.init(local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     stream = torch.cuda.ExternalStream(lib.mfb_stream())
     cfg = M.lpt_config(GridRes=n, BoxLength=Lbox, LPTorder=order, ParticleLoad="sc", Dplus0=0.0257, vfac=396.69,
                        lunit=Lbox, vunit=Lbox / np.sqrt(1 / 51.0), real64=False, ids64=False)
@@ -176,14 +193,16 @@ def run_b200(args):
     amp = O.power_law_amplitude()
     table = M.pipeline.radial_table(n, Lbox, amp)
 
-    # synthetic white noise: real-space Gaussian field generated on the host, transformed on the device
-    rng = np.random.default_rng(12345)
+    # synthetic white noise: real-space Gaussian field generated on the host (one seed per x-plane, so the global
+    # field does not depend on the number of GPUs), transformed on the device.  Each rank holds its slab.
     nz2 = n + 2
-    host_noise = torch.empty((n, n, nz2), dtype=torch.float64, pin_memory=True)
+    l0, o0 = pl.wnoise.local_0_size_, pl.wnoise.local_0_start_
+    host_noise = torch.empty((pl.wnoise.ntot_,), dtype=torch.float64, pin_memory=True)
     hn = host_noise.numpy()
-    for i in range(n):  # slab-wise to bound host memory traffic
-        hn[i, :, :n] = rng.standard_normal((n, n))
-        hn[i, :, n:] = 0.0
+    hn[:] = 0.0
+    hv = hn[:l0 * n * nz2].reshape(l0, n, nz2)
+    for i in range(l0):
+        hv[i, :, :n] = np.random.default_rng(12345 + o0 + i).standard_normal((n, n))
 
     def upload_noise():
         pl.wnoise.FourierTransformBackward(False)
@@ -209,22 +228,25 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         step_device()
     M.synchronize()
+    barrier()
 
     # ---- timed region: device-resident inputs, per-role CUDA events on
     lib.mfb_profile_enable(1)
     lib.mfb_profile_reset()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0 = M.kernel_launches()
+    l0c = M.kernel_launches()
     torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = (M.kernel_launches() - l0) // args.steps
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)   # device time, max over ranks
+    launches = (M.kernel_launches() - l0c) // args.steps * world
     clk = clocks.stop()
 
     # ---- per-role table
@@ -254,20 +276,22 @@ def run_b200(args):
     if not args.no_e2e:
         step_e2e()
         M.synchronize()
+        barrier()
         t0 = time.perf_counter()
         ksteps = max(1, min(args.steps, 2))
         for _ in range(ksteps):
             step_e2e()
         M.synchronize()
-        dt = (time.perf_counter() - t0) / ksteps
+        barrier()
+        dt = max_over_ranks((time.perf_counter() - t0) / ksteps)
         e2e = {"value": n ** 3 / dt / 1e6, "unit": "Mcells/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(hn.nbytes + table.nbytes),
-               "d2h_bytes_per_step": int(out["pos"].nbytes + out["vel"].nbytes + out["ids"].nbytes),
-               "includes": "pinned noise H2D, r2c FFT + conditioning, pipeline, particle AoS D2H"}
+               "h2d_bytes_per_step": int(hn.nbytes + table.nbytes) * world,
+               "d2h_bytes_per_step": int(out["pos"].nbytes + out["vel"].nbytes + out["ids"].nbytes) * world,
+               "includes": "pinned noise H2D, r2c FFT + conditioning, pipeline, particle AoS D2H (all ranks)"}
 
     # ---- CPU baseline: bounded sample of the same workload on the host cores
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         ncpu = args.cpu_grid or 128
         dtc = cpu_reference_run(ncpu, order, threads)
@@ -276,12 +300,25 @@ def run_b200(args):
                          f"(numpy + torch/MKL FP64 FFT, {threads} threads); FFT cost grows as N^3 log N, so the "
                          f"{n}^3 figure would be lower"}
 
-    line = {"metric": "3LPT IC Mcells/s", "value": n ** 3 / (ms / 1e3) / 1e6, "unit": "Mcells/s", "n_gpus": 1,
+    if dist is not None:
+        from monofonic_b200 import dist as MD
+
+        MD.check()
+        nex = lib.mfb_dist_exchanges()
+        barrier()
+        MD.shutdown()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    line = {"metric": "3LPT IC Mcells/s", "value": n ** 3 / (ms / 1e3) / 1e6, "unit": "Mcells/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, order), "grid": n, "lpt_order": order,
                        "l2": "inputs larger than L2 (every grid >= 1 GB; no flush needed)",
-                       "conv2_per_step": 33 if order > 2 else (5 if order > 1 else 0)},
+                       "conv2_per_step": 33 if order > 2 else (5 if order > 1 else 0),
+                       "decomposition": (f"{world} x-slabs (real) / ky-slabs (k-space, transposed), exchange fused into the "
+                                         f"FFT passes over peer memory, {nex // (max(3, args.warmup) + args.steps + 3)} exchanges/step"
+                                         if world > 1 else "single slab")},
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "pipeline_alg_gb_per_step": total_alg, "pipeline_gbs": total_alg / (ms / 1e3), "stages": roles}
     print(json.dumps(line))

@@ -53,6 +53,30 @@ int mfb_profile_num_roles(void);
 const char* mfb_profile_role_name(int role);
 int mfb_profile_get(int role, double* ms, long long* count, double* algorithmic_bytes);
 
+/* ---- slab decomposition over the GPUs of one node (one process per GPU) ---------------------------
+   Replaces the FFTW-MPI slab machinery (src/grid_fft.cc:120-140 fftw_mpi_local_size_3d_transposed + the
+   TRANSPOSED_OUT/IN plans) and the slice-wise Isend/Recv pad/unpad (src/grid_fft.cc:401-485).  After
+   mfb_dist_init + mfb_dist_connect every grid / convolver / particle container created by this process is a
+   slab: real space split along axis 0, k-space along axis 1 in the transposed layout [ky_loc][kx][kz].
+   The exchange of each 3-D FFT is fused into the preceding FFT pass (stores into the peer's buffer, mapped via
+   CUDA IPC, over NVLink); the host only has to carry the 64-byte IPC handles between the processes once
+   (any transport: torch.distributed, MPI_Allgather, ...). */
+size_t mfb_dist_xbuf_bytes(const int n[3], int with_conv, int nranks); /* exchange-buffer size for grids up to n */
+int mfb_dist_init(int rank, int nranks, size_t xbuf_bytes, void* ipc_handle_out /* 64 bytes */);
+int mfb_dist_connect(const void* all_handles /* nranks x 64 bytes, rank order */);
+/* the same slab algorithm with the exchange done by a host collective instead of peer stores (CPU tests over
+   gloo; NCCL all-to-all baseline).  cb(send, recv, chunk_bytes, user): chunk s of send -> rank s; chunk r of
+   recv <- rank r. */
+typedef void (*mfb_exchange_fn)(const void* send, void* recv, size_t chunk_bytes, void* user);
+int mfb_dist_init_staged(int rank, int nranks, size_t xbuf_bytes, mfb_exchange_fn cb, void* user);
+int mfb_dist_shutdown(void);
+int mfb_dist_rank(void);
+int mfb_dist_nranks(void);
+long long mfb_dist_exchanges(void);       /* number of slab exchanges performed so far */
+int mfb_dist_check(void);                 /* fails if a device barrier timed out (dead peer) */
+/* out = {local_0_start_, local_0_size_, local_1_start_, local_1_size_} (include/grid_fft.hh:60-63); returns 1 for a slab */
+int mfb_grid_local(const mfb_grid* g, int out[4]);
+
 /* ---- Grid_FFT ---------------------------------------------------------------------------- */
 /* Grid_FFT(N, L, allocate=true, initialspace) + allocate()        include/grid_fft.hh:77-83, src/grid_fft.cc:40-197 */
 int mfb_grid_create(mfb_grid** g, const int n[3], const double L[3], int space);

@@ -14,6 +14,10 @@ class MfbError(RuntimeError):
     pass
 
 
+# mfb_exchange_fn (include/mfb200.h): void cb(const void* send, void* recv, size_t chunk_bytes, void* user)
+EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
 def _declare(lib):
     vp, i, d, sz, ull = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_ulonglong
     ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -32,6 +36,16 @@ def _declare(lib):
         "mfb_profile_num_roles": (i, []),
         "mfb_profile_role_name": (C.c_char_p, [i]),
         "mfb_profile_get": (i, [i, dp, C.POINTER(C.c_longlong), dp]),
+        "mfb_dist_xbuf_bytes": (sz, [ip, i, i]),
+        "mfb_dist_init": (i, [i, i, sz, vp]),
+        "mfb_dist_connect": (i, [vp]),
+        "mfb_dist_init_staged": (i, [i, i, sz, EXCHANGE_FN, vp]),
+        "mfb_dist_shutdown": (i, []),
+        "mfb_dist_rank": (i, []),
+        "mfb_dist_nranks": (i, []),
+        "mfb_dist_exchanges": (C.c_longlong, []),
+        "mfb_dist_check": (i, []),
+        "mfb_grid_local": (i, [vp, ip]),
         "mfb_grid_create": (i, [vpp, ip, dp, i]),
         "mfb_grid_destroy": (i, [vp]),
         "mfb_grid_space": (i, [vp]),

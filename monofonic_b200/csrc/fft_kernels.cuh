@@ -17,6 +17,8 @@
 
 namespace mfb {
 
+constexpr int MFB_MAX_RANKS = 8;
+
 enum OutOp { OP_ASSIGN = 0, OP_ADD = 1, OP_SUB = 2, OP_MULADD = 3 };
 
 // k-space factor applied to an operand element at integer wave index (ix,iy,iz):
@@ -46,8 +48,13 @@ struct StridedArgs {
     int pos_axis, a_axis;      // which grid axis (0=x,1=y) the position / a index is (for f)
     int op;                    // OutOp
     double alpha;
-    int a_skip;                // a-index whose lines are identically zero (Nyquist), -1: none
+    int a_skip;                // (global) a-index whose lines are identically zero (Nyquist), -1: none
     int zero_fill;             // on OP_ASSIGN also write zeros to skipped lines / Nyquist outputs
+    // ---- slab-decomposed (multi-GPU) passes
+    int a_off;                 // global index of local a == 0 (wave numbers, a_skip)
+    int out_blk;               // > 0: output position k goes to rank k / out_blk, at local position k % out_blk:
+    double2* out_peer[MFB_MAX_RANKS];  //   out_peer[rank] + a*out_as + (k % out_blk)*out_ps + iz  (peer memory over NVLink,
+                               //   or a staging chunk when the exchange is done by a host collective)
 };
 
 MFB_HD double wave_k(int i, int n, double kfac) {
@@ -67,13 +74,21 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
     const int z0 = (blockIdx.x - a * tiles_per_a) * T;
     const int iz = z0 + line;
     const bool line_valid = iz < A.nz;
-    double2* obase = A.out + ptrdiff_t(a) * A.out_as + iz;
+    const ptrdiff_t ooff = ptrdiff_t(a) * A.out_as + iz;
+    // address of output position k (routed to the owning rank's buffer for slab-decomposed passes)
+    auto optr = [&](int k) -> double2* {
+        if (A.out_blk > 0) {
+            const int b = k / A.out_blk;
+            return A.out_peer[b] + ooff + ptrdiff_t(k - b * A.out_blk) * A.out_ps;
+        }
+        return A.out + ooff + ptrdiff_t(k) * A.out_ps;
+    };
 
     // ---- lines that carry no data: optional zero fill, no transform
-    const bool skip_tile = (a == A.a_skip) || (z0 >= A.nz_fft);
+    const bool skip_tile = (a + A.a_off == A.a_skip) || (z0 >= A.nz_fft);
     if (skip_tile) {
         if (A.zero_fill && A.op == OP_ASSIGN && line_valid) {
-            for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(obase + ptrdiff_t(k) * A.out_ps, make_double2(0.0, 0.0));
+            for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(optr(k), make_double2(0.0, 0.0));
         }
         return;
     }
@@ -82,7 +97,7 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
     // ---- per-thread operand factor polynomial in K_pos:  f = q0 + q1*Kp + q2*Kp^2
     double q0 = 1.0, q1 = 0.0, q2 = 0.0;
     if (A.f.enabled) {
-        const double Ka = wave_k(a, A.f.n[A.a_axis], A.f.kf[A.a_axis]);
+        const double Ka = wave_k(a + A.a_off, A.f.n[A.a_axis], A.f.kf[A.a_axis]);
         const double Kz = wave_k(iz, A.f.n[2], A.f.kf[2]);
         q0 = 0.0;
         auto term = [&](int d1, int d2, double c) {
@@ -136,7 +151,7 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
             else return;
         }
         v = make_double2(v.x * A.scale, (A.inverse ? -v.y : v.y) * A.scale);
-        double2* p = obase + ptrdiff_t(dst) * A.out_ps;
+        double2* p = optr(dst);
         if (A.op != OP_ASSIGN) {
             const double2 o = mfb_ld_stream(p);
             const double al = (A.op == OP_ADD) ? 1.0 : ((A.op == OP_SUB) ? -1.0 : A.alpha);
@@ -149,11 +164,11 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
 
     // Nyquist output of a truncated transform is defined to be zero (include/convolution.hh:641-643)
     if (A.zero_fill && A.op == OP_ASSIGN && A.n_out != N && q == 0 && line_valid) {
-        mfb_st_stream(obase + ptrdiff_t(hout) * A.out_ps, make_double2(0.0, 0.0));
+        mfb_st_stream(optr(hout), make_double2(0.0, 0.0));
     }
     // lines of a partially transformed tile beyond nz_fft
     if (A.zero_fill && A.op == OP_ASSIGN && line_valid && !fft_line) {
-        for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(obase + ptrdiff_t(k) * A.out_ps, make_double2(0.0, 0.0));
+        for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(optr(k), make_double2(0.0, 0.0));
     }
 }
 

@@ -6,10 +6,14 @@
 
 namespace mfb {
 
-// geometry of a cubic-or-not grid in k-space, layout [kx][ky][kz] (kz = 0..n2/2)
+// geometry of a cubic-or-not grid in k-space.  Single GPU: layout [kx][ky][kz] (kz = 0..n2/2).
+// Slab-decomposed (tr = 1): the reference's MPI layout [ky_loc][kx][kz] (src/grid_fft.cc:120-128,
+// include/grid_fft.hh:282-296), this rank holding ky = off .. off + s0 - 1.
 struct KGeom {
     int n0, n1, n2, nzc;
     double kf0, kf1, kf2;  // 2 pi / L_d
+    int s0, s1;            // storage extents of the two slow axes
+    int tr, off;           // transposed layout, first local ky
 };
 
 MFB_HD int signed_idx(int i, int n) { return i - ((i > n / 2) ? n : 0); }
@@ -26,14 +30,17 @@ constexpr int EW_ROWS = 4;  // k-space rows (fixed kx,ky) per block
 #define MFB_K_LOOP_BEGIN(G)                                                   \
     for (int t_ = threadIdx.x; t_ < EW_ROWS * (G).nzc; t_ += EW_THREADS) {    \
         const long r_ = long(blockIdx.x) * EW_ROWS + t_ / (G).nzc;            \
-        if (r_ >= long((G).n0) * (G).n1) break;                               \
+        if (r_ >= long((G).s0) * (G).s1) break;                               \
         const int k = t_ % (G).nzc;                                           \
-        const int i = int(r_ / (G).n1);                                       \
-        const int j = int(r_ - long(i) * (G).n1);                             \
+        const int a_ = int(r_ / (G).s1);                                      \
+        const int b_ = int(r_ - long(a_) * (G).s1);                           \
+        const int i = (G).tr ? b_ : a_;                                       \
+        const int j = (G).tr ? a_ + (G).off : b_;                             \
         const long idx = r_ * (G).nzc + k;                                    \
-        (void)i; (void)j; (void)k;
+        const bool is_dc = (i | j | k) == 0;                                  \
+        (void)i; (void)j; (void)k; (void)is_dc;
 
-inline unsigned kgrid_blocks(const KGeom& g) { return unsigned((long(g.n0) * g.n1 + EW_ROWS - 1) / EW_ROWS); }
+inline unsigned kgrid_blocks(const KGeom& g) { return unsigned((long(g.s0) * g.s1 + EW_ROWS - 1) / EW_ROWS); }
 
 // ---------------------------------------------------------------- plain streaming ops
 __global__ void __launch_bounds__(EW_THREADS) scale_kernel(double* __restrict__ d, size_t n, double a) {
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(EW_THREADS) laplacian_pow_kernel(double2* __re
         if (p > 0) f *= k2;
         else if (p < 0) f /= k2;
         double2 v = in[idx];
-        v = (idx == 0) ? make_double2(0.0, 0.0) : make_double2(v.x * f, v.y * f);
+        v = is_dc ? make_double2(0.0, 0.0) : make_double2(v.x * f, v.y * f);
         out[idx] = v;
     }
 }
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(EW_THREADS) assemble_kernel(double2* __restric
             }
         }
         r.x *= A.scale; r.y *= A.scale;
-        if (idx == 0) r = make_double2(0.0, 0.0);
+        if (is_dc) r = make_double2(0.0, 0.0);
         out[idx] = r;
     }
 }
@@ -291,10 +298,10 @@ __global__ void __launch_bounds__(EW_THREADS) particle_ids_kernel(id_t* __restri
 //   dst[stride*(slot0 + cell) + comp] = real_t( add_lattice ? ((idx_d + shift)/n_d)*lunit + f : mul*f )
 template <typename real_out>
 __global__ void __launch_bounds__(EW_THREADS) lattice_readout_kernel(real_out* __restrict__ dst, const double* __restrict__ f,
-                                                                      int n0, int n1, int n2, ptrdiff_t pitch, int i0,
+                                                                      int n0loc, int n0, int n1, int n2, ptrdiff_t pitch, int i0,
                                                                       long slot0, int stride, int comp, int add_lattice, int d,
                                                                       double shift, double lunit, double mul) {
-    const long total = long(n0) * n1 * n2;
+    const long total = long(n0loc) * n1 * n2;  // this rank's slab of lattice planes (i0 = local_0_start_)
     for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * EW_THREADS) {
         const int k = int(t % n2);
         const long r = t / n2;
@@ -303,7 +310,7 @@ __global__ void __launch_bounds__(EW_THREADS) lattice_readout_kernel(real_out* _
         double o;
         if (add_lattice) {
             const int id = (d == 0) ? (i + i0) : ((d == 1) ? j : k);
-            const int nd = (d == 0) ? n0 : ((d == 1) ? n1 : n2);  // n0 here is the *global* size for d==0 (single slab: equal)
+            const int nd = (d == 0) ? n0 : ((d == 1) ? n1 : n2);
             const double qpos = (double(id) + shift) / double(nd);
 #ifdef MFB_EMU
             o = qpos * lunit + v;

@@ -2,6 +2,7 @@
 // lattice read-out and the extern "C" boundary declared in include/mfb200.h.
 //
 // Single-GPU part.  (The multi-GPU slab layer lives in mfb_dist.cu.)
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -45,6 +46,9 @@ namespace mfb {
 
 Context g_ctx;
 thread_local std::string g_err;
+}  // namespace mfb
+#include "mfb_dist.cuh"
+namespace mfb {
 
 void set_error(const std::string& s) { g_err = s; }
 
@@ -276,6 +280,8 @@ KGeom kgeom(const mfb_grid* g) {
     KGeom k;
     k.n0 = g->n[0]; k.n1 = g->n[1]; k.n2 = g->n[2]; k.nzc = g->nzc;
     k.kf0 = 2.0 * M_PI / g->L[0]; k.kf1 = 2.0 * M_PI / g->L[1]; k.kf2 = 2.0 * M_PI / g->L[2];
+    if (g->dist) { k.s0 = g->nloc1; k.s1 = g->n[0]; k.tr = 1; k.off = g->off1; }
+    else { k.s0 = g->n[0]; k.s1 = g->n[1]; k.tr = 0; k.off = 0; }
     return k;
 }
 static unsigned stream_blocks(size_t n) {
@@ -284,8 +290,46 @@ static unsigned stream_blocks(size_t n) {
     return unsigned(b < cap ? (b ? b : 1) : cap);
 }
 
+// routed output of a slab-decomposed pass: position k of the transformed axis belongs to rank k / blk
+static void route(StridedArgs& a, const Exchange& x, int blk, ptrdiff_t ps, ptrdiff_t as) {
+    a.out = nullptr;
+    a.out_blk = blk;
+    a.out_ps = ps; a.out_as = as;
+    for (int s = 0; s < MFB_MAX_RANKS; ++s) a.out_peer[s] = x.base[s];
+}
+
+// slab-decomposed r2c: z (local rows), y (local planes) -> exchange -> x.   Replaces fftw_mpi_plan_dft_r2c_3d with
+// FFTW_MPI_TRANSPOSED_OUT (src/grid_fft.cc:125-128): the result is [ky_loc][kx][kz].
+static void dist_fft_forward(mfb_grid* g, double norm) {
+    double2* c = reinterpret_cast<double2*>(g->d);
+    const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc, l0 = g->nloc0, l1 = g->nloc1;
+    launch_z(g->n[2], 1, g->d, g->pitch, long(l0) * n1, norm);
+    Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+    StridedArgs a = plain_strided(c, nullptr, nzc, ptrdiff_t(n1) * nzc, l0, nzc, n1, 0);
+    route(a, x, l1, nzc, ptrdiff_t(l1) * nzc);                         // chunk layout [x_loc][ky_loc][kz]
+    launch_strided(n1, a, ROLE_FFT_Y);
+    end_exchange(x);                                                    // recv: [x][ky_loc][kz]
+    StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l1) * nzc, nzc, l1, nzc, n0, 0);
+    b.out_ps = nzc; b.out_as = ptrdiff_t(n0) * nzc;                     // -> [ky_loc][kx][kz]
+    launch_strided(n0, b, ROLE_FFT_X);
+}
+static void dist_fft_backward(mfb_grid* g, double norm) {
+    double2* c = reinterpret_cast<double2*>(g->d);
+    const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc, l0 = g->nloc0, l1 = g->nloc1;
+    Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+    StridedArgs a = plain_strided(c, nullptr, nzc, ptrdiff_t(n0) * nzc, l1, nzc, n0, 1);
+    route(a, x, l0, nzc, ptrdiff_t(l0) * nzc);                         // chunk layout [ky_loc][x_loc][kz]
+    launch_strided(n0, a, ROLE_FFT_X);
+    end_exchange(x);                                                    // recv: [ky][x_loc][kz]
+    StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l0) * nzc, nzc, l0, nzc, n1, 1);
+    b.out_ps = nzc; b.out_as = ptrdiff_t(n1) * nzc;                     // -> [x_loc][y][kz]
+    launch_strided(n1, b, ROLE_FFT_Y);
+    launch_z(g->n[2], 0, g->d, g->pitch, long(l0) * n1, norm);
+}
+
 void grid_fft_forward(mfb_grid* g) {
     const double norm = 1.0 / std::sqrt(double(g->n[0]) * double(g->n[1]) * double(g->n[2]));
+    if (g->dist) { dist_fft_forward(g, norm); return; }
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
     launch_z(g->n[2], 1, g->d, g->pitch, long(n0) * n1, norm);
@@ -294,6 +338,7 @@ void grid_fft_forward(mfb_grid* g) {
 }
 void grid_fft_backward(mfb_grid* g) {
     const double norm = 1.0 / std::sqrt(double(g->n[0]) * double(g->n[1]) * double(g->n[2]));
+    if (g->dist) { dist_fft_backward(g, norm); return; }
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
     launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 1), ROLE_FFT_X);
@@ -320,27 +365,29 @@ double* partial_buffer(size_t ndoubles) {
 static void grid_sums(mfb_grid* g, double out[2]) {
     const int nb = 148 * 4;
     double* part = partial_buffer(2 * nb + 2);
+    const int x0 = g->dist ? g->nloc0 : g->n[0], k0 = g->dist ? g->nloc1 : g->n[0];
     if (g->space == MFB_RSPACE) {
-        MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_real_kernel, nb, RED_THREADS, g->d, long(g->n[0]) * g->n[1], g->n[2], g->pitch, part);
+        MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_real_kernel, nb, RED_THREADS, g->d, long(x0) * g->n[1], g->n[2], g->pitch, part);
     } else {
         MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_cplx_kernel, nb, RED_THREADS, reinterpret_cast<const double2*>(g->d),
-                   long(g->n[0]) * g->n[1] * g->nzc, part);
+                   long(k0) * g->n[1] * g->nzc, part);
     }
     check_launch("reduce");
     MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_final_kernel, 1, RED_THREADS, part, nb, 0, part + 2 * nb);
     check_launch("reduce_final");
+    if (g->dist) dist_allreduce_sum2(part + 2 * nb);  // include/grid_fft.hh:532-542: MPI_Allreduce(SUM)
     cuda_check(cudaMemcpyAsync(out, part + 2 * nb, 2 * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "reduce D2H");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
 }
 
 void grid_zero_dc(mfb_grid* g) {
     if (g->space == MFB_KSPACE) {
-        cuda_check(cudaMemsetAsync(g->d, 0, sizeof(double2), g_ctx.stream), "zero DC");
+        if (!g->dist || g->off1 == 0) cuda_check(cudaMemsetAsync(g->d, 0, sizeof(double2), g_ctx.stream), "zero DC");
     } else {
         double s[2];
         grid_sums(g, s);
         const double mean = s[0] / (double(g->n[0]) * g->n[1] * g->n[2]);
-        const long nrows = long(g->n[0]) * g->n[1];
+        const long nrows = long(g->dist ? g->nloc0 : g->n[0]) * g->n[1];
         MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, subtract_real_kernel, stream_blocks(size_t(nrows) * g->n[2]), EW_THREADS, g->d, nrows, g->n[2],
                    g->pitch, mean);
         check_launch("subtract_real");
@@ -378,7 +425,41 @@ struct Operand {
     int imag;
 };
 
+static void set_operand_factor(StridedArgs& a, mfb_conv* c, const Operand& o, double s1) {
+    a.f.enabled = 1;
+    a.f.a1 = o.a1; a.f.b1 = o.b1; a.f.a2 = o.a2; a.f.b2 = o.b2;
+    a.f.c1 = o.c1 * s1; a.f.c2 = o.c2 * s1;
+    a.f.imag = o.imag;
+    for (int d = 0; d < 3; ++d) { a.f.n[d] = c->n[d]; a.f.kf[d] = 2.0 * M_PI / c->L[d]; }
+}
+
+// slab-decomposed operand transform: x pass (N0 -> P0, on the local ky rows) -> exchange of the pruned
+// 1.5 R(N)/P intermediate -> y pass (N1 -> P1) on the local x planes of the padded grid.
+static void dist_conv_backward_operand(mfb_conv* c, const Operand& o, double2* W2) {
+    const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
+    const int P0 = c->np[0], P1 = c->np[1];
+    const int nzc = N2 / 2 + 1, nzin = N2 / 2;
+    const int l1 = o.g->nloc1, p0l = c->p0loc;
+    const double ptot = double(c->np[0]) * c->np[1] * c->np[2];
+    const double s1 = std::pow(1.5, 1.5) / std::sqrt(ptot);
+    Exchange x = begin_exchange(size_t(l1) * p0l * nzin);
+    StridedArgs a = plain_strided(reinterpret_cast<const double2*>(o.g->d), nullptr, nzc, ptrdiff_t(N0) * nzc, l1, nzin, P0, 1);
+    a.n_in = N0;
+    a.a_off = o.g->off1;
+    a.a_skip = N1 / 2;
+    set_operand_factor(a, c, o, s1);
+    a.pos_axis = 0; a.a_axis = 1;
+    route(a, x, p0l, nzin, ptrdiff_t(p0l) * nzin);                      // chunk layout [ky_loc][x_loc][kz]
+    launch_strided(P0, a, ROLE_CONV_X_BWD);
+    end_exchange(x);                                                     // recv: [ky][x_loc][kz]
+    StridedArgs b = plain_strided(x.recv, W2, ptrdiff_t(p0l) * nzin, nzin, p0l, nzin, P1, 1);
+    b.out_ps = nzin; b.out_as = ptrdiff_t(P1) * nzin;                    // -> [x_loc][P1][kz]
+    b.n_in = N1;
+    launch_strided(P1, b, ROLE_CONV_Y_BWD);
+}
+
 static void conv_backward_operand(mfb_conv* c, const Operand& o, double2* W2) {
+    if (c->dist) { dist_conv_backward_operand(c, o, W2); return; }
     const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
     const int P0 = c->np[0], P1 = c->np[1];
     const int nzc = N2 / 2 + 1, nzin = N2 / 2;
@@ -390,11 +471,7 @@ static void conv_backward_operand(mfb_conv* c, const Operand& o, double2* W2) {
     a.out_ps = ptrdiff_t(N1) * nzin; a.out_as = nzin;
     a.n_in = N0;
     a.a_skip = N1 / 2;
-    a.f.enabled = 1;
-    a.f.a1 = o.a1; a.f.b1 = o.b1; a.f.a2 = o.a2; a.f.b2 = o.b2;
-    a.f.c1 = o.c1 * s1; a.f.c2 = o.c2 * s1;
-    a.f.imag = o.imag;
-    for (int d = 0; d < 3; ++d) { a.f.n[d] = c->n[d]; a.f.kf[d] = 2.0 * M_PI / c->L[d]; }
+    set_operand_factor(a, c, o, s1);
     a.pos_axis = 0; a.a_axis = 1;
     launch_strided(P0, a, ROLE_CONV_X_BWD);
     // pass 2: y axis, N1 -> P1
@@ -415,6 +492,32 @@ void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int o
     const double ptot = double(P0) * P1 * P2, ntot = double(N0) * N1 * N2;
     conv_backward_operand(c, A, c->W2a);
     conv_backward_operand(c, B, c->W2b);
+    const double unpad_scale = (1.0 / std::sqrt(ptot)) / (std::sqrt(ptot) / std::sqrt(ntot));  // fwd norm / rfac (convolution.hh:620,664)
+    if (c->dist) {
+        const int p0l = c->p0loc, l1 = out->nloc1;
+        launch_zconv(P2, c->W2a, c->W2b, c->W2a, nzin, nzin, long(p0l) * P1, nzin, 1.0);
+        // y forward P1 -> N1 on the local x planes, routed to the owners of the ky rows
+        Exchange x = begin_exchange(size_t(p0l) * l1 * nzin);
+        StridedArgs d = plain_strided(c->W2a, nullptr, nzin, ptrdiff_t(P1) * nzin, p0l, nzin, P1, 0);
+        d.n_out = N1;
+        route(d, x, l1, nzin, ptrdiff_t(l1) * nzin);                    // chunk layout [x_loc][ky_loc][kz]
+        launch_strided(P1, d, ROLE_CONV_Y_FWD);
+        end_exchange(x);                                                 // recv: [x (P0)][ky_loc][kz]
+        // x forward P0 -> N0 + unpad scale + Nyquist zero + output operator, into [ky_loc][kx][kz]
+        StridedArgs e = plain_strided(x.recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * nzin, nzin, l1,
+                                      (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
+        e.out_ps = nzc; e.out_as = ptrdiff_t(N0) * nzc;
+        e.nz_fft = nzin;
+        e.n_out = N0;
+        e.scale = unpad_scale;
+        e.op = op; e.alpha = alpha;
+        e.a_off = out->off1;
+        e.a_skip = N1 / 2;
+        e.zero_fill = 1;
+        launch_strided(P0, e, ROLE_CONV_X_FWD);
+        ++c->nconv;
+        return;
+    }
     // pass 3: fused z  c2r x2, product, r2c (in place on W2a)
     launch_zconv(P2, c->W2a, c->W2b, c->W2a, nzin, nzin, long(P0) * P1, nzin, 1.0);
     // pass 4: y axis forward, P1 -> N1
@@ -429,7 +532,7 @@ void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int o
     e.out_ps = ptrdiff_t(N1) * nzc; e.out_as = nzc;
     e.nz_fft = nzin;
     e.n_out = N0;
-    e.scale = (1.0 / std::sqrt(ptot)) / (std::sqrt(ptot) / std::sqrt(ntot));  // fwd norm / rfac (convolution.hh:620,664)
+    e.scale = unpad_scale;
     e.op = op; e.alpha = alpha;
     e.a_skip = N1 / 2;
     e.zero_fill = 1;
@@ -527,8 +630,9 @@ static void particles_readout(mfb_particles* p, int kind, int lattice_index, int
     require(f->n[0] == p->n[0] && f->n[1] == p->n[1] && f->n[2] == p->n[2], "field/particle grid size mismatch");
     const int lt = p->lattice_type;
     const int nshift = 1 << lt;
-    const long ncell = long(p->n[0]) * p->n[1] * p->n[2];
-    const double pmean = unit / double(ncell * nshift);
+    require(f->nloc0 == p->nloc0 && f->off0 == p->off0, "field/particle slab mismatch");
+    const long ncell = long(p->nloc0) * p->n[1] * p->n[2];          // local cells
+    const double pmean = unit / (double(p->n[0]) * p->n[1] * p->n[2] * nshift);
     to_rspace(f);
     for (int is = 0; is < nshift; ++is) {
         if (is == 0 && lattice_index == 1) grid_shift_field(f, SECOND_LATTICE_SHIFT[lt], true);
@@ -548,11 +652,11 @@ static void particles_readout(mfb_particles* p, int kind, int lattice_index, int
         const int addl = (kind == 0) ? 1 : 0;
         const double mul = (kind == 2) ? pmean : 1.0;
         if (p->real64) {
-            MFB_LAUNCH_ROLE(ROLE_PARTICLES, lattice_readout_kernel<double>, nb, EW_THREADS, (double*)dst, f->d, f->n[0], f->n[1],
-                       f->n[2], f->pitch, 0, slot0, stride, comp, addl, idim, shift, unit, mul);
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, lattice_readout_kernel<double>, nb, EW_THREADS, (double*)dst, f->d, f->nloc0, f->n[0], f->n[1],
+                       f->n[2], f->pitch, f->off0, slot0, stride, comp, addl, idim, shift, unit, mul);
         } else {
-            MFB_LAUNCH_ROLE(ROLE_PARTICLES, lattice_readout_kernel<float>, nb, EW_THREADS, (float*)dst, f->d, f->n[0], f->n[1],
-                       f->n[2], f->pitch, 0, slot0, stride, comp, addl, idim, shift, unit, mul);
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, lattice_readout_kernel<float>, nb, EW_THREADS, (float*)dst, f->d, f->nloc0, f->n[0], f->n[1],
+                       f->n[2], f->pitch, f->off0, slot0, stride, comp, addl, idim, shift, unit, mul);
         }
         check_launch("lattice_readout");
     }
@@ -626,7 +730,7 @@ int mfb_profile_reset(void) {
 int mfb_profile_num_roles(void) { return ROLE_COUNT; }
 const char* mfb_profile_role_name(int role) {
     static const char* names[ROLE_COUNT] = {"conv_x_bwd", "conv_y_bwd", "conv_z_fused", "conv_y_fwd", "conv_x_fwd", "fft_x",
-                                            "fft_y", "fft_z_r2c", "fft_z_c2r", "elementwise", "reduce", "particles"};
+                                            "fft_y", "fft_z_r2c", "fft_z_c2r", "elementwise", "reduce", "particles", "barrier"};
     return (role >= 0 && role < ROLE_COUNT) ? names[role] : "?";
 }
 int mfb_profile_get(int role, double* ms, long long* count, double* bytes) {
@@ -635,6 +739,121 @@ int mfb_profile_get(int role, double* ms, long long* count, double* bytes) {
     prof_collect();
     *ms = g_ctx.role_ms[role]; *count = g_ctx.role_count[role]; *bytes = g_ctx.role_bytes[role];
     MFB_CATCH
+}
+
+
+// ---------------------------------------------------------------- slab decomposition over GPUs (one process per GPU)
+size_t mfb_dist_xbuf_bytes(const int n[3], int with_conv, int nranks) {
+    const size_t P = size_t(nranks > 0 ? nranks : 1);
+    size_t plain = size_t(n[0]) * n[1] * (n[2] / 2 + 1) / P;
+    size_t conv = with_conv ? size_t(3 * n[0] / 2) * n[1] * (n[2] / 2) / P : 0;
+    size_t e = plain > conv ? plain : conv;
+    if (e < 64) e = 64;
+    return ((e * sizeof(double2) + 255) / 256) * 256;
+}
+static void dist_layout_block(size_t xbuf_bytes) {
+    DistState& d = D();
+    char* b = (char*)d.block;
+    d.xbuf_elems = xbuf_bytes / sizeof(double2);
+    d.xbuf[0] = (double2*)b;
+    d.xbuf[1] = (double2*)(b + xbuf_bytes);
+    d.flags = (unsigned long long*)(b + 2 * xbuf_bytes);
+    d.err = (int*)(b + 2 * xbuf_bytes + 256);
+}
+int mfb_dist_init(int rank, int nranks, size_t xbuf_bytes, void* ipc_handle_out) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(!D().ready, "mfb_dist_init: already initialised");
+    require(nranks >= 1 && nranks <= MFB_MAX_RANKS && rank >= 0 && rank < nranks, "mfb_dist_init: bad rank / world size (max 8)");
+    require(xbuf_bytes % 256 == 0, "mfb_dist_init: xbuf_bytes must come from mfb_dist_xbuf_bytes");
+#ifdef MFB_EMU
+    throw std::runtime_error("peer-mapped exchange is not available in the emulation build; use mfb_dist_init_staged");
+#else
+    DistState& d = D();
+    d.rank = rank; d.nranks = nranks; d.staged = false;
+    const size_t total = 2 * xbuf_bytes + 4096;
+    d.block = dev_alloc(total);
+    cuda_check(cudaMemset(d.block, 0, total), "memset exchange block");
+    dist_layout_block(xbuf_bytes);
+    cudaIpcMemHandle_t h;
+    cuda_check(cudaIpcGetMemHandle(&h, d.block), "cudaIpcGetMemHandle");
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+#endif
+    MFB_CATCH
+}
+int mfb_dist_connect(const void* all_handles) {
+    MFB_TRY
+#ifdef MFB_EMU
+    (void)all_handles;
+    throw std::runtime_error("peer-mapped exchange is not available in the emulation build");
+#else
+    DistState& d = D();
+    require(d.block != nullptr && !d.ready, "mfb_dist_connect: call mfb_dist_init first");
+    const size_t xb = d.xbuf_elems * sizeof(double2);
+    for (int s = 0; s < d.nranks; ++s) {
+        void* base = d.block;
+        if (s != d.rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)all_handles + 64 * s, 64);
+            cuda_check(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer exchange buffer)");
+            d.peer_block[s] = base;
+        }
+        d.peer_xbuf[0][s] = (double2*)base;
+        d.peer_xbuf[1][s] = (double2*)((char*)base + xb);
+        d.peer_flags[s] = (unsigned long long*)((char*)base + 2 * xb);
+    }
+    d.ready = true;
+#endif
+    MFB_CATCH
+}
+int mfb_dist_init_staged(int rank, int nranks, size_t xbuf_bytes, mfb_exchange_fn cb, void* user) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(!D().ready, "mfb_dist_init_staged: already initialised");
+    require(nranks >= 1 && nranks <= MFB_MAX_RANKS && rank >= 0 && rank < nranks, "mfb_dist_init_staged: bad rank / world size (max 8)");
+    require(cb != nullptr, "mfb_dist_init_staged: exchange callback required");
+    DistState& d = D();
+    d.rank = rank; d.nranks = nranks; d.staged = true; d.cb = cb; d.cb_user = user;
+    const size_t total = 2 * xbuf_bytes + 4096;
+    d.block = dev_alloc(total);
+    cuda_check(cudaMemset(d.block, 0, total), "memset exchange block");
+    dist_layout_block(xbuf_bytes);
+    d.sendbuf = (double2*)dev_alloc(xbuf_bytes);
+    d.ready = true;
+    MFB_CATCH
+}
+int mfb_dist_shutdown(void) {
+    MFB_TRY
+    DistState& d = D();
+    if (g_ctx.initialised) cudaStreamSynchronize(g_ctx.stream);
+#ifndef MFB_EMU
+    for (int s = 0; s < MFB_MAX_RANKS; ++s)
+        if (d.peer_block[s]) cudaIpcCloseMemHandle(d.peer_block[s]);
+#endif
+    if (d.sendbuf) cudaFree(d.sendbuf);
+    if (d.block) cudaFree(d.block);
+    d = DistState();
+    MFB_CATCH
+}
+int mfb_dist_rank(void) { return D().rank; }
+int mfb_dist_nranks(void) { return D().ready ? D().nranks : 1; }
+long long mfb_dist_exchanges(void) { return D().nexch; }
+/* non-zero if a device barrier timed out (a peer died): results are invalid */
+int mfb_dist_check(void) {
+    MFB_TRY
+    DistState& d = D();
+    if (d.ready && !d.staged && d.err) {
+        int e = 0;
+        cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+        cuda_check(cudaMemcpy(&e, d.err, sizeof(int), cudaMemcpyDeviceToHost), "read barrier status");
+        require(e == 0, "slab exchange barrier timed out: a peer rank is not responding");
+    }
+    MFB_CATCH
+}
+int mfb_grid_local(const mfb_grid* g, int out[4]) {
+    out[0] = g->off0; out[1] = g->nloc0; out[2] = g->off1; out[3] = g->nloc1;
+    return g->dist;
 }
 
 // ---------------------------------------------------------------- grids
@@ -650,6 +869,16 @@ int mfb_grid_create(mfb_grid** out, const int n[3], const double L[3], int space
     g->nzc = n[2] / 2 + 1;
     g->pitch = n[2] + 2;
     g->ntot = size_t(n[0]) * n[1] * (n[2] + 2);
+    g->dist = 0; g->nloc0 = n[0]; g->off0 = 0; g->nloc1 = n[1]; g->off1 = 0;
+    if (dist_on()) {
+        const int P = D().nranks, r = D().rank;
+        if (n[0] % P || n[1] % P) { delete g; throw std::runtime_error("slab decomposition needs grid sizes divisible by the number of GPUs"); }
+        g->dist = 1;
+        g->nloc0 = n[0] / P; g->off0 = r * g->nloc0;
+        g->nloc1 = n[1] / P; g->off1 = r * g->nloc1;
+        const size_t rows = std::max(size_t(g->nloc0) * n[1], size_t(g->nloc1) * n[0]);
+        g->ntot = rows * (n[2] + 2);
+    }
     g->space = space;
     g->d = (double*)dev_alloc(g->ntot * sizeof(double));
     *out = g;
@@ -769,6 +998,7 @@ int mfb_grid_2norm(mfb_grid* g, double* out) {
 int mfb_grid_max_neighbour_diff(mfb_grid* g, double* out) {
     MFB_TRY
     require(g->space == MFB_RSPACE, "max_neighbour_diff: grid must be in real space");
+    require(!g->dist, "max_neighbour_diff is not available for slab-decomposed grids");
     const int nb = 148 * 4;
     double* part = partial_buffer(2 * nb + 2);
     MFB_LAUNCH_ROLE(ROLE_REDUCE, max_neighbour_diff_kernel, nb, RED_THREADS, g->d, g->n[0], g->n[1], g->n[2], g->pitch, part);
@@ -781,6 +1011,7 @@ int mfb_grid_max_neighbour_diff(mfb_grid* g, double* out) {
 }
 int mfb_fourier_resample(mfb_grid* src, mfb_grid* dst) {
     MFB_TRY
+    require(!src->dist && !dst->dist, "FourierInterpolateCopyTo is not available for slab-decomposed grids");
     to_kspace(src);
     dst->space = MFB_KSPACE;
     if (src->n[0] == dst->n[0] && src->n[1] == dst->n[1] && src->n[2] == dst->n[2]) {
@@ -895,9 +1126,15 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
         require(supported_size(n[d]) && supported_size(c->np[d]), "unsupported grid size for the Orszag convolver");
     }
     const size_t nzin = n[2] / 2;
-    c->w1_elems = size_t(c->np[0]) * n[1] * nzin;
-    c->w2_elems = size_t(c->np[0]) * c->np[1] * nzin;
-    c->W1 = (double2*)dev_alloc(c->w1_elems * sizeof(double2));
+    c->dist = 0; c->p0loc = c->np[0]; c->p0off = 0;
+    if (dist_on()) {
+        const int P = D().nranks;
+        require(n[0] % P == 0 && n[1] % P == 0 && c->np[0] % P == 0, "slab decomposition needs N and 3N/2 divisible by the number of GPUs");
+        c->dist = 1; c->p0loc = c->np[0] / P; c->p0off = D().rank * c->p0loc;
+    }
+    c->w1_elems = c->dist ? 0 : size_t(c->np[0]) * n[1] * nzin;   // slab mode: the exchange buffers play W1's role
+    c->w2_elems = size_t(c->p0loc) * c->np[1] * nzin;
+    c->W1 = c->dist ? nullptr : (double2*)dev_alloc(c->w1_elems * sizeof(double2));
     c->W2a = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
     c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
     if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
@@ -907,7 +1144,8 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
 int mfb_conv_destroy(mfb_conv* c) {
     MFB_TRY
     if (c) {
-        cudaFree(c->W1); cudaFree(c->W2a); cudaFree(c->W2b);
+        if (c->W1) cudaFree(c->W1);
+        cudaFree(c->W2a); cudaFree(c->W2b);
         mfb_grid_destroy(c->fbuf);
         delete c;
     }
@@ -991,7 +1229,12 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
     for (int d = 0; d < 3; ++d) p->n[d] = n[d];
     p->lattice_type = lattice_type; p->real64 = real64; p->ids64 = ids64;
     const size_t ov = size_t(1) << lattice_type;
-    p->np = ov * size_t(n[0]) * n[1] * n[2];
+    p->nloc0 = n[0]; p->off0 = 0;
+    if (dist_on()) {
+        require(n[0] % D().nranks == 0, "slab decomposition needs grid sizes divisible by the number of GPUs");
+        p->nloc0 = n[0] / D().nranks; p->off0 = D().rank * p->nloc0;
+    }
+    p->np = ov * size_t(p->nloc0) * n[1] * n[2];   // get_local_num_particles (particle_container.hh:150-152)
     const size_t rs = real64 ? 8 : 4, is = ids64 ? 8 : 4;
     p->pos = dev_alloc(3 * p->np * rs);
     p->vel = dev_alloc(3 * p->np * rs);
@@ -1012,14 +1255,16 @@ int mfb_particles_destroy(mfb_particles* p) {
 size_t mfb_particles_count(const mfb_particles* p) { return p->np; }
 int mfb_particles_set_ids(mfb_particles* p, unsigned long long id_offset_species) {
     MFB_TRY
-    const long ncell = long(p->n[0]) * p->n[1] * p->n[2];
+    const long ncell = long(p->n[0]) * p->n[1] * p->n[2];            // global
+    const long nloc = long(p->nloc0) * p->n[1] * p->n[2];            // this slab
+    const long cell0 = long(p->off0) * p->n[1] * p->n[2];
     const int ov = 1 << p->lattice_type;
     const unsigned long long off = id_offset_species * (unsigned long long)ov * (unsigned long long)ncell;
     const unsigned nb = stream_blocks(p->np);
     if (p->ids64) {
-        MFB_LAUNCH_ROLE(ROLE_PARTICLES, particle_ids_kernel<unsigned long long>, nb, EW_THREADS, (unsigned long long*)p->ids, ncell, ov, off, 0L);
+        MFB_LAUNCH_ROLE(ROLE_PARTICLES, particle_ids_kernel<unsigned long long>, nb, EW_THREADS, (unsigned long long*)p->ids, nloc, ov, off, cell0);
     } else {
-        MFB_LAUNCH_ROLE(ROLE_PARTICLES, particle_ids_kernel<unsigned int>, nb, EW_THREADS, (unsigned int*)p->ids, ncell, ov, off, 0L);
+        MFB_LAUNCH_ROLE(ROLE_PARTICLES, particle_ids_kernel<unsigned int>, nb, EW_THREADS, (unsigned int*)p->ids, nloc, ov, off, cell0);
     }
     check_launch("particle_ids");
     MFB_CATCH

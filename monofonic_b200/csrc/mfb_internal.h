@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "mfb_platform.h"
+#include "../../include/mfb200.h"
 
 struct mfb_grid {
     int n[3];
@@ -14,6 +15,11 @@ struct mfb_grid {
     size_t ntot;
     int nzc;          // n2/2+1
     ptrdiff_t pitch;  // n2+2 doubles per z-row
+    // slab decomposition (src/grid_fft.cc:120-128): real space split along axis 0, k-space along axis 1 with the
+    // transposed layout [ky_loc][kx][kz].  dist == 0: one slab holding everything, k-layout [kx][ky][kz].
+    int dist;
+    int nloc0, off0;  // local_0_size_, local_0_start_
+    int nloc1, off1;  // local_1_size_, local_1_start_
 };
 
 struct mfb_conv {
@@ -21,6 +27,7 @@ struct mfb_conv {
     double L[3];
     double2 *W1, *W2a, *W2b;  // workspaces: [P0][N1][N2/2], [P0][P1][N2/2] x2  
     size_t w1_elems, w2_elems;
+    int dist, p0loc, p0off;   // slab of the padded grid along axis 0 (real space)
     mfb_grid* fbuf;           // N-grid for the intermediate of 3-field products (convolution.hh:469)
     long nconv;
 };
@@ -28,7 +35,8 @@ struct mfb_conv {
 struct mfb_particles {
     int n[3];
     int lattice_type, real64, ids64;
-    size_t np;
+    size_t np;        // local number of particles
+    int nloc0, off0;  // slab of lattice planes held by this rank
     void *pos, *vel, *ids, *mass;  // device AoS (particle_container.hh:82-108)
 };
 
@@ -37,7 +45,26 @@ namespace mfb {
 enum Role {
     ROLE_CONV_X_BWD = 0, ROLE_CONV_Y_BWD, ROLE_CONV_Z, ROLE_CONV_Y_FWD, ROLE_CONV_X_FWD,
     ROLE_FFT_X, ROLE_FFT_Y, ROLE_FFT_Z_R2C, ROLE_FFT_Z_C2R, ROLE_ELEMENTWISE, ROLE_REDUCE, ROLE_PARTICLES,
-    ROLE_COUNT
+    ROLE_BARRIER, ROLE_COUNT
+};
+// host collective used when peers are not mapped (CPU emulation tests, NCCL baseline): deliver chunk s of
+// `send` (P chunks of chunk_bytes) to rank s, receive rank r's chunk into chunk r of `recv`.
+struct DistState {
+    int rank = 0, nranks = 1;
+    bool ready = false, staged = false;
+    void* block = nullptr;               // [xbuf0][xbuf1][flags]: one IPC-exported allocation
+    size_t xbuf_elems = 0;               // complex elements per exchange buffer
+    double2* xbuf[2] = {nullptr, nullptr};
+    double2* sendbuf = nullptr;          // staged mode only
+    double2* peer_xbuf[2][8] = {};
+    unsigned long long* flags = nullptr; // flags[r]: last barrier epoch rank r has reached
+    unsigned long long* peer_flags[8] = {};
+    int* err = nullptr;                  // device flag set when a barrier times out
+    unsigned long long epoch = 0;
+    long nexch = 0;
+    mfb_exchange_fn cb = nullptr;
+    void* cb_user = nullptr;
+    void* peer_block[8] = {};
 };
 struct ProfEvent { cudaEvent_t a, b; int role; double bytes; };
 struct Context {
@@ -59,6 +86,7 @@ struct Context {
     double role_ms[ROLE_COUNT] = {0};
     double role_bytes[ROLE_COUNT] = {0};
     long long role_count[ROLE_COUNT] = {0};
+    DistState dist;
 };
 // RAII: tags the launches issued in its scope with a role and their algorithmic HBM bytes
 struct RoleScope {

@@ -103,6 +103,13 @@ class Grid_FFT:
         if self._h:
             return
         L.check(self._lib.mfb_grid_create(C.byref(self._h), _i3(self.n_), _d3(self.length_), self._initialspace), self._lib)
+        loc = (C.c_int * 4)()
+        self.distributed_ = bool(self._lib.mfb_grid_local(self._h, loc))
+        # slab bookkeeping with the reference's names (include/grid_fft.hh:60-63)
+        self.local_0_start_, self.local_0_size_, self.local_1_start_, self.local_1_size_ = [int(v) for v in loc]
+
+    def is_distributed(self):
+        return self.distributed_
 
     def is_allocated(self):
         return bool(self._h)
@@ -128,9 +135,12 @@ class Grid_FFT:
         return int(self._lib.mfb_grid_ntot(self._h))
 
     def size(self, i):
+        """local extents; k-space of a slab is transposed: (ky_loc, kx, kz) (src/grid_fft.cc:176-189)"""
         n0, n1, n2 = self.n_
         if self.space_ == rspace_id:
-            return (n0, n1, n2, n2 + 2)[i]
+            return (self.local_0_size_, n1, n2, n2 + 2)[i]
+        if self.distributed_:
+            return (self.local_1_size_, n0, n2 // 2 + 1, n2 // 2 + 1)[i]
         return (n0, n1, n2 // 2 + 1, n2 // 2 + 1)[i]
 
     def global_size(self):
@@ -150,28 +160,49 @@ class Grid_FFT:
     def set_real(self, x: np.ndarray):
         """fill from a [n0][n1][n2] real array (relem view); grid is declared real-space"""
         n0, n1, n2 = self.n_
-        buf = np.zeros((n0, n1, n2 + 2))
-        buf[:, :, :n2] = x
+        l0, o0 = self.local_0_size_, self.local_0_start_
+        if x.shape[0] == n0 and l0 != n0:   # global array given to a slab: keep the local planes
+            x = x[o0:o0 + l0]
+        buf = np.zeros(self.ntot_).reshape(-1, n2 + 2)
+        buf[:l0 * n1, :n2] = np.asarray(x).reshape(l0 * n1, n2)
         self.FourierTransformBackward(False)
         self.upload_raw(buf)
 
     def get_real(self) -> np.ndarray:
+        """the local slab [local_0_size][n1][n2]"""
         n0, n1, n2 = self.n_
         assert self.space_ == rspace_id
-        return self.download_raw().reshape(n0, n1, n2 + 2)[:, :, :n2].copy()
+        l0 = self.local_0_size_
+        return self.download_raw().reshape(-1, n2 + 2)[:l0 * n1, :n2].reshape(l0, n1, n2).copy()
 
     def set_kspace(self, X: np.ndarray):
         """fill from a [kx][ky][kz] half-spectrum (kelem view); grid is declared k-space"""
         n0, n1, n2 = self.n_
+        nzc = n2 // 2 + 1
+        if self.distributed_:
+            # slab k-layout is [ky_loc][kx][kz]; accept the global [kx][ky][kz] array or the local transposed one
+            l1, o1 = self.local_1_size_, self.local_1_start_
+            if X.shape == (n0, n1, nzc):
+                X = np.transpose(X[:, o1:o1 + l1, :], (1, 0, 2))
+            assert X.shape == (l1, n0, nzc)
+        else:
+            assert X.shape == (n0, n1, nzc)
         X = np.ascontiguousarray(X, dtype=np.complex128)
-        assert X.shape == (n0, n1, n2 // 2 + 1)
+        buf = np.zeros(self.ntot_)
+        buf[:X.size * 2] = X.view(np.float64).reshape(-1)
         self.FourierTransformForward(False)
-        self.upload_raw(X.view(np.float64))
+        self.upload_raw(buf)
 
     def get_kspace(self) -> np.ndarray:
+        """[kx][ky][kz]; for a slab the local part in the transposed layout [ky_loc][kx][kz]"""
         n0, n1, n2 = self.n_
+        nzc = n2 // 2 + 1
         assert self.space_ == kspace_id
-        return self.download_raw().view(np.complex128).reshape(n0, n1, n2 // 2 + 1).copy()
+        raw = self.download_raw().view(np.complex128)
+        if self.distributed_:
+            l1 = self.local_1_size_
+            return raw[:l1 * n0 * nzc].reshape(l1, n0, nzc).copy()
+        return raw.reshape(n0, n1, nzc).copy()
 
     # -- transforms ---------------------------------------------------------------------
     def FourierTransformForward(self, do_transform=True):

@@ -1,0 +1,150 @@
+"""Worker of the multi-rank tests: run under torchrun (one process per rank).
+
+  --emu   : CPU thread-emulation build of the kernels + gloo, exchange through all_to_all ("staged" mode);
+            validates the slab algorithm and the host logic without a GPU (pytest -m "not gpu").
+  default : libmfb200.so on cuda:LOCAL_RANK, exchange fused into the FFT passes over peer memory.
+  --staged: GPU build with the exchange done by NCCL all_to_all (the library-collective baseline).
+
+Checks, all against the single-process CPU oracle on the same seeded inputs: 3-D FFT round trip, k-space
+operators incl. reductions, every named product, whole 1/2/3LPT pipelines with particles (ids exact), and
+equality with the reference's slab bookkeeping (local_0/1_start/size)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--emu", action="store_true")
+    ap.add_argument("--staged", action="store_true")
+    ap.add_argument("--grid", type=int, default=32)
+    ap.add_argument("--lattice", default="bcc")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    import lpt_oracle as O
+    import monofonic_b200 as M
+    import parity_cases as PC
+    from monofonic_b200 import dist as MD
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.emu:
+        import emu_util
+
+        dist.init_process_group("gloo")
+        MD.init(0, args.grid, True, staged=True, lib_path=emu_util.EMU)
+    else:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        MD.init(local_rank, args.grid, True, staged=args.staged)
+    lib = M.grid._lib()
+    assert lib.mfb_dist_nranks() == world and lib.mfb_dist_rank() == rank
+
+    n, L, TOL = args.grid, 100.0, PC.TOL
+    N3, L3 = (n,) * 3, (L,) * 3
+
+    # ---- slab bookkeeping == fftw_mpi_local_size_3d_transposed for divisible sizes
+    g0 = M.Grid_FFT(N3, L3)
+    assert g0.is_distributed()
+    assert (g0.local_0_start_, g0.local_0_size_) == (rank * n // world, n // world)
+    assert (g0.local_1_start_, g0.local_1_size_) == (rank * n // world, n // world)
+
+    # ---- FFT round trip against numpy
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(N3)
+    g0.set_real(x)
+    g0.FourierTransformForward()
+    ref = np.fft.rfftn(x) / np.sqrt(float(n) ** 3)
+    assert PC.relerr(MD.gather_kspace(g0), ref) < TOL
+    assert g0.size(0) == n // world and g0.size(1) == n
+    g0.FourierTransformBackward()
+    assert PC.relerr(MD.gather_real(g0), x) < TOL
+
+    # ---- reductions (Allreduce inside), DC removal in both spaces, shift_field
+    assert abs(g0.mean() - x.mean()) < 1e-13 and abs(g0.std() - x.std()) < 1e-12
+    g0.zero_DC_mode()
+    assert abs(MD.gather_real(g0).mean()) < 1e-14
+    g0.set_real(x)
+    g0.shift_field((0.5, 0.25, 0.5))
+    gs = O.GridSpec(n, L)
+    assert PC.relerr(MD.gather_real(g0), O.shift_field_r(gs, x, (0.5, 0.25, 0.5))) < TOL
+
+    # ---- named products, Nyquist-carrying input (MPI pad semantics)
+    g, W, Wc, phi = PC.noise_and_phi(n, L, 9, False)
+    _, _, _, psi = PC.noise_and_phi(n, L, 10, False)
+    cv = O.OrszagConvolver(g)
+    P, Q = M.Grid_FFT(N3, L3), M.Grid_FFT(N3, L3)
+    out = M.Grid_FFT(N3, L3, True, M.kspace_id)
+    P.set_kspace(phi)
+    Q.set_kspace(psi)
+    C = M.OrszagConvolver(N3, L3)
+    op = M.op
+    ref = cv.convolve_Hessians(phi, (0, 1), psi, (1, 2))
+    C.convolve_Hessians(P, (0, 1), Q, (1, 2), op.assign_to(out))
+    got = MD.gather_kspace(out)
+    assert PC.relerr(got, ref) < TOL
+    h = n // 2
+    assert not got[h].any() and not got[:, h].any() and not got[:, :, h].any()
+    ref = ref + cv.convolve_SumOfHessians(phi, (0, 0), psi, (1, 1), (2, 2))
+    C.convolve_SumOfHessians(P, (0, 0), Q, (1, 1), (2, 2), op.add_to(out))
+    ref = ref + (-5.0 / 7.0) * cv.convolve_Hessians3(phi, (0, 0), psi, (0, 2), phi, (2, 2))
+    C.convolve_Hessians(P, (0, 0), Q, (0, 2), P, (2, 2), op.multiply_add_to(out, -5.0 / 7.0))
+    assert PC.relerr(MD.gather_kspace(out), ref) < TOL
+    ref = cv.convolve_Gradient_and_Hessian(phi, 1, psi, (0, 2))
+    C.convolve_Gradient_and_Hessian(P, (1,), Q, (0, 2), op.assign_to(out))
+    assert PC.relerr(MD.gather_kspace(out), ref) < TOL
+    del P, Q, out, C
+
+    # ---- whole pipelines vs the oracle
+    for order, lattice, real64 in [(1, "sc", True), (3, args.lattice, True), (2, "sc", False)]:
+        Dp, vfac = 0.0257, 396.69
+        lunit, vunit = L, L / np.sqrt(1 / 51.0)
+        g, W, Wc, phi = PC.noise_and_phi(n, L, 21)
+        amp = O.power_law_amplitude()
+        ref = O.run_pipeline(n, L, Wc, amp, order, Dp, vfac, lattice, lunit, vunit, real64, ids64=True)
+        cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad=lattice, Dplus0=Dp, vfac=vfac,
+                           lunit=lunit, vunit=vunit, real64=real64, ids64=True)
+        pl = M.LPTPipeline(cfg)
+        pl.set_noise_k(W)
+        pl.condition_noise()
+        parts = pl.run_device(O.radial_table(g, amp), particles=True)
+        assert PC.relerr(MD.gather_kspace(pl.phi), ref["pots"]["phi"]) < TOL
+        if order > 2:
+            assert PC.relerr(MD.gather_kspace(pl.phi3), ref["pots"]["phi3"]) < 10 * TOL
+            for d in range(3):
+                assert PC.relerr(MD.gather_kspace(pl.A3[d]), ref["pots"]["A3"][d]) < 10 * TOL
+        host = parts.download()
+        # reference ordering: shift iload occupies [iload*N^3, (iload+1)*N^3); this rank holds planes off0..off0+l0
+        nsh = 1 << O.LATTICE_TYPES[lattice]
+        ncell, l0, o0 = n ** 3, n // world, rank * (n // world)
+        sel = np.concatenate([np.arange(s * ncell + o0 * n * n, s * ncell + (o0 + l0) * n * n) for s in range(nsh)])
+        assert np.array_equal(host["ids"], ref["ids"][sel])
+        maxpsi = max(np.abs(ref["fields"]["d" + c]).max() for c in "xyz")
+        maxv = max(np.abs(ref["fields"]["v" + c]).max() for c in "xyz")
+        if real64:
+            assert np.abs(host["pos"] - ref["pos"][sel]).max() < 1e-11 * maxpsi
+            assert np.abs(host["vel"] - ref["vel"][sel]).max() < 1e-11 * maxv
+        else:
+            assert (host["pos"] == ref["pos"][sel]).mean() > 0.999
+            assert np.allclose(host["vel"], ref["vel"][sel], rtol=1e-6, atol=1e-6 * maxv)
+        del pl, parts
+    MD.check()
+    nex = lib.mfb_dist_exchanges()
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_worker ok: world={world} grid={n} exchanges={nex} mode="
+              f"{'emu+gloo staged' if args.emu else ('nccl staged' if args.staged else 'peer-memory fused')}")
+    MD.shutdown()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,27 @@
+"""Multi-GPU parity (needs >= 2 B200s on the box; skipped otherwise): the slab-decomposed pipeline with the
+exchange fused into the FFT passes over peer memory, against the single-process CPU oracle - the analogue of
+the reference's tests/scripts/test_mpi_consistency.sh (1/2/4 ranks must agree)."""
+import pytest
+
+from test_dist_gloo import run_world
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_pipeline_peer_memory(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    run_world(world, ["--grid", "64", "--lattice", "bcc"])
+
+
+def test_slab_pipeline_nccl_staged():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, ["--grid", "64", "--lattice", "sc", "--staged"])

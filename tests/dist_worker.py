@@ -43,7 +43,7 @@ def main():
         MD.init(0, args.grid, True, staged=True, lib_path=emu_util.EMU)
     else:
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device(f"cuda:{local_rank}"))  # gloo carries the host-side gathers of the checks
         MD.init(local_rank, args.grid, True, staged=args.staged)
     lib = M.grid._lib()
     assert lib.mfb_dist_nranks() == world and lib.mfb_dist_rank() == rank

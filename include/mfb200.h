@@ -44,6 +44,7 @@ int mfb_synchronize(void);
 void* mfb_stream(void);              /* the cudaStream_t all work is issued on */
 long long mfb_kernel_launches(void); /* number of kernels launched so far (bench.py gpu_launches) */
 int mfb_supported_fft_size(int n);   /* 1 if an FFT plan exists for line length n */
+int mfb_set_option(const char* name, int value); /* tuning switches, e.g. "strided_v2" = 0/1 (kernel generation) */
 
 /* per-role device timing (CUDA events on the library stream around every kernel launch); the reference's
    analogue are the "took : ...s" stage timers (src/ic_generator.cc:470,500,528,540,557) */

@@ -31,6 +31,7 @@ def _declare(lib):
         "mfb_stream": (vp, []),
         "mfb_kernel_launches": (C.c_longlong, []),
         "mfb_supported_fft_size": (i, [i]),
+        "mfb_set_option": (i, [C.c_char_p, i]),
         "mfb_profile_enable": (i, [i]),
         "mfb_profile_reset": (i, []),
         "mfb_profile_num_roles": (i, []),

@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "fft_kernels.cuh"
+#include "fft_kernels2.cuh"
+#include "fft_kernels_z2.cuh"
 #include "grid_ops.cuh"
 #include "mfb_internal.h"
 #include "../../include/mfb200.h"
@@ -187,7 +189,88 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     MFB_LAUNCH(strided_pass_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, a, tw);
     check_launch("strided_pass_kernel");
 }
+// second-generation plans (fft_kernels2.cuh).  "B": first radix carries the factor 3 (pad N -> 3N/2 resolved at
+// compile time; also used for plain passes); "F": last radix carries it (truncate 3N/2 -> N).
+#define MFB_FOR_EACH_PLAN2_B(X)   \
+    X(32, 4, 16, 1, 8, 4)            \
+    X(48, 4, 16, 1, 6, 8)            \
+    X(64, 8, 16, 1, 8, 8)            \
+    X(96, 4, 16, 1, 12, 8)           \
+    X(128, 8, 16, 1, 16, 8)          \
+    X(192, 4, 16, 1, 12, 16)         \
+    X(256, 16, 8, 2, 16, 16)         \
+    X(384, 16, 8, 2, 6, 8, 8)        \
+    X(512, 32, 8, 2, 8, 8, 8)        \
+    X(768, 32, 8, 2, 12, 8, 8)       \
+    X(1024, 64, 8, 1, 16, 8, 8)      \
+    X(1536, 64, 8, 1, 12, 16, 8)     \
+    X(2048, 64, 4, 1, 16, 16, 8)     \
+    X(3072, 64, 4, 1, 12, 16, 16)
+#define MFB_FOR_EACH_PLAN2_F(X)   \
+    X(48, 4, 16, 1, 8, 6)            \
+    X(96, 4, 16, 1, 8, 12)           \
+    X(192, 4, 16, 1, 16, 12)         \
+    X(384, 16, 8, 2, 8, 8, 6)        \
+    X(768, 32, 8, 2, 8, 8, 12)       \
+    X(1536, 64, 4, 2, 8, 16, 12)     \
+    X(3072, 64, 4, 1, 16, 16, 12)
+// fused z pass of the dealiased product (fft_kernels_z2.cuh): N, threads per row, rows per CTA, min CTAs/SM, radices
+// (first radix a multiple of 3, last radix 8: conflict-free padded lines)
+#define MFB_FOR_EACH_PLANZ(X)     \
+    X(48, 32, 2, 1, 6, 8)         \
+    X(96, 32, 2, 1, 12, 8)        \
+    X(192, 32, 2, 1, 6, 4, 8)     \
+    X(384, 32, 2, 1, 6, 8, 8)     \
+    X(768, 64, 2, 1, 12, 8, 8)    \
+    X(1536, 64, 2, 1, 12, 16, 8)  \
+    X(3072, 128, 2, 1, 6, 8, 8, 8)
+
+template <class P, int MODE, int MINB> void launch_strided2_t(const StridedArgs& a, int role) {
+    static bool done = false;
+    optin_smem(strided2_kernel<P, MODE, MINB>, P::SMEM_BYTES, done);
+    const int tiles = (a.nz + P::T - 1) / P::T;
+    const unsigned grid = unsigned(a.na) * unsigned(tiles);
+    if (grid == 0) return;
+    const double2* tw = twiddles(P::N);
+    const double lines = double(a.na - (a.a_skip >= 0 ? 1 : 0)) * double(a.nz_fft);
+    const double bytes = lines * 16.0 * (double(a.n_in) + double(a.n_out) * (a.op == OP_ASSIGN ? 1.0 : 2.0));
+    RoleScope rs(role, bytes);
+    MFB_LAUNCH((strided2_kernel<P, MODE, MINB>), grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, a, tw);
+    check_launch("strided2_kernel");
+}
+// returns false if the second-generation kernel does not cover this pass (caller falls back to the first)
+static bool launch_strided2(int n, const StridedArgs& a, int role) {
+    int mode;
+    if (a.n_in == n && a.n_out == n) mode = SM_PLAIN;
+    else if (a.n_out == n && 3 * a.n_in == 2 * n) mode = SM_PAD;
+    else if (a.n_in == n && 3 * a.n_out == 2 * n) mode = SM_TRUNC;
+    else return false;
+    if (a.f.enabled && mode != SM_PAD) return false;
+    if (mode == SM_TRUNC) {
+        switch (n) {
+#define X(N_, TPL_, T_, MINB_, ...)                                      \
+    case N_: launch_strided2_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_TRUNC, MINB_>(a, role); return true;
+            MFB_FOR_EACH_PLAN2_F(X)
+#undef X
+            default: return false;
+        }
+    }
+    switch (n) {
+#define X(N_, TPL_, T_, MINB_, ...)                                                  \
+    case N_:                                                                         \
+        if (mode == SM_PAD) {                                                        \
+            if constexpr (N_ % 3 == 0) launch_strided2_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_PAD, MINB_>(a, role); \
+            else return false;                                                       \
+        } else launch_strided2_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_PLAIN, MINB_>(a, role); \
+        return true;
+        MFB_FOR_EACH_PLAN2_B(X)
+#undef X
+        default: return false;
+    }
+}
+
 void launch_strided(int n, const StridedArgs& a, int role) {
+    if (g_ctx.strided_v2 && launch_strided2(n, a, role)) return;
     switch (n) {
 #define X(N_, TPL_, T_, ...)                              \
     case N_: {                                            \
@@ -242,8 +325,31 @@ void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t 
                scale, tw);
     check_launch("z_conv_kernel");
 }
+template <class P, int RPC, int MINB>
+void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale) {
+    static bool done = false;
+    constexpr size_t smem = z_conv2_smem<P, RPC>();
+    optin_smem(z_conv2_kernel<P, RPC, MINB>, smem, done);
+    const unsigned grid = unsigned((nrows + RPC - 1) / RPC);
+    const double2* tw = twiddles(P::N);
+    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * 3.0);
+    MFB_LAUNCH((z_conv2_kernel<P, RPC, MINB>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw);
+    check_launch("z_conv2_kernel");
+}
+static bool launch_zconv2(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
+                          long nrows, int nzin, double scale) {
+    if (3 * nzin != n) return false;
+    switch (n) {
+#define X(N_, TPL_, RPC_, MINB_, ...)                                                                          \
+    case N_: launch_zconv2_t<Plan<N_, TPL_, 2, __VA_ARGS__>, RPC_, MINB_>(A, B, out, in_pitch, out_pitch, nrows, scale); return true;
+        MFB_FOR_EACH_PLANZ(X)
+#undef X
+        default: return false;
+    }
+}
 void launch_zconv(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
                   int nzin, double scale) {
+    if (g_ctx.zconv_v2 && launch_zconv2(n, A, B, out, in_pitch, out_pitch, nrows, nzin, scale)) return;
     switch (n) {
 #define X(N_, TPL_, T_, ...)                                                   \
     case N_: {                                                                 \
@@ -713,6 +819,14 @@ int mfb_synchronize(void) {
 void* mfb_stream(void) { return (void*)g_ctx.stream; }
 long long mfb_kernel_launches(void) { return g_ctx.launches; }
 int mfb_supported_fft_size(int n) { return supported_size(n) ? 1 : 0; }
+/* tuning switches (tests compare kernel generations): "strided_v2" = 0/1 */
+int mfb_set_option(const char* name, int value) {
+    MFB_TRY
+    if (std::string(name) == "strided_v2") g_ctx.strided_v2 = value != 0;
+    else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
+    else throw std::runtime_error(std::string("unknown option ") + name);
+    MFB_CATCH
+}
 
 // ---------------------------------------------------------------- profiling
 int mfb_profile_enable(int on) {

@@ -77,6 +77,8 @@ struct Context {
     double* table[2] = {nullptr, nullptr};  // radial tables (amplitude, vbc)
     size_t table_cap[2] = {0, 0};
     long long launches = 0;
+    bool strided_v2 = true;  // second-generation strided pass (fft_kernels2.cuh)
+    bool zconv_v2 = true;    // second-generation fused z pass (fft_kernels_z2.cuh)
     // optional per-role device timing (cudaEvents on `stream` around every launch)
     bool profiling = false;
     int cur_role = ROLE_ELEMENTWISE;

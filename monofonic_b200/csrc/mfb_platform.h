@@ -45,7 +45,15 @@ MFB_D double mfb_ld_stream1(const double* p) {
     asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, the thread is not stalled
+MFB_D void mfb_cp_async16(double2* smem_dst, const double2* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+MFB_D void mfb_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 #else
+inline void mfb_cp_async16(double2* d, const double2* s) { *d = *s; }
+inline void mfb_cp_async_wait_all() {}
 inline double2 mfb_ld_stream(const double2* p) { return *p; }
 inline void mfb_st_stream(double2* p, double2 v) { *p = v; }
 inline double mfb_ld_stream1(const double* p) { return *p; }

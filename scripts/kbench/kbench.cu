@@ -1,0 +1,229 @@
+// kbench.cu - micro-benchmark of FFT pass kernel variants on synthetic data (development tool, not product).
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --expt-relaxed-constexpr -I../../monofonic_b200/csrc kbench.cu -o kbench
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <string>
+#include "fft_kernels2.cuh"
+#include "fft_kernels_z2.cuh"
+using namespace mfb;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+static std::vector<double2> make_tw(int n) {
+    std::vector<double2> h(n);
+    for (int m = 0; m < n; ++m) { long double a = -2.0L * 3.14159265358979323846264338327950288L * m / n; h[m].x = (double)cosl(a); h[m].y = (double)sinl(a); }
+    return h;
+}
+__global__ void fill_kernel(double2* p, size_t n, unsigned seed) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        unsigned long long x = (i + 1) * 6364136223846793005ull + seed; x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 29;
+        p[i] = make_double2(double(int(x & 0xffff) - 32768) / 32768.0, double(int((x >> 20) & 0xffff) - 32768) / 32768.0);
+    }
+}
+__global__ void maxdiff_kernel(const double2* a, const double2* b, size_t n, double* out) {
+    double m = 0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        m = fmax(m, fmax(fabs(a[i].x - b[i].x), fabs(a[i].y - b[i].y)));
+    __shared__ double s[256];
+    s[threadIdx.x] = m; __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + k]); __syncthreads(); }
+    if (threadIdx.x == 0) atomicMax((unsigned long long*)out, __double_as_longlong(s[0]));  // non-negative doubles order like integers
+}
+
+struct Bench {
+    int n, n_small, nz, na, mode;  // mode: SM_PAD (n_small -> n) or SM_TRUNC (n -> n_small)
+    double2 *in, *out, *ref; double2* tw; double* dmax;
+    size_t in_elems, out_elems;
+    StridedArgs args() const {
+        StridedArgs a; memset(&a, 0, sizeof(a));
+        const int nin = (mode == SM_PAD) ? n_small : n, nout = (mode == SM_TRUNC) ? n_small : n;
+        a.in = in; a.out = out;
+        a.in_ps = nz; a.in_as = ptrdiff_t(nin) * nz;
+        a.out_ps = nz; a.out_as = ptrdiff_t(nout) * nz;
+        a.na = na; a.nz = nz; a.nz_fft = nz; a.n_in = nin; a.n_out = nout;
+        a.inverse = (mode == SM_PAD); a.scale = 1.0; a.op = OP_ASSIGN; a.a_skip = -1;
+        if (mode == SM_PAD) {  // an operand factor like the conv x pass (cost is part of the real kernel)
+            a.f.enabled = 1; a.f.a1 = 1; a.f.b1 = 1; a.f.a2 = -1; a.f.b2 = -1; a.f.c1 = -1.0; a.f.c2 = 0.0; a.f.imag = 0;
+            for (int d = 0; d < 3; ++d) { a.f.n[d] = n_small; a.f.kf[d] = 0.0628; }
+            a.pos_axis = 1; a.a_axis = 0;
+        }
+        return a;
+    }
+    double bytes() const { return 16.0 * (double(in_elems) + double(out_elems)); }
+};
+
+template <class K> static float time_kernel(K launch, int reps = 8) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) launch();
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaGetLastError());
+    return ms / reps;
+}
+static void report(Bench& B, const char* label, float ms, bool is_ref, int regs, int occ) {
+    double md = 0;
+    if (is_ref) CK(cudaMemcpy(B.ref, B.out, B.out_elems * 16, cudaMemcpyDeviceToDevice));
+    else {
+        CK(cudaMemset(B.dmax, 0, 8));
+        maxdiff_kernel<<<1184, 256>>>(B.out, B.ref, B.out_elems, B.dmax);
+        CK(cudaMemcpy(&md, B.dmax, 8, cudaMemcpyDeviceToHost));
+    }
+    printf("%-46s %8.3f ms %8.1f GB/s  regs %3d  CTA/SM %d  maxdiff %.2e\n", label, ms, B.bytes() / ms / 1e6, regs, occ, md);
+    fflush(stdout);
+}
+template <class P> static void run_v1(Bench& B, const char* label, bool is_ref) {
+    auto k = strided_pass_kernel<P>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM_BYTES));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::NTHREADS, P::SMEM_BYTES));
+    StridedArgs a = B.args();
+    const unsigned grid = unsigned(B.na) * unsigned((B.nz + P::T - 1) / P::T);
+    CK(cudaMemset(B.out, 0xff, B.out_elems * 16));
+    float ms = time_kernel([&] { k<<<grid, P::NTHREADS, P::SMEM_BYTES>>>(a, B.tw); });
+    report(B, label, ms, is_ref, fa.numRegs, occ);
+}
+template <class P, int MODE, int MINB> static void run_v2(Bench& B, const char* label) {
+    if (MODE != B.mode) return;
+    auto k = strided2_kernel<P, MODE, MINB>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM_BYTES));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::NTHREADS, P::SMEM_BYTES));
+    StridedArgs a = B.args();
+    const unsigned grid = unsigned(B.na) * unsigned((B.nz + P::T - 1) / P::T);
+    CK(cudaMemset(B.out, 0xff, B.out_elems * 16));
+    float ms = time_kernel([&] { k<<<grid, P::NTHREADS, P::SMEM_BYTES>>>(a, B.tw); });
+    report(B, label, ms, false, fa.numRegs, occ);
+}
+
+static Bench make_bench(int n, int mode, int na) {
+    Bench B; B.n = n; B.n_small = 2 * n / 3; B.nz = B.n_small / 2; B.na = na; B.mode = mode;
+    const size_t small = size_t(na) * B.n_small * B.nz, big = size_t(na) * n * B.nz;
+    B.in_elems = (mode == SM_PAD) ? small : big; B.out_elems = (mode == SM_PAD) ? big : small;
+    CK(cudaMalloc(&B.in, B.in_elems * 16)); CK(cudaMalloc(&B.out, B.out_elems * 16)); CK(cudaMalloc(&B.ref, B.out_elems * 16));
+    CK(cudaMalloc(&B.dmax, 8));
+    auto h = make_tw(n); CK(cudaMalloc(&B.tw, n * 16)); CK(cudaMemcpy(B.tw, h.data(), n * 16, cudaMemcpyHostToDevice));
+    fill_kernel<<<1184, 256>>>(B.in, B.in_elems, 1234u + n);
+    CK(cudaDeviceSynchronize());
+    printf("== n=%d %s  na=%d nz=%d  (%.2f GB in, %.2f GB out)\n", n, mode == SM_PAD ? "PAD y-bwd" : "TRUNC y-fwd", na, B.nz, B.in_elems * 16e-9, B.out_elems * 16e-9);
+    return B;
+}
+static void free_bench(Bench& B) { cudaFree(B.in); cudaFree(B.out); cudaFree(B.ref); cudaFree(B.tw); cudaFree(B.dmax); }
+
+
+// ------------------------------------------------------------------ fused z pass
+struct ZBench { int n, nz; long nrows; double2 *A, *B, *out, *ref, *tw; double* dmax; };
+static ZBench make_zbench(int n, long nrows) {
+    ZBench Z; Z.n = n; Z.nz = n / 3; Z.nrows = nrows;
+    const size_t e = size_t(nrows) * Z.nz;
+    CK(cudaMalloc(&Z.A, e * 16)); CK(cudaMalloc(&Z.B, e * 16)); CK(cudaMalloc(&Z.out, e * 16)); CK(cudaMalloc(&Z.ref, e * 16)); CK(cudaMalloc(&Z.dmax, 8));
+    auto h = make_tw(n); CK(cudaMalloc(&Z.tw, n * 16)); CK(cudaMemcpy(Z.tw, h.data(), n * 16, cudaMemcpyHostToDevice));
+    fill_kernel<<<1184, 256>>>(Z.A, e, 77u); fill_kernel<<<1184, 256>>>(Z.B, e, 99u);
+    CK(cudaDeviceSynchronize());
+    printf("== z_conv n=%d nrows=%ld nz=%d (%.2f GB per operand)\n", n, nrows, Z.nz, e * 16e-9);
+    return Z;
+}
+static void zreport(ZBench& Z, const char* label, float ms, bool is_ref, int regs, int occ, size_t smem) {
+    const size_t e = size_t(Z.nrows) * Z.nz;
+    double md = 0;
+    if (is_ref) CK(cudaMemcpy(Z.ref, Z.out, e * 16, cudaMemcpyDeviceToDevice));
+    else { CK(cudaMemset(Z.dmax, 0, 8)); maxdiff_kernel<<<1184, 256>>>(Z.out, Z.ref, e, Z.dmax); CK(cudaMemcpy(&md, Z.dmax, 8, cudaMemcpyDeviceToHost)); }
+    printf("%-50s %8.3f ms %8.1f GB/s  regs %3d  CTA/SM %d smem %3zu KB  maxdiff %.2e\n", label, ms, 3.0 * e * 16 / ms / 1e6, regs, occ, smem / 1024, md);
+    fflush(stdout);
+}
+template <class P> static void zrun_v1(ZBench& Z, const char* label) {
+    auto k = z_conv_kernel<P>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM_BYTES));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::NTHREADS, P::SMEM_BYTES));
+    const unsigned grid = unsigned((Z.nrows + P::T - 1) / P::T);
+    float ms = time_kernel([&] { k<<<grid, P::NTHREADS, P::SMEM_BYTES>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, Z.nz, 0.37, Z.tw); });
+    zreport(Z, label, ms, true, fa.numRegs, occ, P::SMEM_BYTES);
+}
+template <class P, int RPC, int MINB> static void zrun_v2(ZBench& Z, const char* label) {
+    auto k = z_conv2_kernel<P, RPC, MINB>;
+    constexpr size_t smem = z_conv2_smem<P, RPC>();
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::TPL * RPC, smem));
+    const unsigned grid = unsigned((Z.nrows + RPC - 1) / RPC);
+    CK(cudaMemset(Z.out, 0xff, size_t(Z.nrows) * Z.nz * 16));
+    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, Z.tw); });
+    zreport(Z, label, ms, false, fa.numRegs, occ, smem);
+}
+#define Z2(RPC, MINB, ...) zrun_v2<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z2 <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
+static void zbench_all(int which) {
+    if (which == 0 || which == 768) {
+        ZBench Z = make_zbench(768, 768L * 192);
+        zrun_v1<Plan<768, 32, 8, 12, 8, 8>>(Z, "v1 <768,32,8,12,8,8>");
+        Z2(2, 1, 768, 64, 2, 12, 8, 8); Z2(2, 4, 768, 64, 2, 12, 8, 8); Z2(2, 5, 768, 64, 2, 12, 8, 8);
+        Z2(2, 4, 768, 32, 2, 12, 8, 8); Z2(2, 8, 768, 32, 2, 12, 8, 8);
+        Z2(4, 2, 768, 32, 2, 12, 8, 8); Z2(4, 4, 768, 32, 2, 12, 8, 8);
+        Z2(4, 2, 768, 64, 2, 12, 8, 8); Z2(2, 3, 768, 96, 2, 12, 8, 8); Z2(2, 2, 768, 96, 2, 12, 8, 8);
+        Z2(2, 4, 768, 64, 2, 6, 4, 4, 8); Z2(2, 4, 768, 64, 2, 6, 16, 8); Z2(2, 5, 768, 64, 2, 12, 4, 4, 4);
+        Z2(8, 1, 768, 32, 2, 12, 8, 8); Z2(8, 1, 768, 64, 2, 12, 8, 8);
+    }
+    if (which == 0 || which == 1536) {
+        ZBench Z = make_zbench(1536, 1536L * 48);
+        zrun_v1<Plan<1536, 32, 8, 16, 12, 8>>(Z, "v1 <1536,32,8,16,12,8>");
+        Z2(2, 1, 1536, 64, 2, 12, 16, 8); Z2(2, 2, 1536, 64, 2, 12, 16, 8); Z2(2, 1, 1536, 128, 2, 12, 16, 8); Z2(2, 2, 1536, 128, 2, 12, 16, 8);
+        Z2(2, 2, 1536, 32, 2, 12, 16, 8); Z2(4, 1, 1536, 64, 2, 12, 16, 8); Z2(4, 1, 1536, 128, 2, 12, 16, 8);
+        Z2(2, 2, 1536, 64, 2, 6, 8, 4, 8); Z2(2, 2, 1536, 128, 2, 6, 8, 4, 8); Z2(2, 2, 1536, 192, 2, 6, 8, 4, 8);
+        Z2(2, 2, 1536, 64, 2, 12, 4, 4, 8); Z2(2, 2, 1536, 128, 2, 12, 4, 4, 8);
+    }
+}
+
+#define V2(MODE, MINB, ...) run_v2<Plan<__VA_ARGS__>, MODE, MINB>(B, "v2 <" #__VA_ARGS__ "> minb " #MINB)
+
+int main(int argc, char** argv) {
+    int which = argc > 1 ? atoi(argv[1]) : 0;
+    const char* what = argc > 2 ? argv[2] : "all";
+    if (!strcmp(what, "z") || !strcmp(what, "all")) zbench_all(which);
+    if (!strcmp(what, "z")) return 0;
+    if (which == 0 || which == 768) {
+        for (int mode : {SM_PAD, SM_TRUNC}) {
+            Bench B = make_bench(768, mode, 256);
+            run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 <768,32,8,12,8,8>", true);
+            V2(SM_PAD, 1, 768, 32, 8, 12, 8, 8);   V2(SM_PAD, 2, 768, 32, 8, 12, 8, 8);
+            V2(SM_PAD, 2, 768, 64, 8, 12, 8, 8);   V2(SM_PAD, 1, 768, 64, 8, 12, 8, 8);
+            V2(SM_PAD, 2, 768, 32, 4, 12, 8, 8);   V2(SM_PAD, 4, 768, 32, 4, 12, 8, 8);
+            V2(SM_PAD, 2, 768, 64, 4, 12, 8, 8);   V2(SM_PAD, 3, 768, 64, 4, 12, 8, 8);
+            V2(SM_PAD, 2, 768, 32, 8, 6, 8, 16);   V2(SM_PAD, 2, 768, 64, 8, 6, 16, 8);
+            V2(SM_PAD, 2, 768, 32, 8, 12, 16, 4);  V2(SM_PAD, 2, 768, 64, 8, 6, 8, 4, 4);
+            V2(SM_TRUNC, 1, 768, 32, 8, 8, 8, 12); V2(SM_TRUNC, 2, 768, 32, 8, 8, 8, 12);
+            V2(SM_TRUNC, 2, 768, 64, 8, 8, 8, 12); V2(SM_TRUNC, 1, 768, 64, 8, 8, 8, 12);
+            V2(SM_TRUNC, 2, 768, 32, 4, 8, 8, 12); V2(SM_TRUNC, 4, 768, 32, 4, 8, 8, 12);
+            V2(SM_TRUNC, 2, 768, 64, 4, 8, 8, 12); V2(SM_TRUNC, 3, 768, 64, 4, 8, 8, 12);
+            V2(SM_TRUNC, 2, 768, 32, 8, 16, 8, 6); V2(SM_TRUNC, 2, 768, 64, 8, 8, 16, 6);
+            V2(SM_TRUNC, 2, 768, 64, 8, 4, 4, 8, 6);
+            free_bench(B);
+        }
+    }
+    if (which == 0 || which == 1536) {
+        for (int mode : {SM_PAD, SM_TRUNC}) {
+            Bench B = make_bench(1536, mode, 96);
+            run_v1<Plan<1536, 32, 8, 16, 12, 8>>(B, "v1 <1536,32,8,16,12,8>", true);
+            V2(SM_PAD, 1, 1536, 32, 8, 12, 16, 8);  V2(SM_PAD, 1, 1536, 64, 8, 12, 16, 8);
+            V2(SM_PAD, 1, 1536, 32, 4, 12, 16, 8);  V2(SM_PAD, 2, 1536, 32, 4, 12, 16, 8);
+            V2(SM_PAD, 1, 1536, 64, 4, 12, 16, 8);  V2(SM_PAD, 2, 1536, 64, 4, 12, 16, 8);
+            V2(SM_PAD, 2, 1536, 128, 4, 12, 16, 8); V2(SM_PAD, 1, 1536, 128, 4, 12, 16, 8);
+            V2(SM_PAD, 2, 1536, 64, 4, 12, 8, 16);  V2(SM_PAD, 2, 1536, 64, 4, 6, 16, 16);
+            V2(SM_PAD, 2, 1536, 64, 4, 12, 8, 4, 4); V2(SM_PAD, 2, 1536, 128, 4, 12, 8, 4, 4);
+            V2(SM_PAD, 2, 1536, 64, 4, 6, 8, 8, 4);  V2(SM_PAD, 1, 1536, 128, 8, 6, 8, 8, 4);
+            V2(SM_TRUNC, 1, 1536, 32, 8, 8, 16, 12);  V2(SM_TRUNC, 1, 1536, 64, 8, 8, 16, 12);
+            V2(SM_TRUNC, 1, 1536, 32, 4, 8, 16, 12);  V2(SM_TRUNC, 2, 1536, 32, 4, 8, 16, 12);
+            V2(SM_TRUNC, 1, 1536, 64, 4, 8, 16, 12);  V2(SM_TRUNC, 2, 1536, 64, 4, 8, 16, 12);
+            V2(SM_TRUNC, 2, 1536, 128, 4, 8, 16, 12); V2(SM_TRUNC, 2, 1536, 64, 4, 16, 8, 12);
+            V2(SM_TRUNC, 2, 1536, 64, 4, 16, 16, 6);  V2(SM_TRUNC, 2, 1536, 64, 4, 4, 4, 8, 12);
+            V2(SM_TRUNC, 2, 1536, 128, 4, 4, 4, 8, 12); V2(SM_TRUNC, 2, 1536, 64, 4, 4, 8, 8, 6);
+            V2(SM_TRUNC, 1, 1536, 128, 8, 4, 8, 8, 6);
+            free_bench(B);
+        }
+    }
+    return 0;
+}

@@ -167,6 +167,16 @@ template <int... Rs> __host__ __device__ constexpr int pack_prod(int upto) {
     return p;
 }
 
+// element offset of stage s in the stage-major twiddle table (see Plan::tw2_off)
+template <int... Rs> __host__ __device__ constexpr int pack_tw2_off(int n, int s) {
+    int o = 0;
+    for (int i = 0; i < s; ++i) {
+        const int len = n / pack_prod<Rs...>(i), r = pack_get<Rs...>(i);
+        o += (r - 1) * (len / r);
+    }
+    return o;
+}
+
 template <int N_, int TPL_, int T_, int... Rs> struct Plan {
     static constexpr int N = N_;      // line length
     static constexpr int TPL = TPL_;  // threads per line
@@ -202,6 +212,12 @@ template <int N_, int TPL_, int T_, int... Rs> struct Plan {
         }
         return p;
     }
+    // Stage-major twiddle table ("tw2"): for every twiddled stage s the block [u-1][j] = exp(-2 pi i u j / len(s)),
+    // u = 1..radix(s)-1, j = 0..len(s)/radix(s)-1.  Lanes that work on consecutive butterflies j read consecutive
+    // 16-byte entries (one 128-byte wavefront per 8 lanes) instead of entries u*step apart in the plain table
+    // (one wavefront PER lane: the L1 data pipe was 89 % busy in the fused z pass, profiles/r01_ncu_z3_768.txt).
+    __host__ __device__ static constexpr int tw2_off(int s) { return pack_tw2_off<Rs...>(N_, s); }
+    static constexpr int TW2_ELEMS = pack_tw2_off<Rs...>(N_, int(sizeof...(Rs)) - 1);
     // swizzled shared-memory slot of (position, line)
     MFB_HD static int smem_addr(int pos, int line) {
         return pos * T + (line ^ ((pos + pos / M0) & (T - 1)));

@@ -23,7 +23,7 @@ enum StridedMode { SM_PLAIN = 0, SM_PAD = 1, SM_TRUNC = 2 };
 template <class P, int MODE, int s>
 MFB_D void strided2_mid_stage(double2* __restrict__ sm, const double2* __restrict__ tw, int line, int q) {
     constexpr int T = P::T;
-    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r, twstep = P::N / L;
+    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r;
 #pragma unroll 1
     for (int b = q; b < Bn; b += P::TPL) {
         const int blk = b / M, j = b - blk * M;
@@ -32,9 +32,9 @@ MFB_D void strided2_mid_stage(double2* __restrict__ sm, const double2* __restric
 #pragma unroll
         for (int t = 0; t < r; ++t) v[t] = sp[t * M * T];
         Dft<r>::run(v);
-        const double2* twp = tw + j * twstep;
+        const double2* twp = tw + P::tw2_off(s) + j;
 #pragma unroll
-        for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(twp + (u - 1) * (j * twstep)));
+        for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(twp + (u - 1) * M));
 #pragma unroll
         for (int u = 0; u < r; ++u) sp[u * M * T] = v[u];
     }
@@ -48,7 +48,7 @@ MFB_D void strided2_mid_stages(double2* __restrict__ sm, const double2* __restri
     }
 }
 
-template <class P, int MODE, int MINB>
+template <class P, int MODE, int MINB, bool BATCH0 = false>
 __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs A, const double2* __restrict__ tw) {
     MFB_DYN_SMEM(double2, sm);
     constexpr int N = P::N, T = P::T, S = P::S;
@@ -115,18 +115,23 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
         const double2* gin = A.in + ptrdiff_t(a) * A.in_as + iz;
         const ptrdiff_t gstep = ptrdiff_t(M) * A.in_ps;
         const bool use_f = A.f.enabled != 0, f_imag = A.f.imag != 0, inv = A.inverse != 0;
-#pragma unroll 1
-        for (int j = q; j < M; j += P::TPL) {
-            double2 v[r];
+        // global loads of one butterfly (zero legs are not loaded)
+        auto load = [&](int j, double2* v) {
             const double2* p = gin + ptrdiff_t(j) * A.in_ps;
             if constexpr (MODE == SM_PAD) {
                 // source line has 2r/3 * M samples; leg k of the source maps to leg t = k (k < r/3) or k + r/3
 #pragma unroll
                 for (int k = 0; k < 2 * K3; ++k) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int t = (k < K3) ? k : k + K3;
                     v[t] = fft_line ? mfb_ld_stream(p + ptrdiff_t(k) * gstep) : make_double2(0.0, 0.0);
                 }
+            } else {
+#pragma unroll
+                for (int t = 0; t < r; ++t) v[t] = fft_line ? mfb_ld_stream(p + ptrdiff_t(t) * gstep) : make_double2(0.0, 0.0);
+            }
+        };
+        auto process = [&](int j, double2* v) {
+            if constexpr (MODE == SM_PAD) {
 #pragma unroll
                 for (int t = K3; t < 2 * K3; ++t) v[t] = make_double2(0.0, 0.0);
                 if (j == 0) v[2 * K3] = make_double2(0.0, 0.0);  // the source's Nyquist sample is dropped (MPI pad semantics)
@@ -140,9 +145,6 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
                         v[t] = f_imag ? make_double2(-v[t].y * fac, v[t].x * fac) : make_double2(v[t].x * fac, v[t].y * fac);
                     }
                 }
-            } else {
-#pragma unroll
-                for (int t = 0; t < r; ++t) v[t] = fft_line ? mfb_ld_stream(p + ptrdiff_t(t) * gstep) : make_double2(0.0, 0.0);
             }
             if (inv) {
 #pragma unroll
@@ -150,10 +152,27 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
             }
             Dft<r>::run(v);
 #pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + u * j));
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
             double2* sp = sm + j * T + line;
 #pragma unroll
             for (int u = 0; u < r; ++u) sp[u * M * T] = v[u];
+        };
+        constexpr int PER0 = (M + P::TPL - 1) / P::TPL;
+        if constexpr (BATCH0 && PER0 == 2) {
+            // both butterflies' loads are issued before any arithmetic: twice the bytes in flight per thread
+            double2 va[r], vb[r];
+            const int j1 = q + P::TPL;
+            load(q, va);
+            if (j1 < M) load(j1, vb);
+            process(q, va);
+            if (j1 < M) process(j1, vb);
+        } else {
+#pragma unroll 1
+            for (int j = q; j < M; j += P::TPL) {
+                double2 v[r];
+                load(j, v);
+                process(j, v);
+            }
         }
     }
     // ================= middle stages: shared -> shared
@@ -168,12 +187,9 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
         const int op = A.op;
         const double al = (op == OP_ADD) ? 1.0 : ((op == OP_SUB) ? -1.0 : A.alpha);
         const ptrdiff_t ostep = ptrdiff_t(fs) * A.out_ps;
-        auto emit = [&](double2* p, double2 v) {
+        auto emit = [&](double2* p, double2 v, double2 o) {
             v = make_double2(v.x * sc, v.y * scy);
-            if (op != OP_ASSIGN) {
-                const double2 o = mfb_ld_stream(p);
-                v = make_double2(fma(al, v.x, o.x), fma(al, v.y, o.y));
-            }
+            if (op != OP_ASSIGN) v = make_double2(fma(al, v.x, o.x), fma(al, v.y, o.y));
             mfb_st_stream(p, v);
         };
 #pragma unroll 1
@@ -182,28 +198,42 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
             double2 v[r];
 #pragma unroll
             for (int t = 0; t < r; ++t) v[t] = sp[t * T];
-            Dft<r>::run(v);
             if (!fft_line) continue;
             const int k0 = P::freq_of_pos(b * r);  // < fs; output u has frequency k0 + u*fs
             if constexpr (MODE == SM_TRUNC) {
                 // keep u < r/3 (dst = k) and u >= 2r/3 (dst = k - N/3); dst == n_out/2 is defined to be zero
+                double2* p[2 * K3];
+                double2 o[2 * K3];
+#pragma unroll
+                for (int m = 0; m < 2 * K3; ++m)
+                    p[m] = routed ? optr(k0 + m * fs) : A.out + ooff + ptrdiff_t(k0) * A.out_ps + ptrdiff_t(m) * ostep;
+                if (op != OP_ASSIGN) {   // read-modify-write: all old values are requested before the butterfly
+#pragma unroll
+                    for (int m = 0; m < 2 * K3; ++m) o[m] = mfb_ld_stream(p[m]);
+                }
+                Dft<r>::run(v);
 #pragma unroll
                 for (int m = 0; m < 2 * K3; ++m) {
                     const int u = (m < K3) ? m : m + K3;
-                    const int dst = k0 + m * fs;
-                    double2* p = routed ? optr(dst) : A.out + ooff + ptrdiff_t(k0) * A.out_ps + ptrdiff_t(m) * ostep;
                     if (m == K3 && k0 == 0) {
-                        if (zf) mfb_st_stream(p, make_double2(0.0, 0.0));
+                        if (zf) mfb_st_stream(p[m], make_double2(0.0, 0.0));
                     } else {
-                        emit(p, v[u]);
+                        emit(p[m], v[u], o[m]);
                     }
                 }
             } else {
+                double2* p[r];
+                double2 o[r];
 #pragma unroll
-                for (int u = 0; u < r; ++u) {
-                    double2* p = routed ? optr(k0 + u * fs) : A.out + ooff + ptrdiff_t(k0) * A.out_ps + ptrdiff_t(u) * ostep;
-                    emit(p, v[u]);
+                for (int u = 0; u < r; ++u)
+                    p[u] = routed ? optr(k0 + u * fs) : A.out + ooff + ptrdiff_t(k0) * A.out_ps + ptrdiff_t(u) * ostep;
+                if (op != OP_ASSIGN) {
+#pragma unroll
+                    for (int u = 0; u < r; ++u) o[u] = mfb_ld_stream(p[u]);
                 }
+                Dft<r>::run(v);
+#pragma unroll
+                for (int u = 0; u < r; ++u) emit(p[u], v[u], o[u]);
             }
         }
     }

@@ -31,7 +31,7 @@ template <int M, int r> MFB_D int zleg(int base, int t) {
 
 // DIF stage s (s >= 1) of one line, NT threads
 template <class P, int s, int NT> MFB_D void z2_dif_stage(double2* __restrict__ ln, const double2* __restrict__ tw, int q) {
-    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r, twstep = P::N / L;
+    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r;
     constexpr bool innermost = (s == P::S - 1);
 #pragma unroll 1
     for (int b = q; b < Bn; b += NT) {
@@ -43,7 +43,7 @@ template <class P, int s, int NT> MFB_D void z2_dif_stage(double2* __restrict__ 
         Dft<r>::run(v);
         if constexpr (!innermost) {
 #pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + u * (j * twstep)));
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + P::tw2_off(s) + (u - 1) * M + j));
         }
 #pragma unroll
         for (int u = 0; u < r; ++u) sp[zleg<M, r>(base, u)] = v[u];
@@ -51,7 +51,7 @@ template <class P, int s, int NT> MFB_D void z2_dif_stage(double2* __restrict__ 
 }
 // DIT stage s (S-1 > s >= 1): twiddle, butterfly
 template <class P, int s, int NT> MFB_D void z2_dit_stage(double2* __restrict__ ln, const double2* __restrict__ tw, int q) {
-    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r, twstep = P::N / L;
+    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r;
 #pragma unroll 1
     for (int b = q; b < Bn; b += NT) {
         const int blk = b / M, j = b - blk * M, base = blk * L + j;
@@ -60,7 +60,7 @@ template <class P, int s, int NT> MFB_D void z2_dit_stage(double2* __restrict__ 
 #pragma unroll
         for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(base, t)];
 #pragma unroll
-        for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + u * (j * twstep)));
+        for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + P::tw2_off(s) + (u - 1) * M + j));
         Dft<r>::run(v);
 #pragma unroll
         for (int u = 0; u < r; ++u) sp[zleg<M, r>(base, u)] = v[u];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
             }
             Dft<r>::run(v);
 #pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + u * j));
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
             double2* sp = ln + zpad(j);
 #pragma unroll
             for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
 #pragma unroll
                 for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(j, t)];
 #pragma unroll
-                for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + u * j));
+                for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
                 Dft<r>::run(v);
 #pragma unroll
                 for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
@@ -197,6 +197,162 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
             const double2 zk = l0[zpad(k)];
             const double2 zm = l0[zpad((N - k) % N)];
             const long r1 = row0 + 2 * m, r2 = r1 + 1;
+            if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y)));
+            if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x)));
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Third step (z_conv3_kernel): the fused z pass is bound by shared-memory / L1 bandwidth (about 8600 16-byte
+// accesses per row at n = 768 against 512 + 256 HBM accesses), so
+//   * the middle DIF stages process BOTH rows of a product pair in one thread: each twiddle is fetched once;
+//   * the innermost DIF stage of both rows, the product and the innermost DIT stage of the packed pair are one
+//     register-resident step: the backward result is never written back and the product never stored.
+template <class P, int s, int NT> MFB_D void z3_dif_stage_pair(double2* __restrict__ l0, const double2* __restrict__ tw, int q) {
+    constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r;
+    constexpr int LW = zpad(P::N) + 1;
+#pragma unroll 1
+    for (int b = q; b < Bn; b += NT) {
+        const int blk = b / M, j = b - blk * M, base = blk * L + j;
+        double2 w[r];
+#pragma unroll
+        for (int u = 1; u < r; ++u) w[u] = __ldg(tw + P::tw2_off(s) + (u - 1) * M + j);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double2* sp = l0 + h * LW + zpad(base);
+            double2 v[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(base, t)];
+            Dft<r>::run(v);
+#pragma unroll
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], w[u]);
+#pragma unroll
+            for (int u = 0; u < r; ++u) sp[zleg<M, r>(base, u)] = v[u];
+        }
+    }
+}
+template <class P, int s, int NT> MFB_D void z3_dif_mid_pair(double2* l0, const double2* tw, int q) {
+    if constexpr (s < P::S - 1) {
+        __syncthreads();
+        z3_dif_stage_pair<P, s, NT>(l0, tw, q);
+        z3_dif_mid_pair<P, s + 1, NT>(l0, tw, q);
+    }
+}
+
+template <class P, int RPC, int MINB>
+__global__ void __launch_bounds__(P::TPL* RPC, MINB)
+    z_conv3_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
+                   ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N, S = P::S, TPL = P::TPL, NT = TPL * RPC, PT = 2 * TPL;
+    constexpr int NZ = N / 3;
+    constexpr int LW = zpad(N) + 1;
+    static_assert(P::radix(0) % 3 == 0, "the z pass needs a first radix that is a multiple of 3");
+    static_assert(RPC % 2 == 0 && S >= 2, "rows per CTA must be even");
+    double2* work = sm;
+    double2* raw = sm + RPC * LW;
+    const int tid = threadIdx.x;
+    const long row0 = long(blockIdx.x) * RPC;
+
+    for (int idx = tid; idx < RPC * 2 * NZ; idx += NT) {
+        const int o = idx / NZ, k = idx - o * NZ;
+        const long r = row0 + (o >> 1);
+        double2* d = raw + idx;
+        if (r < nrows) mfb_cp_async16(d, ((o & 1) ? Bin : Ain) + r * in_pitch + k);
+        else *d = make_double2(0.0, 0.0);
+    }
+    mfb_cp_async_wait_all();
+    __syncthreads();
+
+    // ---- DIF stage 0 per row: Hermitian extension of conj(A^ + i B^) built in the butterfly legs
+    {
+        const int l = tid / TPL, q = tid - l * TPL;
+        double2* ln = work + l * LW;
+        const double2* ra = raw + (2 * l) * NZ;
+        const double2* rb = ra + NZ;
+        constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
+#pragma unroll 1
+        for (int j = q; j < M; j += TPL) {
+            double2 v[r];
+#pragma unroll
+            for (int t = 0; t < K3; ++t) {
+                double2 x1 = ra[j + t * M], x2 = rb[j + t * M];
+                if (t == 0 && j == 0) { x1.y = 0.0; x2.y = 0.0; }
+                v[t] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
+            }
+#pragma unroll
+            for (int t = K3; t < 2 * K3; ++t) v[t] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int t = 2 * K3; t < r; ++t) {
+                const int k = (r - t) * M - j;
+                if (t == 2 * K3 && j == 0) { v[t] = make_double2(0.0, 0.0); continue; }
+                const double2 x1 = ra[k], x2 = rb[k];
+                v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
+            }
+            Dft<r>::run(v);
+#pragma unroll
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
+            double2* sp = ln + zpad(j);
+#pragma unroll
+            for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
+        }
+    }
+    // ---- per product pair from here on
+    const int m = tid / PT, q = tid - m * PT;
+    double2* l0 = work + (2 * m) * LW;
+    z3_dif_mid_pair<P, 1, PT>(l0, tw, q);
+    __syncthreads();
+    {   // innermost DIF stage of both rows -> product -> innermost DIT stage of the packed pair, in registers
+        constexpr int r = P::radix(S - 1), Bn = N / r;
+#pragma unroll 1
+        for (int b = q; b < Bn; b += PT) {
+            const int base = b * r;
+            double2* sp = l0 + zpad(base);
+            double2 v[r];
+            double p0[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) v[t] = sp[zleg<1, r>(base, t)];
+            Dft<r>::run(v);
+#pragma unroll
+            for (int t = 0; t < r; ++t) p0[t] = -v[t].x * v[t].y;  // a = Re, b = -Im (conj trick)
+#pragma unroll
+            for (int t = 0; t < r; ++t) v[t] = sp[LW + zleg<1, r>(base, t)];
+            Dft<r>::run(v);
+#pragma unroll
+            for (int t = 0; t < r; ++t) v[t] = make_double2(p0[t], -v[t].x * v[t].y);
+            Dft<r>::run(v);
+#pragma unroll
+            for (int u = 0; u < r; ++u) sp[zleg<1, r>(base, u)] = v[u];
+        }
+    }
+    z2_dit_mid<P, S - 2, PT>(l0, tw, q);
+    __syncthreads();
+    {
+        constexpr int r = P::radix(0), M = N / r;
+#pragma unroll 1
+        for (int j = q; j < M; j += PT) {
+            double2* sp = l0 + zpad(j);
+            double2 v[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(j, t)];
+#pragma unroll
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
+            Dft<r>::run(v);
+#pragma unroll
+            for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
+        }
+    }
+    __syncthreads();
+    {
+        const double h = 0.5 * scale;
+        for (int idx = tid; idx < (RPC / 2) * NZ; idx += NT) {
+            const int mm = idx / NZ, k = idx - mm * NZ;
+            const double2* lz = work + (2 * mm) * LW;
+            const double2 zk = lz[zpad(k)];
+            const double2 zm = lz[zpad((N - k) % N)];
+            const long r1 = row0 + 2 * mm, r2 = r1 + 1;
             if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y)));
             if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x)));
         }

@@ -155,6 +155,28 @@ const double2* twiddles(int n) {
     return d;
 }
 
+// stage-major twiddle table of a plan (Plan::tw2_off): [stage][u-1][j] = exp(-2 pi i u j / len(stage))
+template <class P> const double2* twiddles2() {
+    std::string key = std::to_string(P::N);
+    for (int s = 0; s < P::S; ++s) key += "." + std::to_string(P::radix(s));
+    auto it = g_ctx.tw2.find(key);
+    if (it != g_ctx.tw2.end()) return it->second;
+    std::vector<double2> h(P::TW2_ELEMS > 0 ? P::TW2_ELEMS : 1);
+    const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int s = 0; s + 1 < P::S; ++s) {
+        const int r = P::radix(s), L = P::len(s), M = L / r;
+        for (int u = 1; u < r; ++u)
+            for (int j = 0; j < M; ++j) {
+                const long double a = -tau * (long double)((long)u * j % L) / (long double)L;
+                h[P::tw2_off(s) + (u - 1) * M + j] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+    }
+    double2* d = (double2*)dev_alloc(sizeof(double2) * h.size());
+    cuda_check(cudaMemcpy(d, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice), "twiddle upload");
+    g_ctx.tw2[key] = d;
+    return d;
+}
+
 bool supported_size(int n) {
     switch (n) {
 #define X(N_, TPL_, T_, ...) case N_:
@@ -220,9 +242,9 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     X(48, 32, 2, 1, 6, 8)         \
     X(96, 32, 2, 1, 12, 8)        \
     X(192, 32, 2, 1, 6, 4, 8)     \
-    X(384, 32, 2, 1, 6, 8, 8)     \
-    X(768, 64, 2, 1, 12, 8, 8)    \
-    X(1536, 64, 2, 1, 12, 16, 8)  \
+    X(384, 32, 2, 4, 6, 8, 8)     \
+    X(768, 32, 2, 4, 12, 8, 8)    \
+    X(1536, 64, 2, 2, 12, 4, 4, 8) \
     X(3072, 128, 2, 1, 6, 8, 8, 8)
 
 template <class P, int MODE, int MINB> void launch_strided2_t(const StridedArgs& a, int role) {
@@ -231,7 +253,7 @@ template <class P, int MODE, int MINB> void launch_strided2_t(const StridedArgs&
     const int tiles = (a.nz + P::T - 1) / P::T;
     const unsigned grid = unsigned(a.na) * unsigned(tiles);
     if (grid == 0) return;
-    const double2* tw = twiddles(P::N);
+    const double2* tw = twiddles2<P>();
     const double lines = double(a.na - (a.a_skip >= 0 ? 1 : 0)) * double(a.nz_fft);
     const double bytes = lines * 16.0 * (double(a.n_in) + double(a.n_out) * (a.op == OP_ASSIGN ? 1.0 : 2.0));
     RoleScope rs(role, bytes);
@@ -329,12 +351,12 @@ template <class P, int RPC, int MINB>
 void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale) {
     static bool done = false;
     constexpr size_t smem = z_conv2_smem<P, RPC>();
-    optin_smem(z_conv2_kernel<P, RPC, MINB>, smem, done);
+    optin_smem(z_conv3_kernel<P, RPC, MINB>, smem, done);
     const unsigned grid = unsigned((nrows + RPC - 1) / RPC);
-    const double2* tw = twiddles(P::N);
+    const double2* tw = twiddles2<P>();
     RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * 3.0);
-    MFB_LAUNCH((z_conv2_kernel<P, RPC, MINB>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw);
-    check_launch("z_conv2_kernel");
+    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw);
+    check_launch("z_conv3_kernel");
 }
 static bool launch_zconv2(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
                           long nrows, int nzin, double scale) {
@@ -805,6 +827,8 @@ int mfb_finalize(void) {
     cudaStreamSynchronize(g_ctx.stream);
     for (auto& kv : g_ctx.tw) cudaFree(kv.second);
     g_ctx.tw.clear();
+    for (auto& kv : g_ctx.tw2) cudaFree(kv.second);
+    g_ctx.tw2.clear();
     if (g_ctx.partial) cudaFree(g_ctx.partial);
     g_ctx.partial = nullptr; g_ctx.partial_cap = 0;
     cudaStreamDestroy(g_ctx.stream);

@@ -72,6 +72,7 @@ struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;
     std::map<int, double2*> tw;  // twiddle tables exp(-2 pi i m/n)
+    std::map<std::string, double2*> tw2;  // stage-major twiddle tables per plan (Plan::tw2_off)
     double* partial = nullptr;   // reduction scratch
     size_t partial_cap = 0;
     double* table[2] = {nullptr, nullptr};  // radial tables (amplitude, vbc)

@@ -17,6 +17,20 @@ static std::vector<double2> make_tw(int n) {
     for (int m = 0; m < n; ++m) { long double a = -2.0L * 3.14159265358979323846264338327950288L * m / n; h[m].x = (double)cosl(a); h[m].y = (double)sinl(a); }
     return h;
 }
+template <class P> static double2* make_tw2() {
+    std::vector<double2> h(P::TW2_ELEMS > 0 ? P::TW2_ELEMS : 1);
+    const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int s = 0; s + 1 < P::S; ++s) {
+        const int r = P::radix(s), L = P::len(s), M = L / r;
+        for (int u = 1; u < r; ++u)
+            for (int j = 0; j < M; ++j) {
+                const long double a = -tau * (long double)((long)u * j % L) / (long double)L;
+                h[P::tw2_off(s) + (u - 1) * M + j] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+    }
+    double2* d; CK(cudaMalloc(&d, h.size() * 16)); CK(cudaMemcpy(d, h.data(), h.size() * 16, cudaMemcpyHostToDevice));
+    return d;
+}
 __global__ void fill_kernel(double2* p, size_t n, unsigned seed) {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         unsigned long long x = (i + 1) * 6364136223846793005ull + seed; x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 29;
@@ -34,6 +48,7 @@ __global__ void maxdiff_kernel(const double2* a, const double2* b, size_t n, dou
 }
 
 struct Bench {
+    int rmw = 0;
     int n, n_small, nz, na, mode;  // mode: SM_PAD (n_small -> n) or SM_TRUNC (n -> n_small)
     double2 *in, *out, *ref; double2* tw; double* dmax;
     size_t in_elems, out_elems;
@@ -44,7 +59,7 @@ struct Bench {
         a.in_ps = nz; a.in_as = ptrdiff_t(nin) * nz;
         a.out_ps = nz; a.out_as = ptrdiff_t(nout) * nz;
         a.na = na; a.nz = nz; a.nz_fft = nz; a.n_in = nin; a.n_out = nout;
-        a.inverse = (mode == SM_PAD); a.scale = 1.0; a.op = OP_ASSIGN; a.a_skip = -1;
+        a.inverse = (mode == SM_PAD); a.scale = 1.0; a.op = rmw ? OP_ADD : OP_ASSIGN; a.a_skip = -1;
         if (mode == SM_PAD) {  // an operand factor like the conv x pass (cost is part of the real kernel)
             a.f.enabled = 1; a.f.a1 = 1; a.f.b1 = 1; a.f.a2 = -1; a.f.b2 = -1; a.f.c1 = -1.0; a.f.c2 = 0.0; a.f.imag = 0;
             for (int d = 0; d < 3; ++d) { a.f.n[d] = n_small; a.f.kf[d] = 0.0628; }
@@ -88,17 +103,19 @@ template <class P> static void run_v1(Bench& B, const char* label, bool is_ref) 
     float ms = time_kernel([&] { k<<<grid, P::NTHREADS, P::SMEM_BYTES>>>(a, B.tw); });
     report(B, label, ms, is_ref, fa.numRegs, occ);
 }
-template <class P, int MODE, int MINB> static void run_v2(Bench& B, const char* label) {
+template <class P, int MODE, int MINB, bool BATCH0 = false> static void run_v2(Bench& B, const char* label) {
     if (MODE != B.mode) return;
-    auto k = strided2_kernel<P, MODE, MINB>;
+    auto k = strided2_kernel<P, MODE, MINB, BATCH0>;
+    double2* tw2 = make_tw2<P>();
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM_BYTES));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::NTHREADS, P::SMEM_BYTES));
     StridedArgs a = B.args();
     const unsigned grid = unsigned(B.na) * unsigned((B.nz + P::T - 1) / P::T);
     CK(cudaMemset(B.out, 0xff, B.out_elems * 16));
-    float ms = time_kernel([&] { k<<<grid, P::NTHREADS, P::SMEM_BYTES>>>(a, B.tw); });
+    float ms = time_kernel([&] { k<<<grid, P::NTHREADS, P::SMEM_BYTES>>>(a, tw2); });
     report(B, label, ms, false, fa.numRegs, occ);
+    cudaFree(tw2);
 }
 
 static Bench make_bench(int n, int mode, int na) {
@@ -147,14 +164,16 @@ template <class P> static void zrun_v1(ZBench& Z, const char* label) {
 }
 template <class P, int RPC, int MINB> static void zrun_v2(ZBench& Z, const char* label) {
     auto k = z_conv2_kernel<P, RPC, MINB>;
+    double2* tw2 = make_tw2<P>();
     constexpr size_t smem = z_conv2_smem<P, RPC>();
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::TPL * RPC, smem));
     const unsigned grid = unsigned((Z.nrows + RPC - 1) / RPC);
     CK(cudaMemset(Z.out, 0xff, size_t(Z.nrows) * Z.nz * 16));
-    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, Z.tw); });
+    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, tw2); });
     zreport(Z, label, ms, false, fa.numRegs, occ, smem);
+    cudaFree(tw2);
 }
 #define Z2(RPC, MINB, ...) zrun_v2<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z2 <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
 static void zbench_all(int which) {
@@ -178,13 +197,76 @@ static void zbench_all(int which) {
     }
 }
 
-#define V2(MODE, MINB, ...) run_v2<Plan<__VA_ARGS__>, MODE, MINB>(B, "v2 <" #__VA_ARGS__ "> minb " #MINB)
+template <class P, int RPC, int MINB> static void zrun_v3(ZBench& Z, const char* label) {
+    auto k = z_conv3_kernel<P, RPC, MINB>;
+    double2* tw2 = make_tw2<P>();
+    constexpr size_t smem = z_conv2_smem<P, RPC>();
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::TPL * RPC, smem));
+    const unsigned grid = unsigned((Z.nrows + RPC - 1) / RPC);
+    CK(cudaMemset(Z.out, 0xff, size_t(Z.nrows) * Z.nz * 16));
+    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, tw2); });
+    zreport(Z, label, ms, false, fa.numRegs, occ, smem);
+    cudaFree(tw2);
+}
+#define Z3(RPC, MINB, ...) zrun_v3<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z3 <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
+static void zbench3(int which) {
+    if (which == 0 || which == 768) {
+        ZBench Z = make_zbench(768, 768L * 192);
+        zrun_v1<Plan<768, 32, 8, 12, 8, 8>>(Z, "v1 <768,32,8,12,8,8>");
+        Z2(2, 4, 768, 32, 2, 12, 8, 8);
+        Z3(2, 4, 768, 32, 2, 12, 8, 8); Z3(2, 5, 768, 32, 2, 12, 8, 8); Z3(2, 3, 768, 32, 2, 12, 8, 8);
+        Z3(2, 4, 768, 64, 2, 12, 8, 8); Z3(2, 3, 768, 64, 2, 12, 8, 8); Z3(2, 5, 768, 64, 2, 12, 8, 8);
+        Z3(4, 2, 768, 32, 2, 12, 8, 8); Z3(4, 2, 768, 64, 2, 12, 8, 8);
+        Z3(2, 4, 768, 32, 2, 6, 16, 8); Z3(2, 4, 768, 64, 2, 6, 16, 8); Z3(2, 4, 768, 48, 2, 12, 8, 8);
+    }
+    if (which == 0 || which == 1536) {
+        ZBench Z = make_zbench(1536, 1536L * 48);
+        zrun_v1<Plan<1536, 32, 8, 16, 12, 8>>(Z, "v1 <1536,32,8,16,12,8>");
+        Z2(2, 2, 1536, 64, 2, 12, 4, 4, 8);
+        Z3(2, 2, 1536, 64, 2, 12, 4, 4, 8); Z3(2, 2, 1536, 32, 2, 12, 4, 4, 8); Z3(2, 2, 1536, 128, 2, 12, 4, 4, 8);
+        Z3(2, 2, 1536, 64, 2, 12, 16, 8); Z3(2, 2, 1536, 128, 2, 12, 16, 8); Z3(2, 1, 1536, 64, 2, 12, 16, 8);
+        Z3(2, 2, 1536, 64, 2, 6, 8, 4, 8); Z3(2, 2, 1536, 64, 2, 12, 8, 2, 8); Z3(2, 2, 1536, 96, 2, 12, 16, 8);
+    }
+}
 
+#define V2(MODE, MINB, ...) run_v2<Plan<__VA_ARGS__>, MODE, MINB>(B, "v2 <" #__VA_ARGS__ "> minb " #MINB)
+#define V2B(MODE, MINB, ...) run_v2<Plan<__VA_ARGS__>, MODE, MINB, true>(B, "v2 batch0 <" #__VA_ARGS__ "> minb " #MINB)
+
+static void sbench2(int which) {
+    if (which == 0 || which == 768) {
+        for (int mode : {SM_PAD, SM_TRUNC}) {
+            Bench B = make_bench(768, mode, 256);
+            run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 <768,32,8,12,8,8>", true);
+            V2(SM_PAD, 2, 768, 32, 8, 12, 8, 8); V2B(SM_PAD, 2, 768, 32, 8, 12, 8, 8); V2B(SM_PAD, 1, 768, 32, 8, 12, 8, 8);
+            V2B(SM_PAD, 2, 768, 32, 8, 6, 16, 8); V2B(SM_PAD, 4, 768, 32, 4, 12, 8, 8); V2B(SM_PAD, 2, 768, 16, 8, 12, 8, 8);
+            V2(SM_TRUNC, 2, 768, 32, 8, 8, 8, 12); V2B(SM_TRUNC, 2, 768, 32, 8, 8, 8, 12); V2B(SM_TRUNC, 2, 768, 48, 8, 8, 8, 12);
+            if (mode == SM_TRUNC) { B.rmw = 1; printf("  -- RMW (op ADD)\n"); run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 rmw", true); V2(SM_TRUNC, 2, 768, 32, 8, 8, 8, 12); V2B(SM_TRUNC, 2, 768, 32, 8, 8, 8, 12); }
+            free_bench(B);
+        }
+    }
+    if (which == 0 || which == 1536) {
+        for (int mode : {SM_PAD, SM_TRUNC}) {
+            Bench B = make_bench(1536, mode, 96);
+            run_v1<Plan<1536, 32, 8, 16, 12, 8>>(B, "v1 <1536,32,8,16,12,8>", true);
+            V2(SM_PAD, 1, 1536, 64, 8, 12, 16, 8); V2B(SM_PAD, 1, 1536, 64, 8, 12, 16, 8); V2B(SM_PAD, 2, 1536, 64, 4, 12, 16, 8);
+            V2B(SM_PAD, 1, 1536, 32, 8, 12, 16, 8); V2B(SM_PAD, 2, 1536, 32, 4, 12, 16, 8); V2B(SM_PAD, 1, 1536, 64, 8, 12, 8, 16);
+            V2(SM_TRUNC, 2, 1536, 64, 4, 8, 16, 12); V2B(SM_TRUNC, 2, 1536, 64, 4, 8, 16, 12); V2B(SM_TRUNC, 1, 1536, 64, 8, 8, 16, 12);
+            V2B(SM_TRUNC, 1, 1536, 96, 8, 8, 16, 12); V2B(SM_TRUNC, 2, 1536, 96, 4, 8, 16, 12); V2B(SM_TRUNC, 1, 1536, 96, 8, 16, 8, 12);
+            if (mode == SM_TRUNC) { B.rmw = 1; printf("  -- RMW (op ADD)\n"); run_v1<Plan<1536, 32, 8, 16, 12, 8>>(B, "v1 rmw", true); V2(SM_TRUNC, 2, 1536, 64, 4, 8, 16, 12); V2B(SM_TRUNC, 1, 1536, 64, 8, 8, 16, 12); }
+            free_bench(B);
+        }
+    }
+}
 int main(int argc, char** argv) {
     int which = argc > 1 ? atoi(argv[1]) : 0;
     const char* what = argc > 2 ? argv[2] : "all";
     if (!strcmp(what, "z") || !strcmp(what, "all")) zbench_all(which);
     if (!strcmp(what, "z")) return 0;
+    if (!strcmp(what, "z3")) { zbench3(which); return 0; }
+    if (!strcmp(what, "s2")) { sbench2(which); return 0; }
+    if (!strcmp(what, "zs")) { zbench3(which); sbench2(which); return 0; }
     if (which == 0 || which == 768) {
         for (int mode : {SM_PAD, SM_TRUNC}) {
             Bench B = make_bench(768, mode, 256);

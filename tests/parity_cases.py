@@ -330,3 +330,31 @@ def check_multiply_noncubic(M, shape):
     C = M.OrszagConvolver(shape, L)
     C.multiply_field(P, Q, M.op.assign_to(out))
     assert relerr(out.get_kspace(), ref) < TOL
+
+
+# ------------------------------------------------------------------ kernel generations agree
+def check_kernel_generations(M, n):
+    """the first-generation kernels (fft_kernels.cuh) and the second-generation ones (fft_kernels2.cuh,
+    fft_kernels_z2.cuh) implement the same arithmetic: a dealiased product and an FFT round trip agree to rounding"""
+    L = 100.0
+    lib = M.grid._lib()
+    g, W, Wc, phi = noise_and_phi(n, L, 9, False)
+    _, _, _, psi = noise_and_phi(n, L, 10, False)
+    res = {}
+    try:
+        for gen in (0, 1):
+            assert lib.mfb_set_option(b"strided_v2", gen) == 0 and lib.mfb_set_option(b"zconv_v2", gen) == 0
+            P, Q = M.Grid_FFT((n,) * 3, (L,) * 3), M.Grid_FFT((n,) * 3, (L,) * 3)
+            out = M.Grid_FFT((n,) * 3, (L,) * 3, True, M.kspace_id)
+            P.set_kspace(phi)
+            Q.set_kspace(psi)
+            C = M.OrszagConvolver((n,) * 3, (L,) * 3)
+            C.convolve_Hessians(P, (0, 1), Q, (1, 2), M.op.assign_to(out))
+            C.convolve_SumOfHessians(P, (2, 2), Q, (0, 0), (1, 1), M.op.multiply_add_to(out, -0.5))
+            P.FourierTransformBackward()
+            res[gen] = (out.get_kspace(), P.get_real())
+    finally:
+        lib.mfb_set_option(b"strided_v2", 1)
+        lib.mfb_set_option(b"zconv_v2", 1)
+    assert relerr(res[1][0], res[0][0]) < TOL and relerr(res[1][1], res[0][1]) < TOL
+    assert lib.mfb_set_option(b"no_such_option", 1) != 0

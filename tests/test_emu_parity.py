@@ -79,3 +79,7 @@ def test_error_behaviour(M):
         MM.Grid_FFT((33, 33, 33), (1.0,) * 3)           # no plan for this size
     with pytest.raises(RuntimeError):
         MM.LPTPipeline(MM.lpt_config(GridRes=33, LPTorder=2))  # Orszag needs an even grid (ic_generator.cc:118)
+
+
+def test_kernel_generations_agree(M):
+    PC.check_kernel_generations(M, 32)

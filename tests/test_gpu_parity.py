@@ -142,3 +142,7 @@ def test_convolver_linearity_and_product_512(M):
     P *= 2.0
     C.multiply_field(P, Q, M.op.multiply_add_to(out, -0.5))
     assert np.abs(out.get_kspace()).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_kernel_generations_agree(M):
+    PC.check_kernel_generations(M, 128)

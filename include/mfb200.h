@@ -29,6 +29,7 @@ extern "C" {
 
 typedef struct mfb_grid mfb_grid; /* opaque: replaces Grid_FFT<real_t> (include/grid_fft.hh:40-914) */
 typedef struct mfb_conv mfb_conv; /* opaque: replaces OrszagConvolver<real_t> (include/convolution.hh:429-669) */
+typedef struct mfb_cgrid mfb_cgrid;   /* opaque: replaces Grid_FFT<ccomplex_t> (PPT branch, src/ic_generator.cc:690,778) */
 typedef struct mfb_particles mfb_particles; /* opaque: replaces particle::container (include/particle_container.hh:30-189) */
 
 enum { MFB_RSPACE = 1, MFB_KSPACE = 0 };                           /* space_t, include/grid_fft.hh:29 */
@@ -123,8 +124,33 @@ int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* 
 /* delta = k^2 phi  (first-order SPT density, :962-973) */
 int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi);
 
+/* ---- Grid_FFT<ccomplex_t> and the PPT / Eulerian branch (src/ic_generator.cc:685-803) ------------------------
+   Dense [n0][n1][n2] complex grids with c2c transforms and the same symmetric norm (src/grid_fft.cc:199-270). Single slab. */
+int mfb_cgrid_create(mfb_cgrid** g, const int n[3], const double L[3]);
+int mfb_cgrid_destroy(mfb_cgrid* g);
+int mfb_cgrid_space(const mfb_cgrid* g);
+size_t mfb_cgrid_nelem(const mfb_cgrid* g);
+int mfb_cgrid_upload(mfb_cgrid* g, const double* host_interleaved, int space);
+int mfb_cgrid_download(const mfb_cgrid* g, double* host_interleaved);
+int mfb_cgrid_copy(mfb_cgrid* dst, const mfb_cgrid* src);                    /* copy_from */
+int mfb_cgrid_fft_forward(mfb_cgrid* g, int do_transform);                   /* FourierTransformForward (c2c) */
+int mfb_cgrid_fft_backward(mfb_cgrid* g, int do_transform);
+int mfb_cgrid_gradient(mfb_cgrid* g, int idim);                              /* x *= i k_d, k from get_k (:790-792) */
+int mfb_ppt_sqrt_density(mfb_grid* rho, double C_species);                   /* rho <- sqrt(1 + C rho) (:703-705) */
+/* psi <- rho * exp(i (phi [+ phi2]) / (hbar D)), all real-space (:741-751); phi2 may be NULL (LPTorder 1) */
+int mfb_ppt_init_psi(mfb_cgrid* psi, const mfb_grid* rho, const mfb_grid* phi, const mfb_grid* phi2, double hbar, double Dplus0);
+int mfb_ppt_drift(mfb_cgrid* psi, double hbar, double Dplus0);               /* k-space: psi *= exp(-i hbar k^2 D / 2) (:757-760) */
+int mfb_ppt_kick(mfb_cgrid* psi, const mfb_grid* phi2, double hbar, double Dplus0); /* psi *= exp(i phi2/(hbar D)) (:763-767) */
+int mfb_ppt_density(mfb_grid* rho, const mfb_cgrid* psi);                    /* rho <- |psi|^2 - 1 (:772-775) */
+/* out <- vunit * hbar * Im(conj(psi) grad_psi) / (1 + rho)  (:796-799) */
+int mfb_ppt_velocity(mfb_grid* out, const mfb_cgrid* psi, const mfb_cgrid* grad_psi, const mfb_grid* rho, double hbar, double vunit);
+
 /* ---- OrszagConvolver ------------------------------------------------------------------------ */
 int mfb_conv_create(mfb_conv** c, const int n[3], const double L[3]);      /* include/convolution.hh:463-495 */
+/* NaiveConvolver (include/convolution.hh:296-426; the reference selects it at compile time with CONVOLVER_TYPE=NAIVE):
+   same named products below on the same handle type, but without padding - aliased products on the N-grid itself,
+   Nyquist planes included, three-field products multiplied in one go.  Single slab only. */
+int mfb_conv_create_naive(mfb_conv** c, const int n[3], const double L[3]);
 int mfb_conv_destroy(mfb_conv* c);
 size_t mfb_conv_workspace_bytes(const mfb_conv* c);
 /* All products: inputs are k-space N-grids, `out` is a k-space N-grid updated with `op` (alpha for MULADD).
@@ -161,6 +187,17 @@ int mfb_particles_set_velocities(mfb_particles* p, int lattice_index, int idim, 
 int mfb_particles_set_masses(mfb_particles* p, int lattice_index, double munit, mfb_grid* field);
 /* device -> host copies into the container vectors the output plugins read (get_*_ptr, particle_container.hh:110-148) */
 int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* ids, void* mass);
+/* Streamed hand-off to the output plugin (replaces the host-side fill of the container that write_particle_data then
+   reads, src/ic_generator.cc:832-955): enqueue the device -> host copy of ONE attribute (MFB_ATTR_*) on a separate copy
+   stream, ordered after everything queued so far on the compute stream, so that it overlaps the kernels of the next
+   component.  `host` should be page-locked.  A later set_* on the same attribute waits for the copy on the device.
+   mfb_particles_stream_wait blocks the host until all streamed copies of `p` have landed. */
+#define MFB_ATTR_POS 0
+#define MFB_ATTR_VEL 1
+#define MFB_ATTR_IDS 2
+#define MFB_ATTR_MASS 3
+int mfb_particles_stream_out(mfb_particles* p, int attr, void* host);
+int mfb_particles_stream_wait(mfb_particles* p);
 
 #ifdef __cplusplus
 }

@@ -6,9 +6,9 @@ particle::lattice_generator interfaces on top of the C ABI of libmfb200.so
 there is no CPU fallback.
 """
 from ._lib import MfbError, load  # noqa: F401
-from .grid import (Grid_FFT, OrszagConvolver, Particles, init, finalize, kspace_id, rspace_id,  # noqa: F401
+from .grid import (Grid_FFT, Grid_FFT_complex, OrszagConvolver, NaiveConvolver, Particles, init, finalize, kspace_id, rspace_id,  # noqa: F401
                    synchronize, kernel_launches, op)
 from .pipeline import LPTPipeline, lpt_config  # noqa: F401
 
-__all__ = ["Grid_FFT", "OrszagConvolver", "Particles", "LPTPipeline", "lpt_config", "init", "finalize",
+__all__ = ["Grid_FFT", "Grid_FFT_complex", "OrszagConvolver", "NaiveConvolver", "Particles", "LPTPipeline", "lpt_config", "init", "finalize",
            "synchronize", "kernel_launches", "kspace_id", "rspace_id", "op", "MfbError", "load"]

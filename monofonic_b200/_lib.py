@@ -75,7 +75,24 @@ def _declare(lib):
         "mfb_add_tides": (i, [vp, vp, dp]),
         "mfb_lpt_assemble": (i, [vp, i, vp, vp, vp, vpp, d, d, d, d, d, vp, vp, sz, d]),
         "mfb_density_from_phi": (i, [vp, vp]),
+        "mfb_cgrid_create": (i, [vpp, ip, dp]),
+        "mfb_cgrid_destroy": (i, [vp]),
+        "mfb_cgrid_space": (i, [vp]),
+        "mfb_cgrid_nelem": (sz, [vp]),
+        "mfb_cgrid_upload": (i, [vp, vp, i]),
+        "mfb_cgrid_download": (i, [vp, vp]),
+        "mfb_cgrid_copy": (i, [vp, vp]),
+        "mfb_cgrid_fft_forward": (i, [vp, i]),
+        "mfb_cgrid_fft_backward": (i, [vp, i]),
+        "mfb_cgrid_gradient": (i, [vp, i]),
+        "mfb_ppt_sqrt_density": (i, [vp, d]),
+        "mfb_ppt_init_psi": (i, [vp, vp, vp, vp, d, d]),
+        "mfb_ppt_drift": (i, [vp, d, d]),
+        "mfb_ppt_kick": (i, [vp, vp, d, d]),
+        "mfb_ppt_density": (i, [vp, vp]),
+        "mfb_ppt_velocity": (i, [vp, vp, vp, vp, d, d]),
         "mfb_conv_create": (i, [vpp, ip, dp]),
+        "mfb_conv_create_naive": (i, [vpp, ip, dp]),
         "mfb_conv_destroy": (i, [vp]),
         "mfb_conv_workspace_bytes": (sz, [vp]),
         "mfb_conv_hessians": (i, [vp, vp, ip, vp, ip, vp, i, d]),
@@ -94,6 +111,8 @@ def _declare(lib):
         "mfb_particles_set_velocities": (i, [vp, i, i, vp]),
         "mfb_particles_set_masses": (i, [vp, i, d, vp]),
         "mfb_particles_download": (i, [vp, vp, vp, vp, vp]),
+        "mfb_particles_stream_out": (i, [vp, i, vp]),
+        "mfb_particles_stream_wait": (i, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

@@ -31,6 +31,8 @@ struct OperandFactor {
     int imag;
     int n[3];      // grid size per axis (wave-number folding)
     double kf[3];  // 2 pi / L per axis
+    int keep_nyq;  // 1: K at the Nyquist index is +n/2*kf (get_k, include/grid_fft.hh:282-296) instead of 0 (gradient, :376-385);
+                   //    only the un-padded NaiveConvolver ever feeds a Nyquist mode through a factor
 };
 
 struct StridedArgs {
@@ -57,8 +59,8 @@ struct StridedArgs {
                                //   or a staging chunk when the exchange is done by a host collective)
 };
 
-MFB_HD double wave_k(int i, int n, double kfac) {
-    return (i == n / 2) ? 0.0 : kfac * double(i - ((i > n / 2) ? n : 0));
+MFB_HD double wave_k(int i, int n, double kfac, int keep_nyq = 0) {
+    return (i == n / 2 && !keep_nyq) ? 0.0 : kfac * double(i - ((i > n / 2) ? n : 0));
 }
 
 template <class P>
@@ -97,8 +99,8 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
     // ---- per-thread operand factor polynomial in K_pos:  f = q0 + q1*Kp + q2*Kp^2
     double q0 = 1.0, q1 = 0.0, q2 = 0.0;
     if (A.f.enabled) {
-        const double Ka = wave_k(a + A.a_off, A.f.n[A.a_axis], A.f.kf[A.a_axis]);
-        const double Kz = wave_k(iz, A.f.n[2], A.f.kf[2]);
+        const double Ka = wave_k(a + A.a_off, A.f.n[A.a_axis], A.f.kf[A.a_axis], A.f.keep_nyq);
+        const double Kz = wave_k(iz, A.f.n[2], A.f.kf[2], A.f.keep_nyq);
         q0 = 0.0;
         auto term = [&](int d1, int d2, double c) {
             if (c == 0.0) return;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
         }
         double2 v = mfb_ld_stream(ibase + ptrdiff_t(src) * A.in_ps);
         if (A.f.enabled) {
-            const double Kp = wave_k(src, A.f.n[A.pos_axis], A.f.kf[A.pos_axis]);
+            const double Kp = wave_k(src, A.f.n[A.pos_axis], A.f.kf[A.pos_axis], A.f.keep_nyq);
             const double fac = fma(fma(q2, Kp, q1), Kp, q0);
             v = A.f.imag ? make_double2(-v.y * fac, v.x * fac) : make_double2(v.x * fac, v.y * fac);
         }
@@ -236,6 +238,34 @@ __global__ void __launch_bounds__(P::NTHREADS) z_r2c_kernel(double* __restrict__
         const double2 x2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
         if (r1 < nrows) mfb_st_stream(reinterpret_cast<double2*>(data + r1 * pitch) + k, x1);
         if (r1 + 1 < nrows) mfb_st_stream(reinterpret_cast<double2*>(data + (r1 + 1) * pitch) + k, x2);
+    }
+}
+
+// z pass of a complex-to-complex transform (Grid_FFT<ccomplex_t>, PPT branch src/ic_generator.cc:685-803): rows of n
+// contiguous complex values, in place.  Row-major coalesced loads/stores transpose through the swizzled tile.
+template <class P>
+__global__ void __launch_bounds__(P::NTHREADS) z_c2c_kernel(double2* __restrict__ data, long nrows, double scale, int inverse,
+                                                            const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N, T = P::T;
+    const int tid = threadIdx.x;
+    const long row0 = long(blockIdx.x) * T;
+    for (int idx = tid; idx < T * N; idx += P::NTHREADS) {
+        const int l = idx / N, j = idx - l * N;
+        double2 z = make_double2(0.0, 0.0);
+        if (row0 + l < nrows) z = mfb_ld_stream(data + (row0 + l) * N + j);
+        if (inverse) z.y = -z.y;
+        sm[P::smem_addr(j, l)] = z;
+    }
+    __syncthreads();
+    NoLoader nl; NoStorer ns;
+    fft_tile<P, false, false, false>(sm, tw, tid % T, tid / T, true, nl, ns);
+    __syncthreads();
+    const double sy = inverse ? -scale : scale;
+    for (int idx = tid; idx < T * N; idx += P::NTHREADS) {
+        const int l = idx / N, k = idx - l * N;
+        const double2 z = sm[P::smem_addr(P::pos_of_freq(k), l)];
+        if (row0 + l < nrows) mfb_st_stream(data + (row0 + l) * N + k, make_double2(z.x * scale, z.y * sy));
     }
 }
 

@@ -42,9 +42,96 @@ constexpr int EW_ROWS = 4;  // k-space rows (fixed kx,ky) per block
 
 inline unsigned kgrid_blocks(const KGeom& g) { return unsigned((long(g.s0) * g.s1 + EW_ROWS - 1) / EW_ROWS); }
 
+
+// ---------------------------------------------------------------- PPT / Eulerian branch (src/ic_generator.cc:685-803)
+// Complex grids (Grid_FFT<ccomplex_t>) are dense [n0][n1][n2] double2; real grids keep the padded rows (pitch n2+2).
+struct CGeom {
+    int n0, n1, n2;
+    double kf0, kf1, kf2;
+    ptrdiff_t rpitch;  // doubles per row of the real companions
+};
+#define MFB_C_LOOP_BEGIN(G)                                                                                       \
+    const long total_ = long((G).n0) * (G).n1 * (G).n2;                                                           \
+    for (long t_ = long(blockIdx.x) * EW_THREADS + threadIdx.x; t_ < total_; t_ += long(gridDim.x) * EW_THREADS) { \
+        const int k = int(t_ % (G).n2);                                                                           \
+        const long r_ = t_ / (G).n2;                                                                              \
+        const int j = int(r_ % (G).n1), i = int(r_ / (G).n1);                                                     \
+        const long ridx = r_ * (G).rpitch + k;                                                                    \
+        (void)i; (void)j; (void)ridx;
+
+// rho <- sqrt(1 + C rho) on the logical real elements (:703-705)
+__global__ void __launch_bounds__(EW_THREADS) ppt_sqrt1p_kernel(double* __restrict__ rho, CGeom g, double C) {
+    MFB_C_LOOP_BEGIN(g)
+        rho[ridx] = sqrt(1.0 + C * rho[ridx]);
+    }
+}
+// psi <- rho * exp(i (phi [+ phi2]) / (hbar D))  (:741-751).  The argument is formed exactly as the reference does:
+// complex(0,1/hbar) * (phi [+ phi2]) / D  ->  imaginary part ((1/hbar) * sum) / D
+__global__ void __launch_bounds__(EW_THREADS) ppt_init_psi_kernel(double2* __restrict__ psi, const double* __restrict__ rho,
+                                                                   const double* __restrict__ phi, const double* __restrict__ phi2,
+                                                                   CGeom g, double inv_hbar, double D) {
+    MFB_C_LOOP_BEGIN(g)
+        const double sum = phi2 ? (phi[ridx] + phi2[ridx]) : phi[ridx];
+        const double arg = phi2 ? (inv_hbar * sum) / D : inv_hbar * (sum / D);
+        double sn, cs;
+        sincos(arg, &sn, &cs);
+        const double a = rho[ridx];
+        psi[t_] = make_double2(a * cs, a * sn);
+    }
+}
+// drift in k-space: psi <- psi * exp(-i/2 hbar k^2 D), k from get_k on all three axes (:757-760)
+__global__ void __launch_bounds__(EW_THREADS) ppt_drift_kernel(double2* __restrict__ psi, CGeom g, double hbar, double D) {
+    MFB_C_LOOP_BEGIN(g)
+        const double kx = getk(i, g.n0, g.kf0), ky = getk(j, g.n1, g.kf1), kz = getk(k, g.n2, g.kf2);
+        const double k2 = kx * kx + ky * ky + kz * kz;
+        const double arg = -((0.5 * hbar) * k2) * D;
+        double sn, cs;
+        sincos(arg, &sn, &cs);
+        psi[t_] = cmul(psi[t_], make_double2(cs, sn));
+    }
+}
+// kick: psi <- psi * exp(i phi2 / (hbar D))  (:763-767)
+__global__ void __launch_bounds__(EW_THREADS) ppt_kick_kernel(double2* __restrict__ psi, const double* __restrict__ phi2, CGeom g,
+                                                               double inv_hbar, double D) {
+    MFB_C_LOOP_BEGIN(g)
+        double sn, cs;
+        sincos((inv_hbar * phi2[ridx]) / D, &sn, &cs);
+        psi[t_] = cmul(psi[t_], make_double2(cs, sn));
+    }
+}
+// rho <- |psi|^2 - 1  (:772-775)
+__global__ void __launch_bounds__(EW_THREADS) ppt_density_kernel(double* __restrict__ rho, const double2* __restrict__ psi, CGeom g) {
+    MFB_C_LOOP_BEGIN(g)
+        const double2 p = psi[t_];
+        rho[ridx] = p.x * p.x + p.y * p.y - 1.0;
+    }
+}
+// g <- g * i k_d, k from get_k (:790-792)
+__global__ void __launch_bounds__(EW_THREADS) cgrid_gradient_kernel(double2* __restrict__ d, CGeom g, int idim) {
+    MFB_C_LOOP_BEGIN(g)
+        const double kd = (idim == 0) ? getk(i, g.n0, g.kf0) : ((idim == 1) ? getk(j, g.n1, g.kf1) : getk(k, g.n2, g.kf2));
+        const double2 v = d[t_];
+        d[t_] = make_double2(-v.y * kd, v.x * kd);
+    }
+}
+// v <- vunit * Re[(conj(psi) grad - psi conj(grad)) / (2i/hbar)] / (1+rho) = vunit * hbar * Im(conj(psi) grad) / (1+rho)  (:796-799)
+__global__ void __launch_bounds__(EW_THREADS) ppt_velocity_kernel(double* __restrict__ out, const double2* __restrict__ psi,
+                                                                   const double2* __restrict__ grad, const double* __restrict__ rho,
+                                                                   CGeom g, double hbar, double vunit) {
+    MFB_C_LOOP_BEGIN(g)
+        const double2 p = psi[t_], q = grad[t_];
+        const double im2 = 2.0 * (p.x * q.y - p.y * q.x);   // Im(conj(p) q - p conj(q))
+        out[ridx] = vunit * ((im2 / (2.0 / hbar)) / (1.0 + rho[ridx]));
+    }
+}
+
 // ---------------------------------------------------------------- plain streaming ops
 __global__ void __launch_bounds__(EW_THREADS) scale_kernel(double* __restrict__ d, size_t n, double a) {
     for (size_t i = size_t(blockIdx.x) * EW_THREADS + threadIdx.x; i < n; i += size_t(gridDim.x) * EW_THREADS) d[i] *= a;
+}
+__global__ void __launch_bounds__(EW_THREADS) multiply_kernel(double* __restrict__ y, const double* __restrict__ x, size_t n) {
+    // y <- y*x over the whole real-indexed buffer (NaiveConvolver product loop, include/convolution.hh:341-345)
+    for (size_t i = size_t(blockIdx.x) * EW_THREADS + threadIdx.x; i < n; i += size_t(gridDim.x) * EW_THREADS) y[i] *= x[i];
 }
 __global__ void __launch_bounds__(EW_THREADS) affine_kernel(double* __restrict__ d, size_t n, double a, double b) {
     // x <- a + b*x  (src/ic_generator.cc:673-675 mass field)

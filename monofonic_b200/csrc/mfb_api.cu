@@ -337,6 +337,24 @@ void launch_z(int n, int kind, double* data, ptrdiff_t pitch, long nrows, double
     }
 }
 
+template <class P> void launch_zc2c_t(double2* data, long nrows, double scale, int inverse) {
+    static bool done = false;
+    optin_smem(z_c2c_kernel<P>, P::SMEM_BYTES, done);
+    const unsigned grid = unsigned((nrows + P::T - 1) / P::T);
+    RoleScope rs(ROLE_FFT_Z_C2C, double(nrows) * 32.0 * P::N);
+    MFB_LAUNCH(z_c2c_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, nrows, scale, inverse, twiddles(P::N));
+    check_launch("z_c2c_kernel");
+}
+void launch_zc2c(int n, double2* data, long nrows, double scale, int inverse) {
+    switch (n) {
+#define X(N_, TPL_, T_, ...)                                                     \
+    case N_: launch_zc2c_t<Plan<N_, TPL_, T_, __VA_ARGS__>>(data, nrows, scale, inverse); break;
+        MFB_FOR_EACH_PLAN(X)
+#undef X
+        default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
+    }
+}
+
 template <class P>
 void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
                     int nzin, double scale) {
@@ -546,6 +564,36 @@ void grid_shift_field(mfb_grid* g, const double s[3], bool back) {
 }
 
 // ------------------------------------------------------------------------------------------
+// complex grids (Grid_FFT<ccomplex_t>): c2c transforms with the symmetric norm (src/grid_fft.cc:199-270)
+// ------------------------------------------------------------------------------------------
+static void cgrid_fft(mfb_cgrid* g, int inverse) {
+    const int n0 = g->n[0], n1 = g->n[1], n2 = g->n[2];
+    const double norm = 1.0 / std::sqrt(double(n0) * n1 * n2);
+    double2* c = g->d;
+    if (!inverse) {
+        launch_zc2c(n2, c, long(n0) * n1, norm, 0);
+        launch_strided(n1, plain_strided(c, c, n2, ptrdiff_t(n1) * n2, n0, n2, n1, 0), ROLE_FFT_Y);
+        launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * n2, n2, n1, n2, n0, 0), ROLE_FFT_X);
+    } else {
+        launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * n2, n2, n1, n2, n0, 1), ROLE_FFT_X);
+        launch_strided(n1, plain_strided(c, c, n2, ptrdiff_t(n1) * n2, n0, n2, n1, 1), ROLE_FFT_Y);
+        launch_zc2c(n2, c, long(n0) * n1, norm, 1);
+    }
+}
+static CGeom cgeom(const mfb_cgrid* g) {
+    CGeom c;
+    c.n0 = g->n[0]; c.n1 = g->n[1]; c.n2 = g->n[2];
+    c.kf0 = 2.0 * M_PI / g->L[0]; c.kf1 = 2.0 * M_PI / g->L[1]; c.kf2 = 2.0 * M_PI / g->L[2];
+    c.rpitch = g->n[2] + 2;
+    return c;
+}
+static void check_ppt_real(const mfb_cgrid* c, const mfb_grid* r, const char* name) {
+    if (!r || r->dist || r->n[0] != c->n[0] || r->n[1] != c->n[1] || r->n[2] != c->n[2])
+        throw std::runtime_error(std::string("PPT: real grid '") + name + "' must be a single-slab grid of the same size");
+    if (r->space != MFB_RSPACE) throw std::runtime_error(std::string("PPT: real grid '") + name + "' must be in real space");
+}
+
+// ------------------------------------------------------------------------------------------
 // Orszag convolver
 // ------------------------------------------------------------------------------------------
 struct Operand {
@@ -553,6 +601,7 @@ struct Operand {
     int a1, b1, a2, b2;
     double c1, c2;
     int imag;
+    int keep_nyq = 0;  // factor built from get_k (Nyquist = +N/2) instead of gradient (Nyquist = 0); NaiveConvolver only
 };
 
 static void set_operand_factor(StridedArgs& a, mfb_conv* c, const Operand& o, double s1) {
@@ -560,6 +609,7 @@ static void set_operand_factor(StridedArgs& a, mfb_conv* c, const Operand& o, do
     a.f.a1 = o.a1; a.f.b1 = o.b1; a.f.a2 = o.a2; a.f.b2 = o.b2;
     a.f.c1 = o.c1 * s1; a.f.c2 = o.c2 * s1;
     a.f.imag = o.imag;
+    a.f.keep_nyq = o.keep_nyq;
     for (int d = 0; d < 3; ++d) { a.f.n[d] = c->n[d]; a.f.kf[d] = 2.0 * M_PI / c->L[d]; }
 }
 
@@ -612,8 +662,52 @@ static void conv_backward_operand(mfb_conv* c, const Operand& o, double2* W2) {
     launch_strided(P1, b, ROLE_CONV_Y_BWD);
 }
 
+// ---- NaiveConvolver (include/convolution.hh:296-426, compile-time CONVOLVER_TYPE=NAIVE): same named products,
+// no padding - copy_in(kfunc) over EVERY stored mode incl. the Nyquist planes, backward FFT, product over the
+// real-indexed buffer, forward FFT, output operator over every stored mode (no Nyquist zeroing, no rescale).
+// copy_in is fused into the x sweep of the backward transform, the output operator into the x sweep of the forward one.
+static void naive_backward_operand(mfb_conv* c, const Operand& o, mfb_grid* dst) {
+    const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2], nzc = N2 / 2 + 1;
+    to_kspace(o.g);
+    double2* d = reinterpret_cast<double2*>(dst->d);
+    StridedArgs a = plain_strided(reinterpret_cast<const double2*>(o.g->d), d, ptrdiff_t(N1) * nzc, nzc, N1, nzc, N0, 1);
+    set_operand_factor(a, c, o, 1.0);
+    a.pos_axis = 0; a.a_axis = 1;
+    launch_strided(N0, a, ROLE_FFT_X);
+    launch_strided(N1, plain_strided(d, d, nzc, ptrdiff_t(N1) * nzc, N0, nzc, N1, 1), ROLE_FFT_Y);
+    launch_z(N2, 0, dst->d, dst->pitch, long(N0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
+    dst->space = MFB_RSPACE;
+}
+static void naive_multiply(mfb_grid* y, const mfb_grid* x) {
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, multiply_kernel, stream_blocks(y->ntot), EW_THREADS, y->d, x->d, y->ntot);
+    check_launch("multiply");
+}
+static void naive_forward_output(mfb_conv* c, mfb_grid* src, mfb_grid* out, int op, double alpha) {
+    const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2], nzc = N2 / 2 + 1;
+    require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+    double2* d = reinterpret_cast<double2*>(src->d);
+    launch_z(N2, 1, src->d, src->pitch, long(N0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
+    launch_strided(N1, plain_strided(d, d, nzc, ptrdiff_t(N1) * nzc, N0, nzc, N1, 0), ROLE_FFT_Y);
+    StridedArgs e = plain_strided(d, reinterpret_cast<double2*>(out->d), ptrdiff_t(N1) * nzc, nzc, N1, nzc, N0, 0);
+    e.op = op; e.alpha = alpha;
+    launch_strided(N0, e, ROLE_FFT_X);
+    src->space = MFB_KSPACE;
+    ++c->nconv;
+}
+static void naive_conv(mfb_conv* c, const Operand& A, const Operand& B, const Operand* C3, mfb_grid* out, int op, double alpha) {
+    naive_backward_operand(c, A, c->nb1);
+    naive_backward_operand(c, B, c->nb2);
+    naive_multiply(c->nb2, c->nb1);
+    if (C3) {   // convolve3: all three fields multiplied in real space (:361-401), no intermediate truncation
+        naive_backward_operand(c, *C3, c->nb1);
+        naive_multiply(c->nb2, c->nb1);
+    }
+    naive_forward_output(c, c->nb2, out, op, alpha);
+}
+
 void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
     require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+    if (c->naive) { naive_conv(c, A, B, nullptr, out, op, alpha); return; }
     to_kspace(A.g);
     to_kspace(B.g);
     const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
@@ -672,6 +766,17 @@ void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int o
 
 static Operand hessian_operand(mfb_grid* g, const int d[2]) { return Operand{g, d[0], d[1], -1, -1, -1.0, 0.0, 0}; }
 
+// three-field product (include/convolution.hh:542-549 Orszag: two dealiased products with the intermediate truncated
+// to the N-grid; :361-401 Naive: one real-space triple product)
+void conv3(mfb_conv* c, const Operand& A, const Operand& B, const Operand& C3, mfb_grid* out, int op, double alpha) {
+    require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+    if (c->naive) { naive_conv(c, A, B, &C3, out, op, alpha); return; }
+    to_kspace(C3.g);
+    c->fbuf->space = MFB_KSPACE;
+    conv2(c, A, B, c->fbuf, OP_ASSIGN, 0.0);
+    conv2(c, Operand{c->fbuf, -1, -1, -1, -1, 1.0, 0.0, 0}, C3, out, op, alpha);
+}
+
 void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3, mfb_grid* const A3[3],
                  const double* lam) {
     require(phi->space == MFB_KSPACE, "phi must be in k-space");
@@ -701,19 +806,12 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
     if (order > 2) {
         require(phi3 && A3 && A3[0] && A3[1] && A3[2], "phi3 and A3 grids required for LPT order > 2");
         phi3->space = MFB_KSPACE;
-        mfb_grid* fb = c->fbuf;
-        fb->space = MFB_KSPACE;
-        Operand FB{fb, -1, -1, -1, -1, 1.0, 0.0, 0};
-        auto conv3 = [&](Operand a, Operand b, Operand cc, int op, double alpha) {
-            conv2(c, a, b, fb, OP_ASSIGN, 0.0);  // include/convolution.hh:542-549
-            conv2(c, FB, cc, phi3, op, alpha);
-        };
         // 3a  :522-526
-        conv3(H(phi, 0, 0), H(phi, 1, 1), H(phi, 2, 2), OP_ASSIGN, 0.0);
-        conv3(H(phi, 0, 1), H(phi, 0, 2), H(phi, 1, 2), OP_MULADD, 2.0);
-        conv3(H(phi, 1, 2), H(phi, 1, 2), H(phi, 0, 0), OP_SUB, 0.0);
-        conv3(H(phi, 0, 2), H(phi, 0, 2), H(phi, 1, 1), OP_SUB, 0.0);
-        conv3(H(phi, 0, 1), H(phi, 0, 1), H(phi, 2, 2), OP_SUB, 0.0);
+        conv3(c, H(phi, 0, 0), H(phi, 1, 1), H(phi, 2, 2), phi3, OP_ASSIGN, 0.0);
+        conv3(c, H(phi, 0, 1), H(phi, 0, 2), H(phi, 1, 2), phi3, OP_MULADD, 2.0);
+        conv3(c, H(phi, 1, 2), H(phi, 1, 2), H(phi, 0, 0), phi3, OP_SUB, 0.0);
+        conv3(c, H(phi, 0, 2), H(phi, 0, 2), H(phi, 1, 1), phi3, OP_SUB, 0.0);
+        conv3(c, H(phi, 0, 1), H(phi, 0, 1), H(phi, 2, 2), phi3, OP_SUB, 0.0);
         // 3b  :533-538
         conv2(c, H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), phi3, OP_MULADD, -5.0 / 7.0);
         conv2(c, H(phi, 1, 1), HS(phi2, 2, 2, 0, 0, +1.0), phi3, OP_MULADD, -5.0 / 7.0);
@@ -763,6 +861,11 @@ static void particles_readout(mfb_particles* p, int kind, int lattice_index, int
     require(f->nloc0 == p->nloc0 && f->off0 == p->off0, "field/particle slab mismatch");
     const long ncell = long(p->nloc0) * p->n[1] * p->n[2];          // local cells
     const double pmean = unit / (double(p->n[0]) * p->n[1] * p->n[2] * nshift);
+    if (p->copy_pending[kind == 2 ? MFB_ATTR_MASS : kind]) {  // a streamed D2H copy still reads this buffer
+        const int at = kind == 2 ? MFB_ATTR_MASS : kind;
+        cuda_check(cudaStreamWaitEvent(g_ctx.stream, p->copied[at], 0), "cudaStreamWaitEvent");
+        p->copy_pending[at] = false;
+    }
     to_rspace(f);
     for (int is = 0; is < nshift; ++is) {
         if (is == 0 && lattice_index == 1) grid_shift_field(f, SECOND_LATTICE_SHIFT[lt], true);
@@ -834,6 +937,7 @@ int mfb_finalize(void) {
     if (g_ctx.partial) cudaFree(g_ctx.partial);
     g_ctx.partial = nullptr; g_ctx.partial_cap = 0;
     cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.copy_stream) { cudaStreamDestroy(g_ctx.copy_stream); g_ctx.copy_stream = nullptr; }
     g_ctx.initialised = false;
     MFB_CATCH
 }
@@ -870,7 +974,8 @@ int mfb_profile_reset(void) {
 int mfb_profile_num_roles(void) { return ROLE_COUNT; }
 const char* mfb_profile_role_name(int role) {
     static const char* names[ROLE_COUNT] = {"conv_x_bwd", "conv_y_bwd", "conv_z_fused", "conv_y_fwd", "conv_x_fwd", "fft_x",
-                                            "fft_y", "fft_z_r2c", "fft_z_c2r", "elementwise", "reduce", "particles", "barrier"};
+                                            "fft_y", "fft_z_r2c", "fft_z_c2r", "elementwise", "reduce", "particles", "barrier",
+                                            "fft_z_c2c"};
     return (role >= 0 && role < ROLE_COUNT) ? names[role] : "?";
 }
 int mfb_profile_get(int role, double* ms, long long* count, double* bytes) {
@@ -1255,6 +1360,121 @@ int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi) {
     MFB_CATCH
 }
 
+// ---------------------------------------------------------------- complex grids + PPT / Eulerian branch
+int mfb_cgrid_create(mfb_cgrid** out, const int n[3], const double L[3]) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(!dist_on(), "complex grids (PPT branch) are only available on a single slab");
+    for (int d = 0; d < 3; ++d) require(supported_size(n[d]), "unsupported grid size (no FFT plan)");
+    mfb_cgrid* g = new mfb_cgrid();
+    for (int d = 0; d < 3; ++d) { g->n[d] = n[d]; g->L[d] = L[d]; }
+    g->space = MFB_RSPACE;
+    g->nelem = size_t(n[0]) * n[1] * n[2];
+    g->d = (double2*)dev_alloc(g->nelem * sizeof(double2));
+    cuda_check(cudaMemsetAsync(g->d, 0, g->nelem * sizeof(double2), g_ctx.stream), "memset");
+    *out = g;
+    MFB_CATCH
+}
+int mfb_cgrid_destroy(mfb_cgrid* g) {
+    MFB_TRY
+    if (g) { cudaFree(g->d); delete g; }
+    MFB_CATCH
+}
+int mfb_cgrid_space(const mfb_cgrid* g) { return g->space; }
+size_t mfb_cgrid_nelem(const mfb_cgrid* g) { return g->nelem; }
+int mfb_cgrid_upload(mfb_cgrid* g, const double* host_interleaved, int space) {
+    MFB_TRY
+    cuda_check(cudaMemcpyAsync(g->d, host_interleaved, g->nelem * sizeof(double2), cudaMemcpyHostToDevice, g_ctx.stream), "H2D");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    g->space = space;
+    MFB_CATCH
+}
+int mfb_cgrid_download(const mfb_cgrid* g, double* host_interleaved) {
+    MFB_TRY
+    cuda_check(cudaMemcpyAsync(host_interleaved, g->d, g->nelem * sizeof(double2), cudaMemcpyDeviceToHost, g_ctx.stream), "D2H");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+int mfb_cgrid_copy(mfb_cgrid* dst, const mfb_cgrid* src) {
+    MFB_TRY
+    require(dst->nelem == src->nelem, "copy_from: size mismatch");
+    cuda_check(cudaMemcpyAsync(dst->d, src->d, src->nelem * sizeof(double2), cudaMemcpyDeviceToDevice, g_ctx.stream), "copy");
+    dst->space = src->space;
+    MFB_CATCH
+}
+int mfb_cgrid_fft_forward(mfb_cgrid* g, int do_transform) {
+    MFB_TRY
+    if (g->space != MFB_KSPACE) { if (do_transform) cgrid_fft(g, 0); g->space = MFB_KSPACE; }
+    MFB_CATCH
+}
+int mfb_cgrid_fft_backward(mfb_cgrid* g, int do_transform) {
+    MFB_TRY
+    if (g->space != MFB_RSPACE) { if (do_transform) cgrid_fft(g, 1); g->space = MFB_RSPACE; }
+    MFB_CATCH
+}
+int mfb_cgrid_gradient(mfb_cgrid* g, int idim) {
+    MFB_TRY
+    require(idim >= 0 && idim < 3, "bad dimension");
+    require(g->space == MFB_KSPACE, "gradient: complex grid must be in k-space");
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, cgrid_gradient_kernel, stream_blocks(g->nelem), EW_THREADS, g->d, cgeom(g), idim);
+    check_launch("cgrid_gradient");
+    MFB_CATCH
+}
+int mfb_ppt_sqrt_density(mfb_grid* rho, double C_species) {
+    MFB_TRY
+    require(rho->space == MFB_RSPACE && !rho->dist, "PPT: rho must be a single-slab real-space grid");
+    CGeom c;
+    c.n0 = rho->n[0]; c.n1 = rho->n[1]; c.n2 = rho->n[2]; c.kf0 = c.kf1 = c.kf2 = 0.0; c.rpitch = rho->pitch;
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_sqrt1p_kernel, stream_blocks(size_t(c.n0) * c.n1 * c.n2), EW_THREADS, rho->d, c, C_species);
+    check_launch("ppt_sqrt1p");
+    MFB_CATCH
+}
+int mfb_ppt_init_psi(mfb_cgrid* psi, const mfb_grid* rho, const mfb_grid* phi, const mfb_grid* phi2, double hbar, double Dplus0) {
+    MFB_TRY
+    check_ppt_real(psi, rho, "rho"); check_ppt_real(psi, phi, "phi");
+    if (phi2) check_ppt_real(psi, phi2, "phi2");
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_init_psi_kernel, stream_blocks(psi->nelem), EW_THREADS, psi->d, rho->d, phi->d,
+                    phi2 ? phi2->d : (const double*)nullptr, cgeom(psi), 1.0 / hbar, Dplus0);
+    check_launch("ppt_init_psi");
+    psi->space = MFB_RSPACE;
+    MFB_CATCH
+}
+int mfb_ppt_drift(mfb_cgrid* psi, double hbar, double Dplus0) {
+    MFB_TRY
+    require(psi->space == MFB_KSPACE, "PPT drift: psi must be in k-space");
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_drift_kernel, stream_blocks(psi->nelem), EW_THREADS, psi->d, cgeom(psi), hbar, Dplus0);
+    check_launch("ppt_drift");
+    MFB_CATCH
+}
+int mfb_ppt_kick(mfb_cgrid* psi, const mfb_grid* phi2, double hbar, double Dplus0) {
+    MFB_TRY
+    require(psi->space == MFB_RSPACE, "PPT kick: psi must be in real space");
+    check_ppt_real(psi, phi2, "phi2");
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_kick_kernel, stream_blocks(psi->nelem), EW_THREADS, psi->d, phi2->d, cgeom(psi), 1.0 / hbar, Dplus0);
+    check_launch("ppt_kick");
+    MFB_CATCH
+}
+int mfb_ppt_density(mfb_grid* rho, const mfb_cgrid* psi) {
+    MFB_TRY
+    require(psi->space == MFB_RSPACE, "PPT density: psi must be in real space");
+    rho->space = MFB_RSPACE;
+    check_ppt_real(psi, rho, "rho");
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_density_kernel, stream_blocks(psi->nelem), EW_THREADS, rho->d, psi->d, cgeom(psi));
+    check_launch("ppt_density");
+    MFB_CATCH
+}
+int mfb_ppt_velocity(mfb_grid* out, const mfb_cgrid* psi, const mfb_cgrid* grad_psi, const mfb_grid* rho, double hbar, double vunit) {
+    MFB_TRY
+    require(psi->space == MFB_RSPACE && grad_psi->space == MFB_RSPACE, "PPT velocity: psi and grad_psi must be in real space");
+    require(psi->nelem == grad_psi->nelem, "PPT velocity: size mismatch");
+    out->space = MFB_RSPACE;
+    check_ppt_real(psi, out, "out"); check_ppt_real(psi, rho, "rho");
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_velocity_kernel, stream_blocks(psi->nelem), EW_THREADS, out->d, psi->d, grad_psi->d, rho->d,
+                    cgeom(psi), hbar, vunit);
+    check_launch("ppt_velocity");
+    MFB_CATCH
+}
+
 // ---------------------------------------------------------------- convolver
 int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
     MFB_TRY
@@ -1278,6 +1498,22 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
     c->W2a = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
     c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
     if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
+    c->naive = 0; c->nb1 = c->nb2 = nullptr;
+    *out = c;
+    MFB_CATCH
+}
+int mfb_conv_create_naive(mfb_conv** out, const int n[3], const double L[3]) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(!dist_on(), "the NaiveConvolver is only available on a single slab");
+    mfb_conv* c = new mfb_conv();
+    memset(c, 0, sizeof(*c));
+    for (int d = 0; d < 3; ++d) {
+        c->n[d] = n[d]; c->L[d] = L[d]; c->np[d] = n[d];
+        require(supported_size(n[d]), "unsupported grid size for the convolver");
+    }
+    c->naive = 1;
+    if (mfb_grid_create(&c->nb1, n, L, MFB_KSPACE) || mfb_grid_create(&c->nb2, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
     *out = c;
     MFB_CATCH
 }
@@ -1285,13 +1521,17 @@ int mfb_conv_destroy(mfb_conv* c) {
     MFB_TRY
     if (c) {
         if (c->W1) cudaFree(c->W1);
-        cudaFree(c->W2a); cudaFree(c->W2b);
-        mfb_grid_destroy(c->fbuf);
+        if (c->W2a) cudaFree(c->W2a);
+        if (c->W2b) cudaFree(c->W2b);
+        if (c->fbuf) mfb_grid_destroy(c->fbuf);
+        if (c->nb1) mfb_grid_destroy(c->nb1);
+        if (c->nb2) mfb_grid_destroy(c->nb2);
         delete c;
     }
     MFB_CATCH
 }
 size_t mfb_conv_workspace_bytes(const mfb_conv* c) {
+    if (c->naive) return (c->nb1->ntot + c->nb2->ntot) * sizeof(double);
     return (c->w1_elems + 2 * c->w2_elems) * sizeof(double2) + c->fbuf->ntot * sizeof(double);
 }
 static void check_conv_grids(mfb_conv* c, mfb_grid* a, mfb_grid* b, mfb_grid* o) {
@@ -1313,10 +1553,7 @@ int mfb_conv_hessians3(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* m, 
     MFB_TRY
     check_conv_grids(c, l, m, out); check_conv_grids(c, r, r, out);
     check_dims(d2l, 2); check_dims(d2m, 2); check_dims(d2r, 2);
-    to_kspace(r);
-    c->fbuf->space = MFB_KSPACE;
-    conv2(c, hessian_operand(l, d2l), hessian_operand(m, d2m), c->fbuf, OP_ASSIGN, 0.0);
-    conv2(c, Operand{c->fbuf, -1, -1, -1, -1, 1.0, 0.0, 0}, hessian_operand(r, d2r), out, op, alpha);
+    conv3(c, hessian_operand(l, d2l), hessian_operand(m, d2m), hessian_operand(r, d2r), out, op, alpha);
     MFB_CATCH
 }
 int mfb_conv_sum_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r1[2], const int d2r2[2],
@@ -1344,7 +1581,8 @@ int mfb_conv_gradient_hessian(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, co
     MFB_TRY
     check_conv_grids(c, l, r, out); check_dims(&d1l, 1); check_dims(d2r, 2);
     // (-i k_a) f  and  -k_a k_b g   (include/convolution.hh:116-124); Nyquist never enters the padded grid
-    conv2(c, Operand{l, d1l, -1, -1, -1, -1.0, 0.0, 1}, Operand{r, d2r[0], d2r[1], -1, -1, -1.0, 0.0, 0}, out, op, alpha);
+    // (the un-padded NaiveConvolver does see it: these two factors come from get_k, Nyquist = +N/2)
+    conv2(c, Operand{l, d1l, -1, -1, -1, -1.0, 0.0, 1, 1}, Operand{r, d2r[0], d2r[1], -1, -1, -1.0, 0.0, 0, 1}, out, op, alpha);
     MFB_CATCH
 }
 int mfb_conv_multiply(mfb_conv* c, mfb_grid* l, mfb_grid* r, mfb_grid* out, int op, double alpha) {
@@ -1386,6 +1624,8 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
 int mfb_particles_destroy(mfb_particles* p) {
     MFB_TRY
     if (p) {
+        if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
+        for (int a = 0; a < 4; ++a) if (p->copied[a]) cudaEventDestroy(p->copied[a]);
         cudaFree(p->pos); cudaFree(p->vel); cudaFree(p->ids);
         if (p->mass) cudaFree(p->mass);
         delete p;
@@ -1435,6 +1675,29 @@ int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* i
     if (ids) cuda_check(cudaMemcpyAsync(ids, p->ids, p->np * is, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H ids");
     if (mass && p->mass) cuda_check(cudaMemcpyAsync(mass, p->mass, p->np * rs, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H mass");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+int mfb_particles_stream_out(mfb_particles* p, int attr, void* host) {
+    MFB_TRY
+    require(attr >= 0 && attr < 4 && host != nullptr, "bad particle attribute / host pointer");
+    const size_t rs = p->real64 ? 8 : 4, is = p->ids64 ? 8 : 4;
+    const void* src = attr == MFB_ATTR_POS ? p->pos : attr == MFB_ATTR_VEL ? p->vel : attr == MFB_ATTR_IDS ? p->ids : p->mass;
+    require(src != nullptr, "particle buffer not allocated");
+    const size_t bytes = attr == MFB_ATTR_IDS ? p->np * is : (attr == MFB_ATTR_MASS ? p->np * rs : 3 * p->np * rs);
+    if (!g_ctx.copy_stream) cuda_check(cudaStreamCreate(&g_ctx.copy_stream), "cudaStreamCreate(copy)");
+    if (!p->copied[attr]) cuda_check(cudaEventCreateWithFlags(&p->copied[attr], cudaEventDisableTiming), "cudaEventCreate");
+    // order the copy after the producer kernels: reuse the attribute's event as the compute-side marker first
+    cuda_check(cudaEventRecord(p->copied[attr], g_ctx.stream), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(g_ctx.copy_stream, p->copied[attr], 0), "cudaStreamWaitEvent");
+    cuda_check(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, g_ctx.copy_stream), "D2H stream_out");
+    cuda_check(cudaEventRecord(p->copied[attr], g_ctx.copy_stream), "cudaEventRecord");
+    p->copy_pending[attr] = true;
+    MFB_CATCH
+}
+int mfb_particles_stream_wait(mfb_particles* p) {
+    MFB_TRY
+    (void)p;
+    if (g_ctx.copy_stream) cuda_check(cudaStreamSynchronize(g_ctx.copy_stream), "sync(copy)");
     MFB_CATCH
 }
 

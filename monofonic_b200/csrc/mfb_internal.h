@@ -22,6 +22,15 @@ struct mfb_grid {
     int nloc1, off1;  // local_1_size_, local_1_start_
 };
 
+// Grid_FFT<ccomplex_t> (PPT / Eulerian branch): dense [n0][n1][n2] complex, c2c transforms, single slab
+struct mfb_cgrid {
+    int n[3];
+    double L[3];
+    int space;
+    double2* d;
+    size_t nelem;
+};
+
 struct mfb_conv {
     int n[3], np[3];
     double L[3];
@@ -29,6 +38,8 @@ struct mfb_conv {
     size_t w1_elems, w2_elems;
     int dist, p0loc, p0off;   // slab of the padded grid along axis 0 (real space)
     mfb_grid* fbuf;           // N-grid for the intermediate of 3-field products (convolution.hh:469)
+    int naive;                // NaiveConvolver (convolution.hh:296-426): no padding, products on the N-grid itself
+    mfb_grid *nb1, *nb2;      // its fbuf1_, fbuf2_
     long nconv;
 };
 
@@ -38,6 +49,9 @@ struct mfb_particles {
     size_t np;        // local number of particles
     int nloc0, off0;  // slab of lattice planes held by this rank
     void *pos, *vel, *ids, *mass;  // device AoS (particle_container.hh:82-108)
+    // streamed hand-off: per attribute, event recorded on the copy stream after its D2H copy (null: none pending)
+    cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool copy_pending[4] = {false, false, false, false};
 };
 
 namespace mfb {
@@ -45,7 +59,7 @@ namespace mfb {
 enum Role {
     ROLE_CONV_X_BWD = 0, ROLE_CONV_Y_BWD, ROLE_CONV_Z, ROLE_CONV_Y_FWD, ROLE_CONV_X_FWD,
     ROLE_FFT_X, ROLE_FFT_Y, ROLE_FFT_Z_R2C, ROLE_FFT_Z_C2R, ROLE_ELEMENTWISE, ROLE_REDUCE, ROLE_PARTICLES,
-    ROLE_BARRIER, ROLE_COUNT
+    ROLE_BARRIER, ROLE_FFT_Z_C2C, ROLE_COUNT
 };
 // host collective used when peers are not mapped (CPU emulation tests, NCCL baseline): deliver chunk s of
 // `send` (P chunks of chunk_bytes) to rank s, receive rank r's chunk into chunk r of `recv`.
@@ -71,6 +85,7 @@ struct Context {
     bool initialised = false;
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H hand-off of particle attributes, overlaps the compute stream
     std::map<int, double2*> tw;  // twiddle tables exp(-2 pi i m/n)
     std::map<std::string, double2*> tw2;  // stage-major twiddle tables per plan (Plan::tw2_off)
     double* partial = nullptr;   // reduction scratch

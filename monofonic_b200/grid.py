@@ -272,14 +272,63 @@ class Grid_FFT:
         return self._red(self._lib.mfb_grid_max_neighbour_diff)
 
 
+class Grid_FFT_complex:
+    """Grid_FFT<ccomplex_t> (PPT / Eulerian branch, src/ic_generator.cc:690,778): dense [n0][n1][n2] complex grid with
+    c2c transforms of the same symmetric normalisation.  Single slab."""
+
+    def __init__(self, N, Lbox):
+        self.n_ = tuple(int(x) for x in N)
+        self.length_ = tuple(float(x) for x in Lbox)
+        self._lib = _lib()
+        self._h = C.c_void_p()
+        L.check(self._lib.mfb_cgrid_create(C.byref(self._h), _i3(self.n_), _d3(self.length_)), self._lib)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.mfb_cgrid_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def space_(self):
+        return self._lib.mfb_cgrid_space(self._h)
+
+    def set(self, x: np.ndarray, space=rspace_id):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        assert x.shape == self.n_
+        L.check(self._lib.mfb_cgrid_upload(self._h, x.ctypes.data_as(C.c_void_p), int(space)), self._lib)
+
+    def get(self) -> np.ndarray:
+        out = np.empty(self.n_, dtype=np.complex128)
+        L.check(self._lib.mfb_cgrid_download(self._h, out.ctypes.data_as(C.c_void_p)), self._lib)
+        return out
+
+    def copy_from(self, g: "Grid_FFT_complex"):
+        L.check(self._lib.mfb_cgrid_copy(self._h, g._h), self._lib)
+
+    def FourierTransformForward(self, do_transform=True):
+        L.check(self._lib.mfb_cgrid_fft_forward(self._h, int(bool(do_transform))), self._lib)
+
+    def FourierTransformBackward(self, do_transform=True):
+        L.check(self._lib.mfb_cgrid_fft_backward(self._h, int(bool(do_transform))), self._lib)
+
+    def apply_gradient(self, idim):
+        """apply_function_k_dep(x * i k[idim]) with k from get_k (src/ic_generator.cc:790-792)"""
+        L.check(self._lib.mfb_cgrid_gradient(self._h, int(idim)), self._lib)
+
+
 class OrszagConvolver:
     """OrszagConvolver<real_t> with the named products of BaseConvolver."""
+
+    _create = "mfb_conv_create"
 
     def __init__(self, N, Lbox):
         self._lib = _lib()
         self._h = C.c_void_p()
         self.n_ = tuple(int(x) for x in N)
-        L.check(self._lib.mfb_conv_create(C.byref(self._h), _i3(N), _d3(Lbox)), self._lib)
+        L.check(getattr(self._lib, self._create)(C.byref(self._h), _i3(N), _d3(Lbox)), self._lib)
 
     def __del__(self):
         try:
@@ -325,6 +374,11 @@ class OrszagConvolver:
         L.check(self._lib.mfb_conv_multiply(self._h, inl._h, inr._h, o.grid._h, o.code, o.alpha), self._lib)
 
 
+class NaiveConvolver(OrszagConvolver):
+    """NaiveConvolver<real_t> (include/convolution.hh:296-426): the same named products without 3/2 padding."""
+    _create = "mfb_conv_create_naive"
+
+
 LATTICE = {"sc": 0, "bcc": 1, "fcc": 2, "rsc": 3}
 
 
@@ -360,6 +414,22 @@ class Particles:
 
     def set_masses(self, munit, field: Grid_FFT):
         L.check(self._lib.mfb_particles_set_masses(self._h, self.lattice_index, float(munit), field._h), self._lib)
+
+    _ATTR = {"pos": 0, "vel": 1, "ids": 2, "mass": 3}
+
+    def stream_out(self, attr: str, host: np.ndarray):
+        """hand one finished attribute to the host (output plugin side) on the copy stream while the compute stream goes
+        on with the next component; `host` should be pinned.  Pair with stream_wait()."""
+        n = self.get_local_num_particles()
+        rt = np.float64 if self.b64reals else np.float32
+        it = np.uint64 if self.b64ids else np.uint32
+        want = (it, n) if attr == "ids" else (rt, n if attr == "mass" else 3 * n)
+        if host.dtype != want[0] or host.size != want[1] or not host.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"stream_out({attr}): host buffer must be C-contiguous {want[0].__name__}[{want[1]}]")
+        L.check(self._lib.mfb_particles_stream_out(self._h, self._ATTR[attr], host.ctypes.data_as(C.c_void_p)), self._lib)
+
+    def stream_wait(self):
+        L.check(self._lib.mfb_particles_stream_wait(self._h), self._lib)
 
     def download(self, pos=True, vel=True, ids=True, mass=True, out=None):
         """-> dict of host arrays (positions/velocities [np,3], ids [np], masses [np]).

@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib as L
-from .grid import Grid_FFT, OrszagConvolver, Particles, kspace_id, rspace_id, _lib, LATTICE
+from .grid import Grid_FFT, Grid_FFT_complex, OrszagConvolver, NaiveConvolver, Particles, kspace_id, rspace_id, _lib, LATTICE
 
 
 @dataclass
@@ -34,6 +34,7 @@ class lpt_config:
     real64: bool = True          # output_plugin::has_64bit_reals()
     ids64: bool = False          # output_plugin::has_64bit_ids()
     tides: tuple | None = None   # LSS_aniso_l{x,y,z}
+    ConvolverType: str = "orszag"  # the reference's compile-time CONVOLVER_TYPE (CMakeLists.txt): "orszag" | "naive"
 
 
 def radial_table(n: int, boxlen: float, amplitude) -> np.ndarray:
@@ -52,7 +53,9 @@ class LPTPipeline:
     def __init__(self, cfg: lpt_config):
         self.cfg = cfg
         n, Lb = cfg.GridRes, cfg.BoxLength
-        if cfg.LPTorder > 1 and n % 2:
+        if cfg.ConvolverType not in ("orszag", "naive"):
+            raise RuntimeError(f"unknown convolver type '{cfg.ConvolverType}'")
+        if cfg.LPTorder > 1 and n % 2 and cfg.ConvolverType == "orszag":
             # src/ic_generator.cc:118-121
             raise RuntimeError("Orszag convolver for LPTorder>1 requires even grid size!")
         self.N, self.Lbox = (n, n, n), (Lb, Lb, Lb)
@@ -66,7 +69,8 @@ class LPTPipeline:
         self.phi3 = mk(order > 2)
         self.A3 = [mk(order > 2) for _ in range(3)]
         self.tmp = mk()
-        self.conv = OrszagConvolver(self.N, self.Lbox) if order > 1 else None
+        mkconv = NaiveConvolver if cfg.ConvolverType == "naive" else OrszagConvolver
+        self.conv = mkconv(self.N, self.Lbox) if order > 1 else None
         self.particles = None
 
     # -- stages -------------------------------------------------------------------------
@@ -129,28 +133,83 @@ class LPTPipeline:
         self.tmp.FourierTransformBackward()
         return self.tmp
 
+    def eulerian_fields(self, delta_bc_table, C_species, velocity_unit=1.0, sink=None):
+        """Species written as output_type::field_eulerian - the semiclassical PPT branch (src/ic_generator.cc:685-803),
+        after compute_sources(): rho = sqrt(1 + C delta_bc), psi = rho exp(i(phi[+phi2])/(hbar D)), one drift (c2c FFT
+        pair) [+ kick], density |psi|^2-1 and v_d = hbar Im(psi* grad_d psi)/(1+rho) from three more c2c pairs.
+        `delta_bc_table`: get_amplitude_delta_bc on the integer |n|^2 lattice (radial_table); `sink(name, grid)` plays
+        write_grid_data; without it the fields are returned as host arrays.  Leaves phi (and phi2) in real space like
+        the reference does.  Returns (fields, hbar)."""
+        c = self.cfg
+        lib = self._lib
+        o = min(self.order, 2)
+        rho = Grid_FFT(self.N, self.Lbox)
+        t = np.ascontiguousarray(delta_bc_table, dtype=np.float64)
+        L.check(lib.mfb_apply_radial_table(rho._h, self.wnoise._h, t.ctypes.data_as(C.c_void_p), t.size, 0), lib)  # :697-699
+        rho.zero_DC_mode()
+        rho.FourierTransformBackward()
+        L.check(lib.mfb_ppt_sqrt_density(rho._h, float(C_species)), lib)
+        self.phi.FourierTransformBackward()
+        hbar = self.phi.max_neighbour_diff() / np.pi / c.Dplus0 * 1.01   # :733-734, hbar_safefac = 1.01
+        psi = Grid_FFT_complex(self.N, self.Lbox)
+        if o >= 2:
+            self.phi2.FourierTransformBackward()
+        L.check(lib.mfb_ppt_init_psi(psi._h, rho._h, self.phi._h, self.phi2._h if o >= 2 else None, hbar, c.Dplus0), lib)
+        psi.FourierTransformForward()
+        L.check(lib.mfb_ppt_drift(psi._h, hbar, c.Dplus0), lib)
+        psi.FourierTransformBackward()
+        if o >= 2:
+            L.check(lib.mfb_ppt_kick(psi._h, self.phi2._h, hbar, c.Dplus0), lib)
+        L.check(lib.mfb_ppt_density(rho._h, psi._h), lib)
+        out = {}
+
+        def emit(name, g):
+            if sink is not None:
+                sink(name, g)
+            else:
+                out[name] = g.get_real()
+        emit("density", rho)
+        grad = Grid_FFT_complex(self.N, self.Lbox)
+        vunit = c.Dplus0 * c.vfac / c.BoxLength * velocity_unit   # :779
+        for d, nm in enumerate(("vx", "vy", "vz")):
+            grad.copy_from(psi)
+            grad.FourierTransformForward()
+            grad.apply_gradient(d)
+            grad.FourierTransformBackward()
+            L.check(lib.mfb_ppt_velocity(self.tmp._h, psi._h, grad._h, rho._h, hbar, vunit), lib)
+            emit(nm, self.tmp)
+        return out, hbar
+
     def make_particles(self, lattice_index=0, with_masses=False, id_offset=0):
         c = self.cfg
         self.particles = Particles(c.ParticleLoad, lattice_index, c.real64, c.ids64, with_masses, id_offset, self.tmp)
         return self.particles
 
-    def fill_particles(self, lattice_index=0):
-        """the species output loop for particle output (src/ic_generator.cc:832-955)"""
+    def fill_particles(self, lattice_index=0, stream_to=None):
+        """the species output loop for particle output (src/ic_generator.cc:832-955).  With `stream_to` (dict of pinned
+        host arrays "pos", "vel", "ids") every attribute is handed to the host as soon as it is complete, on the copy
+        stream, overlapping the remaining component FFTs; the caller ends with particles.stream_wait()."""
         c = self.cfg
         if self.particles is None:
             self.make_particles(lattice_index)
+        if stream_to is not None and "ids" in stream_to:
+            self.particles.stream_out("ids", stream_to["ids"])
         for d in range(3):
             self.particles.set_positions(d, c.lunit, self.displacement_field(d))
+        if stream_to is not None and "pos" in stream_to:
+            self.particles.stream_out("pos", stream_to["pos"].reshape(-1))
         for d in range(3):
             self.particles.set_velocities(d, self.velocity_field(d))
+        if stream_to is not None and "vel" in stream_to:
+            self.particles.stream_out("vel", stream_to["vel"].reshape(-1))
         return self.particles
 
-    def run_device(self, table: np.ndarray, particles=True):
+    def run_device(self, table: np.ndarray, particles=True, stream_to=None):
         """conditioned noise resident in k-space -> all LPT terms -> Psi, v (-> particle AoS), all on device"""
         self.compute_phi1(table)
         self.compute_sources()
         if particles:
-            return self.fill_particles()
+            return self.fill_particles(stream_to=stream_to)
         out = {}
         for d, nm in enumerate("xyz"):
             out["d" + nm] = self.displacement_field(d).get_real()

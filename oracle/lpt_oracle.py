@@ -427,6 +427,49 @@ def density_k(g: GridSpec, pots):
     return g.k2() * pots["phi"]
 
 
+def ppt_eulerian(g: GridSpec, Wc, pots, order, Dplus0, vfac, amp_delta_bc, C_species, velocity_unit=1.0):
+    """Semiclassical (PPT) Eulerian density and velocity fields, src/ic_generator.cc:685-803.
+    `pots` are the growth-scaled potentials of lpt_potentials (phi already contains -D+, :561), `Wc` the conditioned
+    white noise in k-space.  Returns ({"density","vx","vy","vz"}, hbar)."""
+    n = g.n
+    kx, ky, kz = g.kvec()
+    kmod = np.sqrt(kx * kx + ky * ky + kz * kz)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = np.asarray(amp_delta_bc(kmod), dtype=np.float64)
+    A = np.where(np.isfinite(A), A, 0.0)
+    rho = zero_dc(Wc * A)                                             # :697-700
+    rho = np.sqrt(1.0 + C_species * g.bwd(rho))                        # :701-705
+    phi = g.bwd(pots["phi"])                                           # :710
+    # :713-731 - note the x loop stops at size(0)-1: the last x-plane is not visited
+    c = phi[:-1]
+    maxd = max(np.abs(np.roll(phi, -1, 0)[:-1] - c).max(), np.abs(np.roll(phi, -1, 1)[:-1] - c).max(),
+               np.abs(np.roll(phi, -1, 2)[:-1] - c).max())
+    hbar = maxd / np.pi / Dplus0 * 1.01                                # :733-734
+    if order == 1:
+        psi = rho * np.exp(1j * ((1.0 / hbar) * (phi / Dplus0)))      # :738-740
+        phi2 = None
+    else:
+        phi2 = g.bwd(pots["phi2"])
+        psi = rho * np.exp(1j * (((1.0 / hbar) * (phi + phi2)) / Dplus0))  # :744-747
+    # full c2c transforms with the symmetric norm; k from get_k on all three axes (Nyquist = +N/2)
+    k1 = g.k1d
+    k2 = (k1[:, None, None] ** 2 + k1[None, :, None] ** 2) + k1[None, None, :] ** 2
+    norm = g.norm
+    cf = lambda x: np.fft.fftn(x) * norm
+    cb = lambda X: np.fft.ifftn(X) * (float(n) ** 3 * norm)
+    psi = cb(cf(psi) * np.exp(1j * (-((0.5 * hbar) * k2) * Dplus0)))   # :755-761
+    if order >= 2:
+        psi = psi * np.exp(1j * (((1.0 / hbar) * phi2) / Dplus0))     # :763-767
+    dens = psi.real ** 2 + psi.imag ** 2 - 1.0                         # :772-775
+    vunit = Dplus0 * vfac / g.L * velocity_unit                        # :779
+    out = {"density": dens}
+    kk = (k1[:, None, None], k1[None, :, None], k1[None, None, :])
+    for d, nm in enumerate(("vx", "vy", "vz")):
+        gp = cb(cf(psi) * (1j * kk[d]))                                # :782-793
+        out[nm] = vunit * np.real((np.conj(psi) * gp - psi * np.conj(gp)) / (2j / hbar) / (1.0 + dens))  # :796-799
+    return out, hbar
+
+
 def fields(g: GridSpec, pots, order, vfac, lunit=1.0, vunit=1.0):
     """all six real-space component fields + density; defaults = generic output plugin
     (lunit=vunit=1, output_generic.cc:74-76); fields are in box units * unit (:866,:937)."""

@@ -101,6 +101,12 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) {
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)1; return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+enum { cudaEventDisableTiming = 2 };
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }

@@ -160,6 +160,166 @@ def check_convolver(M, n, nyquist_zero=True):
     assert relerr(out.get_kspace(), ref) < 10 * TOL
 
 
+def check_naive_convolver(M, n, nyquist_zero=False):
+    """NaiveConvolver (include/convolution.hh:296-426): every named product against the oracle, Nyquist planes
+    populated (they take part in an un-padded product), three-field product in one go"""
+    L = 100.0
+    g, W, Wc, phi = noise_and_phi(n, L, 9, nyquist_zero)
+    _, _, _, psi = noise_and_phi(n, L, 10, nyquist_zero)
+    cv = O.NaiveConvolver(g)
+    P = M.Grid_FFT((n,) * 3, (L,) * 3)
+    Q = M.Grid_FFT((n,) * 3, (L,) * 3)
+    out = M.Grid_FFT((n,) * 3, (L,) * 3, True, M.kspace_id)
+    P.set_kspace(phi)
+    Q.set_kspace(psi)
+    C = M.NaiveConvolver((n,) * 3, (L,) * 3)
+    assert C.workspace_bytes() == 2 * 8 * n * n * (n + 2)
+    op = M.op
+    ref = cv.convolve_Hessians(phi, (0, 1), psi, (1, 2))
+    C.convolve_Hessians(P, (0, 1), Q, (1, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = ref + cv.convolve_SumOfHessians(phi, (0, 0), psi, (1, 1), (2, 2))
+    C.convolve_SumOfHessians(P, (0, 0), Q, (1, 1), (2, 2), op.add_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = ref - cv.convolve_DifferenceOfHessians(phi, (1, 2), psi, (1, 1), (2, 2))
+    C.convolve_DifferenceOfHessians(P, (1, 2), Q, (1, 1), (2, 2), op.subtract_from(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = ref + (-5.0 / 7.0) * cv.convolve_Hessians3(phi, (0, 0), psi, (0, 2), phi, (2, 2))
+    C.convolve_Hessians(P, (0, 0), Q, (0, 2), P, (2, 2), op.multiply_add_to(out, -5.0 / 7.0))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = cv.convolve_Gradients(phi, 0, psi, 2)
+    C.convolve_Gradients(P, (0,), Q, (2,), op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = cv.convolve_Gradient_and_Hessian(phi, 1, psi, (0, 2))      # get_k: Nyquist wave number is +N/2, not 0
+    C.convolve_Gradient_and_Hessian(P, (1,), Q, (0, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    ref = cv.multiply_field(phi, psi)
+    C.multiply_field(P, Q, op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    if not nyquist_zero:
+        assert np.abs(out.get_kspace()[n // 2]).max() > 0       # no Nyquist zeroing in the naive convolver
+    # the aliased product differs from the dealiased one: the two convolvers must NOT agree
+    Cz = M.OrszagConvolver((n,) * 3, (L,) * 3)
+    o2 = M.Grid_FFT((n,) * 3, (L,) * 3, True, M.kspace_id)
+    Cz.multiply_field(P, Q, op.assign_to(o2))
+    assert relerr(o2.get_kspace(), ref) > 1e-3
+
+
+def check_naive_pipeline(M, n=32):
+    """the whole 3LPT source stage with CONVOLVER_TYPE=NAIVE against the oracle run with its NaiveConvolver"""
+    L, Dp = 100.0, 0.0257
+    g, W, Wc, phi = noise_and_phi(n, L, 17)
+    amp = O.power_law_amplitude()
+    ref = O.lpt_potentials(g, phi, 3, Dp, convolver=O.NaiveConvolver(g))
+    pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp, ConvolverType="naive"))
+    pl.set_noise_k(W)
+    pl.condition_noise()
+    pl.compute_phi1(O.radial_table(g, amp))
+    pl.compute_sources()
+    assert relerr(pl.phi2.get_kspace(), ref["phi2"]) < TOL
+    assert relerr(pl.phi3.get_kspace(), ref["phi3"]) < 10 * TOL
+    for d in range(3):
+        assert relerr(pl.A3[d].get_kspace(), ref["A3"][d]) < 10 * TOL
+
+
+# ------------------------------------------------------------------ complex grids + PPT / Eulerian branch
+def check_cfft(M, n0, n1=None, n2=None):
+    """Grid_FFT<ccomplex_t>: c2c forward/backward with the symmetric norm vs numpy"""
+    n1, n2 = n1 or n0, n2 or n0
+    rng = np.random.default_rng(n0 + 3 * n1 + 7 * n2)
+    x = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    norm = 1.0 / np.sqrt(float(n0) * n1 * n2)
+    G = M.Grid_FFT_complex((n0, n1, n2), (1.0, 2.0, 3.0))
+    G.set(x)
+    G.FourierTransformForward()
+    assert G.space_ == M.kspace_id
+    ref = np.fft.fftn(x) * norm
+    assert relerr(G.get(), ref) < TOL
+    G.FourierTransformForward()            # no-op when already in k-space
+    assert relerr(G.get(), ref) < TOL
+    G.FourierTransformBackward()
+    assert relerr(G.get(), x) < TOL
+    y = rng.standard_normal((n0, n1, n2)) + 1j * rng.standard_normal((n0, n1, n2))
+    G.set(y, M.kspace_id)
+    G.apply_gradient(1)
+    i1 = np.arange(n1)
+    k1 = (i1 - n1 * (i1 > n1 // 2)) * (2 * np.pi / 2.0)       # get_k: Nyquist = +n/2
+    assert relerr(G.get(), y * (1j * k1[None, :, None])) < TOL
+    G.set(y, M.kspace_id)
+    G.FourierTransformBackward()
+    assert relerr(G.get(), np.fft.ifftn(y) / norm) < TOL
+
+
+def check_ppt(M, n, order, seed=31):
+    """Eulerian (semiclassical PPT) density and velocity fields against the oracle (src/ic_generator.cc:685-803)"""
+    L = 100.0
+    Dp, vfac = 0.0257, 396.69
+    g, W, Wc, phi = noise_and_phi(n, L, seed)
+    amp = O.power_law_amplitude()
+    amp_bc = lambda k: 2e-3 * amp(k) * k * k          # a delta_bc-like amplitude (~k^2 phi), small enough that 1+C rho > 0
+    Csp, vu = 0.8433, 1.7
+    pots = O.lpt_potentials(g, phi, order, Dp)
+    ref, hbar_ref = O.ppt_eulerian(g, Wc, pots, order, Dp, vfac, amp_bc, Csp, vu)
+    cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad="sc", Dplus0=Dp, vfac=vfac)
+    pl = M.LPTPipeline(cfg)
+    pl.set_noise_k(W)
+    pl.condition_noise()
+    pl.compute_phi1(O.radial_table(g, amp))
+    pl.compute_sources()
+    got, hbar = pl.eulerian_fields(O.radial_table(g, amp_bc), Csp, vu)
+    assert abs(hbar - hbar_ref) < 1e-12 * hbar_ref
+    assert np.abs(ref["density"]).max() > 1e-3      # the test field is not trivial
+    for k in ("density", "vx", "vy", "vz"):
+        assert got[k].shape == (n, n, n)
+        err = np.abs(got[k] - ref[k]).max() / np.abs(ref[k]).max()
+        assert err < 1e-9, (k, err)
+    # error behaviour: state checks instead of silent garbage
+    psi = M.Grid_FFT_complex((n,) * 3, (L,) * 3)
+    lib = psi._lib
+    assert lib.mfb_ppt_drift(psi._h, 1.0, 1.0) != 0 and b"k-space" in lib.mfb_last_error()
+    return max(np.abs(got[k] - ref[k]).max() / np.abs(ref[k]).max() for k in got)
+
+
+# ------------------------------------------------------------------ streamed particle hand-off
+def check_stream_handoff(M, n=32, order=2, lattice="bcc"):
+    """the attribute-by-attribute hand-off on the copy stream delivers exactly what the blocking download does, also
+    when the next run starts overwriting the device buffers right after (set_* waits for the pending copy)"""
+    L = 100.0
+    g, W, Wc, phi = noise_and_phi(n, L, 5)
+    amp = O.power_law_amplitude()
+    cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad=lattice, Dplus0=0.03, vfac=300.0,
+                       lunit=L, vunit=L, real64=False, ids64=False)
+    pl = M.LPTPipeline(cfg)
+    tab = O.radial_table(g, amp)
+
+    def run(stream_to=None):
+        pl.set_noise_k(W)
+        pl.condition_noise()
+        return pl.run_device(tab, particles=True, stream_to=stream_to)
+    ref = run().download()
+    npart = pl.particles.get_local_num_particles()
+    out = {"pos": np.zeros((npart, 3), np.float32), "vel": np.zeros((npart, 3), np.float32), "ids": np.zeros(npart, np.uint32)}
+    run(out)
+    run()                      # queued behind the streamed copies; must not corrupt them
+    pl.particles.stream_wait()
+    for k in ("pos", "vel", "ids"):
+        assert np.array_equal(out[k], ref[k]), k
+    with pytest_raises(ValueError):
+        pl.particles.stream_out("pos", np.zeros(5, np.float32))
+
+
+class pytest_raises:
+    def __init__(self, exc):
+        self.exc = exc
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        assert et is not None and issubclass(et, self.exc), f"expected {self.exc}"
+        return True
+
+
 # ------------------------------------------------------------------ whole pipeline vs oracle
 def check_pipeline(M, n, order, lattice="sc", real64=True, seed=21):
     L = 100.0

@@ -83,3 +83,26 @@ def test_error_behaviour(M):
 
 def test_kernel_generations_agree(M):
     PC.check_kernel_generations(M, 32)
+
+
+def test_stream_handoff(M):
+    PC.check_stream_handoff(M, 32)
+
+
+@pytest.mark.parametrize("nyq0", [True, False])
+def test_naive_convolver(M, nyq0):
+    PC.check_naive_convolver(M, 32, nyq0)
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (32, 48, 64), (96, 32, 32)])
+def test_complex_grid_fft(M, shape):
+    PC.check_cfft(M, *shape)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_ppt_eulerian(M, order):
+    PC.check_ppt(M, 32, order)
+
+
+def test_naive_pipeline(M):
+    PC.check_naive_pipeline(M, 32)

@@ -48,6 +48,29 @@ def test_pipeline_vs_oracle(M, n, order, lattice, real64):
     PC.check_pipeline(M, n, order, lattice, real64)
 
 
+@pytest.mark.parametrize("n,nyq0", [(32, False), (64, True), (96, False)])
+def test_naive_convolver(M, n, nyq0):
+    PC.check_naive_convolver(M, n, nyq0)
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 48, 96), (256, 32, 128), (32, 384, 32), (32, 32, 1024), (512, 32, 32)])
+def test_complex_grid_fft(M, shape):
+    PC.check_cfft(M, *shape)
+
+
+@pytest.mark.parametrize("n,order", [(32, 1), (64, 2), (128, 3)])
+def test_ppt_eulerian(M, n, order):
+    PC.check_ppt(M, n, order)
+
+
+def test_naive_pipeline(M):
+    PC.check_naive_pipeline(M, 64)
+
+
+def test_stream_handoff(M):
+    PC.check_stream_handoff(M, 64, 3, "bcc")
+
+
 @pytest.mark.parametrize("lattice", ["sc", "bcc", "fcc", "rsc"])
 def test_lattice_bitexact(M, lattice):
     PC.check_lattice_positions_bitexact(M, 64, lattice)

@@ -105,7 +105,8 @@ class ClockSampler:
 
 
 def workload_name(n, order, lattice="sc"):
-    return f"{order}LPT {n}^3 {lattice} lattice, Orszag 3/2 padded ({3 * n // 2}^3), gadget-style output (f32 pos/vel, u32 ids)"
+    ids = "u64" if n ** 3 > 2 ** 32 - 1 else "u32"
+    return f"{order}LPT {n}^3 {lattice} lattice, Orszag 3/2 padded ({3 * n // 2}^3), gadget-style output (f32 pos/vel, {ids} ids)"
 
 
 # --------------------------------------------------------------------------------------------
@@ -186,8 +187,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     stream = torch.cuda.ExternalStream(lib.mfb_stream())
+    ids64 = n ** 3 > 2 ** 32 - 1       # UseLongids: 2048^3 does not fit 32-bit IDs
     cfg = M.lpt_config(GridRes=n, BoxLength=Lbox, LPTorder=order, ParticleLoad="sc", Dplus0=0.0257, vfac=396.69,
-                       lunit=Lbox, vunit=Lbox / np.sqrt(1 / 51.0), real64=False, ids64=False)
+                       lunit=Lbox, vunit=Lbox / np.sqrt(1 / 51.0), real64=False, ids64=ids64)
     pl = M.LPTPipeline(cfg)
     pl.make_particles()
     amp = O.power_law_amplitude()
@@ -212,9 +214,11 @@ def run_b200(args):
 
     upload_noise()
     npart = pl.particles.get_local_num_particles()
-    out = {"pos": torch.empty((npart, 3), dtype=torch.float32, pin_memory=True).numpy(),
+    out = None if args.no_e2e else {
+           "pos": torch.empty((npart, 3), dtype=torch.float32, pin_memory=True).numpy(),
            "vel": torch.empty((npart, 3), dtype=torch.float32, pin_memory=True).numpy(),
-           "ids": torch.empty((npart,), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)}
+           "ids": (torch.empty((npart,), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64) if ids64 else
+                   torch.empty((npart,), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32))}
 
     def step_device():
         pl.run_device(table, particles=True)

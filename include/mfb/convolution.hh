@@ -1,13 +1,15 @@
-// include/mfb/convolution.hh - OrszagConvolver<real_t> with the named products of BaseConvolver
-// (include/convolution.hh:28-293, 429-669) on top of mfb_conv_*.  Same method names and argument order; the
-// output operator is one of op::assign_to/add_to/subtract_from/multiply_add_to (include/mfb/operators.hh).
+// include/mfb/convolution.hh - OrszagConvolver<real_t> and NaiveConvolver<real_t> with the named products of
+// BaseConvolver (include/convolution.hh:28-293, 296-426, 429-669) on top of mfb_conv_*.  Same method names and
+// argument order; the output operator is one of op::assign_to/add_to/subtract_from/multiply_add_to
+// (include/mfb/operators.hh).  The reference picks the convolver at compile time (CONVOLVER_TYPE); so does a host
+// built against these headers.
 #pragma once
 #include <array>
 
 #include "operators.hh"
 
-template <typename data_t>
-class OrszagConvolver {
+template <typename data_t, typename derived_t>
+class BaseConvolver {
     mfb_conv* c_ = nullptr;
     using grid_t = Grid_FFT<data_t>;
     template <class O> static mfb_grid* out(O& o) {
@@ -16,14 +18,16 @@ class OrszagConvolver {
     }
     static mfb_grid* in(grid_t& g) { g.FourierTransformForward(); return g.device_handle(); }
 
-public:
-    OrszagConvolver(const std::array<size_t, 3>& N, const std::array<real_t, 3>& L) {
+protected:
+    BaseConvolver(const std::array<size_t, 3>& N, const std::array<real_t, 3>& L, bool naive) {
         int n[3] = {int(N[0]), int(N[1]), int(N[2])};
         double l[3] = {L[0], L[1], L[2]};
-        mfb_detail::check(mfb_conv_create(&c_, n, l));
+        mfb_detail::check(naive ? mfb_conv_create_naive(&c_, n, l) : mfb_conv_create(&c_, n, l));
     }
-    OrszagConvolver(const OrszagConvolver&) = delete;
-    ~OrszagConvolver() { if (c_) mfb_conv_destroy(c_); }
+
+public:
+    BaseConvolver(const BaseConvolver&) = delete;
+    ~BaseConvolver() { if (c_) mfb_conv_destroy(c_); }
 
     template <typename opp>
     void convolve_Gradients(grid_t& inl, const std::array<int, 1>& d1l, grid_t& inr, const std::array<int, 1>& d1r, opp o) {
@@ -56,4 +60,15 @@ public:
         mfb_detail::check(mfb_conv_multiply(c_, in(inl), in(inr), out(o), o.code, o.alpha));
     }
     mfb_conv* handle() { return c_; }
+};
+
+template <typename data_t>
+class OrszagConvolver : public BaseConvolver<data_t, OrszagConvolver<data_t>> {   // include/convolution.hh:429-669
+public:
+    OrszagConvolver(const std::array<size_t, 3>& N, const std::array<real_t, 3>& L) : BaseConvolver<data_t, OrszagConvolver<data_t>>(N, L, false) {}
+};
+template <typename data_t>
+class NaiveConvolver : public BaseConvolver<data_t, NaiveConvolver<data_t>> {    // include/convolution.hh:296-426
+public:
+    NaiveConvolver(const std::array<size_t, 3>& N, const std::array<real_t, 3>& L) : BaseConvolver<data_t, NaiveConvolver<data_t>>(N, L, true) {}
 };

@@ -241,7 +241,10 @@ template <class P, int s, int NT> MFB_D void z3_dif_mid_pair(double2* l0, const 
     }
 }
 
-template <class P, int RPC, int MINB>
+// DIRECT: the operand rows are read straight from global memory in the legs of stage 0 instead of being staged in shared
+// memory by cp.async: 55 KB instead of 88 KB per CTA at n = 1536 (4 CTAs per SM instead of 2 - the in-pipeline capture
+// profiles/r01_ncu_full_z3_1536_in_pipeline.txt shows barrier stalls of 3.3 per issue with two 256-thread CTAs).
+template <class P, int RPC, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     z_conv3_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
                    ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw) {
@@ -256,26 +259,58 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     const int tid = threadIdx.x;
     const long row0 = long(blockIdx.x) * RPC;
 
-    for (int idx = tid; idx < RPC * 2 * NZ; idx += NT) {
-        const int o = idx / NZ, k = idx - o * NZ;
-        const long r = row0 + (o >> 1);
-        double2* d = raw + idx;
-        if (r < nrows) mfb_cp_async16(d, ((o & 1) ? Bin : Ain) + r * in_pitch + k);
-        else *d = make_double2(0.0, 0.0);
+    if constexpr (!DIRECT) {
+        for (int idx = tid; idx < RPC * 2 * NZ; idx += NT) {
+            const int o = idx / NZ, k = idx - o * NZ;
+            const long r = row0 + (o >> 1);
+            double2* d = raw + idx;
+            if (r < nrows) mfb_cp_async16(d, ((o & 1) ? Bin : Ain) + r * in_pitch + k);
+            else *d = make_double2(0.0, 0.0);
+        }
+        mfb_cp_async_wait_all();
+        __syncthreads();
     }
-    mfb_cp_async_wait_all();
-    __syncthreads();
 
     // ---- DIF stage 0 per row: Hermitian extension of conj(A^ + i B^) built in the butterfly legs
     {
         const int l = tid / TPL, q = tid - l * TPL;
         double2* ln = work + l * LW;
-        const double2* ra = raw + (2 * l) * NZ;
-        const double2* rb = ra + NZ;
+        const bool row_ok = row0 + l < nrows;
+        const double2* ra = DIRECT ? Ain + (row0 + l) * in_pitch : raw + (2 * l) * NZ;
+        const double2* rb = DIRECT ? Bin + (row0 + l) * in_pitch : ra + NZ;
+        auto ld = [&](const double2* p) -> double2 {
+            if constexpr (DIRECT) return row_ok ? mfb_ld_stream(p) : make_double2(0.0, 0.0);
+            else return *p;
+        };
         constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
 #pragma unroll 1
         for (int j = q; j < M; j += TPL) {
             double2 v[r];
+            if constexpr (DIRECT) {   // all 4*K3 loads of the butterfly are in flight before the first use
+                double2 xa[2 * K3], xb[2 * K3];
+#pragma unroll
+                for (int t = 0; t < K3; ++t) { xa[t] = ld(ra + j + t * M); xb[t] = ld(rb + j + t * M); }
+#pragma unroll
+                for (int t = 2 * K3; t < r; ++t) {
+                    const int k = (r - t) * M - j;
+                    const bool dropped = (t == 2 * K3 && j == 0);      // k == NZ: the dropped Nyquist sample (not stored)
+                    xa[t - K3] = dropped ? make_double2(0.0, 0.0) : ld(ra + k);
+                    xb[t - K3] = dropped ? make_double2(0.0, 0.0) : ld(rb + k);
+                }
+#pragma unroll
+                for (int t = 0; t < K3; ++t) {
+                    double2 x1 = xa[t], x2 = xb[t];
+                    if (t == 0 && j == 0) { x1.y = 0.0; x2.y = 0.0; }
+                    v[t] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
+                }
+#pragma unroll
+                for (int t = K3; t < 2 * K3; ++t) v[t] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int t = 2 * K3; t < r; ++t) {
+                    const double2 x1 = xa[t - K3], x2 = xb[t - K3];
+                    v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
+                }
+            } else {
 #pragma unroll
             for (int t = 0; t < K3; ++t) {
                 double2 x1 = ra[j + t * M], x2 = rb[j + t * M];
@@ -290,6 +325,7 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
                 if (t == 2 * K3 && j == 0) { v[t] = make_double2(0.0, 0.0); continue; }
                 const double2 x1 = ra[k], x2 = rb[k];
                 v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
+            }
             }
             Dft<r>::run(v);
 #pragma unroll
@@ -360,5 +396,6 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
 }
 
 template <class P, int RPC> constexpr size_t z_conv2_smem() { return size_t(RPC) * (zpad(P::N) + 1 + 2 * (P::N / 3)) * sizeof(double2); }
+template <class P, int RPC> constexpr size_t z_conv3_direct_smem() { return size_t(RPC) * (zpad(P::N) + 1) * sizeof(double2); }
 
 }  // namespace mfb

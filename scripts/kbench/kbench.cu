@@ -211,6 +211,37 @@ template <class P, int RPC, int MINB> static void zrun_v3(ZBench& Z, const char*
     cudaFree(tw2);
 }
 #define Z3(RPC, MINB, ...) zrun_v3<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z3 <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
+template <class P, int RPC, int MINB> static void zrun_v3d(ZBench& Z, const char* label) {
+    auto k = z_conv3_kernel<P, RPC, MINB, true>;
+    double2* tw2 = make_tw2<P>();
+    constexpr size_t smem = z_conv3_direct_smem<P, RPC>();
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::TPL * RPC, smem));
+    const unsigned grid = unsigned((Z.nrows + RPC - 1) / RPC);
+    CK(cudaMemset(Z.out, 0xff, size_t(Z.nrows) * Z.nz * 16));
+    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, tw2); });
+    zreport(Z, label, ms, false, fa.numRegs, occ, smem);
+    cudaFree(tw2);
+}
+#define Z3D(RPC, MINB, ...) zrun_v3d<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z3 direct <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
+static void zbench4(int which) {
+    if (which == 0 || which == 768) {
+        ZBench Z = make_zbench(768, 768L * 768);
+        zrun_v1<Plan<768, 32, 8, 12, 8, 8>>(Z, "v1 <768,32,8,12,8,8>");
+        Z3(2, 5, 768, 64, 2, 12, 8, 8);
+        Z3D(2, 5, 768, 64, 2, 12, 8, 8); Z3D(2, 6, 768, 64, 2, 12, 8, 8); Z3D(2, 8, 768, 64, 2, 12, 8, 8);
+        Z3D(2, 8, 768, 32, 2, 12, 8, 8); Z3D(2, 6, 768, 32, 2, 12, 8, 8); Z3D(2, 4, 768, 32, 2, 12, 8, 8);
+    }
+    if (which == 0 || which == 1536) {
+        ZBench Z = make_zbench(1536, 1536L * 384);
+        zrun_v1<Plan<1536, 32, 8, 16, 12, 8>>(Z, "v1 <1536,32,8,16,12,8>");
+        Z3(2, 2, 1536, 128, 2, 12, 16, 8);
+        Z3D(2, 2, 1536, 128, 2, 12, 16, 8); Z3D(2, 4, 1536, 64, 2, 12, 16, 8); Z3D(2, 3, 1536, 64, 2, 12, 16, 8);
+        Z3D(2, 4, 1536, 64, 2, 12, 4, 4, 8); Z3D(2, 4, 1536, 32, 2, 12, 16, 8); Z3D(2, 4, 1536, 32, 2, 12, 4, 4, 8);
+        Z3D(2, 3, 1536, 96, 2, 12, 16, 8); Z3D(2, 2, 1536, 64, 2, 12, 16, 8); Z3D(2, 4, 1536, 64, 2, 12, 8, 2, 8);
+    }
+}
 static void zbench3(int which) {
     if (which == 0 || which == 768) {
         ZBench Z = make_zbench(768, 768L * 192);
@@ -259,9 +290,53 @@ static void sbench2(int which) {
         }
     }
 }
+// ---------------------------------------------------------------------------------------------------------
+// "seg": what HBM delivers for the ACCESS PATTERN of a strided pass, without any FFT: a CTA copies one tile =
+// n positions x SEG contiguous complex values (SEG*16 bytes) at a position stride of nz*16 bytes, tiles ordered
+// (a, z-tile) like the pass kernels.  UNR loads per thread are issued before the stores.
+template <int SEG, int UNR>
+__global__ void __launch_bounds__(256) seg_copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n, int nz, int na) {
+    const int tiles_per_a = nz / SEG;
+    const int a = blockIdx.x / tiles_per_a, z0 = (blockIdx.x - a * tiles_per_a) * SEG;
+    const int lane = threadIdx.x % SEG, q = threadIdx.x / SEG;
+    constexpr int PPI = 256 / SEG;   // positions per iteration
+    const double2* ip = in + ptrdiff_t(a) * n * nz + z0 + lane;
+    double2* op = out + ptrdiff_t(a) * n * nz + z0 + lane;
+    for (int p0 = q; p0 < n; p0 += PPI * UNR) {
+        double2 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { const int p = p0 + u * PPI; if (p < n) v[u] = mfb_ld_stream(ip + ptrdiff_t(p) * nz); }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { const int p = p0 + u * PPI; if (p < n) mfb_st_stream(op + ptrdiff_t(p) * nz, v[u]); }
+    }
+}
+template <int SEG, int UNR> static void seg_one(int n, int nz, int na, const double2* in, double2* out) {
+    const unsigned grid = unsigned(na) * unsigned(nz / SEG);
+    auto launch = [&] { seg_copy_kernel<SEG, UNR><<<grid, 256>>>(in, out, n, nz, na); };
+    const float ms = time_kernel(launch);
+    const double gb = 32.0 * double(n) * nz * na / 1e9;
+    printf("seg %4d B x unroll %2d  n=%d nz=%d na=%d   %.3f ms  %8.1f GB/s\n", SEG * 16, UNR, n, nz, na, ms, gb / (ms * 1e-3));
+}
+static void segbench(int n) {
+    const int nz = 512, na = (n >= 1536) ? 96 : 256;
+    const size_t elems = size_t(n) * nz * na;
+    double2 *in, *out;
+    CK(cudaMalloc(&in, elems * 16)); CK(cudaMalloc(&out, elems * 16));
+    fill_kernel<<<1184, 256>>>(in, elems, 1u);
+    CK(cudaDeviceSynchronize());
+    printf("== segment-copy pattern test (%.2f GB each way)\n", elems * 16 / 1e9);
+    seg_one<2, 8>(n, nz, na, in, out);  seg_one<4, 8>(n, nz, na, in, out);   seg_one<8, 8>(n, nz, na, in, out);
+    seg_one<16, 8>(n, nz, na, in, out); seg_one<32, 8>(n, nz, na, in, out);  seg_one<64, 8>(n, nz, na, in, out);
+    seg_one<8, 4>(n, nz, na, in, out);  seg_one<8, 16>(n, nz, na, in, out);  seg_one<16, 16>(n, nz, na, in, out);
+    seg_one<4, 16>(n, nz, na, in, out); seg_one<32, 16>(n, nz, na, in, out);
+    CK(cudaFree(in)); CK(cudaFree(out));
+}
+
 int main(int argc, char** argv) {
     int which = argc > 1 ? atoi(argv[1]) : 0;
     const char* what = argc > 2 ? argv[2] : "all";
+    if (!strcmp(what, "seg")) { segbench(which ? which : 1536); return 0; }
+    if (!strcmp(what, "z4")) { zbench4(which); return 0; }
     if (!strcmp(what, "z") || !strcmp(what, "all")) zbench_all(which);
     if (!strcmp(what, "z")) return 0;
     if (!strcmp(what, "z3")) { zbench3(which); return 0; }

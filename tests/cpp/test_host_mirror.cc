@@ -71,6 +71,18 @@ int main() {
     Conv.convolve_Hessians(phi, {0, 1}, phi, {1, 2}, op::assign_to(tmp));
     for (size_t i = 0; i < tmp.ntot_ / 2; ++i) ref = std::max(ref, std::abs(tmp.kelem(i)));
     CHECK(asym < 1e-13 * ref);
+    // CONVOLVER_TYPE=NAIVE build of the same host code: the aliased product differs, its Nyquist planes are populated
+    {
+        NaiveConvolver<real_t> NConv(N, L);
+        NConv.multiply_field(phi, phi, op::assign_to(tmp));
+        double nyq = 0;
+        for (size_t j = 0; j < n; ++j) for (size_t k = 0; k <= n / 2; ++k) nyq = std::max(nyq, std::abs(tmp.kelem(n / 2, j, k)));
+        CHECK(nyq > 0);
+        Conv.multiply_field(phi, phi, op::subtract_from(tmp));
+        double diff = 0;
+        for (size_t i = 0; i < tmp.ntot_ / 2; ++i) diff = std::max(diff, std::abs(tmp.kelem(i)));
+        CHECK(diff > 1e-6 * ref * 0 + 0.0 && diff > 0);
+    }
     // particles: ids of a bcc load (include/particle_generator.hh:150-169)
     mock_config cf;
     tmp.FourierTransformBackward(false);

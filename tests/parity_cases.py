@@ -202,7 +202,9 @@ def check_naive_convolver(M, n, nyquist_zero=False):
     Cz = M.OrszagConvolver((n,) * 3, (L,) * 3)
     o2 = M.Grid_FFT((n,) * 3, (L,) * 3, True, M.kspace_id)
     Cz.multiply_field(P, Q, op.assign_to(o2))
-    assert relerr(o2.get_kspace(), ref) > 1e-3
+    dealiased = o2.get_kspace()
+    assert relerr(dealiased, ref) > 1e-10                        # far above round-off (the spectra are red: aliasing is small)
+    assert not dealiased[n // 2].any() and np.abs(ref[n // 2]).max() > 0   # Orszag zeroes the Nyquist planes, Naive fills them
 
 
 def check_naive_pipeline(M, n=32):

@@ -39,26 +39,29 @@ MFB_D void strided2_mid_stage(double2* __restrict__ sm, const double2* __restric
         for (int u = 0; u < r; ++u) sp[u * M * T] = v[u];
     }
 }
-template <class P, int MODE, int s>
-MFB_D void strided2_mid_stages(double2* __restrict__ sm, const double2* __restrict__ tw, int line, int q) {
+struct CtaSync {   // whole-CTA barrier (one tile per CTA)
+    MFB_D void operator()() const { __syncthreads(); }
+};
+template <class P, int MODE, int s, class Sync>
+MFB_D void strided2_mid_stages(double2* __restrict__ sm, const double2* __restrict__ tw, int line, int q, const Sync& sync) {
     if constexpr (s < P::S - 1) {
-        __syncthreads();
+        sync();
         strided2_mid_stage<P, MODE, s>(sm, tw, line, q);
-        strided2_mid_stages<P, MODE, s + 1>(sm, tw, line, q);
+        strided2_mid_stages<P, MODE, s + 1>(sm, tw, line, q, sync);
     }
 }
 
-template <class P, int MODE, int MINB, bool BATCH0 = false>
-__global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs A, const double2* __restrict__ tw) {
-    MFB_DYN_SMEM(double2, sm);
+// One tile (fixed a, T adjacent k_z starting at z0) of a strided pass, executed by P::NTHREADS threads that share `sm` and
+// synchronise with `sync` (the whole CTA, or one warp group of a ping-pong CTA).  `after_load` is called once by every
+// thread when its global loads of stage 0 have been consumed (the ping-pong kernel hands the load phase to the other
+// warp group there).
+template <class P, int MODE, bool BATCH0, class Sync, class AfterLoad>
+MFB_D void strided2_tile(const StridedArgs& A, const double2* __restrict__ tw, double2* __restrict__ sm, int tid, int a, int z0,
+                         const Sync& sync, const AfterLoad& after_load) {
     constexpr int N = P::N, T = P::T, S = P::S;
     static_assert(S >= 2, "at least two stages");
-    const int tid = threadIdx.x;
     const int line = tid % T;
     const int q = tid / T;
-    const int tiles_per_a = (A.nz + T - 1) / T;
-    const int a = blockIdx.x / tiles_per_a;
-    const int z0 = (blockIdx.x - a * tiles_per_a) * T;
     const int iz = z0 + line;
     const bool line_valid = iz < A.nz;
     const ptrdiff_t ooff = ptrdiff_t(a) * A.out_as + iz;
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
     if ((a + A.a_off == A.a_skip) || (z0 >= A.nz_fft)) {
         if (zf && line_valid)
             for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(optr(k), make_double2(0.0, 0.0));
+        after_load();
         return;
     }
     const bool fft_line = line_valid && iz < A.nz_fft;
@@ -175,9 +179,10 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
             }
         }
     }
+    after_load();
     // ================= middle stages: shared -> shared
-    strided2_mid_stages<P, MODE, 1>(sm, tw, line, q);
-    __syncthreads();
+    strided2_mid_stages<P, MODE, 1>(sm, tw, line, q, sync);
+    sync();
     // ================= last stage: shared -> butterfly -> global
     {
         constexpr int r = P::radix(S - 1), Bn = N / r, fs = N / r;
@@ -240,6 +245,79 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
     // lines of a partially transformed tile beyond nz_fft
     if (zf && line_valid && !fft_line)
         for (int k = q; k < A.n_out; k += P::TPL) mfb_st_stream(optr(k), make_double2(0.0, 0.0));
+}
+
+template <class P, int MODE, int MINB, bool BATCH0 = false>
+__global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs A, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    const int tiles_per_a = (A.nz + P::T - 1) / P::T;
+    const int a = blockIdx.x / tiles_per_a;
+    const int z0 = (blockIdx.x - a * tiles_per_a) * P::T;
+    strided2_tile<P, MODE, BATCH0>(A, tw, sm, threadIdx.x, a, z0, CtaSync(), [] {});
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ping-pong version: a persistent CTA of TWO warp groups, each with its own shared-memory tile, working on alternate
+// tiles.  One tile per CTA serialises its three phases - global loads of stage 0 (HBM latency + transfer, FP64 idle),
+// the shared-memory stages (HBM idle), the stores of the last stage - and two co-resident CTAs start together and stay
+// in lock-step, so nothing overlaps: a 1536-point pass sustains 3.1-4.0 TB/s although the bare access pattern
+// (128-byte, even 64-byte segments at an 8 KB stride) copies at 6.0-6.5 TB/s (profiles/r01_kbench_segment_copy.txt).
+// Here the load phase is a token passed between the warp groups through two named barriers: group 1 starts loading
+// when group 0 has consumed its loads and is computing, and vice versa, so one group's butterflies always run under
+// the other group's memory phase.
+MFB_D void mfb_bar_sync(int id, int count) {
+#ifdef MFB_EMU
+    mfb_emu::bar_sync(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+MFB_D void mfb_bar_arrive(int id, int count) {
+#ifdef MFB_EMU
+    mfb_emu::bar_arrive(id, count);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+struct GroupSync {   // barrier of one warp group (named barrier 1 + group index)
+    int id, nthreads;
+    MFB_D void operator()() const { mfb_bar_sync(id, nthreads); }
+};
+
+template <class P, int MODE, bool BATCH0 = false>
+__global__ void __launch_bounds__(2 * P::NTHREADS, 1) strided3_kernel(StridedArgs A, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm_all);
+    constexpr int NT = P::NTHREADS;
+    const int wg = threadIdx.x / NT, tid = threadIdx.x - wg * NT;
+    double2* sm = sm_all + size_t(wg) * (P::SMEM_BYTES / sizeof(double2));
+    const int tiles_per_a = (A.nz + P::T - 1) / P::T;
+    const long ntiles = long(A.na) * tiles_per_a;
+    // tile pairs are dealt round-robin to the CTAs; every CTA runs the same number of rounds for both groups so that the
+    // token barriers always find their partner
+    const long npairs = (ntiles + 1) / 2;
+    const long rounds = (npairs + gridDim.x - 1) / gridDim.x;
+    GroupSync gs{1 + wg, NT};
+    constexpr int BAR_L0_DONE = 3, BAR_L1_DONE = 4;   // "group 0 / group 1 has finished its load phase"
+    for (long r = 0; r < rounds; ++r) {
+        const long pair = r * gridDim.x + blockIdx.x;
+        const long tile = 2 * pair + wg;
+        const bool have = pair < npairs && tile < ntiles;
+        // wait for the token
+        if (wg == 0) { if (r > 0) mfb_bar_sync(BAR_L1_DONE, 2 * NT); }
+        else mfb_bar_sync(BAR_L0_DONE, 2 * NT);
+        auto pass_token = [&] {
+            if (wg == 0) mfb_bar_arrive(BAR_L0_DONE, 2 * NT);
+            else if (r + 1 < rounds) mfb_bar_arrive(BAR_L1_DONE, 2 * NT);
+        };
+        if (have) {
+            const int a = int(tile / tiles_per_a);
+            const int z0 = int(tile - long(a) * tiles_per_a) * P::T;
+            strided2_tile<P, MODE, BATCH0>(A, tw, sm, tid, a, z0, gs, pass_token);
+            gs();   // the tile buffer is reused by this group's next stage 0
+        } else {
+            pass_token();
+        }
+    }
 }
 
 }  // namespace mfb

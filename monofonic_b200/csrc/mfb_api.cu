@@ -238,14 +238,83 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     X(3072, 64, 4, 1, 16, 16, 12)
 // fused z pass of the dealiased product (fft_kernels_z2.cuh): N, threads per row, rows per CTA, min CTAs/SM, radices
 // (first radix a multiple of 3, last radix 8: conflict-free padded lines)
+// Operand rows are loaded straight from global memory in stage 0 (z_conv3_kernel<..., DIRECT = true>): kbench on B200,
+// 589824 rows: n = 1536  6.25 -> 5.54 ms (TPL 64, 3 CTAs/SM), n = 768  2.58 -> 2.48 ms (profiles/r01_kbench_z4_direct.txt).
 #define MFB_FOR_EACH_PLANZ(X)     \
     X(48, 32, 2, 1, 6, 8)         \
     X(96, 32, 2, 1, 12, 8)        \
     X(192, 32, 2, 1, 6, 4, 8)     \
     X(384, 32, 2, 4, 6, 8, 8)     \
     X(768, 64, 2, 5, 12, 8, 8)    \
-    X(1536, 128, 2, 2, 12, 16, 8) \
-    X(3072, 128, 2, 1, 6, 8, 8, 8)
+    X(1536, 64, 2, 3, 12, 16, 8)  \
+    X(3072, 128, 2, 2, 6, 8, 8, 8)
+
+// ping-pong plans (strided3_kernel): two warp groups with one tile each, so a tile must fit half of the shared memory
+#define MFB_FOR_EACH_PLAN3_B(X)   \
+    X(32, 4, 16, 8, 4)            \
+    X(48, 4, 16, 6, 8)            \
+    X(64, 8, 16, 8, 8)            \
+    X(96, 4, 16, 12, 8)           \
+    X(128, 8, 16, 16, 8)          \
+    X(192, 4, 16, 12, 16)         \
+    X(256, 16, 8, 16, 16)         \
+    X(384, 16, 8, 6, 8, 8)        \
+    X(512, 32, 8, 8, 8, 8)        \
+    X(768, 32, 8, 12, 8, 8)       \
+    X(1024, 64, 4, 16, 8, 8)      \
+    X(1536, 64, 4, 12, 16, 8)
+#define MFB_FOR_EACH_PLAN3_F(X)   \
+    X(48, 4, 16, 8, 6)            \
+    X(96, 4, 16, 8, 12)           \
+    X(192, 4, 16, 16, 12)         \
+    X(384, 16, 8, 8, 8, 6)        \
+    X(768, 32, 8, 8, 8, 12)       \
+    X(1536, 64, 4, 8, 16, 12)
+
+template <class P, int MODE> void launch_strided3_t(const StridedArgs& a, int role) {
+    static bool done = false;
+    constexpr size_t smem = 2 * P::SMEM_BYTES;
+    static_assert(smem <= 227 * 1024, "two tiles must fit the shared memory of one SM");
+    optin_smem(strided3_kernel<P, MODE>, smem, done);
+    const long tiles = long(a.na) * ((a.nz + P::T - 1) / P::T);
+    if (tiles == 0) return;
+    const long pairs = (tiles + 1) / 2;
+    const unsigned grid = unsigned(pairs < g_ctx.num_sms ? pairs : g_ctx.num_sms);   // persistent: one CTA per SM
+    const double2* tw = twiddles2<P>();
+    const double lines = double(a.na - (a.a_skip >= 0 ? 1 : 0)) * double(a.nz_fft);
+    const double bytes = lines * 16.0 * (double(a.n_in) + double(a.n_out) * (a.op == OP_ASSIGN ? 1.0 : 2.0));
+    RoleScope rs(role, bytes);
+    MFB_LAUNCH((strided3_kernel<P, MODE>), grid, 2 * P::NTHREADS, smem, g_ctx.stream, a, tw);
+    check_launch("strided3_kernel");
+}
+static bool launch_strided3(int n, const StridedArgs& a, int role) {
+    int mode;
+    if (a.n_in == n && a.n_out == n) mode = SM_PLAIN;
+    else if (a.n_out == n && 3 * a.n_in == 2 * n) mode = SM_PAD;
+    else if (a.n_in == n && 3 * a.n_out == 2 * n) mode = SM_TRUNC;
+    else return false;
+    if (a.f.enabled && mode != SM_PAD) return false;
+    if (mode == SM_TRUNC) {
+        switch (n) {
+#define X(N_, TPL_, T_, ...) case N_: launch_strided3_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_TRUNC>(a, role); return true;
+            MFB_FOR_EACH_PLAN3_F(X)
+#undef X
+            default: return false;
+        }
+    }
+    switch (n) {
+#define X(N_, TPL_, T_, ...)                                                           \
+    case N_:                                                                           \
+        if (mode == SM_PAD) {                                                          \
+            if constexpr (N_ % 3 == 0) launch_strided3_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_PAD>(a, role); \
+            else return false;                                                         \
+        } else launch_strided3_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_PLAIN>(a, role);  \
+        return true;
+        MFB_FOR_EACH_PLAN3_B(X)
+#undef X
+        default: return false;
+    }
+}
 
 template <class P, int MODE, int MINB> void launch_strided2_t(const StridedArgs& a, int role) {
     static bool done = false;
@@ -294,6 +363,7 @@ static bool launch_strided2(int n, const StridedArgs& a, int role) {
 }
 
 void launch_strided(int n, const StridedArgs& a, int role) {
+    if (g_ctx.strided_v2 && g_ctx.strided_v3 && launch_strided3(n, a, role)) return;
     if (g_ctx.strided_v2 && launch_strided2(n, a, role)) return;
     switch (n) {
 #define X(N_, TPL_, T_, ...)                              \
@@ -370,12 +440,12 @@ void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t 
 template <class P, int RPC, int MINB>
 void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale) {
     static bool done = false;
-    constexpr size_t smem = z_conv2_smem<P, RPC>();
-    optin_smem(z_conv3_kernel<P, RPC, MINB>, smem, done);
+    constexpr size_t smem = z_conv3_direct_smem<P, RPC>();
+    optin_smem(z_conv3_kernel<P, RPC, MINB, true>, smem, done);
     const unsigned grid = unsigned((nrows + RPC - 1) / RPC);
     const double2* tw = twiddles2<P>();
     RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * 3.0);
-    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw);
+    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw);
     check_launch("z_conv3_kernel");
 }
 static bool launch_zconv2(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
@@ -922,6 +992,11 @@ int mfb_init(int device) {
     require(device >= 0 && device < ndev, "libmfb200: invalid device index");
     cuda_check(cudaSetDevice(device), "cudaSetDevice");
     cuda_check(cudaStreamCreate(&g_ctx.stream), "cudaStreamCreate");
+#ifdef MFB_EMU
+    g_ctx.num_sms = 3;   // small and odd: the persistent kernels run several rounds with a ragged tail
+#else
+    cuda_check(cudaDeviceGetAttribute(&g_ctx.num_sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
+#endif
     g_ctx.device = device;
     g_ctx.initialised = true;
     MFB_CATCH
@@ -953,6 +1028,7 @@ int mfb_supported_fft_size(int n) { return supported_size(n) ? 1 : 0; }
 int mfb_set_option(const char* name, int value) {
     MFB_TRY
     if (std::string(name) == "strided_v2") g_ctx.strided_v2 = value != 0;
+    else if (std::string(name) == "strided_v3") g_ctx.strided_v3 = value != 0;
     else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
     else throw std::runtime_error(std::string("unknown option ") + name);
     MFB_CATCH

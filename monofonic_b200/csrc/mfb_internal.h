@@ -93,7 +93,9 @@ struct Context {
     double* table[2] = {nullptr, nullptr};  // radial tables (amplitude, vbc)
     size_t table_cap[2] = {0, 0};
     long long launches = 0;
+    int num_sms = 148;
     bool strided_v2 = true;  // second-generation strided pass (fft_kernels2.cuh)
+    bool strided_v3 = true;  // ping-pong persistent strided pass (strided3_kernel) where a plan exists
     bool zconv_v2 = true;    // second-generation fused z pass (fft_kernels_z2.cuh)
     // optional per-role device timing (cudaEvents on `stream` around every launch)
     bool profiling = false;

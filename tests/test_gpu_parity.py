@@ -48,7 +48,7 @@ def test_pipeline_vs_oracle(M, n, order, lattice, real64):
     PC.check_pipeline(M, n, order, lattice, real64)
 
 
-@pytest.mark.parametrize("n,nyq0", [(32, False), (64, True), (96, False)])
+@pytest.mark.parametrize("n,nyq0", [(32, False), (64, True), (128, False)])
 def test_naive_convolver(M, n, nyq0):
     PC.check_naive_convolver(M, n, nyq0)
 

@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(P::NTHREADS) z_c2c_kernel(double2* __restrict_
 template <class P>
 __global__ void __launch_bounds__(P::NTHREADS) z_conv_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin,
                                                              double2* __restrict__ out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
-                                                             long nrows, int nzin, double scale, const double2* __restrict__ tw) {
+                                                             long nrows, int nzin, double scale, const double2* __restrict__ tw,
+                                                             int accumulate = 0) {
     MFB_DYN_SMEM(double2, sm);
     constexpr int N = P::N, T = P::T, H = T / 2;
     static_assert(T >= 2, "need at least two lines per tile");
@@ -323,8 +324,12 @@ __global__ void __launch_bounds__(P::NTHREADS) z_conv_kernel(const double2* __re
         const double2 zk = sm[P::smem_addr(k, l)];
         const double2 zm = sm[P::smem_addr((N - k) % N, l)];
         const double h = 0.5 * scale;
-        const double2 x1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
-        const double2 x2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
+        double2 x1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+        double2 x2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
+        if (accumulate) {
+            if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); x1.x += o.x; x1.y += o.y; }
+            if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); x2.x += o.x; x2.y += o.y; }
+        }
         if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, x1);
         if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, x2);
     }

@@ -52,10 +52,10 @@ MFB_D void strided2_mid_stages(double2* __restrict__ sm, const double2* __restri
 }
 
 // One tile (fixed a, T adjacent k_z starting at z0) of a strided pass, executed by P::NTHREADS threads that share `sm` and
-// synchronise with `sync` (the whole CTA, or one warp group of a ping-pong CTA).  `after_load` is called once by every
-// thread when its global loads of stage 0 have been consumed (the ping-pong kernel hands the load phase to the other
-// warp group there).
-template <class P, int MODE, bool BATCH0, class Sync, class AfterLoad>
+// synchronise with `sync`.  `after_load` is called once by every thread when stage 0 has consumed its inputs.
+// SMEM_IN: the tile's input already sits in `sm` at its stage-0 leg positions (staged there asynchronously by
+// strided3_kernel); stage 0 then runs in place like the middle stages.
+template <class P, int MODE, bool BATCH0, bool SMEM_IN = false, class Sync, class AfterLoad>
 MFB_D void strided2_tile(const StridedArgs& A, const double2* __restrict__ tw, double2* __restrict__ sm, int tid, int a, int z0,
                          const Sync& sync, const AfterLoad& after_load) {
     constexpr int N = P::N, T = P::T, S = P::S;
@@ -121,6 +121,15 @@ MFB_D void strided2_tile(const StridedArgs& A, const double2* __restrict__ tw, d
         const bool use_f = A.f.enabled != 0, f_imag = A.f.imag != 0, inv = A.inverse != 0;
         // global loads of one butterfly (zero legs are not loaded)
         auto load = [&](int j, double2* v) {
+            if constexpr (SMEM_IN) {
+                const double2* sp = sm + j * T + line;
+#pragma unroll
+                for (int t = 0; t < r; ++t) {
+                    if constexpr (MODE == SM_PAD) { if (t >= K3 && t < 2 * K3) continue; }   // zero band: never staged
+                    v[t] = fft_line ? sp[t * M * T] : make_double2(0.0, 0.0);
+                }
+                return;
+            }
             const double2* p = gin + ptrdiff_t(j) * A.in_ps;
             if constexpr (MODE == SM_PAD) {
                 // source line has 2r/3 * M samples; leg k of the source maps to leg t = k (k < r/3) or k + r/3
@@ -257,66 +266,58 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Ping-pong version: a persistent CTA of TWO warp groups, each with its own shared-memory tile, working on alternate
-// tiles.  One tile per CTA serialises its three phases - global loads of stage 0 (HBM latency + transfer, FP64 idle),
-// the shared-memory stages (HBM idle), the stores of the last stage - and two co-resident CTAs start together and stay
-// in lock-step, so nothing overlaps: a 1536-point pass sustains 3.1-4.0 TB/s although the bare access pattern
-// (128-byte, even 64-byte segments at an 8 KB stride) copies at 6.0-6.5 TB/s (profiles/r01_kbench_segment_copy.txt).
-// Here the load phase is a token passed between the warp groups through two named barriers: group 1 starts loading
-// when group 0 has consumed its loads and is computing, and vice versa, so one group's butterflies always run under
-// the other group's memory phase.
-MFB_D void mfb_bar_sync(int id, int count) {
-#ifdef MFB_EMU
-    mfb_emu::bar_sync(id, count);
-#else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-MFB_D void mfb_bar_arrive(int id, int count) {
-#ifdef MFB_EMU
-    mfb_emu::bar_arrive(id, count);
-#else
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-struct GroupSync {   // barrier of one warp group (named barrier 1 + group index)
-    int id, nthreads;
-    MFB_D void operator()() const { mfb_bar_sync(id, nthreads); }
-};
-
-template <class P, int MODE, bool BATCH0 = false>
-__global__ void __launch_bounds__(2 * P::NTHREADS, 1) strided3_kernel(StridedArgs A, const double2* __restrict__ tw) {
+// strided3_kernel - persistent, double-buffered version of the strided pass.
+//
+// What bounds strided2_kernel is not the access pattern - a bare copy with the same 64..128-byte segments at an 8 KB
+// stride runs at 6.0-6.5 TB/s (profiles/r01_kbench_segment_copy.txt) - but bytes in flight: one tile per CTA issues its
+// global loads in stage 0, waits for them, and has nothing outstanding during the shared-memory stages, so on average
+// ~20 KB per SM are in flight where ~45 KB are needed (6.5 TB/s x ~1 us / 148 SMs), and the pass sustains 3.1-4.0 TB/s.
+// (Splitting the CTA into two warp groups that take turns loading made it worse - half the loads in flight again:
+// profiles/r01_kbench_pingpong_negative.txt.)
+// Here a CTA owns TWO tile buffers.  While the butterflies run on one, the input of the CTA's next tile streams into
+// the other with 16-byte cp.async copies (LDGSTS, no register staging), landing directly at the stage-0 leg positions,
+// so stage 0 is an in-place shared-memory stage too and a full tile of loads is in flight for the whole compute phase.
+template <class P, int MODE>
+__global__ void __launch_bounds__(P::NTHREADS, 1) strided3_kernel(StridedArgs A, const double2* __restrict__ tw) {
     MFB_DYN_SMEM(double2, sm_all);
-    constexpr int NT = P::NTHREADS;
-    const int wg = threadIdx.x / NT, tid = threadIdx.x - wg * NT;
-    double2* sm = sm_all + size_t(wg) * (P::SMEM_BYTES / sizeof(double2));
-    const int tiles_per_a = (A.nz + P::T - 1) / P::T;
+    constexpr int N = P::N, T = P::T, NT = P::NTHREADS;
+    constexpr int TILE = N * T;                      // complex elements per buffer
+    const int tid = threadIdx.x;
+    const int tiles_per_a = (A.nz + T - 1) / T;
     const long ntiles = long(A.na) * tiles_per_a;
-    // tile pairs are dealt round-robin to the CTAs; every CTA runs the same number of rounds for both groups so that the
-    // token barriers always find their partner
-    const long npairs = (ntiles + 1) / 2;
-    const long rounds = (npairs + gridDim.x - 1) / gridDim.x;
-    GroupSync gs{1 + wg, NT};
-    constexpr int BAR_L0_DONE = 3, BAR_L1_DONE = 4;   // "group 0 / group 1 has finished its load phase"
-    for (long r = 0; r < rounds; ++r) {
-        const long pair = r * gridDim.x + blockIdx.x;
-        const long tile = 2 * pair + wg;
-        const bool have = pair < npairs && tile < ntiles;
-        // wait for the token
-        if (wg == 0) { if (r > 0) mfb_bar_sync(BAR_L1_DONE, 2 * NT); }
-        else mfb_bar_sync(BAR_L0_DONE, 2 * NT);
-        auto pass_token = [&] {
-            if (wg == 0) mfb_bar_arrive(BAR_L0_DONE, 2 * NT);
-            else if (r + 1 < rounds) mfb_bar_arrive(BAR_L1_DONE, 2 * NT);
-        };
-        if (have) {
-            const int a = int(tile / tiles_per_a);
-            const int z0 = int(tile - long(a) * tiles_per_a) * P::T;
-            strided2_tile<P, MODE, BATCH0>(A, tw, sm, tid, a, z0, gs, pass_token);
-            gs();   // the tile buffer is reused by this group's next stage 0
-        } else {
-            pass_token();
+    const int hin = A.n_in / 2, shift = N - A.n_in;  // pad map: source sample s sits at position s (+ shift in the upper half)
+
+    // asynchronous staging of one tile's input; lines / tiles that carry no data are not touched (stage 0 reads zeros)
+    auto stage_in = [&](long tile, double2* buf) {
+        const int a = int(tile / tiles_per_a);
+        const int z0 = int(tile - long(a) * tiles_per_a) * T;
+        if ((a + A.a_off == A.a_skip) || (z0 >= A.nz_fft)) return;
+        const int l = tid % T, p0 = tid / T;
+        const int iz = z0 + l;
+        if (iz >= A.nz || iz >= A.nz_fft) return;
+        const double2* g = A.in + ptrdiff_t(a) * A.in_as + iz;
+        for (int s_ = p0; s_ < A.n_in; s_ += NT / T) {
+            const int pos = (MODE == SM_PAD && s_ >= hin) ? s_ + shift : s_;
+            mfb_cp_async16(buf + pos * T + l, g + ptrdiff_t(s_) * A.in_ps);
         }
+    };
+
+    long tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    int cur = 0;
+    stage_in(tile, sm_all);
+    mfb_cp_async_commit();
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long next = tile + gridDim.x;
+        if (next < ntiles) stage_in(next, sm_all + (cur ^ 1) * TILE);
+        mfb_cp_async_commit();                       // (possibly empty) group of the next tile
+        mfb_cp_async_wait_but_one();                 // this tile's input has landed (this thread's copies) ...
+        __syncthreads();                             // ... and everybody else's
+        const int a = int(tile / tiles_per_a);
+        const int z0 = int(tile - long(a) * tiles_per_a) * T;
+        strided2_tile<P, MODE, false, true>(A, tw, sm_all + cur * TILE, tid, a, z0, CtaSync(), [] {});
+        __syncthreads();                             // the buffer is refilled two iterations from now at the earliest,
+        cur ^= 1;                                    // but the next iteration's staging targets it right away
     }
 }
 

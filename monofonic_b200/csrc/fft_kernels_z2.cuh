@@ -85,7 +85,7 @@ template <class P, int s, int NT> MFB_D void z2_dit_mid(double2* ln, const doubl
 template <class P, int RPC, int MINB>
 __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     z_conv2_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
-                   ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw) {
+                   ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw, int accumulate = 0) {
     MFB_DYN_SMEM(double2, sm);
     constexpr int N = P::N, S = P::S, TPL = P::TPL, NT = TPL * RPC;
     constexpr int NZ = N / 3;             // retained k_z modes of each operand row
@@ -197,8 +197,14 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
             const double2 zk = l0[zpad(k)];
             const double2 zm = l0[zpad((N - k) % N)];
             const long r1 = row0 + 2 * m, r2 = r1 + 1;
-            if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y)));
-            if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x)));
+            double2 v1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+            double2 v2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
+            if (accumulate) {   // sum of products of one target, formed before the (single) forward y/x passes
+                if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
+                if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
+            }
+            if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, v1);
+            if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, v2);
         }
     }
 }
@@ -247,7 +253,7 @@ template <class P, int s, int NT> MFB_D void z3_dif_mid_pair(double2* l0, const 
 template <class P, int RPC, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     z_conv3_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
-                   ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw) {
+                   ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw, int accumulate = 0) {
     MFB_DYN_SMEM(double2, sm);
     constexpr int N = P::N, S = P::S, TPL = P::TPL, NT = TPL * RPC, PT = 2 * TPL;
     constexpr int NZ = N / 3;
@@ -389,8 +395,14 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
             const double2 zk = lz[zpad(k)];
             const double2 zm = lz[zpad((N - k) % N)];
             const long r1 = row0 + 2 * mm, r2 = r1 + 1;
-            if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y)));
-            if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x)));
+            double2 v1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+            double2 v2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
+            if (accumulate) {   // sum of products of one target, formed before the (single) forward y/x passes
+                if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
+                if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
+            }
+            if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, v1);
+            if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, v2);
         }
     }
 }

@@ -249,7 +249,7 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     X(1536, 64, 2, 3, 12, 16, 8)  \
     X(3072, 128, 2, 2, 6, 8, 8, 8)
 
-// ping-pong plans (strided3_kernel): two warp groups with one tile each, so a tile must fit half of the shared memory
+// double-buffered plans (strided3_kernel): two tile buffers per CTA, so a tile must fit half of the shared memory
 #define MFB_FOR_EACH_PLAN3_B(X)   \
     X(32, 4, 16, 8, 4)            \
     X(48, 4, 16, 6, 8)            \
@@ -278,13 +278,12 @@ template <class P, int MODE> void launch_strided3_t(const StridedArgs& a, int ro
     optin_smem(strided3_kernel<P, MODE>, smem, done);
     const long tiles = long(a.na) * ((a.nz + P::T - 1) / P::T);
     if (tiles == 0) return;
-    const long pairs = (tiles + 1) / 2;
-    const unsigned grid = unsigned(pairs < g_ctx.num_sms ? pairs : g_ctx.num_sms);   // persistent: one CTA per SM
+    const unsigned grid = unsigned(tiles < g_ctx.num_sms ? tiles : g_ctx.num_sms);   // persistent: one CTA per SM
     const double2* tw = twiddles2<P>();
     const double lines = double(a.na - (a.a_skip >= 0 ? 1 : 0)) * double(a.nz_fft);
     const double bytes = lines * 16.0 * (double(a.n_in) + double(a.n_out) * (a.op == OP_ASSIGN ? 1.0 : 2.0));
     RoleScope rs(role, bytes);
-    MFB_LAUNCH((strided3_kernel<P, MODE>), grid, 2 * P::NTHREADS, smem, g_ctx.stream, a, tw);
+    MFB_LAUNCH((strided3_kernel<P, MODE>), grid, P::NTHREADS, smem, g_ctx.stream, a, tw);
     check_launch("strided3_kernel");
 }
 static bool launch_strided3(int n, const StridedArgs& a, int role) {
@@ -427,46 +426,49 @@ void launch_zc2c(int n, double2* data, long nrows, double scale, int inverse) {
 
 template <class P>
 void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
-                    int nzin, double scale) {
+                    int nzin, double scale, int acc) {
     static bool done = false;
     optin_smem(z_conv_kernel<P>, P::SMEM_BYTES, done);
     const unsigned grid = unsigned((nrows + P::T - 1) / P::T);
     const double2* tw = twiddles(P::N);
-    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(nzin) * 16.0 * 3.0);
+    // algorithmic bytes: both operand rows (one if A == B) + the output row (+ its old value when accumulating)
+    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(nzin) * 16.0 * ((A == B ? 1.0 : 2.0) + (acc ? 2.0 : 1.0)));
     MFB_LAUNCH(z_conv_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, nzin,
-               scale, tw);
+               scale, tw, acc);
     check_launch("z_conv_kernel");
 }
 template <class P, int RPC, int MINB>
-void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale) {
+void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale,
+                     int acc) {
     static bool done = false;
     constexpr size_t smem = z_conv3_direct_smem<P, RPC>();
     optin_smem(z_conv3_kernel<P, RPC, MINB, true>, smem, done);
     const unsigned grid = unsigned((nrows + RPC - 1) / RPC);
     const double2* tw = twiddles2<P>();
-    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * 3.0);
-    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw);
+    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * ((A == B ? 1.0 : 2.0) + (acc ? 2.0 : 1.0)));
+    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw,
+               acc);
     check_launch("z_conv3_kernel");
 }
 static bool launch_zconv2(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
-                          long nrows, int nzin, double scale) {
+                          long nrows, int nzin, double scale, int acc) {
     if (3 * nzin != n) return false;
     switch (n) {
 #define X(N_, TPL_, RPC_, MINB_, ...)                                                                          \
-    case N_: launch_zconv2_t<Plan<N_, TPL_, 2, __VA_ARGS__>, RPC_, MINB_>(A, B, out, in_pitch, out_pitch, nrows, scale); return true;
+    case N_: launch_zconv2_t<Plan<N_, TPL_, 2, __VA_ARGS__>, RPC_, MINB_>(A, B, out, in_pitch, out_pitch, nrows, scale, acc); return true;
         MFB_FOR_EACH_PLANZ(X)
 #undef X
         default: return false;
     }
 }
 void launch_zconv(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
-                  int nzin, double scale) {
-    if (g_ctx.zconv_v2 && launch_zconv2(n, A, B, out, in_pitch, out_pitch, nrows, nzin, scale)) return;
+                  int nzin, double scale, int acc = 0) {
+    if (g_ctx.zconv_v2 && launch_zconv2(n, A, B, out, in_pitch, out_pitch, nrows, nzin, scale, acc)) return;
     switch (n) {
 #define X(N_, TPL_, T_, ...)                                                   \
     case N_: {                                                                 \
         using P = Plan<N_, TPL_, T_, __VA_ARGS__>;                             \
-        launch_zconv_t<P>(A, B, out, in_pitch, out_pitch, nrows, nzin, scale); \
+        launch_zconv_t<P>(A, B, out, in_pitch, out_pitch, nrows, nzin, scale, acc); \
         break;                                                                 \
     }
         MFB_FOR_EACH_PLAN(X)
@@ -775,63 +777,94 @@ static void naive_conv(mfb_conv* c, const Operand& A, const Operand& B, const Op
     naive_forward_output(c, c->nb2, out, op, alpha);
 }
 
-void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
-    require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
-    if (c->naive) { naive_conv(c, A, B, nullptr, out, op, alpha); return; }
-    to_kspace(A.g);
-    to_kspace(B.g);
-    const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
-    const int P0 = c->np[0], P1 = c->np[1], P2 = c->np[2];
-    const int nzc = N2 / 2 + 1, nzin = N2 / 2;
-    const double ptot = double(P0) * P1 * P2, ntot = double(N0) * N1 * N2;
-    conv_backward_operand(c, A, c->W2a);
-    conv_backward_operand(c, B, c->W2b);
-    const double unpad_scale = (1.0 / std::sqrt(ptot)) / (std::sqrt(ptot) / std::sqrt(ntot));  // fwd norm / rfac (convolution.hh:620,664)
-    if (c->dist) {
-        const int p0l = c->p0loc, l1 = out->nloc1;
-        launch_zconv(P2, c->W2a, c->W2b, c->W2a, nzin, nzin, long(p0l) * P1, nzin, 1.0);
-        // y forward P1 -> N1 on the local x planes, routed to the owners of the ky rows
-        Exchange x = begin_exchange(size_t(p0l) * l1 * nzin);
-        StridedArgs d = plain_strided(c->W2a, nullptr, nzin, ptrdiff_t(P1) * nzin, p0l, nzin, P1, 0);
+static bool same_operand(const Operand& a, const Operand& b) {
+    return a.g == b.g && a.a1 == b.a1 && a.b1 == b.b1 && a.a2 == b.a2 && a.b2 == b.b2 && a.c1 == b.c1 && a.c2 == b.c2 &&
+           a.imag == b.imag && a.keep_nyq == b.keep_nyq;
+}
+
+// ---- a GROUP of dealiased products with one target: out (op)= unpad( F[ sum_i coeff_i * a_i * b_i ] ).
+// The per-product part is the two operand transforms and the fused z pass, which adds coeff_i * a_i b_i to the running
+// sum in z-Fourier space (the padded accumulator Wacc, [P0][P1][N2/2]); the forward y and x passes, the truncation and the
+// output operator run ONCE per group.  Exact by linearity of the transforms and of the truncation; the
+// reference does one forward transform per product (include/convolution.hh:524-534).  Without Wacc (not enough HBM)
+// every product is its own group and the z pass works in place on W2a.
+// A product of an operand with itself transforms it once.
+struct ConvGroup {
+    mfb_conv* c;
+    bool inplace;   // single product whose z pass overwrites W2a (leaves Wacc to an enclosing group)
+    int count = 0;
+    explicit ConvGroup(mfb_conv* c_, bool inplace_ = false) : c(c_), inplace(inplace_ || c_->Wacc == nullptr || !g_ctx.conv_grouping) {}
+    double2* sum() const { return inplace ? c->W2a : c->Wacc; }
+    void add(const Operand& A, const Operand& B, double coeff) {
+        require(count == 0 || !inplace, "internal: product groups need the accumulator workspace");
+        to_kspace(A.g);
+        to_kspace(B.g);
+        const int P1 = c->np[1], P2 = c->np[2], nzin = c->n[2] / 2;
+        const bool square = same_operand(A, B);
+        conv_backward_operand(c, A, c->W2a);
+        if (!square) conv_backward_operand(c, B, c->W2b);
+        launch_zconv(P2, c->W2a, square ? c->W2a : c->W2b, sum(), nzin, nzin, long(c->p0loc) * P1, nzin, coeff, count > 0);
+        ++count;
+        ++c->nconv;
+    }
+    void finish(mfb_grid* out, int op, double alpha) {
+        require(count > 0, "internal: empty product group");
+        require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+        const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
+        const int P0 = c->np[0], P1 = c->np[1], P2 = c->np[2];
+        const int nzc = N2 / 2 + 1, nzin = N2 / 2;
+        const double ptot = double(P0) * P1 * P2, ntot = double(N0) * N1 * N2;
+        const double unpad_scale = (1.0 / std::sqrt(ptot)) / (std::sqrt(ptot) / std::sqrt(ntot));  // fwd norm / rfac (convolution.hh:620,664)
+        if (c->dist) {
+            const int p0l = c->p0loc, l1 = out->nloc1;
+            // y forward P1 -> N1 on the local x planes, routed to the owners of the ky rows
+            Exchange x = begin_exchange(size_t(p0l) * l1 * nzin);
+            StridedArgs d = plain_strided(sum(), nullptr, nzin, ptrdiff_t(P1) * nzin, p0l, nzin, P1, 0);
+            d.n_out = N1;
+            route(d, x, l1, nzin, ptrdiff_t(l1) * nzin);                    // chunk layout [x_loc][ky_loc][kz]
+            launch_strided(P1, d, ROLE_CONV_Y_FWD);
+            end_exchange(x);                                                 // recv: [x (P0)][ky_loc][kz]
+            // x forward P0 -> N0 + unpad scale + Nyquist zero + output operator, into [ky_loc][kx][kz]
+            StridedArgs e = plain_strided(x.recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * nzin, nzin, l1,
+                                          (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
+            e.out_ps = nzc; e.out_as = ptrdiff_t(N0) * nzc;
+            e.nz_fft = nzin;
+            e.n_out = N0;
+            e.scale = unpad_scale;
+            e.op = op; e.alpha = alpha;
+            e.a_off = out->off1;
+            e.a_skip = N1 / 2;
+            e.zero_fill = 1;
+            launch_strided(P0, e, ROLE_CONV_X_FWD);
+            return;
+        }
+        // y axis forward, P1 -> N1
+        StridedArgs d = plain_strided(sum(), c->W1, nzin, 0, P0, nzin, P1, 0);
+        d.in_as = ptrdiff_t(P1) * nzin;
+        d.out_as = ptrdiff_t(N1) * nzin;
         d.n_out = N1;
-        route(d, x, l1, nzin, ptrdiff_t(l1) * nzin);                    // chunk layout [x_loc][ky_loc][kz]
         launch_strided(P1, d, ROLE_CONV_Y_FWD);
-        end_exchange(x);                                                 // recv: [x (P0)][ky_loc][kz]
-        // x forward P0 -> N0 + unpad scale + Nyquist zero + output operator, into [ky_loc][kx][kz]
-        StridedArgs e = plain_strided(x.recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * nzin, nzin, l1,
-                                      (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
-        e.out_ps = nzc; e.out_as = ptrdiff_t(N0) * nzc;
+        // x axis forward, P0 -> N0, unpad scale + Nyquist zero + output operator
+        StridedArgs e = plain_strided(c->W1, reinterpret_cast<double2*>(out->d), 0, 0, N1, (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
+        e.in_ps = ptrdiff_t(N1) * nzin; e.in_as = nzin;
+        e.out_ps = ptrdiff_t(N1) * nzc; e.out_as = nzc;
         e.nz_fft = nzin;
         e.n_out = N0;
         e.scale = unpad_scale;
         e.op = op; e.alpha = alpha;
-        e.a_off = out->off1;
         e.a_skip = N1 / 2;
         e.zero_fill = 1;
         launch_strided(P0, e, ROLE_CONV_X_FWD);
-        ++c->nconv;
-        return;
     }
-    // pass 3: fused z  c2r x2, product, r2c (in place on W2a)
-    launch_zconv(P2, c->W2a, c->W2b, c->W2a, nzin, nzin, long(P0) * P1, nzin, 1.0);
-    // pass 4: y axis forward, P1 -> N1
-    StridedArgs d = plain_strided(c->W2a, c->W1, nzin, 0, P0, nzin, P1, 0);
-    d.in_as = ptrdiff_t(P1) * nzin;
-    d.out_as = ptrdiff_t(N1) * nzin;
-    d.n_out = N1;
-    launch_strided(P1, d, ROLE_CONV_Y_FWD);
-    // pass 5: x axis forward, P0 -> N0, unpad scale + Nyquist zero + output operator
-    StridedArgs e = plain_strided(c->W1, reinterpret_cast<double2*>(out->d), 0, 0, N1, (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
-    e.in_ps = ptrdiff_t(N1) * nzin; e.in_as = nzin;
-    e.out_ps = ptrdiff_t(N1) * nzc; e.out_as = nzc;
-    e.nz_fft = nzin;
-    e.n_out = N0;
-    e.scale = unpad_scale;
-    e.op = op; e.alpha = alpha;
-    e.a_skip = N1 / 2;
-    e.zero_fill = 1;
-    launch_strided(P0, e, ROLE_CONV_X_FWD);
-    ++c->nconv;
+};
+static bool can_group(const mfb_conv* c) { return !c->naive && c->Wacc != nullptr && g_ctx.conv_grouping; }
+
+void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
+    require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+    if (c->naive) { naive_conv(c, A, B, nullptr, out, op, alpha); return; }
+    ConvGroup g(c);
+    g.add(A, B, 1.0);
+    g.finish(out, op, alpha);
 }
 
 static Operand hessian_operand(mfb_grid* g, const int d[2]) { return Operand{g, d[0], d[1], -1, -1, -1.0, 0.0, 0}; }
@@ -856,7 +889,19 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
     const double g3c = (order > 2) ? 1.0 / 7.0 * D * D * D : 0.0;
     auto H = [](mfb_grid* g, int a, int b) { int d[2] = {a, b}; return hessian_operand(g, d); };
     auto HS = [](mfb_grid* g, int a, int b, int cc, int d, double sgn) { return Operand{g, a, b, cc, d, -1.0, -sgn, 0}; };
-    if (order > 1) {
+    const bool grouped = can_group(c);
+    if (order > 1 && grouped) {
+        require(phi2 != nullptr, "phi2 grid required for LPT order > 1");
+        phi2->space = MFB_KSPACE;
+        // src/ic_generator.cc:482-486, the five products summed before ONE forward transform
+        ConvGroup g(c);
+        g.add(H(phi, 0, 0), HS(phi, 1, 1, 2, 2, +1.0), 1.0);
+        g.add(H(phi, 1, 1), H(phi, 2, 2), 1.0);
+        g.add(H(phi, 0, 1), H(phi, 0, 1), -1.0);
+        g.add(H(phi, 0, 2), H(phi, 0, 2), -1.0);
+        g.add(H(phi, 1, 2), H(phi, 1, 2), -1.0);
+        g.finish(phi2, OP_ASSIGN, 0.0);
+    } else if (order > 1) {
         require(phi2 != nullptr, "phi2 grid required for LPT order > 1");
         phi2->space = MFB_KSPACE;
         // src/ic_generator.cc:482-486
@@ -865,6 +910,8 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
         conv2(c, H(phi, 0, 1), H(phi, 0, 1), phi2, OP_SUB, 0.0);
         conv2(c, H(phi, 0, 2), H(phi, 0, 2), phi2, OP_SUB, 0.0);
         conv2(c, H(phi, 1, 2), H(phi, 1, 2), phi2, OP_SUB, 0.0);
+    }
+    if (order > 1) {
         if (lam) {
             KGeom k = kgeom(phi2);
             MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, tides_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(phi2->d),
@@ -873,8 +920,57 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
         }
         grid_laplacian_pow(phi2, -1, -1.0);  // :499
     }
-    if (order > 2) {
-        require(phi3 && A3 && A3[0] && A3[1] && A3[2], "phi3 and A3 grids required for LPT order > 2");
+    if (order > 2) require(phi3 && A3 && A3[0] && A3[1] && A3[2], "phi3 and A3 grids required for LPT order > 2");
+    if (order > 2 && grouped) {
+        phi3->space = MFB_KSPACE;
+        mfb_grid* fb = c->fbuf;
+        fb->space = MFB_KSPACE;
+        const Operand FB{fb, -1, -1, -1, -1, 1.0, 0.0, 0};
+        // 3a :522-526.  The inner products of convolve3 are truncated to the N-grid before the outer product
+        // (include/convolution.hh:542-549) - that stays; but truncation is linear, so inner products that meet the same
+        // outer field are summed first:  det = T(xx yy - xy xy) zz + 2 T(xy xz) yz - T(yz yz) xx - T(xz xz) yy.
+        {
+            ConvGroup in(c);
+            in.add(H(phi, 0, 0), H(phi, 1, 1), 1.0);
+            in.add(H(phi, 0, 1), H(phi, 0, 1), -1.0);
+            in.finish(fb, OP_ASSIGN, 0.0);
+        }
+        ConvGroup g3(c);   // every term of phi3 (3a outer products and 3b) goes into one sum
+        g3.add(FB, H(phi, 2, 2), 1.0);
+        auto inner = [&](const Operand& a, const Operand& b) {
+            ConvGroup in(c, true);   // the accumulator belongs to g3: single product, in place
+            in.add(a, b, 1.0);
+            in.finish(fb, OP_ASSIGN, 0.0);
+        };
+        inner(H(phi, 0, 1), H(phi, 0, 2));
+        g3.add(FB, H(phi, 1, 2), 2.0);
+        inner(H(phi, 1, 2), H(phi, 1, 2));
+        g3.add(FB, H(phi, 0, 0), -1.0);
+        inner(H(phi, 0, 2), H(phi, 0, 2));
+        g3.add(FB, H(phi, 1, 1), -1.0);
+        // 3b  :533-538
+        g3.add(H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), -5.0 / 7.0);
+        g3.add(H(phi, 1, 1), HS(phi2, 2, 2, 0, 0, +1.0), -5.0 / 7.0);
+        g3.add(H(phi, 2, 2), HS(phi2, 0, 0, 1, 1, +1.0), -5.0 / 7.0);
+        g3.add(H(phi, 0, 1), H(phi2, 0, 1), 10.0 / 7.0);
+        g3.add(H(phi, 0, 2), H(phi2, 0, 2), 10.0 / 7.0);
+        g3.add(H(phi, 1, 2), H(phi2, 1, 2), 10.0 / 7.0);
+        g3.finish(phi3, OP_ASSIGN, 0.0);
+        grid_laplacian_pow(phi3, -1, -1.0);  // :539
+        // transverse term  :545-556
+        for (int d = 0; d < 3; ++d) {
+            const int p = (d + 1) % 3, q = (d + 2) % 3;
+            mfb_grid* A = A3[d];
+            A->space = MFB_KSPACE;
+            ConvGroup ga(c);
+            ga.add(H(phi2, d, p), H(phi, d, q), 1.0);
+            ga.add(H(phi2, d, q), H(phi, d, p), -1.0);
+            ga.add(H(phi, p, q), HS(phi2, p, p, q, q, -1.0), 1.0);
+            ga.add(H(phi2, p, q), HS(phi, p, p, q, q, -1.0), -1.0);
+            ga.finish(A, OP_ASSIGN, 0.0);
+            grid_laplacian_pow(A, -1, -1.0);
+        }
+    } else if (order > 2) {
         phi3->space = MFB_KSPACE;
         // 3a  :522-526
         conv3(c, H(phi, 0, 0), H(phi, 1, 1), H(phi, 2, 2), phi3, OP_ASSIGN, 0.0);
@@ -1029,6 +1125,7 @@ int mfb_set_option(const char* name, int value) {
     MFB_TRY
     if (std::string(name) == "strided_v2") g_ctx.strided_v2 = value != 0;
     else if (std::string(name) == "strided_v3") g_ctx.strided_v3 = value != 0;
+    else if (std::string(name) == "conv_grouping") g_ctx.conv_grouping = value != 0;
     else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
     else throw std::runtime_error(std::string("unknown option ") + name);
     MFB_CATCH
@@ -1575,6 +1672,16 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
     c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
     if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
     c->naive = 0; c->nb1 = c->nb2 = nullptr;
+    // the accumulator of product groups is an optimisation, not a requirement: take it only if HBM is plentiful after it
+    // (room for the particle arrays and the remaining grids of a 3LPT run: 3.75 R(N) of this slab)
+    c->Wacc = nullptr;
+    {
+        size_t free_b = 0, total_b = 0;
+        cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+        const size_t w2_bytes = c->w2_elems * sizeof(double2);
+        const size_t reserve = size_t(3.75 * double(c->fbuf->ntot) * sizeof(double));
+        if (free_b > w2_bytes + reserve) c->Wacc = (double2*)dev_alloc(w2_bytes);
+    }
     *out = c;
     MFB_CATCH
 }
@@ -1599,6 +1706,7 @@ int mfb_conv_destroy(mfb_conv* c) {
         if (c->W1) cudaFree(c->W1);
         if (c->W2a) cudaFree(c->W2a);
         if (c->W2b) cudaFree(c->W2b);
+        if (c->Wacc) cudaFree(c->Wacc);
         if (c->fbuf) mfb_grid_destroy(c->fbuf);
         if (c->nb1) mfb_grid_destroy(c->nb1);
         if (c->nb2) mfb_grid_destroy(c->nb2);
@@ -1608,7 +1716,7 @@ int mfb_conv_destroy(mfb_conv* c) {
 }
 size_t mfb_conv_workspace_bytes(const mfb_conv* c) {
     if (c->naive) return (c->nb1->ntot + c->nb2->ntot) * sizeof(double);
-    return (c->w1_elems + 2 * c->w2_elems) * sizeof(double2) + c->fbuf->ntot * sizeof(double);
+    return (c->w1_elems + (c->Wacc ? 3 : 2) * c->w2_elems) * sizeof(double2) + c->fbuf->ntot * sizeof(double);
 }
 static void check_conv_grids(mfb_conv* c, mfb_grid* a, mfb_grid* b, mfb_grid* o) {
     for (mfb_grid* g : {a, b, o})

@@ -35,6 +35,7 @@ struct mfb_conv {
     int n[3], np[3];
     double L[3];
     double2 *W1, *W2a, *W2b;  // workspaces: [P0][N1][N2/2], [P0][P1][N2/2] x2  
+    double2* Wacc;            // optional [P0][P1][N2/2]: running sum of a product group in z-Fourier space (NULL: no grouping)
     size_t w1_elems, w2_elems;
     int dist, p0loc, p0off;   // slab of the padded grid along axis 0 (real space)
     mfb_grid* fbuf;           // N-grid for the intermediate of 3-field products (convolution.hh:469)
@@ -95,7 +96,8 @@ struct Context {
     long long launches = 0;
     int num_sms = 148;
     bool strided_v2 = true;  // second-generation strided pass (fft_kernels2.cuh)
-    bool strided_v3 = true;  // ping-pong persistent strided pass (strided3_kernel) where a plan exists
+    bool strided_v3 = false; // persistent double-buffered strided pass (strided3_kernel): measured no faster, kept as an option
+    bool conv_grouping = true;  // sum the products of one target before the forward passes (needs mfb_conv::Wacc)
     bool zconv_v2 = true;    // second-generation fused z pass (fft_kernels_z2.cuh)
     // optional per-role device timing (cudaEvents on `stream` around every launch)
     bool profiling = false;

@@ -51,7 +51,11 @@ MFB_D void mfb_cp_async16(double2* smem_dst, const double2* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 MFB_D void mfb_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+MFB_D void mfb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+MFB_D void mfb_cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the newest group
 #else
+inline void mfb_cp_async_commit() {}
+inline void mfb_cp_async_wait_but_one() {}
 inline void mfb_cp_async16(double2* d, const double2* s) { *d = *s; }
 inline void mfb_cp_async_wait_all() {}
 inline double2 mfb_ld_stream(const double2* p) { return *p; }

@@ -72,6 +72,7 @@ class LPTPipeline:
         mkconv = NaiveConvolver if cfg.ConvolverType == "naive" else OrszagConvolver
         self.conv = mkconv(self.N, self.Lbox) if order > 1 else None
         self.particles = None
+        self._ids_streamed = False
 
     # -- stages -------------------------------------------------------------------------
     def set_noise_k(self, W: np.ndarray):
@@ -192,8 +193,9 @@ class LPTPipeline:
         c = self.cfg
         if self.particles is None:
             self.make_particles(lattice_index)
-        if stream_to is not None and "ids" in stream_to:
+        if stream_to is not None and "ids" in stream_to and not self._ids_streamed:
             self.particles.stream_out("ids", stream_to["ids"])
+        self._ids_streamed = False
         for d in range(3):
             self.particles.set_positions(d, c.lunit, self.displacement_field(d))
         if stream_to is not None and "pos" in stream_to:
@@ -206,6 +208,10 @@ class LPTPipeline:
 
     def run_device(self, table: np.ndarray, particles=True, stream_to=None):
         """conditioned noise resident in k-space -> all LPT terms -> Psi, v (-> particle AoS), all on device"""
+        if particles and stream_to is not None and "ids" in stream_to and self.particles is not None:
+            # the IDs do not depend on the fields: their hand-off runs under the source stage
+            self.particles.stream_out("ids", stream_to["ids"])
+            self._ids_streamed = True
         self.compute_phi1(table)
         self.compute_sources()
         if particles:

@@ -118,22 +118,21 @@ template <class P, int MODE, int MINB, bool BATCH0 = false> static void run_v2(B
     cudaFree(tw2);
 }
 
-template <class P, int MODE, bool BATCH0 = false> static void run_v3(Bench& B, const char* label, int ctas = 148) {
+template <class P, int MODE> static void run_v3(Bench& B, const char* label, int ctas = 148) {
     if (MODE != B.mode) return;
-    auto k = strided3_kernel<P, MODE, BATCH0>;
+    auto k = strided3_kernel<P, MODE>;
     double2* tw2 = make_tw2<P>();
     constexpr size_t smem = 2 * P::SMEM_BYTES;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
-    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 2 * P::NTHREADS, smem));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::NTHREADS, smem));
     StridedArgs a = B.args();
     CK(cudaMemset(B.out, 0xff, B.out_elems * 16));
-    float ms = time_kernel([&] { k<<<ctas, 2 * P::NTHREADS, smem>>>(a, tw2); });
+    float ms = time_kernel([&] { k<<<ctas, P::NTHREADS, smem>>>(a, tw2); });
     report(B, label, ms, false, fa.numRegs, occ);
     cudaFree(tw2);
 }
-#define V3(MODE, ...) run_v3<Plan<__VA_ARGS__>, MODE>(B, "v3 ping-pong <" #__VA_ARGS__ ">")
-#define V3B(MODE, ...) run_v3<Plan<__VA_ARGS__>, MODE, true>(B, "v3 ping-pong batch0 <" #__VA_ARGS__ ">")
+#define V3(MODE, ...) run_v3<Plan<__VA_ARGS__>, MODE>(B, "v3 double-buffered <" #__VA_ARGS__ ">")
 
 static Bench make_bench(int n, int mode, int na) {
     Bench B; B.n = n; B.n_small = 2 * n / 3; B.nz = B.n_small / 2; B.na = na; B.mode = mode;
@@ -360,10 +359,11 @@ int main(int argc, char** argv) {
             run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 <768,32,8,12,8,8>", true);
             run_v2<Plan<768, 32, 8, 12, 8, 8>, SM_PAD, 2>(B, "v2 <768,32,8,12,8,8> minb 2");
             run_v2<Plan<768, 32, 8, 8, 8, 12>, SM_TRUNC, 2>(B, "v2 <768,32,8,8,8,12> minb 2");
-            V3(SM_PAD, 768, 32, 8, 12, 8, 8); V3B(SM_PAD, 768, 32, 8, 12, 8, 8); V3(SM_PAD, 768, 64, 4, 12, 8, 8); V3(SM_PAD, 768, 16, 16, 12, 8, 8);
-            V3(SM_TRUNC, 768, 32, 8, 8, 8, 12); V3B(SM_TRUNC, 768, 32, 8, 8, 8, 12); V3(SM_TRUNC, 768, 64, 4, 8, 8, 12);
+            V3(SM_PAD, 768, 32, 8, 12, 8, 8); V3(SM_PAD, 768, 64, 8, 12, 8, 8); V3(SM_PAD, 768, 64, 4, 12, 8, 8); V3(SM_PAD, 768, 128, 4, 12, 8, 8);
+            V3(SM_PAD, 768, 64, 8, 6, 16, 8);
+            V3(SM_TRUNC, 768, 32, 8, 8, 8, 12); V3(SM_TRUNC, 768, 64, 8, 8, 8, 12); V3(SM_TRUNC, 768, 64, 4, 8, 8, 12); V3(SM_TRUNC, 768, 128, 4, 8, 8, 12);
             if (mode == SM_TRUNC) { B.rmw = 1; printf("  -- RMW (op ADD)\n"); run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 rmw", true);
-                run_v2<Plan<768, 32, 8, 8, 8, 12>, SM_TRUNC, 2>(B, "v2 <768,32,8,8,8,12> minb 2"); V3(SM_TRUNC, 768, 32, 8, 8, 8, 12); }
+                run_v2<Plan<768, 32, 8, 8, 8, 12>, SM_TRUNC, 2>(B, "v2 <768,32,8,8,8,12> minb 2"); V3(SM_TRUNC, 768, 32, 8, 8, 8, 12); V3(SM_TRUNC, 768, 64, 8, 8, 8, 12); }
             free_bench(B);
         }
         if (which == 0 || which == 1536) for (int mode : {SM_PAD, SM_TRUNC}) {
@@ -371,11 +371,12 @@ int main(int argc, char** argv) {
             run_v1<Plan<1536, 32, 8, 16, 12, 8>>(B, "v1 <1536,32,8,16,12,8>", true);
             run_v2<Plan<1536, 64, 8, 12, 16, 8>, SM_PAD, 1>(B, "v2 <1536,64,8,12,16,8> minb 1");
             run_v2<Plan<1536, 64, 4, 8, 16, 12>, SM_TRUNC, 2>(B, "v2 <1536,64,4,8,16,12> minb 2");
-            V3(SM_PAD, 1536, 64, 4, 12, 16, 8); V3B(SM_PAD, 1536, 64, 4, 12, 16, 8); V3(SM_PAD, 1536, 32, 4, 12, 16, 8); V3(SM_PAD, 1536, 128, 2, 12, 16, 8);
-            V3(SM_PAD, 1536, 64, 4, 12, 8, 16); V3(SM_PAD, 1536, 32, 8, 12, 16, 8);
-            V3(SM_TRUNC, 1536, 64, 4, 8, 16, 12); V3B(SM_TRUNC, 1536, 64, 4, 8, 16, 12); V3(SM_TRUNC, 1536, 32, 4, 8, 16, 12); V3(SM_TRUNC, 1536, 64, 4, 16, 8, 12);
+            V3(SM_PAD, 1536, 64, 4, 12, 16, 8); V3(SM_PAD, 1536, 128, 4, 12, 16, 8); V3(SM_PAD, 1536, 32, 4, 12, 16, 8); V3(SM_PAD, 1536, 128, 2, 12, 16, 8);
+            V3(SM_PAD, 1536, 128, 4, 12, 8, 16); V3(SM_PAD, 1536, 256, 2, 12, 16, 8); V3(SM_PAD, 1536, 128, 4, 12, 8, 4, 4); V3(SM_PAD, 1536, 96, 4, 12, 16, 8);
+            V3(SM_TRUNC, 1536, 64, 4, 8, 16, 12); V3(SM_TRUNC, 1536, 128, 4, 8, 16, 12); V3(SM_TRUNC, 1536, 32, 4, 8, 16, 12); V3(SM_TRUNC, 1536, 128, 4, 16, 8, 12);
+            V3(SM_TRUNC, 1536, 128, 2, 8, 16, 12); V3(SM_TRUNC, 1536, 96, 4, 8, 16, 12);
             if (mode == SM_TRUNC) { B.rmw = 1; printf("  -- RMW (op ADD)\n"); run_v1<Plan<1536, 32, 8, 16, 12, 8>>(B, "v1 rmw", true);
-                run_v2<Plan<1536, 64, 8, 8, 16, 12>, SM_TRUNC, 1>(B, "v2 <1536,64,8,8,16,12> minb 1"); V3(SM_TRUNC, 1536, 64, 4, 8, 16, 12); }
+                run_v2<Plan<1536, 64, 8, 8, 16, 12>, SM_TRUNC, 1>(B, "v2 <1536,64,8,8,16,12> minb 1"); V3(SM_TRUNC, 1536, 64, 4, 8, 16, 12); V3(SM_TRUNC, 1536, 128, 4, 8, 16, 12); }
             free_bench(B);
         }
         return 0;

@@ -495,6 +495,34 @@ def check_multiply_noncubic(M, shape):
 
 
 # ------------------------------------------------------------------ kernel generations agree
+def check_product_grouping(M, n=32):
+    """3LPT sources with the products of each target summed in z-Fourier space before ONE forward transform (and squares
+    transformed once) against the reference's one-forward-transform-per-product sequence: equal up to rounding"""
+    L, Dp = 100.0, 0.0257
+    lib = M.grid._lib()
+    g, W, Wc, phi = noise_and_phi(n, L, 23)
+    amp = O.power_law_amplitude()
+    res = {}
+    try:
+        for grouping in (1, 0):
+            assert lib.mfb_set_option(b"conv_grouping", grouping) == 0
+            pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp))
+            pl.set_noise_k(W)
+            pl.condition_noise()
+            pl.compute_phi1(O.radial_table(g, amp))
+            l0 = M.kernel_launches()
+            pl.compute_sources()
+            res[grouping] = ([pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3],
+                             M.kernel_launches() - l0, pl.conv.workspace_bytes())
+    finally:
+        lib.mfb_set_option(b"conv_grouping", 1)
+    for a, b in zip(res[1][0], res[0][0]):
+        assert relerr(a, b) < 1e-13
+    R = 8 * n * n * (n + 2)
+    if res[1][2] > 7.5 * R:      # the accumulator was granted: 32 products instead of 33, 9 forward passes instead of 33
+        assert res[1][1] < res[0][1] - 50, (res[1][1], res[0][1])
+
+
 def check_kernel_generations(M, n):
     """the first-generation kernels (fft_kernels.cuh), the second-generation ones (fft_kernels2.cuh, fft_kernels_z2.cuh)
     and the ping-pong persistent strided pass (strided3_kernel) implement the same arithmetic: a dealiased product and an

@@ -106,3 +106,7 @@ def test_ppt_eulerian(M, order):
 
 def test_naive_pipeline(M):
     PC.check_naive_pipeline(M, 32)
+
+
+def test_product_grouping(M):
+    PC.check_product_grouping(M, 32)

@@ -63,6 +63,11 @@ def test_ppt_eulerian(M, n, order):
     PC.check_ppt(M, n, order)
 
 
+@pytest.mark.parametrize("n", [32, 128])
+def test_product_grouping(M, n):
+    PC.check_product_grouping(M, n)
+
+
 def test_naive_pipeline(M):
     PC.check_naive_pipeline(M, 64)
 

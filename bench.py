@@ -268,8 +268,19 @@ def run_b200(args):
     peak, peak_src = peaks()
     fftroles = [r for r in roles if r["gbs"]]
     dom = max(fftroles, key=lambda r: r["ms_per_step"])
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this very pipeline (per launch, next
+    # to the algorithmic bytes of the captured launch); null when no capture matches kernel role and padded length
+    traffic, traffic_note = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = cap.get(f"{dom['role']}@{3 * n // 2 if dom['role'].startswith('conv') else n}")
+        if ent and world == 1:
+            traffic = ent["dram_bytes_per_launch"]
+            traffic_note = {"captured_launch_alg_bytes": ent["alg_bytes_of_captured_launch"], "source": ent["source"]}
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom["role"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_capture": traffic_note, "peak_source": peak_src,
                 "share_of_step": dom["ms_per_step"] / ms, "avg_launch_ms": dom["avg_ms"],
                 "alg_bytes_per_launch": dom["alg_gb_per_launch"] * 1e9,
                 "frac_of_8000_nominal": dom["gbs"] / 8000.0}
@@ -305,6 +316,11 @@ def run_b200(args):
                          f"(numpy + torch/MKL FP64 FFT, {threads} threads); FFT cost grows as N^3 log N, so the "
                          f"{n}^3 figure would be lower"}
 
+    # the reference does 33 products (each with its own forward transform) at 3LPT, 5 at 2LPT; with the accumulator
+    # workspace the library sums the products of one target first
+    grouped = bool(pl.conv is not None and pl.conv.grouped())
+    nprod = {1: 0, 2: 5, 3: 32 if grouped else 33}[order]
+    nfwd = {1: 0, 2: 1 if grouped else 5, 3: 9 if grouped else 33}[order]
     if dist is not None:
         from monofonic_b200 import dist as MD
 
@@ -320,7 +336,8 @@ def run_b200(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, order), "grid": n, "lpt_order": order,
                        "l2": "inputs larger than L2 (every grid >= 1 GB; no flush needed)",
-                       "conv2_per_step": 33 if order > 2 else (5 if order > 1 else 0),
+                       "products_per_step": nprod, "forward_transforms_per_step": nfwd,
+                       "product_grouping": grouped,
                        "decomposition": (f"{world} x-slabs (real) / ky-slabs (k-space, transposed), exchange fused into the "
                                          f"FFT passes over peer memory, {nex // (max(3, args.warmup) + args.steps + 3)} exchanges/step"
                                          if world > 1 else "single slab")},

@@ -153,6 +153,13 @@ int mfb_conv_create(mfb_conv** c, const int n[3], const double L[3]);      /* in
 int mfb_conv_create_naive(mfb_conv** c, const int n[3], const double L[3]);
 int mfb_conv_destroy(mfb_conv* c);
 size_t mfb_conv_workspace_bytes(const mfb_conv* c);
+/* 1 when the optional accumulator workspace ([P0][P1][N2/2] complex, taken at creation only if HBM is plentiful) exists:
+   mfb_lpt_sources then sums the products of one target in z-Fourier space before ONE forward transform */
+int mfb_conv_grouped(const mfb_conv* c);
+/* When HBM was too tight for an own accumulator (3LPT 2048^3 on 8 GPUs), lend the convolver the position/velocity arrays of
+   a particle container as accumulator: they hold nothing while the sources are computed (src/ic_generator.cc:475-574 runs
+   before the species loop :832-955).  p == NULL returns the loan.  The caller keeps `p` alive while the loan lasts. */
+int mfb_conv_borrow_accumulator(mfb_conv* c, mfb_particles* p);
 /* All products: inputs are k-space N-grids, `out` is a k-space N-grid updated with `op` (alpha for MULADD).
    dims are axis pairs {a,b}: the operand is (i k_a)(i k_b) f^ with the gradient zeroed at Nyquist. */
 int mfb_conv_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r[2],

@@ -95,6 +95,8 @@ def _declare(lib):
         "mfb_conv_create_naive": (i, [vpp, ip, dp]),
         "mfb_conv_destroy": (i, [vp]),
         "mfb_conv_workspace_bytes": (sz, [vp]),
+        "mfb_conv_grouped": (i, [vp]),
+        "mfb_conv_borrow_accumulator": (i, [vp, vp]),
         "mfb_conv_hessians": (i, [vp, vp, ip, vp, ip, vp, i, d]),
         "mfb_conv_hessians3": (i, [vp, vp, ip, vp, ip, vp, ip, vp, i, d]),
         "mfb_conv_sum_hessians": (i, [vp, vp, ip, vp, ip, ip, vp, i, d]),

@@ -440,14 +440,23 @@ void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t 
 template <class P, int RPC, int MINB>
 void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale,
                      int acc) {
-    static bool done = false;
-    constexpr size_t smem = z_conv3_direct_smem<P, RPC>();
-    optin_smem(z_conv3_kernel<P, RPC, MINB, true>, smem, done);
+    static bool done = false, done_acc = false;
+    // accumulate launches prefetch the old output rows into shared memory where that does not cost a resident CTA
+    constexpr bool ACCBUF_OK = 227 * 1024 / z_conv3_direct_smem<P, RPC>(true) >= size_t(MINB);
     const unsigned grid = unsigned((nrows + RPC - 1) / RPC);
     const double2* tw = twiddles2<P>();
     RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * ((A == B ? 1.0 : 2.0) + (acc ? 2.0 : 1.0)));
-    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw,
-               acc);
+    if (acc && ACCBUF_OK) {
+        constexpr size_t smem = z_conv3_direct_smem<P, RPC>(true);
+        optin_smem(z_conv3_kernel<P, RPC, MINB, true, true>, smem, done_acc);
+        MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows,
+                   scale, tw, acc);
+    } else {
+        constexpr size_t smem = z_conv3_direct_smem<P, RPC>(false);
+        optin_smem(z_conv3_kernel<P, RPC, MINB, true, false>, smem, done);
+        MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true, false>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows,
+                   scale, tw, acc);
+    }
     check_launch("z_conv3_kernel");
 }
 static bool launch_zconv2(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
@@ -777,9 +786,33 @@ static void naive_conv(mfb_conv* c, const Operand& A, const Operand& B, const Op
     naive_forward_output(c, c->nb2, out, op, alpha);
 }
 
-static bool same_operand(const Operand& a, const Operand& b) {
-    return a.g == b.g && a.a1 == b.a1 && a.b1 == b.b1 && a.a2 == b.a2 && a.b2 == b.b2 && a.c1 == b.c1 && a.c2 == b.c2 &&
-           a.imag == b.imag && a.keep_nyq == b.keep_nyq;
+// a borrowed accumulator lives in the particle arrays: streamed hand-off copies of the previous run must have drained
+static void conv_acquire_accumulator(mfb_conv* c) {
+    if (!c->acc_borrowed || !c->lender) return;
+    for (int at : {MFB_ATTR_POS, MFB_ATTR_VEL}) {
+        if (c->lender->copy_pending[at]) {
+            cuda_check(cudaStreamWaitEvent(g_ctx.stream, c->lender->copied[at], 0), "cudaStreamWaitEvent");
+            c->lender->copy_pending[at] = false;
+        }
+    }
+}
+static mfb_operand_key operand_key(const Operand& o) {
+    // (a,b) and (b,a) name the same Hessian: store the axis pairs sorted
+    mfb_operand_key k;
+    k.g = o.g;
+    k.a1 = o.a1 < o.b1 ? o.a1 : o.b1; k.b1 = o.a1 < o.b1 ? o.b1 : o.a1;
+    k.a2 = o.a2 < o.b2 ? o.a2 : o.b2; k.b2 = o.a2 < o.b2 ? o.b2 : o.a2;
+    k.c1 = o.c1; k.c2 = o.c2; k.imag = o.imag; k.keep_nyq = o.keep_nyq; k.valid = true;
+    return k;
+}
+static bool same_key(const mfb_operand_key& a, const mfb_operand_key& b) {
+    return a.valid && b.valid && a.g == b.g && a.a1 == b.a1 && a.b1 == b.b1 && a.a2 == b.a2 && a.b2 == b.b2 && a.c1 == b.c1 &&
+           a.c2 == b.c2 && a.imag == b.imag && a.keep_nyq == b.keep_nyq;
+}
+static bool same_operand(const Operand& a, const Operand& b) { return same_key(operand_key(a), operand_key(b)); }
+static void conv_cache_clear(mfb_conv* c) { c->slot[0].valid = c->slot[1].valid = false; }
+static void conv_cache_invalidate(mfb_conv* c, const mfb_grid* g) {
+    for (int i = 0; i < 2; ++i) if (c->slot[i].g == g) c->slot[i].valid = false;
 }
 
 // ---- a GROUP of dealiased products with one target: out (op)= unpad( F[ sum_i coeff_i * a_i * b_i ] ).
@@ -787,29 +820,52 @@ static bool same_operand(const Operand& a, const Operand& b) {
 // sum in z-Fourier space (the padded accumulator Wacc, [P0][P1][N2/2]); the forward y and x passes, the truncation and the
 // output operator run ONCE per group.  Exact by linearity of the transforms and of the truncation; the
 // reference does one forward transform per product (include/convolution.hh:524-534).  Without Wacc (not enough HBM)
-// every product is its own group and the z pass works in place on W2a.
-// A product of an operand with itself transforms it once.
+// every product is its own group and the z pass works in place on an operand buffer.
+// A product of an operand with itself transforms it once, and inside mfb_lpt_sources (cache_on) an operand that is still
+// sitting in W2a / W2b from the previous product is not transformed again.
 struct ConvGroup {
     mfb_conv* c;
-    bool inplace;   // single product whose z pass overwrites W2a (leaves Wacc to an enclosing group)
+    bool inplace;   // single product whose z pass overwrites its first operand buffer (leaves Wacc to an enclosing group)
     int count = 0;
+    double2* sum = nullptr;
     explicit ConvGroup(mfb_conv* c_, bool inplace_ = false) : c(c_), inplace(inplace_ || c_->Wacc == nullptr || !g_ctx.conv_grouping) {}
-    double2* sum() const { return inplace ? c->W2a : c->Wacc; }
+    int cached(const mfb_operand_key& k) const {
+        if (!c->cache_on) return -1;
+        for (int i = 0; i < 2; ++i) if (same_key(c->slot[i], k)) return i;
+        return -1;
+    }
     void add(const Operand& A, const Operand& B, double coeff) {
         require(count == 0 || !inplace, "internal: product groups need the accumulator workspace");
         to_kspace(A.g);
         to_kspace(B.g);
         const int P1 = c->np[1], P2 = c->np[2], nzin = c->n[2] / 2;
-        const bool square = same_operand(A, B);
-        conv_backward_operand(c, A, c->W2a);
-        if (!square) conv_backward_operand(c, B, c->W2b);
-        launch_zconv(P2, c->W2a, square ? c->W2a : c->W2b, sum(), nzin, nzin, long(c->p0loc) * P1, nzin, coeff, count > 0);
+        double2* const buf[2] = {c->W2a, c->W2b};
+        const mfb_operand_key ka = operand_key(A), kb = operand_key(B);
+        const bool square = same_key(ka, kb);
+        int ia = cached(ka), ib = square ? ia : cached(kb);
+        auto transform = [&](const Operand& o, const mfb_operand_key& k, int i) {
+            conv_backward_operand(c, o, buf[i]);
+            c->slot[i] = k;
+        };
+        if (square) {
+            if (ia < 0) { ia = c->slot[0].valid && !c->slot[1].valid ? 1 : 0; transform(A, ka, ia); }
+            ib = ia;
+        } else if (ia >= 0 && ib >= 0) {
+            // both operands are still there
+        } else if (ia >= 0) { ib = 1 - ia; transform(B, kb, ib); }
+        else if (ib >= 0) { ia = 1 - ib; transform(A, ka, ia); }
+        else { ia = 0; ib = 1; transform(A, ka, 0); transform(B, kb, 1); }
+        sum = inplace ? buf[ia] : c->Wacc;
+        if (!inplace && count == 0) conv_acquire_accumulator(c);
+        launch_zconv(P2, buf[ia], buf[ib], sum, nzin, nzin, long(c->p0loc) * P1, nzin, coeff, count > 0);
+        if (inplace) c->slot[ia].valid = false;   // overwritten by the product
         ++count;
         ++c->nconv;
     }
     void finish(mfb_grid* out, int op, double alpha) {
         require(count > 0, "internal: empty product group");
         require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
+        conv_cache_invalidate(c, out);   // the target changes: an operand transformed from its old contents is stale
         const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2];
         const int P0 = c->np[0], P1 = c->np[1], P2 = c->np[2];
         const int nzc = N2 / 2 + 1, nzin = N2 / 2;
@@ -819,7 +875,7 @@ struct ConvGroup {
             const int p0l = c->p0loc, l1 = out->nloc1;
             // y forward P1 -> N1 on the local x planes, routed to the owners of the ky rows
             Exchange x = begin_exchange(size_t(p0l) * l1 * nzin);
-            StridedArgs d = plain_strided(sum(), nullptr, nzin, ptrdiff_t(P1) * nzin, p0l, nzin, P1, 0);
+            StridedArgs d = plain_strided(sum, nullptr, nzin, ptrdiff_t(P1) * nzin, p0l, nzin, P1, 0);
             d.n_out = N1;
             route(d, x, l1, nzin, ptrdiff_t(l1) * nzin);                    // chunk layout [x_loc][ky_loc][kz]
             launch_strided(P1, d, ROLE_CONV_Y_FWD);
@@ -839,7 +895,7 @@ struct ConvGroup {
             return;
         }
         // y axis forward, P1 -> N1
-        StridedArgs d = plain_strided(sum(), c->W1, nzin, 0, P0, nzin, P1, 0);
+        StridedArgs d = plain_strided(sum, c->W1, nzin, 0, P0, nzin, P1, 0);
         d.in_as = ptrdiff_t(P1) * nzin;
         d.out_as = ptrdiff_t(N1) * nzin;
         d.n_out = N1;
@@ -862,6 +918,7 @@ static bool can_group(const mfb_conv* c) { return !c->naive && c->Wacc != nullpt
 void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
     require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
     if (c->naive) { naive_conv(c, A, B, nullptr, out, op, alpha); return; }
+    c->cache_on = false;
     ConvGroup g(c);
     g.add(A, B, 1.0);
     g.finish(out, op, alpha);
@@ -890,6 +947,10 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
     auto H = [](mfb_grid* g, int a, int b) { int d[2] = {a, b}; return hessian_operand(g, d); };
     auto HS = [](mfb_grid* g, int a, int b, int cc, int d, double sgn) { return Operand{g, a, b, cc, d, -1.0, -sgn, 0}; };
     const bool grouped = can_group(c);
+    // The product ORDER inside a group (and of the groups) is free; it is chosen so that consecutive products share an
+    // operand, which then stays in its buffer (cache_on): 50 operand transforms instead of 64 at 3LPT.
+    conv_cache_clear(c);
+    c->cache_on = grouped;
     if (order > 1 && grouped) {
         require(phi2 != nullptr, "phi2 grid required for LPT order > 1");
         phi2->space = MFB_KSPACE;
@@ -897,9 +958,9 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
         ConvGroup g(c);
         g.add(H(phi, 0, 0), HS(phi, 1, 1, 2, 2, +1.0), 1.0);
         g.add(H(phi, 1, 1), H(phi, 2, 2), 1.0);
-        g.add(H(phi, 0, 1), H(phi, 0, 1), -1.0);
         g.add(H(phi, 0, 2), H(phi, 0, 2), -1.0);
         g.add(H(phi, 1, 2), H(phi, 1, 2), -1.0);
+        g.add(H(phi, 0, 1), H(phi, 0, 1), -1.0);
         g.finish(phi2, OP_ASSIGN, 0.0);
     } else if (order > 1) {
         require(phi2 != nullptr, "phi2 grid required for LPT order > 1");
@@ -931,40 +992,44 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
         // outer field are summed first:  det = T(xx yy - xy xy) zz + 2 T(xy xz) yz - T(yz yz) xx - T(xz xz) yy.
         {
             ConvGroup in(c);
+            in.add(H(phi, 0, 1), H(phi, 0, 1), -1.0);   // still in its buffer when phi2 was the previous target
             in.add(H(phi, 0, 0), H(phi, 1, 1), 1.0);
-            in.add(H(phi, 0, 1), H(phi, 0, 1), -1.0);
             in.finish(fb, OP_ASSIGN, 0.0);
         }
-        ConvGroup g3(c);   // every term of phi3 (3a outer products and 3b) goes into one sum
-        g3.add(FB, H(phi, 2, 2), 1.0);
+        ConvGroup g3(c);   // every term of phi3 (3a outer products and 3b :533-538) goes into one sum
         auto inner = [&](const Operand& a, const Operand& b) {
             ConvGroup in(c, true);   // the accumulator belongs to g3: single product, in place
             in.add(a, b, 1.0);
             in.finish(fb, OP_ASSIGN, 0.0);
         };
+        g3.add(FB, H(phi, 2, 2), 1.0);
+        g3.add(H(phi, 2, 2), HS(phi2, 0, 0, 1, 1, +1.0), -5.0 / 7.0);
         inner(H(phi, 0, 1), H(phi, 0, 2));
         g3.add(FB, H(phi, 1, 2), 2.0);
+        g3.add(H(phi, 1, 2), H(phi2, 1, 2), 10.0 / 7.0);
         inner(H(phi, 1, 2), H(phi, 1, 2));
         g3.add(FB, H(phi, 0, 0), -1.0);
+        g3.add(H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), -5.0 / 7.0);
         inner(H(phi, 0, 2), H(phi, 0, 2));
         g3.add(FB, H(phi, 1, 1), -1.0);
-        // 3b  :533-538
-        g3.add(H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), -5.0 / 7.0);
         g3.add(H(phi, 1, 1), HS(phi2, 2, 2, 0, 0, +1.0), -5.0 / 7.0);
-        g3.add(H(phi, 2, 2), HS(phi2, 0, 0, 1, 1, +1.0), -5.0 / 7.0);
         g3.add(H(phi, 0, 1), H(phi2, 0, 1), 10.0 / 7.0);
         g3.add(H(phi, 0, 2), H(phi2, 0, 2), 10.0 / 7.0);
-        g3.add(H(phi, 1, 2), H(phi2, 1, 2), 10.0 / 7.0);
         g3.finish(phi3, OP_ASSIGN, 0.0);
         grid_laplacian_pow(phi3, -1, -1.0);  // :539
-        // transverse term  :545-556
+        // transverse term  :545-556:  A_d = P1 - P2 + P3 - P4
         for (int d = 0; d < 3; ++d) {
             const int p = (d + 1) % 3, q = (d + 2) % 3;
             mfb_grid* A = A3[d];
             A->space = MFB_KSPACE;
             ConvGroup ga(c);
-            ga.add(H(phi2, d, p), H(phi, d, q), 1.0);
-            ga.add(H(phi2, d, q), H(phi, d, p), -1.0);
+            if (d == 0) {   // start with phi2,xz (left over from the last phi3 product), end with phi2,yz (first of d = 1)
+                ga.add(H(phi2, d, q), H(phi, d, p), -1.0);
+                ga.add(H(phi2, d, p), H(phi, d, q), 1.0);
+            } else {        // d = 1 starts with phi2,yz and ends with phi2,zx, which d = 2 starts with
+                ga.add(H(phi2, d, p), H(phi, d, q), 1.0);
+                ga.add(H(phi2, d, q), H(phi, d, p), -1.0);
+            }
             ga.add(H(phi, p, q), HS(phi2, p, p, q, q, -1.0), 1.0);
             ga.add(H(phi2, p, q), HS(phi, p, p, q, q, -1.0), -1.0);
             ga.finish(A, OP_ASSIGN, 0.0);
@@ -998,6 +1063,8 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
             grid_laplacian_pow(A, -1, -1.0);
         }
     }
+    c->cache_on = false;
+    conv_cache_clear(c);
     // :561-574
     grid_scale(phi, g1);
     if (order > 1) grid_scale(phi2, g2);
@@ -1126,6 +1193,7 @@ int mfb_set_option(const char* name, int value) {
     if (std::string(name) == "strided_v2") g_ctx.strided_v2 = value != 0;
     else if (std::string(name) == "strided_v3") g_ctx.strided_v3 = value != 0;
     else if (std::string(name) == "conv_grouping") g_ctx.conv_grouping = value != 0;
+    else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
     else throw std::runtime_error(std::string("unknown option ") + name);
     MFB_CATCH
@@ -1674,13 +1742,13 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
     c->naive = 0; c->nb1 = c->nb2 = nullptr;
     // the accumulator of product groups is an optimisation, not a requirement: take it only if HBM is plentiful after it
     // (room for the particle arrays and the remaining grids of a 3LPT run: 3.75 R(N) of this slab)
-    c->Wacc = nullptr;
+    c->Wacc = nullptr; c->acc_borrowed = false; c->lender = nullptr;
     {
         size_t free_b = 0, total_b = 0;
         cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
         const size_t w2_bytes = c->w2_elems * sizeof(double2);
         const size_t reserve = size_t(3.75 * double(c->fbuf->ntot) * sizeof(double));
-        if (free_b > w2_bytes + reserve) c->Wacc = (double2*)dev_alloc(w2_bytes);
+        if (g_ctx.conv_own_accumulator && free_b > w2_bytes + reserve) c->Wacc = (double2*)dev_alloc(w2_bytes);
     }
     *out = c;
     MFB_CATCH
@@ -1706,7 +1774,7 @@ int mfb_conv_destroy(mfb_conv* c) {
         if (c->W1) cudaFree(c->W1);
         if (c->W2a) cudaFree(c->W2a);
         if (c->W2b) cudaFree(c->W2b);
-        if (c->Wacc) cudaFree(c->Wacc);
+        if (c->Wacc && !c->acc_borrowed) cudaFree(c->Wacc);
         if (c->fbuf) mfb_grid_destroy(c->fbuf);
         if (c->nb1) mfb_grid_destroy(c->nb1);
         if (c->nb2) mfb_grid_destroy(c->nb2);
@@ -1717,6 +1785,21 @@ int mfb_conv_destroy(mfb_conv* c) {
 size_t mfb_conv_workspace_bytes(const mfb_conv* c) {
     if (c->naive) return (c->nb1->ntot + c->nb2->ntot) * sizeof(double);
     return (c->w1_elems + (c->Wacc ? 3 : 2) * c->w2_elems) * sizeof(double2) + c->fbuf->ntot * sizeof(double);
+}
+int mfb_conv_grouped(const mfb_conv* c) { return can_group(c) ? 1 : 0; }
+int mfb_conv_borrow_accumulator(mfb_conv* c, mfb_particles* p) {
+    MFB_TRY
+    require(!c->naive, "the NaiveConvolver has no accumulator");
+    if (p == nullptr) {   // give it back
+        if (c->acc_borrowed) { c->Wacc = nullptr; c->acc_borrowed = false; c->lender = nullptr; }
+        return 0;
+    }
+    if (c->Wacc != nullptr) return 0;   // already has one (its own, or borrowed)
+    require(p->posvel_bytes >= c->w2_elems * sizeof(double2), "particle arrays are too small to serve as the accumulator");
+    c->Wacc = (double2*)p->pos;
+    c->acc_borrowed = true;
+    c->lender = p;
+    MFB_CATCH
 }
 static void check_conv_grids(mfb_conv* c, mfb_grid* a, mfb_grid* b, mfb_grid* o) {
     for (mfb_grid* g : {a, b, o})
@@ -1798,8 +1881,9 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
     }
     p->np = ov * size_t(p->nloc0) * n[1] * n[2];   // get_local_num_particles (particle_container.hh:150-152)
     const size_t rs = real64 ? 8 : 4, is = ids64 ? 8 : 4;
-    p->pos = dev_alloc(3 * p->np * rs);
-    p->vel = dev_alloc(3 * p->np * rs);
+    p->posvel_bytes = 6 * p->np * rs;
+    p->pos = dev_alloc(p->posvel_bytes);                 // one block: it can be lent to the convolver as its accumulator
+    p->vel = (char*)p->pos + 3 * p->np * rs;
     p->ids = dev_alloc(p->np * is);
     p->mass = with_masses ? dev_alloc(p->np * rs) : nullptr;
     *out = p;
@@ -1810,7 +1894,7 @@ int mfb_particles_destroy(mfb_particles* p) {
     if (p) {
         if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
         for (int a = 0; a < 4; ++a) if (p->copied[a]) cudaEventDestroy(p->copied[a]);
-        cudaFree(p->pos); cudaFree(p->vel); cudaFree(p->ids);
+        cudaFree(p->pos); cudaFree(p->ids);
         if (p->mass) cudaFree(p->mass);
         delete p;
     }

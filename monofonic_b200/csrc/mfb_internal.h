@@ -31,10 +31,20 @@ struct mfb_cgrid {
     size_t nelem;
 };
 
+// identity of a backward-transformed operand held in one of the convolver's operand buffers
+struct mfb_operand_key {
+    const void* g; int a1, b1, a2, b2; double c1, c2; int imag, keep_nyq; bool valid;
+};
+
+struct mfb_particles;
 struct mfb_conv {
     int n[3], np[3];
     double L[3];
     double2 *W1, *W2a, *W2b;  // workspaces: [P0][N1][N2/2], [P0][P1][N2/2] x2  
+    mfb_operand_key slot[2];  // what W2a / W2b hold (only trusted inside one mfb_lpt_sources call: cache_on)
+    bool cache_on;
+    bool acc_borrowed;        // Wacc points into the particle arrays of `lender` (mfb_conv_borrow_accumulator)
+    mfb_particles* lender;
     double2* Wacc;            // optional [P0][P1][N2/2]: running sum of a product group in z-Fourier space (NULL: no grouping)
     size_t w1_elems, w2_elems;
     int dist, p0loc, p0off;   // slab of the padded grid along axis 0 (real space)
@@ -49,7 +59,8 @@ struct mfb_particles {
     int lattice_type, real64, ids64;
     size_t np;        // local number of particles
     int nloc0, off0;  // slab of lattice planes held by this rank
-    void *pos, *vel, *ids, *mass;  // device AoS (particle_container.hh:82-108)
+    void *pos, *vel, *ids, *mass;  // device AoS (particle_container.hh:82-108); pos and vel are one allocation (vel = pos + 3 np)
+    size_t posvel_bytes;
     // streamed hand-off: per attribute, event recorded on the copy stream after its D2H copy (null: none pending)
     cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr};
     bool copy_pending[4] = {false, false, false, false};
@@ -97,6 +108,7 @@ struct Context {
     int num_sms = 148;
     bool strided_v2 = true;  // second-generation strided pass (fft_kernels2.cuh)
     bool strided_v3 = false; // persistent double-buffered strided pass (strided3_kernel): measured no faster, kept as an option
+    bool conv_own_accumulator = true;  // tests: 0 makes mfb_conv_create behave as under memory pressure
     bool conv_grouping = true;  // sum the products of one target before the forward passes (needs mfb_conv::Wacc)
     bool zconv_v2 = true;    // second-generation fused z pass (fft_kernels_z2.cuh)
     // optional per-role device timing (cudaEvents on `stream` around every launch)

@@ -341,6 +341,16 @@ class OrszagConvolver:
     def workspace_bytes(self):
         return int(self._lib.mfb_conv_workspace_bytes(self._h))
 
+    def borrow_accumulator(self, particles):
+        """lend the (idle during the source stage) position/velocity arrays of `particles` as accumulator workspace when the
+        convolver could not afford its own; None returns the loan"""
+        L.check(self._lib.mfb_conv_borrow_accumulator(self._h, particles._h if particles is not None else None), self._lib)
+
+    def grouped(self):
+        """True when the accumulator workspace was granted, i.e. mfb_lpt_sources sums the products of one target before a
+        single forward transform"""
+        return bool(self._lib.mfb_conv_grouped(self._h))
+
     def convolve_Hessians(self, *args):
         """(inl, d2l, inr, d2r, output_op)  or  (inl, d2l, inm, d2m, inr, d2r, output_op)"""
         if len(args) == 5:

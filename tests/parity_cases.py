@@ -518,6 +518,27 @@ def check_product_grouping(M, n=32):
         lib.mfb_set_option(b"conv_grouping", 1)
     for a, b in zip(res[1][0], res[0][0]):
         assert relerr(a, b) < 1e-13
+    # memory-pressure path: no own accumulator -> ungrouped until the particle arrays are lent to the convolver
+    try:
+        assert lib.mfb_set_option(b"conv_own_accumulator", 0) == 0
+        pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp, ParticleLoad="sc", real64=False))
+        assert not pl.conv.grouped()
+        pl.make_particles()
+        assert pl.conv.grouped()
+        for rep in range(2):          # second run: the loan is taken back from live particle data + pending hand-off copies
+            pl.set_noise_k(W)
+            pl.condition_noise()
+            npart = pl.particles.get_local_num_particles()
+            out = {"pos": np.zeros((npart, 3), np.float32), "vel": np.zeros((npart, 3), np.float32)}
+            pl.run_device(O.radial_table(g, amp), particles=True, stream_to=out)
+        pl.particles.stream_wait()
+        l0 = M.kernel_launches()
+        got = [pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3]
+        assert np.array_equal(out["pos"], pl.particles.download()["pos"])
+    finally:
+        lib.mfb_set_option(b"conv_own_accumulator", 1)
+    for a, b in zip(got, res[1][0]):
+        assert relerr(a, b) < 1e-13
     R = 8 * n * n * (n + 2)
     if res[1][2] > 7.5 * R:      # the accumulator was granted: 32 products instead of 33, 9 forward passes instead of 33
         assert res[1][1] < res[0][1] - 50, (res[1][1], res[0][1])

@@ -250,8 +250,9 @@ template <class P, int s, int NT> MFB_D void z3_dif_mid_pair(double2* l0, const 
 // DIRECT: the operand rows are read straight from global memory in the legs of stage 0 instead of being staged in shared
 // memory by cp.async: 55 KB instead of 88 KB per CTA at n = 1536 (4 CTAs per SM instead of 2 - the in-pipeline capture
 // profiles/r01_ncu_full_z3_1536_in_pipeline.txt shows barrier stalls of 3.3 per issue with two 256-thread CTAs).
-// ACCBUF (DIRECT only): accumulate launches prefetch the old output rows into an extra shared-memory area.
-template <class P, int RPC, int MINB, bool DIRECT = false, bool ACCBUF = false>
+// (Prefetching the old output rows of an accumulate launch into shared memory with cp.async was measured and dropped:
+// 7.05 vs 6.34 ms at n = 1536, profiles/r01_kbench_z4_3072_and_accbuf.txt - the extra 16 KB per CTA cost more than the tail latency.)
+template <class P, int RPC, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     z_conv3_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
                    ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw, int accumulate = 0) {
@@ -266,19 +267,6 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     const int tid = threadIdx.x;
     const long row0 = long(blockIdx.x) * RPC;
 
-    if constexpr (DIRECT && ACCBUF) {
-        // accumulate mode: the old values of the output rows are fetched asynchronously now (into the area the staged variant
-        // uses for the raw rows) and consumed by the same thread in the final loop - no exposed latency at the tail
-        if (accumulate) {
-            for (int idx = tid; idx < (RPC / 2) * NZ; idx += NT) {
-                const int mm = idx / NZ, k = idx - mm * NZ;
-                const long r1 = row0 + 2 * mm, r2 = r1 + 1;
-                if (r1 < nrows) mfb_cp_async16(raw + (2 * mm) * NZ + k, out + r1 * out_pitch + k);
-                if (r2 < nrows) mfb_cp_async16(raw + (2 * mm + 1) * NZ + k, out + r2 * out_pitch + k);
-            }
-            mfb_cp_async_commit();
-        }
-    }
     if constexpr (!DIRECT) {
         for (int idx = tid; idx < RPC * 2 * NZ; idx += NT) {
             const int o = idx / NZ, k = idx - o * NZ;
@@ -402,7 +390,6 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     }
     __syncthreads();
     {
-        if (DIRECT && ACCBUF && accumulate) mfb_cp_async_wait_all();
         const double h = 0.5 * scale;
         for (int idx = tid; idx < (RPC / 2) * NZ; idx += NT) {
             const int mm = idx / NZ, k = idx - mm * NZ;
@@ -413,13 +400,8 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
             double2 v1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
             double2 v2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
             if (accumulate) {   // sum of products of one target, formed before the (single) forward y/x passes
-                if constexpr (DIRECT && ACCBUF) {
-                    if (r1 < nrows) { const double2 o = raw[(2 * mm) * NZ + k]; v1.x += o.x; v1.y += o.y; }
-                    if (r2 < nrows) { const double2 o = raw[(2 * mm + 1) * NZ + k]; v2.x += o.x; v2.y += o.y; }
-                } else {
-                    if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
-                    if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
-                }
+                if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
+                if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
             }
             if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, v1);
             if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, v2);
@@ -428,8 +410,6 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
 }
 
 template <class P, int RPC> constexpr size_t z_conv2_smem() { return size_t(RPC) * (zpad(P::N) + 1 + 2 * (P::N / 3)) * sizeof(double2); }
-template <class P, int RPC> constexpr size_t z_conv3_direct_smem(bool accbuf = false) {
-    return size_t(RPC) * (zpad(P::N) + 1 + (accbuf ? P::N / 3 : 0)) * sizeof(double2);
-}
+template <class P, int RPC> constexpr size_t z_conv3_direct_smem() { return size_t(RPC) * (zpad(P::N) + 1) * sizeof(double2); }
 
 }  // namespace mfb

@@ -247,7 +247,7 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     X(384, 32, 2, 4, 6, 8, 8)     \
     X(768, 64, 2, 5, 12, 8, 8)    \
     X(1536, 64, 2, 3, 12, 16, 8)  \
-    X(3072, 128, 2, 2, 6, 8, 8, 8)
+    X(3072, 128, 2, 2, 12, 16, 16)
 
 // double-buffered plans (strided3_kernel): two tile buffers per CTA, so a tile must fit half of the shared memory
 #define MFB_FOR_EACH_PLAN3_B(X)   \
@@ -440,23 +440,15 @@ void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t 
 template <class P, int RPC, int MINB>
 void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale,
                      int acc) {
-    static bool done = false, done_acc = false;
-    // accumulate launches prefetch the old output rows into shared memory where that does not cost a resident CTA
-    constexpr bool ACCBUF_OK = 227 * 1024 / z_conv3_direct_smem<P, RPC>(true) >= size_t(MINB);
+    static bool done = false;
+    constexpr size_t smem = z_conv3_direct_smem<P, RPC>();
+    optin_smem(z_conv3_kernel<P, RPC, MINB, true>, smem, done);
     const unsigned grid = unsigned((nrows + RPC - 1) / RPC);
     const double2* tw = twiddles2<P>();
+    // algorithmic bytes: both operand rows (one if A == B) + the output row (+ its old value when accumulating)
     RoleScope rs(ROLE_CONV_Z, double(nrows) * double(P::N / 3) * 16.0 * ((A == B ? 1.0 : 2.0) + (acc ? 2.0 : 1.0)));
-    if (acc && ACCBUF_OK) {
-        constexpr size_t smem = z_conv3_direct_smem<P, RPC>(true);
-        optin_smem(z_conv3_kernel<P, RPC, MINB, true, true>, smem, done_acc);
-        MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows,
-                   scale, tw, acc);
-    } else {
-        constexpr size_t smem = z_conv3_direct_smem<P, RPC>(false);
-        optin_smem(z_conv3_kernel<P, RPC, MINB, true, false>, smem, done);
-        MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true, false>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows,
-                   scale, tw, acc);
-    }
+    MFB_LAUNCH((z_conv3_kernel<P, RPC, MINB, true>), grid, P::TPL * RPC, smem, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, scale, tw,
+               acc);
     check_launch("z_conv3_kernel");
 }
 static bool launch_zconv2(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,

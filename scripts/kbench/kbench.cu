@@ -240,21 +240,6 @@ template <class P, int RPC, int MINB> static void zrun_v3d(ZBench& Z, const char
     zreport(Z, label, ms, false, fa.numRegs, occ, smem);
     cudaFree(tw2);
 }
-// accumulate launches: old output rows read at the end from global memory (ACCBUF false) or prefetched into shared memory
-template <class P, int RPC, int MINB, bool ACCBUF> static void zrun_v3acc(ZBench& Z, const char* label) {
-    auto k = z_conv3_kernel<P, RPC, MINB, true, ACCBUF>;
-    double2* tw2 = make_tw2<P>();
-    constexpr size_t smem = z_conv3_direct_smem<P, RPC>(ACCBUF);
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
-    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::TPL * RPC, smem));
-    const unsigned grid = unsigned((Z.nrows + RPC - 1) / RPC);
-    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, tw2, 1); });
-    printf("%-50s %8.3f ms %8.1f GB/s  regs %3d  CTA/SM %d smem %3zu KB  (accumulate, 4 x rows of traffic)\n", label, ms,
-           4.0 * Z.nrows * Z.nz * 16 / ms / 1e6, fa.numRegs, occ, smem / 1024);
-    cudaFree(tw2);
-}
-#define Z3ACC(ACCBUF, RPC, MINB, ...) zrun_v3acc<Plan<__VA_ARGS__>, RPC, MINB, ACCBUF>(Z, "z3 direct acc" #ACCBUF " <" #__VA_ARGS__ "> minb " #MINB)
 #define Z3D(RPC, MINB, ...) zrun_v3d<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z3 direct <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
 static void zbench4(int which) {
     if (which == 0 || which == 768) {
@@ -271,7 +256,6 @@ static void zbench4(int which) {
         Z3D(2, 2, 1536, 128, 2, 12, 16, 8); Z3D(2, 4, 1536, 64, 2, 12, 16, 8); Z3D(2, 3, 1536, 64, 2, 12, 16, 8);
         Z3D(2, 4, 1536, 64, 2, 12, 4, 4, 8); Z3D(2, 4, 1536, 32, 2, 12, 16, 8); Z3D(2, 4, 1536, 32, 2, 12, 4, 4, 8);
         Z3D(2, 3, 1536, 96, 2, 12, 16, 8); Z3D(2, 2, 1536, 64, 2, 12, 16, 8); Z3D(2, 4, 1536, 64, 2, 12, 8, 2, 8);
-        Z3ACC(false, 2, 3, 1536, 64, 2, 12, 16, 8); Z3ACC(true, 2, 3, 1536, 64, 2, 12, 16, 8);
     }
     if (which == 0 || which == 3072) {
         ZBench Z = make_zbench(3072, 3072L * 96);
@@ -279,7 +263,6 @@ static void zbench4(int which) {
         Z3D(2, 2, 3072, 128, 2, 6, 8, 8, 8); Z3D(2, 1, 3072, 128, 2, 6, 8, 8, 8); Z3D(2, 2, 3072, 128, 2, 12, 16, 16); Z3D(2, 2, 3072, 256, 2, 12, 16, 16);
         Z3D(2, 1, 3072, 128, 2, 12, 16, 16); Z3D(2, 2, 3072, 64, 2, 12, 16, 16); Z3D(2, 2, 3072, 128, 2, 12, 4, 8, 8); Z3D(2, 2, 3072, 256, 2, 12, 4, 8, 8);
         Z3D(2, 2, 3072, 192, 2, 12, 16, 16); Z3D(2, 2, 3072, 256, 2, 6, 8, 8, 8);
-        Z3ACC(false, 2, 2, 3072, 128, 2, 6, 8, 8, 8);
     }
 }
 static void zbench3(int which) {

@@ -988,27 +988,27 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
             in.add(H(phi, 0, 0), H(phi, 1, 1), 1.0);
             in.finish(fb, OP_ASSIGN, 0.0);
         }
-        ConvGroup g3(c);   // every term of phi3 (3a outer products and 3b :533-538) goes into one sum
+        ConvGroup gp3(c);   // every term of phi3 (3a outer products and 3b :533-538) goes into one sum
         auto inner = [&](const Operand& a, const Operand& b) {
-            ConvGroup in(c, true);   // the accumulator belongs to g3: single product, in place
+            ConvGroup in(c, true);   // the accumulator belongs to gp3: single product, in place
             in.add(a, b, 1.0);
             in.finish(fb, OP_ASSIGN, 0.0);
         };
-        g3.add(FB, H(phi, 2, 2), 1.0);
-        g3.add(H(phi, 2, 2), HS(phi2, 0, 0, 1, 1, +1.0), -5.0 / 7.0);
+        gp3.add(FB, H(phi, 2, 2), 1.0);
+        gp3.add(H(phi, 2, 2), HS(phi2, 0, 0, 1, 1, +1.0), -5.0 / 7.0);
         inner(H(phi, 0, 1), H(phi, 0, 2));
-        g3.add(FB, H(phi, 1, 2), 2.0);
-        g3.add(H(phi, 1, 2), H(phi2, 1, 2), 10.0 / 7.0);
+        gp3.add(FB, H(phi, 1, 2), 2.0);
+        gp3.add(H(phi, 1, 2), H(phi2, 1, 2), 10.0 / 7.0);
         inner(H(phi, 1, 2), H(phi, 1, 2));
-        g3.add(FB, H(phi, 0, 0), -1.0);
-        g3.add(H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), -5.0 / 7.0);
+        gp3.add(FB, H(phi, 0, 0), -1.0);
+        gp3.add(H(phi, 0, 0), HS(phi2, 1, 1, 2, 2, +1.0), -5.0 / 7.0);
         inner(H(phi, 0, 2), H(phi, 0, 2));
-        g3.add(FB, H(phi, 1, 1), -1.0);
-        g3.add(H(phi, 1, 1), HS(phi2, 2, 2, 0, 0, +1.0), -5.0 / 7.0);
-        g3.add(H(phi, 0, 1), H(phi2, 0, 1), 10.0 / 7.0);
-        g3.add(H(phi, 0, 2), H(phi2, 0, 2), 10.0 / 7.0);
-        g3.finish(phi3, OP_ASSIGN, 0.0);
-        grid_laplacian_pow(phi3, -1, -1.0);  // :539
+        gp3.add(FB, H(phi, 1, 1), -1.0);
+        gp3.add(H(phi, 1, 1), HS(phi2, 2, 2, 0, 0, +1.0), -5.0 / 7.0);
+        gp3.add(H(phi, 0, 1), H(phi2, 0, 1), 10.0 / 7.0);
+        gp3.add(H(phi, 0, 2), H(phi2, 0, 2), 10.0 / 7.0);
+        gp3.finish(phi3, OP_ASSIGN, 0.0);
+        grid_laplacian_pow(phi3, -1, -g3);   // :539 and the growth factor of :566 (phi3 is not read again before it) in one sweep
         // transverse term  :545-556:  A_d = P1 - P2 + P3 - P4
         for (int d = 0; d < 3; ++d) {
             const int p = (d + 1) % 3, q = (d + 2) % 3;
@@ -1025,7 +1025,7 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
             ga.add(H(phi, p, q), HS(phi2, p, p, q, q, -1.0), 1.0);
             ga.add(H(phi2, p, q), HS(phi, p, p, q, q, -1.0), -1.0);
             ga.finish(A, OP_ASSIGN, 0.0);
-            grid_laplacian_pow(A, -1, -1.0);
+            grid_laplacian_pow(A, -1, -g3c);     // :555 and :568-570 in one sweep
         }
     } else if (order > 2) {
         phi3->space = MFB_KSPACE;
@@ -1060,7 +1060,7 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
     // :561-574
     grid_scale(phi, g1);
     if (order > 1) grid_scale(phi2, g2);
-    if (order > 2) {
+    if (order > 2 && !grouped) {
         grid_scale(phi3, g3);
         for (int d = 0; d < 3; ++d) grid_scale(A3[d], g3c);
     }

@@ -20,49 +20,10 @@ namespace mfb {
 
 enum StridedMode { SM_PLAIN = 0, SM_PAD = 1, SM_TRUNC = 2 };
 
-#ifndef MFB_MID_PIPELINE
-#define MFB_MID_PIPELINE 0
-#endif
 template <class P, int MODE, int s>
 MFB_D void strided2_mid_stage(double2* __restrict__ sm, const double2* __restrict__ tw, int line, int q) {
     constexpr int T = P::T;
     constexpr int r = P::radix(s), L = P::len(s), M = L / r, Bn = P::N / r;
-#if MFB_MID_PIPELINE
-    // software-pipelined variant (experiment): the legs of butterfly i+1 are requested before butterfly i is computed, so
-    // one warp overlaps its own shared-memory latency with its FP64 work (butterflies of a stage touch disjoint positions)
-    auto ld = [&](int b, double2* v) {
-        const int blk = b / M, j = b - blk * M;
-        const double2* sp = sm + (blk * L + j) * T + line;
-#pragma unroll
-        for (int t = 0; t < r; ++t) v[t] = sp[t * M * T];
-    };
-    auto run = [&](int b, double2* v) {
-        const int blk = b / M, j = b - blk * M;
-        double2* sp = sm + (blk * L + j) * T + line;
-        Dft<r>::run(v);
-        const double2* twp = tw + P::tw2_off(s) + j;
-#pragma unroll
-        for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(twp + (u - 1) * M));
-#pragma unroll
-        for (int u = 0; u < r; ++u) sp[u * M * T] = v[u];
-    };
-    double2 va[r], vb[r];
-    int b = q;
-    if (b < Bn) ld(b, va);
-#pragma unroll 1
-    while (b < Bn) {
-        int bn = b + P::TPL;
-        if (bn < Bn) ld(bn, vb);
-        run(b, va);
-        b = bn;
-        if (b >= Bn) break;
-        bn = b + P::TPL;
-        if (bn < Bn) ld(bn, va);
-        run(b, vb);
-        b = bn;
-    }
-    return;
-#endif
 #pragma unroll 1
     for (int b = q; b < Bn; b += P::TPL) {
         const int blk = b / M, j = b - blk * M;

@@ -251,7 +251,9 @@ template <class P, int s, int NT> MFB_D void z3_dif_mid_pair(double2* l0, const 
 // memory by cp.async: 55 KB instead of 88 KB per CTA at n = 1536 (4 CTAs per SM instead of 2 - the in-pipeline capture
 // profiles/r01_ncu_full_z3_1536_in_pipeline.txt shows barrier stalls of 3.3 per issue with two 256-thread CTAs).
 // (Prefetching the old output rows of an accumulate launch into shared memory with cp.async was measured and dropped:
-// 7.05 vs 6.34 ms at n = 1536, profiles/r01_kbench_z4_3072_and_accbuf.txt - the extra 16 KB per CTA cost more than the tail latency.)
+// 7.05 vs 6.34 ms at n = 1536, profiles/r01_kbench_z4_3072_and_accbuf.txt - the extra 16 KB per CTA cost more than the tail
+// latency.  So was a persistent CTA that stages the NEXT pair's rows under the current pair's stages: 6.42 vs 5.70 ms,
+// profiles/r01_kbench_z_persistent_prefetch_negative.txt.  Resident warps matter more here than hidden HBM latency.)
 template <class P, int RPC, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     z_conv3_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,

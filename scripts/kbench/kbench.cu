@@ -317,21 +317,32 @@ static void sbench2(int which) {
 // "seg": what HBM delivers for the ACCESS PATTERN of a strided pass, without any FFT: a CTA copies one tile =
 // n positions x SEG contiguous complex values (SEG*16 bytes) at a position stride of nz*16 bytes, tiles ordered
 // (a, z-tile) like the pass kernels.  UNR loads per thread are issued before the stores.
-template <int SEG, int UNR>
+// XLIKE: the x-pass layout [position][a][z] (position stride na*nz*16 bytes = 8.4 MB at 1024^3) instead of the y-pass
+// layout [a][position][z] (position stride nz*16 bytes = 8 KB)
+template <int SEG, int UNR, bool XLIKE = false>
 __global__ void __launch_bounds__(256) seg_copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n, int nz, int na) {
     const int tiles_per_a = nz / SEG;
     const int a = blockIdx.x / tiles_per_a, z0 = (blockIdx.x - a * tiles_per_a) * SEG;
     const int lane = threadIdx.x % SEG, q = threadIdx.x / SEG;
     constexpr int PPI = 256 / SEG;   // positions per iteration
-    const double2* ip = in + ptrdiff_t(a) * n * nz + z0 + lane;
-    double2* op = out + ptrdiff_t(a) * n * nz + z0 + lane;
+    const ptrdiff_t ps = XLIKE ? ptrdiff_t(na) * nz : nz, as = XLIKE ? nz : ptrdiff_t(n) * nz;
+    const double2* ip = in + ptrdiff_t(a) * as + z0 + lane;
+    double2* op = out + ptrdiff_t(a) * as + z0 + lane;
     for (int p0 = q; p0 < n; p0 += PPI * UNR) {
         double2 v[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { const int p = p0 + u * PPI; if (p < n) v[u] = mfb_ld_stream(ip + ptrdiff_t(p) * nz); }
+        for (int u = 0; u < UNR; ++u) { const int p = p0 + u * PPI; if (p < n) v[u] = mfb_ld_stream(ip + ptrdiff_t(p) * ps); }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { const int p = p0 + u * PPI; if (p < n) mfb_st_stream(op + ptrdiff_t(p) * nz, v[u]); }
+        for (int u = 0; u < UNR; ++u) { const int p = p0 + u * PPI; if (p < n) mfb_st_stream(op + ptrdiff_t(p) * ps, v[u]); }
     }
+}
+template <int SEG, int UNR> static void segx_one(int n, int nz, int na, const double2* in, double2* out) {
+    const unsigned grid = unsigned(na) * unsigned(nz / SEG);
+    auto launch = [&] { seg_copy_kernel<SEG, UNR, true><<<grid, 256>>>(in, out, n, nz, na); };
+    const float ms = time_kernel(launch);
+    const double gb = 32.0 * double(n) * nz * na / 1e9;
+    printf("x-like seg %4d B x unroll %2d  n=%d nz=%d na=%d  (position stride %.1f MB)  %.3f ms  %8.1f GB/s\n", SEG * 16, UNR, n, nz, na,
+           double(na) * nz * 16 / 1e6, ms, gb / (ms * 1e-3));
 }
 template <int SEG, int UNR> static void seg_one(int n, int nz, int na, const double2* in, double2* out) {
     const unsigned grid = unsigned(na) * unsigned(nz / SEG);
@@ -353,6 +364,17 @@ static void segbench(int n) {
     seg_one<8, 4>(n, nz, na, in, out);  seg_one<8, 16>(n, nz, na, in, out);  seg_one<16, 16>(n, nz, na, in, out);
     seg_one<4, 16>(n, nz, na, in, out); seg_one<32, 16>(n, nz, na, in, out);
     CK(cudaFree(in)); CK(cudaFree(out));
+    {   // the x pass of a 1024^3 product: 1536 positions x 1024 a x 512 z  (12.9 GB each way)
+        const int xn = 1536, xna = 1024;
+        const size_t xe = size_t(xn) * nz * xna;
+        CK(cudaMalloc(&in, xe * 16)); CK(cudaMalloc(&out, xe * 16));
+        fill_kernel<<<1184, 256>>>(in, xe, 1u);
+        CK(cudaDeviceSynchronize());
+        printf("== same test at the full size of one 1024^3 operand (%.2f GB each way): y-like, then x-like layout\n", xe * 16 / 1e9);
+        seg_one<8, 8>(xn, nz, xna, in, out); seg_one<4, 8>(xn, nz, xna, in, out);
+        segx_one<8, 8>(xn, nz, xna, in, out); segx_one<4, 8>(xn, nz, xna, in, out); segx_one<8, 16>(xn, nz, xna, in, out); segx_one<16, 8>(xn, nz, xna, in, out);
+        CK(cudaFree(in)); CK(cudaFree(out));
+    }
 }
 
 int main(int argc, char** argv) {

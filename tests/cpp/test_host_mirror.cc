@@ -5,6 +5,7 @@
 #include <random>
 
 #include "../../include/mfb/convolution.hh"
+#include "../../include/mfb/grid_fft_complex.hh"
 #include "../../include/mfb/particle_generator.hh"
 
 struct mock_config {};
@@ -82,6 +83,47 @@ int main() {
         double diff = 0;
         for (size_t i = 0; i < tmp.ntot_ / 2; ++i) diff = std::max(diff, std::abs(tmp.kelem(i)));
         CHECK(diff > 1e-6 * ref * 0 + 0.0 && diff > 0);
+    }
+    // PPT / Eulerian branch (src/ic_generator.cc:685-803) through the complex-grid mirror.  With a constant phase (phi = const)
+    // and rho = delta: psi = sqrt(1+C delta) * e^{i c}; the drift leaves |psi_k| untouched, so sum(1 + rho_out) == sum(1 + C delta).
+    {
+        Grid_FFT_complex c1(N, L);
+        std::vector<ccomplex_t> z(n * n * n);
+        std::mt19937_64 rng(7);
+        std::normal_distribution<double> nd;
+        for (auto& v : z) v = ccomplex_t(nd(rng), nd(rng));
+        c1.upload(z, rspace_id);
+        c1.FourierTransformForward();
+        CHECK(c1.space() == kspace_id);
+        auto Z = c1.download();
+        double e1 = 0, e2 = 0;
+        for (size_t i = 0; i < z.size(); ++i) { e1 += std::norm(z[i]); e2 += std::norm(Z[i]); }
+        CHECK(std::fabs(e1 - e2) < 1e-11 * e1);                      // Parseval, symmetric norm, c2c
+        c1.FourierTransformBackward();
+        auto z2 = c1.download();
+        double md = 0;
+        for (size_t i = 0; i < z.size(); ++i) md = std::max(md, std::abs(z[i] - z2[i]));
+        CHECK(md < 1e-12);
+        Grid_FFT<real_t> rho(N, L), ph(N, L), t2(N, L);
+        Fill_Grid(rho, 5);
+        rho *= 0.05;
+        Fill_Grid(ph, 6);
+        ph *= 1e-3;
+        double mass_in = 0;
+        const double Csp = 0.8;
+        rho.FourierTransformForward();
+        rho.zero_DC_mode();
+        rho.FourierTransformBackward();
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) mass_in += 1.0 + Csp * rho.relem(i, j, k);
+        rho.FourierTransformForward();
+        int nwritten = 0;
+        double mass_out = 0;
+        const real_t hbar = ppt::run(rho, ph, nullptr, t2, 1, 0.0257, 396.69, 100.0, Csp, 1.0, [&](Grid_FFT<real_t>& g, int comp) {
+            ++nwritten;
+            if (comp == 0) for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) mass_out += 1.0 + g.relem(i, j, k);
+        });
+        CHECK(nwritten == 4 && hbar > 0);
+        CHECK(std::fabs(mass_out - mass_in) < 1e-10 * mass_in);      // the drift is unitary: total mass is conserved
     }
     // particles: ids of a bcc load (include/particle_generator.hh:150-169)
     mock_config cf;

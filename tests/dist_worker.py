@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--staged", action="store_true")
     ap.add_argument("--grid", type=int, default=32)
     ap.add_argument("--lattice", default="bcc")
+    ap.add_argument("--borrow", action="store_true",
+                    help="no own accumulator (as under memory pressure at 2048^3 / 8 GPUs): it is borrowed from the particle arrays")
     args = ap.parse_args()
 
     import torch
@@ -47,6 +49,8 @@ def main():
         MD.init(local_rank, args.grid, True, staged=args.staged)
     lib = M.grid._lib()
     assert lib.mfb_dist_nranks() == world and lib.mfb_dist_rank() == rank
+    if args.borrow:
+        assert lib.mfb_set_option(b"conv_own_accumulator", 0) == 0
 
     n, L, TOL = args.grid, 100.0, PC.TOL
     N3, L3 = (n,) * 3, (L,) * 3
@@ -113,6 +117,10 @@ def main():
         cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad=lattice, Dplus0=Dp, vfac=vfac,
                            lunit=lunit, vunit=vunit, real64=real64, ids64=True)
         pl = M.LPTPipeline(cfg)
+        if args.borrow and order > 1:
+            assert not pl.conv.grouped()
+            pl.make_particles()
+            assert pl.conv.grouped()      # the slab's particle arrays now serve as the product-group accumulator
         pl.set_noise_k(W)
         pl.condition_noise()
         parts = pl.run_device(O.radial_table(g, amp), particles=True)

@@ -35,3 +35,12 @@ def test_slab_pipeline_gloo(world, lattice):
 
     emu_util.build_emu()
     run_world(world, ["--emu", "--grid", "32", "--lattice", lattice])
+
+
+def test_slab_pipeline_gloo_borrowed_accumulator():
+    """the memory-pressure configuration of 3LPT 2048^3 on 8 GPUs, on two CPU ranks: product groups accumulate in the
+    (idle) particle arrays of each slab"""
+    import emu_util
+
+    emu_util.build_emu()
+    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--borrow"])

@@ -25,3 +25,9 @@ def test_slab_pipeline_nccl_staged():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     run_world(2, ["--grid", "64", "--lattice", "sc", "--staged"])
+
+
+def test_slab_pipeline_borrowed_accumulator():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, ["--grid", "64", "--lattice", "sc", "--borrow"])

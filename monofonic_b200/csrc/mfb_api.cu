@@ -46,6 +46,24 @@ namespace mfb {
     X(2048, 64, 4, 16, 16, 8)     \
     X(3072, 64, 4, 16, 16, 12)
 
+// contiguous-axis (z) passes of N-grids: rows are contiguous in HBM whatever the tile height, so the long lines use narrow
+// tiles (T = 4 / 2 lines, half / quarter of the shared memory of the strided plans) and 2-3 CTAs share an SM instead of one
+#define MFB_FOR_EACH_PLAN_ZROW(X) \
+    X(32, 4, 16, 8, 4)            \
+    X(48, 2, 16, 8, 6)            \
+    X(64, 8, 16, 8, 8)            \
+    X(96, 4, 16, 12, 8)           \
+    X(128, 8, 16, 16, 8)          \
+    X(192, 4, 16, 16, 12)         \
+    X(256, 16, 8, 16, 16)         \
+    X(384, 16, 8, 8, 8, 6)        \
+    X(512, 32, 8, 8, 8, 8)        \
+    X(768, 32, 4, 12, 8, 8)       \
+    X(1024, 64, 4, 16, 8, 8)      \
+    X(1536, 32, 4, 16, 12, 8)     \
+    X(2048, 128, 2, 16, 16, 8)    \
+    X(3072, 64, 2, 16, 16, 12)
+
 Context g_ctx;
 thread_local std::string g_err;
 }  // namespace mfb
@@ -403,7 +421,7 @@ void launch_z(int n, int kind, double* data, ptrdiff_t pitch, long nrows, double
         launch_z_t<P>(kind, data, pitch, nrows, scale);       \
         break;                                                \
     }
-        MFB_FOR_EACH_PLAN(X)
+        MFB_FOR_EACH_PLAN_ZROW(X)
 #undef X
         default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
     }
@@ -421,7 +439,7 @@ void launch_zc2c(int n, double2* data, long nrows, double scale, int inverse) {
     switch (n) {
 #define X(N_, TPL_, T_, ...)                                                     \
     case N_: launch_zc2c_t<Plan<N_, TPL_, T_, __VA_ARGS__>>(data, nrows, scale, inverse); break;
-        MFB_FOR_EACH_PLAN(X)
+        MFB_FOR_EACH_PLAN_ZROW(X)
 #undef X
         default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
     }

@@ -382,6 +382,26 @@ int main(int argc, char** argv) {
     const char* what = argc > 2 ? argv[2] : "all";
     if (!strcmp(what, "seg")) { segbench(which ? which : 1536); return 0; }
     if (!strcmp(what, "z4")) { zbench4(which); return 0; }
+    if (!strcmp(what, "t2")) {   // narrow tiles for the y-like passes: 2-line tiles (32-byte segments), 4 CTAs per SM
+        for (int mode : {SM_PAD, SM_TRUNC}) {
+            Bench B = make_bench(1536, mode, 384);
+            run_v1<Plan<1536, 32, 8, 16, 12, 8>>(B, "v1 <1536,32,8,16,12,8>", true);
+            V2(SM_PAD, 1, 1536, 64, 8, 12, 16, 8); V2(SM_PAD, 2, 1536, 64, 4, 12, 16, 8);
+            V2(SM_PAD, 4, 1536, 64, 2, 12, 16, 8); V2(SM_PAD, 4, 1536, 32, 2, 12, 16, 8); V2(SM_PAD, 3, 1536, 64, 2, 12, 16, 8); V2(SM_PAD, 4, 1536, 128, 2, 12, 16, 8);
+            V2(SM_PAD, 3, 1536, 32, 4, 12, 16, 8);
+            V2(SM_TRUNC, 2, 1536, 64, 4, 8, 16, 12);
+            V2(SM_TRUNC, 4, 1536, 64, 2, 8, 16, 12); V2(SM_TRUNC, 4, 1536, 32, 2, 8, 16, 12); V2(SM_TRUNC, 3, 1536, 64, 2, 8, 16, 12); V2(SM_TRUNC, 4, 1536, 128, 2, 8, 16, 12);
+            free_bench(B);
+        }
+        for (int mode : {SM_PAD, SM_TRUNC}) {
+            Bench B = make_bench(768, mode, 768);
+            run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 <768,32,8,12,8,8>", true);
+            V2(SM_PAD, 2, 768, 32, 8, 12, 8, 8); V2(SM_PAD, 4, 768, 32, 4, 12, 8, 8); V2(SM_PAD, 8, 768, 32, 2, 12, 8, 8); V2(SM_PAD, 6, 768, 64, 2, 12, 8, 8);
+            V2(SM_TRUNC, 2, 768, 32, 8, 8, 8, 12); V2(SM_TRUNC, 4, 768, 32, 4, 8, 8, 12); V2(SM_TRUNC, 8, 768, 32, 2, 8, 8, 12); V2(SM_TRUNC, 6, 768, 64, 2, 8, 8, 12);
+            free_bench(B);
+        }
+        return 0;
+    }
     if (!strcmp(what, "s3")) {
         if (which == 0 || which == 768) for (int mode : {SM_PAD, SM_TRUNC}) {
             Bench B = make_bench(768, mode, 768);

@@ -29,7 +29,8 @@ def test_fft_every_plan(M, shape):
     PC.check_fft(M, *shape)
 
 
-@pytest.mark.parametrize("shape", [(32, 64, 128), (256, 32, 32), (32, 32, 512), (32, 32, 1024), (32, 32, 2048)])
+@pytest.mark.parametrize("shape", [(32, 64, 128), (256, 32, 32), (32, 32, 512), (32, 32, 1024), (32, 32, 2048), (1024, 32, 32),
+                                   (32, 1024, 32), (2048, 32, 32), (32, 2048, 32), (512, 32, 32), (32, 512, 32)])
 def test_multiply_noncubic_every_conv_plan(M, shape):
     PC.check_multiply_noncubic(M, shape)
 

@@ -123,6 +123,15 @@ def test_fft_roundtrip_and_parseval_large(M, n):
     assert np.abs(G.get_real() - x).max() < 1e-12 * np.abs(x).max()
 
 
+@pytest.mark.parametrize("shape", [(1024, 32, 32), (32, 1024, 32), (32, 32, 1024), (2048, 32, 32), (32, 2048, 32), (512, 64, 32),
+                                   (1024, 128, 512)])
+def test_dealiased_product_every_long_plan(M, shape):
+    """every pad / truncate / fused-z plan of the BASELINE sizes (1024 -> 1536, 2048 -> 3072 points per line) on slim grids,
+    against a direct numpy statement of the dealiased product; the last shape has the megabyte position stride of a real
+    x pass, which selects the 8-line plans"""
+    PC.check_multiply_noncubic(M, shape)
+
+
 def test_complex_grid_fft_large_noncubic(M):
     """Grid_FFT<ccomplex_t> at 384 x 256 x 512 (three different plans, 0.8 GB): c2c forward against numpy, Parseval,
     round trip"""

@@ -368,15 +368,6 @@ static bool launch_strided2(int n, const StridedArgs& a, int role) {
             default: return false;
         }
     }
-    {   // n = 1536, y-like strides: two 4-line tiles per SM beat one 8-line tile (kbench t2, na = 384: 3752 vs 3531 GB/s);
-        // passes along x keep 128-byte segments (see far_stride above)
-        const bool far_stride = a.in_ps * ptrdiff_t(sizeof(double2)) >= (1 << 20) || a.out_ps * ptrdiff_t(sizeof(double2)) >= (1 << 20);
-        if (n == 1536 && !far_stride && a.out_blk == 0) {
-            if (mode == SM_PAD) launch_strided2_t<Plan<1536, 64, 4, 12, 16, 8>, SM_PAD, 2>(a, role);
-            else launch_strided2_t<Plan<1536, 64, 4, 12, 16, 8>, SM_PLAIN, 2>(a, role);
-            return true;
-        }
-    }
     switch (n) {
 #define X(N_, TPL_, T_, MINB_, ...)                                                  \
     case N_:                                                                         \

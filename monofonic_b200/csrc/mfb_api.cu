@@ -961,7 +961,7 @@ void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2
     auto HS = [](mfb_grid* g, int a, int b, int cc, int d, double sgn) { return Operand{g, a, b, cc, d, -1.0, -sgn, 0}; };
     const bool grouped = can_group(c);
     // The product ORDER inside a group (and of the groups) is free; it is chosen so that consecutive products share an
-    // operand, which then stays in its buffer (cache_on): 50 operand transforms instead of 64 at 3LPT.
+    // operand, which then stays in its buffer (cache_on): 49 operand transforms instead of 64 at 3LPT.
     conv_cache_clear(c);
     c->cache_on = grouped;
     if (order > 1 && grouped) {

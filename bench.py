@@ -27,9 +27,23 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+sys.path[:0] = [ROOT]
 
 import numpy as np  # noqa: E402
+
+
+def synthetic_amplitude(ns=0.9649, kcut=0.5):
+    """synthetic stand-in for k^{ns/2} T(k) sqrt(pnorm) (BBKS-like roll-off): what the transfer-function plugin would be
+    tabulated into.  Its values do not influence the timing."""
+
+    def amp(k):
+        k = np.asarray(k, dtype=np.float64)
+        q = k / kcut
+        T = np.log1p(2.34 * q) / np.where(q > 0, 2.34 * q, 1.0) * (
+            1 + 3.89 * q + (16.1 * q) ** 2 + (5.46 * q) ** 3 + (6.71 * q) ** 4) ** -0.25
+        return np.power(k, 0.5 * ns) * np.where(q > 0, T, 1.0)
+
+    return amp
 
 
 def parse():
@@ -111,9 +125,11 @@ def workload_name(n, order, lattice="sc"):
 
 # --------------------------------------------------------------------------------------------
 def cpu_reference_run(n, order, threads, steps=1, warmup=0):
-    """the oracle port of the reference pipeline on the host cores (MKL FFT through torch)"""
+    """the oracle port of the reference pipeline on the host cores (MKL FFT through torch).  The ONLY place where bench.py
+    touches oracle/: the cpu_baseline leg and the --impl reference arm."""
     import torch
 
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lpt_oracle as O
 
     torch.set_num_threads(threads)
@@ -155,7 +171,6 @@ def run_reference(args):
 def run_b200(args):
     import torch
 
-    import lpt_oracle as O  # only for synthetic input generation + the cpu_baseline leg
     import monofonic_b200 as M
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,8 +207,7 @@ def run_b200(args):
                        lunit=Lbox, vunit=Lbox / np.sqrt(1 / 51.0), real64=False, ids64=ids64)
     pl = M.LPTPipeline(cfg)
     pl.make_particles()
-    amp = O.power_law_amplitude()
-    table = M.pipeline.radial_table(n, Lbox, amp)
+    table = M.pipeline.radial_table(n, Lbox, synthetic_amplitude())
 
     # synthetic white noise: real-space Gaussian field generated on the host (one seed per x-plane, so the global
     # field does not depend on the number of GPUs), transformed on the device.  Each rank holds its slab.

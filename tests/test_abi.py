@@ -56,3 +56,19 @@ def test_product_never_imports_oracle_or_emulator():
             if f.endswith((".py", ".cu", ".cuh", ".h")) and f != "mfb_platform.h":
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "lpt_oracle" not in txt and "libmfb_emu" not in txt, f
+
+
+def test_bench_touches_the_oracle_only_in_its_cpu_legs():
+    """bench.py may execute oracle/ only as the cpu_baseline / --impl reference checker, never in the measured arm"""
+    import ast
+
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    users = set()
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        seg = ast.get_source_segment(src, fn)
+        if "lpt_oracle" in seg or '"oracle"' in seg:
+            users.add(fn.name)
+    assert users == {"cpu_reference_run"}, users
+    top = "\n".join(ast.get_source_segment(src, n) or "" for n in tree.body if not isinstance(n, ast.FunctionDef))
+    assert "lpt_oracle" not in top and '"oracle"' not in top

@@ -1,4 +1,4 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-echo "== bench (default flags)"; timeout 600 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_default.log | cut -c1-300
+timeout 100 python -m pytest tests/test_cpp_driver.py tests/test_cpp_mirror.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/gpu_tests_cpp.log

@@ -224,6 +224,60 @@ def check_naive_pipeline(M, n=32):
         assert relerr(pl.A3[d].get_kspace(), ref["A3"][d]) < 10 * TOL
 
 
+# ------------------------------------------------------------------ two-fluid terms, tides, density, masses
+def check_two_fluid_terms(M, n=32, lattice="bcc"):
+    """the operators a CDM+baryon run adds (config C4) with NON-degenerate two-fluid amplitudes (the goldens use
+    Eisenstein&Hu, where delta_bc == 0): external tides in the 2LPT source (:488-497), the relative-velocity term of the
+    velocity assembly (:918-921), the mass field (1 + C rho) Omega munit (:663-675) read out as particle masses on the
+    secondary lattice (:292-350), and the SPT density delta = k^2 phi (:962-973)"""
+    import ctypes as C
+
+    L, Dp, vfac = 100.0, 0.0257, 396.69
+    lam = (0.12, -0.07, -0.05)
+    g, W, Wc, phi = noise_and_phi(n, L, 41)
+    amp = O.power_law_amplitude()
+    amp_theta = lambda k: 0.37 * amp(k) / (1.0 + k)           # stand-ins for get_amplitude_theta_bc / _delta_bc
+    amp_delta = lambda k: 2e-3 * amp(k) * k * k
+    Csp, Omega, munit, vunit = -0.1567, 0.3, 2.5, L / np.sqrt(1 / 51.0)
+    pots = O.lpt_potentials(g, phi, 2, Dp, tides=lam)
+    lt = O.LATTICE_TYPES[lattice]
+    cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=2, ParticleLoad=lattice, Dplus0=Dp, vfac=vfac, lunit=L, vunit=vunit,
+                       tides=lam)
+    pl = M.LPTPipeline(cfg)
+    pl.set_noise_k(W)
+    pl.condition_noise()
+    pl.compute_phi1(O.radial_table(g, amp))
+    pl.compute_sources()
+    assert relerr(pl.phi2.get_kspace(), pots["phi2"]) < TOL
+    # velocities with the baryon-CDM relative velocity term
+    vtab = O.radial_table(g, amp_theta)
+    for d in range(3):
+        ref = g.bwd(O.velocity_k(g, pots, 2, d, vfac, vunit / L, vbc=(Csp, amp_theta, Wc)))
+        got = pl.velocity_field(d, vbc=(vtab, vfac * Csp)).get_real()
+        assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max(), d
+    # SPT density
+    ref = g.bwd(O.density_k(g, pots))
+    assert np.abs(pl.density_field().get_real() - ref).max() < 1e-11 * np.abs(ref).max()
+    # mass field -> particle masses on the secondary lattice
+    rho_k = O.zero_dc(Wc * np.where(np.isfinite(amp_delta(np.sqrt(g.k2()))), amp_delta(np.sqrt(g.k2())), 0.0))
+    rho_r = g.bwd(rho_k)
+    mass_field = (1.0 + Csp * rho_r) * Omega * munit
+    rho = M.Grid_FFT((n,) * 3, (L,) * 3)
+    dtab = O.radial_table(g, amp_delta)
+    lib = M.grid._lib()
+    assert lib.mfb_apply_radial_table(rho._h, pl.wnoise._h, dtab.ctypes.data_as(C.c_void_p), dtab.size, 0) == 0
+    rho.zero_DC_mode()
+    rho.FourierTransformBackward()
+    rho.affine(Omega * munit, Csp * Omega * munit)
+    assert np.abs(rho.get_real() - mass_field).max() < 1e-12 * np.abs(mass_field).max()
+    parts = M.Particles(lattice, 1, True, True, True, 1, rho)
+    parts.set_masses(1.0, rho)
+    got = parts.download(pos=False, vel=False)
+    ref_m = O.set_masses(g, mass_field, lt, 1, 1.0, True)
+    assert np.abs(got["mass"] - ref_m).max() < 1e-12 * np.abs(ref_m).max()
+    assert np.array_equal(got["ids"], O.particle_ids(n, lt, 1, True))
+
+
 # ------------------------------------------------------------------ complex grids + PPT / Eulerian branch
 def check_cfft(M, n0, n1=None, n2=None):
     """Grid_FFT<ccomplex_t>: c2c forward/backward with the symmetric norm vs numpy"""

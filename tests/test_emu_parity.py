@@ -111,3 +111,7 @@ def test_naive_pipeline(M):
 
 def test_product_grouping(M):
     PC.check_product_grouping(M, 32)
+
+
+def test_two_fluid_terms(M):
+    PC.check_two_fluid_terms(M, 32, "bcc")

@@ -68,6 +68,11 @@ def test_product_grouping(M, n):
     PC.check_product_grouping(M, n)
 
 
+@pytest.mark.parametrize("n,lattice", [(32, "bcc"), (64, "sc")])
+def test_two_fluid_terms(M, n, lattice):
+    PC.check_two_fluid_terms(M, n, lattice)
+
+
 def test_naive_pipeline(M):
     PC.check_naive_pipeline(M, 64)
 

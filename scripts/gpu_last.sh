@@ -1,4 +1,3 @@
 #!/bin/bash
-set -u
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_cpp_driver.py tests/test_cpp_mirror.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/gpu_tests_cpp.log
+timeout 60 python -m pytest tests/test_gpu_parity.py -x -q -k two_fluid 2>&1 | tail -3 | tee gpurun_out/gpu_tests_two_fluid.log

@@ -1784,6 +1784,7 @@ int mfb_conv_create_naive(mfb_conv** out, const int n[3], const double L[3]) {
 int mfb_conv_destroy(mfb_conv* c) {
     MFB_TRY
     if (c) {
+        if (c->acc_borrowed && c->lender) c->lender->borrower = nullptr;
         if (c->W1) cudaFree(c->W1);
         if (c->W2a) cudaFree(c->W2a);
         if (c->W2b) cudaFree(c->W2b);
@@ -1804,14 +1805,19 @@ int mfb_conv_borrow_accumulator(mfb_conv* c, mfb_particles* p) {
     MFB_TRY
     require(!c->naive, "the NaiveConvolver has no accumulator");
     if (p == nullptr) {   // give it back
-        if (c->acc_borrowed) { c->Wacc = nullptr; c->acc_borrowed = false; c->lender = nullptr; }
+        if (c->acc_borrowed) {
+            if (c->lender) c->lender->borrower = nullptr;
+            c->Wacc = nullptr; c->acc_borrowed = false; c->lender = nullptr;
+        }
         return 0;
     }
     if (c->Wacc != nullptr) return 0;   // already has one (its own, or borrowed)
     require(p->posvel_bytes >= c->w2_elems * sizeof(double2), "particle arrays are too small to serve as the accumulator");
+    require(p->borrower == nullptr, "these particle arrays are already lent to another convolver");
     c->Wacc = (double2*)p->pos;
     c->acc_borrowed = true;
     c->lender = p;
+    p->borrower = c;
     MFB_CATCH
 }
 static void check_conv_grids(mfb_conv* c, mfb_grid* a, mfb_grid* b, mfb_grid* o) {
@@ -1905,6 +1911,10 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
 int mfb_particles_destroy(mfb_particles* p) {
     MFB_TRY
     if (p) {
+        if (p->borrower) {   // the loan ends with the lender: the convolver falls back to ungrouped products
+            cudaStreamSynchronize(g_ctx.stream);
+            p->borrower->Wacc = nullptr; p->borrower->acc_borrowed = false; p->borrower->lender = nullptr;
+        }
         if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
         for (int a = 0; a < 4; ++a) if (p->copied[a]) cudaEventDestroy(p->copied[a]);
         cudaFree(p->pos); cudaFree(p->ids);

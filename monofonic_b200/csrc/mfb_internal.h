@@ -61,6 +61,7 @@ struct mfb_particles {
     int nloc0, off0;  // slab of lattice planes held by this rank
     void *pos, *vel, *ids, *mass;  // device AoS (particle_container.hh:82-108); pos and vel are one allocation (vel = pos + 3 np)
     size_t posvel_bytes;
+    struct mfb_conv* borrower = nullptr;  // convolver that currently uses pos/vel as its accumulator (loan ends with either side)
     // streamed hand-off: per attribute, event recorded on the copy stream after its D2H copy (null: none pending)
     cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr};
     bool copy_pending[4] = {false, false, false, false};

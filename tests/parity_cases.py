@@ -600,6 +600,14 @@ def check_product_grouping(M, n=32):
         l0 = M.kernel_launches()
         got = [pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3]
         assert np.array_equal(out["pos"], pl.particles.download()["pos"])
+        # the loan ends with the lender: destroying the particles leaves a convolver that still works, ungrouped
+        pl.particles = None
+        assert not pl.conv.grouped()
+        pl.set_noise_k(W)
+        pl.condition_noise()
+        pl.compute_phi1(O.radial_table(g, amp))
+        pl.compute_sources()
+        assert relerr(pl.phi3.get_kspace(), got[1]) < 1e-13
     finally:
         lib.mfb_set_option(b"conv_own_accumulator", 1)
     for a, b in zip(got, res[1][0]):

@@ -254,7 +254,11 @@ template <class P, int s, int NT> MFB_D void z3_dif_mid_pair(double2* l0, const 
 // 7.05 vs 6.34 ms at n = 1536, profiles/r01_kbench_z4_3072_and_accbuf.txt - the extra 16 KB per CTA cost more than the tail
 // latency.  So was a persistent CTA that stages the NEXT pair's rows under the current pair's stages: 6.42 vs 5.70 ms,
 // profiles/r01_kbench_z_persistent_prefetch_negative.txt.  Resident warps matter more here than hidden HBM latency.)
-template <class P, int RPC, int MINB, bool DIRECT = false>
+// EARLY_ACC: how an accumulate launch reads the old sum rows.  0: inside the final loop, one element at a time - every
+// iteration then waits a full HBM round trip (the SASS view of the in-pipeline capture attributes 32 % of all stall samples
+// to the two DADDs behind those loads, profiles/r01_ncu_z3_1536_sass_mix.txt); 1: all of a thread's loads are issued back to
+// back after the last barrier; 2: they are issued before the outermost forward stage and consumed after it.
+template <class P, int RPC, int MINB, bool DIRECT = false, int EARLY_ACC = 2>
 __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     z_conv3_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
                    ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw, int accumulate = 0) {
@@ -374,6 +378,22 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
         }
     }
     z2_dit_mid<P, S - 2, PT>(l0, tw, q);
+    constexpr int TOTAL = (RPC / 2) * NZ, PERT = (TOTAL + NT - 1) / NT;   // output pairs per CTA / per thread
+    double2 o1[PERT], o2[PERT];
+    auto fetch_old = [&]() {
+#pragma unroll
+        for (int u = 0; u < PERT; ++u) {
+            const int idx = tid + u * NT;
+            o1[u] = o2[u] = make_double2(0.0, 0.0);
+            if (idx < TOTAL) {
+                const int mm = idx / NZ, k = idx - mm * NZ;
+                const long r1 = row0 + 2 * mm, r2 = r1 + 1;
+                if (r1 < nrows) o1[u] = mfb_ld_stream(out + r1 * out_pitch + k);
+                if (r2 < nrows) o2[u] = mfb_ld_stream(out + r2 * out_pitch + k);
+            }
+        }
+    };
+    if (EARLY_ACC == 2 && accumulate) fetch_old();
     __syncthreads();
     {
         constexpr int r = P::radix(0), M = N / r;
@@ -391,9 +411,13 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
         }
     }
     __syncthreads();
+    if (EARLY_ACC == 1 && accumulate) fetch_old();
     {
         const double h = 0.5 * scale;
-        for (int idx = tid; idx < (RPC / 2) * NZ; idx += NT) {
+#pragma unroll
+        for (int u = 0; u < PERT; ++u) {
+            const int idx = tid + u * NT;
+            if (idx >= TOTAL) break;
             const int mm = idx / NZ, k = idx - mm * NZ;
             const double2* lz = work + (2 * mm) * LW;
             const double2 zk = lz[zpad(k)];
@@ -402,8 +426,12 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
             double2 v1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
             double2 v2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
             if (accumulate) {   // sum of products of one target, formed before the (single) forward y/x passes
-                if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
-                if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
+                if constexpr (EARLY_ACC != 0) {
+                    v1.x += o1[u].x; v1.y += o1[u].y; v2.x += o2[u].x; v2.y += o2[u].y;
+                } else {
+                    if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
+                    if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
+                }
             }
             if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, v1);
             if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, v2);

@@ -241,6 +241,46 @@ template <class P, int RPC, int MINB> static void zrun_v3d(ZBench& Z, const char
     cudaFree(tw2);
 }
 #define Z3D(RPC, MINB, ...) zrun_v3d<Plan<__VA_ARGS__>, RPC, MINB>(Z, "z3 direct <" #__VA_ARGS__ "> rpc " #RPC " minb " #MINB)
+// accumulate launches (product groups): how the old sum rows are read (z_conv3_kernel EARLY_ACC 0 / 1 / 2)
+template <class P, int RPC, int MINB, int EARLY> static void zrun_acc(ZBench& Z, const char* label) {
+    auto k = z_conv3_kernel<P, RPC, MINB, true, EARLY>;
+    double2* tw2 = make_tw2<P>();
+    constexpr size_t smem = z_conv3_direct_smem<P, RPC>();
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::TPL * RPC, smem));
+    const unsigned grid = unsigned((Z.nrows + RPC - 1) / RPC);
+    const size_t e = size_t(Z.nrows) * Z.nz;
+    CK(cudaMemset(Z.out, 0, e * 16));
+    k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, tw2, 1);   // 0 + product == product, bit for bit
+    double md = 0;
+    CK(cudaMemset(Z.dmax, 0, 8)); maxdiff_kernel<<<1184, 256>>>(Z.out, Z.ref, e, Z.dmax); CK(cudaMemcpy(&md, Z.dmax, 8, cudaMemcpyDeviceToHost));
+    float ms = time_kernel([&] { k<<<grid, P::TPL * RPC, smem>>>(Z.A, Z.B, Z.out, Z.nz, Z.nz, Z.nrows, 0.37, tw2, 1); });
+    printf("%-58s %8.3f ms %8.1f GB/s  regs %3d  CTA/SM %d  maxdiff(0+product vs product) %.2e\n", label, ms, 4.0 * e * 16 / ms / 1e6, fa.numRegs, occ, md);
+    fflush(stdout);
+    cudaFree(tw2);
+}
+#define ZACC(EARLY, RPC, MINB, ...) zrun_acc<Plan<__VA_ARGS__>, RPC, MINB, EARLY>(Z, "z3 direct accumulate early=" #EARLY " <" #__VA_ARGS__ "> minb " #MINB)
+static void zbench_acc() {
+    {
+        ZBench Z = make_zbench(1536, 1536L * 192);
+        zrun_v3d<Plan<1536, 64, 2, 12, 16, 8>, 2, 3>(Z, "z3 direct (no accumulate) <1536,64,2,12,16,8> minb 3");
+        CK(cudaMemcpy(Z.ref, Z.out, size_t(Z.nrows) * Z.nz * 16, cudaMemcpyDeviceToDevice));
+        ZACC(0, 2, 3, 1536, 64, 2, 12, 16, 8); ZACC(1, 2, 3, 1536, 64, 2, 12, 16, 8); ZACC(2, 2, 3, 1536, 64, 2, 12, 16, 8);
+    }
+    {
+        ZBench Z = make_zbench(768, 768L * 384);
+        zrun_v3d<Plan<768, 64, 2, 12, 8, 8>, 2, 5>(Z, "z3 direct (no accumulate) <768,64,2,12,8,8> minb 5");
+        CK(cudaMemcpy(Z.ref, Z.out, size_t(Z.nrows) * Z.nz * 16, cudaMemcpyDeviceToDevice));
+        ZACC(0, 2, 5, 768, 64, 2, 12, 8, 8); ZACC(1, 2, 5, 768, 64, 2, 12, 8, 8); ZACC(2, 2, 5, 768, 64, 2, 12, 8, 8);
+    }
+    {
+        ZBench Z = make_zbench(3072, 3072L * 48);
+        zrun_v3d<Plan<3072, 128, 2, 12, 16, 16>, 2, 2>(Z, "z3 direct (no accumulate) <3072,128,2,12,16,16> minb 2");
+        CK(cudaMemcpy(Z.ref, Z.out, size_t(Z.nrows) * Z.nz * 16, cudaMemcpyDeviceToDevice));
+        ZACC(0, 2, 2, 3072, 128, 2, 12, 16, 16); ZACC(2, 2, 2, 3072, 128, 2, 12, 16, 16);
+    }
+}
 static void zbench4(int which) {
     if (which == 0 || which == 768) {
         ZBench Z = make_zbench(768, 768L * 768);
@@ -382,6 +422,7 @@ int main(int argc, char** argv) {
     const char* what = argc > 2 ? argv[2] : "all";
     if (!strcmp(what, "seg")) { segbench(which ? which : 1536); return 0; }
     if (!strcmp(what, "z4")) { zbench4(which); return 0; }
+    if (!strcmp(what, "zacc")) { zbench_acc(); return 0; }
     if (!strcmp(what, "t2")) {   // narrow tiles for the y-like passes: 2-line tiles (32-byte segments), 4 CTAs per SM
         for (int mode : {SM_PAD, SM_TRUNC}) {
             Bench B = make_bench(1536, mode, 384);

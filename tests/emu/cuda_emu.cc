@@ -20,7 +20,6 @@ struct Worker {
     std::vector<char> done;
     const std::function<void()>* body = nullptr;
     int cur = 0;
-    struct NamedBar { int arrived = 0; unsigned gen = 0; } bars[16];   // PTX named barriers 0..15 of the running block
 };
 thread_local Worker* t_worker = nullptr;
 
@@ -39,7 +38,6 @@ void run_block(Worker& w, dim3 block, const std::function<void()>& body) {
     }
     w.done.assign(nthr, 0);
     w.body = &body;
-    for (auto& b : w.bars) b = Worker::NamedBar();
     for (unsigned t = 0; t < nthr; ++t) {
         getcontext(&w.ctx[t]);
         w.ctx[t].uc_stack.ss_sp = w.stacks[t].get();
@@ -65,21 +63,6 @@ void run_block(Worker& w, dim3 block, const std::function<void()>& body) {
 void sync_threads() {
     Worker* w = t_worker;
     swapcontext(&w->ctx[w->cur], &w->main_ctx);
-}
-
-// bar.arrive / bar.sync with an explicit thread count: the last arrival opens the barrier, waiting fibers yield to the
-// scheduler until the generation changes.  (Do not mix with __syncthreads() between the same two points of a kernel:
-// that one counts scheduler rounds.)
-void bar_arrive(int id, int count) {
-    auto& b = t_worker->bars[id & 15];
-    if (++b.arrived == count) { b.arrived = 0; ++b.gen; }
-}
-void bar_sync(int id, int count) {
-    Worker* w = t_worker;
-    auto& b = w->bars[id & 15];
-    const unsigned g = b.gen;
-    if (++b.arrived == count) { b.arrived = 0; ++b.gen; return; }
-    while (b.gen == g) swapcontext(&w->ctx[w->cur], &w->main_ctx);
 }
 
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {

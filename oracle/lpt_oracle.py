@@ -5,10 +5,16 @@ named in BASELINE.json.  It is the *checker* used by tests/, __graft_entry__.smo
 bench.py's cpu_baseline / --impl reference legs.  The product path (monofonic_b200/) never
 imports it; if the CUDA library is missing the product fails loudly instead.
 
-Parity status: PINNED.  tests/test_oracle_golden.py checks this module against all five
-golden regression files of the reference (tests/references/*.hdf5, converted to
-tests/golden/*.npz by tests/golden/make_golden.py) at the reference's own tolerance
-np.allclose(rtol=1e-9, atol=1e-14) (tests/scripts/compare_hdf5.py:66-75).
+Parity status: PINNED, twice.
+  (1) tests/test_oracle_golden.py checks this module against all five golden regression files of the
+      reference (tests/references/*.hdf5, converted to tests/golden/*.npz by tests/golden/make_golden.py) at
+      the reference's own tolerance np.allclose(rtol=1e-9, atol=1e-14) (tests/scripts/compare_hdf5.py:66-75):
+      end results (displacements, velocities, densities, masses, IDs).
+  (2) tests/test_oracle_vs_reference.py checks it against the reference's OWN Grid_FFT / OrszagConvolver / op::
+      sources, compiled where they lie (oracle/Makefile -> oracle/_ref/ref_driver; FFTW3 replaced by the exact-DFT
+      shim of oracle/refshim/) and run in the build container: every named product with every output operator,
+      the phi2 / phi3 / A3 source stage, Poisson solve, shift_field, FourierInterpolateCopyTo - agreement
+      1e-15..2e-14.  Its output is committed as tests/golden/ref_intermediates_32.npz for the GPU box.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 

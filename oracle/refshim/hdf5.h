@@ -1,0 +1,33 @@
+// oracle/refshim/hdf5.h - TEST INFRASTRUCTURE.  src/grid_fft.cc of the reference includes <hdf5.h> unconditionally for its
+// diagnostic dump routines (Write_to_HDF5 & co, :495-1047).  The parity driver never calls them; these inert declarations
+// only let that translation unit compile in a container without HDF5.  Every function reports failure.
+#pragma once
+#include <cstddef>
+typedef long hid_t;
+typedef int herr_t;
+typedef int htri_t;
+typedef unsigned long long hsize_t;
+typedef herr_t (*H5E_auto_t)(void*);
+enum { H5P_DEFAULT = 0, H5S_ALL = 0, H5S_SELECT_SET = 0, H5F_ACC_RDONLY = 0, H5F_ACC_RDWR = 1, H5F_ACC_TRUNC = 2,
+       H5P_DATASET_XFER = 1, H5P_FILE_ACCESS = 2, H5FD_MPIO_COLLECTIVE = 1 };
+enum { H5T_NATIVE_FLOAT = 1, H5T_NATIVE_DOUBLE, H5T_NATIVE_LDOUBLE, H5T_NATIVE_INT, H5T_NATIVE_UINT, H5T_NATIVE_LLONG,
+       H5T_NATIVE_ULLONG };
+inline hid_t H5Fcreate(const char*, unsigned, hid_t, hid_t) { return -1; }
+inline hid_t H5Fopen(const char*, unsigned, hid_t) { return -1; }
+inline herr_t H5Fclose(hid_t) { return -1; }
+inline hid_t H5Screate_simple(int, const hsize_t*, const hsize_t*) { return -1; }
+inline herr_t H5Sclose(hid_t) { return -1; }
+inline herr_t H5Sselect_hyperslab(hid_t, int, const hsize_t*, const hsize_t*, const hsize_t*, const hsize_t*) { return -1; }
+inline int H5Sget_simple_extent_ndims(hid_t) { return -1; }
+inline int H5Sget_simple_extent_dims(hid_t, hsize_t*, hsize_t*) { return -1; }
+inline hid_t H5Dcreate2(hid_t, const char*, hid_t, hid_t, hid_t, hid_t, hid_t) { return -1; }
+inline hid_t H5Dopen1(hid_t, const char*) { return -1; }
+inline hid_t H5Dopen(hid_t, const char*) { return -1; }
+inline hid_t H5Dget_space(hid_t) { return -1; }
+inline herr_t H5Dwrite(hid_t, hid_t, hid_t, hid_t, hid_t, const void*) { return -1; }
+inline herr_t H5Dread(hid_t, hid_t, hid_t, hid_t, hid_t, void*) { return -1; }
+inline herr_t H5Dclose(hid_t) { return -1; }
+inline hid_t H5Pcreate(hid_t) { return -1; }
+inline herr_t H5Pclose(hid_t) { return -1; }
+inline herr_t H5Eset_auto(H5E_auto_t, void*) { return 0; }
+inline herr_t H5Eget_auto(H5E_auto_t*, void**) { return 0; }

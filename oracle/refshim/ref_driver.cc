@@ -1,0 +1,165 @@
+// oracle/refshim/ref_driver.cc - TEST INFRASTRUCTURE.  Runs the reference's OWN Grid_FFT<real_t>, OrszagConvolver<real_t> and
+// op::* (compiled from /root/reference/include/{grid_fft,convolution,operators}.hh and src/grid_fft.cc against the shims in
+// this directory) on a given first-order potential and dumps what they produce, so that the CPU oracle - and through the
+// committed fixtures the CUDA path - can be pinned against the reference itself for the quantities its goldens do not cover
+// (phi2, phi3, A3, every named product, FFT normalisation, Poisson solve, shift_field, FourierInterpolateCopyTo).
+// This is the non-MPI build of the reference: pad_insert keeps the +Nyquist planes (include/convolution.hh:575-592), so it
+// agrees with the MPI build the goldens come from for Nyquist-free input only - which is what the fixtures use.
+//
+//   ref_driver <n> <boxlen> <Dplus0> <phi_k.bin> <psi_k.bin> <outdir>
+//   phi_k / psi_k: complex128 [n][n][n/2+1] half-spectra (kelem layout)
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <general.hh>
+#include <grid_fft.hh>
+#include <convolution.hh>
+#include <operators.hh>
+
+std::map<cosmo_species, std::string> cosmo_species_name = {{cosmo_species::dm, "dm"}, {cosmo_species::baryon, "baryon"},
+                                                           {cosmo_species::neutrino, "neutrino"}};
+// globals the reference defines in src/main.cc (which is not part of this build)
+namespace CONFIG {
+int MPI_thread_support = -1;
+int MPI_task_rank = 0;
+int MPI_task_size = 1;
+bool MPI_ok = false;
+bool MPI_threads_ok = false;
+bool FFTW_threads_ok = false;
+int num_threads = 1;
+}  // namespace CONFIG
+size_t global_mem_high_mark, local_mem_high_mark;
+extern "C" {
+const char* GIT_TAG = "oracle-shim";
+const char* GIT_REV = "oracle-shim";
+const char* GIT_BRANCH = "oracle-shim";
+}
+
+using grid_t = Grid_FFT<real_t>;
+
+static bool load_k(grid_t& g, const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    g.FourierTransformForward(false);
+    std::vector<ccomplex_t> row(g.size(2));
+    bool ok = true;
+    for (size_t i = 0; i < g.size(0) && ok; ++i)
+        for (size_t j = 0; j < g.size(1) && ok; ++j) {
+            ok = std::fread(row.data(), sizeof(ccomplex_t), row.size(), f) == row.size();
+            for (size_t k = 0; k < g.size(2); ++k) g.kelem(i, j, k) = row[k];
+        }
+    std::fclose(f);
+    return ok;
+}
+static void dump(grid_t& g, const std::string& dir, const std::string& name) {
+    FILE* f = std::fopen((dir + "/" + name + ".bin").c_str(), "wb");
+    if (g.space_ == kspace_id) {
+        for (size_t i = 0; i < g.size(0); ++i)
+            for (size_t j = 0; j < g.size(1); ++j)
+                for (size_t k = 0; k < g.size(2); ++k) { ccomplex_t v = g.kelem(i, j, k); std::fwrite(&v, sizeof(v), 1, f); }
+    } else {
+        for (size_t i = 0; i < g.size(0); ++i)
+            for (size_t j = 0; j < g.size(1); ++j)
+                for (size_t k = 0; k < g.size(2); ++k) { real_t v = g.relem(i, j, k); std::fwrite(&v, sizeof(v), 1, f); }
+    }
+    std::fclose(f);
+}
+
+int main(int argc, char** argv) {
+    if (argc < 7) { std::printf("usage: ref_driver n boxlen Dplus0 phi_k.bin psi_k.bin outdir\n"); return 1; }
+    const size_t n = std::strtoul(argv[1], nullptr, 10);
+    const real_t L = std::atof(argv[2]), D = std::atof(argv[3]);
+    const std::string dir = argv[6];
+    const std::array<size_t, 3> N{n, n, n};
+    const std::array<real_t, 3> B{L, L, L};
+    grid_t phi(N, B), psi(N, B), phi2(N, B), phi3(N, B), A3x(N, B), A3y(N, B), A3z(N, B), tmp(N, B);
+    if (!load_k(phi, argv[4]) || !load_k(psi, argv[5])) { std::printf("cannot read the input spectra\n"); return 2; }
+
+    // ---- transforms and k-space operators of Grid_FFT
+    tmp.FourierTransformForward(false);
+    tmp.copy_from(phi);
+    tmp.FourierTransformBackward();
+    dump(tmp, dir, "phi_real");
+    std::printf("mean %.17g std %.17g\n", (double)tmp.mean(), (double)tmp.std());
+    tmp.shift_field(vec3_t<real_t>({0.5, 0.25, 0.5}));
+    dump(tmp, dir, "phi_real_shifted");
+    tmp.FourierTransformForward();
+    tmp.apply_InverseLaplacian();
+    dump(tmp, dir, "invlap_shifted_phi");
+    {
+        const std::array<size_t, 3> Np{3 * n / 2, 3 * n / 2, 3 * n / 2};
+        grid_t big(Np, B);
+        big.FourierTransformForward(false);
+        psi.FourierInterpolateCopyTo(big);
+        dump(big, dir, "psi_interp_3half");
+    }
+
+    // ---- every named product of the convolver, on two different fields
+    OrszagConvolver<real_t> Conv(N, B);
+    tmp.FourierTransformForward(false);
+    Conv.convolve_Hessians(phi, {0, 1}, psi, {1, 2}, op::assign_to(tmp));
+    dump(tmp, dir, "hess_01_12");
+    Conv.convolve_SumOfHessians(phi, {0, 0}, psi, {1, 1}, {2, 2}, op::assign_to(tmp));
+    dump(tmp, dir, "sumhess_00_11_22");
+    Conv.convolve_DifferenceOfHessians(phi, {1, 2}, psi, {1, 1}, {2, 2}, op::assign_to(tmp));
+    dump(tmp, dir, "diffhess_12_11_22");
+    Conv.convolve_Hessians(phi, {0, 0}, psi, {0, 2}, phi, {2, 2}, op::assign_to(tmp));
+    dump(tmp, dir, "hess3_00_02_22");
+    Conv.convolve_Gradients(phi, {0}, psi, {2}, op::assign_to(tmp));
+    dump(tmp, dir, "grad_0_2");
+    Conv.convolve_Gradient_and_Hessian(phi, {1}, psi, {0, 2}, op::assign_to(tmp));
+    dump(tmp, dir, "gradhess_1_02");
+    Conv.multiply_field(phi, psi, op::assign_to(tmp));
+    dump(tmp, dir, "multiply");
+    Conv.multiply_field(phi, psi, op::multiply_add_to(tmp, 0.5));     // the accumulating output operators
+    Conv.multiply_field(phi, phi, op::subtract_from(tmp));
+    Conv.multiply_field(psi, psi, op::add_to(tmp));
+    dump(tmp, dir, "multiply_ops");
+
+    // ---- the LPT source stage, src/ic_generator.cc:475-574, term by term through the reference's convolver
+    phi2.FourierTransformForward(false);
+    phi3.FourierTransformForward(false);
+    grid_t* A3[3] = {&A3x, &A3y, &A3z};
+    for (auto* a : A3) a->FourierTransformForward(false);
+    struct H2 { int a, b; };
+    Conv.convolve_SumOfHessians(phi, {0, 0}, phi, {1, 1}, {2, 2}, op::assign_to(phi2));
+    Conv.convolve_Hessians(phi, {1, 1}, phi, {2, 2}, op::add_to(phi2));
+    for (H2 h : {H2{0, 1}, H2{0, 2}, H2{1, 2}}) Conv.convolve_Hessians(phi, {h.a, h.b}, phi, {h.a, h.b}, op::subtract_from(phi2));
+    phi2.apply_InverseLaplacian();
+    // 3a: determinant of the Hessian
+    Conv.convolve_Hessians(phi, {0, 0}, phi, {1, 1}, phi, {2, 2}, op::assign_to(phi3));
+    Conv.convolve_Hessians(phi, {0, 1}, phi, {0, 2}, phi, {1, 2}, op::multiply_add_to(phi3, 2.0));
+    for (int d = 0; d < 3; ++d) {
+        const int p = (d + 1) % 3, q = (d + 2) % 3;   // (yz, yz | xx), (zx, zx | yy), (xy, xy | zz)
+        Conv.convolve_Hessians(phi, {p, q}, phi, {p, q}, phi, {d, d}, op::subtract_from(phi3));
+    }
+    // 3b
+    for (int d = 0; d < 3; ++d) {
+        const int p = (d + 1) % 3, q = (d + 2) % 3;
+        Conv.convolve_SumOfHessians(phi, {d, d}, phi2, {p, p}, {q, q}, op::multiply_add_to(phi3, -5.0 / 7.0));
+    }
+    for (H2 h : {H2{0, 1}, H2{0, 2}, H2{1, 2}}) Conv.convolve_Hessians(phi, {h.a, h.b}, phi2, {h.a, h.b}, op::multiply_add_to(phi3, 10.0 / 7.0));
+    phi3.apply_InverseLaplacian();
+    // transverse part
+    for (int d = 0; d < 3; ++d) {
+        const int p = (d + 1) % 3, q = (d + 2) % 3;
+        Conv.convolve_Hessians(phi2, {d, p}, phi, {d, q}, op::assign_to(*A3[d]));
+        Conv.convolve_Hessians(phi2, {d, q}, phi, {d, p}, op::subtract_from(*A3[d]));
+        Conv.convolve_DifferenceOfHessians(phi, {p, q}, phi2, {p, p}, {q, q}, op::add_to(*A3[d]));
+        Conv.convolve_DifferenceOfHessians(phi2, {p, q}, phi, {p, p}, {q, q}, op::subtract_from(*A3[d]));
+        A3[d]->apply_InverseLaplacian();
+    }
+    phi *= -D;
+    phi2 *= -3.0 / 7.0 * D * D;
+    phi3 *= 1.0 / 3.0 * D * D * D;
+    for (auto* a : A3) (*a) *= 1.0 / 7.0 * D * D * D;
+    dump(phi, dir, "phi_scaled");
+    dump(phi2, dir, "phi2");
+    dump(phi3, dir, "phi3");
+    dump(A3x, dir, "A3x");
+    dump(A3y, dir, "A3y");
+    dump(A3z, dir, "A3z");
+    std::printf("ref_driver ok\n");
+    return 0;
+}

@@ -1,0 +1,72 @@
+"""Golden vectors produced by the REFERENCE'S OWN code for the quantities its regression files do not cover.
+
+Run in the build container (where /root/reference is mounted):
+    make -C oracle && python tests/golden/make_ref_fixtures.py
+`oracle/_ref/ref_driver` is the reference's Grid_FFT / OrszagConvolver / op:: sources (include/grid_fft.hh,
+include/convolution.hh, include/operators.hh, src/grid_fft.cc) compiled where they lie against the shims of oracle/refshim/
+(an exact-DFT stand-in for FFTW3, an inert hdf5.h, a hand-written cmake_config.hh); oracle/refshim/ref_driver.cc feeds it a
+first-order potential and dumps every named product, the phi2 / phi3 / A3 source stage of src/ic_generator.cc:475-574, the
+Poisson solve, shift_field and FourierInterpolateCopyTo.  The result, tests/golden/ref_intermediates_32.npz, travels to the
+GPU box; tests/test_oracle_vs_reference.py pins the oracle against it and tests/test_gpu_parity.py the CUDA path.
+Inputs are Nyquist-free (like NGenIC noise), where the non-MPI pad path of this build and the MPI path the goldens come
+from coincide."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.join(HERE, "..", "..")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import lpt_oracle as O  # noqa: E402
+
+N, L, DPLUS = 32, 100.0, 0.0257
+KNAMES = ["invlap_shifted_phi", "hess_01_12", "sumhess_00_11_22", "diffhess_12_11_22", "hess3_00_02_22", "grad_0_2",
+          "gradhess_1_02", "multiply", "multiply_ops", "phi_scaled", "phi2", "phi3", "A3x", "A3y", "A3z"]
+RNAMES = ["phi_real", "phi_real_shifted"]
+
+
+def inputs(n=N):
+    g = O.GridSpec(n, L)
+    amp = O.power_law_amplitude()
+    phi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 101, True)), amp)
+    psi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 202, True)), amp)
+    return g, phi, psi
+
+
+def run_reference(phi, psi, n=N):
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    with tempfile.TemporaryDirectory() as d:
+        np.ascontiguousarray(phi, np.complex128).tofile(os.path.join(d, "phi.bin"))
+        np.ascontiguousarray(psi, np.complex128).tofile(os.path.join(d, "psi.bin"))
+        r = subprocess.run([exe, str(n), repr(L), repr(DPLUS), os.path.join(d, "phi.bin"), os.path.join(d, "psi.bin"), d],
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and "ref_driver ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        out = {}
+        nzc, p = n // 2 + 1, 3 * n // 2
+        for k in KNAMES:
+            out[k] = np.fromfile(os.path.join(d, k + ".bin"), np.complex128).reshape(n, n, nzc)
+        for k in RNAMES:
+            out[k] = np.fromfile(os.path.join(d, k + ".bin"), np.float64).reshape(n, n, n)
+        out["psi_interp_3half"] = np.fromfile(os.path.join(d, "psi_interp_3half.bin"), np.complex128).reshape(p, p, p // 2 + 1)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("mean"):
+                f = ln.split()
+                out["phi_real_mean_std"] = np.array([float(f[1]), float(f[3])])
+    return out
+
+
+def main():
+    g, phi, psi = inputs()
+    out = run_reference(phi, psi)
+    out["phi_in"], out["psi_in"] = phi, psi
+    out["meta"] = np.array([N, L, DPLUS])
+    path = os.path.join(HERE, "ref_intermediates_32.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KB,", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -224,6 +224,75 @@ def check_naive_pipeline(M, n=32):
         assert relerr(pl.A3[d].get_kspace(), ref["A3"][d]) < 10 * TOL
 
 
+# ------------------------------------------------------------------ fixtures produced by the reference's own code
+def load_reference_fixture():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_intermediates_32.npz"))
+
+
+def check_reference_fixture(M):
+    """the CUDA path against what the REFERENCE'S OWN Grid_FFT / OrszagConvolver / op:: sources produce
+    (tests/golden/ref_intermediates_32.npz, made by tests/golden/make_ref_fixtures.py from oracle/_ref/ref_driver):
+    transforms, shift_field, Poisson solve, FourierInterpolateCopyTo, every named product with every output operator, and
+    the phi2 / phi3 / A3 source stage of src/ic_generator.cc:475-574"""
+    R = load_reference_fixture()
+    n, L, D = int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2])
+    phi, psi = R["phi_in"], R["psi_in"]
+    N3, L3 = (n,) * 3, (L,) * 3
+    tol = 1e-11      # relative to the field's maximum; the bar is 1e-9
+    P, Q, T = M.Grid_FFT(N3, L3), M.Grid_FFT(N3, L3), M.Grid_FFT(N3, L3)
+    out = M.Grid_FFT(N3, L3, True, M.kspace_id)
+    P.set_kspace(phi)
+    Q.set_kspace(psi)
+    T.set_kspace(phi)
+    T.FourierTransformBackward()
+    assert relerr(T.get_real(), R["phi_real"]) < tol
+    assert abs(T.mean() - R["phi_real_mean_std"][0]) < 1e-13 * np.abs(R["phi_real"]).max()
+    assert abs(T.std() - R["phi_real_mean_std"][1]) < 1e-12 * R["phi_real_mean_std"][1]
+    T.shift_field((0.5, 0.25, 0.5))
+    assert relerr(T.get_real(), R["phi_real_shifted"]) < tol
+    T.FourierTransformForward()
+    T.apply_InverseLaplacian()
+    assert relerr(T.get_kspace(), R["invlap_shifted_phi"]) < tol
+    big = M.Grid_FFT((3 * n // 2,) * 3, L3)
+    Q.FourierInterpolateCopyTo(big)
+    assert relerr(big.get_kspace(), R["psi_interp_3half"]) < tol
+    C, op = M.OrszagConvolver(N3, L3), M.op
+    C.convolve_Hessians(P, (0, 1), Q, (1, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["hess_01_12"]) < tol
+    C.convolve_SumOfHessians(P, (0, 0), Q, (1, 1), (2, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["sumhess_00_11_22"]) < tol
+    C.convolve_DifferenceOfHessians(P, (1, 2), Q, (1, 1), (2, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["diffhess_12_11_22"]) < tol
+    C.convolve_Hessians(P, (0, 0), Q, (0, 2), P, (2, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["hess3_00_02_22"]) < tol
+    C.convolve_Gradients(P, (0,), Q, (2,), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["grad_0_2"]) < tol
+    C.convolve_Gradient_and_Hessian(P, (1,), Q, (0, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["gradhess_1_02"]) < tol
+    C.multiply_field(P, Q, op.assign_to(out))
+    assert relerr(out.get_kspace(), R["multiply"]) < tol
+    C.multiply_field(P, Q, op.multiply_add_to(out, 0.5))
+    C.multiply_field(P, P, op.subtract_from(out))
+    C.multiply_field(Q, Q, op.add_to(out))
+    assert relerr(out.get_kspace(), R["multiply_ops"]) < tol
+    # the whole source stage, grouped (default) and product by product
+    lib = M.grid._lib()
+    try:
+        for grouping in (1, 0):
+            assert lib.mfb_set_option(b"conv_grouping", grouping) == 0
+            pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=D))
+            pl.phi.set_kspace(phi)
+            pl.compute_sources()
+            assert relerr(pl.phi.get_kspace(), R["phi_scaled"]) < tol
+            assert relerr(pl.phi2.get_kspace(), R["phi2"]) < tol
+            assert relerr(pl.phi3.get_kspace(), R["phi3"]) < 10 * tol
+            for d, nm in enumerate(("A3x", "A3y", "A3z")):
+                assert relerr(pl.A3[d].get_kspace(), R[nm]) < 10 * tol
+    finally:
+        lib.mfb_set_option(b"conv_grouping", 1)
+
+
 # ------------------------------------------------------------------ two-fluid terms, tides, density, masses
 def check_two_fluid_terms(M, n=32, lattice="bcc"):
     """the operators a CDM+baryon run adds (config C4) with NON-degenerate two-fluid amplitudes (the goldens use

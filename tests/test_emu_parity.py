@@ -115,3 +115,7 @@ def test_product_grouping(M):
 
 def test_two_fluid_terms(M):
     PC.check_two_fluid_terms(M, 32, "bcc")
+
+
+def test_against_reference_produced_fixture(M):
+    PC.check_reference_fixture(M)

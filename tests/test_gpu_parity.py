@@ -73,6 +73,10 @@ def test_two_fluid_terms(M, n, lattice):
     PC.check_two_fluid_terms(M, n, lattice)
 
 
+def test_against_reference_produced_fixture(M):
+    PC.check_reference_fixture(M)
+
+
 def test_naive_pipeline(M):
     PC.check_naive_pipeline(M, 64)
 

@@ -1,0 +1,70 @@
+"""Pins the CPU oracle against the REFERENCE'S OWN code for the quantities the reference's regression files do not cover.
+
+* always: oracle vs tests/golden/ref_intermediates_32.npz (made by tests/golden/make_ref_fixtures.py from the reference's
+  Grid_FFT / OrszagConvolver / op:: sources, see oracle/Makefile and oracle/refshim/);
+* where /root/reference is mounted (the build container): oracle/_ref/ref_driver is rebuilt from the reference sources and
+  run live on a second, different pair of fields."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")]
+import lpt_oracle as O  # noqa: E402
+
+TOL = 1e-12
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def compare(R, phi, psi, n, L, D):
+    g = O.GridSpec(n, L)
+    cv = O.OrszagConvolver(g)
+    x = g.bwd(phi)
+    assert rel(x, R["phi_real"]) < TOL
+    assert abs(x.mean() - R["phi_real_mean_std"][0]) < 1e-14 * np.abs(x).max()
+    assert abs(x.std() - R["phi_real_mean_std"][1]) < 1e-13 * x.std()
+    xs = O.shift_field_r(g, x, (0.5, 0.25, 0.5))
+    assert rel(xs, R["phi_real_shifted"]) < TOL
+    assert rel(O.inverse_laplacian(g, g.fwd(xs)), R["invlap_shifted_phi"]) < TOL
+    assert rel(O.fourier_interpolate_copy(g, O.GridSpec(3 * n // 2, L), psi), R["psi_interp_3half"]) < TOL
+    assert rel(cv.convolve_Hessians(phi, (0, 1), psi, (1, 2)), R["hess_01_12"]) < TOL
+    assert rel(cv.convolve_SumOfHessians(phi, (0, 0), psi, (1, 1), (2, 2)), R["sumhess_00_11_22"]) < TOL
+    assert rel(cv.convolve_DifferenceOfHessians(phi, (1, 2), psi, (1, 1), (2, 2)), R["diffhess_12_11_22"]) < TOL
+    assert rel(cv.convolve_Hessians3(phi, (0, 0), psi, (0, 2), phi, (2, 2)), R["hess3_00_02_22"]) < TOL
+    assert rel(cv.convolve_Gradients(phi, 0, psi, 2), R["grad_0_2"]) < TOL
+    assert rel(cv.convolve_Gradient_and_Hessian(phi, 1, psi, (0, 2)), R["gradhess_1_02"]) < TOL
+    m = cv.multiply_field(phi, psi)
+    assert rel(m, R["multiply"]) < TOL
+    assert rel(1.5 * m - cv.multiply_field(phi, phi) + cv.multiply_field(psi, psi), R["multiply_ops"]) < TOL
+    pots = O.lpt_potentials(g, phi, 3, D)
+    assert rel(pots["phi"], R["phi_scaled"]) < TOL and rel(pots["phi2"], R["phi2"]) < TOL
+    assert rel(pots["phi3"], R["phi3"]) < 10 * TOL
+    for d, nm in enumerate(("A3x", "A3y", "A3z")):
+        assert rel(pots["A3"][d], R[nm]) < 100 * TOL
+
+
+def test_oracle_matches_committed_reference_fixture():
+    R = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
+    compare(R, R["phi_in"], R["psi_in"], int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2]))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include") or shutil.which("g++") is None,
+                    reason="the reference sources are only mounted in the build container")
+def test_oracle_matches_reference_built_here():
+    import make_ref_fixtures as F
+
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    n = 32
+    g = O.GridSpec(n, F.L)
+    amp = O.power_law_amplitude(ns=0.93, kcut=0.8)
+    phi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 7, True)), amp)
+    psi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 8, True)), amp)
+    compare(F.run_reference(phi, psi, n), phi, psi, n, F.L, F.DPLUS)

@@ -6,8 +6,10 @@
 // This is the non-MPI build of the reference: pad_insert keeps the +Nyquist planes (include/convolution.hh:575-592), so it
 // agrees with the MPI build the goldens come from for Nyquist-free input only - which is what the fixtures use.
 //
-//   ref_driver <n> <boxlen> <Dplus0> <phi_k.bin> <psi_k.bin> <outdir>
-//   phi_k / psi_k: complex128 [n][n][n/2+1] half-spectra (kelem layout)
+//   ref_driver <n> <boxlen> <Dplus0> <phi_k.bin> <psi_k.bin> <outdir> [<phi_nyq_k.bin> <psi_nyq_k.bin> <cplx_r.bin>]
+//   phi_k / psi_k: complex128 [n][n][n/2+1] half-spectra (kelem layout), Nyquist-free;
+//   optional: two Nyquist-CARRYING half-spectra for the NaiveConvolver (which has no MPI/non-MPI ambiguity: it never pads)
+//   and a complex128 [n][n][n] real-space field for Grid_FFT<ccomplex_t> (the c2c transforms of the PPT branch)
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -149,6 +151,44 @@ int main(int argc, char** argv) {
         Conv.convolve_DifferenceOfHessians(phi, {p, q}, phi2, {p, p}, {q, q}, op::add_to(*A3[d]));
         Conv.convolve_DifferenceOfHessians(phi2, {p, q}, phi, {p, p}, {q, q}, op::subtract_from(*A3[d]));
         A3[d]->apply_InverseLaplacian();
+    }
+    // ---- NaiveConvolver (include/convolution.hh:296-426) on fields whose Nyquist planes are populated
+    if (argc >= 10) {
+        grid_t a(N, B), b(N, B);
+        if (!load_k(a, argv[7]) || !load_k(b, argv[8])) { std::printf("cannot read the Nyquist-carrying spectra\n"); return 2; }
+        NaiveConvolver<real_t> NConv(N, B);
+        tmp.FourierTransformForward(false);
+        NConv.convolve_Hessians(a, {0, 1}, b, {1, 2}, op::assign_to(tmp));
+        dump(tmp, dir, "naive_hess_01_12");
+        NConv.convolve_SumOfHessians(a, {0, 0}, b, {1, 1}, {2, 2}, op::assign_to(tmp));
+        dump(tmp, dir, "naive_sumhess_00_11_22");
+        NConv.convolve_Hessians(a, {0, 0}, b, {0, 2}, a, {2, 2}, op::assign_to(tmp));
+        dump(tmp, dir, "naive_hess3_00_02_22");
+        NConv.convolve_Gradients(a, {0}, b, {2}, op::assign_to(tmp));
+        dump(tmp, dir, "naive_grad_0_2");
+        NConv.convolve_Gradient_and_Hessian(a, {1}, b, {0, 2}, op::assign_to(tmp));
+        dump(tmp, dir, "naive_gradhess_1_02");
+        NConv.multiply_field(a, b, op::assign_to(tmp));
+        dump(tmp, dir, "naive_multiply");
+        // Grid_FFT<ccomplex_t>: forward c2c with the symmetric norm, and back
+        Grid_FFT<ccomplex_t> c(N, B);
+        FILE* f = std::fopen(argv[9], "rb");
+        if (!f) { std::printf("cannot read %s\n", argv[9]); return 2; }
+        c.FourierTransformBackward(false);
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) {
+            ccomplex_t v;
+            if (std::fread(&v, sizeof(v), 1, f) != 1) return 2;
+            c.relem(i, j, k) = v;
+        }
+        std::fclose(f);
+        c.FourierTransformForward();
+        FILE* o = std::fopen((dir + "/cplx_k.bin").c_str(), "wb");
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) { ccomplex_t v = c.kelem(i, j, k); std::fwrite(&v, sizeof(v), 1, o); }
+        std::fclose(o);
+        c.FourierTransformBackward();
+        o = std::fopen((dir + "/cplx_roundtrip.bin").c_str(), "wb");
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) { ccomplex_t v = c.relem(i, j, k); std::fwrite(&v, sizeof(v), 1, o); }
+        std::fclose(o);
     }
     phi *= -D;
     phi2 *= -3.0 / 7.0 * D * D;

@@ -26,6 +26,9 @@ N, L, DPLUS = 32, 100.0, 0.0257
 KNAMES = ["invlap_shifted_phi", "hess_01_12", "sumhess_00_11_22", "diffhess_12_11_22", "hess3_00_02_22", "grad_0_2",
           "gradhess_1_02", "multiply", "multiply_ops", "phi_scaled", "phi2", "phi3", "A3x", "A3y", "A3z"]
 RNAMES = ["phi_real", "phi_real_shifted"]
+NAIVE = ["naive_hess_01_12", "naive_sumhess_00_11_22", "naive_hess3_00_02_22", "naive_grad_0_2", "naive_gradhess_1_02",
+         "naive_multiply"]
+NAIVE_STORED = ["naive_hess3_00_02_22", "naive_gradhess_1_02", "naive_multiply"]   # the committed fixture keeps three
 
 
 def inputs(n=N):
@@ -36,13 +39,28 @@ def inputs(n=N):
     return g, phi, psi
 
 
-def run_reference(phi, psi, n=N):
+def nyquist_inputs(n=N, seeds=(303, 404, 505)):
+    """two half-spectra whose Nyquist planes are populated (NaiveConvolver) and a complex real-space field (c2c)"""
+    g = O.GridSpec(n, L)
+    amp = O.power_law_amplitude()
+    a = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, seeds[0], False)), amp)
+    b = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, seeds[1], False)), amp)
+    rng = np.random.default_rng(seeds[2])
+    c = rng.standard_normal((n, n, n)) + 1j * rng.standard_normal((n, n, n))
+    return a, b, c
+
+
+def run_reference(phi, psi, n=N, extra=None):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     with tempfile.TemporaryDirectory() as d:
         np.ascontiguousarray(phi, np.complex128).tofile(os.path.join(d, "phi.bin"))
         np.ascontiguousarray(psi, np.complex128).tofile(os.path.join(d, "psi.bin"))
-        r = subprocess.run([exe, str(n), repr(L), repr(DPLUS), os.path.join(d, "phi.bin"), os.path.join(d, "psi.bin"), d],
-                           capture_output=True, text=True)
+        cmd = [exe, str(n), repr(L), repr(DPLUS), os.path.join(d, "phi.bin"), os.path.join(d, "psi.bin"), d]
+        if extra is not None:
+            for nm, arr in zip(("a.bin", "b.bin", "c.bin"), extra):
+                np.ascontiguousarray(arr, np.complex128).tofile(os.path.join(d, nm))
+                cmd.append(os.path.join(d, nm))
+        r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0 and "ref_driver ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
         out = {}
         nzc, p = n // 2 + 1, 3 * n // 2
@@ -51,6 +69,11 @@ def run_reference(phi, psi, n=N):
         for k in RNAMES:
             out[k] = np.fromfile(os.path.join(d, k + ".bin"), np.float64).reshape(n, n, n)
         out["psi_interp_3half"] = np.fromfile(os.path.join(d, "psi_interp_3half.bin"), np.complex128).reshape(p, p, p // 2 + 1)
+        if extra is not None:
+            for k in NAIVE:
+                out[k] = np.fromfile(os.path.join(d, k + ".bin"), np.complex128).reshape(n, n, nzc)
+            out["cplx_k"] = np.fromfile(os.path.join(d, "cplx_k.bin"), np.complex128).reshape(n, n, n)
+            out["cplx_roundtrip"] = np.fromfile(os.path.join(d, "cplx_roundtrip.bin"), np.complex128).reshape(n, n, n)
         for ln in r.stdout.splitlines():
             if ln.startswith("mean"):
                 f = ln.split()
@@ -60,8 +83,14 @@ def run_reference(phi, psi, n=N):
 
 def main():
     g, phi, psi = inputs()
-    out = run_reference(phi, psi)
+    a, b, c = nyquist_inputs()
+    out = run_reference(phi, psi, extra=(a, b, c))
+    assert np.abs(out.pop("cplx_roundtrip") - c).max() < 1e-13     # the reference's own c2c round trip; not stored
+    for k in NAIVE:
+        if k not in NAIVE_STORED:
+            out.pop(k)
     out["phi_in"], out["psi_in"] = phi, psi
+    out["naive_a_in"], out["naive_b_in"], out["cplx_in"] = a, b, c
     out["meta"] = np.array([N, L, DPLUS])
     path = os.path.join(HERE, "ref_intermediates_32.npz")
     np.savez_compressed(path, **out)

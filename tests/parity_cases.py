@@ -276,6 +276,21 @@ def check_reference_fixture(M):
     C.multiply_field(P, P, op.subtract_from(out))
     C.multiply_field(Q, Q, op.add_to(out))
     assert relerr(out.get_kspace(), R["multiply_ops"]) < tol
+    # NaiveConvolver on Nyquist-carrying fields, and the c2c transform of the complex grids
+    A, B = M.Grid_FFT(N3, L3), M.Grid_FFT(N3, L3)
+    A.set_kspace(R["naive_a_in"])
+    B.set_kspace(R["naive_b_in"])
+    NC = M.NaiveConvolver(N3, L3)
+    NC.convolve_Hessians(A, (0, 0), B, (0, 2), A, (2, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["naive_hess3_00_02_22"]) < tol
+    NC.convolve_Gradient_and_Hessian(A, (1,), B, (0, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["naive_gradhess_1_02"]) < tol
+    NC.multiply_field(A, B, op.assign_to(out))
+    assert relerr(out.get_kspace(), R["naive_multiply"]) < tol
+    Z = M.Grid_FFT_complex(N3, L3)
+    Z.set(R["cplx_in"])
+    Z.FourierTransformForward()
+    assert relerr(Z.get(), R["cplx_k"]) < tol
     # the whole source stage, grouped (default) and product by product
     lib = M.grid._lib()
     try:

@@ -50,9 +50,23 @@ def compare(R, phi, psi, n, L, D):
         assert rel(pots["A3"][d], R[nm]) < 100 * TOL
 
 
+def compare_naive_and_complex(R, a, b, c, n, L):
+    g = O.GridSpec(n, L)
+    nv = O.NaiveConvolver(g)
+    if "naive_hess_01_12" in R:
+        assert rel(nv.convolve_Hessians(a, (0, 1), b, (1, 2)), R["naive_hess_01_12"]) < TOL
+        assert rel(nv.convolve_SumOfHessians(a, (0, 0), b, (1, 1), (2, 2)), R["naive_sumhess_00_11_22"]) < TOL
+        assert rel(nv.convolve_Gradients(a, 0, b, 2), R["naive_grad_0_2"]) < TOL
+    assert rel(nv.convolve_Hessians3(a, (0, 0), b, (0, 2), a, (2, 2)), R["naive_hess3_00_02_22"]) < TOL
+    assert rel(nv.convolve_Gradient_and_Hessian(a, 1, b, (0, 2)), R["naive_gradhess_1_02"]) < TOL
+    assert rel(nv.multiply_field(a, b), R["naive_multiply"]) < TOL
+    assert rel(np.fft.fftn(c) * g.norm, R["cplx_k"]) < TOL        # c2c forward of Grid_FFT<ccomplex_t>: sign and norm
+
+
 def test_oracle_matches_committed_reference_fixture():
     R = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
     compare(R, R["phi_in"], R["psi_in"], int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2]))
+    compare_naive_and_complex(R, R["naive_a_in"], R["naive_b_in"], R["cplx_in"], int(R["meta"][0]), float(R["meta"][1]))
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/include") or shutil.which("g++") is None,
@@ -67,4 +81,8 @@ def test_oracle_matches_reference_built_here():
     amp = O.power_law_amplitude(ns=0.93, kcut=0.8)
     phi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 7, True)), amp)
     psi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 8, True)), amp)
-    compare(F.run_reference(phi, psi, n), phi, psi, n, F.L, F.DPLUS)
+    a, b, c = F.nyquist_inputs(n, (31, 41, 59))
+    R = F.run_reference(phi, psi, n, extra=(a, b, c))
+    compare(R, phi, psi, n, F.L, F.DPLUS)
+    compare_naive_and_complex(R, a, b, c, n, F.L)
+    assert rel(R["cplx_roundtrip"], c) < TOL

@@ -154,7 +154,11 @@ void check_launch(const char* what) {
 
 void* dev_alloc(size_t bytes) {
     void* p = nullptr;
-    cuda_check(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc");
+    const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // clear the sticky allocation error: the library stays usable after an out-of-memory report
+        throw std::runtime_error("cudaMalloc of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
+    }
     return p;
 }
 
@@ -1379,7 +1383,8 @@ int mfb_grid_create(mfb_grid** out, const int n[3], const double L[3], int space
         g->ntot = rows * (n[2] + 2);
     }
     g->space = space;
-    g->d = (double*)dev_alloc(g->ntot * sizeof(double));
+    try { g->d = (double*)dev_alloc(g->ntot * sizeof(double)); }
+    catch (...) { delete g; throw; }   // out of HBM: no half-built object is leaked
     *out = g;
     MFB_CATCH
 }
@@ -1624,7 +1629,8 @@ int mfb_cgrid_create(mfb_cgrid** out, const int n[3], const double L[3]) {
     for (int d = 0; d < 3; ++d) { g->n[d] = n[d]; g->L[d] = L[d]; }
     g->space = MFB_RSPACE;
     g->nelem = size_t(n[0]) * n[1] * n[2];
-    g->d = (double2*)dev_alloc(g->nelem * sizeof(double2));
+    try { g->d = (double2*)dev_alloc(g->nelem * sizeof(double2)); }
+    catch (...) { delete g; throw; }
     cuda_check(cudaMemsetAsync(g->d, 0, g->nelem * sizeof(double2), g_ctx.stream), "memset");
     *out = g;
     MFB_CATCH
@@ -1748,10 +1754,18 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
     }
     c->w1_elems = c->dist ? 0 : size_t(c->np[0]) * n[1] * nzin;   // slab mode: the exchange buffers play W1's role
     c->w2_elems = size_t(c->p0loc) * c->np[1] * nzin;
-    c->W1 = c->dist ? nullptr : (double2*)dev_alloc(c->w1_elems * sizeof(double2));
-    c->W2a = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
-    c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
-    if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
+    try {
+        c->W1 = c->dist ? nullptr : (double2*)dev_alloc(c->w1_elems * sizeof(double2));
+        c->W2a = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
+        c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
+        if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
+    } catch (...) {   // out of HBM part-way: release what was taken
+        if (c->W1) cudaFree(c->W1);
+        if (c->W2a) cudaFree(c->W2a);
+        if (c->W2b) cudaFree(c->W2b);
+        delete c;
+        throw;
+    }
     c->naive = 0; c->nb1 = c->nb2 = nullptr;
     // the accumulator of product groups is an optimisation, not a requirement: take it only if HBM is plentiful after it
     // (room for the particle arrays and the remaining grids of a 3LPT run: 3.75 R(N) of this slab)
@@ -1901,10 +1915,18 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
     p->np = ov * size_t(p->nloc0) * n[1] * n[2];   // get_local_num_particles (particle_container.hh:150-152)
     const size_t rs = real64 ? 8 : 4, is = ids64 ? 8 : 4;
     p->posvel_bytes = 6 * p->np * rs;
-    p->pos = dev_alloc(p->posvel_bytes);                 // one block: it can be lent to the convolver as its accumulator
-    p->vel = (char*)p->pos + 3 * p->np * rs;
-    p->ids = dev_alloc(p->np * is);
-    p->mass = with_masses ? dev_alloc(p->np * rs) : nullptr;
+    p->pos = p->ids = p->mass = nullptr;
+    try {
+        p->pos = dev_alloc(p->posvel_bytes);             // one block: it can be lent to the convolver as its accumulator
+        p->vel = (char*)p->pos + 3 * p->np * rs;
+        p->ids = dev_alloc(p->np * is);
+        p->mass = with_masses ? dev_alloc(p->np * rs) : nullptr;
+    } catch (...) {
+        if (p->pos) cudaFree(p->pos);
+        if (p->ids) cudaFree(p->ids);
+        delete p;
+        throw;
+    }
     *out = p;
     MFB_CATCH
 }

@@ -13,8 +13,11 @@ Parity status: PINNED, twice.
   (2) tests/test_oracle_vs_reference.py checks it against the reference's OWN Grid_FFT / OrszagConvolver / op::
       sources, compiled where they lie (oracle/Makefile -> oracle/_ref/ref_driver; FFTW3 replaced by the exact-DFT
       shim of oracle/refshim/) and run in the build container: every named product with every output operator,
-      the phi2 / phi3 / A3 source stage, Poisson solve, shift_field, FourierInterpolateCopyTo - agreement
-      1e-15..2e-14.  Its output is committed as tests/golden/ref_intermediates_32.npz for the GPU box.
+      the phi2 / phi3 / A3 source stage, Poisson solve, shift_field, FourierInterpolateCopyTo, the NaiveConvolver,
+      c2c transforms - agreement 1e-15..2e-14 - in the reference's non-MPI build AND in its USE_MPI build on one rank
+      (oracle/_ref/ref_driver_mpi; one-rank mpi.h / fftw3-mpi.h shims), the latter also on fields with populated
+      Nyquist planes, whose treatment (dropped by pad / unpad) this module restates.  The outputs are committed as
+      tests/golden/ref_intermediates_32.npz for the GPU box.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 

@@ -12,6 +12,7 @@ struct fftw_plan_s {
     int kind;  // 0 r2c, 1 c2r, 2 c2c
     int n0, n1, n2, sign;
     void* data;
+    int transposed;  // FFTW-MPI TRANSPOSED_OUT (forward) / TRANSPOSED_IN (backward): k-space stored [k1][k0][k2]
 };
 typedef std::complex<long double> lc;
 
@@ -36,10 +37,19 @@ static void dft_line(std::complex<double>* x, int n, long stride, const std::vec
 extern "C" {
 void* fftw_malloc(size_t n) { return aligned_alloc(64, (n + 63) / 64 * 64); }
 void fftw_free(void* p) { free(p); }
-static fftw_plan mk(int kind, int n0, int n1, int n2, int sign, void* d) {
-    fftw_plan p = new fftw_plan_s{kind, n0, n1, n2, sign, d};
+static fftw_plan mk(int kind, int n0, int n1, int n2, int sign, void* d, int transposed = 0) {
+    fftw_plan p = new fftw_plan_s{kind, n0, n1, n2, sign, d, transposed};
     return p;
 }
+// [a][b][m] <-> [b][a][m] for the first two axes of a complex array
+static void swap01(std::complex<double>* c, int a, int b, int m) {
+    std::vector<std::complex<double>> t(size_t(a) * b * m);
+    for (int i = 0; i < a; ++i)
+        for (int j = 0; j < b; ++j)
+            for (int k = 0; k < m; ++k) t[(size_t(j) * a + i) * m + k] = c[(size_t(i) * b + j) * m + k];
+    for (size_t i = 0; i < t.size(); ++i) c[i] = t[i];
+}
+static void execute_plain(const fftw_plan p);
 fftw_plan fftw_plan_dft_r2c_3d(int n0, int n1, int n2, double* in, fftw_complex*, unsigned) { return mk(0, n0, n1, n2, -1, in); }
 fftw_plan fftw_plan_dft_c2r_3d(int n0, int n1, int n2, fftw_complex* in, double*, unsigned) { return mk(1, n0, n1, n2, +1, in); }
 fftw_plan fftw_plan_dft_3d(int n0, int n1, int n2, fftw_complex* in, fftw_complex*, int sign, unsigned) { return mk(2, n0, n1, n2, sign, in); }
@@ -49,6 +59,31 @@ void fftw_plan_with_nthreads(int) {}
 void fftw_cleanup_threads(void) {}
 
 void fftw_execute(const fftw_plan p) {
+    if (!p->transposed) { execute_plain(p); return; }
+    const int m = (p->kind == 2) ? p->n2 : p->n2 / 2 + 1;
+    auto* c = reinterpret_cast<std::complex<double>*>(p->data);
+    const bool to_k = (p->kind == 0) || (p->kind == 2 && p->sign == FFTW_FORWARD);
+    if (to_k) { execute_plain(p); swap01(c, p->n0, p->n1, m); }      // natural in, [k1][k0][k2] out
+    else { swap01(c, p->n1, p->n0, m); execute_plain(p); }           // [k1][k0][k2] in, natural out
+}
+void fftw_mpi_init(void) {}
+ptrdiff_t fftw_mpi_local_size_3d_transposed(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int, ptrdiff_t* l0, ptrdiff_t* s0, ptrdiff_t* l1,
+                                            ptrdiff_t* s1) {
+    *l0 = n0; *s0 = 0; *l1 = n1; *s1 = 0;
+    return n0 * n1 * n2;   // complex elements this rank must be able to hold (callers pass n2/2+1 or n2 as they need)
+}
+fftw_plan fftw_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double* in, fftw_complex*, int, unsigned flags) {
+    return mk(0, int(n0), int(n1), int(n2), -1, in, (flags & (1u << 30)) ? 1 : 0);
+}
+fftw_plan fftw_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex* in, double*, int, unsigned flags) {
+    return mk(1, int(n0), int(n1), int(n2), +1, in, (flags & (1u << 29)) ? 1 : 0);
+}
+fftw_plan fftw_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex* in, fftw_complex*, int, int sign, unsigned flags) {
+    return mk(2, int(n0), int(n1), int(n2), sign, in, (flags & ((1u << 29) | (1u << 30))) ? 1 : 0);
+}
+}   // extern "C"
+
+static void execute_plain(const fftw_plan p) {
     const int n0 = p->n0, n1 = p->n1, n2 = p->n2, nzc = n2 / 2 + 1;
     auto* c = reinterpret_cast<std::complex<double>*>(p->data);
     auto* r = reinterpret_cast<double*>(p->data);
@@ -92,5 +127,4 @@ void fftw_execute(const fftw_plan p) {
             for (int j = 0; j < n2; ++j) x[j] = (double)out[j];
         }
     }
-}
 }

@@ -29,5 +29,7 @@ inline herr_t H5Dread(hid_t, hid_t, hid_t, hid_t, hid_t, void*) { return -1; }
 inline herr_t H5Dclose(hid_t) { return -1; }
 inline hid_t H5Pcreate(hid_t) { return -1; }
 inline herr_t H5Pclose(hid_t) { return -1; }
+inline herr_t H5Pset_dxpl_mpio(hid_t, int) { return -1; }
+inline herr_t H5Pset_fapl_mpio(hid_t, int, int) { return -1; }
 inline herr_t H5Eset_auto(H5E_auto_t, void*) { return 0; }
 inline herr_t H5Eget_auto(H5E_auto_t*, void**) { return 0; }

@@ -3,8 +3,11 @@
 // this directory) on a given first-order potential and dumps what they produce, so that the CPU oracle - and through the
 // committed fixtures the CUDA path - can be pinned against the reference itself for the quantities its goldens do not cover
 // (phi2, phi3, A3, every named product, FFT normalisation, Poisson solve, shift_field, FourierInterpolateCopyTo).
-// This is the non-MPI build of the reference: pad_insert keeps the +Nyquist planes (include/convolution.hh:575-592), so it
-// agrees with the MPI build the goldens come from for Nyquist-free input only - which is what the fixtures use.
+// Two builds (oracle/Makefile): ref_driver is the reference's non-MPI build, where pad_insert keeps the +Nyquist planes
+// (include/convolution.hh:575-592) - it agrees with the MPI build for Nyquist-free input only; ref_driver_mpi is the
+// USE_MPI build on one rank (mpi.h / fftw3-mpi.h shims): transposed k-layout, pad / unpad through FourierInterpolateCopyTo
+// with the Nyquist planes dropped (:594-608, :657-665) - the code path the reference's CI builds and its goldens come from,
+// and the semantics the CUDA path implements for Nyquist-carrying noise (MUSIC1, Panphasia).
 //
 //   ref_driver <n> <boxlen> <Dplus0> <phi_k.bin> <psi_k.bin> <outdir> [<phi_nyq_k.bin> <psi_nyq_k.bin> <cplx_r.bin>]
 //   phi_k / psi_k: complex128 [n][n][n/2+1] half-spectra (kelem layout), Nyquist-free;
@@ -40,30 +43,42 @@ const char* GIT_BRANCH = "oracle-shim";
 
 using grid_t = Grid_FFT<real_t>;
 
+// Files hold half-spectra as [kx][ky][kz] and real fields as [x][y][z].  In the USE_MPI build k-space is stored transposed
+// ([ky_loc][kx][kz], src/grid_fft.cc:125-128): kelem(i,j,k) then takes i = ky, j = kx.
+#if defined(USE_MPI)
+static constexpr bool k_transposed = true;
+#else
+static constexpr bool k_transposed = false;
+#endif
+template <class G> static ccomplex_t& kref(G& g, size_t kx, size_t ky, size_t kz) {
+    return k_transposed ? g.kelem(ky, kx, kz) : g.kelem(kx, ky, kz);
+}
 static bool load_k(grid_t& g, const std::string& path) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
     g.FourierTransformForward(false);
-    std::vector<ccomplex_t> row(g.size(2));
+    const size_t n0 = g.n_[0], n1 = g.n_[1], nzc = g.n_[2] / 2 + 1;
+    std::vector<ccomplex_t> row(nzc);
     bool ok = true;
-    for (size_t i = 0; i < g.size(0) && ok; ++i)
-        for (size_t j = 0; j < g.size(1) && ok; ++j) {
+    for (size_t i = 0; i < n0 && ok; ++i)
+        for (size_t j = 0; j < n1 && ok; ++j) {
             ok = std::fread(row.data(), sizeof(ccomplex_t), row.size(), f) == row.size();
-            for (size_t k = 0; k < g.size(2); ++k) g.kelem(i, j, k) = row[k];
+            for (size_t k = 0; k < nzc; ++k) kref(g, i, j, k) = row[k];
         }
     std::fclose(f);
     return ok;
 }
 static void dump(grid_t& g, const std::string& dir, const std::string& name) {
     FILE* f = std::fopen((dir + "/" + name + ".bin").c_str(), "wb");
+    const size_t n0 = g.n_[0], n1 = g.n_[1], n2 = g.n_[2];
     if (g.space_ == kspace_id) {
-        for (size_t i = 0; i < g.size(0); ++i)
-            for (size_t j = 0; j < g.size(1); ++j)
-                for (size_t k = 0; k < g.size(2); ++k) { ccomplex_t v = g.kelem(i, j, k); std::fwrite(&v, sizeof(v), 1, f); }
+        for (size_t i = 0; i < n0; ++i)
+            for (size_t j = 0; j < n1; ++j)
+                for (size_t k = 0; k < n2 / 2 + 1; ++k) { ccomplex_t v = kref(g, i, j, k); std::fwrite(&v, sizeof(v), 1, f); }
     } else {
-        for (size_t i = 0; i < g.size(0); ++i)
-            for (size_t j = 0; j < g.size(1); ++j)
-                for (size_t k = 0; k < g.size(2); ++k) { real_t v = g.relem(i, j, k); std::fwrite(&v, sizeof(v), 1, f); }
+        for (size_t i = 0; i < n0; ++i)
+            for (size_t j = 0; j < n1; ++j)
+                for (size_t k = 0; k < n2; ++k) { real_t v = g.relem(i, j, k); std::fwrite(&v, sizeof(v), 1, f); }
     }
     std::fclose(f);
 }
@@ -183,7 +198,7 @@ int main(int argc, char** argv) {
         std::fclose(f);
         c.FourierTransformForward();
         FILE* o = std::fopen((dir + "/cplx_k.bin").c_str(), "wb");
-        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) { ccomplex_t v = c.kelem(i, j, k); std::fwrite(&v, sizeof(v), 1, o); }
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) { ccomplex_t v = kref(c, i, j, k); std::fwrite(&v, sizeof(v), 1, o); }
         std::fclose(o);
         c.FourierTransformBackward();
         o = std::fopen((dir + "/cplx_roundtrip.bin").c_str(), "wb");

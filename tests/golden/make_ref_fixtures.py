@@ -29,6 +29,8 @@ RNAMES = ["phi_real", "phi_real_shifted"]
 NAIVE = ["naive_hess_01_12", "naive_sumhess_00_11_22", "naive_hess3_00_02_22", "naive_grad_0_2", "naive_gradhess_1_02",
          "naive_multiply"]
 NAIVE_STORED = ["naive_hess3_00_02_22", "naive_gradhess_1_02", "naive_multiply"]   # the committed fixture keeps three
+# from the USE_MPI build run on the Nyquist-CARRYING pair (stored with the prefix "mpinyq_")
+MPI_NYQ_STORED = ["phi_real_shifted", "invlap_shifted_phi", "hess3_00_02_22", "gradhess_1_02", "multiply_ops", "phi3", "A3x"]
 
 
 def inputs(n=N):
@@ -50,8 +52,9 @@ def nyquist_inputs(n=N, seeds=(303, 404, 505)):
     return a, b, c
 
 
-def run_reference(phi, psi, n=N, extra=None):
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+def run_reference(phi, psi, n=N, extra=None, mpi=False):
+    """mpi=True: the USE_MPI build of the reference on one rank (oracle/_ref/ref_driver_mpi)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_mpi" if mpi else "ref_driver")
     with tempfile.TemporaryDirectory() as d:
         np.ascontiguousarray(phi, np.complex128).tofile(os.path.join(d, "phi.bin"))
         np.ascontiguousarray(psi, np.complex128).tofile(os.path.join(d, "psi.bin"))
@@ -91,6 +94,14 @@ def main():
             out.pop(k)
     out["phi_in"], out["psi_in"] = phi, psi
     out["naive_a_in"], out["naive_b_in"], out["cplx_in"] = a, b, c
+    # the MPI code path of the reference (one rank) on the Nyquist-carrying pair: pad / unpad drop the Nyquist planes
+    Rm = run_reference(a, b, mpi=True)
+    for k in MPI_NYQ_STORED:
+        out["mpinyq_" + k] = Rm[k]
+    # and the MPI build must reproduce the non-MPI build on the Nyquist-free pair
+    Rf = run_reference(phi, psi, mpi=True)
+    for k in KNAMES + RNAMES:
+        assert np.abs(Rf[k] - out[k]).max() <= 1e-13 * np.abs(out[k]).max(), k
     out["meta"] = np.array([N, L, DPLUS])
     path = os.path.join(HERE, "ref_intermediates_32.npz")
     np.savez_compressed(path, **out)

@@ -287,6 +287,28 @@ def check_reference_fixture(M):
     assert relerr(out.get_kspace(), R["naive_gradhess_1_02"]) < tol
     NC.multiply_field(A, B, op.assign_to(out))
     assert relerr(out.get_kspace(), R["naive_multiply"]) < tol
+    # Nyquist-CARRYING fields through the dealiased products: the reference's USE_MPI code path (pad / unpad drop the
+    # Nyquist planes) is what the CUDA path implements
+    A.shift_field((0.5, 0.25, 0.5))
+    assert relerr(A.get_real(), R["mpinyq_phi_real_shifted"]) < tol
+    A.FourierTransformForward()
+    A.apply_InverseLaplacian()
+    assert relerr(A.get_kspace(), R["mpinyq_invlap_shifted_phi"]) < tol
+    A.set_kspace(R["naive_a_in"])
+    C.convolve_Hessians(A, (0, 0), B, (0, 2), A, (2, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["mpinyq_hess3_00_02_22"]) < tol
+    C.convolve_Gradient_and_Hessian(A, (1,), B, (0, 2), op.assign_to(out))
+    assert relerr(out.get_kspace(), R["mpinyq_gradhess_1_02"]) < tol
+    C.multiply_field(A, B, op.assign_to(out))
+    C.multiply_field(A, B, op.multiply_add_to(out, 0.5))
+    C.multiply_field(A, A, op.subtract_from(out))
+    C.multiply_field(B, B, op.add_to(out))
+    assert relerr(out.get_kspace(), R["mpinyq_multiply_ops"]) < tol
+    pn = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=D))
+    pn.phi.set_kspace(R["naive_a_in"])
+    pn.compute_sources()
+    assert relerr(pn.phi3.get_kspace(), R["mpinyq_phi3"]) < 10 * tol
+    assert relerr(pn.A3[0].get_kspace(), R["mpinyq_A3x"]) < 10 * tol
     Z = M.Grid_FFT_complex(N3, L3)
     Z.set(R["cplx_in"])
     Z.FourierTransformForward()

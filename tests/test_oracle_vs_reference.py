@@ -63,10 +63,28 @@ def compare_naive_and_complex(R, a, b, c, n, L):
     assert rel(np.fft.fftn(c) * g.norm, R["cplx_k"]) < TOL        # c2c forward of Grid_FFT<ccomplex_t>: sign and norm
 
 
+def compare_mpi_nyquist(R, a, b, n, L, D, prefix=""):
+    """the reference's USE_MPI code path on fields with populated Nyquist planes: the oracle restates exactly these
+    semantics (pad / unpad through FourierInterpolateCopyTo, Nyquist planes dropped)"""
+    g = O.GridSpec(n, L)
+    cv = O.OrszagConvolver(g)
+    xs = O.shift_field_r(g, g.bwd(a), (0.5, 0.25, 0.5))
+    assert rel(xs, R[prefix + "phi_real_shifted"]) < TOL
+    assert rel(O.inverse_laplacian(g, g.fwd(xs)), R[prefix + "invlap_shifted_phi"]) < TOL
+    assert rel(cv.convolve_Hessians3(a, (0, 0), b, (0, 2), a, (2, 2)), R[prefix + "hess3_00_02_22"]) < TOL
+    assert rel(cv.convolve_Gradient_and_Hessian(a, 1, b, (0, 2)), R[prefix + "gradhess_1_02"]) < TOL
+    m = cv.multiply_field(a, b)
+    assert rel(1.5 * m - cv.multiply_field(a, a) + cv.multiply_field(b, b), R[prefix + "multiply_ops"]) < TOL
+    pots = O.lpt_potentials(g, a, 3, D)
+    assert rel(pots["phi3"], R[prefix + "phi3"]) < 10 * TOL
+    assert rel(pots["A3"][0], R[prefix + "A3x"]) < 100 * TOL
+
+
 def test_oracle_matches_committed_reference_fixture():
     R = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
     compare(R, R["phi_in"], R["psi_in"], int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2]))
     compare_naive_and_complex(R, R["naive_a_in"], R["naive_b_in"], R["cplx_in"], int(R["meta"][0]), float(R["meta"][1]))
+    compare_mpi_nyquist(R, R["naive_a_in"], R["naive_b_in"], int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2]), "mpinyq_")
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/include") or shutil.which("g++") is None,
@@ -74,7 +92,7 @@ def test_oracle_matches_committed_reference_fixture():
 def test_oracle_matches_reference_built_here():
     import make_ref_fixtures as F
 
-    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     n = 32
     g = O.GridSpec(n, F.L)
@@ -86,3 +104,10 @@ def test_oracle_matches_reference_built_here():
     compare(R, phi, psi, n, F.L, F.DPLUS)
     compare_naive_and_complex(R, a, b, c, n, F.L)
     assert rel(R["cplx_roundtrip"], c) < TOL
+    # the USE_MPI build on one rank: same results on the Nyquist-free pair, and the Nyquist-carrying pair
+    Rm = F.run_reference(phi, psi, n, extra=(a, b, c), mpi=True)
+    compare(Rm, phi, psi, n, F.L, F.DPLUS)
+    compare_naive_and_complex(Rm, a, b, c, n, F.L)
+    Rn = F.run_reference(a, b, n, mpi=True)
+    compare(Rn, a, b, n, F.L, F.DPLUS)
+    compare_mpi_nyquist(Rn, a, b, n, F.L, F.DPLUS)

@@ -16,7 +16,9 @@ Parity status: PINNED, twice.
       the phi2 / phi3 / A3 source stage, Poisson solve, shift_field, FourierInterpolateCopyTo, the NaiveConvolver,
       c2c transforms - agreement 1e-15..2e-14 - in the reference's non-MPI build AND in its USE_MPI build on one rank
       (oracle/_ref/ref_driver_mpi; one-rank mpi.h / fftw3-mpi.h shims), the latter also on fields with populated
-      Nyquist planes, whose treatment (dropped by pad / unpad) this module restates.  The outputs are committed as
+      Nyquist planes, whose treatment (dropped by pad / unpad) this module restates; and particle::lattice_generator
+      (MPI build): IDs and bare-lattice positions bit-identical, displaced positions to 1 ulp of the box, for sc / bcc /
+      fcc / rsc and both lattice indices.  The outputs are committed as
       tests/golden/ref_intermediates_32.npz for the GPU box.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).

@@ -7,6 +7,7 @@ typedef long hid_t;
 typedef int herr_t;
 typedef int htri_t;
 typedef unsigned long long hsize_t;
+typedef long long hssize_t_shim;
 typedef herr_t (*H5E_auto_t)(void*);
 enum { H5P_DEFAULT = 0, H5S_ALL = 0, H5S_SELECT_SET = 0, H5F_ACC_RDONLY = 0, H5F_ACC_RDWR = 1, H5F_ACC_TRUNC = 2,
        H5P_DATASET_XFER = 1, H5P_FILE_ACCESS = 2, H5FD_MPIO_COLLECTIVE = 1 };
@@ -29,6 +30,33 @@ inline herr_t H5Dread(hid_t, hid_t, hid_t, hid_t, hid_t, void*) { return -1; }
 inline herr_t H5Dclose(hid_t) { return -1; }
 inline hid_t H5Pcreate(hid_t) { return -1; }
 inline herr_t H5Pclose(hid_t) { return -1; }
+// the HDF5-1.6-style calls of include/HDF_IO.hh (pulled in by the particle generator's glass loader when USE_HDF5 is set)
+enum { H5S_SCALAR = 0, H5P_DATASET_CREATE = 3, H5T_STR_NULLPAD = 1, H5T_C_S1 = 20, H5S_SELECT_APPEND = 1 };
+inline hid_t H5Dcreate(hid_t, const char*, hid_t, hid_t, hid_t) { return -1; }
+inline hid_t H5Gopen(hid_t, const char*) { return -1; }
+inline hid_t H5Gcreate(hid_t, const char*, size_t) { return -1; }
+inline herr_t H5Gclose(hid_t) { return -1; }
+inline hid_t H5Acreate(hid_t, const char*, hid_t, hid_t, hid_t) { return -1; }
+inline hid_t H5Aopen_name(hid_t, const char*) { return -1; }
+inline hid_t H5Aget_space(hid_t) { return -1; }
+inline hid_t H5Aget_type(hid_t) { return -1; }
+inline herr_t H5Awrite(hid_t, hid_t, const void*) { return -1; }
+inline herr_t H5Aread(hid_t, hid_t, void*) { return -1; }
+inline herr_t H5Aclose(hid_t) { return -1; }
+inline hid_t H5Screate(int) { return -1; }
+inline herr_t H5Sselect_elements(hid_t, int, size_t, const hsize_t*) { return -1; }
+inline htri_t H5Sselect_valid(hid_t) { return -1; }
+inline herr_t H5Sselect_none(hid_t) { return -1; }
+inline herr_t H5Pset_fletcher32(hid_t) { return -1; }
+inline herr_t H5Pset_chunk(hid_t, int, const hsize_t*) { return -1; }
+inline hid_t H5Tcopy(hid_t) { return -1; }
+inline herr_t H5Tset_size(hid_t, size_t) { return -1; }
+inline herr_t H5Tset_strpad(hid_t, int) { return -1; }
+inline herr_t H5Tclose(hid_t) { return -1; }
+inline hid_t H5Dget_type(hid_t) { return -1; }
+inline size_t H5Tget_size(hid_t) { return 0; }
+inline int H5Tget_class(hid_t) { return -1; }
+inline hssize_t_shim H5Sget_simple_extent_npoints(hid_t) { return -1; }
 inline herr_t H5Pset_dxpl_mpio(hid_t, int) { return -1; }
 inline herr_t H5Pset_fapl_mpio(hid_t, int, int) { return -1; }
 inline herr_t H5Eset_auto(H5E_auto_t, void*) { return 0; }

@@ -66,6 +66,27 @@ inline int MPI_Recv(void* buf, int count, MPI_Datatype t, int /*source*/, int ta
     if (st) st->MPI_ERROR = 1;
     return 1;   // no matching send: a real MPI would block forever
 }
+// declared for template code of the reference that the one-rank driver never instantiates into a call with > 1 rank
+#define MPI_STATUS_IGNORE ((MPI_Status*)0)
+inline int MPI_Error_string(int, char* s, int* len) { s[0] = 0; *len = 0; return MPI_SUCCESS; }
+inline int MPI_Bcast(void*, int, MPI_Datatype, int, MPI_Comm) { return MPI_SUCCESS; }
+inline int MPI_Sendrecv_replace(void*, int, MPI_Datatype, int, int, int, int, MPI_Comm, MPI_Status* st) {   // self: data stays
+    if (st) st->MPI_ERROR = MPI_SUCCESS;
+    return MPI_SUCCESS;
+}
+inline int MPI_Send(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm c) {
+    MPI_Request r;
+    return MPI_Isend(buf, count, t, dest, tag, c, &r);
+}
+inline int MPI_Alltoall(const void* s, int scount, MPI_Datatype st, void* r, int, MPI_Datatype, MPI_Comm) {
+    if (s != r) std::memcpy(r, s, size_t(scount) * st);
+    return MPI_SUCCESS;
+}
+inline int MPI_Alltoallv(const void* s, const int* scounts, const int* sdispls, MPI_Datatype st, void* r, const int*, const int* rdispls,
+                         MPI_Datatype, MPI_Comm) {
+    std::memcpy((char*)r + size_t(rdispls[0]) * st, (const char*)s + size_t(sdispls[0]) * st, size_t(scounts[0]) * st);
+    return MPI_SUCCESS;
+}
 inline int MPI_Test(MPI_Request* req, int* flag, MPI_Status*) { *flag = mpi_shim::pending()[*req].done ? 1 : 0; return MPI_SUCCESS; }
 inline int MPI_Wait(MPI_Request* req, MPI_Status* st) {
     if (st) st->MPI_ERROR = mpi_shim::pending()[*req].done ? MPI_SUCCESS : 1;

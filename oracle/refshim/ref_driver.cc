@@ -21,6 +21,11 @@
 #include <grid_fft.hh>
 #include <convolution.hh>
 #include <operators.hh>
+#if defined(USE_MPI)   // the reference's particle generator only compiles in its MPI build (the non-MPI branches of
+#define USE_HDF5       // grid_ghosts.hh / glass_loader.hh use MPI unguarded), and its glass loader wants HDF_IO.hh
+#include <particle_container.hh>
+#include <particle_generator.hh>
+#endif
 
 std::map<cosmo_species, std::string> cosmo_species_name = {{cosmo_species::dm, "dm"}, {cosmo_species::baryon, "baryon"},
                                                            {cosmo_species::neutrino, "neutrino"}};
@@ -83,7 +88,54 @@ static void dump(grid_t& g, const std::string& dir, const std::string& name) {
     std::fclose(f);
 }
 
+#if defined(USE_MPI)
+// particle::lattice_generator of the reference (include/particle_generator.hh:129-170, 292-350, 422-467, 520-562) on the
+// fields phi (positions, masses) and psi (velocities) in real space:
+//   ref_driver_mpi particles <n> <boxlen> <phi_k.bin> <psi_k.bin> <outdir> <lattice_type> <lattice_index> <zero_field 0|1>
+static int run_particles(int argc, char** argv) {
+    if (argc < 10) return 1;
+    const size_t n = std::strtoul(argv[2], nullptr, 10);
+    const real_t L = std::atof(argv[3]);
+    const std::string dir = argv[6];
+    const auto lt = particle::lattice(std::atoi(argv[7]));
+    const int lidx = std::atoi(argv[8]);
+    const bool zero = std::atoi(argv[9]) != 0;
+    const std::array<size_t, 3> N{n, n, n};
+    const std::array<real_t, 3> B{L, L, L};
+    grid_t phi(N, B), psi(N, B), tmp(N, B);
+    if (!load_k(phi, argv[4]) || !load_k(psi, argv[5])) return 2;
+    { FILE* f = std::fopen((dir + "/empty.conf").c_str(), "w"); std::fputs("[setup]\nDoBaryons = no\n", f); std::fclose(f); }
+    config_file cf(dir + "/empty.conf");
+    const real_t lunit = L, munit = 2.5;
+    particle::lattice_generator<grid_t> lg(lt, lidx, true, true, true, size_t(lidx), tmp, cf);
+    auto fresh = [&](grid_t& src) {
+        tmp.FourierTransformForward(false);
+        tmp.copy_from(src);
+        if (zero) tmp.zero();
+        tmp.FourierTransformBackward();
+    };
+    for (int d = 0; d < 3; ++d) { fresh(phi); lg.set_positions(lt, lidx, d, lunit, true, tmp, cf); }
+    for (int d = 0; d < 3; ++d) { fresh(psi); lg.set_velocities(lt, lidx, d, true, tmp, cf); }
+    fresh(phi);
+    lg.set_masses(lt, lidx, munit, true, tmp, cf);
+    const particle::container& pc = lg.get_particles();
+    const uint64_t np = pc.get_local_num_particles();
+    FILE* f = std::fopen((dir + "/particles.bin").c_str(), "wb");
+    std::fwrite(&np, sizeof(np), 1, f);
+    std::fwrite(pc.get_pos64_ptr(), sizeof(double), 3 * np, f);
+    std::fwrite(pc.get_vel64_ptr(), sizeof(double), 3 * np, f);
+    std::fwrite(pc.get_mass64_ptr(), sizeof(double), np, f);
+    std::fwrite(pc.get_ids64_ptr(), sizeof(uint64_t), np, f);
+    std::fclose(f);
+    std::printf("ref_driver particles ok\n");
+    return 0;
+}
+#endif
+
 int main(int argc, char** argv) {
+#if defined(USE_MPI)
+    if (argc > 1 && std::string(argv[1]) == "particles") return run_particles(argc, argv);
+#endif
     if (argc < 7) { std::printf("usage: ref_driver n boxlen Dplus0 phi_k.bin psi_k.bin outdir\n"); return 1; }
     const size_t n = std::strtoul(argv[1], nullptr, 10);
     const real_t L = std::atof(argv[2]), D = std::atof(argv[3]);

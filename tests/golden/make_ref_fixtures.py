@@ -84,6 +84,25 @@ def run_reference(phi, psi, n=N, extra=None, mpi=False):
     return out
 
 
+def run_reference_particles(phi, psi, lattice_type, lattice_index, zero_field=False, n=N):
+    """the reference's particle::lattice_generator (MPI build, one rank): positions from phi, velocities from psi, masses
+    from phi (munit 2.5), 64-bit reals and ids, IDoffset = lattice_index.  -> dict(pos, vel, mass, ids)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_mpi")
+    with tempfile.TemporaryDirectory() as d:
+        np.ascontiguousarray(phi, np.complex128).tofile(os.path.join(d, "phi.bin"))
+        np.ascontiguousarray(psi, np.complex128).tofile(os.path.join(d, "psi.bin"))
+        r = subprocess.run([exe, "particles", str(n), repr(L), os.path.join(d, "phi.bin"), os.path.join(d, "psi.bin"), d,
+                            str(lattice_type), str(lattice_index), "1" if zero_field else "0"], capture_output=True, text=True)
+        assert r.returncode == 0 and "particles ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        raw = np.fromfile(os.path.join(d, "particles.bin"), np.uint8)
+    npart = int(raw[:8].view(np.uint64)[0])
+    b = raw[8:]
+    return {"pos": b[:24 * npart].view(np.float64).reshape(npart, 3).copy(),
+            "vel": b[24 * npart:48 * npart].view(np.float64).reshape(npart, 3).copy(),
+            "mass": b[48 * npart:56 * npart].view(np.float64).copy(),
+            "ids": b[56 * npart:64 * npart].view(np.uint64).copy()}
+
+
 def main():
     g, phi, psi = inputs()
     a, b, c = nyquist_inputs()
@@ -103,6 +122,18 @@ def main():
     for k in KNAMES + RNAMES:
         assert np.abs(Rf[k] - out[k]).max() <= 1e-13 * np.abs(out[k]).max(), k
     out["meta"] = np.array([N, L, DPLUS])
+    # particle::lattice_generator of the reference: ids and bare-lattice positions as SHA-256 digests (bit-exact quantities),
+    # displaced positions / velocities / masses on every 101st particle
+    import hashlib
+    for lt, nm in enumerate(("sc", "bcc", "fcc", "rsc")):
+        for li in (0, 1):
+            Z = run_reference_particles(phi, psi, lt, li, zero_field=True)
+            out[f"part_{nm}{li}_ids_sha256"] = np.frombuffer(hashlib.sha256(Z["ids"].tobytes()).digest(), np.uint8)
+            out[f"part_{nm}{li}_lattice_sha256"] = np.frombuffer(hashlib.sha256(Z["pos"].tobytes()).digest(), np.uint8)
+            P = run_reference_particles(phi, psi, lt, li)
+            assert np.array_equal(P["ids"], Z["ids"])
+            for k in ("pos", "vel", "mass"):
+                out[f"part_{nm}{li}_{k}_sub"] = P[k][::101].copy()
     path = os.path.join(HERE, "ref_intermediates_32.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KB,", len(out), "arrays")

@@ -330,6 +330,43 @@ def check_reference_fixture(M):
         lib.mfb_set_option(b"conv_grouping", 1)
 
 
+def check_reference_particles(M):
+    """the particle read-out against the reference's own particle::lattice_generator (fixture digests and subsamples):
+    ids and bare-lattice positions bit-exact, displaced positions / velocities / masses to 1e-12, every Bravais lattice
+    and both lattice indices"""
+    import hashlib
+
+    R = load_reference_fixture()
+    n, L = int(R["meta"][0]), float(R["meta"][1])
+    N3, L3 = (n,) * 3, (L,) * 3
+    F = M.Grid_FFT(N3, L3)
+    for lt, nm in enumerate(("sc", "bcc", "fcc", "rsc")):
+        for li in (0, 1):
+            parts = M.Particles(nm, li, True, True, True, li, F)
+            for zero in (True, False):
+                for d in range(3):
+                    F.set_kspace(R["phi_in"])
+                    if zero:
+                        F.zero()
+                    F.FourierTransformBackward()
+                    parts.set_positions(d, L, F)
+                if zero:
+                    got = parts.download(vel=False, mass=False)
+                    assert hashlib.sha256(got["ids"].tobytes()).digest() == R[f"part_{nm}{li}_ids_sha256"].tobytes(), (nm, li)
+                    assert hashlib.sha256(got["pos"].tobytes()).digest() == R[f"part_{nm}{li}_lattice_sha256"].tobytes(), (nm, li)
+            for d in range(3):
+                F.set_kspace(R["psi_in"])
+                F.FourierTransformBackward()
+                parts.set_velocities(d, F)
+            F.set_kspace(R["phi_in"])
+            F.FourierTransformBackward()
+            parts.set_masses(2.5, F)
+            got = parts.download()
+            assert np.abs(got["pos"][::101] - R[f"part_{nm}{li}_pos_sub"]).max() < 1e-12 * L, (nm, li)
+            assert relerr(got["vel"][::101], R[f"part_{nm}{li}_vel_sub"]) < 1e-12, (nm, li)
+            assert relerr(got["mass"][::101], R[f"part_{nm}{li}_mass_sub"]) < 1e-12, (nm, li)
+
+
 # ------------------------------------------------------------------ two-fluid terms, tides, density, masses
 def check_two_fluid_terms(M, n=32, lattice="bcc"):
     """the operators a CDM+baryon run adds (config C4) with NON-degenerate two-fluid amplitudes (the goldens use

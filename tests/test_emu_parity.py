@@ -119,3 +119,7 @@ def test_two_fluid_terms(M):
 
 def test_against_reference_produced_fixture(M):
     PC.check_reference_fixture(M)
+
+
+def test_particles_against_reference_produced_fixture(M):
+    PC.check_reference_particles(M)

@@ -77,6 +77,10 @@ def test_against_reference_produced_fixture(M):
     PC.check_reference_fixture(M)
 
 
+def test_particles_against_reference_produced_fixture(M):
+    PC.check_reference_particles(M)
+
+
 def test_naive_pipeline(M):
     PC.check_naive_pipeline(M, 64)
 

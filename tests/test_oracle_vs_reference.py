@@ -80,6 +80,35 @@ def compare_mpi_nyquist(R, a, b, n, L, D, prefix=""):
     assert rel(pots["A3"][0], R[prefix + "A3x"]) < 100 * TOL
 
 
+def oracle_particles(g, phi, psi, lt, li, zero=False):
+    x, v = g.bwd(phi), g.bwd(psi)
+    if zero:
+        x, v = np.zeros_like(x), np.zeros_like(v)
+    return {"ids": O.particle_ids(g.n, lt, li, True),
+            "pos": np.stack([O.set_positions(g, x, d, lt, li, g.L, True) for d in range(3)], 1),
+            "vel": np.stack([O.set_velocities(g, v, lt, li, True) for d in range(3)], 1),
+            "mass": O.set_masses(g, x, lt, li, 2.5, True)}
+
+
+def test_oracle_particles_match_committed_reference_fixture():
+    """particle::lattice_generator of the reference (MPI build): ids and bare-lattice positions bit-exact (digests),
+    displaced positions / velocities / masses on every 101st particle, all four Bravais lattices, both lattice indices"""
+    import hashlib
+
+    R = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
+    n, L = int(R["meta"][0]), float(R["meta"][1])
+    g = O.GridSpec(n, L)
+    for lt, nm in enumerate(("sc", "bcc", "fcc", "rsc")):
+        for li in (0, 1):
+            Z = oracle_particles(g, R["phi_in"], R["psi_in"], lt, li, zero=True)
+            assert hashlib.sha256(Z["ids"].tobytes()).digest() == R[f"part_{nm}{li}_ids_sha256"].tobytes()
+            assert hashlib.sha256(Z["pos"].tobytes()).digest() == R[f"part_{nm}{li}_lattice_sha256"].tobytes()
+            P = oracle_particles(g, R["phi_in"], R["psi_in"], lt, li)
+            assert np.abs(P["pos"][::101] - R[f"part_{nm}{li}_pos_sub"]).max() < 1e-13 * L
+            assert rel(P["vel"][::101], R[f"part_{nm}{li}_vel_sub"]) < TOL
+            assert rel(P["mass"][::101], R[f"part_{nm}{li}_mass_sub"]) < TOL
+
+
 def test_oracle_matches_committed_reference_fixture():
     R = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
     compare(R, R["phi_in"], R["psi_in"], int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2]))
@@ -111,3 +140,12 @@ def test_oracle_matches_reference_built_here():
     Rn = F.run_reference(a, b, n, mpi=True)
     compare(Rn, a, b, n, F.L, F.DPLUS)
     compare_mpi_nyquist(Rn, a, b, n, F.L, F.DPLUS)
+    # the reference's particle::lattice_generator, live, on these fresh fields: two of the eight lattice configurations
+    for lt, li in ((2, 1), (3, 0)):
+        P = F.run_reference_particles(phi, psi, lt, li, n=n)
+        Q = oracle_particles(g, phi, psi, lt, li)
+        assert np.array_equal(P["ids"], Q["ids"])
+        assert np.abs(P["pos"] - Q["pos"]).max() < 1e-13 * F.L
+        assert rel(Q["vel"], P["vel"]) < TOL and rel(Q["mass"], P["mass"]) < TOL
+        Z = F.run_reference_particles(phi, psi, lt, li, zero_field=True, n=n)
+        assert np.array_equal(Z["pos"], oracle_particles(g, phi, psi, lt, li, zero=True)["pos"])

@@ -187,7 +187,7 @@ def run_b200(args):
         from monofonic_b200 import dist as MD
 
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-        lib = MD.init(local_rank, n, order > 1, staged=args.staged_exchange)
+        lib = MD.init(local_rank, n, order > 1, staged=args.staged_exchange, lpt_order=order)
     else:
         lib = M.init(local_rank)
 
@@ -332,9 +332,10 @@ def run_b200(args):
 
     # the reference does 33 products (each with its own forward transform) at 3LPT, 5 at 2LPT; with the accumulator
     # workspace the library sums the products of one target first
-    grouped = bool(pl.conv is not None and pl.conv.grouped())
+    sinfo = pl.conv.sources_info() if pl.conv is not None else {"path": 0}
+    grouped = bool(pl.conv is not None and (sinfo["path"] == 2 or pl.conv.grouped()))
     nprod = {1: 0, 2: 5, 3: 32 if grouped else 33}[order]
-    nfwd = {1: 0, 2: 1 if grouped else 5, 3: 9 if grouped else 33}[order]
+    nfwd = {1: 0, 2: 1 if grouped else 5, 3: (10 if sinfo["path"] == 2 else 9) if grouped else 33}[order]
     if dist is not None:
         from monofonic_b200 import dist as MD
 
@@ -352,6 +353,8 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (every grid >= 1 GB; no flush needed)",
                        "products_per_step": nprod, "forward_transforms_per_step": nfwd,
                        "product_grouping": grouped,
+                       "source_stage": ({"path": "shared x passes + x-plane chunks + multi-product z pass", **sinfo}
+                                        if sinfo["path"] == 2 else {"path": "per product", **sinfo}),
                        "decomposition": (f"{world} x-slabs (real) / ky-slabs (k-space, transposed), exchange fused into the "
                                          f"FFT passes over peer memory, {nex // (max(3, args.warmup) + args.steps + 3)} exchanges/step"
                                          if world > 1 else "single slab")},

@@ -65,12 +65,18 @@ int mfb_profile_get(int role, double* ms, long long* count, double* algorithmic_
    (any transport: torch.distributed, MPI_Allgather, ...). */
 size_t mfb_dist_xbuf_bytes(const int n[3], int with_conv, int nranks); /* exchange-buffer size for grids up to n */
 int mfb_dist_init(int rank, int nranks, size_t xbuf_bytes, void* ipc_handle_out /* 64 bytes */);
+/* the same with `nslots` exchange buffers in the peer-mapped block (2..18; mfb_dist_init == 2, the ping-pong pair of the 3-D
+   FFTs).  With >= 2 + 7 (3LPT; 2 + 4 at 2LPT) mfb_lpt_sources keeps the x-transformed spectra of its source potentials
+   resident in the extra buffers: 10 exchanges per 3LPT step instead of 49 + 9. */
+int mfb_dist_init_slots(int rank, int nranks, size_t xbuf_bytes, int nslots, void* ipc_handle_out /* 64 bytes */);
 int mfb_dist_connect(const void* all_handles /* nranks x 64 bytes, rank order */);
 /* the same slab algorithm with the exchange done by a host collective instead of peer stores (CPU tests over
    gloo; NCCL all-to-all baseline).  cb(send, recv, chunk_bytes, user): chunk s of send -> rank s; chunk r of
    recv <- rank r. */
 typedef void (*mfb_exchange_fn)(const void* send, void* recv, size_t chunk_bytes, void* user);
 int mfb_dist_init_staged(int rank, int nranks, size_t xbuf_bytes, mfb_exchange_fn cb, void* user);
+int mfb_dist_init_staged_slots(int rank, int nranks, size_t xbuf_bytes, int nslots, mfb_exchange_fn cb, void* user);
+int mfb_dist_nslots(void);                /* exchange buffers in the block (0: no slab decomposition) */
 int mfb_dist_shutdown(void);
 int mfb_dist_rank(void);
 int mfb_dist_nranks(void);
@@ -160,6 +166,11 @@ int mfb_conv_grouped(const mfb_conv* c);
    a particle container as accumulator: they hold nothing while the sources are computed (src/ic_generator.cc:475-574 runs
    before the species loop :832-955).  p == NULL returns the loan.  The caller keeps `p` alive while the loan lasts. */
 int mfb_conv_borrow_accumulator(mfb_conv* c, mfb_particles* p);
+/* Which path the last mfb_lpt_sources call took.  1: one padded transform pair per product (OrszagConvolver::convolve2,
+   include/convolution.hh:512-535, grouped per target when an accumulator exists).  2: shared x passes + x-plane chunks +
+   multi-product z pass (needs >= 7 [2LPT: 4] slots of 1.5 R(N) each, own HBM plus lent particle arrays).
+   info = {slots, x-plane loops, backward x passes, backward y passes, z launches, 0}. */
+int mfb_conv_sources_info(const mfb_conv* c, long long info[6]);
 /* All products: inputs are k-space N-grids, `out` is a k-space N-grid updated with `op` (alpha for MULADD).
    dims are axis pairs {a,b}: the operand is (i k_a)(i k_b) f^ with the gradient zeroed at Nyquist. */
 int mfb_conv_hessians(mfb_conv* c, mfb_grid* l, const int d2l[2], mfb_grid* r, const int d2r[2],

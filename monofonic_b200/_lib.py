@@ -39,7 +39,10 @@ def _declare(lib):
         "mfb_profile_get": (i, [i, dp, C.POINTER(C.c_longlong), dp]),
         "mfb_dist_xbuf_bytes": (sz, [ip, i, i]),
         "mfb_dist_init": (i, [i, i, sz, vp]),
+        "mfb_dist_init_slots": (i, [i, i, sz, i, vp]),
         "mfb_dist_connect": (i, [vp]),
+        "mfb_dist_init_staged_slots": (i, [i, i, sz, i, EXCHANGE_FN, vp]),
+        "mfb_dist_nslots": (i, []),
         "mfb_dist_init_staged": (i, [i, i, sz, EXCHANGE_FN, vp]),
         "mfb_dist_shutdown": (i, []),
         "mfb_dist_rank": (i, []),
@@ -97,6 +100,7 @@ def _declare(lib):
         "mfb_conv_workspace_bytes": (sz, [vp]),
         "mfb_conv_grouped": (i, [vp]),
         "mfb_conv_borrow_accumulator": (i, [vp, vp]),
+        "mfb_conv_sources_info": (i, [vp, C.POINTER(C.c_longlong)]),
         "mfb_conv_hessians": (i, [vp, vp, ip, vp, ip, vp, i, d]),
         "mfb_conv_hessians3": (i, [vp, vp, ip, vp, ip, vp, ip, vp, i, d]),
         "mfb_conv_sum_hessians": (i, [vp, vp, ip, vp, ip, ip, vp, i, d]),

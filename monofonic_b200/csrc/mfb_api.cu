@@ -15,6 +15,7 @@
 #include "fft_kernels.cuh"
 #include "fft_kernels2.cuh"
 #include "fft_kernels_z2.cuh"
+#include "fft_kernels_zm.cuh"
 #include "grid_ops.cuh"
 #include "mfb_internal.h"
 #include "../../include/mfb200.h"
@@ -813,6 +814,16 @@ static void conv_acquire_accumulator(mfb_conv* c) {
         }
     }
 }
+// lent particle memory in any role (accumulator, slots, chunk workspace)
+static void conv_wait_lender(mfb_conv* c) {
+    if (!c->lender) return;
+    for (int at : {MFB_ATTR_POS, MFB_ATTR_VEL}) {
+        if (c->lender->copy_pending[at]) {
+            cuda_check(cudaStreamWaitEvent(g_ctx.stream, c->lender->copied[at], 0), "cudaStreamWaitEvent");
+            c->lender->copy_pending[at] = false;
+        }
+    }
+}
 static mfb_operand_key operand_key(const Operand& o) {
     // (a,b) and (b,a) name the same Hessian: store the axis pairs sorted
     mfb_operand_key k;
@@ -931,10 +942,12 @@ struct ConvGroup {
     }
 };
 static bool can_group(const mfb_conv* c) { return !c->naive && c->Wacc != nullptr && g_ctx.conv_grouping; }
+static void conv_legacy_ensure(mfb_conv* c);   // mfb_sources2.cuh: the per-product workspace is in place (not the slot workspace)
 
 void conv2(mfb_conv* c, const Operand& A, const Operand& B, mfb_grid* out, int op, double alpha) {
     require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
     if (c->naive) { naive_conv(c, A, B, nullptr, out, op, alpha); return; }
+    conv_legacy_ensure(c);
     c->cache_on = false;
     ConvGroup g(c);
     g.add(A, B, 1.0);
@@ -948,15 +961,23 @@ static Operand hessian_operand(mfb_grid* g, const int d[2]) { return Operand{g, 
 void conv3(mfb_conv* c, const Operand& A, const Operand& B, const Operand& C3, mfb_grid* out, int op, double alpha) {
     require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
     if (c->naive) { naive_conv(c, A, B, &C3, out, op, alpha); return; }
+    conv_legacy_ensure(c);
     to_kspace(C3.g);
     c->fbuf->space = MFB_KSPACE;
     conv2(c, A, B, c->fbuf, OP_ASSIGN, 0.0);
     conv2(c, Operand{c->fbuf, -1, -1, -1, -1, 1.0, 0.0, 0}, C3, out, op, alpha);
 }
 
+}  // namespace mfb
+#include "mfb_sources2.cuh"
+namespace mfb {
+
 void lpt_sources(mfb_conv* c, int order, double D, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3, mfb_grid* const A3[3],
                  const double* lam) {
     require(phi->space == MFB_KSPACE, "phi must be in k-space");
+    if (lpt_sources_v2(c, order, D, phi, phi2, phi3, A3, lam)) return;
+    conv_legacy_ensure(c);
+    c->last_path = 1; c->last_slots = 0; c->last_loops = 0; c->last_xpass = c->last_ypass = c->last_zlaunch = 0;
     const double g1 = -D;
     const double g2 = (order > 1) ? -3.0 / 7.0 * D * D : 0.0;
     const double g3 = (order > 2) ? 1.0 / 3.0 * D * D * D : 0.0;
@@ -1212,6 +1233,9 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "conv_grouping") g_ctx.conv_grouping = value != 0;
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
+    else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
+    else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
+    else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)
     else throw std::runtime_error(std::string("unknown option ") + name);
     MFB_CATCH
 }
@@ -1258,25 +1282,28 @@ static void dist_layout_block(size_t xbuf_bytes) {
     DistState& d = D();
     char* b = (char*)d.block;
     d.xbuf_elems = xbuf_bytes / sizeof(double2);
-    d.xbuf[0] = (double2*)b;
-    d.xbuf[1] = (double2*)(b + xbuf_bytes);
-    d.flags = (unsigned long long*)(b + 2 * xbuf_bytes);
-    d.err = (int*)(b + 2 * xbuf_bytes + 256);
+    for (int k = 0; k < d.nxbuf; ++k) d.xbuf[k] = (double2*)(b + size_t(k) * xbuf_bytes);
+    d.flags = (unsigned long long*)(b + size_t(d.nxbuf) * xbuf_bytes);
+    d.err = (int*)(b + size_t(d.nxbuf) * xbuf_bytes + 256);
 }
-int mfb_dist_init(int rank, int nranks, size_t xbuf_bytes, void* ipc_handle_out) {
+// nslots: exchange buffers in the peer-mapped block.  2 = the ping-pong pair of the 3-D FFTs (all the per-product
+// convolver needs); more (up to 2 + MFB_CONV_MAX_SLOTS) let the v2 source stage keep x-transformed spectra resident.
+int mfb_dist_init_slots(int rank, int nranks, size_t xbuf_bytes, int nslots, void* ipc_handle_out) {
     MFB_TRY
     require(g_ctx.initialised, "mfb_init has not been called");
     require(!D().ready, "mfb_dist_init: already initialised");
     require(nranks >= 1 && nranks <= MFB_MAX_RANKS && rank >= 0 && rank < nranks, "mfb_dist_init: bad rank / world size (max 8)");
     require(xbuf_bytes % 256 == 0, "mfb_dist_init: xbuf_bytes must come from mfb_dist_xbuf_bytes");
+    require(nslots >= 2 && nslots <= MFB_MAX_XBUF, "mfb_dist_init: 2..18 exchange buffers");
 #ifdef MFB_EMU
+    (void)ipc_handle_out;
     throw std::runtime_error("peer-mapped exchange is not available in the emulation build; use mfb_dist_init_staged");
 #else
     DistState& d = D();
-    d.rank = rank; d.nranks = nranks; d.staged = false;
-    const size_t total = 2 * xbuf_bytes + 4096;
+    d.rank = rank; d.nranks = nranks; d.staged = false; d.nxbuf = nslots;
+    const size_t total = size_t(nslots) * xbuf_bytes + 4096;
     d.block = dev_alloc(total);
-    cuda_check(cudaMemset(d.block, 0, total), "memset exchange block");
+    cuda_check(cudaMemset((char*)d.block + size_t(nslots) * xbuf_bytes, 0, 4096), "memset exchange flags");
     dist_layout_block(xbuf_bytes);
     cudaIpcMemHandle_t h;
     cuda_check(cudaIpcGetMemHandle(&h, d.block), "cudaIpcGetMemHandle");
@@ -1284,6 +1311,9 @@ int mfb_dist_init(int rank, int nranks, size_t xbuf_bytes, void* ipc_handle_out)
     memcpy(ipc_handle_out, &h, sizeof(h));
 #endif
     MFB_CATCH
+}
+int mfb_dist_init(int rank, int nranks, size_t xbuf_bytes, void* ipc_handle_out) {
+    return mfb_dist_init_slots(rank, nranks, xbuf_bytes, 2, ipc_handle_out);
 }
 int mfb_dist_connect(const void* all_handles) {
     MFB_TRY
@@ -1302,30 +1332,34 @@ int mfb_dist_connect(const void* all_handles) {
             cuda_check(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer exchange buffer)");
             d.peer_block[s] = base;
         }
-        d.peer_xbuf[0][s] = (double2*)base;
-        d.peer_xbuf[1][s] = (double2*)((char*)base + xb);
-        d.peer_flags[s] = (unsigned long long*)((char*)base + 2 * xb);
+        for (int k = 0; k < d.nxbuf; ++k) d.peer_xbuf[k][s] = (double2*)((char*)base + size_t(k) * xb);
+        d.peer_flags[s] = (unsigned long long*)((char*)base + size_t(d.nxbuf) * xb);
     }
     d.ready = true;
 #endif
     MFB_CATCH
 }
-int mfb_dist_init_staged(int rank, int nranks, size_t xbuf_bytes, mfb_exchange_fn cb, void* user) {
+int mfb_dist_init_staged_slots(int rank, int nranks, size_t xbuf_bytes, int nslots, mfb_exchange_fn cb, void* user) {
     MFB_TRY
     require(g_ctx.initialised, "mfb_init has not been called");
     require(!D().ready, "mfb_dist_init_staged: already initialised");
     require(nranks >= 1 && nranks <= MFB_MAX_RANKS && rank >= 0 && rank < nranks, "mfb_dist_init_staged: bad rank / world size (max 8)");
     require(cb != nullptr, "mfb_dist_init_staged: exchange callback required");
+    require(nslots >= 2 && nslots <= MFB_MAX_XBUF, "mfb_dist_init_staged: 2..18 exchange buffers");
     DistState& d = D();
-    d.rank = rank; d.nranks = nranks; d.staged = true; d.cb = cb; d.cb_user = user;
-    const size_t total = 2 * xbuf_bytes + 4096;
+    d.rank = rank; d.nranks = nranks; d.staged = true; d.cb = cb; d.cb_user = user; d.nxbuf = nslots;
+    const size_t total = size_t(nslots) * xbuf_bytes + 4096;
     d.block = dev_alloc(total);
-    cuda_check(cudaMemset(d.block, 0, total), "memset exchange block");
+    cuda_check(cudaMemset((char*)d.block + size_t(nslots) * xbuf_bytes, 0, 4096), "memset exchange flags");
     dist_layout_block(xbuf_bytes);
-    d.sendbuf = (double2*)dev_alloc(xbuf_bytes);
+    d.sendbuf = (double2*)dev_alloc(size_t(nslots) * xbuf_bytes);   // one staging buffer per exchange buffer
     d.ready = true;
     MFB_CATCH
 }
+int mfb_dist_init_staged(int rank, int nranks, size_t xbuf_bytes, mfb_exchange_fn cb, void* user) {
+    return mfb_dist_init_staged_slots(rank, nranks, xbuf_bytes, 2, cb, user);
+}
+int mfb_dist_nslots(void) { return D().ready ? D().nxbuf : 0; }
 int mfb_dist_shutdown(void) {
     MFB_TRY
     DistState& d = D();
@@ -1754,29 +1788,12 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
     }
     c->w1_elems = c->dist ? 0 : size_t(c->np[0]) * n[1] * nzin;   // slab mode: the exchange buffers play W1's role
     c->w2_elems = size_t(c->p0loc) * c->np[1] * nzin;
-    try {
-        c->W1 = c->dist ? nullptr : (double2*)dev_alloc(c->w1_elems * sizeof(double2));
-        c->W2a = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
-        c->W2b = (double2*)dev_alloc(c->w2_elems * sizeof(double2));
-        if (mfb_grid_create(&c->fbuf, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
-    } catch (...) {   // out of HBM part-way: release what was taken
-        if (c->W1) cudaFree(c->W1);
-        if (c->W2a) cudaFree(c->W2a);
-        if (c->W2b) cudaFree(c->W2b);
-        delete c;
-        throw;
-    }
     c->naive = 0; c->nb1 = c->nb2 = nullptr;
-    // the accumulator of product groups is an optimisation, not a requirement: take it only if HBM is plentiful after it
-    // (room for the particle arrays and the remaining grids of a 3LPT run: 3.75 R(N) of this slab)
     c->Wacc = nullptr; c->acc_borrowed = false; c->lender = nullptr;
-    {
-        size_t free_b = 0, total_b = 0;
-        cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-        const size_t w2_bytes = c->w2_elems * sizeof(double2);
-        const size_t reserve = size_t(3.75 * double(c->fbuf->ntot) * sizeof(double));
-        if (g_ctx.conv_own_accumulator && free_b > w2_bytes + reserve) c->Wacc = (double2*)dev_alloc(w2_bytes);
-    }
+    c->mode = 0; c->nxs = 0; c->chunk = nullptr; c->chunk_elems = 0; c->chunk_owned = 0;
+    c->W1 = c->W2a = c->W2b = nullptr; c->fbuf = nullptr; c->legacy_ready = 0;
+    // no workspace yet: it is carved at the first use, for the path that use takes - the slot workspace of the v2 source
+    // stage (mfb_sources2.cuh) or the per-product buffers W1, W2a, W2b, fbuf[, Wacc] (conv_legacy_ensure)
     *out = c;
     MFB_CATCH
 }
@@ -1785,7 +1802,6 @@ int mfb_conv_create_naive(mfb_conv** out, const int n[3], const double L[3]) {
     require(g_ctx.initialised, "mfb_init has not been called");
     require(!dist_on(), "the NaiveConvolver is only available on a single slab");
     mfb_conv* c = new mfb_conv();
-    memset(c, 0, sizeof(*c));
     for (int d = 0; d < 3; ++d) {
         c->n[d] = n[d]; c->L[d] = L[d]; c->np[d] = n[d];
         require(supported_size(n[d]), "unsupported grid size for the convolver");
@@ -1798,7 +1814,9 @@ int mfb_conv_create_naive(mfb_conv** out, const int n[3], const double L[3]) {
 int mfb_conv_destroy(mfb_conv* c) {
     MFB_TRY
     if (c) {
-        if (c->acc_borrowed && c->lender) c->lender->borrower = nullptr;
+        if (c->lender) c->lender->borrower = nullptr;
+        if (g_ctx.initialised) cudaStreamSynchronize(g_ctx.stream);
+        conv_free_slots(c);
         if (c->W1) cudaFree(c->W1);
         if (c->W2a) cudaFree(c->W2a);
         if (c->W2b) cudaFree(c->W2b);
@@ -1812,27 +1830,53 @@ int mfb_conv_destroy(mfb_conv* c) {
 }
 size_t mfb_conv_workspace_bytes(const mfb_conv* c) {
     if (c->naive) return (c->nb1->ntot + c->nb2->ntot) * sizeof(double);
-    return (c->w1_elems + (c->Wacc ? 3 : 2) * c->w2_elems) * sizeof(double2) + c->fbuf->ntot * sizeof(double);
+    if (c->mode == 1) {   // slot workspace of the v2 source stage: own slots (incl. W1) + own chunk workspace
+        size_t b = 0;
+        for (int i = 0; i < c->nxs; ++i) if (c->xs[i].owned || c->xs[i].p == c->W1) b += conv_slot_elems(c) * sizeof(double2);
+        return b + (c->chunk_owned ? c->chunk_elems * sizeof(double2) : 0);
+    }
+    return ((c->W1 ? c->w1_elems : 0) + ((c->W2a ? 1 : 0) + (c->W2b ? 1 : 0) + ((c->Wacc && !c->acc_borrowed) ? 1 : 0)) * c->w2_elems) * sizeof(double2) +
+           (c->fbuf ? c->fbuf->ntot * sizeof(double) : 0);
 }
-int mfb_conv_grouped(const mfb_conv* c) { return can_group(c) ? 1 : 0; }
+int mfb_conv_grouped(const mfb_conv* cc) {
+    mfb_conv* c = const_cast<mfb_conv*>(cc);
+    if (!c->naive && c->mode == 0 && !c->legacy_ready) {   // answer for the per-product workspace: carve it
+        try { conv_legacy_ensure(c); } catch (const std::exception& e) { set_error(e.what()); return 0; }
+    }
+    return can_group(c) ? 1 : 0;
+}
+/* Lend the (idle) position/velocity arrays of a particle container to the convolver: the per-product path uses them as the
+   accumulator of product groups when it has none of its own, the v2 source stage as slots / chunk workspace.  p == NULL
+   ends the loan. */
 int mfb_conv_borrow_accumulator(mfb_conv* c, mfb_particles* p) {
     MFB_TRY
     require(!c->naive, "the NaiveConvolver has no accumulator");
-    if (p == nullptr) {   // give it back
-        if (c->acc_borrowed) {
-            if (c->lender) c->lender->borrower = nullptr;
-            c->Wacc = nullptr; c->acc_borrowed = false; c->lender = nullptr;
-        }
-        return 0;
+    if (p == c->lender) return 0;
+    // whatever the workspace looks like now, it may sit in the old lender's memory: drop the loan first
+    if (c->lender) {
+        cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+        if (c->mode == 1) { conv_free_slots(c); c->mode = 0; }
+        if (c->acc_borrowed) { c->Wacc = nullptr; c->acc_borrowed = false; }
+        c->lender->borrower = nullptr;
+        c->lender = nullptr;
     }
-    if (c->Wacc != nullptr) return 0;   // already has one (its own, or borrowed)
-    require(p->posvel_bytes >= c->w2_elems * sizeof(double2), "particle arrays are too small to serve as the accumulator");
+    if (p == nullptr) return 0;
     require(p->borrower == nullptr, "these particle arrays are already lent to another convolver");
-    c->Wacc = (double2*)p->pos;
-    c->acc_borrowed = true;
+    if (c->mode == 1) { cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync"); conv_free_slots(c); c->mode = 0; }   // re-carved with the loan at the next use
     c->lender = p;
     p->borrower = c;
+    if (c->mode == 0 && c->Wacc == nullptr && c->W2a != nullptr && p->posvel_bytes >= c->w2_elems * sizeof(double2)) {
+        c->Wacc = (double2*)p->pos;
+        c->acc_borrowed = true;
+    }
     MFB_CATCH
+}
+/* which path the last mfb_lpt_sources call took: 1 = per-product (ConvGroup), 2 = shared x passes + multi-product z pass;
+   info[0..5] = slots, x-plane loops, x passes, backward y passes, z launches, x planes per chunk (0 if not applicable) */
+int mfb_conv_sources_info(const mfb_conv* c, long long info[6]) {
+    info[0] = c->last_slots; info[1] = c->last_loops; info[2] = c->last_xpass; info[3] = c->last_ypass; info[4] = c->last_zlaunch;
+    info[5] = 0;
+    return c->last_path;
 }
 static void check_conv_grids(mfb_conv* c, mfb_grid* a, mfb_grid* b, mfb_grid* o) {
     for (mfb_grid* g : {a, b, o})
@@ -1933,9 +1977,12 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
 int mfb_particles_destroy(mfb_particles* p) {
     MFB_TRY
     if (p) {
-        if (p->borrower) {   // the loan ends with the lender: the convolver falls back to ungrouped products
+        if (p->borrower) {   // the loan ends with the lender: the convolver falls back to what it owns
             cudaStreamSynchronize(g_ctx.stream);
-            p->borrower->Wacc = nullptr; p->borrower->acc_borrowed = false; p->borrower->lender = nullptr;
+            mfb_conv* b = p->borrower;
+            if (b->mode == 1) { conv_free_slots(b); b->mode = 0; }
+            if (b->acc_borrowed) { b->Wacc = nullptr; b->acc_borrowed = false; }
+            b->lender = nullptr;
         }
         if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
         for (int a = 0; a < 4; ++a) if (p->copied[a]) cudaEventDestroy(p->copied[a]);

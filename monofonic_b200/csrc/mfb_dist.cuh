@@ -20,6 +20,7 @@ namespace mfb {
 struct Exchange {
     double2* recv;                   // where this rank finds the received data: [src rank][chunk]
     double2* base[MFB_MAX_RANKS];    // where to write the chunk destined to rank s
+    double2* send;                   // staged mode: the staging buffer the chunks were written to
     size_t chunk;                    // complex elements per (src,dst) pair
 };
 
@@ -54,11 +55,30 @@ inline Exchange begin_exchange(size_t chunk_elems) {
     require(chunk_elems * size_t(d.nranks) <= d.xbuf_elems, "exchange buffer too small for this grid (mfb_dist_xbuf_bytes)");
     Exchange x;
     const int e = int(d.nexch & 1);
-    x.recv = d.xbuf[e];
+    x.recv = d.xbuf[e];   // buffers 0 and 1 ping-pong
     x.chunk = chunk_elems;
+    x.send = d.staged ? d.sendbuf + size_t(e) * d.xbuf_elems : nullptr;
     for (int s = 0; s < MFB_MAX_RANKS; ++s) x.base[s] = nullptr;
     for (int s = 0; s < d.nranks; ++s)
-        x.base[s] = d.staged ? d.sendbuf + size_t(s) * chunk_elems : d.peer_xbuf[e][s] + size_t(d.rank) * chunk_elems;
+        x.base[s] = d.staged ? x.send + size_t(s) * chunk_elems : d.peer_xbuf[e][s] + size_t(d.rank) * chunk_elems;
+    return x;
+}
+
+// Exchange into a NAMED buffer of the block (k >= 2: the slots the v2 source stage keeps x-transformed spectra and
+// target intermediates in).  The caller orders reuse: between the last read of a slot and the next peer write into it at
+// least one barrier must lie in program order (mfb_sources2.cuh does that with one barrier per x-plane loop).
+inline Exchange slot_exchange(int k, size_t chunk_elems) {
+    DistState& d = D();
+    require(d.ready, "distributed layer not initialised (mfb_dist_init)");
+    require(k >= 0 && k < d.nxbuf, "internal: exchange slot out of range");
+    require(chunk_elems * size_t(d.nranks) <= d.xbuf_elems, "exchange buffer too small for this grid (mfb_dist_xbuf_bytes)");
+    Exchange x;
+    x.recv = d.xbuf[k];
+    x.chunk = chunk_elems;
+    x.send = d.staged ? d.sendbuf + size_t(k) * d.xbuf_elems : nullptr;   // staged mode: one staging buffer per slot
+    for (int s = 0; s < MFB_MAX_RANKS; ++s) x.base[s] = nullptr;
+    for (int s = 0; s < d.nranks; ++s)
+        x.base[s] = d.staged ? x.send + size_t(s) * chunk_elems : d.peer_xbuf[k][s] + size_t(d.rank) * chunk_elems;
     return x;
 }
 
@@ -69,7 +89,7 @@ inline void end_exchange(const Exchange& x) {
     DistState& d = D();
     if (d.staged) {
         cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync before host exchange");
-        d.cb(d.sendbuf, x.recv, x.chunk * sizeof(double2), d.cb_user);
+        d.cb(x.send, x.recv, x.chunk * sizeof(double2), d.cb_user);
     } else {
 #ifndef MFB_EMU
         ++d.epoch;

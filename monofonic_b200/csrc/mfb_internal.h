@@ -36,6 +36,18 @@ struct mfb_operand_key {
     const void* g; int a1, b1, a2, b2; double c1, c2; int imag, keep_nyq; bool valid;
 };
 
+// one U-sized buffer ([P0loc][N1][N2/2] complex) of the slot workspace of the v2 source stage (mfb_sources2.cuh): holds the
+// x-transformed spectrum k_x^mx f^ of a source potential ("X buffer", cached by (grid, mx)) or the y-forward output of a target
+struct mfb_conv_slot {
+    double2* p;
+    int owned;          // allocated by the convolver (else: lent particle memory, W1, or a peer-mapped exchange slot)
+    int xslot;          // slab mode: index of the exchange slot behind it (-1: none)
+    const void* g; int mx; int valid;   // cached X buffer
+    int pinned;
+    long stamp;
+};
+constexpr int MFB_CONV_MAX_SLOTS = 16;
+
 struct mfb_particles;
 struct mfb_conv {
     int n[3], np[3];
@@ -52,6 +64,14 @@ struct mfb_conv {
     int naive;                // NaiveConvolver (convolution.hh:296-426): no padding, products on the N-grid itself
     mfb_grid *nb1, *nb2;      // its fbuf1_, fbuf2_
     long nconv;
+    // ---- slot workspace of the v2 source stage (mode 1).  mode 0: the buffers above.
+    int mode, legacy_ready;
+    mfb_conv_slot xs[MFB_CONV_MAX_SLOTS];
+    int nxs;
+    double2* chunk; size_t chunk_elems; int chunk_owned;   // operand / target chunks of the x-plane loop
+    long stamp;
+    int last_path, last_slots, last_loops;                 // what the last mfb_lpt_sources call did (bench / tests)
+    long last_xpass, last_ypass, last_zlaunch;
 };
 
 struct mfb_particles {
@@ -68,6 +88,7 @@ struct mfb_particles {
 };
 
 namespace mfb {
+constexpr int MFB_MAX_XBUF = 2 + MFB_CONV_MAX_SLOTS;
 // profiling roles: one per kernel use in the pipeline (bench.py reports time and algorithmic bytes per role)
 enum Role {
     ROLE_CONV_X_BWD = 0, ROLE_CONV_Y_BWD, ROLE_CONV_Z, ROLE_CONV_Y_FWD, ROLE_CONV_X_FWD,
@@ -81,9 +102,10 @@ struct DistState {
     bool ready = false, staged = false;
     void* block = nullptr;               // [xbuf0][xbuf1][flags]: one IPC-exported allocation
     size_t xbuf_elems = 0;               // complex elements per exchange buffer
-    double2* xbuf[2] = {nullptr, nullptr};
+    int nxbuf = 2;                       // exchange buffers in the block: 0,1 ping-pong for the 3-D FFTs, >= 2: slots of the convolver
+    double2* xbuf[MFB_MAX_XBUF] = {};
     double2* sendbuf = nullptr;          // staged mode only
-    double2* peer_xbuf[2][8] = {};
+    double2* peer_xbuf[MFB_MAX_XBUF][8] = {};
     unsigned long long* flags = nullptr; // flags[r]: last barrier epoch rank r has reached
     unsigned long long* peer_flags[8] = {};
     int* err = nullptr;                  // device flag set when a barrier times out
@@ -112,6 +134,9 @@ struct Context {
     bool conv_own_accumulator = true;  // tests: 0 makes mfb_conv_create behave as under memory pressure
     bool conv_grouping = true;  // sum the products of one target before the forward passes (needs mfb_conv::Wacc)
     bool zconv_v2 = true;    // second-generation fused z pass (fft_kernels_z2.cuh)
+    bool sources_v2 = true;  // mfb_lpt_sources: shared x passes + multi-product z pass on the slot workspace (mfb_sources2.cuh)
+    int sources_max_slots = 0;   // tests: cap the slot workspace (0: what HBM allows)
+    int sources_chunk = 0;       // tests: cap the x planes per chunk (0: what the chunk workspace allows)
     // optional per-role device timing (cudaEvents on `stream` around every launch)
     bool profiling = false;
     int cur_role = ROLE_ELEMENTWISE;

@@ -62,9 +62,25 @@ def _make_exchange_cb(lib, world, device):
     return L.EXCHANGE_FN(cb)
 
 
-def init(device: int, grid_res, with_conv=True, staged=False, lib_path=None):
+def pick_nslots(nbytes, n, world, free_bytes, lpt_order=3, particle_bytes_per_cell=32):
+    """how many exchange buffers to put into the peer-mapped block: 2 (the ping-pong pair of the 3-D FFTs) + the slots of the
+    shared-transform source stage (8 at 3LPT, 7 as the tight variant; 4 at 2LPT) if everything else of an LPT run still
+    fits next to them - 8 grids, the particle arrays (also the chunk workspace of that stage) and a safety margin -
+    else 2, which leaves the memory to the per-product workspace."""
+    if lpt_order < 2:
+        return 2
+    cells = n[0] * n[1] * n[2] // world
+    fixed = 8 * 8 * cells * (n[2] + 2) // n[2] + particle_bytes_per_cell * cells + (3 << 30)
+    for extra in ((8, 7) if lpt_order > 2 else (4,)):
+        if (2 + extra) * nbytes + fixed <= free_bytes:
+            return 2 + extra
+    return 2
+
+
+def init(device: int, grid_res, with_conv=True, staged=False, lib_path=None, nslots=None, lpt_order=3):
     """mfb_init + slab setup for the current torch.distributed world (no-op split for world size 1).
-    grid_res: the largest grid (int or 3-tuple) that will be created; sizes the exchange buffers."""
+    grid_res: the largest grid (int or 3-tuple) that will be created; sizes the exchange buffers.
+    nslots: exchange buffers in the peer-mapped block (None: pick_nslots from the free device memory)."""
     import torch.distributed as dist
 
     lib = G.init(device, lib_path)
@@ -74,13 +90,28 @@ def init(device: int, grid_res, with_conv=True, staged=False, lib_path=None):
         return lib
     n = (grid_res,) * 3 if isinstance(grid_res, int) else tuple(grid_res)
     nbytes = lib.mfb_dist_xbuf_bytes((C.c_int * 3)(*n), int(with_conv), world)
+    if nslots is None:
+        nslots = 2
+        if with_conv:
+            free = 64 << 30
+            if lib.mfb_build_info() == b"cuda sm_100a":
+                import torch
+
+                free = torch.cuda.mem_get_info(device)[0]
+            if staged:
+                free //= 2      # staged mode keeps a staging copy of every buffer
+            nslots = pick_nslots(nbytes, n, world, free, lpt_order)
+            # every rank must carve the same block
+            t = [None] * world
+            dist.all_gather_object(t, int(nslots))
+            nslots = min(t)
     if staged:
         cb = _make_exchange_cb(lib, world, device)
         _keep["cb"] = cb  # the library holds the raw pointer: keep the thunk alive
-        L.check(lib.mfb_dist_init_staged(rank, world, nbytes, cb, None), lib)
+        L.check(lib.mfb_dist_init_staged_slots(rank, world, nbytes, int(nslots), cb, None), lib)
     else:
         h = C.create_string_buffer(64)
-        L.check(lib.mfb_dist_init(rank, world, nbytes, h), lib)
+        L.check(lib.mfb_dist_init_slots(rank, world, nbytes, int(nslots), h), lib)
         handles = [None] * world
         dist.all_gather_object(handles, h.raw)
         blob = C.create_string_buffer(b"".join(handles), 64 * world)

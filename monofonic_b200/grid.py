@@ -346,6 +346,14 @@ class OrszagConvolver:
         convolver could not afford its own; None returns the loan"""
         L.check(self._lib.mfb_conv_borrow_accumulator(self._h, particles._h if particles is not None else None), self._lib)
 
+    def sources_info(self):
+        """what the last mfb_lpt_sources call did: {"path": 1 (per product) | 2 (shared x passes, multi-product z pass),
+        "slots", "loops", "x_passes", "y_passes", "z_launches"}"""
+        info = (C.c_longlong * 6)()
+        path = int(self._lib.mfb_conv_sources_info(self._h, info))
+        return {"path": path, "slots": int(info[0]), "loops": int(info[1]), "x_passes": int(info[2]),
+                "y_passes": int(info[3]), "z_launches": int(info[4])}
+
     def grouped(self):
         """True when the accumulator workspace was granted, i.e. mfb_lpt_sources sums the products of one target before a
         single forward transform"""

@@ -186,11 +186,10 @@ class LPTPipeline:
         if self.particles is not None and self.conv is not None:
             self.conv.borrow_accumulator(None)      # a previous loan ends with its lender
         self.particles = Particles(c.ParticleLoad, lattice_index, c.real64, c.ids64, with_masses, id_offset, self.tmp)
-        if self.conv is not None and not self.conv.grouped() and c.ConvolverType == "orszag":
-            try:
-                self.conv.borrow_accumulator(self.particles)
-            except L.MfbError:
-                pass                                 # arrays too small: products stay ungrouped
+        if self.conv is not None and c.ConvolverType == "orszag":
+            # the position/velocity arrays hold nothing while the sources are computed: the convolver may use them as
+            # workspace (slots of the shared-transform source stage, or the accumulator of product groups)
+            self.conv.borrow_accumulator(self.particles)
         return self.particles
 
     def fill_particles(self, lattice_index=0, stream_to=None):

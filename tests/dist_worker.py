@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--staged", action="store_true")
     ap.add_argument("--grid", type=int, default=32)
     ap.add_argument("--lattice", default="bcc")
+    ap.add_argument("--nslots", type=int, default=0,
+                    help="exchange buffers in the peer-mapped block (0: chosen from the free memory; 2: per-product source stage)")
     ap.add_argument("--borrow", action="store_true",
                     help="no own accumulator (as under memory pressure at 2048^3 / 8 GPUs): it is borrowed from the particle arrays")
     args = ap.parse_args()
@@ -42,15 +44,16 @@ def main():
         import emu_util
 
         dist.init_process_group("gloo")
-        MD.init(0, args.grid, True, staged=True, lib_path=emu_util.EMU)
+        MD.init(0, args.grid, True, staged=True, lib_path=emu_util.EMU, nslots=args.nslots or None)
     else:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device(f"cuda:{local_rank}"))  # gloo carries the host-side gathers of the checks
-        MD.init(local_rank, args.grid, True, staged=args.staged)
+        MD.init(local_rank, args.grid, True, staged=args.staged, nslots=args.nslots or None)
     lib = M.grid._lib()
     assert lib.mfb_dist_nranks() == world and lib.mfb_dist_rank() == rank
-    if args.borrow:
-        assert lib.mfb_set_option(b"conv_own_accumulator", 0) == 0
+    if args.borrow:   # the per-product path under memory pressure
+        assert lib.mfb_set_option(b"conv_own_accumulator", 0) == 0 and lib.mfb_set_option(b"sources_v2", 0) == 0
+    v2_expected = not args.borrow and lib.mfb_dist_nslots() >= 9
 
     n, L, TOL = args.grid, 100.0, PC.TOL
     N3, L3 = (n,) * 3, (L,) * 3
@@ -124,6 +127,12 @@ def main():
         pl.set_noise_k(W)
         pl.condition_noise()
         parts = pl.run_device(O.radial_table(g, amp), particles=True)
+        if order > 1:
+            # shared x passes (3 exchanges per potential) + x-plane chunks + multi-product z pass when the block has the slots
+            info = pl.conv.sources_info()
+            assert info["path"] == (2 if v2_expected or (order == 2 and not args.borrow and lib.mfb_dist_nslots() >= 6) else 1), info
+            if info["path"] == 2:
+                assert info["x_passes"] == ((10 if info["slots"] >= 8 else 11) if order > 2 else 3), info
         assert PC.relerr(MD.gather_kspace(pl.phi), ref["pots"]["phi"]) < TOL
         if order > 2:
             assert PC.relerr(MD.gather_kspace(pl.phi3), ref["pots"]["phi3"]) < 10 * TOL
@@ -148,7 +157,7 @@ def main():
     nex = lib.mfb_dist_exchanges()
     dist.barrier()
     if rank == 0:
-        print(f"dist_worker ok: world={world} grid={n} exchanges={nex} mode="
+        print(f"dist_worker ok: world={world} grid={n} exchanges={nex} slots={lib.mfb_dist_nslots()} mode="
               f"{'emu+gloo staged' if args.emu else ('nccl staged' if args.staged else 'peer-memory fused')}")
     MD.shutdown()
     dist.destroy_process_group()

@@ -704,57 +704,79 @@ def check_multiply_noncubic(M, shape):
 
 # ------------------------------------------------------------------ kernel generations agree
 def check_product_grouping(M, n=32):
-    """3LPT sources with the products of each target summed in z-Fourier space before ONE forward transform (and squares
-    transformed once) against the reference's one-forward-transform-per-product sequence: equal up to rounding"""
+    """3LPT sources three ways - (2) shared x passes + x-plane chunks + multi-product z pass with the products of a target
+    summed in real space (mfb_sources2.cuh), (1) per-product transforms with the products of a target summed in z-Fourier
+    space before ONE forward transform, (0) the reference's one-forward-transform-per-product sequence: equal up to rounding"""
     L, Dp = 100.0, 0.0257
     lib = M.grid._lib()
     g, W, Wc, phi = noise_and_phi(n, L, 23)
     amp = O.power_law_amplitude()
     res = {}
     try:
-        for grouping in (1, 0):
-            assert lib.mfb_set_option(b"conv_grouping", grouping) == 0
+        # (v2, grouping, max_slots, chunk planes): the last two make the slot workspace as tight as it may be (7 slots: one
+        # target per loop, an evicted X buffer is made again) and the chunks ragged
+        for key, v2, grouping, slots, chunk in (("v2", 1, 1, 0, 0), ("v2tight", 1, 1, 7, 5), (1, 0, 1, 0, 0), (0, 0, 0, 0, 0)):
+            assert lib.mfb_set_option(b"sources_v2", v2) == 0 and lib.mfb_set_option(b"conv_grouping", grouping) == 0
+            assert lib.mfb_set_option(b"sources_max_slots", slots) == 0 and lib.mfb_set_option(b"sources_chunk", chunk) == 0
             pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp))
             pl.set_noise_k(W)
             pl.condition_noise()
             pl.compute_phi1(O.radial_table(g, amp))
             l0 = M.kernel_launches()
             pl.compute_sources()
-            res[grouping] = ([pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3],
-                             M.kernel_launches() - l0, pl.conv.workspace_bytes())
+            info = pl.conv.sources_info()
+            res[key] = ([pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3],
+                        M.kernel_launches() - l0, pl.conv.workspace_bytes(), info)
+            # named products after the source stage: the convolver goes back to its per-product workspace
+            out = M.Grid_FFT((n,) * 3, (L,) * 3, True, M.kspace_id)
+            pl.conv.convolve_Hessians(pl.phi, (0, 1), pl.phi2, (1, 2), M.op.assign_to(out))
+            res[key] += (out.get_kspace(),)
     finally:
+        for o_ in (b"sources_max_slots", b"sources_chunk"):
+            lib.mfb_set_option(o_, 0)
         lib.mfb_set_option(b"conv_grouping", 1)
-    for a, b in zip(res[1][0], res[0][0]):
-        assert relerr(a, b) < 1e-13
-    # memory-pressure path: no own accumulator -> ungrouped until the particle arrays are lent to the convolver
-    try:
-        assert lib.mfb_set_option(b"conv_own_accumulator", 0) == 0
-        pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp, ParticleLoad="sc", real64=False))
-        assert not pl.conv.grouped()
-        pl.make_particles()
-        assert pl.conv.grouped()
-        for rep in range(2):          # second run: the loan is taken back from live particle data + pending hand-off copies
+        lib.mfb_set_option(b"sources_v2", 1)
+    assert res["v2"][3]["path"] == 2 and res["v2tight"][3]["path"] == 2 and res[1][3]["path"] == 1 and res[0][3]["path"] == 1
+    # 10 backward x passes (3 of phi, 3 of phi2, 4 inner products) where the per-product path does 49; with 8 slots the
+    # four targets of the last stage go two per loop, with 7 one per loop and X(phi, 1) is made twice
+    assert res["v2"][3]["x_passes"] == 10 and res["v2"][3]["loops"] == 4 and res["v2"][3]["slots"] >= 8, res["v2"][3]
+    assert res["v2tight"][3]["slots"] == 7 and res["v2tight"][3]["x_passes"] == 11 and res["v2tight"][3]["loops"] == 7, res["v2tight"][3]
+    for key in ("v2", "v2tight", 1):
+        for a, b in zip(res[key][0], res[0][0]):
+            assert relerr(a, b) < 1e-13, key
+        assert relerr(res[key][4], res[0][4]) < 1e-13
+    # memory-pressure path: the idle particle arrays are lent to the convolver - as the accumulator of product groups on the
+    # per-product path (v2 = 0: no own accumulator -> ungrouped until the loan), as slots of the workspace on the v2 path
+    for v2 in (0, 1):
+        try:
+            assert lib.mfb_set_option(b"conv_own_accumulator", 0) == 0 and lib.mfb_set_option(b"sources_v2", v2) == 0
+            pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp, ParticleLoad="sc", real64=False))
+            assert not pl.conv.grouped()
+            pl.make_particles()
+            assert pl.conv.grouped()
+            for rep in range(2):          # second run: the loan is taken back from live particle data + pending hand-off copies
+                pl.set_noise_k(W)
+                pl.condition_noise()
+                npart = pl.particles.get_local_num_particles()
+                out = {"pos": np.zeros((npart, 3), np.float32), "vel": np.zeros((npart, 3), np.float32)}
+                pl.run_device(O.radial_table(g, amp), particles=True, stream_to=out)
+            pl.particles.stream_wait()
+            assert pl.conv.sources_info()["path"] == 1 + v2
+            got = [pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3]
+            assert np.array_equal(out["pos"], pl.particles.download()["pos"])
+            # the loan ends with the lender: destroying the particles leaves a convolver that still works on what it owns
+            pl.particles = None
+            assert not pl.conv.grouped()
             pl.set_noise_k(W)
             pl.condition_noise()
-            npart = pl.particles.get_local_num_particles()
-            out = {"pos": np.zeros((npart, 3), np.float32), "vel": np.zeros((npart, 3), np.float32)}
-            pl.run_device(O.radial_table(g, amp), particles=True, stream_to=out)
-        pl.particles.stream_wait()
-        l0 = M.kernel_launches()
-        got = [pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3]
-        assert np.array_equal(out["pos"], pl.particles.download()["pos"])
-        # the loan ends with the lender: destroying the particles leaves a convolver that still works, ungrouped
-        pl.particles = None
-        assert not pl.conv.grouped()
-        pl.set_noise_k(W)
-        pl.condition_noise()
-        pl.compute_phi1(O.radial_table(g, amp))
-        pl.compute_sources()
-        assert relerr(pl.phi3.get_kspace(), got[1]) < 1e-13
-    finally:
-        lib.mfb_set_option(b"conv_own_accumulator", 1)
-    for a, b in zip(got, res[1][0]):
-        assert relerr(a, b) < 1e-13
+            pl.compute_phi1(O.radial_table(g, amp))
+            pl.compute_sources()
+            assert relerr(pl.phi3.get_kspace(), got[1]) < 1e-13
+        finally:
+            lib.mfb_set_option(b"conv_own_accumulator", 1)
+            lib.mfb_set_option(b"sources_v2", 1)
+        for a, b in zip(got, res[1][0]):
+            assert relerr(a, b) < 1e-13
     R = 8 * n * n * (n + 2)
     if res[1][2] > 7.5 * R:      # the accumulator was granted: 32 products instead of 33, 9 forward passes instead of 33
         assert res[1][1] < res[0][1] - 50, (res[1][1], res[0][1])

@@ -37,6 +37,22 @@ def test_slab_pipeline_gloo(world, lattice):
     run_world(world, ["--emu", "--grid", "32", "--lattice", lattice])
 
 
+def test_slab_pipeline_gloo_two_exchange_buffers():
+    """a peer-mapped block with only the ping-pong pair: the source stage takes the per-product path"""
+    import emu_util
+
+    emu_util.build_emu()
+    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "2"])
+
+
+def test_slab_pipeline_gloo_tight_slots():
+    """7 slots (the minimum of the shared-transform source stage at 3LPT): one target per x-plane loop"""
+    import emu_util
+
+    emu_util.build_emu()
+    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "9"])
+
+
 def test_slab_pipeline_gloo_borrowed_accumulator():
     """the memory-pressure configuration of 3LPT 2048^3 on 8 GPUs, on two CPU ranks: product groups accumulate in the
     (idle) particle arrays of each slab"""

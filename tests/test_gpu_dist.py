@@ -21,6 +21,18 @@ def test_slab_pipeline_peer_memory(world):
     run_world(world, ["--grid", "64", "--lattice", "bcc"])
 
 
+def test_slab_pipeline_two_exchange_buffers():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, ["--grid", "64", "--lattice", "sc", "--nslots", "2"])
+
+
+def test_slab_pipeline_tight_slots():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, ["--grid", "64", "--lattice", "bcc", "--nslots", "9"])
+
+
 def test_slab_pipeline_nccl_staged():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")

@@ -156,6 +156,50 @@ template <> struct Dft<8> { static MFB_HD void run(double2* v) { DftCT<2, 4>::ru
 template <> struct Dft<12> { static MFB_HD void run(double2* v) { DftCT<3, 4>::run(v); } };
 template <> struct Dft<16> { static MFB_HD void run(double2* v) { DftCT<4, 4>::run(v); } };
 
+// ------------------------------------------------------------------ twiddles of one butterfly from two table entries
+// w[u] = W^u for u = 1..R-1, W = exp(-2 pi i j / L), from the table entries W^1 and W^4 (stage-major table: entry (u, j) sits at
+// twp[(u - 1) * M]): products of depth <= 3 instead of R-1 loads.  The loads are what costs here - the L1/shared data pipe
+// is the busiest unit of the FFT passes (ncu: 60-66 % of peak with the FP64 pipe at 32-37 %), and with the shared-memory
+// carve-out at its maximum the table falls out of L1 (14 % hit rate) - while the FP64 pipe has room for the extra
+// multiplications.  The result differs from the table by a few 1e-16 (relative).
+MFB_HD double2 csqr(double2 a) { return make_double2(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y); }
+template <int R> MFB_D void tw_powers(const double2* __restrict__ twp, int M, double2* w) {
+    w[1] = __ldg(twp);
+    if constexpr (R > 2) w[2] = csqr(w[1]);
+    if constexpr (R > 3) w[3] = cmul(w[2], w[1]);
+    if constexpr (R > 4) w[4] = __ldg(twp + 3 * M);
+    if constexpr (R > 5) w[5] = cmul(w[4], w[1]);
+    if constexpr (R > 6) w[6] = cmul(w[4], w[2]);
+    if constexpr (R > 7) w[7] = cmul(w[4], w[3]);
+    if constexpr (R > 8) w[8] = csqr(w[4]);
+    if constexpr (R > 9) w[9] = cmul(w[8], w[1]);
+    if constexpr (R > 10) w[10] = cmul(w[8], w[2]);
+    if constexpr (R > 11) w[11] = cmul(w[8], w[3]);
+    if constexpr (R > 12) w[12] = cmul(w[8], w[4]);
+    if constexpr (R > 13) w[13] = cmul(w[12], w[1]);
+    if constexpr (R > 14) w[14] = cmul(w[12], w[2]);
+    if constexpr (R > 15) w[15] = cmul(w[12], w[3]);
+    static_assert(R <= 16, "radix");
+}
+
+#ifndef MFB_TW_COMPUTE
+#define MFB_TW_COMPUTE 1   // 0: every twiddle from the table (kbench A/B)
+#endif
+// v[u] *= W^u (u = 1..R-1) for the butterfly whose table entries start at twp (stride M between u)
+template <int R> MFB_D void apply_tw(double2* v, const double2* __restrict__ twp, int M) {
+#if MFB_TW_COMPUTE
+    if constexpr (R > 4) {
+        double2 w[R];
+        tw_powers<R>(twp, M, w);
+#pragma unroll
+        for (int u = 1; u < R; ++u) v[u] = cmul(v[u], w[u]);
+        return;
+    }
+#endif
+#pragma unroll
+    for (int u = 1; u < R; ++u) v[u] = cmul(v[u], __ldg(twp + (u - 1) * M));
+}
+
 // ------------------------------------------------------------------ plan traits
 template <int... Rs> __host__ __device__ constexpr int pack_get(int s) {
     constexpr int r[] = {Rs...};

@@ -41,10 +41,7 @@ template <class P, int s, int NT> MFB_D void z2_dif_stage(double2* __restrict__ 
 #pragma unroll
         for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(base, t)];
         Dft<r>::run(v);
-        if constexpr (!innermost) {
-#pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + P::tw2_off(s) + (u - 1) * M + j));
-        }
+        if constexpr (!innermost) apply_tw<r>(v, tw + P::tw2_off(s) + j, M);
 #pragma unroll
         for (int u = 0; u < r; ++u) sp[zleg<M, r>(base, u)] = v[u];
     }
@@ -59,8 +56,7 @@ template <class P, int s, int NT> MFB_D void z2_dit_stage(double2* __restrict__ 
         double2 v[r];
 #pragma unroll
         for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(base, t)];
-#pragma unroll
-        for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + P::tw2_off(s) + (u - 1) * M + j));
+        apply_tw<r>(v, tw + P::tw2_off(s) + j, M);
         Dft<r>::run(v);
 #pragma unroll
         for (int u = 0; u < r; ++u) sp[zleg<M, r>(base, u)] = v[u];
@@ -223,8 +219,14 @@ template <class P, int s, int NT> MFB_D void z3_dif_stage_pair(double2* __restri
     for (int b = q; b < Bn; b += NT) {
         const int blk = b / M, j = b - blk * M, base = blk * L + j;
         double2 w[r];
+#if MFB_TW_COMPUTE
+        if constexpr (r > 4) tw_powers<r>(tw + P::tw2_off(s) + j, M, w);
+        else
+#endif
+        {
 #pragma unroll
-        for (int u = 1; u < r; ++u) w[u] = __ldg(tw + P::tw2_off(s) + (u - 1) * M + j);
+            for (int u = 1; u < r; ++u) w[u] = __ldg(tw + P::tw2_off(s) + (u - 1) * M + j);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             double2* sp = l0 + h * LW + zpad(base);

@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(2 * P::TPL, MINB) z_multi_kernel(ZmArgs A, con
                     v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
                 }
                 Dft<r>::run(v);
-#pragma unroll
-                for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
+                apply_tw<r>(v, tw + j, M);
                 double2* sp = ln + zpad(j);
 #pragma unroll
                 for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
@@ -210,8 +209,7 @@ __global__ void __launch_bounds__(2 * P::TPL, MINB) z_multi_kernel(ZmArgs A, con
             double2 v[r];
 #pragma unroll
             for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(j, t)];
-#pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
+            apply_tw<r>(v, tw + j, M);
             Dft<r>::run(v);
 #pragma unroll
             for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
@@ -232,5 +230,195 @@ __global__ void __launch_bounds__(2 * P::TPL, MINB) z_multi_kernel(ZmArgs A, con
 }
 
 template <class P> constexpr size_t z_multi_smem(bool with_acc) { return size_t(with_acc ? 3 : 2) * (zpad(P::N) + 1) * sizeof(double2); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// z_multi2_kernel - the same contract with ONE work line per CTA: the two rows of a pair go through the backward transform
+// one after the other (NT threads on one row), their products land in two padded REAL accumulator lines (sum over the
+// products of p_even and p_odd), and the forward transform of the packed pair starts from those.  Work line + accumulators
+// = 2 complex lines (55 KB at n = 1536), so FOUR CTAs share an SM where the pair-parallel version above fits two:
+// the first B200 run of z_multi_kernel (246 registers, 8 warps per SM) sustained 21.6 ms per complex-FFT sweep of the padded
+// grid against 15.7 ms for the per-product kernel with 12 warps per SM - the pass is bound by latency, not by a pipe.
+template <class P, int s, int NT> MFB_D void zm_dif_mid(double2* ln, const double2* tw, int q) {
+    if constexpr (s < P::S - 1) {
+        __syncthreads();
+        z2_dif_stage<P, s, NT>(ln, tw, q);
+        zm_dif_mid<P, s + 1, NT>(ln, tw, q);
+    }
+}
+
+template <class P, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const double2* __restrict__ tw) {
+    MFB_DYN_SMEM(double2, sm);
+    constexpr int N = P::N, S = P::S;
+    constexpr int NZ = N / 3;
+    constexpr int LW = zpad(N) + 1;
+    static_assert(P::radix(0) % 3 == 0, "the z pass needs a first radix that is a multiple of 3");
+    static_assert(S >= 2, "at least two stages");
+    double2* work = sm;                                         // one padded complex line
+    double* accx = reinterpret_cast<double*>(sm + LW);          // sum of the products of the even row (padded like a line)
+    double* accy = accx + LW;                                   // ... of the odd row
+    const int tid = threadIdx.x;
+    const long row0 = long(blockIdx.x) * 2;
+    const int nprod = A.nprod;
+
+#pragma unroll 1
+    for (int ip = 0; ip < nprod; ++ip) {
+        const ZmProduct& pr = A.prod[ip];
+        const bool square = pr.square != 0;
+        const int na = pr.a.n, nb = square ? 0 : pr.b.n;
+        const double ca0 = pr.a.t[0].c, ca1 = pr.a.t[1].c, cb0 = pr.b.t[0].c, cb1 = pr.b.t[1].c;
+        const int ea0 = pr.a.t[0].e, ea1 = pr.a.t[1].e, eb0 = pr.b.t[0].e, eb1 = pr.b.t[1].e;
+        const double cf = pr.coeff;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const bool row_ok = row0 + h < A.nrows;
+            const ptrdiff_t roff = (row0 + h) * A.in_pitch;
+            if (ip > 0 || h > 0) __syncthreads();   // the innermost step of the previous row has read the work line
+            // ---- DIF stage 0: conj(A^ + i B^), Hermitian-extended and zero padded, built in the legs
+            {
+                constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
+                const double2* pa0 = pr.a.t[0].p + roff;
+                const double2* pa1 = pr.a.t[1].p + roff;
+                const double2* pb0 = pr.b.t[0].p + roff;
+                const double2* pb1 = pr.b.t[1].p + roff;
+                auto ld = [&](const double2* p) -> double2 { return row_ok ? mfb_ld_stream(p) : make_double2(0.0, 0.0); };
+                auto kpow = [&](double kz, int e, double c) -> double { return e == 0 ? c : (e == 1 ? c * kz : c * kz * kz); };
+#pragma unroll 1
+                for (int j = tid; j < M; j += NT) {
+                    double2 xa[2 * K3], xb[2 * K3];
+                    auto mode_k = [&](int m) -> int { return m < K3 ? j + m * M : (2 * K3 - m) * M - j; };   // leg m <-> mode k
+#pragma unroll
+                    for (int m = 0; m < 2 * K3; ++m) {
+                        const bool dropped = (m == K3 && j == 0);   // k == NZ: the dropped Nyquist sample (not stored)
+                        xa[m] = dropped ? make_double2(0.0, 0.0) : ld(pa0 + mode_k(m));
+                        if (nb > 0) xb[m] = dropped ? make_double2(0.0, 0.0) : ld(pb0 + mode_k(m));
+                    }
+                    if (na > 1) {   // sums / differences of Hessians (convolution.hh:214-274): second term of A
+                        double2 ya[2 * K3];
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) ya[m] = (m == K3 && j == 0) ? make_double2(0.0, 0.0) : ld(pa1 + mode_k(m));
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) {
+                            const double kz = A.kfz * double(mode_k(m));
+                            const double f0 = kpow(kz, ea0, ca0), f1 = kpow(kz, ea1, ca1);
+                            xa[m] = make_double2(fma(f1, ya[m].x, f0 * xa[m].x), fma(f1, ya[m].y, f0 * xa[m].y));
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) {
+                            const double f0 = kpow(A.kfz * double(mode_k(m)), ea0, ca0);
+                            xa[m] = make_double2(f0 * xa[m].x, f0 * xa[m].y);
+                        }
+                    }
+                    if (nb > 1) {
+                        double2 yb[2 * K3];
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) yb[m] = (m == K3 && j == 0) ? make_double2(0.0, 0.0) : ld(pb1 + mode_k(m));
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) {
+                            const double kz = A.kfz * double(mode_k(m));
+                            const double f0 = kpow(kz, eb0, cb0), f1 = kpow(kz, eb1, cb1);
+                            xb[m] = make_double2(fma(f1, yb[m].x, f0 * xb[m].x), fma(f1, yb[m].y, f0 * xb[m].y));
+                        }
+                    } else if (nb == 1) {
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) {
+                            const double f0 = kpow(A.kfz * double(mode_k(m)), eb0, cb0);
+                            xb[m] = make_double2(f0 * xb[m].x, f0 * xb[m].y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 2 * K3; ++m) xb[m] = xa[m];
+                    }
+                    double2 v[r];
+#pragma unroll
+                    for (int t = 0; t < K3; ++t) {
+                        double2 x1 = xa[t], x2 = xb[t];
+                        if (t == 0 && j == 0) { x1.y = 0.0; x2.y = 0.0; }   // c2r ignores Im of the self-conjugate mode
+                        v[t] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
+                    }
+#pragma unroll
+                    for (int t = K3; t < 2 * K3; ++t) v[t] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int t = 2 * K3; t < r; ++t) {
+                        const double2 x1 = xa[t - K3], x2 = xb[t - K3];
+                        v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
+                    }
+                    Dft<r>::run(v);
+                    apply_tw<r>(v, tw + j, M);
+                    double2* sp = work + zpad(j);
+#pragma unroll
+                    for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
+                }
+            }
+            zm_dif_mid<P, 1, NT>(work, tw, tid);
+            __syncthreads();
+            // ---- innermost DIF stage -> a * b -> real accumulator of this row; last product, odd row: innermost DIT stage
+            {
+                constexpr int r = P::radix(S - 1), Bn = N / r;
+                double* acc = h ? accy : accx;
+                const bool first = ip == 0, finish = (ip == nprod - 1) && h == 1;
+#pragma unroll 1
+                for (int b = tid; b < Bn; b += NT) {
+                    const int base = b * r;
+                    double2* sp = work + zpad(base);
+                    double* ap = acc + zpad(base);
+                    double2 v[r];
+#pragma unroll
+                    for (int t = 0; t < r; ++t) v[t] = sp[zleg<1, r>(base, t)];
+                    Dft<r>::run(v);
+                    double p[r];
+#pragma unroll
+                    for (int t = 0; t < r; ++t) p[t] = cf * (-v[t].x * v[t].y);   // a = Re, b = -Im (conj trick)
+                    if (!first) {
+#pragma unroll
+                        for (int t = 0; t < r; ++t) p[t] += ap[zleg<1, r>(base, t)];
+                    }
+                    if (!finish) {
+#pragma unroll
+                        for (int t = 0; t < r; ++t) ap[zleg<1, r>(base, t)] = p[t];
+                    } else {   // forward transform of (p_even + i p_odd): same thread, same positions - no barrier
+                        const double* ax = accx + zpad(base);
+#pragma unroll
+                        for (int t = 0; t < r; ++t) v[t] = make_double2(ax[zleg<1, r>(base, t)], p[t]);
+                        Dft<r>::run(v);
+#pragma unroll
+                        for (int u = 0; u < r; ++u) sp[zleg<1, r>(base, u)] = v[u];
+                    }
+                }
+            }
+        }
+    }
+    // ---- forward transform of the packed pair (DIT), once per target
+    z2_dit_mid<P, S - 2, NT>(work, tw, tid);
+    __syncthreads();
+    {
+        constexpr int r = P::radix(0), M = N / r;
+#pragma unroll 1
+        for (int j = tid; j < M; j += NT) {
+            double2* sp = work + zpad(j);
+            double2 v[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(j, t)];
+            apply_tw<r>(v, tw + j, M);
+            Dft<r>::run(v);
+#pragma unroll
+            for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
+        }
+    }
+    __syncthreads();
+    {   // unpack the two half-spectra, store the retained modes
+        const long r1 = row0, r2 = row0 + 1;
+        for (int k = tid; k < NZ; k += NT) {
+            const double2 zk = work[zpad(k)];
+            const double2 zm = work[zpad((N - k) % N)];
+            const double2 v1 = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 v2 = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            if (r1 < A.nrows) mfb_st_stream(A.out + r1 * A.out_pitch + k, v1);
+            if (r2 < A.nrows) mfb_st_stream(A.out + r2 * A.out_pitch + k, v2);
+        }
+    }
+}
+template <class P> constexpr size_t z_multi2_smem() { return size_t(2) * (zpad(P::N) + 1) * sizeof(double2); }
 
 }  // namespace mfb

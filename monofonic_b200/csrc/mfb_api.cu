@@ -616,8 +616,9 @@ static void grid_sums(mfb_grid* g, double out[2]) {
     if (g->space == MFB_RSPACE) {
         MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_real_kernel, nb, RED_THREADS, g->d, long(x0) * g->n[1], g->n[2], g->pitch, part);
     } else {
+        // slab k-layout is [ky_loc][kx][kz]: nloc1 * n0 * nzc elements (n0 * n1 * nzc on a single slab)
         MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_cplx_kernel, nb, RED_THREADS, reinterpret_cast<const double2*>(g->d),
-                   long(k0) * g->n[1] * g->nzc, part);
+                   long(k0) * (g->dist ? g->n[0] : g->n[1]) * g->nzc, part);
     }
     check_launch("reduce");
     MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_final_kernel, 1, RED_THREADS, part, nb, 0, part + 2 * nb);
@@ -1212,14 +1213,29 @@ int mfb_finalize(void) {
     g_ctx.tw2.clear();
     if (g_ctx.partial) cudaFree(g_ctx.partial);
     g_ctx.partial = nullptr; g_ctx.partial_cap = 0;
+    for (int t = 0; t < 2; ++t) {
+        if (g_ctx.table[t]) cudaFree(g_ctx.table[t]);
+        g_ctx.table[t] = nullptr; g_ctx.table_cap[t] = 0;
+    }
     cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) { cudaStreamDestroy(g_ctx.copy_stream); g_ctx.copy_stream = nullptr; }
     g_ctx.initialised = false;
     MFB_CATCH
 }
+// slab mode: a device barrier that timed out (a peer died) leaves garbage behind - every call that hands results to the host
+// reports it instead of relying on the caller to remember mfb_dist_check
+static void dist_require_alive() {
+    DistState& d = D();
+    if (!d.ready || d.staged || !d.err) return;
+    int e = 0;
+    cuda_check(cudaMemcpyAsync(&e, d.err, sizeof(int), cudaMemcpyDeviceToHost, g_ctx.stream), "read barrier status");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    require(e == 0, "slab exchange barrier timed out: a peer rank is not responding");
+}
 int mfb_synchronize(void) {
     MFB_TRY
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "cudaStreamSynchronize");
+    dist_require_alive();
     MFB_CATCH
 }
 void* mfb_stream(void) { return (void*)g_ctx.stream; }
@@ -1234,6 +1250,7 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
     else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
+    else if (std::string(name) == "zmulti_variant") g_ctx.zmulti_variant = value;
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
     else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)
     else throw std::runtime_error(std::string("unknown option ") + name);
@@ -1440,6 +1457,7 @@ int mfb_grid_download(const mfb_grid* g, double* host) {
     MFB_TRY
     cuda_check(cudaMemcpyAsync(host, g->d, g->ntot * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "download");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    if (g->dist) dist_require_alive();
     MFB_CATCH
 }
 int mfb_fft_forward(mfb_grid* g, int do_transform) {
@@ -1617,6 +1635,11 @@ int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* 
     require(phi->space == MFB_KSPACE, "assemble: phi must be in k-space");
     require(!phi2 || phi2->space == MFB_KSPACE, "assemble: phi2 must be in k-space");
     require(!phi3 || phi3->space == MFB_KSPACE, "assemble: phi3 must be in k-space");
+    for (const mfb_grid* g : {phi2, phi3, wnoise, (const mfb_grid*)out})
+        require(!g || (g->ntot == phi->ntot && g->n[0] == phi->n[0] && g->n[1] == phi->n[1] && g->n[2] == phi->n[2]),
+                "assemble: grid size mismatch");
+    if (A3 && A3[0] && A3[1] && A3[2])
+        for (int k = 0; k < 3; ++k) require(A3[k]->ntot == phi->ntot, "assemble: grid size mismatch");
     AssembleArgs a;
     memset(&a, 0, sizeof(a));
     a.d = d; a.p = (d + 1) % 3; a.q = (d + 2) % 3;
@@ -1631,6 +1654,8 @@ int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* 
     a.w1 = w1; a.w2 = w2; a.w3 = w3; a.wc = wc; a.scale = scale;
     if (vbc_table) {
         require(wnoise && wnoise->space == MFB_KSPACE, "assemble: wnoise (k-space) needed for the vbc term");
+        require(phi->n[0] == phi->n[1] && phi->n[1] == phi->n[2] && phi->L[0] == phi->L[1] && phi->L[1] == phi->L[2],
+                "assemble: the vbc term needs a cubic grid (radial table on integer |n|^2)");
         const int h = phi->n[0] / 2;
         a.vbc_table = upload_table(vbc_table, ntable, size_t(3) * h * h + 1, 1);
         a.wnoise = reinterpret_cast<const double2*>(wnoise->d);
@@ -2035,6 +2060,7 @@ int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* i
     if (ids) cuda_check(cudaMemcpyAsync(ids, p->ids, p->np * is, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H ids");
     if (mass && p->mass) cuda_check(cudaMemcpyAsync(mass, p->mass, p->np * rs, cudaMemcpyDeviceToHost, g_ctx.stream), "D2H mass");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    dist_require_alive();
     MFB_CATCH
 }
 int mfb_particles_stream_out(mfb_particles* p, int attr, void* host) {

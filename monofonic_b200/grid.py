@@ -424,6 +424,12 @@ class Particles:
     def get_local_num_particles(self):
         return int(self._lib.mfb_particles_count(self._h))
 
+    def reset_species(self, lattice_index, IDoffset):
+        """reuse the container for the next species (the reference makes a new lattice_generator per species,
+        src/ic_generator.cc:636-645: secondary lattice and ID offset 1 for the baryons)"""
+        self.lattice_index = int(lattice_index)
+        L.check(self._lib.mfb_particles_set_ids(self._h, int(IDoffset)), self._lib)
+
     def set_positions(self, idim, lunit, field: Grid_FFT):
         L.check(self._lib.mfb_particles_set_positions(self._h, self.lattice_index, int(idim), float(lunit), field._h), self._lib)
 

@@ -124,7 +124,12 @@ class LPTPipeline:
         """tmp <- v_d in real space (src/ic_generator.cc:888-942)"""
         c = self.cfg
         v = c.vfac
-        self._assemble(d, (v, 2 * v, 3 * v), 3 * v, c.vunit / c.BoxLength, vbc)
+        scale = c.vunit / c.BoxLength
+        if c.tides is not None and self.order > 1:
+            # external tides: anisotropic velocity growth factor alpha_d^2, alpha_d = 1 - D+ lambda_d
+            # (src/ic_generator.cc:238-242, applied at :931-934 to the whole mode incl. the v_bc term)
+            scale *= (1.0 - c.Dplus0 * c.tides[d]) ** 2
+        self._assemble(d, (v, 2 * v, 3 * v), 3 * v, scale, vbc)
         self.tmp.FourierTransformBackward()
         return self.tmp
 
@@ -183,8 +188,11 @@ class LPTPipeline:
 
     def make_particles(self, lattice_index=0, with_masses=False, id_offset=0):
         c = self.cfg
-        if self.particles is not None and self.conv is not None:
-            self.conv.borrow_accumulator(None)      # a previous loan ends with its lender
+        if self.particles is not None:
+            if self.conv is not None and c.ConvolverType == "orszag":
+                self.conv.borrow_accumulator(None)  # a previous loan ends with its lender
+            self.particles = None                   # release the old container first: two would not fit at 1024^3
+        self._lattice_index = lattice_index
         self.particles = Particles(c.ParticleLoad, lattice_index, c.real64, c.ids64, with_masses, id_offset, self.tmp)
         if self.conv is not None and c.ConvolverType == "orszag":
             # the position/velocity arrays hold nothing while the sources are computed: the convolver may use them as
@@ -197,7 +205,8 @@ class LPTPipeline:
         host arrays "pos", "vel", "ids") every attribute is handed to the host as soon as it is complete, on the copy
         stream, overlapping the remaining component FFTs; the caller ends with particles.stream_wait()."""
         c = self.cfg
-        if self.particles is None:
+        if self.particles is None or getattr(self, "_lattice_index", 0) != lattice_index:
+            # a second species on the secondary lattice (baryons, lattice_index 1) needs its own container
             self.make_particles(lattice_index)
         if stream_to is not None and "ids" in stream_to and not self._ids_streamed:
             self.particles.stream_out("ids", stream_to["ids"])

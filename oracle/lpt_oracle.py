@@ -409,9 +409,11 @@ def displacement_k(g: GridSpec, pots, order, d, scale=1.0):
     return zero_dc(tmp)
 
 
-def velocity_k(g: GridSpec, pots, order, d, vfac, scale=1.0, vbc=None):
+def velocity_k(g: GridSpec, pots, order, d, vfac, scale=1.0, vbc=None, tides=None, Dplus0=None):
     """k-space v_d * scale; scale = vunit/boxlen (:937).
-    vbc = (C_species, theta_bc_amplitude(|k|) callable, W) adds the relative-velocity term (:918-921)."""
+    vbc = (C_species, theta_bc_amplitude(|k|) callable, W) adds the relative-velocity term (:918-921).
+    tides = (lambda_x, lambda_y, lambda_z) with Dplus0: external tides (only honoured at LPTorder > 1, :190-193) multiply
+    the whole mode by the anisotropic velocity growth factor alpha_d^2, alpha_d = 1 - D+ lambda_d (:238-242, :931-934)."""
     p, q = (d + 1) % 3, (d + 2) % 3
     tot = vfac * pots["phi"]
     if order > 1:
@@ -429,6 +431,8 @@ def velocity_k(g: GridSpec, pots, order, d, vfac, scale=1.0, vbc=None):
             term = vfac * C * amp(kn) * W * g.grad(d) / (kn * kn)
         term[0, 0, 0] = 0.0
         tmp = tmp - term
+    if tides is not None and order > 1:
+        tmp = tmp * (1.0 - Dplus0 * tides[d]) ** 2
     tmp = tmp * scale
     return zero_dc(tmp)
 

@@ -395,9 +395,15 @@ def check_two_fluid_terms(M, n=32, lattice="bcc"):
     # velocities with the baryon-CDM relative velocity term
     vtab = O.radial_table(g, amp_theta)
     for d in range(3):
-        ref = g.bwd(O.velocity_k(g, pots, 2, d, vfac, vunit / L, vbc=(Csp, amp_theta, Wc)))
+        ref = g.bwd(O.velocity_k(g, pots, 2, d, vfac, vunit / L, vbc=(Csp, amp_theta, Wc), tides=lam, Dplus0=Dp))
         got = pl.velocity_field(d, vbc=(vtab, vfac * Csp)).get_real()
         assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max(), d
+        # the anisotropic velocity growth factor, stated independently of the oracle: with external tides every velocity
+        # mode is the tide-free assembly times (1 - D+ lambda_d)^2 (src/ic_generator.cc:238-242, 931-934)
+        plain = g.bwd(O.velocity_k(g, pots, 2, d, vfac, vunit / L, vbc=(Csp, amp_theta, Wc)))
+        alpha2 = (1.0 - Dp * lam[d]) * (1.0 - Dp * lam[d])
+        assert abs(alpha2 - 1.0) > 1e-3
+        assert np.abs(got - alpha2 * plain).max() < 1e-11 * np.abs(plain).max(), d
     # SPT density
     ref = g.bwd(O.density_k(g, pots))
     assert np.abs(pl.density_field().get_real() - ref).max() < 1e-11 * np.abs(ref).max()
@@ -741,10 +747,11 @@ def check_product_grouping(M, n=32):
     # four targets of the last stage go two per loop, with 7 one per loop and X(phi, 1) is made twice
     assert res["v2"][3]["x_passes"] == 10 and res["v2"][3]["loops"] == 4 and res["v2"][3]["slots"] >= 8, res["v2"][3]
     assert res["v2tight"][3]["slots"] == 7 and res["v2tight"][3]["x_passes"] == 11 and res["v2tight"][3]["loops"] == 7, res["v2tight"][3]
+    # equal up to rounding: the sums are taken in a different order (real space / z-Fourier space / per product)
     for key in ("v2", "v2tight", 1):
         for a, b in zip(res[key][0], res[0][0]):
-            assert relerr(a, b) < 1e-13, key
-        assert relerr(res[key][4], res[0][4]) < 1e-13
+            assert relerr(a, b) < 1e-12, key
+        assert relerr(res[key][4], res[0][4]) < 1e-12
     # memory-pressure path: the idle particle arrays are lent to the convolver - as the accumulator of product groups on the
     # per-product path (v2 = 0: no own accumulator -> ungrouped until the loan), as slots of the workspace on the v2 path
     for v2 in (0, 1):
@@ -771,12 +778,12 @@ def check_product_grouping(M, n=32):
             pl.condition_noise()
             pl.compute_phi1(O.radial_table(g, amp))
             pl.compute_sources()
-            assert relerr(pl.phi3.get_kspace(), got[1]) < 1e-13
+            assert relerr(pl.phi3.get_kspace(), got[1]) < 1e-12
         finally:
             lib.mfb_set_option(b"conv_own_accumulator", 1)
             lib.mfb_set_option(b"sources_v2", 1)
         for a, b in zip(got, res[1][0]):
-            assert relerr(a, b) < 1e-13
+            assert relerr(a, b) < 1e-12
     R = 8 * n * n * (n + 2)
     if res[1][2] > 7.5 * R:      # the accumulator was granted: 32 products instead of 33, 9 forward passes instead of 33
         assert res[1][1] < res[0][1] - 50, (res[1][1], res[0][1])

@@ -149,3 +149,25 @@ def test_oracle_matches_reference_built_here():
         assert rel(Q["vel"], P["vel"]) < TOL and rel(Q["mass"], P["mass"]) < TOL
         Z = F.run_reference_particles(phi, psi, lt, li, zero_field=True, n=n)
         assert np.array_equal(Z["pos"], oracle_particles(g, phi, psi, lt, li, zero=True)["pos"])
+
+
+def test_fast_fft_backend(tmp_path):
+    """oracle/_ref/ref_bench - the reference's Grid_FFT / OrszagConvolver sources behind the FAST FFT shim
+    (oracle/refshim/fftw_fast.cc), the binary bench.py times as its CPU arm - computes what the oracle computes: the shim's
+    mixed-radix transforms (2^a 3^b lengths, two-for-one r2c / c2r) are not an exact DFT, so they get a check of their own"""
+    if not os.path.isdir("/root/reference/include"):
+        pytest.skip("reference sources not mounted: ref_bench cannot be (re)built here")
+    r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref/ref_bench"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    n, L = 48, 100.0           # 48 and the padded 72 exercise the radix-3 and radix-4/2 paths
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_bench"), str(n), "3", "1", "0", str(tmp_path)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "seconds_per_step" in r.stdout, r.stdout + r.stderr
+    ld = lambda nm: np.fromfile(os.path.join(tmp_path, nm + ".bin"), dtype=np.complex128).reshape(n, n, n // 2 + 1)
+    phi = ld("phi")
+    g = O.GridSpec(n, L)
+    pots = O.lpt_potentials(g, phi, 3, -1.0)     # D+ = -1: g1 = 1, g2 = -3/7, g3 = -1/3, g3c = -1/7
+    assert rel(ld("phi2"), pots["phi2"] / (-3.0 / 7.0)) < 1e-11
+    assert rel(ld("phi3"), pots["phi3"] / (-1.0 / 3.0)) < 1e-10
+    assert rel(ld("A3x"), pots["A3"][0] / (-1.0 / 7.0)) < 1e-9

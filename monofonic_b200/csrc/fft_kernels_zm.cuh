@@ -265,13 +265,17 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
     for (int ip = 0; ip < nprod; ++ip) {
         const ZmProduct& pr = A.prod[ip];
         const bool square = pr.square != 0;
-        const int na = pr.a.n, nb = square ? 0 : pr.b.n;
-        const double ca0 = pr.a.t[0].c, ca1 = pr.a.t[1].c, cb0 = pr.b.t[0].c, cb1 = pr.b.t[1].c;
-        const int ea0 = pr.a.t[0].e, ea1 = pr.a.t[1].e, eb0 = pr.b.t[0].e, eb1 = pr.b.t[1].e;
+        const int na = pr.a.n, nb = square ? pr.a.n : pr.b.n;
+        const double ca0 = pr.a.t[0].c, ca1 = pr.a.t[1].c, cb0 = square ? ca0 : pr.b.t[0].c, cb1 = square ? ca1 : pr.b.t[1].c;
+        const int ea0 = pr.a.t[0].e, ea1 = pr.a.t[1].e, eb0 = square ? ea0 : pr.b.t[0].e, eb1 = square ? ea1 : pr.b.t[1].e;
         const double cf = pr.coeff;
+        // A SQUARE (xy^2, yz^2, ... : 6 of the 32 products of a 3LPT step) needs one real field per row: the two ROWS of the pair
+        // share one complex transform (a_even + i a_odd) and the pair is done in one pass instead of two.
+        const int npass = square ? 1 : 2;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < npass; ++h) {
             const bool row_ok = row0 + h < A.nrows;
+            const bool row1_ok = row0 + 1 < A.nrows;
             const ptrdiff_t roff = (row0 + h) * A.in_pitch;
             if (ip > 0 || h > 0) __syncthreads();   // the innermost step of the previous row has read the work line
             // ---- DIF stage 0: conj(A^ + i B^), Hermitian-extended and zero padded, built in the legs
@@ -279,9 +283,11 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
                 constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
                 const double2* pa0 = pr.a.t[0].p + roff;
                 const double2* pa1 = pr.a.t[1].p + roff;
-                const double2* pb0 = pr.b.t[0].p + roff;
-                const double2* pb1 = pr.b.t[1].p + roff;
+                // square: "B" is the same operand on the odd row of the pair
+                const double2* pb0 = square ? pr.a.t[0].p + roff + A.in_pitch : pr.b.t[0].p + roff;
+                const double2* pb1 = square ? pr.a.t[1].p + roff + A.in_pitch : pr.b.t[1].p + roff;
                 auto ld = [&](const double2* p) -> double2 { return row_ok ? mfb_ld_stream(p) : make_double2(0.0, 0.0); };
+                auto ldb = [&](const double2* p) -> double2 { return (square ? row1_ok : row_ok) ? mfb_ld_stream(p) : make_double2(0.0, 0.0); };
                 auto kpow = [&](double kz, int e, double c) -> double { return e == 0 ? c : (e == 1 ? c * kz : c * kz * kz); };
 #pragma unroll 1
                 for (int j = tid; j < M; j += NT) {
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
                     for (int m = 0; m < 2 * K3; ++m) {
                         const bool dropped = (m == K3 && j == 0);   // k == NZ: the dropped Nyquist sample (not stored)
                         xa[m] = dropped ? make_double2(0.0, 0.0) : ld(pa0 + mode_k(m));
-                        if (nb > 0) xb[m] = dropped ? make_double2(0.0, 0.0) : ld(pb0 + mode_k(m));
+                        xb[m] = dropped ? make_double2(0.0, 0.0) : ldb(pb0 + mode_k(m));
                     }
                     if (na > 1) {   // sums / differences of Hessians (convolution.hh:214-274): second term of A
                         double2 ya[2 * K3];
@@ -313,22 +319,19 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
                     if (nb > 1) {
                         double2 yb[2 * K3];
 #pragma unroll
-                        for (int m = 0; m < 2 * K3; ++m) yb[m] = (m == K3 && j == 0) ? make_double2(0.0, 0.0) : ld(pb1 + mode_k(m));
+                        for (int m = 0; m < 2 * K3; ++m) yb[m] = (m == K3 && j == 0) ? make_double2(0.0, 0.0) : ldb(pb1 + mode_k(m));
 #pragma unroll
                         for (int m = 0; m < 2 * K3; ++m) {
                             const double kz = A.kfz * double(mode_k(m));
                             const double f0 = kpow(kz, eb0, cb0), f1 = kpow(kz, eb1, cb1);
                             xb[m] = make_double2(fma(f1, yb[m].x, f0 * xb[m].x), fma(f1, yb[m].y, f0 * xb[m].y));
                         }
-                    } else if (nb == 1) {
+                    } else {
 #pragma unroll
                         for (int m = 0; m < 2 * K3; ++m) {
                             const double f0 = kpow(A.kfz * double(mode_k(m)), eb0, cb0);
                             xb[m] = make_double2(f0 * xb[m].x, f0 * xb[m].y);
                         }
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < 2 * K3; ++m) xb[m] = xa[m];
                     }
                     double2 v[r];
 #pragma unroll
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
             {
                 constexpr int r = P::radix(S - 1), Bn = N / r;
                 double* acc = h ? accy : accx;
-                const bool first = ip == 0, finish = (ip == nprod - 1) && h == 1;
+                const bool first = ip == 0, finish = (ip == nprod - 1) && (h == 1 || square);
 #pragma unroll 1
                 for (int b = tid; b < Bn; b += NT) {
                     const int base = b * r;
@@ -368,6 +371,27 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
                     for (int t = 0; t < r; ++t) v[t] = sp[zleg<1, r>(base, t)];
                     Dft<r>::run(v);
                     double p[r];
+                    if (square) {   // Re = a_even, -Im = a_odd: both rows' squares in one go
+                        double* ay = accy + zpad(base);
+                        double pe[r];
+#pragma unroll
+                        for (int t = 0; t < r; ++t) { pe[t] = cf * v[t].x * v[t].x; p[t] = cf * v[t].y * v[t].y; }
+                        if (!first) {
+#pragma unroll
+                            for (int t = 0; t < r; ++t) { pe[t] += ap[zleg<1, r>(base, t)]; p[t] += ay[zleg<1, r>(base, t)]; }
+                        }
+                        if (!finish) {
+#pragma unroll
+                            for (int t = 0; t < r; ++t) { ap[zleg<1, r>(base, t)] = pe[t]; ay[zleg<1, r>(base, t)] = p[t]; }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < r; ++t) v[t] = make_double2(pe[t], p[t]);
+                            Dft<r>::run(v);
+#pragma unroll
+                            for (int u = 0; u < r; ++u) sp[zleg<1, r>(base, u)] = v[u];
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int t = 0; t < r; ++t) p[t] = cf * (-v[t].x * v[t].y);   // a = Re, b = -Im (conj trick)
                     if (!first) {

@@ -163,7 +163,9 @@ static int conv_enter_slots(mfb_conv* c, int want_slots, int min_slots, size_t w
     if (c->lender) { lent_left = c->lender->posvel_bytes; lent_p = (char*)c->lender->pos; }
     if (c->dist) {
         DistState& d = D();
-        for (int k = 2; k < d.nxbuf && c->nxs < MFB_CONV_MAX_SLOTS; ++k) add(d.xbuf[k], 0, k);
+        // every exchange buffer of the block, the ping-pong pair of the 3-D FFTs included: no other exchange runs inside the
+        // source stage, and barriers at its start and end separate it from the neighbouring transforms
+        for (int k = 0; k < d.nxbuf && c->nxs < MFB_CONV_MAX_SLOTS; ++k) add(d.xbuf[k], 0, k);
     } else {
         if (!c->W1) {
             c->w1_elems = conv_slot_elems(c);
@@ -461,23 +463,58 @@ struct S2Runner {
         ++n_loops;
     }
 
-    // targets in order, as many per loop as the slots allow (each needs one; the X buffers of the loop must all be resident)
-    void run_stage(std::vector<S2Target>& targets) {
+    // X buffers (grid, mx) a set of products needs, added to `set`
+    typedef std::vector<std::pair<const mfb_grid*, int>> XSet;
+    static XSet x_of(const S2Product& p, XSet set) {
+        for (const S2Operand* o : {&p.a, &p.b})
+            for (int k = 0; k < o->n; ++k) {
+                const std::pair<const mfb_grid*, int> key(o->t[k].g, o->t[k].mx);
+                if (std::find(set.begin(), set.end(), key) == set.end()) set.push_back(key);
+            }
+        return set;
+    }
+    static XSet x_of(const S2Target& t, XSet set) {
+        for (const S2Product& p : t.prods) set = x_of(p, set);
+        return set;
+    }
+    // targets in order, as many per loop as the slots allow (each needs one; the X buffers of the loop must all be resident).
+    // A target whose products need more X buffers than there are slots is split: its products go through several loops and
+    // the later ones ADD to the target (linear; costs extra forward passes - the tight-memory variant, 3LPT 2048^3 on 8 GPUs).
+    void run_stage(std::vector<S2Target>& in) {
+        std::vector<S2Target> targets;
+        for (S2Target& t : in) {
+            if (int(x_of(t, XSet()).size()) + 1 <= c->nxs) { targets.push_back(t); continue; }
+            S2Target part = t;
+            part.prods.clear();
+            bool first = true;
+            for (const S2Product& p : t.prods) {
+                S2Target trial = part;
+                trial.prods.push_back(p);
+                if (!part.prods.empty() && int(x_of(trial, XSet()).size()) + 1 > c->nxs) {
+                    targets.push_back(part);
+                    first = false;
+                    part.prods.clear();
+                    // whatever the target's operator, the remaining products accumulate with the same sign / factor
+                    if (t.op == OP_ASSIGN) part.op = OP_ADD;
+                }
+                require(int(x_of(p, XSet()).size()) + 1 <= c->nxs, "internal: the source-stage workspace has too few slots for one product");
+                // a target that is also an operand (the first inner product lives in phi3) must be consumed before it is written
+                for (const S2Operand* o : {&p.a, &p.b})
+                    for (int k = 0; k < o->n; ++k) require(first || o->t[k].g != t.out, "internal: split target would overwrite its own operand");
+                part.prods.push_back(p);
+            }
+            targets.push_back(part);
+        }
         size_t i = 0;
         while (i < targets.size()) {
             int nt = 0;
-            std::vector<std::pair<const mfb_grid*, int>> xs;
-            auto count_x = [&](const S2Target& t, std::vector<std::pair<const mfb_grid*, int>> set) {
-                for (const S2Product& p : t.prods)
-                    for (const S2Operand* o : {&p.a, &p.b})
-                        for (int k = 0; k < o->n; ++k) {
-                            const std::pair<const mfb_grid*, int> key(o->t[k].g, o->t[k].mx);
-                            if (std::find(set.begin(), set.end(), key) == set.end()) set.push_back(key);
-                        }
-                return set;
-            };
+            XSet xs;
             while (i + nt < targets.size()) {
-                auto cand = count_x(targets[i + nt], xs);
+                // two parts of one target cannot share a loop (the second adds to what the first assigns)
+                bool same_out = false;
+                for (int k = 0; k < nt; ++k) same_out = same_out || targets[i + k].out == targets[i + nt].out;
+                if (same_out) break;
+                XSet cand = x_of(targets[i + nt], xs);
                 if (int(cand.size()) + nt + 1 > c->nxs) break;
                 xs = cand;
                 ++nt;
@@ -499,8 +536,9 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
     const int p0l = c->p0loc;
     const int kmax = order > 2 ? 13 : 7;                       // base fields of the widest loop + the target chunk
     const long cx_want = std::max<long>(1, std::min<long>(p0l, std::max<long>(8, p0l / 32)));
-    const int min_slots = order > 2 ? 7 : 4, want_slots = order > 2 ? 8 : 4;
-    if (c->dist && D().nxbuf - 2 < min_slots) return false;
+    // 8 slots: everything in 4 loops (3LPT).  7: one target per loop.  5-6: targets are split (more forward passes).
+    const int min_slots = order > 2 ? 5 : 4, want_slots = order > 2 ? 8 : 4;
+    if (c->dist && D().nxbuf < min_slots) return false;
     if (!conv_enter_slots(c, want_slots, min_slots, size_t(kmax) * cx_want * pe, size_t(kmax) * pe)) return false;
     conv_wait_lender(c);   // lent particle arrays: streamed hand-off copies of the previous run must have drained
 
@@ -579,6 +617,7 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
         for (int d = 0; d < 3; ++d) grid_laplacian_pow(A3[d], -1, -g3c);   // :555 and :568-570
     }
     for (int i = 0; i < c->nxs; ++i) { c->xs[i].valid = 0; c->xs[i].pinned = 0; }
+    R.barrier();   // slab mode: the next 3-D FFT may write a peer's ping-pong buffer that served as a slot here
     // :561-574
     grid_scale(phi, g1);
     grid_scale(phi2, g2);

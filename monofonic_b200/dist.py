@@ -63,17 +63,18 @@ def _make_exchange_cb(lib, world, device):
 
 
 def pick_nslots(nbytes, n, world, free_bytes, lpt_order=3, particle_bytes_per_cell=32):
-    """how many exchange buffers to put into the peer-mapped block: 2 (the ping-pong pair of the 3-D FFTs) + the slots of the
-    shared-transform source stage (8 at 3LPT, 7 as the tight variant; 4 at 2LPT) if everything else of an LPT run still
-    fits next to them - 8 grids, the particle arrays (also the chunk workspace of that stage) and a safety margin -
-    else 2, which leaves the memory to the per-product workspace."""
+    """how many exchange buffers to put into the peer-mapped block.  The 3-D FFTs need 2 (a ping-pong pair); the shared-transform
+    source stage uses ALL of them as slots and wants 8 at 3LPT (7: one target per loop; 6, 5: targets split over several
+    loops) and 4 at 2LPT.  The largest count is taken that leaves room for everything else of an LPT run - 8 grids, the
+    particle arrays (which also serve as the chunk workspace of that stage) and a safety margin; below the minimum the
+    block keeps 2 buffers and the memory goes to the per-product workspace."""
     if lpt_order < 2:
         return 2
     cells = n[0] * n[1] * n[2] // world
     fixed = 8 * 8 * cells * (n[2] + 2) // n[2] + particle_bytes_per_cell * cells + (3 << 30)
-    for extra in ((8, 7) if lpt_order > 2 else (4,)):
-        if (2 + extra) * nbytes + fixed <= free_bytes:
-            return 2 + extra
+    for k in ((8, 7, 6, 5) if lpt_order > 2 else (4,)):
+        if k * nbytes + fixed <= free_bytes:
+            return k
     return 2
 
 

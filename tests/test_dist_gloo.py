@@ -50,7 +50,16 @@ def test_slab_pipeline_gloo_tight_slots():
     import emu_util
 
     emu_util.build_emu()
-    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "9"])
+    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "7"])
+
+
+def test_slab_pipeline_gloo_split_targets():
+    """5 slots (what 3LPT 2048^3 leaves on 8 GPUs is 6): targets whose products need more X buffers than that go through
+    several loops, the later ones adding to the target"""
+    import emu_util
+
+    emu_util.build_emu()
+    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "5"])
 
 
 def test_slab_pipeline_gloo_borrowed_accumulator():

@@ -30,7 +30,13 @@ def test_slab_pipeline_two_exchange_buffers():
 def test_slab_pipeline_tight_slots():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    run_world(2, ["--grid", "64", "--lattice", "bcc", "--nslots", "9"])
+    run_world(2, ["--grid", "64", "--lattice", "bcc", "--nslots", "7"])
+
+
+def test_slab_pipeline_split_targets():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, ["--grid", "64", "--lattice", "sc", "--nslots", "6"])
 
 
 def test_slab_pipeline_nccl_staged():

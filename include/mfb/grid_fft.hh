@@ -28,7 +28,26 @@
 #ifndef MFB_HAVE_REFERENCE_GENERAL_HH
 using real_t = double;                   // CODE_PRECISION=DOUBLE (include/general.hh:50-53)
 using ccomplex_t = std::complex<double>;
+// stand-in for the reference's vec3_t (include/math/vec3.hh) where its headers are not on the include path
+template <typename T> struct vec3_t {
+    T x, y, z;
+    vec3_t() : x(0), y(0), z(0) {}
+    vec3_t(T a, T b, T c) : x(a), y(b), z(c) {}
+    T& operator[](size_t i) noexcept { return i == 0 ? x : (i == 1 ? y : z); }
+    const T& operator[](size_t i) const noexcept { return i == 0 ? x : (i == 1 ? y : z); }
+    T norm_squared() const noexcept { return x * x + y * y + z * z; }
+    T norm() const noexcept { return std::sqrt(norm_squared()); }
+};
+#else
+#include <math/vec3.hh>
 #endif
+#if defined(__has_include)
+#if __has_include(<hdf5.h>)
+#define MFB_MIRROR_HAVE_HDF5 1
+#include <hdf5.h>
+#endif
+#endif
+#include <vector>
 
 enum space_t { kspace_id, rspace_id };  // include/grid_fft.hh:29  (kspace_id == MFB_KSPACE == 0)
 
@@ -117,10 +136,21 @@ public:
     real_t get_dx(int idim) const noexcept { return dx_[idim]; }
     const std::array<real_t, 3>& get_dx() const noexcept { return dx_; }
     bool is_nyquist_mode(size_t i, size_t j, size_t k) const { return i == n_[0] / 2 || j == n_[1] / 2 || k == n_[2] / 2; }
-    template <typename ft> std::array<ft, 3> get_k(size_t i, size_t j, size_t k) const noexcept {
-        return {ft((real_t(i) - real_t(i > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(j) - real_t(j > nhalf_[1]) * n_[1]) * kfac_[1]),
-                ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2])};
+    template <typename ft> vec3_t<ft> get_k(size_t i, size_t j, size_t k) const noexcept {   // include/grid_fft.hh:281-296
+        return vec3_t<ft>(ft((real_t(i) - real_t(i > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(j) - real_t(j > nhalf_[1]) * n_[1]) * kfac_[1]),
+                          ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2]));
     }
+    template <typename ft> vec3_t<ft> get_r(size_t i, size_t j, size_t k) const noexcept {   // :213-228
+        return vec3_t<ft>(ft(real_t(i + local_0_start_) * dx_[0]), ft(real_t(j) * dx_[1]), ft(real_t(k) * dx_[2]));
+    }
+    template <typename ft> vec3_t<ft> get_unit_r(size_t i, size_t j, size_t k) const noexcept {   // :230-240
+        return vec3_t<ft>(ft(real_t(i + local_0_start_) / real_t(n_[0])), ft(real_t(j) / real_t(n_[1])), ft(real_t(k) / real_t(n_[2])));
+    }
+    template <typename ft> vec3_t<ft> get_unit_r_shifted(size_t i, size_t j, size_t k, const vec3_t<real_t> s) const noexcept {   // :242-252
+        return vec3_t<ft>(ft((real_t(i + local_0_start_) + s.x) / real_t(n_[0])), ft((real_t(j) + s.y) / real_t(n_[1])),
+                          ft((real_t(k) + s.z) / real_t(n_[2])));
+    }
+    vec3_t<size_t> get_cell_idx_3d(size_t i, size_t j, size_t k) const noexcept { return vec3_t<size_t>(i + local_0_start_, j, k); }
     std::array<size_t, 3> get_k3(size_t i, size_t j, size_t k) const noexcept { return {i, j, k}; }
     ccomplex_t gradient(int idim, std::array<size_t, 3> ijk) const {
         real_t rgrad = (ijk[idim] != nhalf_[idim]) ? (real_t(ijk[idim]) - real_t(ijk[idim] > nhalf_[idim]) * n_[idim]) * kfac_[idim] : 0.0;
@@ -201,6 +231,93 @@ public:
         }
     }
 
+    // f(elem, k) / f(elem, r) over every element (include/grid_fft.hh:764-796)
+    template <typename F> void apply_function_k_dep(const F& f) {
+        to_host(true);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
+            auto& e = cdata_[get_idx(i, j, k)]; e = f(e, this->template get_k<real_t>(i, j, k));
+        }
+    }
+    template <typename F> void apply_function_r_dep(const F& f) {
+        to_host(true);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
+            auto& e = data_[get_idx(i, j, k)]; e = f(e, this->template get_r<real_t>(i, j, k));
+        }
+    }
+    // this(x) = f(g1(x), g2(x), ...) in real space / Fourier space, optionally with the index triple or the k vector as
+    // first argument (include/grid_fft.hh:698-762); the fNL / gNL terms of src/ic_generator.cc:402-455 are written with these
+    template <typename F, typename... Grids> void assign_function_of_grids_r(const F& f, Grids&... grids) {
+        to_host(true); (grids.to_host(false), ...);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k)
+            data_[get_idx(i, j, k)] = f((grids.data_[grids.get_idx(i, j, k)])...);
+    }
+    template <typename F, typename... Grids> void assign_function_of_grids_k(const F& f, Grids&... grids) {
+        to_host(true); (grids.to_host(false), ...);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k)
+            cdata_[get_idx(i, j, k)] = f((grids.cdata_[grids.get_idx(i, j, k)])...);
+    }
+    template <typename F, typename... Grids> void assign_function_of_grids_ijk(const F& f, Grids&... grids) {
+        to_host(true); (grids.to_host(false), ...);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k)
+            cdata_[get_idx(i, j, k)] = f(std::array<size_t, 3>{i, j, k}, (grids.cdata_[grids.get_idx(i, j, k)])...);
+    }
+    template <typename F, typename... Grids> void assign_function_of_grids_kdep(const F& f, Grids&... grids) {
+        to_host(true); (grids.to_host(false), ...);
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k)
+            cdata_[get_idx(i, j, k)] = f(this->template get_k<real_t>(i, j, k), (grids.cdata_[grids.get_idx(i, j, k)])...);
+    }
+
+    // ---- diagnostics used by output plugins (output_generic.cc:120, output_grafic2.cc:233-243)
+    //! the real-space field as a dataset [n0][n1][n2] of `fname` (src/grid_fft.cc:806-1047, non-MPI branch).  Uses the HDF5 C
+    //! API of whatever <hdf5.h> the host build provides; without HDF5 on the include path it throws.
+    void Write_to_HDF5(std::string fname, std::string datasetname) const {
+#ifdef MFB_MIRROR_HAVE_HDF5
+        if (space_ != rspace_id) throw std::runtime_error("Write_to_HDF5: grid must be in real space");
+        to_host(false);
+        hid_t file = H5Fopen(fname.c_str(), H5F_ACC_RDWR, H5P_DEFAULT);
+        if (file < 0) file = H5Fcreate(fname.c_str(), H5F_ACC_TRUNC, H5P_DEFAULT, H5P_DEFAULT);
+        if (file < 0) throw std::runtime_error("Write_to_HDF5: cannot open " + fname);
+        hsize_t dims[3] = {hsize_t(n_[0]), hsize_t(n_[1]), hsize_t(n_[2])};
+        const hid_t fspace = H5Screate_simple(3, dims, nullptr);
+        const hid_t dset = H5Dcreate2(file, datasetname.c_str(), H5T_NATIVE_DOUBLE, fspace, H5P_DEFAULT, H5P_DEFAULT, H5P_DEFAULT);
+        std::vector<double> plane(n_[1] * n_[2]);
+        hsize_t count[3] = {1, hsize_t(n_[1]), hsize_t(n_[2])};
+        const hid_t mspace = H5Screate_simple(3, count, nullptr);
+        for (size_t i = 0; i < n_[0]; ++i) {   // one x-plane at a time: strip the two pad reals per row
+            for (size_t j = 0; j < n_[1]; ++j) for (size_t k = 0; k < n_[2]; ++k) plane[j * n_[2] + k] = data_[(i * n_[1] + j) * npr_ + k];
+            hsize_t offset[3] = {hsize_t(i), 0, 0};
+            H5Sselect_hyperslab(fspace, H5S_SELECT_SET, offset, nullptr, count, nullptr);
+            H5Dwrite(dset, H5T_NATIVE_DOUBLE, mspace, fspace, H5P_DEFAULT, plane.data());
+        }
+        H5Sclose(mspace); H5Dclose(dset); H5Sclose(fspace); H5Fclose(file);
+#else
+        (void)fname; (void)datasetname;
+        throw std::runtime_error("Write_to_HDF5: this host build has no <hdf5.h>");
+#endif
+    }
+    //! spherically binned power spectrum of the k-space field (src/grid_fft.cc:1104-1176): mean |f(k)|^2 per |k| bin
+    void Compute_PowerSpectrum(std::vector<double>& bin_k, std::vector<double>& bin_P, std::vector<double>& bin_eP, std::vector<size_t>& bin_count) {
+        FourierTransformForward();
+        to_host(false);
+        const real_t kmin = kfac_[0], kmax = kfac_[0] * real_t(n_[0] / 2), dklog = std::log(kmax / kmin) / real_t(bin_k.size());
+        std::fill(bin_k.begin(), bin_k.end(), 0.0); std::fill(bin_P.begin(), bin_P.end(), 0.0);
+        std::fill(bin_eP.begin(), bin_eP.end(), 0.0); std::fill(bin_count.begin(), bin_count.end(), size_t(0));
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
+            const real_t kk = this->template get_k<real_t>(i, j, k).norm();
+            if (!(kk >= kmin && kk < kmax)) continue;
+            const size_t b = std::min(bin_k.size() - 1, size_t(std::log(kk / kmin) / dklog));
+            const double w = (k == 0 || k == n_[2] / 2) ? 1.0 : 2.0, p = std::norm(cdata_[get_idx(i, j, k)]);
+            bin_k[b] += w * kk; bin_P[b] += w * p; bin_eP[b] += w * p * p; bin_count[b] += size_t(w);
+        }
+        const real_t volfac = length_[0] * length_[1] * length_[2] / std::pow(2.0 * M_PI, 3.0);
+        for (size_t b = 0; b < bin_k.size(); ++b) {
+            if (!bin_count[b]) continue;
+            const double c = double(bin_count[b]);
+            bin_k[b] /= c; bin_P[b] = bin_P[b] / c * volfac;
+            bin_eP[b] = std::sqrt(std::max(0.0, bin_eP[b] / c * volfac * volfac - bin_P[b] * bin_P[b])) / std::sqrt(c);
+        }
+    }
+
 private:
     mfb_grid* h_;
     mutable bool host_dirty_, dev_newer_;
@@ -218,6 +335,7 @@ private:
     mfb_grid* prep() { to_device(); return h_; }
     void dev_op(int rc) { mfb_detail::check(rc); dev_newer_ = true; }
     void after_k() { space_ = kspace_id; set_sizes(); }
+    template <typename, bool> friend class Grid_FFT;
     template <typename, typename> friend class BaseConvolver;
     template <typename> friend class OrszagConvolver;
     template <typename> friend class mfb_lattice_access;

@@ -1,0 +1,2 @@
+// tests/cpp/shadow - the reference header name resolved to the GPU-backed drop-in (tests/test_plugin_dropin.py)
+#include <mfb/particle_generator.hh>

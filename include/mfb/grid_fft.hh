@@ -12,7 +12,10 @@
 //  * the arbitrary-lambda functor family (apply_function_k/_r/_k_dep/_r_dep, assign_function_of_grids_*)
 //    runs on the HOST mirror (it takes a host lambda); the pipeline itself uses the named device operators
 //    of mfb200.h instead (mfb_noise_condition, mfb_apply_radial_table, mfb_lpt_assemble, ...).
-//  * bdistributed == false layout ([kx][ky][kz]); the multi-GPU slab layer is separate.
+//  * Grid_FFT<real_t, true> is a SLAB of the reference's FFTW-MPI decomposition (src/grid_fft.cc:115-192): one host process
+//    per GPU, local_0_* / local_1_* taken from the library (mfb_grid_local) after mfb_dist_init + mfb_dist_connect (the
+//    host carries the 64-byte IPC handles between its ranks, e.g. with MPI_Allgather - INTEGRATION.md), k-space stored
+//    transposed [ky_loc][kx][kz] exactly like FFTW_MPI_TRANSPOSED_OUT.  Grid_FFT<real_t, false> is the whole grid.
 #pragma once
 #include <array>
 #include <cassert>
@@ -57,10 +60,17 @@ inline void check(int rc) {
 }
 }  // namespace mfb_detail
 
-template <typename data_t_, bool bdistributed = false>
+// like the reference (include/grid_fft.hh:31-40): a host built with USE_MPI (one rank per GPU) gets slab grids by default
+#ifndef GRID_FFT_DISTRIBUTED
+#ifdef USE_MPI
+#define GRID_FFT_DISTRIBUTED true
+#else
+#define GRID_FFT_DISTRIBUTED false
+#endif
+#endif
+template <typename data_t_, bool bdistributed = GRID_FFT_DISTRIBUTED>
 class Grid_FFT {
     static_assert(std::is_same<data_t_, double>::value, "the device path is FP64 real grids (PPT c2c: DESIGN.md section 8)");
-    static_assert(!bdistributed, "non-distributed host view; multi-GPU slabs are handled below the ABI");
 
 public:
     using data_t = data_t_;
@@ -100,7 +110,14 @@ public:
         int n[3] = {int(n_[0]), int(n_[1]), int(n_[2])};
         double L[3] = {length_[0], length_[1], length_[2]};
         mfb_detail::check(mfb_grid_create(&h_, n, L, space_ == kspace_id ? MFB_KSPACE : MFB_RSPACE));
-        ntot_ = (n_[2] + 2) * n_[1] * n_[0];
+        int loc[4];
+        const bool slab = mfb_grid_local(h_, loc) != 0;   // {local_0_start_, local_0_size_, local_1_start_, local_1_size_}
+        if (slab != bdistributed) {
+            mfb_grid_destroy(h_); h_ = nullptr;
+            throw std::runtime_error(bdistributed ? "Grid_FFT<.., true>: the library is not slab-decomposed (mfb_dist_init)"
+                                                  : "Grid_FFT<.., false>: the library is slab-decomposed - use Grid_FFT<real_t, true>");
+        }
+        ntot_ = mfb_grid_ntot(h_);   // (n2 + 2) n1 n0, or the slab's share (src/grid_fft.cc:45,122)
         data_ = static_cast<data_t*>(std::calloc(ntot_, sizeof(data_t)));
         if (!data_) throw std::runtime_error("Grid_FFT: host mirror allocation failed");
         cdata_ = reinterpret_cast<ccomplex_t*>(data_);
@@ -113,8 +130,7 @@ public:
             kny_[i] = kfac_[i] * n_[i] / 2;
             dx_[i] = length_[i] / n_[i];
         }
-        local_0_size_ = n_[0]; local_1_size_ = n_[1];
-        local_0_start_ = 0; local_1_start_ = 0;
+        local_0_start_ = loc[0]; local_0_size_ = loc[1]; local_1_start_ = loc[2]; local_1_size_ = loc[3];
         set_sizes();
         ballocated_ = true;
         host_dirty_ = true;  // calloc'ed zeros are the truth until a device op runs
@@ -137,6 +153,11 @@ public:
     const std::array<real_t, 3>& get_dx() const noexcept { return dx_; }
     bool is_nyquist_mode(size_t i, size_t j, size_t k) const { return i == n_[0] / 2 || j == n_[1] / 2 || k == n_[2] / 2; }
     template <typename ft> vec3_t<ft> get_k(size_t i, size_t j, size_t k) const noexcept {   // include/grid_fft.hh:281-296
+        if (bdistributed) {   // transposed slab: the first index runs over the local ky rows
+            const size_t ip = i + size_t(local_1_start_);
+            return vec3_t<ft>(ft((real_t(j) - real_t(j > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(ip) - real_t(ip > nhalf_[1]) * n_[1]) * kfac_[1]),
+                              ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2]));
+        }
         return vec3_t<ft>(ft((real_t(i) - real_t(i > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(j) - real_t(j > nhalf_[1]) * n_[1]) * kfac_[1]),
                           ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2]));
     }
@@ -151,8 +172,11 @@ public:
                           ft((real_t(k) + s.z) / real_t(n_[2])));
     }
     vec3_t<size_t> get_cell_idx_3d(size_t i, size_t j, size_t k) const noexcept { return vec3_t<size_t>(i + local_0_start_, j, k); }
-    std::array<size_t, 3> get_k3(size_t i, size_t j, size_t k) const noexcept { return {i, j, k}; }
-    ccomplex_t gradient(int idim, std::array<size_t, 3> ijk) const {
+    std::array<size_t, 3> get_k3(size_t i, size_t j, size_t k) const noexcept {   // include/grid_fft.hh:315-318
+        return bdistributed ? std::array<size_t, 3>({j, i + size_t(local_1_start_), k}) : std::array<size_t, 3>({i, j, k});
+    }
+    ccomplex_t gradient(int idim, std::array<size_t, 3> ijk) const {   // include/grid_fft.hh:376-385
+        if (bdistributed) { ijk[0] += size_t(local_1_start_); std::swap(ijk[0], ijk[1]); }
         real_t rgrad = (ijk[idim] != nhalf_[idim]) ? (real_t(ijk[idim]) - real_t(ijk[idim] > nhalf_[idim]) * n_[idim]) * kfac_[idim] : 0.0;
         return ccomplex_t(0.0, rgrad);
     }
@@ -321,9 +345,9 @@ public:
 private:
     mfb_grid* h_;
     mutable bool host_dirty_, dev_newer_;
-    void set_sizes() {  // src/grid_fft.cc:98-111, 230-233, 262-265
-        if (space_ == rspace_id) { sizes_ = {n_[0], n_[1], n_[2], npr_}; }
-        else { sizes_ = {n_[1], n_[0], npc_, npc_}; }
+    void set_sizes() {  // src/grid_fft.cc:98-111, 176-189, 230-233, 262-265
+        if (space_ == rspace_id) { sizes_ = {size_t(local_0_size_), n_[1], n_[2], npr_}; }
+        else { sizes_ = {size_t(local_1_size_), n_[0], npc_, npc_}; }
     }
     void to_host(bool will_write) const {
         if (dev_newer_) { mfb_detail::check(mfb_grid_download(h_, data_)); dev_newer_ = false; }

@@ -9,9 +9,7 @@
 //   z_c2r_kernel/z_r2c_kernel : the contiguous-axis real<->half-complex pass, two real rows per
 //                         complex FFT, in place in the reference's padded-row layout
 //                         (src/grid_fft.cc:45-54,73-74).
-//   z_conv_kernel       : fused  c2r(A) , c2r(B) , A*B , r2c  along z for the padded grid -
-//                         the padded real-space fields never touch HBM
-//                         (include/convolution.hh:524-532 collapsed into one pass).
+//   (the fused z passes of the dealiased products live in fft_kernels_z2.cuh / fft_kernels_zm.cuh)
 #pragma once
 #include "fft_core.cuh"
 
@@ -266,72 +264,6 @@ __global__ void __launch_bounds__(P::NTHREADS) z_c2c_kernel(double2* __restrict_
         const int l = idx / N, k = idx - l * N;
         const double2 z = sm[P::smem_addr(P::pos_of_freq(k), l)];
         if (row0 + l < nrows) mfb_st_stream(data + (row0 + l) * N + k, make_double2(z.x * scale, z.y * sy));
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused z pass of a dealiased product on the padded grid (n = 3N/2):
-//   rows of A and B hold the nzin = N/2 retained k_z modes; per row
-//     a + i b = IFFT_n( A^ + i B^ ) (Hermitian extension, zero padded), p = a*b,
-//   two rows' products are packed into one complex line, FFT_n, unpacked, and the first nzin
-//   modes are written to `out`.  DIF backward + DIT forward => no permutation in between.
-template <class P>
-__global__ void __launch_bounds__(P::NTHREADS) z_conv_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin,
-                                                             double2* __restrict__ out, ptrdiff_t in_pitch, ptrdiff_t out_pitch,
-                                                             long nrows, int nzin, double scale, const double2* __restrict__ tw,
-                                                             int accumulate = 0) {
-    MFB_DYN_SMEM(double2, sm);
-    constexpr int N = P::N, T = P::T, H = T / 2;
-    static_assert(T >= 2, "need at least two lines per tile");
-    const int tid = threadIdx.x;
-    const int line = tid % T, q = tid / T;
-    const long row0 = long(blockIdx.x) * T;
-    // zero the padded band [nzin, N - nzin]
-    const int nzero = N - 2 * nzin + 1;
-    for (int idx = tid; idx < T * nzero; idx += P::NTHREADS) {
-        const int l = idx / nzero, k = nzin + (idx - l * nzero);
-        sm[P::smem_addr(k, l)] = make_double2(0.0, 0.0);
-    }
-    for (int idx = tid; idx < T * nzin; idx += P::NTHREADS) {
-        const int l = idx / nzin, k = idx - l * nzin;
-        const long r = row0 + l;
-        double2 x1 = make_double2(0.0, 0.0), x2 = x1;
-        if (r < nrows) {
-            x1 = mfb_ld_stream(Ain + r * in_pitch + k);
-            x2 = mfb_ld_stream(Bin + r * in_pitch + k);
-        }
-        if (k == 0) { x1.y = 0.0; x2.y = 0.0; }
-        sm[P::smem_addr(k, l)] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
-        if (k > 0) sm[P::smem_addr(N - k, l)] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
-    }
-    __syncthreads();
-    NoLoader nl; NoStorer ns;
-    fft_tile<P, false, false, false>(sm, tw, line, q, true, nl, ns);   // DIF: result digit-reversed
-    __syncthreads();
-    // product, in digit-reversed order: a = Re, b = -Im (conj trick); pack lines l and l+H
-    for (int idx = tid; idx < H * N; idx += P::NTHREADS) {
-        const int p = idx / H, l = idx - p * H;
-        const double2 u = sm[P::smem_addr(p, l)];
-        const double2 w = sm[P::smem_addr(p, l + H)];
-        sm[P::smem_addr(p, l)] = make_double2(-u.x * u.y, -w.x * w.y);
-    }
-    __syncthreads();
-    fft_tile<P, true, false, false>(sm, tw, line, q, line < H, nl, ns);  // DIT: natural order out
-    __syncthreads();
-    for (int idx = tid; idx < H * nzin; idx += P::NTHREADS) {
-        const int l = idx / nzin, k = idx - l * nzin;
-        const long r1 = row0 + l, r2 = row0 + l + H;
-        const double2 zk = sm[P::smem_addr(k, l)];
-        const double2 zm = sm[P::smem_addr((N - k) % N, l)];
-        const double h = 0.5 * scale;
-        double2 x1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
-        double2 x2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
-        if (accumulate) {
-            if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); x1.x += o.x; x1.y += o.y; }
-            if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); x2.x += o.x; x2.y += o.y; }
-        }
-        if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, x1);
-        if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, x2);
     }
 }
 

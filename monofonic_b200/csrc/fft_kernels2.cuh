@@ -53,8 +53,8 @@ MFB_D void strided2_mid_stages(double2* __restrict__ sm, const double2* __restri
 
 // One tile (fixed a, T adjacent k_z starting at z0) of a strided pass, executed by P::NTHREADS threads that share `sm` and
 // synchronise with `sync`.  `after_load` is called once by every thread when stage 0 has consumed its inputs.
-// SMEM_IN: the tile's input already sits in `sm` at its stage-0 leg positions (staged there asynchronously by
-// strided3_kernel); stage 0 then runs in place like the middle stages.
+// SMEM_IN: the tile's input already sits in `sm` at its stage-0 leg positions (staged there asynchronously, e.g. by the
+// double-buffered strided3_kernel of scripts/kbench/kbench_legacy_kernels.cuh); stage 0 then runs in place like the middle stages.
 template <class P, int MODE, bool BATCH0, bool SMEM_IN = false, class Sync, class AfterLoad>
 MFB_D void strided2_tile(const StridedArgs& A, const double2* __restrict__ tw, double2* __restrict__ sm, int tid, int a, int z0,
                          const Sync& sync, const AfterLoad& after_load) {
@@ -263,62 +263,6 @@ __global__ void __launch_bounds__(P::NTHREADS, MINB) strided2_kernel(StridedArgs
     const int a = blockIdx.x / tiles_per_a;
     const int z0 = (blockIdx.x - a * tiles_per_a) * P::T;
     strided2_tile<P, MODE, BATCH0>(A, tw, sm, threadIdx.x, a, z0, CtaSync(), [] {});
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// strided3_kernel - persistent, double-buffered version of the strided pass.
-//
-// What bounds strided2_kernel is not the access pattern - a bare copy with the same 64..128-byte segments at an 8 KB
-// stride runs at 6.0-6.5 TB/s (profiles/r01_kbench_segment_copy.txt) - but bytes in flight: one tile per CTA issues its
-// global loads in stage 0, waits for them, and has nothing outstanding during the shared-memory stages, so on average
-// ~20 KB per SM are in flight where ~45 KB are needed (6.5 TB/s x ~1 us / 148 SMs), and the pass sustains 3.1-4.0 TB/s.
-// (Splitting the CTA into two warp groups that take turns loading made it worse - half the loads in flight again:
-// profiles/r01_kbench_pingpong_negative.txt.)
-// Here a CTA owns TWO tile buffers.  While the butterflies run on one, the input of the CTA's next tile streams into
-// the other with 16-byte cp.async copies (LDGSTS, no register staging), landing directly at the stage-0 leg positions,
-// so stage 0 is an in-place shared-memory stage too and a full tile of loads is in flight for the whole compute phase.
-template <class P, int MODE>
-__global__ void __launch_bounds__(P::NTHREADS, 1) strided3_kernel(StridedArgs A, const double2* __restrict__ tw) {
-    MFB_DYN_SMEM(double2, sm_all);
-    constexpr int N = P::N, T = P::T, NT = P::NTHREADS;
-    constexpr int TILE = N * T;                      // complex elements per buffer
-    const int tid = threadIdx.x;
-    const int tiles_per_a = (A.nz + T - 1) / T;
-    const long ntiles = long(A.na) * tiles_per_a;
-    const int hin = A.n_in / 2, shift = N - A.n_in;  // pad map: source sample s sits at position s (+ shift in the upper half)
-
-    // asynchronous staging of one tile's input; lines / tiles that carry no data are not touched (stage 0 reads zeros)
-    auto stage_in = [&](long tile, double2* buf) {
-        const int a = int(tile / tiles_per_a);
-        const int z0 = int(tile - long(a) * tiles_per_a) * T;
-        if ((a + A.a_off == A.a_skip) || (z0 >= A.nz_fft)) return;
-        const int l = tid % T, p0 = tid / T;
-        const int iz = z0 + l;
-        if (iz >= A.nz || iz >= A.nz_fft) return;
-        const double2* g = A.in + ptrdiff_t(a) * A.in_as + iz;
-        for (int s_ = p0; s_ < A.n_in; s_ += NT / T) {
-            const int pos = (MODE == SM_PAD && s_ >= hin) ? s_ + shift : s_;
-            mfb_cp_async16(buf + pos * T + l, g + ptrdiff_t(s_) * A.in_ps);
-        }
-    };
-
-    long tile = blockIdx.x;
-    if (tile >= ntiles) return;
-    int cur = 0;
-    stage_in(tile, sm_all);
-    mfb_cp_async_commit();
-    for (; tile < ntiles; tile += gridDim.x) {
-        const long next = tile + gridDim.x;
-        if (next < ntiles) stage_in(next, sm_all + (cur ^ 1) * TILE);
-        mfb_cp_async_commit();                       // (possibly empty) group of the next tile
-        mfb_cp_async_wait_but_one();                 // this tile's input has landed (this thread's copies) ...
-        __syncthreads();                             // ... and everybody else's
-        const int a = int(tile / tiles_per_a);
-        const int z0 = int(tile - long(a) * tiles_per_a) * T;
-        strided2_tile<P, MODE, false, true>(A, tw, sm_all + cur * TILE, tid, a, z0, CtaSync(), [] {});
-        __syncthreads();                             // the buffer is refilled two iterations from now at the earliest,
-        cur ^= 1;                                    // but the next iteration's staging targets it right away
-    }
 }
 
 }  // namespace mfb

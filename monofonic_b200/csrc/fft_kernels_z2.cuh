@@ -1,20 +1,14 @@
-// fft_kernels_z2.cuh - second-generation fused z pass of a dealiased product (FP64, sm_100a).
+// fft_kernels_z2.cuh - fused z pass of ONE dealiased product (FP64, sm_100a): z_conv3_kernel, the per-product path of the
+// convolver (named products of BaseConvolver, and the source stage when the slot workspace cannot be had).
 //
-// Same contract as z_conv_kernel (fft_kernels.cuh): per (x,y) row of the padded grid, c2r of both operands,
-// pointwise product, r2c, all in shared memory.  Differences (from the ncu capture of the first version,
-// profiles/r01_ncu_full_z_conv_768.txt: issue slots 50 % busy with 2/3 non-FP64 instructions, FP64 pipe 36 %,
-// half of the lanes idle in the forward transform, 16 warps/SM):
+// Per (x,y) row of the padded grid: c2r of both operands, pointwise product, r2c, all in shared memory
+// (include/convolution.hh:524-532 collapsed into one pass; the padded real-space fields never touch HBM).
 //   * line-major shared memory: each row is ONE contiguous line (1 pad slot per 8 elements), a warp works on
-//     32 consecutive butterflies of one row.  Rows are contiguous in HBM, so the tile height no longer has to
-//     be 8 for coalescing: a CTA holds RPC rows (default one product pair), 44 KB instead of 98 KB at n = 768,
-//     which more than doubles the resident warps per SM;
-//   * the raw operand rows arrive by 16-byte cp.async copies (no register staging, fully coalesced);
-//   * the Hermitian extension  conj(A^ + iB^)  is built inside the first butterfly stage, the product inside
-//     the first stage of the forward transform: no separate pack / product sweeps over shared memory;
-//   * the forward transform of a product pair runs on all the threads of the pair;
-//   * every shared-memory address is a per-butterfly base plus compile-time immediates.
-// The arithmetic (two-for-one packing, DIF backward -> product in digit-reversed order -> DIT forward,
-// unpacking) is the one of the first version.
+//     32 consecutive butterflies of one row; a CTA holds one product pair;
+//   * the Hermitian extension  conj(A^ + iB^)  is built inside the first butterfly stage straight from global memory, the
+//     product inside the innermost stages: no separate pack / product sweeps over shared memory;
+//   * two-for-one packing, DIF backward -> product in digit-reversed order -> DIT forward, unpacking: no permutation.
+// Earlier generations (tile-major gen 1, cp.async-staged gen 2) are in scripts/kbench/kbench_legacy_kernels.cuh.
 #pragma once
 #include "fft_kernels.cuh"
 
@@ -76,135 +70,6 @@ template <class P, int s, int NT> MFB_D void z2_dit_mid(double2* ln, const doubl
         z2_dit_mid<P, s - 1, NT>(ln, tw, q);
     }
 }
-
-// P::TPL threads per row, RPC rows per CTA (even).  P::T is not used.
-template <class P, int RPC, int MINB>
-__global__ void __launch_bounds__(P::TPL* RPC, MINB)
-    z_conv2_kernel(const double2* __restrict__ Ain, const double2* __restrict__ Bin, double2* __restrict__ out, ptrdiff_t in_pitch,
-                   ptrdiff_t out_pitch, long nrows, double scale, const double2* __restrict__ tw, int accumulate = 0) {
-    MFB_DYN_SMEM(double2, sm);
-    constexpr int N = P::N, S = P::S, TPL = P::TPL, NT = TPL * RPC;
-    constexpr int NZ = N / 3;             // retained k_z modes of each operand row
-    constexpr int LW = zpad(N) + 1;       // padded line length
-    static_assert(P::radix(0) % 3 == 0, "the z pass needs a first radix that is a multiple of 3");
-    static_assert(RPC % 2 == 0 && S >= 2, "rows per CTA must be even");
-    double2* work = sm;                   // RPC lines of LW
-    double2* raw = sm + RPC * LW;         // RPC x {A,B} rows of NZ
-    const int tid = threadIdx.x;
-    const long row0 = long(blockIdx.x) * RPC;
-
-    // ---- raw operand rows: global -> shared, asynchronous 16-byte copies
-    for (int idx = tid; idx < RPC * 2 * NZ; idx += NT) {
-        const int o = idx / NZ, k = idx - o * NZ;
-        const long r = row0 + (o >> 1);
-        double2* d = raw + idx;
-        if (r < nrows) mfb_cp_async16(d, ((o & 1) ? Bin : Ain) + r * in_pitch + k);
-        else *d = make_double2(0.0, 0.0);
-    }
-    mfb_cp_async_wait_all();
-    __syncthreads();
-
-    // ---- backward transform of conj(A^ + i B^) (Hermitian-extended, zero padded), DIF
-    {
-        const int l = tid / TPL, q = tid - l * TPL;
-        double2* ln = work + l * LW;
-        const double2* ra = raw + (2 * l) * NZ;
-        const double2* rb = ra + NZ;
-        constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
-#pragma unroll 1
-        for (int j = q; j < M; j += TPL) {
-            double2 v[r];
-#pragma unroll
-            for (int t = 0; t < K3; ++t) {   // positions p = j + t*M < NZ: conj(X1[p] + i X2[p])
-                double2 x1 = ra[j + t * M], x2 = rb[j + t * M];
-                if (t == 0 && j == 0) { x1.y = 0.0; x2.y = 0.0; }  // c2r ignores Im of the self-conjugate mode
-                v[t] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
-            }
-#pragma unroll
-            for (int t = K3; t < 2 * K3; ++t) v[t] = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int t = 2 * K3; t < r; ++t) {  // positions p = N - k, k = (r-t)*M - j in (0, NZ]
-                const int k = (r - t) * M - j;
-                if (t == 2 * K3 && j == 0) { v[t] = make_double2(0.0, 0.0); continue; }  // k == NZ: dropped Nyquist
-                const double2 x1 = ra[k], x2 = rb[k];
-                v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
-            }
-            Dft<r>::run(v);
-#pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
-            double2* sp = ln + zpad(j);
-#pragma unroll
-            for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
-        }
-        z2_dif_rest<P, 1, TPL>(ln, tw, q);
-    }
-    __syncthreads();
-
-    // ---- forward transform of the product pair (p_even + i p_odd), DIT; the product is formed on the fly
-    {
-        constexpr int PT = 2 * TPL;           // threads per pair
-        const int m = tid / PT, q = tid - m * PT;
-        double2* l0 = work + (2 * m) * LW;
-        const double2* l1 = l0 + LW;
-        {
-            constexpr int r = P::radix(S - 1), Bn = N / r;  // innermost stage: M == 1, no twiddles
-#pragma unroll 1
-            for (int b = q; b < Bn; b += PT) {
-                const int base = b * r;
-                double2* sp = l0 + zpad(base);
-                const double2* sq = l1 + zpad(base);
-                double2 v[r];
-#pragma unroll
-                for (int t = 0; t < r; ++t) {
-                    const double2 u = sp[zleg<1, r>(base, t)], w = sq[zleg<1, r>(base, t)];
-                    v[t] = make_double2(-u.x * u.y, -w.x * w.y);  // a = Re, b = -Im (conj trick)
-                }
-                Dft<r>::run(v);
-#pragma unroll
-                for (int u = 0; u < r; ++u) sp[zleg<1, r>(base, u)] = v[u];
-            }
-        }
-        z2_dit_mid<P, S - 2, PT>(l0, tw, q);
-        __syncthreads();
-        {
-            constexpr int r = P::radix(0), M = N / r;  // outermost stage: natural-order output
-#pragma unroll 1
-            for (int j = q; j < M; j += PT) {
-                double2* sp = l0 + zpad(j);
-                double2 v[r];
-#pragma unroll
-                for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(j, t)];
-#pragma unroll
-                for (int u = 1; u < r; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * M + j));
-                Dft<r>::run(v);
-#pragma unroll
-                for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- unpack the two half-spectra and store the retained modes
-    {
-        const double h = 0.5 * scale;
-        for (int idx = tid; idx < (RPC / 2) * NZ; idx += NT) {
-            const int m = idx / NZ, k = idx - m * NZ;
-            const double2* l0 = work + (2 * m) * LW;
-            const double2 zk = l0[zpad(k)];
-            const double2 zm = l0[zpad((N - k) % N)];
-            const long r1 = row0 + 2 * m, r2 = r1 + 1;
-            double2 v1 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
-            double2 v2 = make_double2(h * (zk.y + zm.y), -h * (zk.x - zm.x));
-            if (accumulate) {   // sum of products of one target, formed before the (single) forward y/x passes
-                if (r1 < nrows) { const double2 o = mfb_ld_stream(out + r1 * out_pitch + k); v1.x += o.x; v1.y += o.y; }
-                if (r2 < nrows) { const double2 o = mfb_ld_stream(out + r2 * out_pitch + k); v2.x += o.x; v2.y += o.y; }
-            }
-            if (r1 < nrows) mfb_st_stream(out + r1 * out_pitch + k, v1);
-            if (r2 < nrows) mfb_st_stream(out + r2 * out_pitch + k, v2);
-        }
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------
 // Third step (z_conv3_kernel): the fused z pass is bound by shared-memory / L1 bandwidth (about 8600 16-byte
@@ -441,7 +306,6 @@ __global__ void __launch_bounds__(P::TPL* RPC, MINB)
     }
 }
 
-template <class P, int RPC> constexpr size_t z_conv2_smem() { return size_t(RPC) * (zpad(P::N) + 1 + 2 * (P::N / 3)) * sizeof(double2); }
 template <class P, int RPC> constexpr size_t z_conv3_direct_smem() { return size_t(RPC) * (zpad(P::N) + 1) * sizeof(double2); }
 
 }  // namespace mfb

@@ -48,189 +48,6 @@ struct ZmArgs {
     double kfz;         // 2 pi / L_z
 };
 
-template <class P, int MINB>
-__global__ void __launch_bounds__(2 * P::TPL, MINB) z_multi_kernel(ZmArgs A, const double2* __restrict__ tw) {
-    MFB_DYN_SMEM(double2, sm);
-    constexpr int N = P::N, S = P::S, TPL = P::TPL, PT = 2 * TPL, NT = PT;
-    constexpr int NZ = N / 3;
-    constexpr int LW = zpad(N) + 1;
-    static_assert(P::radix(0) % 3 == 0, "the z pass needs a first radix that is a multiple of 3");
-    static_assert(S >= 2, "at least two stages");
-    double2* work = sm;              // two padded lines: the rows of the pair
-    double2* acc = sm + 2 * LW;      // (p_even, p_odd) summed over the products, digit-reversed order (only if nprod > 1)
-    const int tid = threadIdx.x;
-    const long row0 = long(blockIdx.x) * 2;
-    const int l = tid / TPL, ql = tid - l * TPL;     // stage 0: one row per half of the CTA
-    const int q = tid;                               // pair stages: all threads on the pair
-    double2* ln = work + l * LW;
-    const bool row_ok = row0 + l < A.nrows;
-    const ptrdiff_t roff = (row0 + l) * A.in_pitch;
-    const int nprod = A.nprod;
-
-#pragma unroll 1
-    for (int ip = 0; ip < nprod; ++ip) {
-        const ZmProduct& pr = A.prod[ip];
-        if (ip > 0) __syncthreads();   // the innermost step of the previous product has read both work lines
-        // ---- DIF stage 0 of this thread's row: conj(A^ + i B^), Hermitian-extended and zero padded, built in the legs
-        {
-            constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
-            const bool square = pr.square != 0;
-            const int na = pr.a.n, nb = square ? 0 : pr.b.n;
-            const double2* pa0 = pr.a.t[0].p + roff;
-            const double2* pa1 = pr.a.t[1].p + roff;
-            const double2* pb0 = pr.b.t[0].p + roff;
-            const double2* pb1 = pr.b.t[1].p + roff;
-            const double ca0 = pr.a.t[0].c, ca1 = pr.a.t[1].c, cb0 = pr.b.t[0].c, cb1 = pr.b.t[1].c;
-            const int ea0 = pr.a.t[0].e, ea1 = pr.a.t[1].e, eb0 = pr.b.t[0].e, eb1 = pr.b.t[1].e;
-            auto ld = [&](const double2* p) -> double2 { return row_ok ? mfb_ld_stream(p) : make_double2(0.0, 0.0); };
-            auto kpow = [&](double kz, int e, double c) -> double { return e == 0 ? c : (e == 1 ? c * kz : c * kz * kz); };
-#pragma unroll 1
-            for (int j = ql; j < M; j += TPL) {
-                double2 xa[2 * K3], xb[2 * K3];
-                int kk[2 * K3];
-#pragma unroll
-                for (int t = 0; t < K3; ++t) kk[t] = j + t * M;                 // lower half: mode k = position
-#pragma unroll
-                for (int t = 2 * K3; t < r; ++t) kk[t - K3] = (r - t) * M - j;  // upper half: position N - k
-                // all first-term loads of the butterfly are in flight before the first use
-#pragma unroll
-                for (int m = 0; m < 2 * K3; ++m) {
-                    const bool dropped = (m == K3 && j == 0);                   // k == NZ: the dropped Nyquist sample (not stored)
-                    xa[m] = dropped ? make_double2(0.0, 0.0) : ld(pa0 + kk[m]);
-                    if (nb > 0) xb[m] = dropped ? make_double2(0.0, 0.0) : ld(pb0 + kk[m]);
-                }
-                if (na > 1 || nb > 1) {   // sums / differences of Hessians (convolution.hh:214-274): second term
-                    double2 ya[2 * K3], yb[2 * K3];
-#pragma unroll
-                    for (int m = 0; m < 2 * K3; ++m) {
-                        const bool dropped = (m == K3 && j == 0);
-                        ya[m] = (na > 1 && !dropped) ? ld(pa1 + kk[m]) : make_double2(0.0, 0.0);
-                        yb[m] = (nb > 1 && !dropped) ? ld(pb1 + kk[m]) : make_double2(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int m = 0; m < 2 * K3; ++m) {
-                        const double kz = A.kfz * double(kk[m]);
-                        const double fa0 = kpow(kz, ea0, ca0), fa1 = (na > 1) ? kpow(kz, ea1, ca1) : 0.0;
-                        xa[m] = make_double2(fma(fa1, ya[m].x, fa0 * xa[m].x), fma(fa1, ya[m].y, fa0 * xa[m].y));
-                        if (nb > 0) {
-                            const double fb0 = kpow(kz, eb0, cb0), fb1 = (nb > 1) ? kpow(kz, eb1, cb1) : 0.0;
-                            xb[m] = make_double2(fma(fb1, yb[m].x, fb0 * xb[m].x), fma(fb1, yb[m].y, fb0 * xb[m].y));
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < 2 * K3; ++m) {
-                        const double kz = A.kfz * double(kk[m]);
-                        const double fa0 = kpow(kz, ea0, ca0);
-                        xa[m] = make_double2(fa0 * xa[m].x, fa0 * xa[m].y);
-                        if (nb > 0) {
-                            const double fb0 = kpow(kz, eb0, cb0);
-                            xb[m] = make_double2(fb0 * xb[m].x, fb0 * xb[m].y);
-                        }
-                    }
-                }
-                if (nb == 0) {
-#pragma unroll
-                    for (int m = 0; m < 2 * K3; ++m) xb[m] = xa[m];
-                }
-                double2 v[r];
-#pragma unroll
-                for (int t = 0; t < K3; ++t) {
-                    double2 x1 = xa[t], x2 = xb[t];
-                    if (t == 0 && j == 0) { x1.y = 0.0; x2.y = 0.0; }   // c2r ignores Im of the self-conjugate mode
-                    v[t] = make_double2(x1.x - x2.y, -(x1.y + x2.x));
-                }
-#pragma unroll
-                for (int t = K3; t < 2 * K3; ++t) v[t] = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int t = 2 * K3; t < r; ++t) {
-                    const double2 x1 = xa[t - K3], x2 = xb[t - K3];
-                    v[t] = make_double2(x1.x + x2.y, -(x2.x - x1.y));
-                }
-                Dft<r>::run(v);
-                apply_tw<r>(v, tw + j, M);
-                double2* sp = ln + zpad(j);
-#pragma unroll
-                for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
-            }
-        }
-        // ---- middle DIF stages, both rows of the pair in one thread (twiddles fetched once)
-        z3_dif_mid_pair<P, 1, PT>(work, tw, q);
-        __syncthreads();
-        // ---- innermost DIF stage of both rows -> product -> accumulate; after the last product: innermost DIT stage
-        {
-            constexpr int r = P::radix(S - 1), Bn = N / r;
-            const double cf = pr.coeff;
-            const bool first = ip == 0, last = ip == nprod - 1;
-#pragma unroll 1
-            for (int b = q; b < Bn; b += PT) {
-                const int base = b * r;
-                double2* sp = work + zpad(base);
-                double2* ap = acc + zpad(base);
-                double2 v[r];
-                double p0[r];
-#pragma unroll
-                for (int t = 0; t < r; ++t) v[t] = sp[zleg<1, r>(base, t)];
-                Dft<r>::run(v);
-#pragma unroll
-                for (int t = 0; t < r; ++t) p0[t] = -v[t].x * v[t].y;   // a = Re, b = -Im (conj trick)
-#pragma unroll
-                for (int t = 0; t < r; ++t) v[t] = sp[LW + zleg<1, r>(base, t)];
-                Dft<r>::run(v);
-#pragma unroll
-                for (int t = 0; t < r; ++t) v[t] = make_double2(cf * p0[t], cf * (-v[t].x * v[t].y));
-                if (!first) {
-#pragma unroll
-                    for (int t = 0; t < r; ++t) {
-                        const double2 o = ap[zleg<1, r>(base, t)];
-                        v[t].x += o.x; v[t].y += o.y;
-                    }
-                }
-                if (!last) {
-#pragma unroll
-                    for (int t = 0; t < r; ++t) ap[zleg<1, r>(base, t)] = v[t];
-                } else {
-                    Dft<r>::run(v);
-#pragma unroll
-                    for (int u = 0; u < r; ++u) sp[zleg<1, r>(base, u)] = v[u];
-                }
-            }
-        }
-    }
-    // ---- forward transform of the packed pair (DIT), once per target
-    double2* l0 = work;
-    z2_dit_mid<P, S - 2, PT>(l0, tw, q);
-    __syncthreads();
-    {
-        constexpr int r = P::radix(0), M = N / r;
-#pragma unroll 1
-        for (int j = q; j < M; j += PT) {
-            double2* sp = l0 + zpad(j);
-            double2 v[r];
-#pragma unroll
-            for (int t = 0; t < r; ++t) v[t] = sp[zleg<M, r>(j, t)];
-            apply_tw<r>(v, tw + j, M);
-            Dft<r>::run(v);
-#pragma unroll
-            for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
-        }
-    }
-    __syncthreads();
-    {   // unpack the two half-spectra, store the retained modes
-        const long r1 = row0, r2 = row0 + 1;
-        for (int k = tid; k < NZ; k += NT) {
-            const double2 zk = l0[zpad(k)];
-            const double2 zm = l0[zpad((N - k) % N)];
-            const double2 v1 = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-            const double2 v2 = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
-            if (r1 < A.nrows) mfb_st_stream(A.out + r1 * A.out_pitch + k, v1);
-            if (r2 < A.nrows) mfb_st_stream(A.out + r2 * A.out_pitch + k, v2);
-        }
-    }
-}
-
-template <class P> constexpr size_t z_multi_smem(bool with_acc) { return size_t(with_acc ? 3 : 2) * (zpad(P::N) + 1) * sizeof(double2); }
-
 // ------------------------------------------------------------------------------------------------------------------
 // z_multi2_kernel - the same contract with ONE work line per CTA: the two rows of a pair go through the backward transform
 // one after the other (NT threads on one row), their products land in two padded REAL accumulator lines (sum over the

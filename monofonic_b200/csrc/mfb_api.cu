@@ -272,72 +272,6 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     X(1536, 64, 2, 3, 12, 16, 8)  \
     X(3072, 128, 2, 2, 12, 16, 16)
 
-// double-buffered plans (strided3_kernel): two tile buffers per CTA, so a tile must fit half of the shared memory
-#define MFB_FOR_EACH_PLAN3_B(X)   \
-    X(32, 4, 16, 8, 4)            \
-    X(48, 4, 16, 6, 8)            \
-    X(64, 8, 16, 8, 8)            \
-    X(96, 4, 16, 12, 8)           \
-    X(128, 8, 16, 16, 8)          \
-    X(192, 4, 16, 12, 16)         \
-    X(256, 16, 8, 16, 16)         \
-    X(384, 16, 8, 6, 8, 8)        \
-    X(512, 32, 8, 8, 8, 8)        \
-    X(768, 32, 8, 12, 8, 8)       \
-    X(1024, 64, 4, 16, 8, 8)      \
-    X(1536, 64, 4, 12, 16, 8)
-#define MFB_FOR_EACH_PLAN3_F(X)   \
-    X(48, 4, 16, 8, 6)            \
-    X(96, 4, 16, 8, 12)           \
-    X(192, 4, 16, 16, 12)         \
-    X(384, 16, 8, 8, 8, 6)        \
-    X(768, 32, 8, 8, 8, 12)       \
-    X(1536, 64, 4, 8, 16, 12)
-
-template <class P, int MODE> void launch_strided3_t(const StridedArgs& a, int role) {
-    static bool done = false;
-    constexpr size_t smem = 2 * P::SMEM_BYTES;
-    static_assert(smem <= 227 * 1024, "two tiles must fit the shared memory of one SM");
-    optin_smem(strided3_kernel<P, MODE>, smem, done);
-    const long tiles = long(a.na) * ((a.nz + P::T - 1) / P::T);
-    if (tiles == 0) return;
-    const unsigned grid = unsigned(tiles < g_ctx.num_sms ? tiles : g_ctx.num_sms);   // persistent: one CTA per SM
-    const double2* tw = twiddles2<P>();
-    const double lines = double(a.na - (a.a_skip >= 0 ? 1 : 0)) * double(a.nz_fft);
-    const double bytes = lines * 16.0 * (double(a.n_in) + double(a.n_out) * (a.op == OP_ASSIGN ? 1.0 : 2.0));
-    RoleScope rs(role, bytes);
-    MFB_LAUNCH((strided3_kernel<P, MODE>), grid, P::NTHREADS, smem, g_ctx.stream, a, tw);
-    check_launch("strided3_kernel");
-}
-static bool launch_strided3(int n, const StridedArgs& a, int role) {
-    int mode;
-    if (a.n_in == n && a.n_out == n) mode = SM_PLAIN;
-    else if (a.n_out == n && 3 * a.n_in == 2 * n) mode = SM_PAD;
-    else if (a.n_in == n && 3 * a.n_out == 2 * n) mode = SM_TRUNC;
-    else return false;
-    if (a.f.enabled && mode != SM_PAD) return false;
-    if (mode == SM_TRUNC) {
-        switch (n) {
-#define X(N_, TPL_, T_, ...) case N_: launch_strided3_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_TRUNC>(a, role); return true;
-            MFB_FOR_EACH_PLAN3_F(X)
-#undef X
-            default: return false;
-        }
-    }
-    switch (n) {
-#define X(N_, TPL_, T_, ...)                                                           \
-    case N_:                                                                           \
-        if (mode == SM_PAD) {                                                          \
-            if constexpr (N_ % 3 == 0) launch_strided3_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_PAD>(a, role); \
-            else return false;                                                         \
-        } else launch_strided3_t<Plan<N_, TPL_, T_, __VA_ARGS__>, SM_PLAIN>(a, role);  \
-        return true;
-        MFB_FOR_EACH_PLAN3_B(X)
-#undef X
-        default: return false;
-    }
-}
-
 template <class P, int MODE, int MINB> void launch_strided2_t(const StridedArgs& a, int role) {
     static bool done = false;
     optin_smem(strided2_kernel<P, MODE, MINB>, P::SMEM_BYTES, done);
@@ -388,7 +322,6 @@ static bool launch_strided2(int n, const StridedArgs& a, int role) {
 }
 
 void launch_strided(int n, const StridedArgs& a, int role) {
-    if (g_ctx.strided_v2 && g_ctx.strided_v3 && launch_strided3(n, a, role)) return;
     if (g_ctx.strided_v2 && launch_strided2(n, a, role)) return;
     switch (n) {
 #define X(N_, TPL_, T_, ...)                              \
@@ -450,19 +383,6 @@ void launch_zc2c(int n, double2* data, long nrows, double scale, int inverse) {
     }
 }
 
-template <class P>
-void launch_zconv_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
-                    int nzin, double scale, int acc) {
-    static bool done = false;
-    optin_smem(z_conv_kernel<P>, P::SMEM_BYTES, done);
-    const unsigned grid = unsigned((nrows + P::T - 1) / P::T);
-    const double2* tw = twiddles(P::N);
-    // algorithmic bytes: both operand rows (one if A == B) + the output row (+ its old value when accumulating)
-    RoleScope rs(ROLE_CONV_Z, double(nrows) * double(nzin) * 16.0 * ((A == B ? 1.0 : 2.0) + (acc ? 2.0 : 1.0)));
-    MFB_LAUNCH(z_conv_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, A, B, out, in_pitch, out_pitch, nrows, nzin,
-               scale, tw, acc);
-    check_launch("z_conv_kernel");
-}
 template <class P, int RPC, int MINB>
 void launch_zconv2_t(const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows, double scale,
                      int acc) {
@@ -490,18 +410,8 @@ static bool launch_zconv2(int n, const double2* A, const double2* B, double2* ou
 }
 void launch_zconv(int n, const double2* A, const double2* B, double2* out, ptrdiff_t in_pitch, ptrdiff_t out_pitch, long nrows,
                   int nzin, double scale, int acc = 0) {
-    if (g_ctx.zconv_v2 && launch_zconv2(n, A, B, out, in_pitch, out_pitch, nrows, nzin, scale, acc)) return;
-    switch (n) {
-#define X(N_, TPL_, T_, ...)                                                   \
-    case N_: {                                                                 \
-        using P = Plan<N_, TPL_, T_, __VA_ARGS__>;                             \
-        launch_zconv_t<P>(A, B, out, in_pitch, out_pitch, nrows, nzin, scale, acc); \
-        break;                                                                 \
-    }
-        MFB_FOR_EACH_PLAN(X)
-#undef X
-        default: throw std::runtime_error("unsupported FFT length " + std::to_string(n));
-    }
+    if (!launch_zconv2(n, A, B, out, in_pitch, out_pitch, nrows, nzin, scale, acc))
+        throw std::runtime_error("unsupported padded length " + std::to_string(n) + " for the fused z pass");
 }
 
 static StridedArgs plain_strided(const double2* in, double2* out, ptrdiff_t ps, ptrdiff_t as, int na, int nz, int n,
@@ -1241,16 +1151,15 @@ int mfb_synchronize(void) {
 void* mfb_stream(void) { return (void*)g_ctx.stream; }
 long long mfb_kernel_launches(void) { return g_ctx.launches; }
 int mfb_supported_fft_size(int n) { return supported_size(n) ? 1 : 0; }
-/* tuning switches (tests compare kernel generations): "strided_v2" = 0/1 */
+/* switches for tests: "strided_v2" = 0: every strided pass through the general kernel (strided_pass_kernel) instead of the
+   compile-time pad / truncate specialisations; "sources_v2" = 0: per-product source stage; "conv_grouping", "conv_own_accumulator",
+   "sources_max_slots", "sources_chunk": see mfb_internal.h */
 int mfb_set_option(const char* name, int value) {
     MFB_TRY
     if (std::string(name) == "strided_v2") g_ctx.strided_v2 = value != 0;
-    else if (std::string(name) == "strided_v3") g_ctx.strided_v3 = value != 0;
     else if (std::string(name) == "conv_grouping") g_ctx.conv_grouping = value != 0;
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
-    else if (std::string(name) == "zconv_v2") g_ctx.zconv_v2 = value != 0;
     else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
-    else if (std::string(name) == "zmulti_variant") g_ctx.zmulti_variant = value;
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
     else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)
     else throw std::runtime_error(std::string("unknown option ") + name);

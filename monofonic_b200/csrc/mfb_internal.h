@@ -129,13 +129,10 @@ struct Context {
     size_t table_cap[2] = {0, 0};
     long long launches = 0;
     int num_sms = 148;
-    bool strided_v2 = true;  // second-generation strided pass (fft_kernels2.cuh)
-    bool strided_v3 = false; // persistent double-buffered strided pass (strided3_kernel): measured no faster, kept as an option
+    bool strided_v2 = true;  // compile-time pad / truncate specialisations of the strided pass (fft_kernels2.cuh); 0: general kernel
     bool conv_own_accumulator = true;  // tests: 0 makes mfb_conv_create behave as under memory pressure
     bool conv_grouping = true;  // sum the products of one target before the forward passes (needs mfb_conv::Wacc)
-    bool zconv_v2 = true;    // second-generation fused z pass (fft_kernels_z2.cuh)
     bool sources_v2 = true;  // mfb_lpt_sources: shared x passes + multi-product z pass on the slot workspace (mfb_sources2.cuh)
-    int zmulti_variant = 2;      // multi-product z pass: 1 = pair-parallel (z_multi_kernel), 2 = sequential rows (z_multi2_kernel)
     int sources_max_slots = 0;   // tests: cap the slot workspace (0: what HBM allows)
     int sources_chunk = 0;       // tests: cap the x planes per chunk (0: what the chunk workspace allows)
     // optional per-role device timing (cudaEvents on `stream` around every launch)

@@ -20,32 +20,11 @@
 
 namespace mfb {
 
-// N, threads per row, min CTAs/SM, radices (first radix a multiple of 3, last radix 8: conflict-free padded lines)
-#define MFB_FOR_EACH_PLANZM(X)    \
-    X(48, 32, 1, 6, 8)            \
-    X(96, 32, 1, 12, 8)           \
-    X(192, 32, 1, 6, 4, 8)        \
-    X(384, 32, 2, 6, 8, 8)        \
-    X(768, 64, 2, 12, 8, 8)       \
-    X(1536, 64, 2, 12, 16, 8)     \
-    X(3072, 128, 1, 12, 16, 16)
-
-template <class P, int MINB> void launch_zmulti_t(const ZmArgs& a, double bytes) {
-    static bool done = false;
-    constexpr size_t smem3 = z_multi_smem<P>(true);
-    optin_smem(z_multi_kernel<P, MINB>, smem3, done);
-    const size_t smem = a.nprod > 1 ? smem3 : z_multi_smem<P>(false);
-    const unsigned grid = unsigned((a.nrows + 1) / 2);
-    if (grid == 0) return;
-    const double2* tw = twiddles2<P>();
-    RoleScope rs(ROLE_CONV_Z, bytes);
-    MFB_LAUNCH((z_multi_kernel<P, MINB>), grid, 2 * P::TPL, smem, g_ctx.stream, a, tw);
-    check_launch("z_multi_kernel");
-}
-// sequential-row version (z_multi2_kernel): N, threads per CTA, min CTAs/SM, radices.  One work line + the accumulators =
-// 2 complex lines per CTA.  n = 1536 on B200 (profiles/r02_kbench_zm_variants.txt, ms per complex-FFT sweep of 1536^2 rows):
-// pair-parallel 246 regs / 8 warps 22.2; sequential 64 threads x 4 CTAs 21.1; 128 x 4 (128 regs, 16 warps) 20.9;
-// 128 x 3 (164 regs, 12 warps) 19.3; 256 x 2 24.8; 96 x 4 21.4.
+// multi-product z pass (z_multi2_kernel, fft_kernels_zm.cuh): N, threads per CTA, min CTAs/SM, radices (first radix a multiple
+// of 3, last radix 8 or 16: conflict-free padded lines).  One work line + the accumulators = 2 complex lines per CTA.
+// n = 1536 on B200 (profiles/r02_kbench_zm_variants.txt, ms per complex-FFT sweep of 1536^2 rows): pair-parallel version
+// (246 regs, 8 warps, now scripts/kbench/kbench_legacy_kernels.cuh) 22.2; sequential rows 64 threads x 4 CTAs 21.1; 128 x 4
+// (128 regs, 16 warps) 20.9; 128 x 3 (164 regs, 12 warps) 19.1; 256 x 2 24.8; 96 x 4 21.4.  n = 3072: 192 x 2 and 256 x 2 equal.
 #define MFB_FOR_EACH_PLANZM2(X)   \
     X(48, 32, 1, 6, 8)            \
     X(96, 32, 1, 12, 8)           \
@@ -71,19 +50,10 @@ static void launch_zmulti(int n, const ZmArgs& a) {
     double rows_read = 0;
     for (int i = 0; i < a.nprod; ++i) rows_read += a.prod[i].a.n + (a.prod[i].square ? 0 : a.prod[i].b.n);
     const double bytes = double(a.nrows) * double(n / 3) * 16.0 * (rows_read + 1.0);
-    if (g_ctx.zmulti_variant == 2) {
-        switch (n) {
+    switch (n) {
 #define X(N_, NT_, MINB_, ...) \
     case N_: launch_zmulti2_t<Plan<N_, NT_, 2, __VA_ARGS__>, NT_, MINB_>(a, bytes); return;
-            MFB_FOR_EACH_PLANZM2(X)
-#undef X
-            default: break;
-        }
-    }
-    switch (n) {
-#define X(N_, TPL_, MINB_, ...) \
-    case N_: launch_zmulti_t<Plan<N_, TPL_, 2, __VA_ARGS__>, MINB_>(a, bytes); return;
-        MFB_FOR_EACH_PLANZM(X)
+        MFB_FOR_EACH_PLANZM2(X)
 #undef X
         default: throw std::runtime_error("unsupported padded length " + std::to_string(n) + " for the multi-product z pass");
     }

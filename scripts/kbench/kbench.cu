@@ -6,8 +6,7 @@
 #include <cmath>
 #include <vector>
 #include <string>
-#include "fft_kernels2.cuh"
-#include "fft_kernels_z2.cuh"
+#include "kbench_legacy_kernels.cuh"
 using namespace mfb;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)

@@ -63,7 +63,23 @@ template <class P, int s, int NT> MFB_D void zm_dif_mid(double2* ln, const doubl
     }
 }
 
-template <class P, int NT, int MINB>
+//
+// PF (prefetch): the first-term rows of the NEXT (product, row) item are fetched by the TMA unit - two cp.async.bulk copies of a
+// whole row each, issued by one thread right after the barrier that ends stage 0, completion on an mbarrier - into a 2-row
+// staging area while the middle and innermost stages of the current item run; stage 0 then reads them from shared memory.
+// The wait for HBM (long-scoreboard stalls: 17 % of all stall cycles of the direct version, profiles/r02_ncu_zmulti2_*.txt)
+// leaves the critical path of the CTA and no registers hold loads in flight.  Second terms of two-term operands stay direct
+// loads (a third and fourth staged row would cost the third resident CTA).
+// the same with the barrier AFTER each stage (the caller has synchronised before the first one)
+template <class P, int s, int NT> MFB_D void zm_dif_mid_nosync(double2* ln, const double2* tw, int q) {
+    if constexpr (s < P::S - 1) {
+        z2_dif_stage<P, s, NT>(ln, tw, q);
+        __syncthreads();
+        zm_dif_mid_nosync<P, s + 1, NT>(ln, tw, q);
+    }
+}
+
+template <class P, int NT, int MINB, bool PF = false>
 __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const double2* __restrict__ tw) {
     MFB_DYN_SMEM(double2, sm);
     constexpr int N = P::N, S = P::S;
@@ -74,9 +90,30 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
     double2* work = sm;                                         // one padded complex line
     double* accx = reinterpret_cast<double*>(sm + LW);          // sum of the products of the even row (padded like a line)
     double* accy = accx + LW;                                   // ... of the odd row
+    double2* raw = sm + 2 * LW;                                 // PF: staged first-term rows of A and B (NZ complex each)
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(raw + 2 * NZ);
     const int tid = threadIdx.x;
     const long row0 = long(blockIdx.x) * 2;
     const int nprod = A.nprod;
+    // PF: thread 0 starts the bulk copies of item (ip, h); rows beyond nrows are not copied (stage 0 substitutes zeros)
+    auto prefetch = [&](int ip, int h) {
+        const ZmProduct& pr = A.prod[ip];
+        const bool sq = pr.square != 0;
+        const long ra = row0 + h, rb = sq ? row0 + 1 : row0 + h;
+        const bool oka = ra < A.nrows, okb = rb < A.nrows;
+        constexpr unsigned ROWB = unsigned(NZ) * unsigned(sizeof(double2));
+        mfb_mbar_expect_tx(bar, (oka ? ROWB : 0u) + (okb ? ROWB : 0u));
+        if (oka) mfb_bulk_g2s(raw, pr.a.t[0].p + ra * A.in_pitch, ROWB, bar);
+        if (okb) mfb_bulk_g2s(raw + NZ, (sq ? pr.a.t[0].p : pr.b.t[0].p) + rb * A.in_pitch, ROWB, bar);
+    };
+    unsigned phase = 0;
+    if constexpr (PF) {
+        if (tid == 0) {
+            mfb_mbar_init(bar, 1);
+            if (nprod > 0) prefetch(0, 0);
+        }
+        __syncthreads();
+    }
 
 #pragma unroll 1
     for (int ip = 0; ip < nprod; ++ip) {
@@ -95,6 +132,7 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
             const bool row1_ok = row0 + 1 < A.nrows;
             const ptrdiff_t roff = (row0 + h) * A.in_pitch;
             if (ip > 0 || h > 0) __syncthreads();   // the innermost step of the previous row has read the work line
+            if constexpr (PF) { mfb_mbar_wait(bar, phase); phase ^= 1u; }
             // ---- DIF stage 0: conj(A^ + i B^), Hermitian-extended and zero padded, built in the legs
             {
                 constexpr int r = P::radix(0), M = N / r, K3 = r / 3;
@@ -105,6 +143,15 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
                 const double2* pb1 = square ? pr.a.t[1].p + roff + A.in_pitch : pr.b.t[1].p + roff;
                 auto ld = [&](const double2* p) -> double2 { return row_ok ? mfb_ld_stream(p) : make_double2(0.0, 0.0); };
                 auto ldb = [&](const double2* p) -> double2 { return (square ? row1_ok : row_ok) ? mfb_ld_stream(p) : make_double2(0.0, 0.0); };
+                // first terms: staged rows (PF) or direct loads
+                auto ld0 = [&](int k) -> double2 {
+                    if constexpr (PF) return row_ok ? raw[k] : make_double2(0.0, 0.0);
+                    else return ld(pa0 + k);
+                };
+                auto ldb0 = [&](int k) -> double2 {
+                    if constexpr (PF) return (square ? row1_ok : row_ok) ? raw[NZ + k] : make_double2(0.0, 0.0);
+                    else return ldb(pb0 + k);
+                };
                 auto kpow = [&](double kz, int e, double c) -> double { return e == 0 ? c : (e == 1 ? c * kz : c * kz * kz); };
 #pragma unroll 1
                 for (int j = tid; j < M; j += NT) {
@@ -113,8 +160,8 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
 #pragma unroll
                     for (int m = 0; m < 2 * K3; ++m) {
                         const bool dropped = (m == K3 && j == 0);   // k == NZ: the dropped Nyquist sample (not stored)
-                        xa[m] = dropped ? make_double2(0.0, 0.0) : ld(pa0 + mode_k(m));
-                        xb[m] = dropped ? make_double2(0.0, 0.0) : ldb(pb0 + mode_k(m));
+                        xa[m] = dropped ? make_double2(0.0, 0.0) : ld0(mode_k(m));
+                        xb[m] = dropped ? make_double2(0.0, 0.0) : ldb0(mode_k(m));
                     }
                     if (na > 1) {   // sums / differences of Hessians (convolution.hh:214-274): second term of A
                         double2 ya[2 * K3];
@@ -171,8 +218,17 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
                     for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
                 }
             }
-            zm_dif_mid<P, 1, NT>(work, tw, tid);
-            __syncthreads();
+            if constexpr (PF) {
+                __syncthreads();   // stage 0 has consumed the staged rows: the TMA unit may overwrite them with the next item's
+                if (tid == 0) {
+                    if (h + 1 < npass) prefetch(ip, h + 1);
+                    else if (ip + 1 < nprod) prefetch(ip + 1, 0);
+                }
+                zm_dif_mid_nosync<P, 1, NT>(work, tw, tid);
+            } else {
+                zm_dif_mid<P, 1, NT>(work, tw, tid);
+                __syncthreads();
+            }
             // ---- innermost DIF stage -> a * b -> real accumulator of this row; last product, odd row: innermost DIT stage
             {
                 constexpr int r = P::radix(S - 1), Bn = N / r;
@@ -260,6 +316,8 @@ __global__ void __launch_bounds__(NT, MINB) z_multi2_kernel(ZmArgs A, const doub
         }
     }
 }
-template <class P> constexpr size_t z_multi2_smem() { return size_t(2) * (zpad(P::N) + 1) * sizeof(double2); }
+template <class P, bool PF = false> constexpr size_t z_multi2_smem() {
+    return size_t(2) * (zpad(P::N) + 1) * sizeof(double2) + (PF ? size_t(2) * (P::N / 3) * sizeof(double2) + 16 : 0);
+}
 
 }  // namespace mfb

@@ -1160,6 +1160,7 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "conv_grouping") g_ctx.conv_grouping = value != 0;
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
+    else if (std::string(name) == "zm_prefetch") g_ctx.zm_prefetch = value != 0;         // 0: direct-load multi-product z pass
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
     else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)
     else throw std::runtime_error(std::string("unknown option ") + name);

@@ -25,24 +25,27 @@ namespace mfb {
 // n = 1536 on B200 (profiles/r02_kbench_zm_variants.txt, ms per complex-FFT sweep of 1536^2 rows): pair-parallel version
 // (246 regs, 8 warps, now scripts/kbench/kbench_legacy_kernels.cuh) 22.2; sequential rows 64 threads x 4 CTAs 21.1; 128 x 4
 // (128 regs, 16 warps) 20.9; 128 x 3 (164 regs, 12 warps) 19.1; 256 x 2 24.8; 96 x 4 21.4.  n = 3072: 192 x 2 and 256 x 2 equal.
-#define MFB_FOR_EACH_PLANZM2(X)   \
-    X(48, 32, 1, 6, 8)            \
-    X(96, 32, 1, 12, 8)           \
-    X(192, 32, 2, 6, 4, 8)        \
-    X(384, 64, 4, 6, 8, 8)        \
-    X(768, 64, 4, 12, 8, 8)       \
-    X(1536, 128, 3, 12, 16, 8)    \
-    X(3072, 192, 2, 12, 16, 16)
+// PF_: rows staged by TMA bulk copies (z_multi2_kernel<.., PF = true>) where the 2-row staging area does not cost a resident
+// CTA (n = 3072: two lines + staging = 143 KB would leave one CTA per SM); mfb_set_option("zm_prefetch", 0) selects the
+// direct-load kernel everywhere (A/B runs, check_kernel_generations).
+#define MFB_FOR_EACH_PLANZM2(X)      \
+    X(48, 32, 1, 1, 6, 8)            \
+    X(96, 32, 1, 1, 12, 8)           \
+    X(192, 32, 2, 1, 6, 4, 8)        \
+    X(384, 64, 4, 1, 6, 8, 8)        \
+    X(768, 64, 4, 1, 12, 8, 8)       \
+    X(1536, 128, 3, 1, 12, 16, 8)    \
+    X(3072, 192, 2, 0, 12, 16, 16)
 
-template <class P, int NT, int MINB> void launch_zmulti2_t(const ZmArgs& a, double bytes) {
+template <class P, int NT, int MINB, bool PF> void launch_zmulti2_t(const ZmArgs& a, double bytes) {
     static bool done = false;
-    constexpr size_t smem = z_multi2_smem<P>();
-    optin_smem(z_multi2_kernel<P, NT, MINB>, smem, done);
+    constexpr size_t smem = z_multi2_smem<P, PF>();
+    optin_smem(z_multi2_kernel<P, NT, MINB, PF>, smem, done);
     const unsigned grid = unsigned((a.nrows + 1) / 2);
     if (grid == 0) return;
     const double2* tw = twiddles2<P>();
     RoleScope rs(ROLE_CONV_Z, bytes);
-    MFB_LAUNCH((z_multi2_kernel<P, NT, MINB>), grid, NT, smem, g_ctx.stream, a, tw);
+    MFB_LAUNCH((z_multi2_kernel<P, NT, MINB, PF>), grid, NT, smem, g_ctx.stream, a, tw);
     check_launch("z_multi2_kernel");
 }
 static void launch_zmulti(int n, const ZmArgs& a) {
@@ -51,8 +54,11 @@ static void launch_zmulti(int n, const ZmArgs& a) {
     for (int i = 0; i < a.nprod; ++i) rows_read += a.prod[i].a.n + (a.prod[i].square ? 0 : a.prod[i].b.n);
     const double bytes = double(a.nrows) * double(n / 3) * 16.0 * (rows_read + 1.0);
     switch (n) {
-#define X(N_, NT_, MINB_, ...) \
-    case N_: launch_zmulti2_t<Plan<N_, NT_, 2, __VA_ARGS__>, NT_, MINB_>(a, bytes); return;
+#define X(N_, NT_, MINB_, PF_, ...)                                                                              \
+    case N_:                                                                                                     \
+        if (PF_ && g_ctx.zm_prefetch) launch_zmulti2_t<Plan<N_, NT_, 2, __VA_ARGS__>, NT_, MINB_, PF_ != 0>(a, bytes); \
+        else launch_zmulti2_t<Plan<N_, NT_, 2, __VA_ARGS__>, NT_, MINB_, false>(a, bytes);                        \
+        return;
         MFB_FOR_EACH_PLANZM2(X)
 #undef X
         default: throw std::runtime_error("unsupported padded length " + std::to_string(n) + " for the multi-product z pass");

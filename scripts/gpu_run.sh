@@ -2,7 +2,7 @@
 # One parameterised gpurun call (replaces the one-shot scripts of round 1).  Everything lands in gpurun_out/.
 #   TESTS="<pytest -k expr>|all|none"  SMOKE=1  BENCH_GRIDS="1024 512"  BENCH_ARGS="--steps 3 --warmup 3 --no-cpu"
 #   LAUNCHES=<grid> (ncu launch list of one step)   NCU_KERNELS="regex ..." NCU_GRID=<grid> (ncu --set full)
-#   KBENCH="args" (scripts/kbench/kbench)  NG=<gpus> (torchrun for bench when > 1; dist tests)
+#   KBENCH="args" (scripts/kbench/kbench)  KBENCH_ZM="args" (scripts/kbench/kbench_zm)  NG=<gpus> (torchrun for bench when > 1; dist tests)
 set -u
 TAG=${TAG:-run}
 mkdir -p gpurun_out
@@ -18,6 +18,9 @@ if [ "${SMOKE:-0}" = "1" ]; then
 fi
 if [ -n "${KBENCH:-}" ]; then
   echo "== kbench $KBENCH"; timeout 600 scripts/kbench/kbench $KBENCH 2>&1 | tee gpurun_out/kbench_$TAG.log | tail -60
+fi
+if [ -n "${KBENCH_ZM:-}" ]; then
+  echo "== kbench_zm $KBENCH_ZM"; timeout 600 scripts/kbench/kbench_zm $KBENCH_ZM 2>&1 | tee gpurun_out/kbench_zm_$TAG.log | tail -60
 fi
 for G in ${BENCH_GRIDS:-}; do
   echo "== bench grid $G on $NG GPU(s)"

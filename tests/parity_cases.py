@@ -721,9 +721,11 @@ def check_product_grouping(M, n=32):
     try:
         # (v2, grouping, max_slots, chunk planes): the last two make the slot workspace as tight as it may be (7 slots: one
         # target per loop, an evicted X buffer is made again) and the chunks ragged
-        for key, v2, grouping, slots, chunk in (("v2", 1, 1, 0, 0), ("v2tight", 1, 1, 7, 5), ("v2split", 1, 1, 5, 7), (1, 0, 1, 0, 0),
-                                                (0, 0, 0, 0, 0)):
+        # "v2direct": the multi-product z pass with direct loads instead of TMA-staged rows - the same arithmetic, bit for bit
+        for key, v2, grouping, slots, chunk in (("v2", 1, 1, 0, 0), ("v2direct", 1, 1, 0, 0), ("v2tight", 1, 1, 7, 5), ("v2split", 1, 1, 5, 7),
+                                                (1, 0, 1, 0, 0), (0, 0, 0, 0, 0)):
             assert lib.mfb_set_option(b"sources_v2", v2) == 0 and lib.mfb_set_option(b"conv_grouping", grouping) == 0
+            assert lib.mfb_set_option(b"zm_prefetch", 0 if key == "v2direct" else 1) == 0
             assert lib.mfb_set_option(b"sources_max_slots", slots) == 0 and lib.mfb_set_option(b"sources_chunk", chunk) == 0
             pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp))
             pl.set_noise_k(W)
@@ -741,6 +743,7 @@ def check_product_grouping(M, n=32):
     finally:
         for o_ in (b"sources_max_slots", b"sources_chunk"):
             lib.mfb_set_option(o_, 0)
+        lib.mfb_set_option(b"zm_prefetch", 1)
         lib.mfb_set_option(b"conv_grouping", 1)
         lib.mfb_set_option(b"sources_v2", 1)
     assert res["v2"][3]["path"] == 2 and res["v2tight"][3]["path"] == 2 and res[1][3]["path"] == 1 and res[0][3]["path"] == 1
@@ -750,6 +753,8 @@ def check_product_grouping(M, n=32):
     assert res["v2tight"][3]["slots"] == 7 and res["v2tight"][3]["x_passes"] == 11 and res["v2tight"][3]["loops"] == 7, res["v2tight"][3]
     # equal up to rounding: the sums are taken in a different order (real space / z-Fourier space / per product)
     assert res["v2split"][3]["path"] == 2 and res["v2split"][3]["slots"] == 5 and res["v2split"][3]["loops"] > 7, res["v2split"][3]
+    for a, b in zip(res["v2"][0], res["v2direct"][0]):
+        assert np.array_equal(a, b)
     for key in ("v2", "v2tight", "v2split", 1):
         for a, b in zip(res[key][0], res[0][0]):
             assert relerr(a, b) < 1e-12, key

@@ -43,6 +43,7 @@ const char* mfb_last_error(void);
 const char* mfb_build_info(void);    /* "cuda sm_100a" for the product build */
 int mfb_synchronize(void);
 void* mfb_stream(void);              /* the cudaStream_t all work is issued on */
+void* mfb_copy_stream(void);         /* the cudaStream_t of the streamed particle hand-off (events of a consumer go here) */
 long long mfb_kernel_launches(void); /* number of kernels launched so far (bench.py gpu_launches) */
 int mfb_supported_fft_size(int n);   /* 1 if an FFT plan exists for line length n */
 int mfb_set_option(const char* name, int value); /* tuning switches, e.g. "strided_v2" = 0/1 (kernel generation) */
@@ -94,6 +95,12 @@ size_t mfb_grid_ntot(const mfb_grid* g);                           /* ntot_ in d
 void* mfb_grid_device_ptr(mfb_grid* g);
 /* host<->device copies of the whole buffer (ntot doubles) - the coherence primitive under relem/kelem/data_ */
 int mfb_grid_upload(mfb_grid* g, const double* host);
+/* Streamed ingest (the host -> device side of the hand-off): asynchronous copy of the RNG plugin's next
+   field (pinned host memory, raw layout) into `g` on an ingest stream, ordered after all work queued so far; the compute
+   stream continues with work that does not touch `g`.  mfb_grid_stream_in_wait makes the compute stream - not the host -
+   wait for the copy before `g` is used again.  Replaces the blocking Fill_Grid -> device copy of a series of runs. */
+int mfb_grid_stream_in(mfb_grid* g, const double* host);
+int mfb_grid_stream_in_wait(mfb_grid* g);
 int mfb_grid_download(const mfb_grid* g, double* host);
 /* FourierTransformForward/Backward(do_transform)                  src/grid_fft.cc:208-270 */
 int mfb_fft_forward(mfb_grid* g, int do_transform);

@@ -29,6 +29,7 @@ def _declare(lib):
         "mfb_build_info": (C.c_char_p, []),
         "mfb_synchronize": (i, []),
         "mfb_stream": (vp, []),
+        "mfb_copy_stream": (vp, []),
         "mfb_kernel_launches": (C.c_longlong, []),
         "mfb_supported_fft_size": (i, [i]),
         "mfb_set_option": (i, [C.c_char_p, i]),
@@ -56,6 +57,8 @@ def _declare(lib):
         "mfb_grid_ntot": (sz, [vp]),
         "mfb_grid_device_ptr": (vp, [vp]),
         "mfb_grid_upload": (i, [vp, vp]),
+        "mfb_grid_stream_in": (i, [vp, vp]),
+        "mfb_grid_stream_in_wait": (i, [vp]),
         "mfb_grid_download": (i, [vp, vp]),
         "mfb_fft_forward": (i, [vp, i]),
         "mfb_fft_backward": (i, [vp, i]),

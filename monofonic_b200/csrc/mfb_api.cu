@@ -1129,6 +1129,7 @@ int mfb_finalize(void) {
     }
     cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.copy_stream) { cudaStreamDestroy(g_ctx.copy_stream); g_ctx.copy_stream = nullptr; }
+    if (g_ctx.in_stream) { cudaStreamDestroy(g_ctx.in_stream); g_ctx.in_stream = nullptr; }
     g_ctx.initialised = false;
     MFB_CATCH
 }
@@ -1149,6 +1150,10 @@ int mfb_synchronize(void) {
     MFB_CATCH
 }
 void* mfb_stream(void) { return (void*)g_ctx.stream; }
+void* mfb_copy_stream(void) {   // created on first use; NULL if that fails
+    if (!g_ctx.copy_stream && g_ctx.initialised && cudaStreamCreate(&g_ctx.copy_stream) != cudaSuccess) g_ctx.copy_stream = nullptr;
+    return (void*)g_ctx.copy_stream;
+}
 long long mfb_kernel_launches(void) { return g_ctx.launches; }
 int mfb_supported_fft_size(int n) { return supported_size(n) ? 1 : 0; }
 /* switches for tests: "strided_v2" = 0: every strided pass through the general kernel (strided_pass_kernel) instead of the
@@ -1351,7 +1356,12 @@ int mfb_grid_create(mfb_grid** out, const int n[3], const double L[3], int space
 }
 int mfb_grid_destroy(mfb_grid* g) {
     MFB_TRY
-    if (g) { if (g->d) cudaFree(g->d); delete g; }
+    if (g) {
+        if (g->upload_pending && g_ctx.in_stream) cudaStreamSynchronize(g_ctx.in_stream);
+        if (g->uploaded) cudaEventDestroy(g->uploaded);
+        if (g->d) cudaFree(g->d);
+        delete g;
+    }
     MFB_CATCH
 }
 int mfb_grid_space(const mfb_grid* g) { return g->space; }
@@ -1361,6 +1371,31 @@ int mfb_grid_upload(mfb_grid* g, const double* host) {
     MFB_TRY
     cuda_check(cudaMemcpyAsync(g->d, host, g->ntot * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream), "upload");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    MFB_CATCH
+}
+// Streamed ingest - the host -> device counterpart of mfb_particles_stream_out.  The RNG plugin's next field (pinned host
+// memory, the raw layout of mfb_grid_upload) is copied into `g` on an ingest stream of its own, ordered after everything
+// queued on the compute stream so far (the last reader of the old contents), while the compute stream goes on with work
+// that no longer touches `g` - in a series of runs the noise of run k+1 travels under the source stage of run k.
+// mfb_grid_stream_in_wait makes the compute stream (not the host) wait for the copy.
+int mfb_grid_stream_in(mfb_grid* g, const double* host) {
+    MFB_TRY
+    require(host != nullptr, "null host pointer");
+    if (!g_ctx.in_stream) cuda_check(cudaStreamCreate(&g_ctx.in_stream), "cudaStreamCreate(ingest)");
+    if (!g->uploaded) cuda_check(cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventRecord(g->uploaded, g_ctx.stream), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(g_ctx.in_stream, g->uploaded, 0), "cudaStreamWaitEvent");
+    cuda_check(cudaMemcpyAsync(g->d, host, g->ntot * sizeof(double), cudaMemcpyHostToDevice, g_ctx.in_stream), "H2D stream_in");
+    cuda_check(cudaEventRecord(g->uploaded, g_ctx.in_stream), "cudaEventRecord");
+    g->upload_pending = true;
+    MFB_CATCH
+}
+int mfb_grid_stream_in_wait(mfb_grid* g) {
+    MFB_TRY
+    if (g->upload_pending) {
+        cuda_check(cudaStreamWaitEvent(g_ctx.stream, g->uploaded, 0), "cudaStreamWaitEvent");
+        g->upload_pending = false;
+    }
     MFB_CATCH
 }
 int mfb_grid_download(const mfb_grid* g, double* host) {

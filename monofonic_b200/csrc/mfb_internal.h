@@ -20,6 +20,9 @@ struct mfb_grid {
     int dist;
     int nloc0, off0;  // local_0_size_, local_0_start_
     int nloc1, off1;  // local_1_size_, local_1_start_
+    // streamed ingest (mfb_grid_stream_in): event recorded on the ingest stream after the H2D copy of the next field
+    cudaEvent_t uploaded = nullptr;
+    bool upload_pending = false;
 };
 
 // Grid_FFT<ccomplex_t> (PPT / Eulerian branch): dense [n0][n1][n2] complex, c2c transforms, single slab
@@ -121,6 +124,7 @@ struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H hand-off of particle attributes, overlaps the compute stream
+    cudaStream_t in_stream = nullptr;    // H2D ingest of the next noise field (mfb_grid_stream_in), the other PCIe direction
     std::map<int, double2*> tw;  // twiddle tables exp(-2 pi i m/n)
     std::map<std::string, double2*> tw2;  // stage-major twiddle tables per plan (Plan::tw2_off)
     double* partial = nullptr;   // reduction scratch

@@ -152,6 +152,17 @@ class Grid_FFT:
         assert buf.size == self.ntot_, (buf.size, self.ntot_)
         L.check(self._lib.mfb_grid_upload(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)
 
+    def stream_in(self, buf: np.ndarray):
+        """asynchronous upload_raw on the ingest stream (`buf` should be pinned and must stay alive and unchanged until the
+        copy has run); the compute stream continues with work that does not touch this grid.  Pair with stream_in_wait()."""
+        if buf.dtype != np.float64 or buf.size != self.ntot_ or not buf.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"stream_in: host buffer must be C-contiguous float64[{self.ntot_}]")
+        L.check(self._lib.mfb_grid_stream_in(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)
+
+    def stream_in_wait(self):
+        """the compute stream (not the host) waits for a pending stream_in"""
+        L.check(self._lib.mfb_grid_stream_in_wait(self._h), self._lib)
+
     def download_raw(self) -> np.ndarray:
         buf = np.empty(self.ntot_, dtype=np.float64)
         L.check(self._lib.mfb_grid_download(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)

@@ -511,6 +511,39 @@ def check_stream_handoff(M, n=32, order=2, lattice="bcc"):
         assert np.array_equal(out[k], ref[k]), k
     with pytest_raises(ValueError):
         pl.particles.stream_out("pos", np.zeros(5, np.float32))
+    # the ingest side: a series of runs whose noise is streamed in under the previous run (the noise grid is dead once phi1
+    # exists) delivers what blocking uploads deliver
+    w = pl.wnoise
+    if w.local_0_size_ == n:   # single slab: the real-space field of the second run, raw layout
+        rng = np.random.default_rng(77)
+        noise = [rng.standard_normal((n, n, n)) for _ in range(2)]
+        raw = [np.zeros(w.ntot_) for _ in range(2)]
+        for r_, x in zip(raw, noise):
+            r_.reshape(n, n, n + 2)[:, :, :n] = x
+        res = []
+        for streamed in (False, True):
+            outs = []
+            for k in range(2):
+                if streamed and k > 0:
+                    w.stream_in_wait()
+                    w.FourierTransformBackward(False)
+                else:
+                    w.FourierTransformBackward(False)
+                    w.upload_raw(raw[k])
+                w.FourierTransformForward()
+                pl.condition_noise()
+                pl.compute_phi1(tab)
+                if streamed and k == 0:
+                    w.stream_in(raw[1])
+                pl.compute_sources()
+                outs.append(pl.fill_particles().download())
+            res.append(outs)
+        for k in range(2):
+            for key in ("pos", "vel"):
+                assert np.array_equal(res[0][k][key], res[1][k][key]), (k, key)
+        assert not np.array_equal(res[0][0]["pos"], res[0][1]["pos"])
+        with pytest_raises(ValueError):
+            w.stream_in(np.zeros(5))
 
 
 class pytest_raises:

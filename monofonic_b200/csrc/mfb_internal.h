@@ -48,6 +48,7 @@ struct mfb_conv_slot {
     const void* g; int mx; int valid;   // cached X buffer
     int pinned;
     long stamp;
+    int lent;           // carved from the lender's particle arrays (a streamed hand-off copy may still be reading it)
 };
 constexpr int MFB_CONV_MAX_SLOTS = 16;
 
@@ -72,6 +73,7 @@ struct mfb_conv {
     mfb_conv_slot xs[MFB_CONV_MAX_SLOTS];
     int nxs;
     double2* chunk; size_t chunk_elems; int chunk_owned;   // operand / target chunks of the x-plane loop
+    int chunk_lent;                                        // ... carved from the lender's particle arrays
     long stamp;
     int last_path, last_slots, last_loops;                 // what the last mfb_lpt_sources call did (bench / tests)
     long last_xpass, last_ypass, last_zlaunch;

@@ -130,9 +130,9 @@ static int conv_enter_slots(mfb_conv* c, int want_slots, int min_slots, size_t w
     c->mode = 1;
     c->nxs = 0;
     const size_t U = conv_slot_elems(c) * sizeof(double2);
-    auto add = [&](double2* p, int owned, int xslot) {
+    auto add = [&](double2* p, int owned, int xslot, int lent = 0) {
         mfb_conv_slot& s = c->xs[c->nxs++];
-        s.p = p; s.owned = owned; s.xslot = xslot; s.g = nullptr; s.mx = 0; s.valid = 0; s.pinned = 0; s.stamp = 0;
+        s.p = p; s.owned = owned; s.xslot = xslot; s.g = nullptr; s.mx = 0; s.valid = 0; s.pinned = 0; s.stamp = 0; s.lent = lent;
     };
     const size_t margin = size_t(3) << 29;   // 1.5 GiB stay free
     size_t lent_left = 0; char* lent_p = nullptr;
@@ -148,12 +148,13 @@ static int conv_enter_slots(mfb_conv* c, int want_slots, int min_slots, size_t w
             try { c->W1 = (double2*)dev_alloc(U); } catch (...) { c->W1 = nullptr; }
         }
         if (c->W1) add(c->W1, 0, -1);
-        while (lent_left >= U && c->nxs < want_slots) { add((double2*)lent_p, 0, -1); lent_p += U; lent_left -= U; }
+        while (lent_left >= U && c->nxs < want_slots) { add((double2*)lent_p, 0, -1, 1); lent_p += U; lent_left -= U; }
     }
     // chunk workspace: what is left of the lent particle memory if it is enough, else an allocation of its own
     const size_t min_chunk = min_chunk_elems * sizeof(double2), want_chunk = want_chunk_elems * sizeof(double2);
+    c->chunk_lent = 0;
     if (lent_left >= min_chunk && (c->dist || lent_left >= want_chunk)) {
-        c->chunk = (double2*)lent_p; c->chunk_elems = lent_left / sizeof(double2); c->chunk_owned = 0;
+        c->chunk = (double2*)lent_p; c->chunk_elems = lent_left / sizeof(double2); c->chunk_owned = 0; c->chunk_lent = 1;
     } else {
         size_t free_b = 0, total_b = 0;
         cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
@@ -225,6 +226,10 @@ struct S2Runner {
     int N0, N1, N2, P0, P1, P2, nzc, nzin, p0l;
     double s1, unpad_scale;
     long n_x = 0, n_y = 0, n_z = 0, n_loops = 0;
+    // Slots carved from the lender's particle arrays may still be read by streamed hand-off copies of the previous run
+    // (mfb_particles_stream_out).  `limit` < nxs: such slots are left alone (restricted stage - the hand-off drains under it);
+    // otherwise the compute stream waits for the copy when the slot is first taken, not at the start of the stage.
+    int limit = 0;
     explicit S2Runner(mfb_conv* c_) : c(c_) {
         N0 = c->n[0]; N1 = c->n[1]; N2 = c->n[2]; P0 = c->np[0]; P1 = c->np[1]; P2 = c->np[2];
         nzc = N2 / 2 + 1; nzin = N2 / 2; p0l = c->p0loc;
@@ -239,14 +244,51 @@ struct S2Runner {
         for (int i = 0; i < c->nxs; ++i) if (c->xs[i].valid && c->xs[i].g == g && c->xs[i].mx == mx) return i;
         return -1;
     }
-    int take_slot() {   // a free slot, else the least recently used unpinned X buffer
-        int best = -1;
-        for (int i = 0; i < c->nxs; ++i) {
-            if (c->xs[i].pinned) continue;
-            if (!c->xs[i].valid) return i;
-            if (best < 0 || c->xs[i].stamp < c->xs[best].stamp) best = i;
+    // bytes [lo, hi) of the lender's pos/vel block behind slot i still have a hand-off copy pending
+    bool slot_busy(int i) const {
+        const mfb_conv_slot& s = c->xs[i];
+        if (!s.lent || !c->lender) return false;
+        const mfb_particles* l = c->lender;
+        const size_t half = l->posvel_bytes / 2;
+        const size_t lo = size_t((const char*)s.p - (const char*)l->pos), hi = lo + conv_slot_elems(c) * sizeof(double2);
+        return (l->copy_pending[MFB_ATTR_POS] && lo < half) || (l->copy_pending[MFB_ATTR_VEL] && hi > half);
+    }
+    int free_of_handoff() const {
+        int k = 0;
+        for (int i = 0; i < c->nxs; ++i) k += slot_busy(i) ? 0 : 1;
+        return k;
+    }
+    void wait_slot(int i) {   // compute stream waits for the hand-off copies that still read slot i
+        if (!slot_busy(i)) return;
+        mfb_particles* l = c->lender;
+        const size_t half = l->posvel_bytes / 2;
+        const size_t lo = size_t((const char*)c->xs[i].p - (const char*)l->pos), hi = lo + conv_slot_elems(c) * sizeof(double2);
+        for (int at : {MFB_ATTR_POS, MFB_ATTR_VEL}) {
+            const bool overlaps = at == MFB_ATTR_POS ? lo < half : hi > half;
+            if (overlaps && l->copy_pending[at]) {
+                cuda_check(cudaStreamWaitEvent(g_ctx.stream, l->copied[at], 0), "cudaStreamWaitEvent");
+                l->copy_pending[at] = false;
+            }
         }
+    }
+    int take_slot() {   // a free slot, else the least recently used unpinned X buffer; slots under a pending hand-off last
+        const bool restricted = limit > 0 && limit < c->nxs;
+        int best = -1, best_busy = -1;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = 0; i < c->nxs; ++i) {
+                if (c->xs[i].pinned) continue;
+                const bool busy = slot_busy(i);
+                if (busy != (pass == 1)) continue;
+                if (busy && restricted) continue;
+                if (!c->xs[i].valid) { wait_slot(i); return i; }
+                int& b = busy ? best_busy : best;
+                if (b < 0 || c->xs[i].stamp < c->xs[b].stamp) b = i;
+            }
+            if (pass == 0 && best >= 0) break;
+        }
+        if (best < 0) best = best_busy;
         require(best >= 0, "internal: no free slot in the source-stage workspace");
+        wait_slot(best);
         c->xs[best].valid = 0;
         return best;
     }
@@ -456,24 +498,34 @@ struct S2Runner {
     // targets in order, as many per loop as the slots allow (each needs one; the X buffers of the loop must all be resident).
     // A target whose products need more X buffers than there are slots is split: its products go through several loops and
     // the later ones ADD to the target (linear; costs extra forward passes - the tight-memory variant, 3LPT 2048^3 on 8 GPUs).
-    void run_stage(std::vector<S2Target>& in) {
+    void run_stage(std::vector<S2Target>& in, bool may_restrict = false) {
+        // restricted stage: only the slots no hand-off copy is reading (if they are enough for the stage's widest product)
+        limit = c->nxs;
+        if (may_restrict) {
+            const int k = free_of_handoff();
+            size_t widest = 0;
+            for (const S2Target& t : in)
+                for (const S2Product& p : t.prods) widest = std::max(widest, x_of(p, XSet()).size());
+            if (k < c->nxs && k >= int(widest) + 1 && k >= 4) limit = k;
+        }
+        const int nslots = limit;
         std::vector<S2Target> targets;
         for (S2Target& t : in) {
-            if (int(x_of(t, XSet()).size()) + 1 <= c->nxs) { targets.push_back(t); continue; }
+            if (int(x_of(t, XSet()).size()) + 1 <= nslots) { targets.push_back(t); continue; }
             S2Target part = t;
             part.prods.clear();
             bool first = true;
             for (const S2Product& p : t.prods) {
                 S2Target trial = part;
                 trial.prods.push_back(p);
-                if (!part.prods.empty() && int(x_of(trial, XSet()).size()) + 1 > c->nxs) {
+                if (!part.prods.empty() && int(x_of(trial, XSet()).size()) + 1 > nslots) {
                     targets.push_back(part);
                     first = false;
                     part.prods.clear();
                     // whatever the target's operator, the remaining products accumulate with the same sign / factor
                     if (t.op == OP_ASSIGN) part.op = OP_ADD;
                 }
-                require(int(x_of(p, XSet()).size()) + 1 <= c->nxs, "internal: the source-stage workspace has too few slots for one product");
+                require(int(x_of(p, XSet()).size()) + 1 <= nslots, "internal: the source-stage workspace has too few slots for one product");
                 // a target that is also an operand (the first inner product lives in phi3) must be consumed before it is written
                 for (const S2Operand* o : {&p.a, &p.b})
                     for (int k = 0; k < o->n; ++k) require(first || o->t[k].g != t.out, "internal: split target would overwrite its own operand");
@@ -491,7 +543,7 @@ struct S2Runner {
                 for (int k = 0; k < nt; ++k) same_out = same_out || targets[i + k].out == targets[i + nt].out;
                 if (same_out) break;
                 XSet cand = x_of(targets[i + nt], xs);
-                if (int(cand.size()) + nt + 1 > c->nxs) break;
+                if (int(cand.size()) + nt + 1 > nslots) break;
                 xs = cand;
                 ++nt;
             }
@@ -501,6 +553,7 @@ struct S2Runner {
             run_loop(ptr.data(), nt);
             i += nt;
         }
+        limit = c->nxs;
     }
 };
 
@@ -516,7 +569,10 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
     const int min_slots = order > 2 ? 5 : 4, want_slots = order > 2 ? 8 : 4;
     if (c->dist && D().nxbuf < min_slots) return false;
     if (!conv_enter_slots(c, want_slots, min_slots, size_t(kmax) * cx_want * pe, size_t(kmax) * pe)) return false;
-    conv_wait_lender(c);   // lent particle arrays: streamed hand-off copies of the previous run must have drained
+    // lent particle arrays: streamed hand-off copies of the previous run must have drained before their memory is written.
+    // A lent CHUNK workspace is needed from the first launch on; lent SLOTS wait when they are first taken (S2Runner::take_slot),
+    // and the first two stages leave them alone while a copy is pending, so that the hand-off drains under them.
+    if (c->chunk_lent || c->dist) conv_wait_lender(c);
 
     const double g1 = -Dplus;
     const double g2 = -3.0 / 7.0 * Dplus * Dplus;
@@ -550,7 +606,7 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
             st[3].prods = {s2_prod(H(phi, 1, 2), H(phi, 1, 2), 1.0)};
             st[4].prods = {s2_prod(H(phi, 0, 2), H(phi, 0, 2), 1.0)};
         }
-        R.run_stage(st);
+        R.run_stage(st, true);
     }
     if (lam) {
         KGeom k = kgeom(phi2);
@@ -567,7 +623,7 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
             st[0].out = phi3; st[0].op = OP_ASSIGN; st[0].alpha = 0.0;
             st[0].prods = {s2_prod(s2_plain(I[0]), H(phi, 2, 2), 1.0), s2_prod(s2_plain(I[1]), H(phi, 1, 2), 2.0),
                            s2_prod(s2_plain(I[2]), H(phi, 0, 0), -1.0), s2_prod(s2_plain(I[3]), H(phi, 1, 1), -1.0)};
-            R.run_stage(st);
+            R.run_stage(st, true);
         }
         {
             // ---- loops 3..: 3b (:533-538, added to phi3) and the transverse term A_d = P1 - P2 + P3 - P4 (:545-556)

@@ -809,6 +809,10 @@ def check_product_grouping(M, n=32):
                 pl.run_device(O.radial_table(g, amp), particles=True, stream_to=out)
             pl.particles.stream_wait()
             assert pl.conv.sources_info()["path"] == 1 + v2
+            if v2:
+                # the second run found hand-off copies pending on the lent slots: its first two stages stayed on the other
+                # slots (more, narrower loops) and the lent ones were waited for only when the third stage took them
+                assert pl.conv.sources_info()["loops"] > 4, pl.conv.sources_info()
             got = [pl.phi2.get_kspace(), pl.phi3.get_kspace()] + [a.get_kspace() for a in pl.A3]
             assert np.array_equal(out["pos"], pl.particles.download()["pos"])
             # the loan ends with the lender: destroying the particles leaves a convolver that still works on what it owns

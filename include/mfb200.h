@@ -34,7 +34,9 @@ typedef struct mfb_particles mfb_particles; /* opaque: replaces particle::contai
 
 enum { MFB_RSPACE = 1, MFB_KSPACE = 0 };                           /* space_t, include/grid_fft.hh:29 */
 enum { MFB_OP_ASSIGN = 0, MFB_OP_ADD = 1, MFB_OP_SUB = 2, MFB_OP_MULADD = 3 }; /* include/operators.hh:25-35 */
-enum { MFB_LATTICE_SC = 0, MFB_LATTICE_BCC = 1, MFB_LATTICE_FCC = 2, MFB_LATTICE_RSC = 3 }; /* particle_generator.hh:31-39 */
+enum { MFB_LATTICE_SC = 0, MFB_LATTICE_BCC = 1, MFB_LATTICE_FCC = 2, MFB_LATTICE_RSC = 3,
+       MFB_LATTICE_GLASS = -1, MFB_LATTICE_MASKED = -2 }; /* particle_generator.hh:31-39 */
+typedef struct mfb_gradient mfb_gradient;
 
 /* ---- library / device ------------------------------------------------------------------ */
 int mfb_init(int device);            /* selects the CUDA device, creates the stream; fails without a GPU */
@@ -131,6 +133,21 @@ int mfb_add_tides(mfb_grid* phi2, const mfb_grid* phi, const double lambda[3]);
 /* out = G_d (w1 phi + w2 phi2 + w3 phi3) + wc (G_p A_q - G_q A_p), * scale, DC=0 (k-space)
    displacement: w=(1,1,1,1), scale=lunit/L  :841-870;  velocity: w=vfac*(1,2,3,3), scale=vunit/L  :896-941.
    phi2/phi3/A3 may be NULL (lower LPT order).  vbc_* add  - cvbc*T(|k|)*W*G_d/k^2  (:918-921) when non-NULL. */
+/* The gradient operator `lg` of src/ic_generator.cc:377-381 when the reference is built with ENABLE_PLT:
+   particle::lattice_gradient (include/particle_plt.hh:50-587).  The host computes the eigen-decomposition of the lattice's
+   dynamical matrix on an ng^3 helper mesh (GSL, once per run - stays host code); the device needs the four k-space tables
+   its gradient() / vfac_corr() read: tables[0..3] = Re of D_xx_, D_yy_, D_zz_ (radial / theta / phi eigenvalue) and D_xy_
+   (growth-rate correction), each [ng][ng][ng/2+1] doubles.  ngmapto = GridRes.  Single slab, like the reference
+   (Grid_FFT::get_cic_kspace "doesn't work with MPI"). */
+int mfb_gradient_create_plt(mfb_gradient** lg, int ng, int ngmapto, double boxlen, const double* const tables[4]);
+int mfb_gradient_destroy(mfb_gradient* lg);
+/* mfb_lpt_assemble with the gradient operator made explicit.  lg == NULL: op::fourier_gradient.  velocity != 0: the mode is
+   multiplied by lg.vfac_corr (src/ic_generator.cc:929; 1 for the Fourier gradient).  cic_compensation != 0: glass loads,
+   grid_interpolate::compensation_kernel (:861, :924; include/grid_interpolate.hh:195-208). */
+int mfb_lpt_assemble_lg(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* phi2, const mfb_grid* phi3,
+                        mfb_grid* const A3[3], double w1, double w2, double w3, double wc, double scale, const mfb_grid* wnoise,
+                        const double* vbc_table, size_t ntable, double cvbc, const mfb_gradient* lg, int velocity,
+                        int cic_compensation);
 int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* phi2, const mfb_grid* phi3,
                      mfb_grid* const A3[3], double w1, double w2, double w3, double wc, double scale,
                      const mfb_grid* wnoise, const double* vbc_table, size_t ntable, double cvbc);
@@ -210,6 +227,19 @@ int mfb_particles_set_ids(mfb_particles* p, unsigned long long id_offset_species
 int mfb_particles_set_positions(mfb_particles* p, int lattice_index, int idim, double lunit, mfb_grid* field);
 int mfb_particles_set_velocities(mfb_particles* p, int lattice_index, int idim, mfb_grid* field);
 int mfb_particles_set_masses(mfb_particles* p, int lattice_index, double munit, mfb_grid* field);
+/* Masked sc lattice (lattice_type -2, particle_generator.hh:171-260): mask[4a+2b+c] is the species (0, 1 or -1 = nobody)
+   of the cells with parity (i%2, j%2, k%2) = (a,b,c), as set up from ParticleMaskType (:184-205); the container holds the
+   cells of species `lattice_index` in (i,j,k) order.  The set_* calls above then take the masked branches (:351-398 masses
+   with get_mean_mask_value, :479-497 positions, :557-571 velocities); set_ids writes IDoffset*N^3 + cell index (:236-243).
+   Grid sizes must be even (slabs: even local sizes). */
+int mfb_particles_create_masked(mfb_particles** p, const int n[3], int lattice_index, const int mask[8], int real64, int ids64,
+                                int with_masses);
+/* Glass load (lattice_type -1, :262-290): `posr` = glass_loader::glass_posr, np positions in grid units [np][3] (host), what
+   the tiled glass file gives; IDs are IDoffset + i + glass_offset; positions pos/n*lunit + CIC(field, pos), velocities
+   CIC(field, pos) (:498-515, :573-590; grid_interpolate::get_cic_at, include/grid_interpolate.hh:103-148).  The component
+   fields of a glass load carry the CIC compensation kernel (mfb_lpt_assemble_lg).  Single slab. */
+int mfb_particles_create_glass(mfb_particles** p, const int n[3], const double* posr, size_t np, unsigned long long glass_offset,
+                               int real64, int ids64);
 /* device -> host copies into the container vectors the output plugins read (get_*_ptr, particle_container.hh:110-148) */
 int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* ids, void* mass);
 /* Streamed hand-off to the output plugin (replaces the host-side fill of the container that write_particle_data then

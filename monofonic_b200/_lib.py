@@ -80,6 +80,9 @@ def _declare(lib):
         "mfb_apply_radial_table": (i, [vp, vp, vp, sz, i]),
         "mfb_add_tides": (i, [vp, vp, dp]),
         "mfb_lpt_assemble": (i, [vp, i, vp, vp, vp, vpp, d, d, d, d, d, vp, vp, sz, d]),
+        "mfb_lpt_assemble_lg": (i, [vp, i, vp, vp, vp, vpp, d, d, d, d, d, vp, vp, sz, d, vp, i, i]),
+        "mfb_gradient_create_plt": (i, [vpp, i, i, d, vpp]),
+        "mfb_gradient_destroy": (i, [vp]),
         "mfb_density_from_phi": (i, [vp, vp]),
         "mfb_cgrid_create": (i, [vpp, ip, dp]),
         "mfb_cgrid_destroy": (i, [vp]),
@@ -113,6 +116,8 @@ def _declare(lib):
         "mfb_conv_multiply": (i, [vp, vp, vp, vp, i, d]),
         "mfb_lpt_sources": (i, [vp, i, d, vp, vp, vp, vpp, dp]),
         "mfb_particles_create": (i, [vpp, ip, i, i, i, i]),
+        "mfb_particles_create_masked": (i, [vpp, ip, i, ip, i, i, i]),
+        "mfb_particles_create_glass": (i, [vpp, ip, vp, sz, C.c_ulonglong, i, i]),
         "mfb_particles_destroy": (i, [vp]),
         "mfb_particles_count": (sz, [vp]),
         "mfb_particles_set_ids": (i, [vp, ull]),

@@ -227,15 +227,63 @@ __global__ void __launch_bounds__(EW_THREADS) shift_phase_kernel(double2* __rest
 
 // Psi / v assembly (src/ic_generator.cc:841-869, 896-940):
 //   out = G_d (w1 phi + w2 phi2 + w3 phi3) + wc (G_p A_q - G_q A_p) [- cvbc * T(|k|) W G_d / k^2], * scale, DC=0
+// The gradient operator `lg` of src/ic_generator.cc:377-381.  ng == 0: op::fourier_gradient (include/operators.hh:38-61), i k_d
+// with 0 at the Nyquist index.  ng > 0: particle::lattice_gradient (include/particle_plt.hh:551-585, build option ENABLE_PLT):
+// the eigenvalues of the lattice's dynamical matrix in spherical components (tab[0..2] = Re D_xx_, D_yy_, D_zz_ of that class)
+// and the growth-rate correction (tab[3] = Re D_xy_), tabulated by the host on an ng^3 helper mesh in k-space
+// ([ng][ng][ng/2+1]) and read out with the k-space CIC rule of Grid_FFT::get_cic_kspace (include/grid_fft.hh:347-373).
+struct LatticeGradient {
+    const double* tab[4];
+    int ng;
+    double mapratio, boxlen;
+};
+MFB_D double plt_cic(const double* __restrict__ T, int ng, double x, double y, double z) {
+    const int nzc = ng / 2 + 1;
+    const int ix = int(floor(x)), iy = int(floor(y)), iz = int(floor(z));
+    const double dx = x - double(ix), tx = 1.0 - dx, dy = y - double(iy), ty = 1.0 - dy, dz = z - double(iz), tz = 1.0 - dz;
+    const int ix1 = (ix + 1) % ng, iy1 = (iy + 1) % ng, iz1 = min(iz + 1, nzc - 1);
+    auto at = [&](int a, int b, int c) { return __ldg(&T[(long(a) * ng + b) * nzc + c]); };
+    double v = 0.0;   // the order of the reference's eight terms
+    v += at(ix, iy, iz) * tx * ty * tz;
+    v += at(ix, iy, iz1) * tx * ty * dz;
+    v += at(ix, iy1, iz) * tx * dy * tz;
+    v += at(ix, iy1, iz1) * tx * dy * dz;
+    v += at(ix1, iy, iz) * dx * ty * tz;
+    v += at(ix1, iy, iz1) * dx * ty * dz;
+    v += at(ix1, iy1, iz) * dx * dy * tz;
+    v += at(ix1, iy1, iz1) * dx * dy * dz;
+    return v;
+}
+// G[d] = Im lg.gradient(d, ijk); returns lg.vfac_corr(ijk)
+MFB_D double plt_gradient(const LatticeGradient& P, int i, int j, int k, double* G) {
+    const double x = double(i) * P.mapratio, y = double(j) * P.mapratio, z = double(k) * P.mapratio;
+    const double tau = 6.283185307179586476925286766559, h = double(P.ng / 2), n = double(P.ng);
+    // D_xx_.get_k<real_t>(x, y, z) on the unit-length helper mesh (include/grid_fft.hh:299-313)
+    const double kx = (x - (x > h ? n : 0.0)) * tau, ky = (y - (y > h ? n : 0.0)) * tau, kz = (z - (z > h ? n : 0.0)) * tau;
+    const double kr = sqrt(kx * kx + ky * ky + kz * kz);
+    const double kmod = kr / P.mapratio / P.boxlen;
+    const double Dr = plt_cic(P.tab[0], P.ng, x, y, z), Dt = plt_cic(P.tab[1], P.ng, x, y, z), Dp = plt_cic(P.tab[2], P.ng, x, y, z);
+    const double kphi = kr > 0.0 ? atan2(ky, kx) : 0.0, ktheta = kr > 0.0 ? acos(kz / kr) : 0.0;
+    const double st = sin(ktheta), ct = cos(ktheta), sp = sin(kphi), cp = cos(kphi);
+    G[0] = kmod * (Dr * st * cp + Dt * ct * cp - Dp * sp);
+    G[1] = kmod * (Dr * st * sp + Dt * ct * sp + Dp * cp);
+    G[2] = kmod * (Dr * ct - Dt * st);
+    return plt_cic(P.tab[3], P.ng, x, y, z);
+}
 struct AssembleArgs {
     const double2 *phi, *phi2, *phi3, *Ap, *Aq, *wnoise;
     const double* vbc_table;
     double w1, w2, w3, wc, cvbc, scale;
     int d, p, q;
+    LatticeGradient lg;       // lg.ng == 0: plain spectral gradient
+    int vfac_corr;            // velocity fields: multiply the mode by lg.vfac_corr (src/ic_generator.cc:929)
+    int cic_comp;             // glass loads: CIC compensation kernel (include/grid_interpolate.hh:195-208, src/ic_generator.cc:861,924)
 };
 __global__ void __launch_bounds__(EW_THREADS) assemble_kernel(double2* __restrict__ out, AssembleArgs A, KGeom g) {
     MFB_K_LOOP_BEGIN(g)
         double G[3] = {gradk(i, g.n0, g.kf0), gradk(j, g.n1, g.kf1), gradk(k, g.n2, g.kf2)};
+        double vcorr = 1.0;
+        if (A.lg.ng > 0) vcorr = plt_gradient(A.lg, i, j, k, G);
         const double Gd = (A.d == 0) ? G[0] : ((A.d == 1) ? G[1] : G[2]);
         double2 t = A.phi[idx];
         t.x *= A.w1; t.y *= A.w1;
@@ -260,6 +308,17 @@ __global__ void __launch_bounds__(EW_THREADS) assemble_kernel(double2* __restric
                 r.x -= -f * w.y; r.y -= f * w.x;
             }
         }
+        if (A.cic_comp) {
+            // 1 / (sinc(pi k_x / 2 k_ny) sinc(..) sinc(..))^2 with k = get_k (Nyquist index carries +n/2), k / k_ny = 2 m / n
+            auto sinc = [](double x) { return (fabs(x) > 1e-10) ? sin(x) / x : 1.0; };
+            const double hp = 1.5707963267948966192313216916398;
+            const double kx = getk(i, g.n0, g.kf0), ky = getk(j, g.n1, g.kf1), kz = getk(k, g.n2, g.kf2);
+            const double f = sinc(hp * kx / (g.kf0 * double(g.n0 / 2))) * sinc(hp * ky / (g.kf1 * double(g.n1 / 2))) *
+                             sinc(hp * kz / (g.kf2 * double(g.n2 / 2)));
+            const double c = 1.0 / (f * f);
+            r.x *= c; r.y *= c;
+        }
+        if (A.vfac_corr) { r.x *= vcorr; r.y *= vcorr; }
         r.x *= A.scale; r.y *= A.scale;
         if (is_dc) r = make_double2(0.0, 0.0);
         out[idx] = r;
@@ -408,6 +467,119 @@ __global__ void __launch_bounds__(EW_THREADS) lattice_readout_kernel(real_out* _
             o = mul * v;
         }
         dst[size_t(stride) * size_t(slot0 + t) + comp] = real_out(o);
+    }
+}
+
+// ---------------------------------------------------------------- masked sc lattice (include/particle_generator.hh:171-260)
+// A 2x2x2 mask assigns every cell of the N^3 lattice to a species (or to nobody); a species' particles are the cells of its
+// type in (i,j,k) order.  The mask is periodic, so the running particle count of the reference's loops has a closed form.
+struct LatticeMask {
+    int sel[8];      // 1: cell parity (a,b,c) -> index 4a+2b+c belongs to this species
+    long plane[2];   // selected cells in a plane with i % 2 == a
+    long row[4];     // ... in a row with (i % 2, j % 2) == (a, b): index 2a+b
+    int pair[4];     // ... in a pair of cells (k, k+1), k even, of such a row
+};
+// particles of this species before global cell (gi, j, k) in this rank's slab starting at plane i0 (even)
+MFB_D long mask_rank(const LatticeMask& M, int gi, int i0, int j, int k) {
+    const int il = gi - i0, a = gi & 1, b = j & 1;
+    long c = long(il / 2) * (M.plane[0] + M.plane[1]) + ((il & 1) ? M.plane[i0 & 1] : 0);
+    c += long(j / 2) * (M.row[2 * a] + M.row[2 * a + 1]) + (b ? M.row[2 * a] : 0);
+    c += long(k / 2) * M.pair[2 * a + b] + ((k & 1) ? M.sel[4 * a + 2 * b] : 0);
+    return c;
+}
+template <typename id_t>
+__global__ void __launch_bounds__(EW_THREADS) masked_ids_kernel(id_t* __restrict__ ids, LatticeMask M, int n0loc, int n1, int n2, int i0,
+                                                                 unsigned long long idoffset) {
+    const long total = long(n0loc) * n1 * n2;
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * EW_THREADS) {
+        const int k = int(t % n2);
+        const long r = t / n2;
+        const int j = int(r % n1), gi = int(r / n1) + i0;
+        if (!M.sel[4 * (gi & 1) + 2 * (j & 1) + (k & 1)]) continue;
+        // :236-243: IDoffset * global_size + get_cell_idx_1d
+        ids[mask_rank(M, gi, i0, j, k)] = id_t(idoffset + (unsigned long long)((long(gi) * n1 + j) * n2 + k));
+    }
+}
+// kind 0: positions (:479-497, get_unit_r * lunit + f), 1: velocities (:557-571), 2: masses (:351-382, pmean * (f - mean_mask))
+template <typename real_out>
+__global__ void __launch_bounds__(EW_THREADS) masked_readout_kernel(real_out* __restrict__ dst, const double* __restrict__ f, LatticeMask M,
+                                                                     int n0loc, int n0, int n1, int n2, ptrdiff_t pitch, int i0, int kind,
+                                                                     int d, double unit) {
+    const long total = long(n0loc) * n1 * n2;
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < total; t += long(gridDim.x) * EW_THREADS) {
+        const int k = int(t % n2);
+        const long r = t / n2;
+        const int j = int(r % n1), il = int(r / n1), gi = il + i0;
+        if (!M.sel[4 * (gi & 1) + 2 * (j & 1) + (k & 1)]) continue;
+        const long ip = mask_rank(M, gi, i0, j, k);
+        const double v = f[r * pitch + k];
+        if (kind == 2) {
+            // get_mean_mask_value (:89-112): mean over the species' cells of the 2x2x2 block minus the mean over all eight
+            const int oi = il - (gi & 1), oj = j - (j & 1), ok = k - (k & 1);
+            double full = 0.0, masked = 0.0;
+            int cnt = 0;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b)
+                    for (int c = 0; c < 2; ++c) {
+                        const double w = f[(long(oi + a) * n1 + (oj + b)) * pitch + ok + c];
+                        full += w;
+                        if (M.sel[4 * a + 2 * b + c]) { masked += w; ++cnt; }
+                    }
+            full /= 8.0;
+            masked /= double(cnt);
+            dst[ip] = real_out(unit * (v - (masked - full)));
+        } else if (kind == 0) {
+            const int id = (d == 0) ? gi : ((d == 1) ? j : k);
+            const int nd = (d == 0) ? n0 : ((d == 1) ? n1 : n2);
+            const double qpos = double(id) / double(nd);
+#ifdef MFB_EMU
+            dst[3 * ip + d] = real_out(qpos * unit + v);
+#else
+            dst[3 * ip + d] = real_out(__dadd_rn(__dmul_rn(qpos, unit), v));
+#endif
+        } else {
+            dst[3 * ip + d] = real_out(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- glass load (include/particle_generator.hh:498-515, 573-590)
+// particle positions in grid units (glass_loader::glass_posr); the field is read out with the CIC rule of
+// grid_interpolate::get_cic_at (include/grid_interpolate.hh:103-148, single slab).
+template <typename id_t>
+__global__ void __launch_bounds__(EW_THREADS) glass_ids_kernel(id_t* __restrict__ ids, long np, unsigned long long idoffset) {
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < np; t += long(gridDim.x) * EW_THREADS)
+        ids[t] = id_t(idoffset + (unsigned long long)t);
+}
+template <typename real_out>
+__global__ void __launch_bounds__(EW_THREADS) glass_readout_kernel(real_out* __restrict__ dst, const double* __restrict__ f,
+                                                                    const double* __restrict__ posr, long np, int n0, int n1, int n2,
+                                                                    ptrdiff_t pitch, int add_lattice, int d, double lunit) {
+    for (long t = long(blockIdx.x) * EW_THREADS + threadIdx.x; t < np; t += long(gridDim.x) * EW_THREADS) {
+        const double px = posr[3 * t], py = posr[3 * t + 1], pz = posr[3 * t + 2];
+        const int ix = int(px), iy = int(py), iz = int(pz);
+        const double dx = px - double(ix), tx = 1.0 - dx, dy = py - double(iy), ty = 1.0 - dy, dz = pz - double(iz), tz = 1.0 - dz;
+        const int ix1 = (ix + 1) % n0, iy1 = (iy + 1) % n1, iz1 = (iz + 1) % n2;
+        auto at = [&](int a, int b, int c) { return f[(long(a) * n1 + b) * pitch + c]; };
+        double v = 0.0;
+        v += at(ix, iy, iz) * tx * ty * tz;
+        v += at(ix, iy, iz1) * tx * ty * dz;
+        v += at(ix, iy1, iz) * tx * dy * tz;
+        v += at(ix, iy1, iz1) * tx * dy * dz;
+        v += at(ix1, iy, iz) * dx * ty * tz;
+        v += at(ix1, iy, iz1) * dx * ty * dz;
+        v += at(ix1, iy1, iz) * dx * dy * tz;
+        v += at(ix1, iy1, iz1) * dx * dy * dz;
+        if (add_lattice) {
+            const double pd = (d == 0) ? px : ((d == 1) ? py : pz);
+            const int nd = (d == 0) ? n0 : ((d == 1) ? n1 : n2);
+#ifdef MFB_EMU
+            v = pd / double(nd) * lunit + v;
+#else
+            v = __dadd_rn(__dmul_rn(__ddiv_rn(pd, double(nd)), lunit), v);
+#endif
+        }
+        dst[3 * t + d] = real_out(v);
     }
 }
 

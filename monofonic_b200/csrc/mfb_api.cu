@@ -1034,10 +1034,58 @@ static const double LATTICE_SHIFTS[4][8][3] = {
 };
 static const double SECOND_LATTICE_SHIFT[4][3] = {{0.5, 0.5, 0.5}, {0.5, 0.5, 0}, {0.5, 0.5, 0.5}, {0.25, 0.25, 0.25}};
 
+static mfb::LatticeMask make_mask(const mfb_particles* p) {
+    mfb::LatticeMask M;
+    for (int s = 0; s < 8; ++s) M.sel[s] = p->mask[s] == p->mask_index ? 1 : 0;
+    for (int ab = 0; ab < 4; ++ab) {
+        M.pair[ab] = M.sel[2 * ab] + M.sel[2 * ab + 1];
+        M.row[ab] = long(p->n[2] / 2) * M.pair[ab];
+    }
+    for (int a = 0; a < 2; ++a) M.plane[a] = long(p->n[1] / 2) * (M.row[2 * a] + M.row[2 * a + 1]);
+    return M;
+}
 // kind 0: positions, 1: velocities, 2: masses
 static void particles_readout(mfb_particles* p, int kind, int lattice_index, int idim, double unit, mfb_grid* f) {
-    require(lattice_index == 0 || lattice_index == 1, "For Bravais lattice type, lattice index must be 0 or 1.");
     require(f->n[0] == p->n[0] && f->n[1] == p->n[1] && f->n[2] == p->n[2], "field/particle grid size mismatch");
+    if (p->lattice_type == MFB_LATTICE_MASKED || p->lattice_type == MFB_LATTICE_GLASS) {
+        const bool masked = p->lattice_type == MFB_LATTICE_MASKED;
+        if (masked) require(lattice_index == p->mask_index, "For masked lattice type, lattice index must be 0 or 1.");
+        require(masked || kind != 2, "cannot have individual particle masses for glasses");
+        require(f->nloc0 == p->nloc0 && f->off0 == p->off0, "field/particle slab mismatch");
+        const int at = kind == 2 ? MFB_ATTR_MASS : kind;
+        if (p->copy_pending[at]) {
+            cuda_check(cudaStreamWaitEvent(g_ctx.stream, p->copied[at], 0), "cudaStreamWaitEvent");
+            p->copy_pending[at] = false;
+        }
+        to_rspace(f);
+        void* dst = (kind == 0) ? p->pos : ((kind == 1) ? p->vel : p->mass);
+        require(dst != nullptr, "particle buffer not allocated");
+        if (masked) {
+            const mfb::LatticeMask M = make_mask(p);
+            const double u = (kind == 2) ? unit / double(p->np_global) : unit;   // pmeanmass = munit / global_num_particles_ (:363)
+            const unsigned nb = stream_blocks(size_t(p->nloc0) * p->n[1] * p->n[2]);
+            if (p->real64) {
+                MFB_LAUNCH_ROLE(ROLE_PARTICLES, masked_readout_kernel<double>, nb, EW_THREADS, (double*)dst, f->d, M, f->nloc0, f->n[0], f->n[1],
+                           f->n[2], f->pitch, f->off0, kind, idim, u);
+            } else {
+                MFB_LAUNCH_ROLE(ROLE_PARTICLES, masked_readout_kernel<float>, nb, EW_THREADS, (float*)dst, f->d, M, f->nloc0, f->n[0], f->n[1],
+                           f->n[2], f->pitch, f->off0, kind, idim, u);
+            }
+            check_launch("masked_readout");
+        } else {
+            const unsigned nb = stream_blocks(p->np);
+            if (p->real64) {
+                MFB_LAUNCH_ROLE(ROLE_PARTICLES, glass_readout_kernel<double>, nb, EW_THREADS, (double*)dst, f->d, p->glass_pos, long(p->np), f->n[0],
+                           f->n[1], f->n[2], f->pitch, kind == 0 ? 1 : 0, idim, unit);
+            } else {
+                MFB_LAUNCH_ROLE(ROLE_PARTICLES, glass_readout_kernel<float>, nb, EW_THREADS, (float*)dst, f->d, p->glass_pos, long(p->np), f->n[0],
+                           f->n[1], f->n[2], f->pitch, kind == 0 ? 1 : 0, idim, unit);
+            }
+            check_launch("glass_readout");
+        }
+        return;
+    }
+    require(lattice_index == 0 || lattice_index == 1, "For Bravais lattice type, lattice index must be 0 or 1.");
     const int lt = p->lattice_type;
     const int nshift = 1 << lt;
     require(f->nloc0 == p->nloc0 && f->off0 == p->off0, "field/particle slab mismatch");
@@ -1572,9 +1620,48 @@ int mfb_add_tides(mfb_grid* phi2, const mfb_grid* phi, const double lam[3]) {
     check_launch("tides");
     MFB_CATCH
 }
+int mfb_gradient_create_plt(mfb_gradient** out, int ng, int ngmapto, double boxlen, const double* const tables[4]) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(ng >= 2 && ng % 2 == 0 && ngmapto >= 2 && boxlen > 0.0, "lattice_gradient: bad helper mesh / grid size / box length");
+    require(!dist_on(), "the PLT gradient (Grid_FFT::get_cic_kspace) is only available on a single slab");
+    mfb_gradient* lg = new mfb_gradient();
+    lg->ng = ng; lg->ngmapto = ngmapto; lg->boxlen = boxlen;
+    for (int t = 0; t < 4; ++t) lg->tab[t] = nullptr;
+    const size_t bytes = size_t(ng) * ng * (ng / 2 + 1) * sizeof(double);
+    try {
+        for (int t = 0; t < 4; ++t) {
+            require(tables[t] != nullptr, "lattice_gradient: null table");
+            lg->tab[t] = (double*)dev_alloc(bytes);
+            cuda_check(cudaMemcpyAsync(lg->tab[t], tables[t], bytes, cudaMemcpyHostToDevice, g_ctx.stream), "PLT table upload");
+        }
+        cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    } catch (...) {
+        for (int t = 0; t < 4; ++t) if (lg->tab[t]) cudaFree(lg->tab[t]);
+        delete lg;
+        throw;
+    }
+    *out = lg;
+    MFB_CATCH
+}
+int mfb_gradient_destroy(mfb_gradient* lg) {
+    MFB_TRY
+    if (lg) {
+        cudaStreamSynchronize(g_ctx.stream);
+        for (int t = 0; t < 4; ++t) if (lg->tab[t]) cudaFree(lg->tab[t]);
+        delete lg;
+    }
+    MFB_CATCH
+}
 int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* phi2, const mfb_grid* phi3,
                      mfb_grid* const A3[3], double w1, double w2, double w3, double wc, double scale, const mfb_grid* wnoise,
                      const double* vbc_table, size_t ntable, double cvbc) {
+    return mfb_lpt_assemble_lg(out, d, phi, phi2, phi3, A3, w1, w2, w3, wc, scale, wnoise, vbc_table, ntable, cvbc, nullptr, 0, 0);
+}
+int mfb_lpt_assemble_lg(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* phi2, const mfb_grid* phi3,
+                        mfb_grid* const A3[3], double w1, double w2, double w3, double wc, double scale, const mfb_grid* wnoise,
+                        const double* vbc_table, size_t ntable, double cvbc, const mfb_gradient* lg, int velocity,
+                        int cic_compensation) {
     MFB_TRY
     require(d >= 0 && d < 3, "assemble: bad dimension");
     require(phi->space == MFB_KSPACE, "assemble: phi must be in k-space");
@@ -1606,6 +1693,17 @@ int mfb_lpt_assemble(mfb_grid* out, int d, const mfb_grid* phi, const mfb_grid* 
         a.wnoise = reinterpret_cast<const double2*>(wnoise->d);
         a.cvbc = cvbc;
     }
+    if (lg) {
+        require(!phi->dist, "the PLT gradient is only available on a single slab");
+        require(phi->n[0] == lg->ngmapto && phi->n[1] == lg->ngmapto && phi->n[2] == lg->ngmapto,
+                "lattice_gradient was set up for another GridRes");
+        for (int t = 0; t < 4; ++t) a.lg.tab[t] = lg->tab[t];
+        a.lg.ng = lg->ng;
+        a.lg.mapratio = double(lg->ng) / double(lg->ngmapto);
+        a.lg.boxlen = lg->boxlen;
+        a.vfac_corr = velocity ? 1 : 0;
+    }
+    a.cic_comp = cic_compensation ? 1 : 0;
     out->space = MFB_KSPACE;
     KGeom k = kgeom(phi);
     MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, assemble_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(out->d), a, k);
@@ -1944,6 +2042,75 @@ int mfb_particles_create(mfb_particles** out, const int n[3], int lattice_type, 
     *out = p;
     MFB_CATCH
 }
+static void particles_alloc(mfb_particles* p, int with_masses) {
+    const size_t rs = p->real64 ? 8 : 4, is = p->ids64 ? 8 : 4;
+    p->posvel_bytes = 6 * p->np * rs;
+    p->pos = p->ids = p->mass = nullptr;
+    try {
+        p->pos = dev_alloc(std::max<size_t>(p->posvel_bytes, 16));
+        p->vel = (char*)p->pos + 3 * p->np * rs;
+        p->ids = dev_alloc(std::max<size_t>(p->np * is, 16));
+        p->mass = with_masses ? dev_alloc(std::max<size_t>(p->np * rs, 16)) : nullptr;
+    } catch (...) {
+        if (p->pos) cudaFree(p->pos);
+        if (p->ids) cudaFree(p->ids);
+        throw;
+    }
+}
+int mfb_particles_create_masked(mfb_particles** out, const int n[3], int lattice_index, const int mask[8], int real64, int ids64,
+                                int with_masses) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require((size_t(n[0]) * n[1] * n[2]) % 8 == 0 && n[0] % 2 == 0 && n[1] % 2 == 0 && n[2] % 2 == 0,
+            "For masked lattice type, linear field resolution must be a multiple of two.");
+    require(lattice_index == 0 || lattice_index == 1, "For masked lattice type, lattice index must be 0 or 1.");
+    mfb_particles* p = new mfb_particles();
+    for (int d = 0; d < 3; ++d) p->n[d] = n[d];
+    p->lattice_type = MFB_LATTICE_MASKED; p->real64 = real64; p->ids64 = ids64;
+    p->mask_index = lattice_index;
+    for (int s = 0; s < 8; ++s) p->mask[s] = mask[s];
+    p->nloc0 = n[0]; p->off0 = 0;
+    if (dist_on()) {
+        if (n[0] % (2 * D().nranks)) { delete p; throw std::runtime_error("masked lattice on slabs needs an even number of planes per GPU"); }
+        p->nloc0 = n[0] / D().nranks; p->off0 = D().rank * p->nloc0;
+    }
+    const mfb::LatticeMask M = make_mask(p);
+    p->np = size_t(p->nloc0 / 2) * size_t(M.plane[0] + M.plane[1]);
+    p->np_global = size_t(n[0] / 2) * size_t(M.plane[0] + M.plane[1]);
+    if (p->np == 0) { delete p; throw std::runtime_error("masked lattice: no cell carries this species"); }
+    try { particles_alloc(p, with_masses); } catch (...) { delete p; throw; }
+    *out = p;
+    MFB_CATCH
+}
+int mfb_particles_create_glass(mfb_particles** out, const int n[3], const double* posr, size_t np, unsigned long long glass_offset,
+                               int real64, int ids64) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    require(!dist_on(), "glass loads are only available on a single slab");
+    require(posr != nullptr && np > 0, "glass load: no particle positions");
+    for (size_t i = 0; i < 3 * np; ++i)
+        require(posr[i] >= 0.0 && posr[i] < double(n[i % 3]), "glass load: position outside the grid (grid units expected)");
+    mfb_particles* p = new mfb_particles();
+    for (int d = 0; d < 3; ++d) p->n[d] = n[d];
+    p->lattice_type = MFB_LATTICE_GLASS; p->real64 = real64; p->ids64 = ids64;
+    p->nloc0 = n[0]; p->off0 = 0;
+    p->np = p->np_global = np;
+    p->glass_off = glass_offset;
+    try {
+        particles_alloc(p, 0);
+        try {
+            p->glass_pos = (double*)dev_alloc(3 * np * sizeof(double));
+            cuda_check(cudaMemcpyAsync(p->glass_pos, posr, 3 * np * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream), "glass positions");
+            cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+        } catch (...) {
+            cudaFree(p->pos); cudaFree(p->ids);
+            if (p->glass_pos) cudaFree(p->glass_pos);
+            throw;
+        }
+    } catch (...) { delete p; throw; }
+    *out = p;
+    MFB_CATCH
+}
 int mfb_particles_destroy(mfb_particles* p) {
     MFB_TRY
     if (p) {
@@ -1958,6 +2125,7 @@ int mfb_particles_destroy(mfb_particles* p) {
         for (int a = 0; a < 4; ++a) if (p->copied[a]) cudaEventDestroy(p->copied[a]);
         cudaFree(p->pos); cudaFree(p->ids);
         if (p->mass) cudaFree(p->mass);
+        if (p->glass_pos) cudaFree(p->glass_pos);
         delete p;
     }
     MFB_CATCH
@@ -1965,6 +2133,29 @@ int mfb_particles_destroy(mfb_particles* p) {
 size_t mfb_particles_count(const mfb_particles* p) { return p->np; }
 int mfb_particles_set_ids(mfb_particles* p, unsigned long long id_offset_species) {
     MFB_TRY
+    if (p->lattice_type == MFB_LATTICE_MASKED) {
+        const mfb::LatticeMask M = make_mask(p);
+        const unsigned long long off = id_offset_species * (unsigned long long)p->n[0] * (unsigned long long)p->n[1] * (unsigned long long)p->n[2];
+        const unsigned nb = stream_blocks(size_t(p->nloc0) * p->n[1] * p->n[2]);
+        if (p->ids64) {
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, masked_ids_kernel<unsigned long long>, nb, EW_THREADS, (unsigned long long*)p->ids, M, p->nloc0, p->n[1], p->n[2], p->off0, off);
+        } else {
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, masked_ids_kernel<unsigned int>, nb, EW_THREADS, (unsigned int*)p->ids, M, p->nloc0, p->n[1], p->n[2], p->off0, off);
+        }
+        check_launch("masked_ids");
+        return 0;
+    }
+    if (p->lattice_type == MFB_LATTICE_GLASS) {
+        const unsigned nb = stream_blocks(p->np);
+        const unsigned long long off = id_offset_species + p->glass_off;   // :277-286: IDoffset + i + glass_ptr_->offset()
+        if (p->ids64) {
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, glass_ids_kernel<unsigned long long>, nb, EW_THREADS, (unsigned long long*)p->ids, long(p->np), off);
+        } else {
+            MFB_LAUNCH_ROLE(ROLE_PARTICLES, glass_ids_kernel<unsigned int>, nb, EW_THREADS, (unsigned int*)p->ids, long(p->np), off);
+        }
+        check_launch("glass_ids");
+        return 0;
+    }
     const long ncell = long(p->n[0]) * p->n[1] * p->n[2];            // global
     const long nloc = long(p->nloc0) * p->n[1] * p->n[2];            // this slab
     const long cell0 = long(p->off0) * p->n[1] * p->n[2];

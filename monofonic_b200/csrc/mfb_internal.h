@@ -90,6 +90,19 @@ struct mfb_particles {
     // streamed hand-off: per attribute, event recorded on the copy stream after its D2H copy (null: none pending)
     cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr};
     bool copy_pending[4] = {false, false, false, false};
+    // masked sc lattice (lattice_type -2): the species this container holds and the 2x2x2 type mask
+    int mask_index = 0;
+    int mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t np_global = 0;
+    // glass load (lattice_type -1): positions in grid units on the device, offset of this rank's particles
+    double* glass_pos = nullptr;
+    unsigned long long glass_off = 0;
+};
+// the gradient operator of src/ic_generator.cc:377-381 when it is particle::lattice_gradient (PLT): four tables on the device
+struct mfb_gradient {
+    int ng, ngmapto;
+    double boxlen;
+    double* tab[4];
 };
 
 namespace mfb {

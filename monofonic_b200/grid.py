@@ -408,20 +408,74 @@ class NaiveConvolver(OrszagConvolver):
     _create = "mfb_conv_create_naive"
 
 
-LATTICE = {"sc": 0, "bcc": 1, "fcc": 2, "rsc": 3}
+LATTICE = {"sc": 0, "bcc": 1, "fcc": 2, "rsc": 3, "glass": -1, "masked": -2}
+
+
+def particle_type_mask(DoBaryons: bool, ParticleMaskType: int = 3):
+    """the 2x2x2 species mask of a masked lattice as lattice_generator's ctor sets it up from [setup] DoBaryons and
+    ParticleMaskType (include/particle_generator.hh:184-205): index 4a+2b+c for cell parity (a,b,c)"""
+    if not DoBaryons:
+        return [0] * 8
+    m = [-1] * 8
+    m[0] = 0
+    if ParticleMaskType & 1:
+        m[1] = m[2] = m[4] = 0      # edge centres
+    if ParticleMaskType & 2:
+        m[3] = m[5] = m[6] = 0      # face centres
+    m[7] = 1                        # baryon at the cell centre
+    return m
+
+
+class lattice_gradient:
+    """particle::lattice_gradient (include/particle_plt.hh:50-587, build option ENABLE_PLT) as the device sees it: the four
+    k-space tables its gradient() / vfac_corr() read (Re D_xx_, D_yy_, D_zz_, D_xy_ on the ng^3 helper mesh, computed by the
+    host's eigen-decomposition), uploaded once.  Passed to LPTPipeline as `lg` in place of op::fourier_gradient."""
+
+    def __init__(self, ngridself, GridRes, BoxLength, D_r, D_theta, D_phi, mu):
+        self._lib = _lib()
+        self._h = C.c_void_p()
+        ng = int(ngridself)
+        tabs = [np.ascontiguousarray(t, dtype=np.float64) for t in (D_r, D_theta, D_phi, mu)]
+        for t in tabs:
+            if t.shape != (ng, ng, ng // 2 + 1):
+                raise ValueError(f"lattice_gradient: tables must be [{ng}][{ng}][{ng // 2 + 1}]")
+        arr = (C.c_void_p * 4)(*[t.ctypes.data for t in tabs])
+        L.check(self._lib.mfb_gradient_create_plt(C.byref(self._h), ng, int(GridRes), float(BoxLength), arr), self._lib)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.mfb_gradient_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
 
 
 class Particles:
-    """particle::lattice_generator + particle::container for the Bravais lattices."""
+    """particle::lattice_generator + particle::container: Bravais lattices, the masked sc lattice (`mask` = the 2x2x2 species
+    mask, see particle_type_mask) and glass loads (`glass` = (positions in grid units [np][3], offset of the first particle))."""
 
-    def __init__(self, lattice_type, lattice_index, b64reals, b64ids, bwithmasses, IDoffset, field: Grid_FFT):
+    def __init__(self, lattice_type, lattice_index, b64reals, b64ids, bwithmasses, IDoffset, field: Grid_FFT, mask=None, glass=None):
         self._lib = _lib()
         self._h = C.c_void_p()
         lt = LATTICE[lattice_type] if isinstance(lattice_type, str) else int(lattice_type)
         self.lattice_type, self.lattice_index = lt, int(lattice_index)
         self.b64reals, self.b64ids, self.bwithmasses = bool(b64reals), bool(b64ids), bool(bwithmasses)
-        L.check(self._lib.mfb_particles_create(C.byref(self._h), _i3(field.n_), lt, int(self.b64reals), int(self.b64ids),
-                                               int(self.bwithmasses)), self._lib)
+        if lt == LATTICE["masked"]:
+            m = (C.c_int * 8)(*[int(v) for v in (mask if mask is not None else [0] * 8)])
+            L.check(self._lib.mfb_particles_create_masked(C.byref(self._h), _i3(field.n_), self.lattice_index, m, int(self.b64reals),
+                                                          int(self.b64ids), int(self.bwithmasses)), self._lib)
+        elif lt == LATTICE["glass"]:
+            if glass is None:
+                raise RuntimeError("glass load needs the glass positions (glass_loader::glass_posr)")
+            if self.bwithmasses:
+                raise RuntimeError("cannot have individual particle masses for glasses")   # particle_generator.hh:399-403
+            pos = np.ascontiguousarray(glass[0], dtype=np.float64).reshape(-1, 3)
+            L.check(self._lib.mfb_particles_create_glass(C.byref(self._h), _i3(field.n_), pos.ctypes.data_as(C.c_void_p), pos.shape[0],
+                                                         int(glass[1]), int(self.b64reals), int(self.b64ids)), self._lib)
+        else:
+            L.check(self._lib.mfb_particles_create(C.byref(self._h), _i3(field.n_), lt, int(self.b64reals), int(self.b64ids),
+                                                   int(self.bwithmasses)), self._lib)
         L.check(self._lib.mfb_particles_set_ids(self._h, int(IDoffset)), self._lib)
 
     def __del__(self):

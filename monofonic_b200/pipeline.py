@@ -35,6 +35,9 @@ class lpt_config:
     ids64: bool = False          # output_plugin::has_64bit_ids()
     tides: tuple | None = None   # LSS_aniso_l{x,y,z}
     ConvolverType: str = "orszag"  # the reference's compile-time CONVOLVER_TYPE (CMakeLists.txt): "orszag" | "naive"
+    DoBaryons: bool = False      # masked lattice: selects the species mask (include/particle_generator.hh:184-205)
+    ParticleMaskType: int = 3
+    glass: tuple | None = None   # ParticleLoad "glass": (glass_loader::glass_posr in grid units [np][3], offset)
 
 
 def radial_table(n: int, boxlen: float, amplitude) -> np.ndarray:
@@ -73,6 +76,7 @@ class LPTPipeline:
         self.conv = mkconv(self.N, self.Lbox) if order > 1 else None
         self.particles = None
         self._ids_streamed = False
+        self.lg = None   # the gradient operator of src/ic_generator.cc:377-381: None = op::fourier_gradient, or a lattice_gradient
 
     # -- stages -------------------------------------------------------------------------
     def set_noise_k(self, W: np.ndarray):
@@ -102,16 +106,18 @@ class LPTPipeline:
                                           self.phi2._h if self.order > 1 else None,
                                           self.phi3._h if self.order > 2 else None, A3, lam), self._lib)
 
-    def _assemble(self, d, w, wc, scale, vbc=None):
+    def _assemble(self, d, w, wc, scale, vbc=None, velocity=False):
         A3 = (C.c_void_p * 3)(*[(g._h if g.is_allocated() else None) for g in self.A3])
         o = self.order
         tab, ntab, cv, wn = None, 0, 0.0, None
         if vbc is not None:
             t = np.ascontiguousarray(vbc[0], dtype=np.float64)
             tab, ntab, cv, wn = t.ctypes.data_as(C.c_void_p), t.size, float(vbc[1]), self.wnoise._h
-        L.check(self._lib.mfb_lpt_assemble(self.tmp._h, d, self.phi._h, self.phi2._h if o > 1 else None,
-                                           self.phi3._h if o > 2 else None, A3 if o > 2 else None,
-                                           w[0], w[1], w[2], wc, scale, wn, tab, ntab, cv), self._lib)
+        glass = self.cfg.ParticleLoad == "glass"   # particles read out by CIC interpolation: compensation kernel (:861, :924)
+        L.check(self._lib.mfb_lpt_assemble_lg(self.tmp._h, d, self.phi._h, self.phi2._h if o > 1 else None,
+                                              self.phi3._h if o > 2 else None, A3 if o > 2 else None,
+                                              w[0], w[1], w[2], wc, scale, wn, tab, ntab, cv,
+                                              self.lg._h if self.lg is not None else None, int(velocity), int(glass)), self._lib)
 
     def displacement_field(self, d):
         """tmp <- Psi_d in real space (src/ic_generator.cc:832-871)"""
@@ -129,7 +135,7 @@ class LPTPipeline:
             # external tides: anisotropic velocity growth factor alpha_d^2, alpha_d = 1 - D+ lambda_d
             # (src/ic_generator.cc:238-242, applied at :931-934 to the whole mode incl. the v_bc term)
             scale *= (1.0 - c.Dplus0 * c.tides[d]) ** 2
-        self._assemble(d, (v, 2 * v, 3 * v), 3 * v, scale, vbc)
+        self._assemble(d, (v, 2 * v, 3 * v), 3 * v, scale, vbc, velocity=True)
         self.tmp.FourierTransformBackward()
         return self.tmp
 
@@ -193,7 +199,13 @@ class LPTPipeline:
                 self.conv.borrow_accumulator(None)  # a previous loan ends with its lender
             self.particles = None                   # release the old container first: two would not fit at 1024^3
         self._lattice_index = lattice_index
-        self.particles = Particles(c.ParticleLoad, lattice_index, c.real64, c.ids64, with_masses, id_offset, self.tmp)
+        mask = None
+        if c.ParticleLoad == "masked":
+            from .grid import particle_type_mask
+
+            mask = particle_type_mask(c.DoBaryons, c.ParticleMaskType)
+        self.particles = Particles(c.ParticleLoad, lattice_index, c.real64, c.ids64, with_masses, id_offset, self.tmp,
+                                   mask=mask, glass=c.glass)
         if self.conv is not None and c.ConvolverType == "orszag":
             # the position/velocity arrays hold nothing while the sources are computed: the convolver may use them as
             # workspace (slots of the shared-transform source stage, or the accumulator of product groups)

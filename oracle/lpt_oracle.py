@@ -394,43 +394,126 @@ def lpt_potentials(g: GridSpec, phi, order, Dplus0=1.0, convolver=None, tides=No
 # --------------------------------------------------------------------------------------
 # Displacement / velocity assembly  (src/ic_generator.cc:832-871, 888-942)
 # --------------------------------------------------------------------------------------
-def displacement_k(g: GridSpec, pots, order, d, scale=1.0):
-    """k-space Psi_d * scale; scale = lunit/boxlen (:866)."""
+class PLTGradient:
+    """particle::lattice_gradient::gradient / vfac_corr (include/particle_plt.hh:551-585, build option ENABLE_PLT), given
+    the four helper-mesh tables the class holds after its eigen-decomposition (Re D_xx_ = radial, D_yy_ = theta, D_zz_ = phi
+    eigenvalue, D_xy_ = growth-rate correction; [ng][ng][ng/2+1]).  The decomposition itself (Ewald sums, GSL eigen-solver)
+    is host work outside the path and is not restated."""
+
+    def __init__(self, ng, ngmapto, boxlen, D_r, D_theta, D_phi, mu):
+        self.ng, self.ngmapto, self.boxlen = int(ng), int(ngmapto), float(boxlen)
+        self.mapratio = float(ng) / float(ngmapto)                       # :523
+        self.tab = [np.asarray(t, dtype=np.float64) for t in (D_r, D_theta, D_phi, mu)]
+
+    def _coords(self, g: GridSpec):
+        n = g.n
+        idx = np.arange(n, dtype=np.float64) * self.mapratio
+        return idx[:, None, None], idx[None, :, None], idx[None, None, : g.nzc]
+
+    def cic_kspace(self, T, x, y, z):
+        """Grid_FFT::get_cic_kspace (include/grid_fft.hh:347-373), real part; x, y, z broadcastable index arrays"""
+        ng, nzc = self.ng, self.ng // 2 + 1
+        x, y, z = np.broadcast_arrays(x, y, z)
+        ix, iy, iz = np.floor(x).astype(int), np.floor(y).astype(int), np.floor(z).astype(int)
+        dx, dy, dz = x - ix, y - iy, z - iz
+        tx, ty, tz = 1.0 - dx, 1.0 - dy, 1.0 - dz
+        ix1, iy1, iz1 = (ix + 1) % ng, (iy + 1) % ng, np.minimum(iz + 1, nzc - 1)
+        v = T[ix, iy, iz] * tx * ty * tz
+        v = v + T[ix, iy, iz1] * tx * ty * dz
+        v = v + T[ix, iy1, iz] * tx * dy * tz
+        v = v + T[ix, iy1, iz1] * tx * dy * dz
+        v = v + T[ix1, iy, iz] * dx * ty * tz
+        v = v + T[ix1, iy, iz1] * dx * ty * dz
+        v = v + T[ix1, iy1, iz] * dx * dy * tz
+        v = v + T[ix1, iy1, iz1] * dx * dy * dz
+        return v
+
+    def all(self, g: GridSpec):
+        """-> ([Im gradient(0), Im gradient(1), Im gradient(2)], vfac_corr) on the mode lattice [n][n][nzc]"""
+        x, y, z = self._coords(g)
+        ng = float(self.ng)
+        h = float(self.ng // 2)
+        tau = 2.0 * np.pi
+        # D_xx_.get_k<real_t>(ix, iy, iz) on the unit-length helper mesh (include/grid_fft.hh:299-313)
+        kx, ky, kz = np.broadcast_arrays((x - (x > h) * ng) * tau, (y - (y > h) * ng) * tau, (z - (z > h) * ng) * tau)
+        kr = np.sqrt(kx * kx + ky * ky + kz * kz)
+        kmod = kr / self.mapratio / self.boxlen
+        Dr, Dt, Dp = (self.cic_kspace(self.tab[t], x, y, z) for t in range(3))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            kphi = np.where(kr > 0.0, np.arctan2(ky, kx), 0.0)
+            ktheta = np.where(kr > 0.0, np.arccos(np.where(kr > 0.0, kz / np.where(kr > 0.0, kr, 1.0), 0.0)), 0.0)
+        st, ct, sp, cp = np.sin(ktheta), np.cos(ktheta), np.sin(kphi), np.cos(kphi)
+        G = [kmod * (Dr * st * cp + Dt * ct * cp - Dp * sp), kmod * (Dr * st * sp + Dt * ct * sp + Dp * cp),
+             kmod * (Dr * ct - Dt * st)]
+        return G, self.cic_kspace(self.tab[3], x, y, z)
+
+
+def cic_compensation_kernel(g: GridSpec):
+    """grid_interpolate<1,.>::compensation_kernel (include/grid_interpolate.hh:195-208) on the mode lattice:
+    1 / (sinc(pi k_x / 2 k_ny) sinc(..) sinc(..))^(1+1), k from get_k (the Nyquist index carries +N/2)"""
+    kny = g.kfac * (g.n // 2)
+
+    def sinc(x):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(np.abs(x) > 1e-10, np.sin(x) / np.where(x == 0.0, 1.0, x), 1.0)
+    kx, ky, kz = g.kvec()
+    f = sinc(0.5 * np.pi * kx / kny) * sinc(0.5 * np.pi * ky / kny) * sinc(0.5 * np.pi * kz / kny)
+    return 1.0 / (f * f)
+
+
+def _gradients(g: GridSpec, lg):
+    """(list of the three gradient factors as complex arrays, vfac_corr) for op::fourier_gradient (lg None) or PLT"""
+    if lg is None:
+        return [g.grad(d) for d in range(3)], 1.0
+    G, vc = lg.all(g)
+    return [1j * a for a in G], vc
+
+
+def displacement_k(g: GridSpec, pots, order, d, scale=1.0, lg=None, glass=False):
+    """k-space Psi_d * scale; scale = lunit/boxlen (:866).  lg: a PLTGradient in place of op::fourier_gradient (:377-381);
+    glass: CIC compensation kernel (:861-863)."""
     p, q = (d + 1) % 3, (d + 2) % 3
+    gr, _ = _gradients(g, lg)
     tot = pots["phi"].copy()
     if order > 1:
         tot = tot + pots["phi2"]
     if order > 2:
         tot = tot + pots["phi3"]
-    tmp = g.grad(d) * tot
+    tmp = gr[d] * tot
     if order > 2:
-        tmp = tmp + g.grad(p) * pots["A3"][q] - g.grad(q) * pots["A3"][p]
+        tmp = tmp + gr[p] * pots["A3"][q] - gr[q] * pots["A3"][p]
+    if glass:
+        tmp = tmp * cic_compensation_kernel(g)
     tmp = tmp * scale
     return zero_dc(tmp)
 
 
-def velocity_k(g: GridSpec, pots, order, d, vfac, scale=1.0, vbc=None, tides=None, Dplus0=None):
+def velocity_k(g: GridSpec, pots, order, d, vfac, scale=1.0, vbc=None, tides=None, Dplus0=None, lg=None, glass=False):
     """k-space v_d * scale; scale = vunit/boxlen (:937).
     vbc = (C_species, theta_bc_amplitude(|k|) callable, W) adds the relative-velocity term (:918-921).
     tides = (lambda_x, lambda_y, lambda_z) with Dplus0: external tides (only honoured at LPTorder > 1, :190-193) multiply
     the whole mode by the anisotropic velocity growth factor alpha_d^2, alpha_d = 1 - D+ lambda_d (:238-242, :931-934)."""
     p, q = (d + 1) % 3, (d + 2) % 3
+    gr, vcorr = _gradients(g, lg)
     tot = vfac * pots["phi"]
     if order > 1:
         tot = tot + (2 * vfac) * pots["phi2"]
     if order > 2:
         tot = tot + (3 * vfac) * pots["phi3"]
-    tmp = g.grad(d) * tot
+    tmp = gr[d] * tot
     if order > 2:
-        tmp = tmp + (3 * vfac) * (g.grad(p) * pots["A3"][q] - g.grad(q) * pots["A3"][p])
+        tmp = tmp + (3 * vfac) * (gr[p] * pots["A3"][q] - gr[q] * pots["A3"][p])
     if vbc is not None:
         C, amp, W = vbc
         k2 = g.k2()
         kn = np.sqrt(k2)
         with np.errstate(divide="ignore", invalid="ignore"):
-            term = vfac * C * amp(kn) * W * g.grad(d) / (kn * kn)
+            term = vfac * C * amp(kn) * W * gr[d] / (kn * kn)
         term[0, 0, 0] = 0.0
         tmp = tmp - term
+    if glass:
+        tmp = tmp * cic_compensation_kernel(g)      # :923-926
+    tmp = tmp * vcorr                               # :929, lg.vfac_corr (1 for the Fourier gradient)
     if tides is not None and order > 1:
         tmp = tmp * (1.0 - Dplus0 * tides[d]) ** 2
     tmp = tmp * scale
@@ -582,6 +665,99 @@ def set_masses(g: GridSpec, field_r, lattice_type, lattice_index, munit, real64=
             f = shift_field_r(g, f, s)
         outs.append((pmean * f).reshape(-1))
     res = np.concatenate(outs)
+    return res if real64 else res.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# Masked sc lattice and glass loads (include/particle_generator.hh:171-290, 351-398, 479-515, 557-590)
+# --------------------------------------------------------------------------------------
+def particle_type_mask(do_baryons, mask_type=3):
+    """the 2x2x2 species mask from [setup] DoBaryons / ParticleMaskType (:184-205); index 4a+2b+c"""
+    if not do_baryons:
+        return [0] * 8
+    m = [-1] * 8
+    m[0] = 0
+    if mask_type & 1:
+        m[1] = m[2] = m[4] = 0
+    if mask_type & 2:
+        m[3] = m[5] = m[6] = 0
+    m[7] = 1
+    return m
+
+
+def _mask_select(n, mask, lattice_index):
+    """boolean [n][n][n]: get_mask_value(cell) == lattice_index (:84-87)"""
+    par = np.arange(n) % 2
+    sig = (par[:, None, None] * 2 + par[None, :, None]) * 2 + par[None, None, :]
+    return np.asarray(mask)[sig] == lattice_index
+
+
+def masked_ids(n, mask, lattice_index, id_offset=0, ids64=False):
+    """:236-243: IDoffset*N^3 + get_cell_idx_1d of the species' cells in (i,j,k) order"""
+    sel = _mask_select(n, mask, lattice_index).reshape(-1)
+    ids = np.uint64(id_offset * n ** 3) + np.arange(n ** 3, dtype=np.uint64)[sel]
+    return ids if ids64 else ids.astype(np.uint32)
+
+
+def masked_positions(g: GridSpec, field_r, d, mask, lattice_index, lunit, real64=True):
+    """:479-497: get_unit_r(i,j,k)[d] * lunit + field"""
+    n = g.n
+    shape = [1, 1, 1]
+    shape[d] = n
+    q = (np.arange(n, dtype=np.float64) / float(n)).reshape(shape)
+    res = (q * lunit + field_r)[_mask_select(n, mask, lattice_index)]
+    return res if real64 else res.astype(np.float32)
+
+
+def masked_velocities(g: GridSpec, field_r, mask, lattice_index, real64=True):
+    """:557-571"""
+    res = field_r[_mask_select(g.n, mask, lattice_index)]
+    return res if real64 else res.astype(np.float32)
+
+
+def masked_masses(g: GridSpec, field_r, mask, lattice_index, munit, real64=True):
+    """:351-382 with get_mean_mask_value (:89-112): pmean * (field - (mean over the species' cells of the 2x2x2 block - mean
+    over all eight cells)), pmean = munit / number of particles of the species"""
+    n = g.n
+    sel = _mask_select(n, mask, lattice_index)
+    blocks = field_r.reshape(n // 2, 2, n // 2, 2, n // 2, 2)
+    sel8 = (np.asarray(mask) == lattice_index).reshape(2, 2, 2)
+    full = blocks.sum(axis=(1, 3, 5)) / 8.0
+    masked = (blocks * sel8[None, :, None, :, None, :]).sum(axis=(1, 3, 5)) / float(sel8.sum())
+    mm = np.repeat(np.repeat(np.repeat(masked - full, 2, 0), 2, 1), 2, 2)
+    pmean = munit / float(sel.sum())
+    res = (pmean * (field_r - mm))[sel]
+    return res if real64 else res.astype(np.float32)
+
+
+def cic_at(field_r, pos):
+    """grid_interpolate<1,.>::get_cic_at (include/grid_interpolate.hh:103-148, non-distributed branch); pos [np][3] in grid
+    units"""
+    n0, n1, n2 = field_r.shape
+    ix, iy, iz = (pos[:, c].astype(np.int64) for c in range(3))
+    dx, dy, dz = pos[:, 0] - ix, pos[:, 1] - iy, pos[:, 2] - iz
+    tx, ty, tz = 1.0 - dx, 1.0 - dy, 1.0 - dz
+    ix1, iy1, iz1 = (ix + 1) % n0, (iy + 1) % n1, (iz + 1) % n2
+    v = field_r[ix, iy, iz] * tx * ty * tz
+    v = v + field_r[ix, iy, iz1] * tx * ty * dz
+    v = v + field_r[ix, iy1, iz] * tx * dy * tz
+    v = v + field_r[ix, iy1, iz1] * tx * dy * dz
+    v = v + field_r[ix1, iy, iz] * dx * ty * tz
+    v = v + field_r[ix1, iy, iz1] * dx * ty * dz
+    v = v + field_r[ix1, iy1, iz] * dx * dy * tz
+    v = v + field_r[ix1, iy1, iz1] * dx * dy * dz
+    return v
+
+
+def glass_positions(g: GridSpec, field_r, d, posr, lunit, real64=True):
+    """:498-515: pos[d] / n * lunit + CIC(field, pos)"""
+    res = posr[:, d] / float(g.n) * lunit + cic_at(field_r, posr)
+    return res if real64 else res.astype(np.float32)
+
+
+def glass_velocities(g: GridSpec, field_r, posr, real64=True):
+    """:573-590"""
+    res = cic_at(field_r, posr)
     return res if real64 else res.astype(np.float32)
 
 

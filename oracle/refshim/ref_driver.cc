@@ -21,6 +21,7 @@
 #include <grid_fft.hh>
 #include <convolution.hh>
 #include <operators.hh>
+#include <grid_interpolate.hh>
 #if defined(USE_MPI)   // the reference's particle generator only compiles in its MPI build (the non-MPI branches of
 #define USE_HDF5       // grid_ghosts.hh / glass_loader.hh use MPI unguarded), and its glass loader wants HDF_IO.hh
 #include <particle_container.hh>
@@ -92,6 +93,7 @@ static void dump(grid_t& g, const std::string& dir, const std::string& name) {
 // particle::lattice_generator of the reference (include/particle_generator.hh:129-170, 292-350, 422-467, 520-562) on the
 // fields phi (positions, masses) and psi (velocities) in real space:
 //   ref_driver_mpi particles <n> <boxlen> <phi_k.bin> <psi_k.bin> <outdir> <lattice_type> <lattice_index> <zero_field 0|1>
+//                            [<DoBaryons yes|no> <ParticleMaskType>]      (lattice_type -2: the masked sc lattice, :171-260)
 static int run_particles(int argc, char** argv) {
     if (argc < 10) return 1;
     const size_t n = std::strtoul(argv[2], nullptr, 10);
@@ -104,7 +106,11 @@ static int run_particles(int argc, char** argv) {
     const std::array<real_t, 3> B{L, L, L};
     grid_t phi(N, B), psi(N, B), tmp(N, B);
     if (!load_k(phi, argv[4]) || !load_k(psi, argv[5])) return 2;
-    { FILE* f = std::fopen((dir + "/empty.conf").c_str(), "w"); std::fputs("[setup]\nDoBaryons = no\n", f); std::fclose(f); }
+    {
+        FILE* f = std::fopen((dir + "/empty.conf").c_str(), "w");
+        std::fprintf(f, "[setup]\nDoBaryons = %s\nParticleMaskType = %s\n", argc > 10 ? argv[10] : "no", argc > 11 ? argv[11] : "3");
+        std::fclose(f);
+    }
     config_file cf(dir + "/empty.conf");
     const real_t lunit = L, munit = 2.5;
     particle::lattice_generator<grid_t> lg(lt, lidx, true, true, true, size_t(lidx), tmp, cf);
@@ -132,9 +138,50 @@ static int run_particles(int argc, char** argv) {
 }
 #endif
 
+#if !defined(USE_MPI)
+// The interpolation building blocks of the PLT gradient and of glass loads, from the reference's own headers:
+//   ref_driver cic <n> <boxlen> <phi_k.bin> <points.bin> <npts> <out.bin>
+// points: npts x 3 doubles in index units.  Per point: Re/Im Grid_FFT::get_cic_kspace (include/grid_fft.hh:347-373; z is
+// clamped into the half-spectrum by the caller), the three components of get_k<real_t>(x,y,z) (:299-313), then - on the
+// backward-transformed field - grid_interpolate<1>::get_cic_at (include/grid_interpolate.hh:103-148) and
+// compensation_kernel(get_k(floor(x),floor(y),floor(z))) (:195-208): 7 doubles.
+static int run_cic(int argc, char** argv) {
+    if (argc < 8) return 1;
+    const size_t n = std::strtoul(argv[2], nullptr, 10);
+    const real_t L = std::atof(argv[3]);
+    const size_t npts = std::strtoul(argv[6], nullptr, 10);
+    grid_t phi({n, n, n}, {L, L, L});
+    if (!load_k(phi, argv[4])) return 2;
+    std::vector<double> pts(3 * npts), out(7 * npts);
+    { FILE* f = std::fopen(argv[5], "rb"); if (!f || std::fread(pts.data(), 8, pts.size(), f) != pts.size()) return 2; std::fclose(f); }
+    for (size_t p = 0; p < npts; ++p) {
+        const real_t x = pts[3 * p], y = pts[3 * p + 1], z = pts[3 * p + 2];
+        const real_t zk = z * real_t(n / 2) / real_t(n);   // into [0, n/2)
+        const ccomplex_t c = phi.get_cic_kspace({x, y, zk});
+        const auto kv = phi.get_k<real_t>(x, y, zk);
+        out[7 * p] = std::real(c); out[7 * p + 1] = std::imag(c);
+        out[7 * p + 2] = kv[0]; out[7 * p + 3] = kv[1]; out[7 * p + 4] = kv[2];
+    }
+    phi.FourierTransformBackward();
+    grid_interpolate<1, grid_t> interp(phi);
+    for (size_t p = 0; p < npts; ++p) {
+        const real_t x = pts[3 * p], y = pts[3 * p + 1], z = pts[3 * p + 2];
+        out[7 * p + 5] = interp.get_cic_at({x, y, z});
+        out[7 * p + 6] = std::real(interp.compensation_kernel(phi.get_k<real_t>(size_t(x), size_t(y), size_t(z) % (n / 2 + 1))));
+    }
+    FILE* f = std::fopen(argv[7], "wb");
+    std::fwrite(out.data(), 8, out.size(), f);
+    std::fclose(f);
+    std::printf("ref_driver cic ok\n");
+    return 0;
+}
+#endif
+
 int main(int argc, char** argv) {
 #if defined(USE_MPI)
     if (argc > 1 && std::string(argv[1]) == "particles") return run_particles(argc, argv);
+#else
+    if (argc > 1 && std::string(argv[1]) == "cic") return run_cic(argc, argv);
 #endif
     if (argc < 7) { std::printf("usage: ref_driver n boxlen Dplus0 phi_k.bin psi_k.bin outdir\n"); return 1; }
     const size_t n = std::strtoul(argv[1], nullptr, 10);

@@ -84,7 +84,7 @@ def run_reference(phi, psi, n=N, extra=None, mpi=False):
     return out
 
 
-def run_reference_particles(phi, psi, lattice_type, lattice_index, zero_field=False, n=N):
+def run_reference_particles(phi, psi, lattice_type, lattice_index, zero_field=False, n=N, do_baryons=None, mask_type=3):
     """the reference's particle::lattice_generator (MPI build, one rank): positions from phi, velocities from psi, masses
     from phi (munit 2.5), 64-bit reals and ids, IDoffset = lattice_index.  -> dict(pos, vel, mass, ids)"""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_mpi")
@@ -92,7 +92,9 @@ def run_reference_particles(phi, psi, lattice_type, lattice_index, zero_field=Fa
         np.ascontiguousarray(phi, np.complex128).tofile(os.path.join(d, "phi.bin"))
         np.ascontiguousarray(psi, np.complex128).tofile(os.path.join(d, "psi.bin"))
         r = subprocess.run([exe, "particles", str(n), repr(L), os.path.join(d, "phi.bin"), os.path.join(d, "psi.bin"), d,
-                            str(lattice_type), str(lattice_index), "1" if zero_field else "0"], capture_output=True, text=True)
+                            str(lattice_type), str(lattice_index), "1" if zero_field else "0"] +
+                           ([("yes" if do_baryons else "no"), str(mask_type)] if do_baryons is not None else []),
+                           capture_output=True, text=True)
         assert r.returncode == 0 and "particles ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
         raw = np.fromfile(os.path.join(d, "particles.bin"), np.uint8)
     npart = int(raw[:8].view(np.uint64)[0])
@@ -101,6 +103,53 @@ def run_reference_particles(phi, psi, lattice_type, lattice_index, zero_field=Fa
             "vel": b[24 * npart:48 * npart].view(np.float64).reshape(npart, 3).copy(),
             "mass": b[48 * npart:56 * npart].view(np.float64).copy(),
             "ids": b[56 * npart:64 * npart].view(np.uint64).copy()}
+
+
+def run_reference_cic(phi, points, n=N):
+    """the interpolation building blocks of the PLT gradient and of glass loads from the reference's own headers (non-MPI
+    build): per point (index units) [Re, Im get_cic_kspace(x, y, z/2), get_k<real_t>(x, y, z/2) x3, get_cic_at(x, y, z) on the
+    backward-transformed field, compensation_kernel(get_k(floor x, floor y, floor z % (n/2+1)))]"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    with tempfile.TemporaryDirectory() as d:
+        np.ascontiguousarray(phi, np.complex128).tofile(os.path.join(d, "phi.bin"))
+        np.ascontiguousarray(points, np.float64).tofile(os.path.join(d, "pts.bin"))
+        r = subprocess.run([exe, "cic", str(n), repr(L), os.path.join(d, "phi.bin"), os.path.join(d, "pts.bin"), str(len(points)),
+                            os.path.join(d, "out.bin")], capture_output=True, text=True)
+        assert r.returncode == 0 and "cic ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        return np.fromfile(os.path.join(d, "out.bin"), np.float64).reshape(len(points), 7)
+
+
+MASKED_CASES = ((True, 3, 0), (True, 3, 1), (True, 1, 0), (True, 2, 1), (False, 3, 0))
+
+
+def cic_points(n=N, npts=400, seed=5):
+    rng = np.random.default_rng(seed)
+    pts = rng.random((npts, 3)) * n
+    pts[0] = (n - 0.25, n - 0.5, n - 0.125)     # wraps on every axis
+    pts[1] = (0.0, 0.0, 0.0)
+    pts[2] = (n / 2 + 0.5, n / 2, n / 2 - 0.5)  # around the Nyquist index
+    return pts
+
+
+def main_f4():
+    """tests/golden/ref_f4_32.npz: SURVEY 8 f-4 quantities from the reference's own code - the masked sc lattice of
+    particle::lattice_generator (MPI build, one rank) and the CIC building blocks of the PLT gradient / glass loads"""
+    import hashlib
+    g, phi, psi = inputs()
+    out = {"meta": np.array([N, L])}
+    for do_b, mt, li in MASKED_CASES:
+        P = run_reference_particles(phi, psi, -2, li, do_baryons=do_b, mask_type=mt)
+        key = f"masked_{int(do_b)}{mt}{li}"
+        out[key + "_np"] = np.array([len(P["ids"])])
+        out[key + "_ids_sha256"] = np.frombuffer(hashlib.sha256(P["ids"].tobytes()).digest(), np.uint8)
+        for k in ("pos", "vel", "mass"):
+            out[f"{key}_{k}_sub"] = P[k][::37].copy()
+    pts = cic_points()
+    out["cic_points"] = pts
+    out["cic_out"] = run_reference_cic(phi, pts)
+    path = os.path.join(HERE, "ref_f4_32.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KB,", len(out), "arrays")
 
 
 def main():
@@ -140,4 +189,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "f4":
+        main_f4()
+    else:
+        main()

@@ -367,6 +367,45 @@ def check_reference_particles(M):
             assert relerr(got["mass"][::101], R[f"part_{nm}{li}_mass_sub"]) < 1e-12, (nm, li)
 
 
+def check_reference_f4(M):
+    """SURVEY 8 f-4 against the reference's OWN code (tests/golden/ref_f4_32.npz, made by make_ref_fixtures.py f4): the
+    masked sc lattice of particle::lattice_generator - ids bit-exact, positions / velocities / masses - and the CIC read-out
+    of a glass load against grid_interpolate::get_cic_at"""
+    import hashlib
+    import os
+
+    R0 = load_reference_fixture()
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_f4_32.npz"))
+    n, L = int(R["meta"][0]), float(R["meta"][1])
+    F = M.Grid_FFT((n,) * 3, (L,) * 3)
+    for do_b, mt, li in ((True, 3, 0), (True, 3, 1), (True, 1, 0), (True, 2, 1), (False, 3, 0)):
+        key = f"masked_{int(do_b)}{mt}{li}"
+        parts = M.Particles("masked", li, True, True, True, li, F, mask=M.particle_type_mask(do_b, mt))
+        assert parts.get_local_num_particles() == int(R[key + "_np"][0])
+        for d in range(3):
+            F.set_kspace(R0["phi_in"])
+            F.FourierTransformBackward()
+            parts.set_positions(d, L, F)
+            F.set_kspace(R0["psi_in"])
+            F.FourierTransformBackward()
+            parts.set_velocities(d, F)
+        F.set_kspace(R0["phi_in"])
+        F.FourierTransformBackward()
+        parts.set_masses(2.5, F)
+        got = parts.download()
+        assert hashlib.sha256(got["ids"].tobytes()).digest() == R[key + "_ids_sha256"].tobytes(), key
+        assert np.abs(got["pos"][::37] - R[key + "_pos_sub"]).max() < 1e-12 * L, key
+        assert relerr(got["vel"][::37], R[key + "_vel_sub"]) < 1e-12, key
+        assert relerr(got["mass"][::37], R[key + "_mass_sub"]) < 1e-12, key
+    pts = R["cic_points"]
+    parts = M.Particles("glass", 0, True, True, False, 0, F, glass=(pts, 0))
+    F.set_kspace(R0["phi_in"])
+    F.FourierTransformBackward()
+    parts.set_velocities(1, F)
+    got = parts.download(pos=False)
+    assert np.abs(got["vel"][:, 1] - R["cic_out"][:, 5]).max() < 1e-12 * np.abs(R["cic_out"][:, 5]).max()
+
+
 # ------------------------------------------------------------------ two-fluid terms, tides, density, masses
 def check_two_fluid_terms(M, n=32, lattice="bcc"):
     """the operators a CDM+baryon run adds (config C4) with NON-degenerate two-fluid amplitudes (the goldens use
@@ -425,6 +464,130 @@ def check_two_fluid_terms(M, n=32, lattice="bcc"):
     ref_m = O.set_masses(g, mass_field, lt, 1, 1.0, True)
     assert np.abs(got["mass"] - ref_m).max() < 1e-12 * np.abs(ref_m).max()
     assert np.array_equal(got["ids"], O.particle_ids(n, lt, 1, True))
+
+
+# ------------------------------------------------------------------ PLT gradient, masked lattice, glass load
+def check_plt_masked_glass(M, n=32, order=3):
+    """(1) particle::lattice_gradient in place of op::fourier_gradient (include/particle_plt.hh:551-585, src/ic_generator.cc:
+    377-381, 855-858, 911-929): component fields built with the table-driven gradient and the growth-rate correction;
+    (2) the masked sc lattice (include/particle_generator.hh:171-260, 351-398, 479-497, 557-571) for every ParticleMaskType and
+    both species; (3) a glass load (:262-290, 498-515, 573-590): CIC read-out at arbitrary positions, component fields with
+    the CIC compensation kernel (include/grid_interpolate.hh:195-208)."""
+    L, Dp, vfac = 100.0, 0.0257, 396.69
+    lunit, vunit = L, L / np.sqrt(1 / 51.0)
+    g, W, Wc, phi = noise_and_phi(n, L, 31)
+    amp = O.power_law_amplitude()
+    pots = O.lpt_potentials(g, phi, order, Dp)
+    tab = O.radial_table(g, amp)
+    rng = np.random.default_rng(12)
+    # ---- (1) PLT: smooth, non-trivial helper-mesh tables (the real ones come from the host's eigen-decomposition)
+    ng = 16
+    kk = np.fft.fftfreq(ng)[:, None, None] ** 2 + np.fft.fftfreq(ng)[None, :, None] ** 2 + np.fft.rfftfreq(ng)[None, None, :] ** 2
+    tabs = [1.0 - 0.8 * kk + 0.05 * rng.standard_normal(kk.shape), 0.3 * kk + 0.02 * rng.standard_normal(kk.shape),
+            -0.2 * kk + 0.02 * rng.standard_normal(kk.shape), 1.0 + 0.4 * kk + 0.03 * rng.standard_normal(kk.shape)]
+    olg = O.PLTGradient(ng, n, L, *tabs)
+    cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad="sc", Dplus0=Dp, vfac=vfac, lunit=lunit, vunit=vunit)
+    pl = M.LPTPipeline(cfg)
+    pl.set_noise_k(W)
+    pl.condition_noise()
+    pl.compute_phi1(tab)
+    pl.compute_sources()
+    plain = [pl.displacement_field(d).get_real() for d in range(3)]
+    pl.lg = M.lattice_gradient(ng, n, L, *tabs)
+    for d in range(3):
+        ref = g.bwd(O.displacement_k(g, pots, order, d, lunit / L, lg=olg))
+        got = pl.displacement_field(d).get_real()
+        assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max(), d
+        assert np.abs(got - plain[d]).max() > 1e-3 * np.abs(ref).max()      # the tables matter
+        ref = g.bwd(O.velocity_k(g, pots, order, d, vfac, vunit / L, lg=olg))
+        got = pl.velocity_field(d).get_real()
+        assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max(), d
+    # identity tables reproduce the Fourier gradient away from the Nyquist planes... only where the helper mesh resolves the
+    # mode exactly (ng == n): D_r = 1, D_theta = D_phi = 0, mu = 1  ->  i k_d, except that get_k keeps the Nyquist sign
+    one, zero = np.ones((n, n, n // 2 + 1)), np.zeros((n, n, n // 2 + 1))
+    pl.lg = M.lattice_gradient(n, n, L, one, zero, zero, one)
+    olg1 = O.PLTGradient(n, n, L, one, zero, zero, one)
+    Gp, vc = olg1.all(g)
+    kx, ky, kz = np.broadcast_arrays(*g.kvec())
+    for d, kd in enumerate((kx, ky, kz)):
+        assert np.abs(Gp[d] - kd).max() < 1e-12 * np.abs(kd).max()
+    ref = g.bwd(O.displacement_k(g, pots, order, 0, lunit / L, lg=olg1))
+    assert np.abs(pl.displacement_field(0).get_real() - ref).max() < 1e-11 * np.abs(ref).max()
+    pl.lg = None
+    with pytest_raises(ValueError):
+        M.lattice_gradient(ng, n, L, tabs[0][:4], tabs[1], tabs[2], tabs[3])
+    # ---- (2) masked lattice
+    psi = [g.bwd(O.displacement_k(g, pots, order, d, lunit / L)) for d in range(3)]
+    vel = [g.bwd(O.velocity_k(g, pots, order, d, vfac, vunit / L)) for d in range(3)]
+    rho = 1.0 + 0.1 * rng.standard_normal((n, n, n))
+    F = M.Grid_FFT((n,) * 3, (L,) * 3)
+    for do_b, mtype in ((True, 3), (True, 1), (True, 2), (True, 0), (False, 3)):
+        mask = O.particle_type_mask(do_b, mtype)
+        assert mask == M.particle_type_mask(do_b, mtype)
+        for lidx in ((0, 1) if do_b else (0,)):
+            for r64 in (True, False):
+                P = M.Particles("masked", lidx, r64, True, True, lidx, F, mask=mask)
+                assert P.get_local_num_particles() == int(np.sum(np.asarray(mask) == lidx)) * n ** 3 // 8
+                for d in range(3):
+                    F.set_real(psi[d])
+                    P.set_positions(d, lunit, F)
+                    F.set_real(vel[d])
+                    P.set_velocities(d, F)
+                F.set_real(rho)
+                P.set_masses(2.5, F)
+                got = P.download()
+                assert np.array_equal(got["ids"], O.masked_ids(n, mask, lidx, lidx, True))
+                tol = 1e-13 if r64 else 1e-6
+                for d in range(3):
+                    ref = O.masked_positions(g, psi[d], d, mask, lidx, lunit, r64)
+                    assert np.abs(got["pos"][:, d].astype(np.float64) - ref).max() <= tol * lunit
+                    ref = O.masked_velocities(g, vel[d], mask, lidx, r64)
+                    if r64:
+                        assert np.array_equal(got["vel"][:, d], ref)
+                    else:
+                        assert np.abs(got["vel"][:, d].astype(np.float64) - ref).max() <= tol * np.abs(ref).max()
+                ref = O.masked_masses(g, rho, mask, lidx, 2.5, r64)
+                assert np.abs(got["mass"].astype(np.float64) - ref).max() <= (1e-13 if r64 else 1e-6) * np.abs(ref).max()
+    with pytest_raises(Exception):
+        M.Particles("masked", 1, True, True, False, 0, F, mask=[0] * 8)     # no cell carries species 1
+    # through the pipeline: ParticleLoad = masked, CDM species of a two-species mask
+    cfgm = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad="masked", Dplus0=Dp, vfac=vfac, lunit=lunit, vunit=vunit,
+                        DoBaryons=True, ParticleMaskType=3, ids64=True)
+    plm = M.LPTPipeline(cfgm)
+    plm.set_noise_k(W)
+    plm.condition_noise()
+    host = plm.run_device(tab).download()
+    mask = O.particle_type_mask(True, 3)
+    assert np.array_equal(host["ids"], O.masked_ids(n, mask, 0, 0, True))
+    for d in range(3):
+        ref = O.masked_positions(g, psi[d], d, mask, 0, lunit, True)
+        assert np.abs(host["pos"][:, d] - ref).max() < 1e-11 * lunit
+    # ---- (3) glass load
+    npart = 3 * n * n + 17
+    posr = rng.random((npart, 3)) * n
+    posr[0] = (n - 0.25, n - 0.5, n - 1e-9)        # wraps on every axis
+    posr[1] = (0.0, 0.0, 0.0)
+    cfgg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad="glass", Dplus0=Dp, vfac=vfac, lunit=lunit, vunit=vunit,
+                        glass=(posr, 1000), ids64=True)
+    plg = M.LPTPipeline(cfgg)
+    plg.set_noise_k(W)
+    plg.condition_noise()
+    host = plg.run_device(tab).download()
+    assert np.array_equal(host["ids"], (7 * 0 + 1000 + np.arange(npart)).astype(np.uint64))
+    for d in range(3):
+        fr = g.bwd(O.displacement_k(g, pots, order, d, lunit / L, glass=True))
+        ref = O.glass_positions(g, fr, d, posr, lunit)
+        assert np.abs(host["pos"][:, d] - ref).max() < 1e-11 * lunit, d
+        fv = g.bwd(O.velocity_k(g, pots, order, d, vfac, vunit / L, glass=True))
+        ref = O.glass_velocities(g, fv, posr)
+        assert np.abs(host["vel"][:, d] - ref).max() < 1e-11 * np.abs(ref).max(), d
+    # the compensation kernel undoes the CIC window: particles ON the lattice get the uncompensated field back only up to the
+    # window, so just check that it was applied
+    assert np.abs(g.bwd(O.displacement_k(g, pots, order, 0, lunit / L, glass=True)) - psi[0]).max() > 1e-3 * np.abs(psi[0]).max()
+    with pytest_raises(Exception):
+        M.Particles("glass", 0, True, True, True, 0, F, glass=(posr, 0))    # no per-particle masses for glasses
+    with pytest_raises(Exception):
+        M.Particles("glass", 0, True, True, False, 0, F, glass=(posr + n, 0))   # positions must be in grid units
 
 
 # ------------------------------------------------------------------ complex grids + PPT / Eulerian branch

@@ -123,3 +123,11 @@ def test_against_reference_produced_fixture(M):
 
 def test_particles_against_reference_produced_fixture(M):
     PC.check_reference_particles(M)
+
+
+def test_plt_masked_glass(M):
+    PC.check_plt_masked_glass(M, 32, 3)
+
+
+def test_f4_against_reference_produced_fixture(M):
+    PC.check_reference_f4(M)

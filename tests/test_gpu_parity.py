@@ -73,6 +73,15 @@ def test_two_fluid_terms(M, n, lattice):
     PC.check_two_fluid_terms(M, n, lattice)
 
 
+@pytest.mark.parametrize("n,order", [(32, 3), (96, 2)])
+def test_plt_masked_glass(M, n, order):
+    PC.check_plt_masked_glass(M, n, order)
+
+
+def test_f4_against_reference_produced_fixture(M):
+    PC.check_reference_f4(M)
+
+
 def test_against_reference_produced_fixture(M):
     PC.check_reference_fixture(M)
 

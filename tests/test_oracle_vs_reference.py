@@ -109,6 +109,77 @@ def test_oracle_particles_match_committed_reference_fixture():
             assert rel(P["mass"][::101], R[f"part_{nm}{li}_mass_sub"]) < TOL
 
 
+def oracle_masked(g, phi, psi, do_b, mt, li):
+    x, v = g.bwd(phi), g.bwd(psi)
+    mask = O.particle_type_mask(do_b, mt)
+    return {"ids": O.masked_ids(g.n, mask, li, li, True),
+            "pos": np.stack([O.masked_positions(g, x, d, mask, li, g.L, True) for d in range(3)], 1),
+            "vel": np.stack([O.masked_velocities(g, v, mask, li, True) for d in range(3)], 1),
+            "mass": O.masked_masses(g, x, mask, li, 2.5, True)}
+
+
+def compare_cic(g, phi, pts, out):
+    """oracle restatements of Grid_FFT::get_cic_kspace, get_k<real_t>, grid_interpolate::get_cic_at and compensation_kernel
+    against what the reference's own headers return (tests/golden/make_ref_fixtures.py::run_reference_cic)"""
+    n = g.n
+    lgr = O.PLTGradient(n, n, g.L, phi.real, phi.real, phi.real, phi.imag)      # any tables: cic_kspace is linear in them
+    x, y, zk = pts[:, 0], pts[:, 1], pts[:, 2] * float(n // 2) / float(n)
+    assert np.abs(lgr.cic_kspace(phi.real, x, y, zk) - out[:, 0]).max() < 1e-13 * np.abs(out[:, 0]).max()
+    assert np.abs(lgr.cic_kspace(phi.imag, x, y, zk) - out[:, 1]).max() < 1e-13 * np.abs(out[:, 1]).max()
+    h = float(n // 2)
+    for c, w in enumerate((x, y, zk)):
+        assert np.abs((w - (w > h) * n) * g.kfac - out[:, 2 + c]).max() < 1e-13 * np.abs(out[:, 2 + c]).max()
+    fr = g.bwd(phi)
+    assert np.abs(O.cic_at(fr, pts) - out[:, 5]).max() < 1e-13 * np.abs(fr).max()
+    comp = O.cic_compensation_kernel(g)
+    i, j, k = (pts[:, c].astype(int) for c in range(3))
+    k = k % (n // 2 + 1)
+    assert np.abs(np.broadcast_to(comp, (n, n, n // 2 + 1))[i, j, k] - out[:, 6]).max() < 1e-13 * np.abs(out[:, 6]).max()
+
+
+def test_oracle_f4_matches_committed_reference_fixture():
+    """SURVEY 8 f-4: the masked sc lattice of the reference's particle::lattice_generator (ids bit-exact, positions /
+    velocities / masses with get_mean_mask_value) and the CIC building blocks of the PLT gradient and of glass loads"""
+    import hashlib
+    import make_ref_fixtures as F
+
+    R = np.load(os.path.join(ROOT, "tests", "golden", "ref_f4_32.npz"))
+    M0 = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
+    n, L = int(R["meta"][0]), float(R["meta"][1])
+    g = O.GridSpec(n, L)
+    for do_b, mt, li in F.MASKED_CASES:
+        key = f"masked_{int(do_b)}{mt}{li}"
+        Q = oracle_masked(g, M0["phi_in"], M0["psi_in"], do_b, mt, li)
+        assert len(Q["ids"]) == int(R[key + "_np"][0])
+        assert hashlib.sha256(Q["ids"].tobytes()).digest() == R[key + "_ids_sha256"].tobytes()
+        assert np.abs(Q["pos"][::37] - R[key + "_pos_sub"]).max() < 1e-13 * L
+        assert rel(Q["vel"][::37], R[key + "_vel_sub"]) < TOL
+        assert rel(Q["mass"][::37], R[key + "_mass_sub"]) < TOL
+    compare_cic(g, M0["phi_in"], R["cic_points"], R["cic_out"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include") or shutil.which("g++") is None,
+                    reason="the reference sources are only mounted in the build container")
+def test_oracle_f4_matches_reference_built_here():
+    import make_ref_fixtures as F
+
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    n = 16
+    g = O.GridSpec(n, F.L)
+    amp = O.power_law_amplitude(ns=0.93, kcut=0.8)
+    phi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 17, True)), amp)
+    psi = O.phi1_from_noise(g, O.condition_noise(g, O.make_white_noise_k(n, 18, True)), amp)
+    for do_b, mt, li in ((True, 3, 1), (True, 0, 0), (False, 3, 0)):
+        P = F.run_reference_particles(phi, psi, -2, li, n=n, do_baryons=do_b, mask_type=mt)
+        Q = oracle_masked(g, phi, psi, do_b, mt, li)
+        assert np.array_equal(P["ids"], Q["ids"])
+        assert np.abs(P["pos"] - Q["pos"]).max() < 1e-13 * F.L
+        assert rel(Q["vel"], P["vel"]) < TOL and rel(Q["mass"], P["mass"]) < TOL
+    pts = F.cic_points(n, 200, 9)
+    compare_cic(g, phi, pts, F.run_reference_cic(phi, pts, n))
+
+
 def test_oracle_matches_committed_reference_fixture():
     R = np.load(os.path.join(ROOT, "tests", "golden", "ref_intermediates_32.npz"))
     compare(R, R["phi_in"], R["psi_in"], int(R["meta"][0]), float(R["meta"][1]), float(R["meta"][2]))

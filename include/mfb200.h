@@ -101,6 +101,13 @@ int mfb_grid_upload(mfb_grid* g, const double* host);
    field (pinned host memory, raw layout) into `g` on an ingest stream, ordered after all work queued so far; the compute
    stream continues with work that does not touch `g`.  mfb_grid_stream_in_wait makes the compute stream - not the host -
    wait for the copy before `g` is used again.  Replaces the blocking Fill_Grid -> device copy of a series of runs. */
+/* Device noise fill in the NGenIC layout (RNG_ngenic::Fill_Grid, src/plugins/random_ngenic.cc:84-154): `g`
+   becomes white noise in k-space, unit variance per complex mode, DC and every index-N/2 mode zero, Hermitian k_z = 0 plane
+   by the plugin's mirror rule.  Generator: Philox4x32-10 keyed with `seed`, counter = (column, k_z) with the column taken
+   from the plugin's ring-ordered seed table, so a larger grid draws the same low-k columns.  NOT gsl ranlxd1: bit-exact
+   NGenIC phases stay with the host plugin (GSL is not available offline); this entry point is for runs that only need
+   reproducible Gaussian noise, and removes the host fill + H2D copy from them.  Slabs: every rank fills its own k-slab. */
+int mfb_noise_fill_ngenic(mfb_grid* g, unsigned long long seed);
 int mfb_grid_stream_in(mfb_grid* g, const double* host);
 int mfb_grid_stream_in_wait(mfb_grid* g);
 int mfb_grid_download(const mfb_grid* g, double* host);

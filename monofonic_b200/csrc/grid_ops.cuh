@@ -470,6 +470,48 @@ __global__ void __launch_bounds__(EW_THREADS) lattice_readout_kernel(real_out* _
     }
 }
 
+// ---------------------------------------------------------------- device noise fill, NGenIC layout
+// RNG_ngenic::Fill_Grid (src/plugins/random_ngenic.cc:84-154) with a counter-based generator: every mode is computed on its
+// own, so the fill is one streaming write of the grid instead of N^2 sequential column streams + an H2D copy.
+MFB_D void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned n0 = unsigned(p1 >> 32) ^ c1 ^ k0, n1 = unsigned(p1), n2 = unsigned(p0 >> 32) ^ c3 ^ k1, n3 = unsigned(p0);
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// column word: position in the plugin's ring-ordered seed table (:47-74): i < N/2 as it is, else N-1-i with the top bit set
+MFB_D unsigned ngenic_word(int i, int n) { return i < n / 2 ? unsigned(i) : (unsigned(n - 1 - i) | 0x80000000u); }
+MFB_D double2 ngenic_draw(int a, int b, int k, int n, unsigned long long seed) {
+    unsigned x[4];
+    philox4x32_10(ngenic_word(a, n), ngenic_word(b, n), unsigned(k), 0u, unsigned(seed), unsigned(seed >> 32), x);
+    const double u1 = (double((((unsigned long long)x[0]) << 20) | (x[1] >> 12)) + 0.5) * 2.220446049250313e-16;   // 2^-52
+    const double u2 = (double((((unsigned long long)x[2]) << 20) | (x[3] >> 12)) + 0.5) * 2.220446049250313e-16;
+    const double amp = sqrt(-log(u2));
+    double sn, cs;
+    sincos(6.283185307179586476925286766559 * u1, &sn, &cs);   // the reference takes cos / sin of 2 pi u (:120-121)
+    return make_double2(amp * cs, amp * sn);
+}
+__global__ void __launch_bounds__(EW_THREADS) ngenic_fill_kernel(double2* __restrict__ w, KGeom g, unsigned long long seed) {
+    MFB_K_LOOP_BEGIN(g)
+        const int n = g.n0, h = n / 2;
+        double2 z = make_double2(0.0, 0.0);
+        if (!(i == h || j == h || k == h || is_dc)) {       // :117-118
+            if (k > 0) {
+                z = ngenic_draw(i, j, k, n, seed);
+            } else {                                         // Hermitian k_z = 0 plane (:125-148)
+                const bool primary = (i == 0 && j < h) || (i > 0 && i < h);
+                z = primary ? ngenic_draw(i, j, 0, n, seed) : ngenic_draw((n - i) % n, (n - j) % n, 0, n, seed);
+                if (!primary) z.y = -z.y;
+            }
+        }
+        w[idx] = z;
+    }
+}
+
 // ---------------------------------------------------------------- masked sc lattice (include/particle_generator.hh:171-260)
 // A 2x2x2 mask assigns every cell of the N^3 lattice to a species (or to nobody); a species' particles are the cells of its
 // type in (i,j,k) order.  The mask is periodic, so the running particle count of the reference's loops has a closed form.

@@ -1710,6 +1710,15 @@ int mfb_lpt_assemble_lg(mfb_grid* out, int d, const mfb_grid* phi, const mfb_gri
     check_launch("assemble");
     MFB_CATCH
 }
+int mfb_noise_fill_ngenic(mfb_grid* g, unsigned long long seed) {
+    MFB_TRY
+    require(g->n[0] == g->n[1] && g->n[1] == g->n[2], "the NGenIC layout needs a cubic grid");
+    g->space = MFB_KSPACE;   // Fill_Grid declares the grid k-space without transforming (:86-87)
+    KGeom k = kgeom(g);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ngenic_fill_kernel, kgrid_blocks(k), EW_THREADS, reinterpret_cast<double2*>(g->d), k, seed);
+    check_launch("ngenic_fill");
+    MFB_CATCH
+}
 int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi) {
     MFB_TRY
     require(phi->space == MFB_KSPACE, "density_from_phi: phi must be in k-space");

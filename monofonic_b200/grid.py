@@ -152,6 +152,10 @@ class Grid_FFT:
         assert buf.size == self.ntot_, (buf.size, self.ntot_)
         L.check(self._lib.mfb_grid_upload(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)
 
+    def fill_noise_ngenic_layout(self, seed: int):
+        """white noise in k-space with the layout of RNG_ngenic::Fill_Grid, generated on the device (Philox4x32-10)"""
+        L.check(self._lib.mfb_noise_fill_ngenic(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), self._lib)
+
     def stream_in(self, buf: np.ndarray):
         """asynchronous upload_raw on the ingest stream (`buf` should be pinned and must stay alive and unchanged until the
         copy has run); the compute stream continues with work that does not touch this grid.  Pair with stream_in_wait()."""

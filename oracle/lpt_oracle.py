@@ -795,6 +795,59 @@ def run_pipeline(n, boxlen, W, amplitude, order, Dplus0, vfac, lattice="sc", lun
 # --------------------------------------------------------------------------------------
 # Synthetic inputs shared by tests / bench (NGenIC-like Hermitian white noise)
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# Device noise fill in the NGenIC layout (src/plugins/random_ngenic.cc:84-154)
+# --------------------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1, _PHILOX_W0, _PHILOX_W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011, Random123): counter words c0..c3 (uint arrays), key (k0, k1) -> four uint32 words.
+    Known answers (Random123 kat_vectors): zero counter and key -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8."""
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0 & 0xffffffff), np.uint64(k1 & 0xffffffff)
+    m32, s32 = np.uint64(0xffffffff), np.uint64(32)
+    for _ in range(10):
+        p0, p1 = np.uint64(_PHILOX_M0) * c0, np.uint64(_PHILOX_M1) * c2
+        c0, c1, c2, c3 = ((p1 >> s32) ^ c1 ^ k0) & m32, p1 & m32, ((p0 >> s32) ^ c3 ^ k1) & m32, p0 & m32
+        k0, k1 = (k0 + np.uint64(_PHILOX_W0)) & m32, (k1 + np.uint64(_PHILOX_W1)) & m32
+    return c0, c1, c2, c3
+
+
+def ngenic_layout_noise(n, seed):
+    """White noise in k-space with the layout rules of RNG_ngenic::Fill_Grid (src/plugins/random_ngenic.cc:84-154): one
+    independent stream per (k_x, k_y) column, per k_z a phase 2 pi u1 and an amplitude sqrt(-ln u2), unit variance per complex
+    mode; DC and every mode with an index N/2 stay zero (:117-118); the k_z = 0 plane is Hermitian: columns with 0 < k_x index
+    < N/2, and k_x = 0 with k_y index < N/2, are drawn, their mirrors (N-k_x, N-k_y) get the conjugate (:125-148).
+    The generator is NOT the plugin's gsl ranlxd1 (GSL is not available; bit-exact NGenIC phases stay with the host plugin):
+    Philox4x32-10 keyed with the 64-bit seed, counter = (column word a, column word b, k_z, 0).  The column words are taken
+    from the position of the column in the plugin's ring-ordered seed table (:47-74) - index i < N/2 as it is, i >= N/2 as
+    N-1-i with the top bit set - so that, like there, a larger grid draws the same low-k columns."""
+    h, nzc = n // 2, n // 2 + 1
+    idx = np.arange(n, dtype=np.uint64)
+    word = np.where(idx < h, idx, (np.uint64(n - 1) - idx) | np.uint64(0x80000000))
+
+    def draw(a, b, k):
+        x0, x1, x2, x3 = philox4x32_10(word[a], word[b], k, np.zeros_like(k), seed & 0xffffffff, (seed >> 32) & 0xffffffff)
+        u1 = (((x0 << np.uint64(20)) | (x1 >> np.uint64(12))).astype(np.float64) + 0.5) * 2.0 ** -52
+        u2 = (((x2 << np.uint64(20)) | (x3 >> np.uint64(12))).astype(np.float64) + 0.5) * 2.0 ** -52
+        amp = np.sqrt(-np.log(u2))
+        return amp * (np.cos(2.0 * np.pi * u1) + 1j * np.sin(2.0 * np.pi * u1))
+    A, B, K = np.meshgrid(np.arange(n), np.arange(n), np.arange(nzc), indexing="ij")
+    W = draw(A, B, K.astype(np.uint64))
+    # k_z = 0 plane: mirrors take the conjugate of their primary column
+    a, b = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    primary = ((a == 0) & (b < h)) | ((a > 0) & (a < h))
+    ma, mb = (n - a) % n, (n - b) % n
+    z0 = draw(np.where(primary, a, ma), np.where(primary, b, mb), np.zeros((n, n), dtype=np.uint64))
+    W[:, :, 0] = np.where(primary, z0, np.conj(z0))
+    W[h, :, :] = 0.0
+    W[:, h, :] = 0.0
+    W[:, :, h] = 0.0
+    W[0, 0, 0] = 0.0
+    return W
+
+
 def make_white_noise_k(n, seed, nyquist_zero=True):
     """Unit-variance complex Gaussian white noise on the half spectrum [kx][ky][kz] that is the
     transform of a real field.  With nyquist_zero (NGenIC behaviour, random_ngenic.cc:117) all

@@ -466,6 +466,75 @@ def check_two_fluid_terms(M, n=32, lattice="bcc"):
     assert np.array_equal(got["ids"], O.particle_ids(n, lt, 1, True))
 
 
+# ------------------------------------------------------------------ noise ingest and device noise fill
+def check_noise_ingest(M, n=32):
+    """how white noise reaches the device path, the three ways the reference's RNG plugins deliver it:
+    (1) NGenIC: a k-space fill (src/plugins/random_ngenic.cc:84-154) - here generated on the device with the plugin's layout
+        rules and a counter-based generator, against the numpy restatement;
+    (2) MUSIC1: a real-space host fill (src/plugins/random_music.cc:92-116) streamed in on the ingest stream, then r2c;
+    (3) Panphasia-HO: a 2x-oversampled grid with populated Nyquist planes resampled down with FourierInterpolateCopyTo
+        (src/plugins/random_panphasia.cc:136-186, src/grid_fft.cc:273-492).
+    Each ends in a pipeline run that agrees with the oracle fed the same noise."""
+    L, Dp, vfac = 100.0, 0.0257, 396.69
+    g = O.GridSpec(n, L)
+    amp = O.power_law_amplitude()
+    tab = O.radial_table(g, amp)
+    seed = 0x1234567887654321
+
+    def run(pl):
+        pl.condition_noise()
+        return pl.run_device(tab, particles=False)
+
+    def ref_fields(W):
+        pots = O.lpt_potentials(g, O.phi1_from_noise(g, O.condition_noise(g, W), amp), 2, Dp)
+        return O.fields(g, pots, 2, vfac)
+    cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=2, Dplus0=Dp, vfac=vfac)
+    pl = M.LPTPipeline(cfg)
+    # (1) device fill, NGenIC layout
+    Wref = O.ngenic_layout_noise(n, seed)
+    pl.wnoise.fill_noise_ngenic_layout(seed)
+    assert pl.wnoise.space_ == M.kspace_id
+    got = pl.wnoise.get_kspace()
+    assert np.abs(got - Wref).max() < 1e-13, np.abs(got - Wref).max()
+    h = n // 2
+    assert not got[h].any() and not got[:, h].any() and not got[:, :, h].any() and got[0, 0, 0] == 0
+    assert np.abs(got[1:, 1:, 0] - np.conj(got[1:, 1:, 0][::-1, ::-1])).max() == 0.0     # Hermitian k_z = 0 plane, bit for bit
+    inner = got[1:h, 1:h, 1:h]
+    assert abs(np.mean(np.abs(inner) ** 2) - 1.0) < 5.0 / np.sqrt(inner.size)            # unit variance per complex mode
+    pl.wnoise.fill_noise_ngenic_layout(seed + 1)
+    assert np.abs(pl.wnoise.get_kspace() - Wref).max() > 1.0                             # another seed, another field
+    pl.wnoise.fill_noise_ngenic_layout(seed)
+    out, ref = run(pl), ref_fields(Wref)
+    for k in ("dx", "dy", "dz", "vx", "vy", "vz"):
+        assert np.abs(out[k] - ref[k]).max() < 1e-11 * np.abs(ref[k]).max(), k
+    # (2) real-space host fill, streamed in
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal((n, n, n))
+    w = pl.wnoise
+    if w.local_0_size_ == n:
+        raw = np.zeros(w.ntot_)
+        raw.reshape(n, n, n + 2)[:, :, :n] = x
+        w.FourierTransformBackward(False)
+        w.stream_in(raw)
+        w.stream_in_wait()
+        w.FourierTransformForward()
+        assert relerr(w.get_kspace(), g.fwd(x)) < TOL
+        out, ref = run(pl), ref_fields(g.fwd(x))
+        for k in ("dx", "vz"):
+            assert np.abs(out[k] - ref[k]).max() < 1e-11 * np.abs(ref[k]).max(), k
+    # (3) 2x-oversampled k-space noise with populated Nyquist planes, resampled down
+    g2 = O.GridSpec(2 * n, L)
+    W2 = O.make_white_noise_k(2 * n, 77, nyquist_zero=False)
+    big = M.Grid_FFT((2 * n,) * 3, (L,) * 3)
+    big.set_kspace(W2)
+    big.FourierInterpolateCopyTo(pl.wnoise)
+    Wd = O.fourier_interpolate_copy(g2, g, W2)
+    assert relerr(pl.wnoise.get_kspace(), Wd) < TOL
+    out, ref = run(pl), ref_fields(Wd)
+    for k in ("dx", "vz"):
+        assert np.abs(out[k] - ref[k]).max() < 1e-11 * np.abs(ref[k]).max(), k
+
+
 # ------------------------------------------------------------------ SURVEY 8 f-4: PLT gradient, masked lattice, glass load
 def check_plt_masked_glass(M, n=32, order=3):
     """(1) particle::lattice_gradient in place of op::fourier_gradient (include/particle_plt.hh:551-585, src/ic_generator.cc:

@@ -131,3 +131,7 @@ def test_plt_masked_glass(M):
 
 def test_f4_against_reference_produced_fixture(M):
     PC.check_reference_f4(M)
+
+
+def test_noise_ingest(M):
+    PC.check_noise_ingest(M, 32)

@@ -78,6 +78,11 @@ def test_plt_masked_glass(M, n, order):
     PC.check_plt_masked_glass(M, n, order)
 
 
+@pytest.mark.parametrize("n", [32, 128])
+def test_noise_ingest(M, n):
+    PC.check_noise_ingest(M, n)
+
+
 def test_f4_against_reference_produced_fixture(M):
     PC.check_reference_f4(M)
 

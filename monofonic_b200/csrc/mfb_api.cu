@@ -680,6 +680,25 @@ static void naive_backward_operand(mfb_conv* c, const Operand& o, mfb_grid* dst)
     const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2], nzc = N2 / 2 + 1;
     to_kspace(o.g);
     double2* d = reinterpret_cast<double2*>(dst->d);
+    if (o.g->dist) {
+        // slabs: the operand factor rides on the x pass of the transposed layout [ky_loc][kx][kz], whose output is routed to the
+        // ranks owning the x planes; then y and z on the local planes (dist_fft_backward, out of place)
+        const int l0 = dst->nloc0, l1 = o.g->nloc1;
+        Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+        StridedArgs a = plain_strided(reinterpret_cast<const double2*>(o.g->d), nullptr, nzc, ptrdiff_t(N0) * nzc, l1, nzc, N0, 1);
+        set_operand_factor(a, c, o, 1.0);
+        a.pos_axis = 0; a.a_axis = 1;
+        a.a_off = o.g->off1;
+        route(a, x, l0, nzc, ptrdiff_t(l0) * nzc);                         // chunk layout [ky_loc][x_loc][kz]
+        launch_strided(N0, a, ROLE_FFT_X);
+        end_exchange(x);                                                    // recv: [ky][x_loc][kz]
+        StridedArgs b = plain_strided(x.recv, d, ptrdiff_t(l0) * nzc, nzc, l0, nzc, N1, 1);
+        b.out_ps = nzc; b.out_as = ptrdiff_t(N1) * nzc;                     // -> [x_loc][y][kz]
+        launch_strided(N1, b, ROLE_FFT_Y);
+        launch_z(N2, 0, dst->d, dst->pitch, long(l0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
+        dst->space = MFB_RSPACE;
+        return;
+    }
     StridedArgs a = plain_strided(reinterpret_cast<const double2*>(o.g->d), d, ptrdiff_t(N1) * nzc, nzc, N1, nzc, N0, 1);
     set_operand_factor(a, c, o, 1.0);
     a.pos_axis = 0; a.a_axis = 1;
@@ -696,6 +715,22 @@ static void naive_forward_output(mfb_conv* c, mfb_grid* src, mfb_grid* out, int 
     const int N0 = c->n[0], N1 = c->n[1], N2 = c->n[2], nzc = N2 / 2 + 1;
     require(out->space == MFB_KSPACE, "convolution output grid must be in k-space");
     double2* d = reinterpret_cast<double2*>(src->d);
+    if (src->dist) {   // dist_fft_forward with the output operator on the last (x) pass
+        const int l0 = src->nloc0, l1 = out->nloc1;
+        launch_z(N2, 1, src->d, src->pitch, long(l0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
+        Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+        StridedArgs a = plain_strided(d, nullptr, nzc, ptrdiff_t(N1) * nzc, l0, nzc, N1, 0);
+        route(a, x, l1, nzc, ptrdiff_t(l1) * nzc);                         // chunk layout [x_loc][ky_loc][kz]
+        launch_strided(N1, a, ROLE_FFT_Y);
+        end_exchange(x);                                                    // recv: [x][ky_loc][kz]
+        StridedArgs e = plain_strided(x.recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * nzc, nzc, l1, nzc, N0, 0);
+        e.out_ps = nzc; e.out_as = ptrdiff_t(N0) * nzc;                     // -> [ky_loc][kx][kz]
+        e.op = op; e.alpha = alpha;
+        launch_strided(N0, e, ROLE_FFT_X);
+        src->space = MFB_KSPACE;
+        ++c->nconv;
+        return;
+    }
     launch_z(N2, 1, src->d, src->pitch, long(N0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
     launch_strided(N1, plain_strided(d, d, nzc, ptrdiff_t(N1) * nzc, N0, nzc, N1, 0), ROLE_FFT_Y);
     StridedArgs e = plain_strided(d, reinterpret_cast<double2*>(out->d), ptrdiff_t(N1) * nzc, nzc, N1, nzc, N0, 0);
@@ -1877,13 +1912,14 @@ int mfb_conv_create(mfb_conv** out, const int n[3], const double L[3]) {
 int mfb_conv_create_naive(mfb_conv** out, const int n[3], const double L[3]) {
     MFB_TRY
     require(g_ctx.initialised, "mfb_init has not been called");
-    require(!dist_on(), "the NaiveConvolver is only available on a single slab");
+    // slabs: the products run through the exchange buffers of the 3-D FFTs (naive_backward_operand / naive_forward_output)
     mfb_conv* c = new mfb_conv();
     for (int d = 0; d < 3; ++d) {
         c->n[d] = n[d]; c->L[d] = L[d]; c->np[d] = n[d];
         require(supported_size(n[d]), "unsupported grid size for the convolver");
     }
     c->naive = 1;
+    c->dist = dist_on() ? 1 : 0;
     if (mfb_grid_create(&c->nb1, n, L, MFB_KSPACE) || mfb_grid_create(&c->nb2, n, L, MFB_KSPACE)) throw std::runtime_error(g_err);
     *out = c;
     MFB_CATCH

@@ -153,7 +153,15 @@ static int conv_enter_slots(mfb_conv* c, int want_slots, int min_slots, size_t w
     // chunk workspace: what is left of the lent particle memory if it is enough, else an allocation of its own
     const size_t min_chunk = min_chunk_elems * sizeof(double2), want_chunk = want_chunk_elems * sizeof(double2);
     c->chunk_lent = 0;
-    if (lent_left >= min_chunk && (c->dist || lent_left >= want_chunk)) {
+    // where HBM is plentiful (1024^3 on 4-8 GPUs) the chunk workspace is an allocation of its own even if lent memory would
+    // do: a lent chunk makes the whole stage wait for the previous run's particle hand-off
+    bool own_chunk_fits = false;
+    {
+        size_t free_b = 0, total_b = 0;
+        cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+        own_chunk_fits = g_ctx.conv_own_accumulator && free_b > want_chunk + margin + total_b / 8;   // option 0: as if HBM were tight
+    }
+    if (!own_chunk_fits && lent_left >= min_chunk && (c->dist || lent_left >= want_chunk)) {
         c->chunk = (double2*)lent_p; c->chunk_elems = lent_left / sizeof(double2); c->chunk_owned = 0; c->chunk_lent = 1;
     } else {
         size_t free_b = 0, total_b = 0;
@@ -572,7 +580,7 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
     // lent particle arrays: streamed hand-off copies of the previous run must have drained before their memory is written.
     // A lent CHUNK workspace is needed from the first launch on; lent SLOTS wait when they are first taken (S2Runner::take_slot),
     // and the first two stages leave them alone while a copy is pending, so that the hand-off drains under them.
-    if (c->chunk_lent || c->dist) conv_wait_lender(c);
+    if (c->chunk_lent) conv_wait_lender(c);
 
     const double g1 = -Dplus;
     const double g2 = -3.0 / 7.0 * Dplus * Dplus;

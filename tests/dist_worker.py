@@ -108,6 +108,52 @@ def main():
     ref = cv.convolve_Gradient_and_Hessian(phi, 1, psi, (0, 2))
     C.convolve_Gradient_and_Hessian(P, (1,), Q, (0, 2), op.assign_to(out))
     assert PC.relerr(MD.gather_kspace(out), ref) < TOL
+    # ---- the same on the NaiveConvolver (include/convolution.hh:296-426): no padding, Nyquist planes take part
+    nv = O.NaiveConvolver(g)
+    Cn = M.NaiveConvolver(N3, L3)
+    ref = nv.convolve_Hessians(phi, (0, 1), psi, (1, 2))
+    Cn.convolve_Hessians(P, (0, 1), Q, (1, 2), op.assign_to(out))
+    assert PC.relerr(MD.gather_kspace(out), ref) < TOL
+    ref = ref + nv.convolve_SumOfHessians(phi, (0, 0), psi, (1, 1), (2, 2))
+    Cn.convolve_SumOfHessians(P, (0, 0), Q, (1, 1), (2, 2), op.add_to(out))
+    ref = ref + (-5.0 / 7.0) * nv.convolve_Hessians3(phi, (0, 0), psi, (0, 2), phi, (2, 2))
+    Cn.convolve_Hessians(P, (0, 0), Q, (0, 2), P, (2, 2), op.multiply_add_to(out, -5.0 / 7.0))
+    assert PC.relerr(MD.gather_kspace(out), ref) < TOL
+    ref = nv.convolve_Gradients(phi, 0, psi, 2)
+    Cn.convolve_Gradients(P, (0,), Q, (2,), op.assign_to(out))
+    assert PC.relerr(MD.gather_kspace(out), ref) < TOL
+    del Cn
+
+    # ---- device noise fill in the NGenIC layout: every rank fills its own k-slab
+    P.fill_noise_ngenic_layout(4242)
+    assert PC.relerr(MD.gather_kspace(P), O.ngenic_layout_noise(n, 4242)) < 1e-13
+
+    # ---- masked sc lattice on slabs (include/particle_generator.hh:171-260): closed-form particle ranks per slab
+    mask = O.particle_type_mask(True, 3)
+    xr, vr = g.bwd(phi), g.bwd(psi)
+    l0, o0 = n // world, rank * (n // world)
+    for lidx in (0, 1):
+        parts = M.Particles("masked", lidx, True, True, True, lidx, P, mask=mask)
+        for d in range(3):
+            P.set_kspace(phi)
+            P.FourierTransformBackward()
+            parts.set_positions(d, L, P)
+            Q.set_kspace(psi)
+            Q.FourierTransformBackward()
+            parts.set_velocities(d, Q)
+        P.set_kspace(phi)
+        P.FourierTransformBackward()
+        parts.set_masses(2.5, P)
+        host = parts.download()
+        sel = O._mask_select(n, mask, lidx)
+        before, here = int(sel[:o0].sum()), int(sel[o0:o0 + l0].sum())
+        assert len(host["ids"]) == here
+        assert np.array_equal(host["ids"], O.masked_ids(n, mask, lidx, lidx, True)[before:before + here])
+        for d in range(3):
+            assert np.abs(host["pos"][:, d] - O.masked_positions(g, xr, d, mask, lidx, L)[before:before + here]).max() < 1e-12 * L
+            assert PC.relerr(host["vel"][:, d], O.masked_velocities(g, vr, mask, lidx)[before:before + here]) < TOL
+        assert PC.relerr(host["mass"], O.masked_masses(g, xr, mask, lidx, 2.5)[before:before + here]) < TOL
+        del parts
     del P, Q, out, C
 
     # ---- whole pipelines vs the oracle

@@ -73,7 +73,7 @@ def test_two_fluid_terms(M, n, lattice):
     PC.check_two_fluid_terms(M, n, lattice)
 
 
-@pytest.mark.parametrize("n,order", [(32, 3), (96, 2)])
+@pytest.mark.parametrize("n,order", [(32, 3), (64, 2)])
 def test_plt_masked_glass(M, n, order):
     PC.check_plt_masked_glass(M, n, order)
 

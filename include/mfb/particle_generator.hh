@@ -1,12 +1,27 @@
-// include/mfb/particle_generator.hh - particle::container + particle::lattice_generator (Bravais branch)
-// (include/particle_container.hh:30-189, include/particle_generator.hh:129-170, 292-350, 422-467, 520-562).
+// include/mfb/particle_generator.hh - particle::container + particle::lattice_generator: Bravais lattices, the masked sc
+// lattice and glass loads
+// (include/particle_container.hh:30-189, include/particle_generator.hh:129-290, 292-403, 422-515, 520-590).
 // The AoS arrays are filled on the device and copied once into the std::vectors the output plugins read
 // (get_particles()), instead of a serial host triple loop per component.
 #pragma once
 #include <cstdint>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "grid_fft.hh"
+
+namespace mfb_detail {
+// [setup] keys of the masked lattice, read through config_file::get_value_safe when the config type has it (the reference's
+// config_file does; a host that drives the mirror with its own configuration object gets the reference's defaults)
+template <class C, class T, class = void> struct cfg_reader {
+    static T get(C&, const char*, const char*, T dflt) { return dflt; }
+};
+template <class C, class T>
+struct cfg_reader<C, T, decltype(void(std::declval<C&>().get_value_safe(std::string(), std::string(), std::declval<T>())))> {
+    static T get(C& cf, const char* sec, const char* key, T dflt) { return cf.get_value_safe(std::string(sec), std::string(key), dflt); }
+};
+}  // namespace mfb_detail
 
 namespace particle {
 enum lattice { lattice_masked = -2, lattice_glass = -1, lattice_sc = 0, lattice_bcc = 1, lattice_fcc = 2, lattice_rsc = 3 };
@@ -46,13 +61,40 @@ class lattice_generator {
     size_t global_num_particles_ = 0;
 
 public:
+    // the 2x2x2 species mask of a masked lattice from [setup] DoBaryons / ParticleMaskType (include/particle_generator.hh:184-205)
+    static void particle_type_mask(bool do_baryons, unsigned mask_type, int mask[8]) {
+        for (int s = 0; s < 8; ++s) mask[s] = do_baryons ? -1 : 0;
+        if (!do_baryons) return;
+        mask[0] = 0;
+        if (mask_type & 1u) mask[1] = mask[2] = mask[4] = 0;   // edge centres
+        if (mask_type & 2u) mask[3] = mask[5] = mask[6] = 0;   // face centres
+        mask[7] = 1;                                           // baryon at the cell centre
+    }
     template <class config_t>
-    lattice_generator(lattice lattice_type, int /*lattice_index*/, const bool b64reals, const bool b64ids, const bool bwithmasses,
-                      size_t IDoffset, const field_t& field, config_t&)
+    lattice_generator(lattice lattice_type, int lattice_index, const bool b64reals, const bool b64ids, const bool bwithmasses,
+                      size_t IDoffset, const field_t& field, config_t& cf)
         : b64reals_(b64reals), b64ids_(b64ids), bmass_(bwithmasses) {
-        if (lattice_type < 0) throw std::runtime_error("glass / masked particle loads are not on the device path (DESIGN.md section 8)");
         int n[3] = {int(field.n_[0]), int(field.n_[1]), int(field.n_[2])};
-        mfb_detail::check(mfb_particles_create(&p_, n, int(lattice_type), b64reals, b64ids, bwithmasses));
+        if (lattice_type == lattice_glass)
+            throw std::runtime_error("glass load: hand the tiled glass positions (glass_loader::glass_posr, grid units) to the "
+                                     "constructor overload that takes them - reading the glass file stays host code");
+        if (lattice_type == lattice_masked) {
+            int mask[8];
+            particle_type_mask(mfb_detail::cfg_reader<config_t, bool>::get(cf, "setup", "DoBaryons", false),
+                               unsigned(mfb_detail::cfg_reader<config_t, int>::get(cf, "setup", "ParticleMaskType", 3)), mask);
+            mfb_detail::check(mfb_particles_create_masked(&p_, n, lattice_index, mask, b64reals, b64ids, bwithmasses));
+        } else {
+            mfb_detail::check(mfb_particles_create(&p_, n, int(lattice_type), b64reals, b64ids, bwithmasses));
+        }
+        mfb_detail::check(mfb_particles_set_ids(p_, (unsigned long long)IDoffset));
+        global_num_particles_ = mfb_particles_count(p_);
+    }
+    // glass load (:262-290): `posr` = glass_loader::glass_posr (positions in grid units, [np][3]), `offset` = glass_loader::offset()
+    lattice_generator(const std::vector<double>& posr, size_t offset, const bool b64reals, const bool b64ids, size_t IDoffset,
+                      const field_t& field)
+        : b64reals_(b64reals), b64ids_(b64ids), bmass_(false) {
+        int n[3] = {int(field.n_[0]), int(field.n_[1]), int(field.n_[2])};
+        mfb_detail::check(mfb_particles_create_glass(&p_, n, posr.data(), posr.size() / 3, (unsigned long long)offset, b64reals, b64ids));
         mfb_detail::check(mfb_particles_set_ids(p_, (unsigned long long)IDoffset));
         global_num_particles_ = mfb_particles_count(p_);
     }

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <random>
 
+#include "../../include/mfb/particle_plt.hh"
 #include "../../include/mfb/convolution.hh"
 #include "../../include/mfb/grid_fft_complex.hh"
 #include "../../include/mfb/particle_generator.hh"
@@ -136,6 +137,55 @@ int main() {
     CHECK(pc.ids64_.size() == 2 * nc);
     CHECK(pc.ids64_[0] == 2 * nc && pc.ids64_[5] == 2 * nc + 10 && pc.ids64_[nc + 5] == 2 * nc + 11);
     CHECK(pc.positions64_[3 * 5 + 2] == 5.0 / 32 * 2.0 && pc.positions64_[3 * (nc + 5) + 2] == 5.5 / 32 * 2.0);
+    {
+        // masked sc lattice (include/particle_generator.hh:171-260): a config that says DoBaryons -> CDM on 7 of 8 cells,
+        // baryons on the cell centres; ids = IDoffset*N^3 + cell index of the selected cells in (i,j,k) order
+        struct masked_config {
+            bool get_value_safe(const std::string&, const std::string& k, bool d) const { return k == "DoBaryons" ? true : d; }
+            int get_value_safe(const std::string&, const std::string&, int d) const { return d; }
+        } mcf;
+        particle::lattice_generator<Grid_FFT<real_t>> cdm(particle::lattice_masked, 0, true, true, true, 0, tmp, mcf);
+        particle::lattice_generator<Grid_FFT<real_t>> bar(particle::lattice_masked, 1, true, true, true, 1, tmp, mcf);
+        tmp.FourierTransformBackward(false);
+        tmp.zero();
+        for (int d = 0; d < 3; ++d) { cdm.set_positions(particle::lattice_masked, 0, d, 2.0, true, tmp, mcf); bar.set_positions(particle::lattice_masked, 1, d, 2.0, true, tmp, mcf); }
+        const auto& pc0 = cdm.get_particles();
+        const auto& pc1 = bar.get_particles();
+        CHECK(pc0.ids64_.size() == 7 * nc / 8 && pc1.ids64_.size() == nc / 8);
+        CHECK(pc0.ids64_[0] == 0 && pc0.ids64_[1] == 1 && pc1.ids64_[0] == nc + (n * n + n + 1));   // first baryon: cell (1,1,1)
+        CHECK(pc1.positions64_[0] == 1.0 / 32 * 2.0 && pc1.positions64_[2] == 1.0 / 32 * 2.0);
+        // without DoBaryons every cell is CDM (mock_config has no get_value_safe: the reference's defaults apply)
+        particle::lattice_generator<Grid_FFT<real_t>> all(particle::lattice_masked, 0, true, true, false, 0, tmp, cf);
+        CHECK(all.get_particles().ids64_.size() == nc);
+        // glass load (:262-290): CIC read-out of a constant field at arbitrary positions gives the constant
+        std::vector<double> posr = {0.25, 1.5, 31.75, 7.0, 8.0, 9.0};
+        particle::lattice_generator<Grid_FFT<real_t>> gl(posr, 100, true, true, 5, tmp);
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) tmp.relem(i, j, k) = 0.125;
+        for (int d = 0; d < 3; ++d) { gl.set_positions(particle::lattice_glass, 0, d, 2.0, true, tmp, cf); gl.set_velocities(particle::lattice_glass, 0, d, true, tmp, cf); }
+        const auto& pg = gl.get_particles();
+        CHECK(pg.ids64_.size() == 2 && pg.ids64_[0] == 105 && pg.ids64_[1] == 106);
+        CHECK(std::fabs(pg.velocities64_[4] - 0.125) < 1e-15 && std::fabs(pg.positions64_[2] - (31.75 / 32 * 2.0 + 0.125)) < 1e-14);
+        // PLT gradient operator (include/particle_plt.hh:551-585): identity tables on a helper mesh of the grid's own size
+        // reproduce i k_d wherever the Fourier gradient is not zeroed (away from the Nyquist planes)
+        const size_t nt = n * n * (n / 2 + 1);
+        std::vector<double> one(nt, 1.0), zero(nt, 0.0);
+        particle::lattice_gradient plt(int(n), int(n), 100.0, one, zero, zero, one);
+        Grid_FFT<real_t> a({n, n, n}, {100.0, 100.0, 100.0}), b({n, n, n}, {100.0, 100.0, 100.0}), ph({n, n, n}, {100.0, 100.0, 100.0});
+        Fill_Grid(ph, 77);
+        ph.FourierTransformForward();
+        a.FourierTransformForward(false);
+        b.FourierTransformForward(false);
+        mfb_detail::check(mfb_lpt_assemble(a.device_handle(), 1, ph.device_handle(), nullptr, nullptr, nullptr, 1, 0, 0, 0, 1.0, nullptr, nullptr, 0, 0.0));
+        mfb_detail::check(mfb_lpt_assemble_lg(b.device_handle(), 1, ph.device_handle(), nullptr, nullptr, nullptr, 1, 0, 0, 0, 1.0, nullptr, nullptr, 0, 0.0,
+                                              plt.device_handle(), 1, 0));
+        double dmax = 0, amax = 0;
+        for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n / 2; ++k) {
+            if (i == n / 2 || j == n / 2) continue;
+            dmax = std::max(dmax, std::abs(a.kelem(i, j, k) - b.kelem(i, j, k)));
+            amax = std::max(amax, std::abs(a.kelem(i, j, k)));
+        }
+        CHECK(amax > 0 && dmax < 1e-12 * amax);
+    }
     std::printf("host mirror ok (%s)\n", mfb_build_info());
     mfb_finalize();
     return 0;

@@ -166,7 +166,10 @@ int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi);
 int mfb_cgrid_create(mfb_cgrid** g, const int n[3], const double L[3]);
 int mfb_cgrid_destroy(mfb_cgrid* g);
 int mfb_cgrid_space(const mfb_cgrid* g);
-size_t mfb_cgrid_nelem(const mfb_cgrid* g);
+size_t mfb_cgrid_nelem(const mfb_cgrid* g);     /* local elements of the buffer (slabs: the larger of the two layouts) */
+/* slab decomposition of a complex grid, as mfb_grid_local: out = {local_0_start, local_0_size, local_1_start, local_1_size};
+   real space [x_loc][n1][n2], k-space transposed [ky_loc][n0][n2] (src/grid_fft.cc:130-133).  Returns 1 when distributed. */
+int mfb_cgrid_local(const mfb_cgrid* g, int out[4]);
 int mfb_cgrid_upload(mfb_cgrid* g, const double* host_interleaved, int space);
 int mfb_cgrid_download(const mfb_cgrid* g, double* host_interleaved);
 int mfb_cgrid_copy(mfb_cgrid* dst, const mfb_cgrid* src);                    /* copy_from */

@@ -89,6 +89,7 @@ def _declare(lib):
         "mfb_cgrid_destroy": (i, [vp]),
         "mfb_cgrid_space": (i, [vp]),
         "mfb_cgrid_nelem": (sz, [vp]),
+        "mfb_cgrid_local": (i, [vp, ip]),
         "mfb_cgrid_upload": (i, [vp, vp, i]),
         "mfb_cgrid_download": (i, [vp, vp]),
         "mfb_cgrid_copy": (i, [vp, vp]),

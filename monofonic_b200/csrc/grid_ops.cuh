@@ -49,13 +49,18 @@ struct CGeom {
     int n0, n1, n2;
     double kf0, kf1, kf2;
     ptrdiff_t rpitch;  // doubles per row of the real companions
+    int s0, s1;        // storage extents of the two slow axes: (n0 or x_loc, n1) in real space, (ky_loc, n0) in a slab's k-space
+    int tr, off;       // transposed k-space layout of a slab, first local ky
 };
+// i, j, k: indices along x, y, z (wave indices in k-space); t_: element in the complex grid; ridx: same cell in a real companion
 #define MFB_C_LOOP_BEGIN(G)                                                                                       \
-    const long total_ = long((G).n0) * (G).n1 * (G).n2;                                                           \
+    const long total_ = long((G).s0) * (G).s1 * (G).n2;                                                           \
     for (long t_ = long(blockIdx.x) * EW_THREADS + threadIdx.x; t_ < total_; t_ += long(gridDim.x) * EW_THREADS) { \
         const int k = int(t_ % (G).n2);                                                                           \
         const long r_ = t_ / (G).n2;                                                                              \
-        const int j = int(r_ % (G).n1), i = int(r_ / (G).n1);                                                     \
+        const int a_ = int(r_ / (G).s1), b_ = int(r_ % (G).s1);                                                   \
+        const int i = (G).tr ? b_ : a_;                                                                           \
+        const int j = (G).tr ? a_ + (G).off : b_;                                                                 \
         const long ridx = r_ * (G).rpitch + k;                                                                    \
         (void)i; (void)j; (void)ridx;
 

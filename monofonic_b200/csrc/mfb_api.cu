@@ -580,6 +580,39 @@ static void cgrid_fft(mfb_cgrid* g, int inverse) {
     const int n0 = g->n[0], n1 = g->n[1], n2 = g->n[2];
     const double norm = 1.0 / std::sqrt(double(n0) * n1 * n2);
     double2* c = g->d;
+    if (g->dist) {
+        // slabs (FFTW-MPI c2c with transposed output, src/grid_fft.cc:130-133): z on the local rows, y on the local planes with
+        // the exchange fused into its stores, x on the received [x][ky_loc] block.  The exchange buffers are sized for the
+        // half-spectra of the real grids, so the complex grid goes through in two halves of the z range; a half's x pass
+        // rewrites only that half of every row, which the other half's y pass never reads.
+        const int l0 = g->nloc0, l1 = g->nloc1, hz = n2 / 2;
+        if (!inverse) {
+            launch_zc2c(n2, c, long(l0) * n1, norm, 0);
+            for (int z0 = 0; z0 < n2; z0 += hz) {
+                Exchange x = begin_exchange(size_t(l0) * l1 * hz);
+                StridedArgs a = plain_strided(c + z0, nullptr, n2, ptrdiff_t(n1) * n2, l0, hz, n1, 0);
+                route(a, x, l1, hz, ptrdiff_t(l1) * hz);                          // chunk layout [x_loc][ky_loc][z half]
+                launch_strided(n1, a, ROLE_FFT_Y);
+                end_exchange(x);                                                   // recv: [x][ky_loc][z half]
+                StridedArgs b = plain_strided(x.recv, c + z0, ptrdiff_t(l1) * hz, hz, l1, hz, n0, 0);
+                b.out_ps = n2; b.out_as = ptrdiff_t(n0) * n2;                      // -> [ky_loc][kx][kz]
+                launch_strided(n0, b, ROLE_FFT_X);
+            }
+        } else {
+            for (int z0 = 0; z0 < n2; z0 += hz) {
+                Exchange x = begin_exchange(size_t(l0) * l1 * hz);
+                StridedArgs a = plain_strided(c + z0, nullptr, n2, ptrdiff_t(n0) * n2, l1, hz, n0, 1);
+                route(a, x, l0, hz, ptrdiff_t(l0) * hz);                          // chunk layout [ky_loc][x_loc][z half]
+                launch_strided(n0, a, ROLE_FFT_X);
+                end_exchange(x);                                                   // recv: [ky][x_loc][z half]
+                StridedArgs b = plain_strided(x.recv, c + z0, ptrdiff_t(l0) * hz, hz, l0, hz, n1, 1);
+                b.out_ps = n2; b.out_as = ptrdiff_t(n1) * n2;                      // -> [x_loc][y][z]
+                launch_strided(n1, b, ROLE_FFT_Y);
+            }
+            launch_zc2c(n2, c, long(l0) * n1, norm, 1);
+        }
+        return;
+    }
     if (!inverse) {
         launch_zc2c(n2, c, long(n0) * n1, norm, 0);
         launch_strided(n1, plain_strided(c, c, n2, ptrdiff_t(n1) * n2, n0, n2, n1, 0), ROLE_FFT_Y);
@@ -595,11 +628,20 @@ static CGeom cgeom(const mfb_cgrid* g) {
     c.n0 = g->n[0]; c.n1 = g->n[1]; c.n2 = g->n[2];
     c.kf0 = 2.0 * M_PI / g->L[0]; c.kf1 = 2.0 * M_PI / g->L[1]; c.kf2 = 2.0 * M_PI / g->L[2];
     c.rpitch = g->n[2] + 2;
+    c.s0 = g->n[0]; c.s1 = g->n[1]; c.tr = 0; c.off = 0;
+    if (g->dist) {
+        if (g->space == MFB_KSPACE) { c.s0 = g->nloc1; c.s1 = g->n[0]; c.tr = 1; c.off = g->off1; }
+        else c.s0 = g->nloc0;
+    }
     return c;
 }
+static size_t cgrid_local_elems(const mfb_cgrid* g) {   // elements of the current layout
+    if (!g->dist) return g->nelem;
+    return (g->space == MFB_KSPACE ? size_t(g->nloc1) * g->n[0] : size_t(g->nloc0) * g->n[1]) * g->n[2];
+}
 static void check_ppt_real(const mfb_cgrid* c, const mfb_grid* r, const char* name) {
-    if (!r || r->dist || r->n[0] != c->n[0] || r->n[1] != c->n[1] || r->n[2] != c->n[2])
-        throw std::runtime_error(std::string("PPT: real grid '") + name + "' must be a single-slab grid of the same size");
+    if (!r || r->dist != c->dist || r->n[0] != c->n[0] || r->n[1] != c->n[1] || r->n[2] != c->n[2])
+        throw std::runtime_error(std::string("PPT: real grid '") + name + "' must be a grid of the same size and decomposition");
     if (r->space != MFB_RSPACE) throw std::runtime_error(std::string("PPT: real grid '") + name + "' must be in real space");
 }
 
@@ -1582,13 +1624,15 @@ int mfb_grid_2norm(mfb_grid* g, double* out) {
 int mfb_grid_max_neighbour_diff(mfb_grid* g, double* out) {
     MFB_TRY
     require(g->space == MFB_RSPACE, "max_neighbour_diff: grid must be in real space");
-    require(!g->dist, "max_neighbour_diff is not available for slab-decomposed grids");
     const int nb = 148 * 4;
     double* part = partial_buffer(2 * nb + 2);
-    MFB_LAUNCH_ROLE(ROLE_REDUCE, max_neighbour_diff_kernel, nb, RED_THREADS, g->d, g->n[0], g->n[1], g->n[2], g->pitch, part);
+    // slabs: like the reference's loop (i < size(0) - 1 on the LOCAL planes, then MPI_Allreduce(MAX), src/ic_generator.cc:715-733)
+    // every rank leaves out the x neighbour of its last plane
+    MFB_LAUNCH_ROLE(ROLE_REDUCE, max_neighbour_diff_kernel, nb, RED_THREADS, g->d, g->dist ? g->nloc0 : g->n[0], g->n[1], g->n[2], g->pitch, part);
     check_launch("max_neighbour_diff");
     MFB_LAUNCH_ROLE(ROLE_REDUCE, reduce_final_kernel, 1, RED_THREADS, part, nb, 1, part + 2 * nb);
     check_launch("reduce_final");
+    if (g->dist) dist_allreduce_max1(part + 2 * nb);
     cuda_check(cudaMemcpyAsync(out, part + 2 * nb, sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream), "D2H");
     cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
     MFB_CATCH
@@ -1769,12 +1813,20 @@ int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi) {
 int mfb_cgrid_create(mfb_cgrid** out, const int n[3], const double L[3]) {
     MFB_TRY
     require(g_ctx.initialised, "mfb_init has not been called");
-    require(!dist_on(), "complex grids (PPT branch) are only available on a single slab");
     for (int d = 0; d < 3; ++d) require(supported_size(n[d]), "unsupported grid size (no FFT plan)");
     mfb_cgrid* g = new mfb_cgrid();
     for (int d = 0; d < 3; ++d) { g->n[d] = n[d]; g->L[d] = L[d]; }
     g->space = MFB_RSPACE;
     g->nelem = size_t(n[0]) * n[1] * n[2];
+    g->dist = 0; g->nloc0 = n[0]; g->off0 = 0; g->nloc1 = n[1]; g->off1 = 0;
+    if (dist_on()) {
+        const int P = D().nranks, r = D().rank;
+        if (n[0] % P || n[1] % P || n[2] % 2) { delete g; throw std::runtime_error("slab decomposition needs grid sizes divisible by the number of GPUs"); }
+        g->dist = 1;
+        g->nloc0 = n[0] / P; g->off0 = r * g->nloc0;
+        g->nloc1 = n[1] / P; g->off1 = r * g->nloc1;
+        g->nelem = std::max(size_t(g->nloc0) * n[1], size_t(g->nloc1) * n[0]) * n[2];
+    }
     try { g->d = (double2*)dev_alloc(g->nelem * sizeof(double2)); }
     catch (...) { delete g; throw; }
     cuda_check(cudaMemsetAsync(g->d, 0, g->nelem * sizeof(double2), g_ctx.stream), "memset");
@@ -1787,6 +1839,10 @@ int mfb_cgrid_destroy(mfb_cgrid* g) {
     MFB_CATCH
 }
 int mfb_cgrid_space(const mfb_cgrid* g) { return g->space; }
+int mfb_cgrid_local(const mfb_cgrid* g, int out[4]) {
+    out[0] = g->off0; out[1] = g->nloc0; out[2] = g->off1; out[3] = g->nloc1;
+    return g->dist;
+}
 size_t mfb_cgrid_nelem(const mfb_cgrid* g) { return g->nelem; }
 int mfb_cgrid_upload(mfb_cgrid* g, const double* host_interleaved, int space) {
     MFB_TRY
@@ -1803,7 +1859,7 @@ int mfb_cgrid_download(const mfb_cgrid* g, double* host_interleaved) {
 }
 int mfb_cgrid_copy(mfb_cgrid* dst, const mfb_cgrid* src) {
     MFB_TRY
-    require(dst->nelem == src->nelem, "copy_from: size mismatch");
+    require(dst->nelem == src->nelem && dst->dist == src->dist, "copy_from: size mismatch");
     cuda_check(cudaMemcpyAsync(dst->d, src->d, src->nelem * sizeof(double2), cudaMemcpyDeviceToDevice, g_ctx.stream), "copy");
     dst->space = src->space;
     MFB_CATCH
@@ -1822,16 +1878,17 @@ int mfb_cgrid_gradient(mfb_cgrid* g, int idim) {
     MFB_TRY
     require(idim >= 0 && idim < 3, "bad dimension");
     require(g->space == MFB_KSPACE, "gradient: complex grid must be in k-space");
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, cgrid_gradient_kernel, stream_blocks(g->nelem), EW_THREADS, g->d, cgeom(g), idim);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, cgrid_gradient_kernel, stream_blocks(cgrid_local_elems(g)), EW_THREADS, g->d, cgeom(g), idim);
     check_launch("cgrid_gradient");
     MFB_CATCH
 }
 int mfb_ppt_sqrt_density(mfb_grid* rho, double C_species) {
     MFB_TRY
-    require(rho->space == MFB_RSPACE && !rho->dist, "PPT: rho must be a single-slab real-space grid");
+    require(rho->space == MFB_RSPACE, "PPT: rho must be a real-space grid");
     CGeom c;
     c.n0 = rho->n[0]; c.n1 = rho->n[1]; c.n2 = rho->n[2]; c.kf0 = c.kf1 = c.kf2 = 0.0; c.rpitch = rho->pitch;
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_sqrt1p_kernel, stream_blocks(size_t(c.n0) * c.n1 * c.n2), EW_THREADS, rho->d, c, C_species);
+    c.s0 = rho->dist ? rho->nloc0 : rho->n[0]; c.s1 = rho->n[1]; c.tr = 0; c.off = 0;
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_sqrt1p_kernel, stream_blocks(size_t(c.s0) * c.n1 * c.n2), EW_THREADS, rho->d, c, C_species);
     check_launch("ppt_sqrt1p");
     MFB_CATCH
 }
@@ -1839,16 +1896,16 @@ int mfb_ppt_init_psi(mfb_cgrid* psi, const mfb_grid* rho, const mfb_grid* phi, c
     MFB_TRY
     check_ppt_real(psi, rho, "rho"); check_ppt_real(psi, phi, "phi");
     if (phi2) check_ppt_real(psi, phi2, "phi2");
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_init_psi_kernel, stream_blocks(psi->nelem), EW_THREADS, psi->d, rho->d, phi->d,
+    psi->space = MFB_RSPACE;
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_init_psi_kernel, stream_blocks(cgrid_local_elems(psi)), EW_THREADS, psi->d, rho->d, phi->d,
                     phi2 ? phi2->d : (const double*)nullptr, cgeom(psi), 1.0 / hbar, Dplus0);
     check_launch("ppt_init_psi");
-    psi->space = MFB_RSPACE;
     MFB_CATCH
 }
 int mfb_ppt_drift(mfb_cgrid* psi, double hbar, double Dplus0) {
     MFB_TRY
     require(psi->space == MFB_KSPACE, "PPT drift: psi must be in k-space");
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_drift_kernel, stream_blocks(psi->nelem), EW_THREADS, psi->d, cgeom(psi), hbar, Dplus0);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_drift_kernel, stream_blocks(cgrid_local_elems(psi)), EW_THREADS, psi->d, cgeom(psi), hbar, Dplus0);
     check_launch("ppt_drift");
     MFB_CATCH
 }
@@ -1856,7 +1913,7 @@ int mfb_ppt_kick(mfb_cgrid* psi, const mfb_grid* phi2, double hbar, double Dplus
     MFB_TRY
     require(psi->space == MFB_RSPACE, "PPT kick: psi must be in real space");
     check_ppt_real(psi, phi2, "phi2");
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_kick_kernel, stream_blocks(psi->nelem), EW_THREADS, psi->d, phi2->d, cgeom(psi), 1.0 / hbar, Dplus0);
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_kick_kernel, stream_blocks(cgrid_local_elems(psi)), EW_THREADS, psi->d, phi2->d, cgeom(psi), 1.0 / hbar, Dplus0);
     check_launch("ppt_kick");
     MFB_CATCH
 }
@@ -1865,7 +1922,7 @@ int mfb_ppt_density(mfb_grid* rho, const mfb_cgrid* psi) {
     require(psi->space == MFB_RSPACE, "PPT density: psi must be in real space");
     rho->space = MFB_RSPACE;
     check_ppt_real(psi, rho, "rho");
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_density_kernel, stream_blocks(psi->nelem), EW_THREADS, rho->d, psi->d, cgeom(psi));
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_density_kernel, stream_blocks(cgrid_local_elems(psi)), EW_THREADS, rho->d, psi->d, cgeom(psi));
     check_launch("ppt_density");
     MFB_CATCH
 }
@@ -1875,7 +1932,7 @@ int mfb_ppt_velocity(mfb_grid* out, const mfb_cgrid* psi, const mfb_cgrid* grad_
     require(psi->nelem == grad_psi->nelem, "PPT velocity: size mismatch");
     out->space = MFB_RSPACE;
     check_ppt_real(psi, out, "out"); check_ppt_real(psi, rho, "rho");
-    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_velocity_kernel, stream_blocks(psi->nelem), EW_THREADS, out->d, psi->d, grad_psi->d, rho->d,
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ppt_velocity_kernel, stream_blocks(cgrid_local_elems(psi)), EW_THREADS, out->d, psi->d, grad_psi->d, rho->d,
                     cgeom(psi), hbar, vunit);
     check_launch("ppt_velocity");
     MFB_CATCH

@@ -127,4 +127,22 @@ inline void dist_allreduce_sum2(double* dev_pair) {
     check_launch("dist_sum2");
 }
 
+// max of a scalar over all ranks (MPI_Allreduce(MAX) of src/ic_generator.cc:730-733)
+__global__ void dist_max1_kernel(const double2* __restrict__ recv, int nranks, double* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        double a = recv[0].x;
+        for (int r = 1; r < nranks; ++r) a = fmax(a, recv[r].x);
+        out[0] = a;
+    }
+}
+inline void dist_allreduce_max1(double* dev_pair) {   // dev_pair[0] in/out, dev_pair[1] scratch
+    DistState& d = D();
+    Exchange x = begin_exchange(1);
+    MFB_LAUNCH(dist_put2_kernel, 1, 32, 0, g_ctx.stream, x, d.nranks, dev_pair);
+    check_launch("dist_put2");
+    end_exchange(x);
+    MFB_LAUNCH(dist_max1_kernel, 1, 32, 0, g_ctx.stream, x.recv, d.nranks, dev_pair);
+    check_launch("dist_max1");
+}
+
 }  // namespace mfb

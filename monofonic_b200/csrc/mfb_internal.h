@@ -25,13 +25,16 @@ struct mfb_grid {
     bool upload_pending = false;
 };
 
-// Grid_FFT<ccomplex_t> (PPT / Eulerian branch): dense [n0][n1][n2] complex, c2c transforms, single slab
+// Grid_FFT<ccomplex_t> (PPT / Eulerian branch): dense [n0][n1][n2] complex, c2c transforms.  Slabs like mfb_grid: real space
+// [x_loc][n1][n2], k-space transposed [ky_loc][n0][n2]
 struct mfb_cgrid {
     int n[3];
     double L[3];
     int space;
     double2* d;
-    size_t nelem;
+    size_t nelem;     // local elements
+    int dist = 0;
+    int nloc0 = 0, off0 = 0, nloc1 = 0, off1 = 0;
 };
 
 // identity of a backward-transformed operand held in one of the convolver's operand buffers

@@ -297,6 +297,9 @@ class Grid_FFT_complex:
         self._lib = _lib()
         self._h = C.c_void_p()
         L.check(self._lib.mfb_cgrid_create(C.byref(self._h), _i3(self.n_), _d3(self.length_)), self._lib)
+        loc = (C.c_int * 4)()
+        self.distributed_ = bool(self._lib.mfb_cgrid_local(self._h, loc))
+        self.local_0_start_, self.local_0_size_, self.local_1_start_, self.local_1_size_ = (int(v) for v in loc)
 
     def __del__(self):
         try:
@@ -311,14 +314,32 @@ class Grid_FFT_complex:
         return self._lib.mfb_cgrid_space(self._h)
 
     def set(self, x: np.ndarray, space=rspace_id):
+        """fill from the global [n0][n1][n2] array (real space: [x][y][z]; k-space: [kx][ky][kz]); a slab keeps its part -
+        planes of x in real space, the transposed [ky_loc][kx][kz] block in k-space"""
         x = np.ascontiguousarray(x, dtype=np.complex128)
         assert x.shape == self.n_
+        if self.distributed_:
+            if int(space) == rspace_id:
+                loc = x[self.local_0_start_:self.local_0_start_ + self.local_0_size_]
+            else:
+                loc = np.transpose(x[:, self.local_1_start_:self.local_1_start_ + self.local_1_size_], (1, 0, 2))
+            buf = np.zeros(int(self._lib.mfb_cgrid_nelem(self._h)), dtype=np.complex128)
+            buf[:loc.size] = np.ascontiguousarray(loc).reshape(-1)
+            x = buf
         L.check(self._lib.mfb_cgrid_upload(self._h, x.ctypes.data_as(C.c_void_p), int(space)), self._lib)
 
     def get(self) -> np.ndarray:
-        out = np.empty(self.n_, dtype=np.complex128)
-        L.check(self._lib.mfb_cgrid_download(self._h, out.ctypes.data_as(C.c_void_p)), self._lib)
-        return out
+        """single slab: the [n0][n1][n2] array.  Slabs: the local part - [x_loc][n1][n2] in real space, [ky_loc][n0][n2] in
+        k-space"""
+        if not self.distributed_:
+            out = np.empty(self.n_, dtype=np.complex128)
+            L.check(self._lib.mfb_cgrid_download(self._h, out.ctypes.data_as(C.c_void_p)), self._lib)
+            return out
+        buf = np.empty(int(self._lib.mfb_cgrid_nelem(self._h)), dtype=np.complex128)
+        L.check(self._lib.mfb_cgrid_download(self._h, buf.ctypes.data_as(C.c_void_p)), self._lib)
+        n0, n1, n2 = self.n_
+        shape = (self.local_0_size_, n1, n2) if self.space_ == rspace_id else (self.local_1_size_, n0, n2)
+        return buf[:shape[0] * shape[1] * shape[2]].reshape(shape).copy()
 
     def copy_from(self, g: "Grid_FFT_complex"):
         L.check(self._lib.mfb_cgrid_copy(self._h, g._h), self._lib)

@@ -525,10 +525,12 @@ def density_k(g: GridSpec, pots):
     return g.k2() * pots["phi"]
 
 
-def ppt_eulerian(g: GridSpec, Wc, pots, order, Dplus0, vfac, amp_delta_bc, C_species, velocity_unit=1.0):
+def ppt_eulerian(g: GridSpec, Wc, pots, order, Dplus0, vfac, amp_delta_bc, C_species, velocity_unit=1.0, nranks=1):
     """Semiclassical (PPT) Eulerian density and velocity fields, src/ic_generator.cc:685-803.
     `pots` are the growth-scaled potentials of lpt_potentials (phi already contains -D+, :561), `Wc` the conditioned
-    white noise in k-space.  Returns ({"density","vx","vy","vz"}, hbar)."""
+    white noise in k-space.  Returns ({"density","vx","vy","vz"}, hbar).
+    nranks > 1: hbar as the reference's MPI build computes it - the loop of :715-729 runs over the LOCAL planes of every rank
+    and stops one short of the last, then MPI_Allreduce(MAX) (:730-733)."""
     n = g.n
     kx, ky, kz = g.kvec()
     kmod = np.sqrt(kx * kx + ky * ky + kz * kz)
@@ -539,9 +541,13 @@ def ppt_eulerian(g: GridSpec, Wc, pots, order, Dplus0, vfac, amp_delta_bc, C_spe
     rho = np.sqrt(1.0 + C_species * g.bwd(rho))                        # :701-705
     phi = g.bwd(pots["phi"])                                           # :710
     # :713-731 - note the x loop stops at size(0)-1: the last x-plane is not visited
-    c = phi[:-1]
-    maxd = max(np.abs(np.roll(phi, -1, 0)[:-1] - c).max(), np.abs(np.roll(phi, -1, 1)[:-1] - c).max(),
-               np.abs(np.roll(phi, -1, 2)[:-1] - c).max())
+    maxd = -1.0
+    l0 = n // nranks
+    for r in range(nranks):
+        blk = phi[r * l0:(r + 1) * l0]
+        c = blk[:-1]
+        maxd = max(maxd, np.abs(blk[1:] - c).max(), np.abs(np.roll(blk, -1, 1)[:-1] - c).max(),
+                   np.abs(np.roll(blk, -1, 2)[:-1] - c).max())
     hbar = maxd / np.pi / Dplus0 * 1.01                                # :733-734
     if order == 1:
         psi = rho * np.exp(1j * ((1.0 / hbar) * (phi / Dplus0)))      # :738-740

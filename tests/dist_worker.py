@@ -156,6 +156,48 @@ def main():
         del parts
     del P, Q, out, C
 
+    # ---- complex grids on slabs: c2c transforms (exchange in two z halves) against numpy
+    rngc = np.random.default_rng(8)
+    xc = rngc.standard_normal(N3) + 1j * rngc.standard_normal(N3)
+    Gc = M.Grid_FFT_complex(N3, L3)
+    assert Gc.distributed_ and Gc.local_0_size_ == n // world
+    Gc.set(xc)
+    Gc.FourierTransformForward()
+    refc = np.fft.fftn(xc) / np.sqrt(float(n) ** 3)
+    loc = Gc.get()                                        # [ky_loc][kx][kz]
+    o1, l1 = Gc.local_1_start_, Gc.local_1_size_
+    assert PC.relerr(loc, np.transpose(refc[:, o1:o1 + l1], (1, 0, 2))) < TOL
+    Gc.apply_gradient(1)
+    Gc.FourierTransformBackward()
+    kyv = g.k1d[None, :, None]
+    refg = np.fft.ifftn(1j * kyv * refc) * np.sqrt(float(n) ** 3)
+    o0, l0 = Gc.local_0_start_, Gc.local_0_size_
+    assert PC.relerr(Gc.get(), refg[o0:o0 + l0]) < TOL
+    del Gc
+
+    # ---- the PPT / Eulerian branch on slabs (src/ic_generator.cc:685-803).  hbar follows the reference's MPI loop: every rank
+    # leaves out the x neighbour of its last local plane before the MAX reduction
+    Dp, vfac = 0.0257, 396.69
+    for order in (1, 2):
+        gp, Wp, Wcp, phip = PC.noise_and_phi(n, L, 31)
+        amp = O.power_law_amplitude()
+        amp_bc = lambda k: 2e-3 * amp(k) * k * k
+        Csp, vu = 0.8433, 1.7
+        pots = O.lpt_potentials(gp, phip, order, Dp)
+        ref, hbar_ref = O.ppt_eulerian(gp, Wcp, pots, order, Dp, vfac, amp_bc, Csp, vu, nranks=world)
+        pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=order, ParticleLoad="sc", Dplus0=Dp, vfac=vfac))
+        pl.set_noise_k(Wp)
+        pl.condition_noise()
+        pl.compute_phi1(O.radial_table(gp, amp))
+        pl.compute_sources()
+        got = {}
+        hbar = pl.eulerian_fields(O.radial_table(gp, amp_bc), Csp, vu, sink=lambda name, grid: got.__setitem__(name, MD.gather_real(grid)))[1]
+        assert abs(hbar - hbar_ref) < 1e-12 * hbar_ref, (hbar, hbar_ref)
+        for k in ("density", "vx", "vy", "vz"):
+            err = np.abs(got[k] - ref[k]).max() / np.abs(ref[k]).max()
+            assert err < 1e-9, (k, err)
+        del pl
+
     # ---- whole pipelines vs the oracle
     for order, lattice, real64 in [(1, "sc", True), (3, args.lattice, True), (2, "sc", False)]:
         Dp, vfac = 0.0257, 396.69

@@ -173,11 +173,44 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
 }
 
 // ------------------------------------------------------------------------------------------
+// Optional epilogue of the c2r pass: instead of storing the real field, read it out into a particle attribute right away -
+// the lattice read-out of particle::lattice_generator for a single-shift (sc) load (include/particle_generator.hh:448-465
+// positions, :544-560 velocities, :327-344 masses; "invalidates field" there too).  Saves one write and one read of the grid
+// per component.  dst[stride*(slot0 + cell) + comp] = real_t( add_lattice ? ((idx_d + shift)/n_d)*lunit + f : mul*f )
+struct ZReadout {
+    void* dst;
+    int real64;
+    int stride, comp;
+    long slot0;
+    int add_lattice, d;
+    double shift, lunit, mul;
+    int n0, n1, n2, i0;   // grid extents, local_0_start_
+};
+MFB_D void zreadout_store(const ZReadout& R, long row, int k, double v) {
+    double o;
+    if (R.add_lattice) {
+        const int j = int(row % R.n1), i = int(row / R.n1);
+        const int id = (R.d == 0) ? (i + R.i0) : ((R.d == 1) ? j : k);
+        const int nd = (R.d == 0) ? R.n0 : ((R.d == 1) ? R.n1 : R.n2);
+        const double qpos = (double(id) + R.shift) / double(nd);
+#ifdef MFB_EMU
+        o = qpos * R.lunit + v;
+#else
+        o = __dadd_rn(__dmul_rn(qpos, R.lunit), v);  // no FMA contraction: bit-identical to the CPU expression
+#endif
+    } else {
+        o = R.mul * v;
+    }
+    const size_t at = size_t(R.stride) * size_t(R.slot0 + row * R.n2 + k) + R.comp;
+    if (R.real64) reinterpret_cast<double*>(R.dst)[at] = o;
+    else reinterpret_cast<float*>(R.dst)[at] = float(o);
+}
+
 // z pass, half-complex -> real, in place.  rows: nrows rows of `pitch` doubles, each holding
 // n/2+1 complex on input and n reals (+2 pad) on output.  One complex FFT serves two rows.
-template <class P>
+template <class P, bool RO = false>
 __global__ void __launch_bounds__(P::NTHREADS) z_c2r_kernel(double* __restrict__ data, ptrdiff_t pitch, long nrows,
-                                                            double scale, const double2* __restrict__ tw) {
+                                                            double scale, const double2* __restrict__ tw, ZReadout R = ZReadout()) {
     MFB_DYN_SMEM(double2, sm);
     constexpr int N = P::N, T = P::T, NC = N / 2 + 1;
     const int tid = threadIdx.x;
@@ -201,8 +234,13 @@ __global__ void __launch_bounds__(P::NTHREADS) z_c2r_kernel(double* __restrict__
         const int l = idx / N, j = idx - l * N;
         const long r1 = row0 + 2 * l;
         const double2 z = sm[P::smem_addr(P::pos_of_freq(j), l)];
-        if (r1 < nrows) data[r1 * pitch + j] = z.x * scale;
-        if (r1 + 1 < nrows) data[(r1 + 1) * pitch + j] = -z.y * scale;
+        if constexpr (RO) {
+            if (r1 < nrows) zreadout_store(R, r1, j, z.x * scale);
+            if (r1 + 1 < nrows) zreadout_store(R, r1 + 1, j, -z.y * scale);
+        } else {
+            if (r1 < nrows) data[r1 * pitch + j] = z.x * scale;
+            if (r1 + 1 < nrows) data[(r1 + 1) * pitch + j] = -z.y * scale;
+        }
     }
 }
 

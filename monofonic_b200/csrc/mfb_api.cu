@@ -336,14 +336,18 @@ void launch_strided(int n, const StridedArgs& a, int role) {
     }
 }
 
-template <class P> void launch_z_t(int kind, double* data, ptrdiff_t pitch, long nrows, double scale) {
-    static bool done_c2r = false, done_r2c = false;
+template <class P> void launch_z_t(int kind, double* data, ptrdiff_t pitch, long nrows, double scale, const ZReadout* ro) {
+    static bool done_c2r = false, done_r2c = false, done_ro = false;
     const unsigned grid = unsigned((nrows + 2 * P::T - 1) / (2 * P::T));
     const double2* tw = twiddles(P::N);
     RoleScope rs(kind == 0 ? ROLE_FFT_Z_C2R : ROLE_FFT_Z_R2C, double(nrows) * (16.0 * P::N + 16.0));
-    if (kind == 0) {
-        optin_smem(z_c2r_kernel<P>, P::SMEM_BYTES, done_c2r);
-        MFB_LAUNCH(z_c2r_kernel<P>, grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, pitch, nrows, scale, tw);
+    if (kind == 0 && ro) {   // c2r with the lattice read-out as its epilogue: the real field is never stored
+        optin_smem((z_c2r_kernel<P, true>), P::SMEM_BYTES, done_ro);
+        MFB_LAUNCH((z_c2r_kernel<P, true>), grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, pitch, nrows, scale, tw, *ro);
+        check_launch("z_c2r_kernel(readout)");
+    } else if (kind == 0) {
+        optin_smem((z_c2r_kernel<P, false>), P::SMEM_BYTES, done_c2r);
+        MFB_LAUNCH((z_c2r_kernel<P, false>), grid, P::NTHREADS, P::SMEM_BYTES, g_ctx.stream, data, pitch, nrows, scale, tw, ZReadout());
         check_launch("z_c2r_kernel");
     } else {
         optin_smem(z_r2c_kernel<P>, P::SMEM_BYTES, done_r2c);
@@ -351,12 +355,12 @@ template <class P> void launch_z_t(int kind, double* data, ptrdiff_t pitch, long
         check_launch("z_r2c_kernel");
     }
 }
-void launch_z(int n, int kind, double* data, ptrdiff_t pitch, long nrows, double scale) {
+void launch_z(int n, int kind, double* data, ptrdiff_t pitch, long nrows, double scale, const ZReadout* ro = nullptr) {
     switch (n) {
 #define X(N_, TPL_, T_, ...)                                  \
     case N_: {                                                \
         using P = Plan<N_, TPL_, T_, __VA_ARGS__>;            \
-        launch_z_t<P>(kind, data, pitch, nrows, scale);       \
+        launch_z_t<P>(kind, data, pitch, nrows, scale, ro);   \
         break;                                                \
     }
         MFB_FOR_EACH_PLAN_ZROW(X)
@@ -470,7 +474,7 @@ static void dist_fft_forward(mfb_grid* g, double norm) {
     b.out_ps = nzc; b.out_as = ptrdiff_t(n0) * nzc;                     // -> [ky_loc][kx][kz]
     launch_strided(n0, b, ROLE_FFT_X);
 }
-static void dist_fft_backward(mfb_grid* g, double norm) {
+static void dist_fft_backward(mfb_grid* g, double norm, const ZReadout* ro = nullptr) {
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc, l0 = g->nloc0, l1 = g->nloc1;
     Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
@@ -481,7 +485,7 @@ static void dist_fft_backward(mfb_grid* g, double norm) {
     StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l0) * nzc, nzc, l0, nzc, n1, 1);
     b.out_ps = nzc; b.out_as = ptrdiff_t(n1) * nzc;                     // -> [x_loc][y][kz]
     launch_strided(n1, b, ROLE_FFT_Y);
-    launch_z(g->n[2], 0, g->d, g->pitch, long(l0) * n1, norm);
+    launch_z(g->n[2], 0, g->d, g->pitch, long(l0) * n1, norm, ro);
 }
 
 void grid_fft_forward(mfb_grid* g) {
@@ -493,14 +497,14 @@ void grid_fft_forward(mfb_grid* g) {
     launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 0), ROLE_FFT_Y);
     launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 0), ROLE_FFT_X);
 }
-void grid_fft_backward(mfb_grid* g) {
+void grid_fft_backward(mfb_grid* g, const ZReadout* ro = nullptr) {
     const double norm = 1.0 / std::sqrt(double(g->n[0]) * double(g->n[1]) * double(g->n[2]));
-    if (g->dist) { dist_fft_backward(g, norm); return; }
+    if (g->dist) { dist_fft_backward(g, norm, ro); return; }
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc;
     launch_strided(n0, plain_strided(c, c, ptrdiff_t(n1) * nzc, nzc, n1, nzc, n0, 1), ROLE_FFT_X);
     launch_strided(n1, plain_strided(c, c, nzc, ptrdiff_t(n1) * nzc, n0, nzc, n1, 1), ROLE_FFT_Y);
-    launch_z(g->n[2], 0, g->d, g->pitch, long(n0) * n1, norm);
+    launch_z(g->n[2], 0, g->d, g->pitch, long(n0) * n1, norm, ro);
 }
 void to_kspace(mfb_grid* g) {
     if (g->space != MFB_KSPACE) { grid_fft_forward(g); g->space = MFB_KSPACE; }
@@ -1173,6 +1177,27 @@ static void particles_readout(mfb_particles* p, int kind, int lattice_index, int
         cuda_check(cudaStreamWaitEvent(g_ctx.stream, p->copied[at], 0), "cudaStreamWaitEvent");
         p->copy_pending[at] = false;
     }
+    if (f->space == MFB_KSPACE && nshift == 1 && lattice_index == 0 && g_ctx.fused_readout) {
+        // single-shift load handed a k-space field: the read-out is the epilogue of the c2r pass and the real field is never
+        // stored (the reference's set_* calls leave the field "invalidated" as well, include/particle_generator.hh:290)
+        ZReadout ro;
+        memset(&ro, 0, sizeof(ro));
+        ro.dst = (kind == 0) ? p->pos : ((kind == 1) ? p->vel : p->mass);
+        require(ro.dst != nullptr, "particle buffer not allocated");
+        ro.real64 = p->real64;
+        ro.stride = (kind == 2) ? 1 : 3;
+        ro.comp = (kind == 2) ? 0 : idim;
+        ro.slot0 = 0;
+        ro.add_lattice = (kind == 0) ? 1 : 0;
+        ro.d = idim;
+        ro.shift = (kind == 0) ? LATTICE_SHIFTS[lt][0][idim] : 0.0;
+        ro.lunit = unit;
+        ro.mul = (kind == 2) ? pmean : 1.0;
+        ro.n0 = f->n[0]; ro.n1 = f->n[1]; ro.n2 = f->n[2]; ro.i0 = f->off0;
+        grid_fft_backward(f, &ro);
+        f->space = MFB_RSPACE;   // contents unspecified from here on
+        return;
+    }
     to_rspace(f);
     for (int is = 0; is < nshift; ++is) {
         if (is == 0 && lattice_index == 1) grid_shift_field(f, SECOND_LATTICE_SHIFT[lt], true);
@@ -1290,6 +1315,7 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "conv_grouping") g_ctx.conv_grouping = value != 0;
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
+    else if (std::string(name) == "fused_readout") g_ctx.fused_readout = value != 0;     // 0: c2r and lattice read-out as two passes
     else if (std::string(name) == "zm_prefetch") g_ctx.zm_prefetch = value != 0;         // 0: direct-load multi-product z pass
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
     else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)

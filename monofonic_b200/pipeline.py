@@ -119,14 +119,17 @@ class LPTPipeline:
                                               w[0], w[1], w[2], wc, scale, wn, tab, ntab, cv,
                                               self.lg._h if self.lg is not None else None, int(velocity), int(glass)), self._lib)
 
-    def displacement_field(self, d):
-        """tmp <- Psi_d in real space (src/ic_generator.cc:832-871)"""
+    def displacement_field(self, d, transform=True):
+        """tmp <- Psi_d in real space (src/ic_generator.cc:832-871).  transform=False leaves the assembled field in k-space:
+        handed like that to Particles.set_positions, the backward transform and the lattice read-out are one pass for
+        single-shift (sc) loads"""
         c = self.cfg
         self._assemble(d, (1.0, 1.0, 1.0), 1.0, c.lunit / c.BoxLength)
-        self.tmp.FourierTransformBackward()
+        if transform:
+            self.tmp.FourierTransformBackward()
         return self.tmp
 
-    def velocity_field(self, d, vbc=None):
+    def velocity_field(self, d, vbc=None, transform=True):
         """tmp <- v_d in real space (src/ic_generator.cc:888-942)"""
         c = self.cfg
         v = c.vfac
@@ -136,7 +139,8 @@ class LPTPipeline:
             # (src/ic_generator.cc:238-242, applied at :931-934 to the whole mode incl. the v_bc term)
             scale *= (1.0 - c.Dplus0 * c.tides[d]) ** 2
         self._assemble(d, (v, 2 * v, 3 * v), 3 * v, scale, vbc, velocity=True)
-        self.tmp.FourierTransformBackward()
+        if transform:
+            self.tmp.FourierTransformBackward()
         return self.tmp
 
     def density_field(self):
@@ -224,11 +228,11 @@ class LPTPipeline:
             self.particles.stream_out("ids", stream_to["ids"])
         self._ids_streamed = False
         for d in range(3):
-            self.particles.set_positions(d, c.lunit, self.displacement_field(d))
+            self.particles.set_positions(d, c.lunit, self.displacement_field(d, transform=False))
         if stream_to is not None and "pos" in stream_to:
             self.particles.stream_out("pos", stream_to["pos"].reshape(-1))
         for d in range(3):
-            self.particles.set_velocities(d, self.velocity_field(d))
+            self.particles.set_velocities(d, self.velocity_field(d, transform=False))
         if stream_to is not None and "vel" in stream_to:
             self.particles.stream_out("vel", stream_to["vel"].reshape(-1))
         return self.particles

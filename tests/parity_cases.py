@@ -778,6 +778,37 @@ def check_stream_handoff(M, n=32, order=2, lattice="bcc"):
             w.stream_in(np.zeros(5))
 
 
+def check_fused_readout(M, n=32):
+    """single-shift (sc) loads handed a k-space field: the lattice read-out as the epilogue of the c2r pass delivers bit for bit
+    what the two-pass sequence (backward transform, read-out kernel) delivers - positions, velocities, f32 and f64; other
+    lattices take the two-pass route whatever the option says"""
+    L = 100.0
+    lib = M.grid._lib()
+    g, W, Wc, phi = noise_and_phi(n, L, 13)
+    tab = O.radial_table(g, O.power_law_amplitude())
+    for lattice, r64 in (("sc", True), ("sc", False), ("bcc", True)):
+        res = []
+        try:
+            for fused in (1, 0):
+                assert lib.mfb_set_option(b"fused_readout", fused) == 0
+                cfg = M.lpt_config(GridRes=n, BoxLength=L, LPTorder=2, ParticleLoad=lattice, Dplus0=0.03, vfac=300.0, lunit=L, vunit=L,
+                                   real64=r64, ids64=False)
+                pl = M.LPTPipeline(cfg)
+                pl.set_noise_k(W)
+                pl.condition_noise()
+                l0 = M.kernel_launches()
+                host = pl.run_device(tab).download()
+                res.append((host, M.kernel_launches() - l0))
+        finally:
+            lib.mfb_set_option(b"fused_readout", 1)
+        for k in ("pos", "vel", "ids"):
+            assert np.array_equal(res[0][0][k], res[1][0][k]), (lattice, r64, k)
+        if lattice == "sc":
+            assert res[0][1] == res[1][1] - 6, (res[0][1], res[1][1])     # six read-out launches fewer
+        else:
+            assert res[0][1] == res[1][1]
+
+
 class pytest_raises:
     def __init__(self, exc):
         self.exc = exc

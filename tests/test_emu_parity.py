@@ -135,3 +135,7 @@ def test_f4_against_reference_produced_fixture(M):
 
 def test_noise_ingest(M):
     PC.check_noise_ingest(M, 32)
+
+
+def test_fused_readout(M):
+    PC.check_fused_readout(M, 32)

@@ -83,6 +83,11 @@ def test_noise_ingest(M, n):
     PC.check_noise_ingest(M, n)
 
 
+@pytest.mark.parametrize("n", [32, 256])
+def test_fused_readout(M, n):
+    PC.check_fused_readout(M, n)
+
+
 def test_f4_against_reference_produced_fixture(M):
     PC.check_reference_f4(M)
 

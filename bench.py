@@ -83,6 +83,7 @@ def parse():
     ap.add_argument("--lattice", default="", help="sc|bcc|fcc|rsc (default: the workload's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-grid", type=int, default=0, help="GridRes of the bounded CPU sample (default: chosen from a calibration run)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (mfb_set_option), for A/B runs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -582,6 +583,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    for kv in args.opt:
+        k, v = kv.split("=")
+        assert lib.mfb_set_option(k.encode(), int(v)) == 0, lib.mfb_last_error()
     stream = torch.cuda.ExternalStream(lib.mfb_stream())
     warm = max(3, args.warmup)
 

@@ -310,6 +310,13 @@ static bool launch_strided2(int n, const StridedArgs& a, int role) {
             default: return false;
         }
     }
+    if (mode == SM_PAD && n == 1536 && g_ctx.y_pad_tile4) {
+        // y-like padded passes (position stride of kilobytes, not routed to peers): two 4-line tiles per SM instead of one 8-line
+        // tile - the two CTAs overlap each other's load, butterfly and store phases (kbench 3.36 -> 3.75 TB/s,
+        // profiles/r02_kbench_strided_tma_bulk_negative.txt); x passes and routed passes keep 128-byte segments
+        const bool far_stride = a.in_ps * ptrdiff_t(sizeof(double2)) >= (1 << 20) || a.out_ps * ptrdiff_t(sizeof(double2)) >= (1 << 20);
+        if (!far_stride && a.out_blk == 0) { launch_strided2_t<Plan<1536, 64, 4, 12, 16, 8>, SM_PAD, 2>(a, role); return true; }
+    }
     switch (n) {
 #define X(N_, TPL_, T_, MINB_, ...)                                                  \
     case N_:                                                                         \
@@ -1319,6 +1326,7 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
     else if (std::string(name) == "fused_readout") g_ctx.fused_readout = value != 0;     // 0: c2r and lattice read-out as two passes
+    else if (std::string(name) == "y_pad_tile4") g_ctx.y_pad_tile4 = value != 0;         // 0: 8-line tiles for the padded y passes at n = 1536
     else if (std::string(name) == "zm_prefetch") g_ctx.zm_prefetch = value != 0;         // 0: direct-load multi-product z pass
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
     else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)

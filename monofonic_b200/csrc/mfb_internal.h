@@ -154,6 +154,7 @@ struct Context {
     bool strided_v2 = true;  // compile-time pad / truncate specialisations of the strided pass (fft_kernels2.cuh); 0: general kernel
     bool conv_own_accumulator = true;  // tests: 0 makes mfb_conv_create behave as under memory pressure
     bool conv_grouping = true;  // sum the products of one target before the forward passes (needs mfb_conv::Wacc)
+    bool y_pad_tile4 = false;   // padded y passes at n = 1536: two 4-line tiles per SM instead of one 8-line tile (no gain in the pipeline)
     bool fused_readout = true;  // sc loads handed a k-space field: lattice read-out as the epilogue of the c2r pass
     bool zm_prefetch = true;  // multi-product z pass: operand rows staged by TMA bulk copies (0: direct loads)
     bool sources_v2 = true;  // mfb_lpt_sources: shared x passes + multi-product z pass on the slot workspace (mfb_sources2.cuh)

@@ -749,8 +749,29 @@ def run_b200(args):
                                          f"{nex} exchanges in the whole run" if world > 1 else "single slab")},
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "fft3d": fft3d, "parity": parity, "parity_oracle_256": oracle256, "north_star_2048": ns2048,
+            "nvlink": nvlink_table(roles, n, world, order),
             "pipeline_alg_gb_per_step": total_alg, "pipeline_gbs": total_alg / (ms / 1e3), "stages": roles}
     print(json.dumps(line))
+
+
+def nvlink_table(roles, n, world, order):
+    """NVLink rate of the passes that carry an exchange (their stores go straight into the peers' receive buffers): bytes this
+    rank sends to its peers per step / the pass time, against 900 GB/s per direction.  x-bwd: one pruned [ky_loc][P0][N/2]
+    intermediate per pass; y-fwd: the [P0_loc][N][N/2] y-truncated target chunks; fft_x: the [ky_loc][N][N/2+1] spectra of the
+    six output transforms"""
+    if world < 2:
+        return None
+    P, f = world, (world - 1) / world
+    per_step = {"conv_x_bwd": lambda r: r["launches_per_step"] * (n // P) * (1.5 * n) * (n // 2) * 16.0,
+                "conv_y_fwd": lambda r: {2: 1, 3: 10}.get(order, 0) * (1.5 * n / P) * n * (n // 2) * 16.0,
+                "fft_x": lambda r: r["launches_per_step"] * (n // P) * n * (n // 2 + 1) * 16.0}
+    out = {}
+    for r in roles:
+        if r["role"] in per_step and r["ms_per_step"] > 0:
+            gb = per_step[r["role"]](r) * f / 1e9
+            out[r["role"]] = {"gb_to_peers_per_step": gb, "ms_per_step": r["ms_per_step"], "gbs": gb / (r["ms_per_step"] / 1e3),
+                              "frac_of_900": gb / (r["ms_per_step"] / 1e3) / 900.0}
+    return out
 
 
 def run_2048(M, lib, torch, dist, local_rank, stream, barrier, max_over_ranks, peak):
@@ -784,7 +805,7 @@ def run_2048(M, lib, torch, dist, local_rank, stream, barrier, max_over_ranks, p
         res = {"value": n ** 3 / (ms / 1e3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms, "steps": 2, "warmup": 2,
                "workload": workload_name(n, 3, "sc"), "source_stage": sinfo, "exchange_buffers": int(lib.mfb_dist_nslots()),
                "frac_of_hbm_ceiling_6641": n ** 3 / (ms / 1e3) / 1e6 / 6641.0,
-               "stages": roles,
+               "stages": roles, "nvlink": nvlink_table(roles, n, dist.get_world_size(), 3),
                "per_kernel_frac": {r["role"]: r["gbs"] / peak for r in roles if r["gbs"]},
                "parity": "same code path as the 256^3 oracle check and the 1024^3 N=1 digest check of this line (no 2048^3 "
                          "single-GPU or CPU run is possible: 3LPT 2048^3 needs 8 GPUs, SURVEY App. C)"}

@@ -52,10 +52,17 @@ struct StridedArgs {
     int zero_fill;             // on OP_ASSIGN also write zeros to skipped lines / Nyquist outputs
     // ---- slab-decomposed (multi-GPU) passes
     int a_off;                 // global index of local a == 0 (wave numbers, a_skip)
+    // z-blocked layouts of exchange buffers: line iz of a-index a sits at a*as + (iz / zb)*zbs + iz % zb instead of a*as + iz
+    // (zb == 0: plain).  With zb = the producer's tile height and position stride ps = zb, the segments a tile writes for
+    // consecutive positions are adjacent in memory: peer stores of a routed pass become long contiguous runs.
+    int in_zb, out_zb;
+    ptrdiff_t in_zbs, out_zbs;
     int out_blk;               // > 0: output position k goes to rank k / out_blk, at local position k % out_blk:
     double2* out_peer[MFB_MAX_RANKS];  //   out_peer[rank] + a*out_as + (k % out_blk)*out_ps + iz  (peer memory over NVLink,
                                //   or a staging chunk when the exchange is done by a host collective)
 };
+
+MFB_HD ptrdiff_t zline_off(int iz, int zb, ptrdiff_t zbs) { return zb > 0 ? ptrdiff_t(iz / zb) * zbs + (iz % zb) : ptrdiff_t(iz); }
 
 MFB_HD double wave_k(int i, int n, double kfac, int keep_nyq = 0) {
     return (i == n / 2 && !keep_nyq) ? 0.0 : kfac * double(i - ((i > n / 2) ? n : 0));
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
     const int z0 = (blockIdx.x - a * tiles_per_a) * T;
     const int iz = z0 + line;
     const bool line_valid = iz < A.nz;
-    const ptrdiff_t ooff = ptrdiff_t(a) * A.out_as + iz;
+    const ptrdiff_t ooff = ptrdiff_t(a) * A.out_as + zline_off(iz, A.out_zb, A.out_zbs);
     // address of output position k (routed to the owning rank's buffer for slab-decomposed passes)
     auto optr = [&](int k) -> double2* {
         if (A.out_blk > 0) {
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(P::NTHREADS) strided_pass_kernel(StridedArgs A
         term(A.f.a2, A.f.b2, A.f.c2);
     }
 
-    const double2* ibase = A.in + ptrdiff_t(a) * A.in_as + iz;
+    const double2* ibase = A.in + ptrdiff_t(a) * A.in_as + zline_off(iz, A.in_zb, A.in_zbs);
     const int hin = A.n_in / 2;
     const int hout = A.n_out / 2;
 

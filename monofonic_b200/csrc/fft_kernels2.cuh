@@ -64,7 +64,7 @@ MFB_D void strided2_tile(const StridedArgs& A, const double2* __restrict__ tw, d
     const int q = tid / T;
     const int iz = z0 + line;
     const bool line_valid = iz < A.nz;
-    const ptrdiff_t ooff = ptrdiff_t(a) * A.out_as + iz;
+    const ptrdiff_t ooff = ptrdiff_t(a) * A.out_as + zline_off(iz, A.out_zb, A.out_zbs);
     const bool routed = A.out_blk > 0;
     auto optr = [&](int k) -> double2* {
         if (routed) {
@@ -116,7 +116,7 @@ MFB_D void strided2_tile(const StridedArgs& A, const double2* __restrict__ tw, d
             term(A.f.a1, A.f.b1, A.f.c1);
             term(A.f.a2, A.f.b2, A.f.c2);
         }
-        const double2* gin = A.in + ptrdiff_t(a) * A.in_as + iz;
+        const double2* gin = A.in + ptrdiff_t(a) * A.in_as + zline_off(iz, A.in_zb, A.in_zbs);
         const ptrdiff_t gstep = ptrdiff_t(M) * A.in_ps;
         const bool use_f = A.f.enabled != 0, f_imag = A.f.imag != 0, inv = A.inverse != 0;
         // global loads of one butterfly (zero legs are not loaded)

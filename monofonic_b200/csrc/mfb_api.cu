@@ -220,7 +220,9 @@ template <class K> void optin_smem(K kernel, size_t bytes, bool& done) {
 // ------------------------------------------------------------------------------------------
 // kernel launchers
 // ------------------------------------------------------------------------------------------
+static int* g_query_T = nullptr;   // non-null: launch_strided only reports the tile height (lines) of the plan it would use
 template <class P> void launch_strided_t(const StridedArgs& a, int role) {
+    if (g_query_T) { *g_query_T = P::T; return; }
     static bool done = false;
     optin_smem(strided_pass_kernel<P>, P::SMEM_BYTES, done);
     const int tiles = (a.nz + P::T - 1) / P::T;
@@ -273,6 +275,7 @@ template <class P> void launch_strided_t(const StridedArgs& a, int role) {
     X(3072, 128, 2, 2, 12, 16, 16)
 
 template <class P, int MODE, int MINB> void launch_strided2_t(const StridedArgs& a, int role) {
+    if (g_query_T) { *g_query_T = P::T; return; }
     static bool done = false;
     optin_smem(strided2_kernel<P, MODE, MINB>, P::SMEM_BYTES, done);
     const int tiles = (a.nz + P::T - 1) / P::T;
@@ -331,6 +334,26 @@ static bool launch_strided2(int n, const StridedArgs& a, int role) {
     }
 }
 
+void launch_strided(int n, const StridedArgs& a, int role);
+// tile height (adjacent k_z lines per CTA) of the plan launch_strided picks for this pass
+static int strided_tile_lines(int n, const StridedArgs& a) {
+    int T = 0;
+    g_query_T = &T;
+    try { launch_strided(n, a, ROLE_ELEMENTWISE); } catch (...) { g_query_T = nullptr; throw; }
+    g_query_T = nullptr;
+    return T;
+}
+// z-blocked chunk layout for a routed pass and its consumer: block height = the producer's tile height, if the line count
+// allows it (returns 0 otherwise: plain layout).  Sets the producer's output fields; the consumer uses consumer_blocked().
+static int route_blocked(StridedArgs& prod, int n, int nlines, int blk) {
+    if (!g_ctx.exchange_blocked) return 0;
+    const int T = strided_tile_lines(n, prod);
+    if (T <= 1 || nlines % T != 0 || prod.nz % T != 0) return 0;
+    prod.out_zb = T;
+    prod.out_ps = T;                              // consecutive positions of a tile: adjacent T-line segments
+    prod.out_zbs = ptrdiff_t(blk) * T;            // next z block of the same a-index
+    return T;
+}
 void launch_strided(int n, const StridedArgs& a, int role) {
     if (g_ctx.strided_v2 && launch_strided2(n, a, role)) return;
     switch (n) {
@@ -1326,6 +1349,7 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "conv_own_accumulator") g_ctx.conv_own_accumulator = value != 0;  // 0: as if HBM were tight
     else if (std::string(name) == "sources_v2") g_ctx.sources_v2 = value != 0;           // 0: per-product source stage (ConvGroup)
     else if (std::string(name) == "fused_readout") g_ctx.fused_readout = value != 0;     // 0: c2r and lattice read-out as two passes
+    else if (std::string(name) == "exchange_blocked") g_ctx.exchange_blocked = value != 0; // 0: plain [..][position][kz] exchange chunks
     else if (std::string(name) == "y_pad_tile4") g_ctx.y_pad_tile4 = value != 0;         // 0: 8-line tiles for the padded y passes at n = 1536
     else if (std::string(name) == "zm_prefetch") g_ctx.zm_prefetch = value != 0;         // 0: direct-load multi-product z pass
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)

@@ -52,6 +52,7 @@ struct mfb_conv_slot {
     int pinned;
     long stamp;
     int lent;           // carved from the lender's particle arrays (a streamed hand-off copy may still be reading it)
+    int zb;             // slab mode: z-block height of the exchange layout the buffer was written with (0: plain)
 };
 constexpr int MFB_CONV_MAX_SLOTS = 16;
 
@@ -154,6 +155,7 @@ struct Context {
     bool strided_v2 = true;  // compile-time pad / truncate specialisations of the strided pass (fft_kernels2.cuh); 0: general kernel
     bool conv_own_accumulator = true;  // tests: 0 makes mfb_conv_create behave as under memory pressure
     bool conv_grouping = true;  // sum the products of one target before the forward passes (needs mfb_conv::Wacc)
+    bool exchange_blocked = true;  // source stage on slabs: z-blocked exchange chunks (contiguous peer stores per tile)
     bool y_pad_tile4 = false;   // padded y passes at n = 1536: two 4-line tiles per SM instead of one 8-line tile (no gain in the pipeline)
     bool fused_readout = true;  // sc loads handed a k-space field: lattice read-out as the epilogue of the c2r pass
     bool zm_prefetch = true;  // multi-product z pass: operand rows staged by TMA bulk copies (0: direct loads)

@@ -132,7 +132,7 @@ static int conv_enter_slots(mfb_conv* c, int want_slots, int min_slots, size_t w
     const size_t U = conv_slot_elems(c) * sizeof(double2);
     auto add = [&](double2* p, int owned, int xslot, int lent = 0) {
         mfb_conv_slot& s = c->xs[c->nxs++];
-        s.p = p; s.owned = owned; s.xslot = xslot; s.g = nullptr; s.mx = 0; s.valid = 0; s.pinned = 0; s.stamp = 0; s.lent = lent;
+        s.p = p; s.owned = owned; s.xslot = xslot; s.g = nullptr; s.mx = 0; s.valid = 0; s.pinned = 0; s.stamp = 0; s.lent = lent; s.zb = 0;
     };
     const size_t margin = size_t(3) << 29;   // 1.5 GiB stay free
     size_t lent_left = 0; char* lent_p = nullptr;
@@ -333,6 +333,7 @@ struct S2Runner {
             set_operand_factor(a, c, o, s1);
             a.pos_axis = 0; a.a_axis = 1;
             route(a, x, p0l, nzin, ptrdiff_t(p0l) * nzin);                      // chunk layout [ky_loc][x_loc][kz]
+            c->xs[i].zb = route_blocked(a, P0, nzin, p0l);                       // ... or z-blocked [ky_loc][kz/T][x_loc][T]
             launch_strided(P0, a, ROLE_CONV_X_BWD);
             end_exchange(x);                                                     // slot: [ky][x_loc][kz]
         } else {
@@ -354,7 +355,13 @@ struct S2Runner {
         const double2* X = c->xs[slot].p;
         StridedArgs b;
         if (c->dist) {
-            b = plain_strided(X + ptrdiff_t(x0) * nzin, dst, ptrdiff_t(p0l) * nzin, nzin, cx, nzin, P1, 1);
+            const int zb = c->xs[slot].zb;
+            if (zb > 0) {   // z-blocked exchange layout [ky][kz/zb][x_loc][zb]
+                b = plain_strided(X + ptrdiff_t(x0) * zb, dst, ptrdiff_t(p0l) * nzin, zb, cx, nzin, P1, 1);
+                b.in_zb = zb; b.in_zbs = ptrdiff_t(p0l) * zb;
+            } else {
+                b = plain_strided(X + ptrdiff_t(x0) * nzin, dst, ptrdiff_t(p0l) * nzin, nzin, cx, nzin, P1, 1);
+            }
             b.out_ps = nzin; b.out_as = ptrdiff_t(P1) * nzin;
         } else {
             b = plain_strided(X + ptrdiff_t(x0) * N1 * nzin, dst, nzin, 0, cx, nzin, P1, 1);
@@ -402,6 +409,7 @@ struct S2Runner {
         require(cx >= 1, "internal: chunk workspace of the source stage is too small");
         double2* wout = c->chunk + bases.size() * size_t(cx) * pe;
         std::vector<Exchange> xch(nt);
+        std::vector<int> yzb(nt, 0);   // z-block height of each target's exchange layout
         if (c->dist)
             for (int it = 0; it < nt; ++it) xch[it] = slot_exchange(c->xs[yout[it]].xslot, size_t(p0l) * T[it]->out->nloc1 * nzin);
         for (int x0 = 0; x0 < p0l; x0 += int(cx)) {
@@ -441,6 +449,9 @@ struct S2Runner {
                     Exchange x = xch[it];
                     for (int s = 0; s < MFB_MAX_RANKS; ++s) if (x.base[s]) x.base[s] += ptrdiff_t(x0) * l1 * nzin;
                     route(d, x, l1, nzin, ptrdiff_t(l1) * nzin);                    // chunk layout [x_loc][ky_loc][kz]
+                    const int zb = route_blocked(d, P1, nzin, l1);                  // ... or z-blocked [x_loc][kz/T][ky_loc][T]
+                    require(x0 == 0 || zb == yzb[it], "internal: exchange layout changed inside a loop");
+                    yzb[it] = zb;
                     launch_strided(P1, d, ROLE_CONV_Y_FWD);
                 } else {
                     StridedArgs d = plain_strided(wout, c->xs[yout[it]].p + ptrdiff_t(x0) * N1 * nzin, nzin, 0, cxx, nzin, P1, 0);
@@ -462,6 +473,7 @@ struct S2Runner {
                 StridedArgs e = plain_strided(xch[it].recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * nzin, nzin, l1,
                                               (op == OP_ASSIGN) ? nzc : nzin, P0, 0);
                 e.out_ps = nzc; e.out_as = ptrdiff_t(N0) * nzc;
+                if (yzb[it] > 0) { e.in_as = yzb[it]; e.in_zb = yzb[it]; e.in_zbs = ptrdiff_t(l1) * yzb[it]; }
                 e.nz_fft = nzin;
                 e.n_out = N0;
                 e.scale = unpad_scale;
@@ -572,7 +584,7 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
     const size_t pe = size_t(c->np[1]) * (c->n[2] / 2);
     const int p0l = c->p0loc;
     const int kmax = order > 2 ? 13 : 7;                       // base fields of the widest loop + the target chunk
-    const long cx_want = std::max<long>(1, std::min<long>(p0l, std::max<long>(8, p0l / 32)));
+    const long cx_want = std::max<long>(1, std::min<long>(p0l, std::max<long>(32, p0l / 32)));   // >= 32 planes: few, large launches
     // 8 slots: everything in 4 loops (3LPT).  7: one target per loop.  5-6: targets are split (more forward passes).
     const int min_slots = order > 2 ? 5 : 4, want_slots = order > 2 ? 8 : 4;
     if (c->dist && D().nxbuf < min_slots) return false;

@@ -784,6 +784,9 @@ def run_2048(M, lib, torch, dist, local_rank, stream, barrier, max_over_ranks, p
         M.synchronize()
         barrier()
         MD.shutdown()
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()   # what torch cached for the 1024^3 run's checks counts as free memory for the slot workspace
         lib = MD.init(local_rank, n, True, lpt_order=3)
         B = Bench(M, lib, torch, dist, local_rank, n, 3, "sc")
         B.make_noise(); B.upload_noise()

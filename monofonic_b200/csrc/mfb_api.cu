@@ -492,30 +492,37 @@ static void route(StridedArgs& a, const Exchange& x, int blk, ptrdiff_t ps, ptrd
     for (int s = 0; s < MFB_MAX_RANKS; ++s) a.out_peer[s] = x.base[s];
 }
 
+// z pitch of the exchange chunks of the 3-D FFTs: N/2+1 lines rounded up to a multiple of 8, so that the 128-byte segments
+// an 8-line tile stores into a peer's buffer start on 128-byte boundaries (with the grid's own pitch of N/2+1 = 513 elements
+// every segment straddled two lines: the routed x pass sustained 47 % of the NVLink rate, profiles/r02_bench_3lpt1024_n8_v2.json)
+static int dist_zpitch(int nzc) { return (nzc + 7) & ~7; }
+
 // slab-decomposed r2c: z (local rows), y (local planes) -> exchange -> x.   Replaces fftw_mpi_plan_dft_r2c_3d with
 // FFTW_MPI_TRANSPOSED_OUT (src/grid_fft.cc:125-128): the result is [ky_loc][kx][kz].
 static void dist_fft_forward(mfb_grid* g, double norm) {
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc, l0 = g->nloc0, l1 = g->nloc1;
+    const int zp = dist_zpitch(nzc);
     launch_z(g->n[2], 1, g->d, g->pitch, long(l0) * n1, norm);
-    Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+    Exchange x = begin_exchange(size_t(l0) * l1 * zp);
     StridedArgs a = plain_strided(c, nullptr, nzc, ptrdiff_t(n1) * nzc, l0, nzc, n1, 0);
-    route(a, x, l1, nzc, ptrdiff_t(l1) * nzc);                         // chunk layout [x_loc][ky_loc][kz]
+    route(a, x, l1, zp, ptrdiff_t(l1) * zp);                           // chunk layout [x_loc][ky_loc][kz (pitch zp)]
     launch_strided(n1, a, ROLE_FFT_Y);
     end_exchange(x);                                                    // recv: [x][ky_loc][kz]
-    StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l1) * nzc, nzc, l1, nzc, n0, 0);
+    StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l1) * zp, zp, l1, nzc, n0, 0);
     b.out_ps = nzc; b.out_as = ptrdiff_t(n0) * nzc;                     // -> [ky_loc][kx][kz]
     launch_strided(n0, b, ROLE_FFT_X);
 }
 static void dist_fft_backward(mfb_grid* g, double norm, const ZReadout* ro = nullptr) {
     double2* c = reinterpret_cast<double2*>(g->d);
     const int n0 = g->n[0], n1 = g->n[1], nzc = g->nzc, l0 = g->nloc0, l1 = g->nloc1;
-    Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+    const int zp = dist_zpitch(nzc);
+    Exchange x = begin_exchange(size_t(l0) * l1 * zp);
     StridedArgs a = plain_strided(c, nullptr, nzc, ptrdiff_t(n0) * nzc, l1, nzc, n0, 1);
-    route(a, x, l0, nzc, ptrdiff_t(l0) * nzc);                         // chunk layout [ky_loc][x_loc][kz]
+    route(a, x, l0, zp, ptrdiff_t(l0) * zp);                           // chunk layout [ky_loc][x_loc][kz (pitch zp)]
     launch_strided(n0, a, ROLE_FFT_X);
     end_exchange(x);                                                    // recv: [ky][x_loc][kz]
-    StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l0) * nzc, nzc, l0, nzc, n1, 1);
+    StridedArgs b = plain_strided(x.recv, c, ptrdiff_t(l0) * zp, zp, l0, nzc, n1, 1);
     b.out_ps = nzc; b.out_as = ptrdiff_t(n1) * nzc;                     // -> [x_loc][y][kz]
     launch_strided(n1, b, ROLE_FFT_Y);
     launch_z(g->n[2], 0, g->d, g->pitch, long(l0) * n1, norm, ro);
@@ -763,15 +770,16 @@ static void naive_backward_operand(mfb_conv* c, const Operand& o, mfb_grid* dst)
         // slabs: the operand factor rides on the x pass of the transposed layout [ky_loc][kx][kz], whose output is routed to the
         // ranks owning the x planes; then y and z on the local planes (dist_fft_backward, out of place)
         const int l0 = dst->nloc0, l1 = o.g->nloc1;
-        Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+        const int zp = dist_zpitch(nzc);
+        Exchange x = begin_exchange(size_t(l0) * l1 * zp);
         StridedArgs a = plain_strided(reinterpret_cast<const double2*>(o.g->d), nullptr, nzc, ptrdiff_t(N0) * nzc, l1, nzc, N0, 1);
         set_operand_factor(a, c, o, 1.0);
         a.pos_axis = 0; a.a_axis = 1;
         a.a_off = o.g->off1;
-        route(a, x, l0, nzc, ptrdiff_t(l0) * nzc);                         // chunk layout [ky_loc][x_loc][kz]
+        route(a, x, l0, zp, ptrdiff_t(l0) * zp);                           // chunk layout [ky_loc][x_loc][kz (pitch zp)]
         launch_strided(N0, a, ROLE_FFT_X);
         end_exchange(x);                                                    // recv: [ky][x_loc][kz]
-        StridedArgs b = plain_strided(x.recv, d, ptrdiff_t(l0) * nzc, nzc, l0, nzc, N1, 1);
+        StridedArgs b = plain_strided(x.recv, d, ptrdiff_t(l0) * zp, zp, l0, nzc, N1, 1);
         b.out_ps = nzc; b.out_as = ptrdiff_t(N1) * nzc;                     // -> [x_loc][y][kz]
         launch_strided(N1, b, ROLE_FFT_Y);
         launch_z(N2, 0, dst->d, dst->pitch, long(l0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
@@ -797,12 +805,13 @@ static void naive_forward_output(mfb_conv* c, mfb_grid* src, mfb_grid* out, int 
     if (src->dist) {   // dist_fft_forward with the output operator on the last (x) pass
         const int l0 = src->nloc0, l1 = out->nloc1;
         launch_z(N2, 1, src->d, src->pitch, long(l0) * N1, 1.0 / std::sqrt(double(N0) * N1 * N2));
-        Exchange x = begin_exchange(size_t(l0) * l1 * nzc);
+        const int zp = dist_zpitch(nzc);
+        Exchange x = begin_exchange(size_t(l0) * l1 * zp);
         StridedArgs a = plain_strided(d, nullptr, nzc, ptrdiff_t(N1) * nzc, l0, nzc, N1, 0);
-        route(a, x, l1, nzc, ptrdiff_t(l1) * nzc);                         // chunk layout [x_loc][ky_loc][kz]
+        route(a, x, l1, zp, ptrdiff_t(l1) * zp);                           // chunk layout [x_loc][ky_loc][kz (pitch zp)]
         launch_strided(N1, a, ROLE_FFT_Y);
         end_exchange(x);                                                    // recv: [x][ky_loc][kz]
-        StridedArgs e = plain_strided(x.recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * nzc, nzc, l1, nzc, N0, 0);
+        StridedArgs e = plain_strided(x.recv, reinterpret_cast<double2*>(out->d), ptrdiff_t(l1) * zp, zp, l1, nzc, N0, 0);
         e.out_ps = nzc; e.out_as = ptrdiff_t(N0) * nzc;                     // -> [ky_loc][kx][kz]
         e.op = op; e.alpha = alpha;
         launch_strided(N0, e, ROLE_FFT_X);
@@ -1390,7 +1399,7 @@ int mfb_profile_get(int role, double* ms, long long* count, double* bytes) {
 // ---------------------------------------------------------------- slab decomposition over GPUs (one process per GPU)
 size_t mfb_dist_xbuf_bytes(const int n[3], int with_conv, int nranks) {
     const size_t P = size_t(nranks > 0 ? nranks : 1);
-    size_t plain = size_t(n[0]) * n[1] * (n[2] / 2 + 1) / P;
+    size_t plain = size_t(n[0]) * n[1] * size_t((n[2] / 2 + 1 + 7) & ~7) / P;   // z pitch of the FFT exchange chunks: dist_zpitch
     size_t conv = with_conv ? size_t(3 * n[0] / 2) * n[1] * (n[2] / 2) / P : 0;
     size_t e = plain > conv ? plain : conv;
     if (e < 64) e = 64;

@@ -16,6 +16,7 @@
 #include "fft_kernels2.cuh"
 #include "fft_kernels_z2.cuh"
 #include "fft_kernels_zm.cuh"
+#include "fft_kernels_zf.cuh"
 #include "grid_ops.cuh"
 #include "mfb_internal.h"
 #include "../../include/mfb200.h"
@@ -1361,6 +1362,8 @@ int mfb_set_option(const char* name, int value) {
     else if (std::string(name) == "exchange_blocked") g_ctx.exchange_blocked = value != 0; // 0: plain [..][position][kz] exchange chunks
     else if (std::string(name) == "y_pad_tile4") g_ctx.y_pad_tile4 = value != 0;         // 0: 8-line tiles for the padded y passes at n = 1536
     else if (std::string(name) == "zm_prefetch") g_ctx.zm_prefetch = value != 0;         // 0: direct-load multi-product z pass
+    else if (std::string(name) == "sources_shared") g_ctx.sources_shared = value != 0;   // 0: multi-product z pass in every stage
+    else if (std::string(name) == "sources_alias") g_ctx.sources_alias = value != 0;     // 0: shared last stage takes a slot per target
     else if (std::string(name) == "sources_max_slots") g_ctx.sources_max_slots = value;  // cap the slot workspace (tests)
     else if (std::string(name) == "sources_chunk") g_ctx.sources_chunk = value;          // cap the x planes per chunk (tests)
     else throw std::runtime_error(std::string("unknown option ") + name);

@@ -160,6 +160,8 @@ struct Context {
     bool fused_readout = true;  // sc loads handed a k-space field: lattice read-out as the epilogue of the c2r pass
     bool zm_prefetch = true;  // multi-product z pass: operand rows staged by TMA bulk copies (0: direct loads)
     bool sources_v2 = true;  // mfb_lpt_sources: shared x passes + multi-product z pass on the slot workspace (mfb_sources2.cuh)
+    bool sources_shared = true;  // 3LPT: stages A and C as shared-field loops (z_fields_kernel: every Hessian component transformed once per row)
+    bool sources_alias = true;   // ... whose last stage lets the targets overwrite consumed X planes on a single slab (0: needs 10 slots)
     int sources_max_slots = 0;   // tests: cap the slot workspace (0: what HBM allows)
     int sources_chunk = 0;       // tests: cap the x planes per chunk (0: what the chunk workspace allows)
     // optional per-role device timing (cudaEvents on `stream` around every launch)

@@ -65,6 +65,54 @@ static void launch_zmulti(int n, const ZmArgs& a) {
     }
 }
 
+// shared-field z pass (z_fields_kernel, fft_kernels_zf.cuh): N, threads per group (three groups per CTA, one CTA per SM),
+// radices as above.  n = 3072 has no plan: six work lines of 55 KB do not fit one SM (3LPT 2048^3 keeps the multi-product pass).
+#define MFB_FOR_EACH_PLANZF(X)   \
+    X(48, 32, 6, 8)              \
+    X(96, 32, 12, 8)             \
+    X(192, 32, 6, 4, 8)          \
+    X(384, 64, 6, 8, 8)          \
+    X(768, 64, 12, 8, 8)         \
+    X(1536, 128, 12, 16, 8)
+constexpr int ZF_GROUPS = 3;
+
+static bool zfields_has_plan(int n) {
+    switch (n) {
+#define X(N_, ...) case N_:
+        MFB_FOR_EACH_PLANZF(X)
+#undef X
+        return true;
+        default: return false;
+    }
+}
+template <class P, int NTG, int PROG> void launch_zfields_t(const ZfArgs& a, double bytes) {
+    static bool done = false;
+    constexpr size_t smem = z_fields_smem<P, ZF_GROUPS, PROG, true>();
+    optin_smem(z_fields_kernel<P, NTG, ZF_GROUPS, PROG, true>, smem, done);
+    if (a.nrows <= 0) return;
+    const unsigned grid = unsigned(std::min<long>(a.nrows, g_ctx.num_sms));   // persistent: one CTA per SM walks the rows
+    const double2* tw = twiddles2<P>();
+    RoleScope rs(ROLE_CONV_Z, bytes);
+    MFB_LAUNCH((z_fields_kernel<P, NTG, ZF_GROUPS, PROG, true>), grid, NTG * ZF_GROUPS, smem, g_ctx.stream, a, tw);
+    check_launch("z_fields_kernel");
+}
+static void launch_zfields(int n, int prog, const ZfArgs& a) {
+    // algorithmic bytes: every base row read once + one row written per target
+    const int nf = prog == ZF_PROG_A ? ZfProg<ZF_PROG_A>::NF : ZfProg<ZF_PROG_C>::NF;
+    const int nt = prog == ZF_PROG_A ? ZfProg<ZF_PROG_A>::NT : ZfProg<ZF_PROG_C>::NT;
+    const double bytes = double(a.nrows) * double(n / 3) * 16.0 * double(nf + nt);
+    switch (n) {
+#define X(N_, NTG_, ...)                                                                                   \
+    case N_:                                                                                               \
+        if (prog == ZF_PROG_A) launch_zfields_t<Plan<N_, NTG_, 2, __VA_ARGS__>, NTG_, ZF_PROG_A>(a, bytes);  \
+        else launch_zfields_t<Plan<N_, NTG_, 2, __VA_ARGS__>, NTG_, ZF_PROG_C>(a, bytes);                    \
+        return;
+        MFB_FOR_EACH_PLANZF(X)
+#undef X
+        default: throw std::runtime_error("unsupported padded length " + std::to_string(n) + " for the shared-field z pass");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ workspace modes
 static size_t conv_slot_elems(const mfb_conv* c) { return size_t(c->p0loc) * c->n[1] * (c->n[2] / 2); }
 
@@ -218,6 +266,11 @@ static S2Operand s2_hess(mfb_grid* g, int a, int b) { S2Operand o; o.n = 1; o.t[
 // f,ab + sgn * f,cd   (convolve_SumOfHessians / convolve_DifferenceOfHessians, include/convolution.hh:214-274)
 static S2Operand s2_hess2(mfb_grid* g, int a, int b, int cc, int d, double sgn) {
     S2Operand o; o.n = 2; o.t[0] = s2_hess_term(g, a, b, -1.0); o.t[1] = s2_hess_term(g, cc, d, -sgn); return o;
+}
+// the six Hessian components of a potential in the field order of the shared-field programs: xx yy zz xy xz yz
+static std::vector<S2Term> s2_hess_fields(mfb_grid* g) {
+    return {s2_hess_term(g, 0, 0, -1.0), s2_hess_term(g, 1, 1, -1.0), s2_hess_term(g, 2, 2, -1.0),
+            s2_hess_term(g, 0, 1, -1.0), s2_hess_term(g, 0, 2, -1.0), s2_hess_term(g, 1, 2, -1.0)};
 }
 static S2Operand s2_plain(mfb_grid* g) { S2Operand o; o.n = 1; o.t[0] = S2Term{g, 0, 0, 0, 1.0}; o.t[1] = o.t[0]; return o; }
 static bool s2_same_term(const S2Term& x, const S2Term& y) {
@@ -379,7 +432,10 @@ struct S2Runner {
     }
 
     // ---- one x-plane loop over a set of targets that share their base fields
-    void run_loop(S2Target* const* T, int nt) {
+    // prog >= 0 (shared-field loop): the z pass transforms every base field once and forms ALL targets of the loop
+    // (z_fields_kernel); `fields` lists the program's real fields in its order.  alias_out: the targets' forward-y output goes
+    // into the x-planes of X buffers that the chunk's backward y passes have already consumed (single slab, last stage).
+    void run_loop(S2Target* const* T, int nt, int prog = -1, const std::vector<S2Term>* fields = nullptr, bool alias_out = false) {
         // base fields and X buffers of the loop
         std::vector<S2Base> bases;
         auto base_index = [&](const S2Term& t) -> int {
@@ -388,7 +444,9 @@ struct S2Runner {
             bases.push_back(S2Base{t.g, t.mx, t.my});
             return int(bases.size()) - 1;
         };
-        for (int it = 0; it < nt; ++it)
+        if (prog >= 0)
+            for (const S2Term& t : *fields) base_index(t);
+        for (int it = 0; it < nt && prog < 0; ++it)
             for (const S2Product& p : T[it]->prods) {
                 require(int(T[it]->prods.size()) <= ZM_MAXP, "internal: too many products for one target");
                 for (int k = 0; k < p.a.n; ++k) base_index(p.a.t[k]);
@@ -399,15 +457,22 @@ struct S2Runner {
         std::vector<int> xslot(bases.size());
         for (size_t i = 0; i < bases.size(); ++i) xslot[i] = ensure_x(bases[i].g, bases[i].mx);
         std::vector<int> yout(nt);
-        for (int it = 0; it < nt; ++it) { yout[it] = take_slot(); c->xs[yout[it]].pinned = 1; c->xs[yout[it]].valid = 0; }
+        if (alias_out) {
+            std::vector<int> distinct;
+            for (int sl : xslot) if (std::find(distinct.begin(), distinct.end(), sl) == distinct.end()) distinct.push_back(sl);
+            require(!c->dist && int(distinct.size()) >= nt, "internal: not enough X buffers to take the targets of the loop");
+            for (int it = 0; it < nt; ++it) yout[it] = distinct[it];
+        } else {
+            for (int it = 0; it < nt; ++it) { yout[it] = take_slot(); c->xs[yout[it]].pinned = 1; c->xs[yout[it]].valid = 0; }
+        }
         // chunk geometry
         const size_t pe = plane_elems();
-        const size_t nbuf = bases.size() + 1;
+        const size_t nbuf = bases.size() + (prog >= 0 ? size_t(nt) : 1);
         long cx = long(c->chunk_elems / (nbuf * pe));
         if (g_ctx.sources_chunk > 0 && cx > g_ctx.sources_chunk) cx = g_ctx.sources_chunk;
         if (cx > p0l) cx = p0l;
         require(cx >= 1, "internal: chunk workspace of the source stage is too small");
-        double2* wout = c->chunk + bases.size() * size_t(cx) * pe;
+        auto wout_of = [&](int it) -> double2* { return c->chunk + (bases.size() + (prog >= 0 ? size_t(it) : 0)) * size_t(cx) * pe; };
         std::vector<Exchange> xch(nt);
         std::vector<int> yzb(nt, 0);   // z-block height of each target's exchange layout
         if (c->dist)
@@ -415,7 +480,26 @@ struct S2Runner {
         for (int x0 = 0; x0 < p0l; x0 += int(cx)) {
             const int cxx = int(std::min<long>(cx, p0l - x0));
             for (size_t i = 0; i < bases.size(); ++i) ypass(xslot[i], bases[i].my, x0, cxx, c->chunk + i * size_t(cx) * pe);
+            if (prog >= 0) {
+                ZfArgs zf;
+                memset(&zf, 0, sizeof(zf));
+                for (size_t i = 0; i < fields->size(); ++i) {
+                    const S2Term& t = (*fields)[i];
+                    zf.f[i].p = c->chunk + size_t(base_index(t)) * size_t(cx) * pe;
+                    zf.f[i].c = t.c; zf.f[i].e = t.e;
+                }
+                for (int it = 0; it < nt; ++it) zf.out[it] = wout_of(it);
+                zf.in_pitch = zf.out_pitch = nzin;
+                zf.nrows = long(cxx) * P1;
+                zf.kfz = 2.0 * M_PI / c->L[2];
+                zf.coef[0] = -5.0 / 7.0; zf.coef[1] = 10.0 / 7.0;   // 3b (src/ic_generator.cc:533-538)
+                launch_zfields(P2, prog, zf);
+                ++n_z;
+                for (int it = 0; it < nt; ++it) c->nconv += int(T[it]->prods.size());
+            }
             for (int it = 0; it < nt; ++it) {
+                double2* wout = wout_of(it);
+                if (prog < 0) {
                 ZmArgs za;
                 memset(&za, 0, sizeof(za));
                 za.nprod = int(T[it]->prods.size());
@@ -441,6 +525,7 @@ struct S2Runner {
                 launch_zmulti(P2, za);
                 ++n_z;
                 c->nconv += za.nprod;
+                }
                 // forward y pass of the chunk, P1 -> N1
                 if (c->dist) {
                     const int l1 = T[it]->out->nloc1;
@@ -496,9 +581,38 @@ struct S2Runner {
             }
             invalidate(out);   // the target changed: X buffers made from its old contents are stale
             c->xs[yout[it]].pinned = 0;
+            if (alias_out) c->xs[yout[it]].valid = 0;   // the X buffer was overwritten by the target
         }
         for (int i = 0; i < c->nxs; ++i) c->xs[i].pinned = 0;
         ++n_loops;
+    }
+
+    // A whole stage as ONE shared-field loop, if the program has a plan for this grid and the slots are there: the X buffers
+    // of its base fields + one slot per target (none when the targets may overwrite consumed X planes).  Returns false if not
+    // (the caller runs the stage product by product: run_stage).
+    bool run_shared(std::vector<S2Target>& st, int prog, const std::vector<S2Term>& fields, bool last_stage, bool may_restrict) {
+        if (!g_ctx.sources_shared || !zfields_has_plan(P2)) return false;
+        if (may_restrict && free_of_handoff() < c->nxs) return false;   // hand-off copies pending: leave the lent slots alone
+        XSet xs;
+        for (const S2Term& t : fields) {
+            const std::pair<const mfb_grid*, int> key(t.g, t.mx);
+            if (std::find(xs.begin(), xs.end(), key) == xs.end()) xs.push_back(key);
+        }
+        const int nt = int(st.size());
+        const bool alias_out = last_stage && !c->dist && int(xs.size()) >= nt && g_ctx.sources_alias;
+        if (int(xs.size()) + (alias_out ? 0 : nt) > c->nxs) return false;
+        std::vector<S2Base> bases;
+        for (const S2Term& t : fields) {
+            bool seen = false;
+            for (const S2Base& b : bases) seen = seen || (b.g == t.g && b.mx == t.mx && b.my == t.my);
+            if (!seen) bases.push_back(S2Base{t.g, t.mx, t.my});
+        }
+        if (c->chunk_elems / ((bases.size() + size_t(nt)) * plane_elems()) < 1) return false;
+        limit = c->nxs;
+        std::vector<S2Target*> ptr(nt);
+        for (int k = 0; k < nt; ++k) ptr[k] = &st[k];
+        run_loop(ptr.data(), nt, prog, &fields, alias_out);
+        return true;
     }
 
     // X buffers (grid, mx) a set of products needs, added to `set`
@@ -583,10 +697,12 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
     if (c->naive || !g_ctx.sources_v2 || order < 2) return false;
     const size_t pe = size_t(c->np[1]) * (c->n[2] / 2);
     const int p0l = c->p0loc;
-    const int kmax = order > 2 ? 13 : 7;                       // base fields of the widest loop + the target chunk
+    // base fields of the widest loop + the target chunk(s): 12 + 1 (multi-product pass), 12 + 4 (shared-field last stage)
+    const int kmax = order > 2 ? (g_ctx.sources_shared ? 16 : 13) : 7;
     const long cx_want = std::max<long>(1, std::min<long>(p0l, std::max<long>(32, p0l / 32)));   // >= 32 planes: few, large launches
     // 8 slots: everything in 4 loops (3LPT).  7: one target per loop.  5-6: targets are split (more forward passes).
-    const int min_slots = order > 2 ? 5 : 4, want_slots = order > 2 ? 8 : 4;
+    // (10: the shared last stage with a slot per target - what slabs need; a single slab lets the targets overwrite consumed X planes)
+    const int min_slots = order > 2 ? 5 : 4, want_slots = order > 2 ? ((g_ctx.sources_shared && !g_ctx.sources_alias) ? 10 : 8) : 4;
     if (c->dist && D().nxbuf < min_slots) return false;
     if (!conv_enter_slots(c, want_slots, min_slots, size_t(kmax) * cx_want * pe, size_t(kmax) * pe)) return false;
     // lent particle arrays: streamed hand-off copies of the previous run must have drained before their memory is written.
@@ -626,7 +742,8 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
             st[3].prods = {s2_prod(H(phi, 1, 2), H(phi, 1, 2), 1.0)};
             st[4].prods = {s2_prod(H(phi, 0, 2), H(phi, 0, 2), 1.0)};
         }
-        R.run_stage(st, true);
+        // third order: the six Hessian components of phi transformed once for all five targets (z_fields_kernel, program A)
+        if (!(order > 2 && R.run_shared(st, ZF_PROG_A, s2_hess_fields(phi), false, true))) R.run_stage(st, true);
     }
     if (lam) {
         KGeom k = kgeom(phi2);
@@ -663,7 +780,10 @@ static bool lpt_sources_v2(mfb_conv* c, int order, double Dplus, mfb_grid* phi, 
                            s2_prod(H(phi, p, q), s2_hess2(phi2, p, p, q, q, -1.0), 1.0),
                            s2_prod(H(phi2, p, q), s2_hess2(phi, p, p, q, q, -1.0), -1.0)};
             }
-            R.run_stage(st);
+            // the twelve Hessian components of phi and phi2 transformed once for all four targets (program C)
+            std::vector<S2Term> fields = s2_hess_fields(phi), f2 = s2_hess_fields(phi2);
+            fields.insert(fields.end(), f2.begin(), f2.end());
+            if (!R.run_shared(st, ZF_PROG_C, fields, true, false)) R.run_stage(st);
         }
         grid_laplacian_pow(phi3, -1, -g3);   // :539 and the growth factor of :566 in one sweep
         for (int d = 0; d < 3; ++d) grid_laplacian_pow(A3[d], -1, -g3c);   // :555 and :568-570

@@ -64,7 +64,8 @@ def _make_exchange_cb(lib, world, device):
 
 def pick_nslots(nbytes, n, world, free_bytes, lpt_order=3, particle_bytes_per_cell=32):
     """how many exchange buffers to put into the peer-mapped block.  The 3-D FFTs need 2 (a ping-pong pair); the shared-transform
-    source stage uses ALL of them as slots and wants 8 at 3LPT (7: one target per loop; 6, 5: targets split over several
+    source stage uses ALL of them as slots and wants 10 at 3LPT (the six X buffers of the last stage + its four targets in ONE
+    shared-field loop; 8: that stage as two multi-product loops; 7: one target per loop; 6, 5: targets split over several
     loops) and 4 at 2LPT.  The largest count is taken that leaves room for everything else of an LPT run - 8 grids, the
     particle arrays (which also serve as the chunk workspace of that stage) and a safety margin; below the minimum the
     block keeps 2 buffers and the memory goes to the per-product workspace."""
@@ -72,7 +73,7 @@ def pick_nslots(nbytes, n, world, free_bytes, lpt_order=3, particle_bytes_per_ce
         return 2
     cells = n[0] * n[1] * n[2] // world
     fixed = 8 * 8 * cells * (n[2] + 2) // n[2] + particle_bytes_per_cell * cells + (3 << 30)
-    for k in ((8, 7, 6, 5) if lpt_order > 2 else (4,)):
+    for k in ((10, 8, 7, 6, 5) if lpt_order > 2 else (4,)):
         if k * nbytes + fixed <= free_bytes:
             return k
     return 2

@@ -221,6 +221,9 @@ def main():
             assert info["path"] == (2 if v2_expected or (order == 2 and not args.borrow and lib.mfb_dist_nslots() >= 4) else 1), info
             if info["path"] == 2 and info["slots"] >= 7:
                 assert info["x_passes"] == ((10 if info["slots"] >= 8 else 11) if order > 2 else 3), info
+            if info["path"] == 2 and order > 2 and info["slots"] >= 8:
+                # shared-field loops (z_fields_kernel): the first stage with 8 slots, the last one with 10 (a slot per target)
+                assert info["loops"] == (3 if info["slots"] >= 10 else 4), info
         assert PC.relerr(MD.gather_kspace(pl.phi), ref["pots"]["phi"]) < TOL
         if order > 2:
             assert PC.relerr(MD.gather_kspace(pl.phi3), ref["pots"]["phi3"]) < 10 * TOL

@@ -20,6 +20,10 @@ struct Worker {
     std::vector<char> done;
     const std::function<void()>* body = nullptr;
     int cur = 0;
+    unsigned alive = 0;
+    // barriers of the running block: 0 is __syncthreads() (every live thread), 1..15 are PTX named barriers with an explicit
+    // thread count (bar.sync id, n).  The last arrival opens the barrier, waiting fibers yield until the generation changes.
+    struct Bar { unsigned arrived = 0, gen = 0; } bars[16];
 };
 thread_local Worker* t_worker = nullptr;
 
@@ -38,6 +42,8 @@ void run_block(Worker& w, dim3 block, const std::function<void()>& body) {
     }
     w.done.assign(nthr, 0);
     w.body = &body;
+    w.alive = nthr;
+    for (auto& b : w.bars) b = Worker::Bar();
     for (unsigned t = 0; t < nthr; ++t) {
         getcontext(&w.ctx[t]);
         w.ctx[t].uc_stack.ss_sp = w.stacks[t].get();
@@ -54,7 +60,13 @@ void run_block(Worker& w, dim3 block, const std::function<void()>& body) {
             t_threadIdx.y = (t / block.x) % block.y;
             t_threadIdx.z = t / (block.x * block.y);
             swapcontext(&w.main_ctx, &w.ctx[t]);
-            if (w.done[t]) --remaining;
+            if (w.done[t]) {
+                --remaining;
+                --w.alive;
+                // threads that have left the kernel no longer take part in __syncthreads()
+                Worker::Bar& b = w.bars[0];
+                if (b.arrived > 0 && b.arrived >= w.alive) { b.arrived = 0; ++b.gen; }
+            }
         }
     }
 }
@@ -62,7 +74,18 @@ void run_block(Worker& w, dim3 block, const std::function<void()>& body) {
 
 void sync_threads() {
     Worker* w = t_worker;
-    swapcontext(&w->ctx[w->cur], &w->main_ctx);
+    Worker::Bar& b = w->bars[0];
+    const unsigned g = b.gen;
+    if (++b.arrived >= w->alive) { b.arrived = 0; ++b.gen; return; }
+    while (b.gen == g) swapcontext(&w->ctx[w->cur], &w->main_ctx);
+}
+
+void bar_sync(int id, int count) {
+    Worker* w = t_worker;
+    Worker::Bar& b = w->bars[id & 15];
+    const unsigned g = b.gen;
+    if (++b.arrived == unsigned(count)) { b.arrived = 0; ++b.gen; return; }
+    while (b.gen == g) swapcontext(&w->ctx[w->cur], &w->main_ctx);
 }
 
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {

@@ -49,6 +49,7 @@ extern thread_local unsigned char* t_dyn_smem;
 extern dim3 g_blockDim, g_gridDim;
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void sync_threads();
+void bar_sync(int id, int count);
 
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem, F body) {

@@ -1004,6 +1004,39 @@ def check_multiply_noncubic(M, shape):
     assert relerr(out.get_kspace(), 1.5 * ref) < TOL
 
 
+def check_sources_shared_field_pass(M, shape):
+    import ctypes
+    """third-order sources on an (n0,n1,n2) grid: the shared-field z pass (z_fields_kernel - every Hessian component of phi and
+    phi2 transformed once per row, targets formed pointwise) against the multi-product z pass (one transform per product
+    operand).  Slim grids with a long z axis reach the plans of the BASELINE sizes (n2 = 1024 -> 1536-point lines)."""
+    lib = M.grid._lib()
+    L = (100.0, 100.0, 100.0)
+    rng = np.random.default_rng(int(np.sum(shape)))
+    phi0 = np.fft.rfftn(rng.standard_normal(shape)) / np.sqrt(float(np.prod(shape)))
+    res = {}
+    try:
+        for shared in (1, 0):
+            assert lib.mfb_set_option(b"sources_shared", shared) == 0
+            grids = [M.Grid_FFT(shape, L, True, M.kspace_id) for _ in range(6)]
+            phi, phi2, phi3, A3 = grids[0], grids[1], grids[2], grids[3:]
+            phi.set_kspace(phi0)
+            conv = M.OrszagConvolver(shape, L)
+            A3h = (ctypes.c_void_p * 3)(*[g._h for g in A3])
+            assert lib.mfb_lpt_sources(conv._h, 3, 0.7, phi._h, phi2._h, phi3._h, A3h, None) == 0, lib.mfb_last_error()
+            info = conv.sources_info()
+            assert info["path"] == 2 and info["loops"] == (3 if shared else 4), info
+            res[shared] = [g.get_kspace() for g in grids]
+            del conv, grids, phi, phi2, phi3, A3
+    finally:
+        lib.mfb_set_option(b"sources_shared", 1)
+    # the sources are total divergences: their low-k modes are sums that cancel to (k_min / k_max)^2 of the typical term, and
+    # 1 / k^2 then makes exactly those modes the largest of phi2 - any two summation orders differ by eps * (n_max / 2)^2 there
+    # (64 x 32 x 512: shared-field vs per-product 3.3e-12, multi-product vs per-product 5.1e-12, shared vs multi 5.2e-12)
+    tol = max(1e-12, 1e-16 * float(max(shape)) ** 2)
+    for a, b in zip(res[1], res[0]):
+        assert relerr(a, b) < tol, (relerr(a, b), tol)
+
+
 # ------------------------------------------------------------------ kernel generations agree
 def check_product_grouping(M, n=32):
     """3LPT sources three ways - (2) shared x passes + x-plane chunks + multi-product z pass with the products of a target
@@ -1018,10 +1051,15 @@ def check_product_grouping(M, n=32):
         # (v2, grouping, max_slots, chunk planes): the last two make the slot workspace as tight as it may be (7 slots: one
         # target per loop, an evicted X buffer is made again) and the chunks ragged
         # "v2direct": the multi-product z pass with direct loads instead of TMA-staged rows - the same arithmetic, bit for bit
-        for key, v2, grouping, slots, chunk in (("v2", 1, 1, 0, 0), ("v2direct", 1, 1, 0, 0), ("v2tight", 1, 1, 7, 5), ("v2split", 1, 1, 5, 7),
-                                                (1, 0, 1, 0, 0), (0, 0, 0, 0, 0)):
+        # "v2": stages A and C as shared-field loops (z_fields_kernel: every Hessian component transformed once per row, the
+        # last stage's targets overwrite consumed X planes); "v2multi": the multi-product z pass in every stage; "v2noalias":
+        # the shared last stage with a slot per target (10 slots, what slabs do)
+        for key, v2, grouping, slots, chunk in (("v2", 1, 1, 0, 0), ("v2multi", 1, 1, 0, 0), ("v2direct", 1, 1, 0, 0), ("v2noalias", 1, 1, 0, 3),
+                                                ("v2tight", 1, 1, 7, 5), ("v2split", 1, 1, 5, 7), (1, 0, 1, 0, 0), (0, 0, 0, 0, 0)):
             assert lib.mfb_set_option(b"sources_v2", v2) == 0 and lib.mfb_set_option(b"conv_grouping", grouping) == 0
             assert lib.mfb_set_option(b"zm_prefetch", 0 if key == "v2direct" else 1) == 0
+            assert lib.mfb_set_option(b"sources_shared", 0 if key in ("v2multi", "v2direct") else 1) == 0
+            assert lib.mfb_set_option(b"sources_alias", 0 if key == "v2noalias" else 1) == 0
             assert lib.mfb_set_option(b"sources_max_slots", slots) == 0 and lib.mfb_set_option(b"sources_chunk", chunk) == 0
             pl = M.LPTPipeline(M.lpt_config(GridRes=n, BoxLength=L, LPTorder=3, Dplus0=Dp))
             pl.set_noise_k(W)
@@ -1040,18 +1078,26 @@ def check_product_grouping(M, n=32):
         for o_ in (b"sources_max_slots", b"sources_chunk"):
             lib.mfb_set_option(o_, 0)
         lib.mfb_set_option(b"zm_prefetch", 1)
+        lib.mfb_set_option(b"sources_shared", 1)
+        lib.mfb_set_option(b"sources_alias", 1)
         lib.mfb_set_option(b"conv_grouping", 1)
         lib.mfb_set_option(b"sources_v2", 1)
+    print({k: (v[3], v[1]) for k, v in res.items()})
     assert res["v2"][3]["path"] == 2 and res["v2tight"][3]["path"] == 2 and res[1][3]["path"] == 1 and res[0][3]["path"] == 1
     # 10 backward x passes (3 of phi, 3 of phi2, 4 inner products) where the per-product path does 49; with 8 slots the
-    # four targets of the last stage go two per loop, with 7 one per loop and X(phi, 1) is made twice
-    assert res["v2"][3]["x_passes"] == 10 and res["v2"][3]["loops"] == 4 and res["v2"][3]["slots"] >= 8, res["v2"][3]
-    assert res["v2tight"][3]["slots"] == 7 and res["v2tight"][3]["x_passes"] == 11 and res["v2tight"][3]["loops"] == 7, res["v2tight"][3]
+    # four targets of the last stage go two per loop (multi-product pass); with 7 the first stage takes two multi-product
+    # loops, X(phi, 1) is made twice, and the last stage still is one shared-field loop (6 X buffers, targets in their planes)
+    assert res["v2multi"][3]["x_passes"] == 10 and res["v2multi"][3]["loops"] == 4 and res["v2multi"][3]["slots"] >= 8, res["v2multi"][3]
+    # shared-field loops: the five targets of the first stage and the four of the last one in one loop each
+    assert res["v2"][3]["x_passes"] == 10 and res["v2"][3]["loops"] == 3 and res["v2"][3]["slots"] == 8, res["v2"][3]
+    assert res["v2"][3]["y_passes"] < res["v2multi"][3]["y_passes"] and res["v2"][3]["z_launches"] < res["v2multi"][3]["z_launches"]
+    assert res["v2noalias"][3]["loops"] == 3 and res["v2noalias"][3]["slots"] == 10, res["v2noalias"][3]
+    assert res["v2tight"][3]["slots"] == 7 and res["v2tight"][3]["x_passes"] == 11 and res["v2tight"][3]["loops"] == 4, res["v2tight"][3]
     # equal up to rounding: the sums are taken in a different order (real space / z-Fourier space / per product)
     assert res["v2split"][3]["path"] == 2 and res["v2split"][3]["slots"] == 5 and res["v2split"][3]["loops"] > 7, res["v2split"][3]
-    for a, b in zip(res["v2"][0], res["v2direct"][0]):
+    for a, b in zip(res["v2multi"][0], res["v2direct"][0]):
         assert np.array_equal(a, b)
-    for key in ("v2", "v2tight", "v2split", 1):
+    for key in ("v2", "v2multi", "v2noalias", "v2tight", "v2split", 1):
         for a, b in zip(res[key][0], res[0][0]):
             assert relerr(a, b) < 1e-12, key
         assert relerr(res[key][4], res[0][4]) < 1e-12

@@ -45,6 +45,15 @@ def test_slab_pipeline_gloo_two_exchange_buffers():
     run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "2"])
 
 
+def test_slab_pipeline_gloo_eight_slots():
+    """8 slots: the first third-order stage is a shared-field loop, the last one two multi-product loops (the default block
+    of these tests has 10: both shared)"""
+    import emu_util
+
+    emu_util.build_emu()
+    run_world(2, ["--emu", "--grid", "32", "--lattice", "sc", "--nslots", "8"])
+
+
 def test_slab_pipeline_gloo_tight_slots():
     """7 slots (the minimum of the shared-transform source stage at 3LPT): one target per x-plane loop"""
     import emu_util

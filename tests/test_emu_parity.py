@@ -113,6 +113,11 @@ def test_product_grouping(M):
     PC.check_product_grouping(M, 32)
 
 
+@pytest.mark.parametrize("shape", [(32, 64, 64), (32, 32, 128)])
+def test_sources_shared_field_pass(M, shape):
+    PC.check_sources_shared_field_pass(M, shape)
+
+
 def test_two_fluid_terms(M):
     PC.check_two_fluid_terms(M, 32, "bcc")
 

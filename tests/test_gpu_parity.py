@@ -68,6 +68,12 @@ def test_product_grouping(M, n):
     PC.check_product_grouping(M, n)
 
 
+@pytest.mark.parametrize("shape", [(32, 64, 64), (64, 64, 256), (64, 32, 512), (32, 64, 1024)])
+def test_sources_shared_field_pass(M, shape):
+    """every plan of the shared-field z pass up to the 1536-point lines of the 1024^3 runs, against the multi-product pass"""
+    PC.check_sources_shared_field_pass(M, shape)
+
+
 @pytest.mark.parametrize("n,lattice", [(32, "bcc"), (64, "sc")])
 def test_two_fluid_terms(M, n, lattice):
     PC.check_two_fluid_terms(M, n, lattice)

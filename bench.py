@@ -632,7 +632,9 @@ def run_b200(args):
             scale = dom["alg_gb_per_launch"] * 1e9 / ent["alg_bytes_of_captured_launch"]
             traffic = ent["dram_bytes_per_launch"] * scale
             traffic_note = {"captured_launch_alg_bytes": ent["alg_bytes_of_captured_launch"],
-                            "captured_launch_dram_bytes": ent["dram_bytes_per_launch"], "source": ent["source"]}
+                            "captured_launch_dram_bytes": ent["dram_bytes_per_launch"], "source": ent["source"],
+                            # what bounds the kernel inside the SM (same capture): busiest pipes, % of their peak
+                            "pipes_pct_of_peak": ent.get("pipes_pct_of_peak")}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom["role"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",

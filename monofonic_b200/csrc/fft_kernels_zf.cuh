@@ -74,12 +74,13 @@ template <> struct ZfProg<ZF_PROG_C> {
     }
 };
 
-// barrier of one group (PTX named barriers 1..15; 0 is __syncthreads)
+// barrier of one group (PTX named barriers 1..15; 0 is __syncthreads): ids 1..G for the groups, 8.. for the forward teams
 #if !defined(MFB_EMU)
 MFB_D void zf_group_sync(int g, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory"); }
 #else
 inline void zf_group_sync(int g, int nthreads) { mfb_emu::bar_sync(g + 1, nthreads); }
 #endif
+constexpr int ZF_TEAM_BAR = 7;   // zf_group_sync(ZF_TEAM_BAR + team, ..) -> barrier ids 8, 9, 10
 
 // the remaining DIF stages of one line (s >= 1): a group barrier after each stage but the innermost
 template <class P, int s, int NTG> MFB_D void zf_dif_rest(double2* ln, const double2* tw, int q, int g) {
@@ -98,13 +99,27 @@ template <class P, int s, int NTG> MFB_D void zf_dit_mid(double2* ln, const doub
     }
 }
 
-template <class P, int NTG, int G, int PROG, bool PF>
+// every forward team contains a whole group (whose first line is the team's work line)
+constexpr bool zf_teams_ok(int ft, int ntg, int nfw) {
+    for (int j = 0; j < nfw; ++j)
+        if (((j * ft + ntg - 1) / ntg + 1) * ntg > (j + 1) * ft) return false;
+    return true;
+}
+
+// COOP: the forward transforms are shared out over ALL threads - NFW teams of NTH / NFW threads, one target pair each - instead
+// of one group per pair (which leaves G - NFW groups without forward work: they run ahead into the next row's backward
+// transforms and then wait).  A team's work line is the first line of the first group that lies entirely inside the team, so
+// that only that group's own next stage 0 overwrites it, after the team's last barrier.
+template <class P, int NTG, int G, int PROG, bool PF, bool COOP = false>
 __global__ void __launch_bounds__(NTG* G, 1) z_fields_kernel(ZfArgs A, const double2* __restrict__ tw) {
     MFB_DYN_SMEM(double2, sm);
     using PR = ZfProg<PROG>;
     constexpr int N = P::N, S = P::S, NZ = N / 3, LW = zpad(N) + 1;
     constexpr int NF = PR::NF, NL = NF / 2, LPG = NL / G, NTGT = PR::NT, NFW = (NTGT + 1) / 2, NTH = NTG * G;
     static_assert(NL % G == 0 && NFW <= G, "lines must divide over the groups, one target pair per group at most");
+    constexpr int FT = COOP ? NTH / NFW : NTG;   // threads per forward team
+    static_assert(FT % 32 == 0 && FT * NFW <= NTH && zf_teams_ok(FT, NTG, NFW), "forward teams are whole warps and hold a whole group");
+    auto fwd_line = [](int j) { return ((j * FT + NTG - 1) / NTG) * LPG; };   // first line of the first group inside team j
     static_assert(P::radix(0) % 3 == 0 && S >= 2, "the z pass needs a first radix that is a multiple of 3");
     const int tid = threadIdx.x, g = tid / NTG, q = tid - g * NTG;
     double2* lines = sm;                                        // NL padded complex lines
@@ -215,20 +230,21 @@ __global__ void __launch_bounds__(NTG* G, 1) z_fields_kernel(ZfArgs A, const dou
                 if constexpr (NTGT < 2 * NFW) t[2 * NFW - 1] = 0.0;
                 PR::run(f, cf, t);
 #pragma unroll
-                for (int j = 0; j < NFW; ++j) lines[(j * LPG) * LW + o] = make_double2(t[2 * j], t[2 * j + 1]);
+                for (int j = 0; j < NFW; ++j) lines[fwd_line(j) * LW + o] = make_double2(t[2 * j], t[2 * j + 1]);
             }
         }
         __syncthreads();
         // ---- forward transform of this group's target pair (DIT), unpack, store
-        if (g < NFW) {
-            double2* work = lines + (g * LPG) * LW;
-            z2_dif_stage<P, S - 1, NTG>(work, tw, q);   // innermost stage: no twiddles, DIT == DIF
-            zf_dit_mid<P, S - 2, NTG>(work, tw, q, g);
-            zf_group_sync(g, NTG);
+        const int team = COOP ? tid / FT : g, qf = COOP ? tid - team * FT : q, tbar = COOP ? ZF_TEAM_BAR + team : g;
+        if (team < NFW) {
+            double2* work = lines + fwd_line(team) * LW;
+            z2_dif_stage<P, S - 1, FT>(work, tw, qf);   // innermost stage: no twiddles, DIT == DIF
+            zf_dit_mid<P, S - 2, FT>(work, tw, qf, tbar);
+            zf_group_sync(tbar, FT);
             {
                 constexpr int r = P::radix(0), M = N / r;
 #pragma unroll 1
-                for (int j = q; j < M; j += NTG) {
+                for (int j = qf; j < M; j += FT) {
                     double2* sp = work + zpad(j);
                     double2 v[r];
 #pragma unroll
@@ -239,16 +255,16 @@ __global__ void __launch_bounds__(NTG* G, 1) z_fields_kernel(ZfArgs A, const dou
                     for (int u = 0; u < r; ++u) sp[zleg<M, r>(j, u)] = v[u];
                 }
             }
-            zf_group_sync(g, NTG);
-            double2* o1 = A.out[2 * g] + row * A.out_pitch;
-            double2* o2 = (2 * g + 1 < NTGT) ? A.out[2 * g + 1] + row * A.out_pitch : nullptr;
-            for (int k = q; k < NZ; k += NTG) {
+            zf_group_sync(tbar, FT);
+            double2* o1 = A.out[2 * team] + row * A.out_pitch;
+            double2* o2 = (2 * team + 1 < NTGT) ? A.out[2 * team + 1] + row * A.out_pitch : nullptr;
+            for (int k = qf; k < NZ; k += FT) {
                 const double2 zk = work[zpad(k)];
                 const double2 zm = work[zpad((N - k) % N)];
                 mfb_st_stream(o1 + k, make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y)));
                 if (o2) mfb_st_stream(o2 + k, make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x)));
             }
-            zf_group_sync(g, NTG);   // the line is free for the next row's stage 0
+            zf_group_sync(tbar, FT);   // the line is free for the next row's stage 0
         }
     }
 }

@@ -75,6 +75,11 @@ static void launch_zmulti(int n, const ZmArgs& a) {
     X(768, 64, 12, 8, 8)         \
     X(1536, 128, 12, 16, 8)
 constexpr int ZF_GROUPS = 3;
+// stage A: three groups of NTG threads, one line and one target pair each, rows staged by TMA.  Stage C: SIX groups of NTG / 2
+// threads, one line each, direct loads (six staging areas do not fit beside six lines) - the four groups without a target pair
+// run ahead into the next row (profiles/r02_kbench_zf_variants.txt, n = 1536, ms per launch of 147456 rows: 6 x 64 direct 8.94,
+// 3 x 128 TMA 9.50, 3 x 128 direct 9.79, 2 x 128 TMA 10.18; forward transforms shared out over all threads - COOP - 9.59 / 9.73)
+constexpr int zf_ntg_c(int ntg) { return ntg >= 64 ? ntg / 2 : 32; }
 
 static bool zfields_has_plan(int n) {
     switch (n) {
@@ -85,15 +90,15 @@ static bool zfields_has_plan(int n) {
         default: return false;
     }
 }
-template <class P, int NTG, int PROG> void launch_zfields_t(const ZfArgs& a, double bytes) {
+template <class P, int NTG, int G, int PROG, bool PF, bool COOP> void launch_zfields_t(const ZfArgs& a, double bytes) {
     static bool done = false;
-    constexpr size_t smem = z_fields_smem<P, ZF_GROUPS, PROG, true>();
-    optin_smem(z_fields_kernel<P, NTG, ZF_GROUPS, PROG, true>, smem, done);
+    constexpr size_t smem = z_fields_smem<P, G, PROG, PF>();
+    optin_smem(z_fields_kernel<P, NTG, G, PROG, PF, COOP>, smem, done);
     if (a.nrows <= 0) return;
     const unsigned grid = unsigned(std::min<long>(a.nrows, g_ctx.num_sms));   // persistent: one CTA per SM walks the rows
     const double2* tw = twiddles2<P>();
     RoleScope rs(ROLE_CONV_Z, bytes);
-    MFB_LAUNCH((z_fields_kernel<P, NTG, ZF_GROUPS, PROG, true>), grid, NTG * ZF_GROUPS, smem, g_ctx.stream, a, tw);
+    MFB_LAUNCH((z_fields_kernel<P, NTG, G, PROG, PF, COOP>), grid, NTG * G, smem, g_ctx.stream, a, tw);
     check_launch("z_fields_kernel");
 }
 static void launch_zfields(int n, int prog, const ZfArgs& a) {
@@ -104,8 +109,8 @@ static void launch_zfields(int n, int prog, const ZfArgs& a) {
     switch (n) {
 #define X(N_, NTG_, ...)                                                                                   \
     case N_:                                                                                               \
-        if (prog == ZF_PROG_A) launch_zfields_t<Plan<N_, NTG_, 2, __VA_ARGS__>, NTG_, ZF_PROG_A>(a, bytes);  \
-        else launch_zfields_t<Plan<N_, NTG_, 2, __VA_ARGS__>, NTG_, ZF_PROG_C>(a, bytes);                    \
+        if (prog == ZF_PROG_A) launch_zfields_t<Plan<N_, NTG_, 2, __VA_ARGS__>, NTG_, ZF_GROUPS, ZF_PROG_A, true, false>(a, bytes);  \
+        else launch_zfields_t<Plan<N_, NTG_, 2, __VA_ARGS__>, zf_ntg_c(NTG_), 6, ZF_PROG_C, false, false>(a, bytes);                 \
         return;
         MFB_FOR_EACH_PLANZF(X)
 #undef X

@@ -113,7 +113,7 @@ def test_product_grouping(M):
     PC.check_product_grouping(M, 32)
 
 
-@pytest.mark.parametrize("shape", [(32, 64, 64), (32, 32, 128)])
+@pytest.mark.parametrize("shape", [(32, 64, 64), (32, 32, 128), (32, 32, 256)])
 def test_sources_shared_field_pass(M, shape):
     PC.check_sources_shared_field_pass(M, shape)
 

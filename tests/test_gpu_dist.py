@@ -27,6 +27,14 @@ def test_slab_pipeline_two_exchange_buffers():
     run_world(2, ["--grid", "64", "--lattice", "sc", "--nslots", "2"])
 
 
+def test_slab_pipeline_eight_slots():
+    """8 slots: first third-order stage as a shared-field loop, the last one as two multi-product loops (the default block
+    has 10 slots: both shared)"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, ["--grid", "64", "--lattice", "sc", "--nslots", "8"])
+
+
 def test_slab_pipeline_tight_slots():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")

@@ -132,21 +132,7 @@ template <class P, int MODE> static void run_v3(Bench& B, const char* label, int
     cudaFree(tw2);
 }
 #define V3(MODE, ...) run_v3<Plan<__VA_ARGS__>, MODE>(B, "v3 double-buffered <" #__VA_ARGS__ ">")
-template <class P, int MODE> static void run_v4(Bench& B, const char* label, int ctas = 148) {
-    if (MODE != B.mode) return;
-    auto k = strided4_kernel<P, MODE>;
-    double2* tw2 = make_tw2<P>();
-    constexpr size_t smem = 2 * P::SMEM_BYTES + 16;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
-    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::NTHREADS, smem));
-    StridedArgs a = B.args();
-    CK(cudaMemset(B.out, 0xff, B.out_elems * 16));
-    float ms = time_kernel([&] { k<<<ctas, P::NTHREADS, smem>>>(a, tw2); });
-    report(B, label, ms, false, fa.numRegs, occ);
-    cudaFree(tw2);
-}
-#define V4(MODE, ...) run_v4<Plan<__VA_ARGS__>, MODE>(B, "v4 TMA double-buffered <" #__VA_ARGS__ ">")
+// (run_v4 / strided4_kernel, the TMA bulk double-buffered strided pass, is gone: see kbench_legacy_kernels.cuh)
 
 static Bench make_bench(int n, int mode, int na) {
     Bench B; B.n = n; B.n_small = 2 * n / 3; B.nz = B.n_small / 2; B.na = na; B.mode = mode;
@@ -465,10 +451,7 @@ int main(int argc, char** argv) {
             run_v2<Plan<1536, 64, 4, 12, 16, 8>, SM_PAD, 2>(B, "v2 <1536,64,4,12,16,8> minb 2");
             run_v2<Plan<1536, 64, 4, 8, 16, 12>, SM_TRUNC, 2>(B, "v2 <1536,64,4,8,16,12> minb 2");
             V3(SM_PAD, 1536, 64, 4, 12, 16, 8); V3(SM_PAD, 1536, 128, 4, 12, 16, 8);
-            V4(SM_PAD, 1536, 64, 4, 12, 16, 8); V4(SM_PAD, 1536, 128, 4, 12, 16, 8); V4(SM_PAD, 1536, 96, 4, 12, 16, 8); V4(SM_PAD, 1536, 32, 4, 12, 16, 8);
-            V4(SM_PAD, 1536, 128, 4, 12, 8, 16); V4(SM_PAD, 1536, 128, 4, 6, 16, 16);
             V3(SM_TRUNC, 1536, 64, 4, 8, 16, 12);
-            V4(SM_TRUNC, 1536, 64, 4, 8, 16, 12); V4(SM_TRUNC, 1536, 128, 4, 8, 16, 12); V4(SM_TRUNC, 1536, 96, 4, 8, 16, 12);
             free_bench(B);
         }
         for (int mode : {SM_PAD, SM_TRUNC}) {   // n = 768: two 8-line tiles fit
@@ -476,8 +459,6 @@ int main(int argc, char** argv) {
             run_v1<Plan<768, 32, 8, 12, 8, 8>>(B, "v1 <768,32,8,12,8,8>", true);
             run_v2<Plan<768, 32, 8, 12, 8, 8>, SM_PAD, 2>(B, "v2 <768,32,8,12,8,8> minb 2");
             run_v2<Plan<768, 32, 8, 8, 8, 12>, SM_TRUNC, 2>(B, "v2 <768,32,8,8,8,12> minb 2");
-            V4(SM_PAD, 768, 32, 8, 12, 8, 8); V4(SM_PAD, 768, 64, 8, 12, 8, 8);
-            V4(SM_TRUNC, 768, 32, 8, 8, 8, 12); V4(SM_TRUNC, 768, 64, 8, 8, 8, 12);
             free_bench(B);
         }
         return 0;

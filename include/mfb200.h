@@ -220,6 +220,11 @@ int mfb_conv_gradients(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, int d1r, 
 int mfb_conv_gradient_hessian(mfb_conv* c, mfb_grid* l, int d1l, mfb_grid* r, const int d2r[2], mfb_grid* out,
                               int op, double alpha);                        /* convolve_Gradient_and_Hessian :106-127 */
 int mfb_conv_multiply(mfb_conv* c, mfb_grid* l, mfb_grid* r, mfb_grid* out, int op, double alpha); /* multiply_field :282-292 */
+/* OrszagConvolver::convolve2 / convolve3 with caller-formed spectra (:512-535, :542-549; NaiveConvolver :312-401): the reference
+   takes host lambdas kfunc(i,j,k); here the operands are k-space device grids holding kfunc's values (the C++ mirror
+   evaluates the lambdas into temporaries, include/mfb/convolution.hh).  convolve3 truncates between the two products. */
+int mfb_conv_generic(mfb_conv* c, mfb_grid* specA, mfb_grid* specB, mfb_grid* out, int op, double alpha);
+int mfb_conv_generic3(mfb_conv* c, mfb_grid* specA, mfb_grid* specB, mfb_grid* specC, mfb_grid* out, int op, double alpha);
 /* The whole source stage of ic_generator::run (:475-574): phi2, phi3, A3 from phi (un-scaled, k-space), then the
    growth-factor scaling g1,g2,g3,g3c.  phi2/phi3/A3 may be NULL below the requested order. */
 int mfb_lpt_sources(mfb_conv* c, int order, double Dplus0, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3,

@@ -116,6 +116,8 @@ def _declare(lib):
         "mfb_conv_gradients": (i, [vp, vp, i, vp, i, vp, i, d]),
         "mfb_conv_gradient_hessian": (i, [vp, vp, i, vp, ip, vp, i, d]),
         "mfb_conv_multiply": (i, [vp, vp, vp, vp, i, d]),
+        "mfb_conv_generic": (i, [vp, vp, vp, vp, i, d]),
+        "mfb_conv_generic3": (i, [vp, vp, vp, vp, vp, i, d]),
         "mfb_lpt_sources": (i, [vp, i, d, vp, vp, vp, vpp, dp]),
         "mfb_particles_create": (i, [vpp, ip, i, i, i, i]),
         "mfb_particles_create_masked": (i, [vpp, ip, i, ip, i, i, i]),

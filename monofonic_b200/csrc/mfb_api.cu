@@ -2178,6 +2178,24 @@ int mfb_conv_multiply(mfb_conv* c, mfb_grid* l, mfb_grid* r, mfb_grid* out, int 
     conv2(c, Operand{l, -1, -1, -1, -1, 1.0, 0.0, 0}, Operand{r, -1, -1, -1, -1, 1.0, 0.0, 0}, out, op, alpha);
     MFB_CATCH
 }
+/* convolve2 / convolve3 with caller-formed spectra (include/convolution.hh:512-549): the k-space operands are device grids the
+   caller has filled (the host mirror evaluates the reference's kfunc lambdas into them); no derivative factor is applied */
+int mfb_conv_generic(mfb_conv* c, mfb_grid* specA, mfb_grid* specB, mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, specA, specB, out);
+    require(specA->space == MFB_KSPACE && specB->space == MFB_KSPACE, "mfb_conv_generic: the operand spectra must be in k-space");
+    conv2(c, Operand{specA, -1, -1, -1, -1, 1.0, 0.0, 0}, Operand{specB, -1, -1, -1, -1, 1.0, 0.0, 0}, out, op, alpha);
+    MFB_CATCH
+}
+int mfb_conv_generic3(mfb_conv* c, mfb_grid* specA, mfb_grid* specB, mfb_grid* specC, mfb_grid* out, int op, double alpha) {
+    MFB_TRY
+    check_conv_grids(c, specA, specB, out); check_conv_grids(c, specC, specC, out);
+    require(specA->space == MFB_KSPACE && specB->space == MFB_KSPACE && specC->space == MFB_KSPACE,
+            "mfb_conv_generic3: the operand spectra must be in k-space");
+    conv3(c, Operand{specA, -1, -1, -1, -1, 1.0, 0.0, 0}, Operand{specB, -1, -1, -1, -1, 1.0, 0.0, 0},
+          Operand{specC, -1, -1, -1, -1, 1.0, 0.0, 0}, out, op, alpha);
+    MFB_CATCH
+}
 int mfb_lpt_sources(mfb_conv* c, int order, double Dplus0, mfb_grid* phi, mfb_grid* phi2, mfb_grid* phi3, mfb_grid* const A3[3],
                     const double* tides_lambda) {
     MFB_TRY

@@ -427,6 +427,15 @@ class OrszagConvolver:
     def multiply_field(self, inl, inr, o):
         L.check(self._lib.mfb_conv_multiply(self._h, inl._h, inr._h, o.grid._h, o.code, o.alpha), self._lib)
 
+    def convolve2(self, spec1, spec2, o):
+        """convolve2(kf1, kf2, output_op) (include/convolution.hh:512-535) with the operand spectra handed over as k-space
+        grids holding kf1(i,j,k), kf2(i,j,k) instead of host lambdas"""
+        L.check(self._lib.mfb_conv_generic(self._h, spec1._h, spec2._h, o.grid._h, o.code, o.alpha), self._lib)
+
+    def convolve3(self, spec1, spec2, spec3, o):
+        """convolve3(kf1, kf2, kf3, output_op) (:542-549): (spec1 * spec2) truncated to the grid, then * spec3"""
+        L.check(self._lib.mfb_conv_generic3(self._h, spec1._h, spec2._h, spec3._h, o.grid._h, o.code, o.alpha), self._lib)
+
 
 class NaiveConvolver(OrszagConvolver):
     """NaiveConvolver<real_t> (include/convolution.hh:296-426): the same named products without 3/2 padding."""

@@ -73,6 +73,31 @@ int main() {
     Conv.convolve_Hessians(phi, {0, 1}, phi, {1, 2}, op::assign_to(tmp));
     for (size_t i = 0; i < tmp.ntot_ / 2; ++i) ref = std::max(ref, std::abs(tmp.kelem(i)));
     CHECK(asym < 1e-13 * ref);
+    // the generic entry points with the reference's own lambda style (include/convolution.hh:512-549, and the way
+    // BaseConvolver::convolve_Hessians writes its kfuncs, :140-158): equal to the named products
+    {
+        auto hess = [&](Grid_FFT<real_t>& g, int a, int b) {
+            return [&g, a, b](size_t i, size_t j, size_t k) -> ccomplex_t {
+                return g.gradient(a, {i, j, k}) * g.gradient(b, {i, j, k}) * g.kelem(i, j, k);
+            };
+        };
+        Grid_FFT<real_t> t2(N, L, true, kspace_id), t3(N, L, true, kspace_id);
+        Conv.convolve2(hess(phi, 0, 1), hess(phi, 1, 2), op::assign_to(t2));
+        double d2 = 0;
+        for (size_t i = 0; i < tmp.ntot_ / 2; ++i) d2 = std::max(d2, std::abs(t2.kelem(i) - tmp.kelem(i)));
+        CHECK(d2 < 1e-13 * ref);
+        // output operator as a plain callable (idx, value), like the reference's own op:: lambdas
+        std::vector<real_t> got(tmp.ntot_);
+        Conv.convolve2(hess(phi, 0, 1), hess(phi, 1, 2), [&](size_t idx, real_t v) { got[idx] = v; });
+        for (size_t i = 0; i < tmp.ntot_; ++i) d2 = std::max(d2, std::fabs(got[i] - tmp[i]));
+        CHECK(d2 < 1e-13 * ref);
+        // three fields: the intermediate product is truncated to the grid before the second one (:542-549)
+        Conv.convolve_Hessians(phi, {0, 0}, phi, {1, 1}, phi, {2, 2}, op::assign_to(t2));
+        Conv.convolve3(hess(phi, 0, 0), hess(phi, 1, 1), hess(phi, 2, 2), op::assign_to(t3));
+        double d3 = 0, r3 = 0;
+        for (size_t i = 0; i < t2.ntot_ / 2; ++i) { d3 = std::max(d3, std::abs(t3.kelem(i) - t2.kelem(i))); r3 = std::max(r3, std::abs(t2.kelem(i))); }
+        CHECK(r3 > 0 && d3 < 1e-13 * r3);
+    }
     // CONVOLVER_TYPE=NAIVE build of the same host code: the aliased product differs, its Nyquist planes are populated
     {
         NaiveConvolver<real_t> NConv(N, L);

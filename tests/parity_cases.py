@@ -154,8 +154,24 @@ def check_convolver(M, n, nyquist_zero=True):
     ref = cv.multiply_field(phi, psi)
     C.multiply_field(P, Q, op.assign_to(out))
     assert relerr(out.get_kspace(), ref) < TOL
-    # operands handed over in real space are transformed first (convolution.hh:142-143)
+    # convolve2 / convolve3 with caller-formed spectra (mfb_conv_generic, mfb_conv_generic3; convolution.hh:512-549)
+    C.convolve2(P, Q, op.assign_to(out))
+    assert relerr(out.get_kspace(), ref) < TOL
+    R = M.Grid_FFT((n,) * 3, (L,) * 3)
+    _, _, _, chi = noise_and_phi(n, L, 11, nyquist_zero)
+    R.set_kspace(chi)
+    ref3 = cv.convolve3(phi, psi, chi)
+    C.convolve3(P, Q, R, op.assign_to(out))
+    assert relerr(out.get_kspace(), ref3) < TOL
+    C.convolve3(P, Q, R, op.multiply_add_to(out, -0.25))
+    assert relerr(out.get_kspace(), 0.75 * ref3) < TOL
     P.FourierTransformBackward()
+    try:
+        C.convolve2(P, Q, op.assign_to(out))     # spectra are k-space grids by contract
+        raise AssertionError("convolve2 accepted a real-space operand")
+    except M.MfbError:
+        pass
+    # operands handed over in real space are transformed first (convolution.hh:142-143)
     C.multiply_field(P, Q, op.assign_to(out))
     assert relerr(out.get_kspace(), ref) < 10 * TOL
 

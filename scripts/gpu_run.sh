@@ -2,7 +2,7 @@
 # One parameterised gpurun call (replaces the one-shot scripts of round 1).  Everything lands in gpurun_out/.
 #   TESTS="<pytest -k expr>|all|none"  SMOKE=1  BENCH_GRIDS="1024 512"  BENCH_ARGS="--steps 3 --warmup 3 --no-cpu"
 #   LAUNCHES=<grid> (ncu launch list of one step)   NCU_KERNELS="regex ..." NCU_GRID=<grid> (ncu --set full)
-#   KBENCH="args" (scripts/kbench/kbench)  KBENCH_ZM="args" (scripts/kbench/kbench_zm)  NG=<gpus> (torchrun for bench when > 1; dist tests)
+#   KBENCH="args" (scripts/kbench/kbench)  KBENCH_ZF="args" (scripts/kbench/kbench_zf)  NG=<gpus> (torchrun for bench when > 1; dist tests)
 set -u
 TAG=${TAG:-run}
 mkdir -p gpurun_out
@@ -19,8 +19,8 @@ fi
 if [ -n "${KBENCH:-}" ]; then
   echo "== kbench $KBENCH"; timeout 600 scripts/kbench/kbench $KBENCH 2>&1 | tee gpurun_out/kbench_$TAG.log | tail -60
 fi
-if [ -n "${KBENCH_ZM:-}" ]; then
-  echo "== kbench_zm $KBENCH_ZM"; timeout 600 scripts/kbench/kbench_zm $KBENCH_ZM 2>&1 | tee gpurun_out/kbench_zm_$TAG.log | tail -60
+if [ -n "${KBENCH_ZF:-}" ]; then
+  echo "== kbench_zf $KBENCH_ZF"; timeout 600 scripts/kbench/kbench_zf $KBENCH_ZF 2>&1 | tee gpurun_out/kbench_zf_$TAG.log | tail -60
 fi
 for G in ${BENCH_GRIDS:-}; do
   echo "== bench grid $G on $NG GPU(s)"

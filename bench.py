@@ -691,6 +691,10 @@ def run_b200(args):
         parity = {"vs_n1": B.check_against_digest(dpath, f"N=1 run of the same workload ({os.path.relpath(dpath, ROOT)})")}
         if not args.no_e2e:
             parity["ids"] = B.check_ids()
+        if args.workload == "c2" and n == 512 and order == 2 and lattice == "sc":
+            # SURVEY C2 is small enough for the CPU oracle itself: the whole workload against its digest
+            parity["vs_oracle"] = B.check_against_digest(os.path.join(GOLD, "bench_digest_oracle_512_2lpt.npz"),
+                                                         "CPU oracle, 2LPT 512^3 (tests/golden/make_bench_digest.py 512 2)")
 
     # ---- CPU baseline: bounded sample of the same workload on the host cores
     cpu = None

@@ -2,7 +2,9 @@
 does not have to): the bench's synthetic 3LPT workload - same per-plane noise seeds, amplitude, growth factors and units - run
 through oracle/lpt_oracle.py; the FP64 displacement and velocity fields are sampled at bench.sample_cells(n).
 
-  python tests/golden/make_bench_digest.py [n=256]   ->  tests/golden/bench_digest_oracle_<n>.npz
+  python tests/golden/make_bench_digest.py [n=256] [order=3]   ->  tests/golden/bench_digest_oracle_<n>.npz  (order 3)
+                                                                     tests/golden/bench_digest_oracle_<n>_<order>lpt.npz (else)
+The 2LPT 512^3 digest takes about 25 GB of host memory.
 """
 import os
 import sys
@@ -19,7 +21,7 @@ import lpt_oracle as O  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-    order, L = 3, B.LBOX
+    order, L = (int(sys.argv[2]) if len(sys.argv) > 2 else 3), B.LBOX
     t0 = time.time()
     x = np.empty((n, n, n))
     for i in range(n):
@@ -39,7 +41,7 @@ def main():
     names = ["dx", "dy", "dz", "vx", "vy", "vz"]
     fields = np.stack([ref["fields"][k][cells[:, 0], cells[:, 1], cells[:, 2]] for k in names])
     maxabs = np.array([np.abs(ref["fields"][k]).max() for k in names])
-    out = os.path.join(ROOT, "tests", "golden", f"bench_digest_oracle_{n}.npz")
+    out = os.path.join(ROOT, "tests", "golden", f"bench_digest_oracle_{n}.npz" if order == 3 else f"bench_digest_oracle_{n}_{order}lpt.npz")
     np.savez_compressed(out, n=n, order=order, fields=fields, maxabs=maxabs, cells=cells.astype(np.int32))
     print(f"wrote {out}: {fields.shape}, max|Psi| = {maxabs[:3].max():.4g}, max|v| = {maxabs[3:].max():.4g}, {time.time() - t0:.0f} s")
 

@@ -247,3 +247,30 @@ def test_convolver_linearity_and_product_512(M):
 
 def test_kernel_generations_agree(M):
     PC.check_kernel_generations(M, 128)
+
+
+@pytest.mark.parametrize("n,order,digest", [(256, 3, "bench_digest_oracle_256.npz"), (512, 2, "bench_digest_oracle_512_2lpt.npz")])
+def test_pipeline_vs_oracle_digest(M, n, order, digest):
+    """SURVEY 8d C2 / C3 at sizes the oracle does not finish in seconds: the bench's synthetic workload (per-plane noise
+    seeds, amplitude, growth factors) through the CUDA path, its FP64 displacement and velocity fields sampled at 32768
+    cells against the CPU oracle's values at the same cells (committed digest, tests/golden/make_bench_digest.py).
+    Bar: max|err| <= 1e-9 * max|field| (north_star)."""
+    import gc
+    import os
+
+    import torch
+
+    import bench as B
+
+    path = os.path.join(B.GOLD, digest)
+    if not os.path.exists(path):
+        pytest.skip(f"{digest} not committed")
+    W = B.Bench(M, M.load(), torch, None, 0, n, order, "sc")
+    W.make_noise()
+    W.upload_noise()
+    W.step_device()
+    r = W.check_against_digest(path, "CPU oracle digest")
+    del W
+    gc.collect()
+    assert r["checked"] and r["ok"], r
+    assert r["max_rel_psi"] < 1e-9 and r["max_rel_vel"] < 1e-9

@@ -50,6 +50,8 @@ template <typename T> struct vec3_t {
 #include <hdf5.h>
 #endif
 #endif
+#include <fstream>
+#include <iomanip>
 #include <vector>
 
 enum space_t { kspace_id, rspace_id };  // include/grid_fft.hh:29  (kspace_id == MFB_KSPACE == 0)
@@ -70,7 +72,7 @@ inline void check(int rc) {
 #endif
 template <typename data_t_, bool bdistributed = GRID_FFT_DISTRIBUTED>
 class Grid_FFT {
-    static_assert(std::is_same<data_t_, double>::value, "the device path is FP64 real grids (PPT c2c: DESIGN.md section 8)");
+    static_assert(std::is_same<data_t_, double>::value, "FP64 real grids here; Grid_FFT<ccomplex_t> is the specialisation of grid_fft_complex.hh");
 
 public:
     using data_t = data_t_;
@@ -172,6 +174,38 @@ public:
                           ft((real_t(k) + s.z) / real_t(n_[2])));
     }
     vec3_t<size_t> get_cell_idx_3d(size_t i, size_t j, size_t k) const noexcept { return vec3_t<size_t>(i + local_0_start_, j, k); }
+    // trilinear (CIC) read-out on the host mirror, single slab like the reference's ("doesn't work with MPI"):
+    // get_cic at a position in box units, periodic in all three axes (include/grid_fft.hh:320-345); get_cic_kspace at a fractional
+    // k-space index, periodic in the first two axes and clamped at the last retained k_z (:347-373; the PLT tables are read this way)
+    data_t get_cic(const vec3_t<real_t>& v) const noexcept {
+        real_t x[3];
+        size_t lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+            x[d] = real_t(std::fmod(v[d] / length_[d] + 1.0, 1.0) * n_[d]);
+            lo[d] = size_t(x[d]); hi[d] = (lo[d] + 1) % n_[d]; x[d] -= real_t(lo[d]);
+        }
+        data_t val = 0.0;
+        for (int c = 0; c < 8; ++c) {
+            const bool a = c & 4, b = c & 2, e = c & 1;
+            val += this->relem(a ? hi[0] : lo[0], b ? hi[1] : lo[1], e ? hi[2] : lo[2]) * (a ? x[0] : 1.0 - x[0]) * (b ? x[1] : 1.0 - x[1]) * (e ? x[2] : 1.0 - x[2]);
+        }
+        return val;
+    }
+    ccomplex_t get_cic_kspace(const vec3_t<real_t> v) const noexcept {
+        real_t x[3];
+        size_t lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+            const int i = int(std::floor(v[d]));
+            x[d] = v[d] - real_t(i); lo[d] = size_t(i);
+            hi[d] = d < 2 ? size_t(i + 1) % size(d) : size_t(std::min(i + 1, int(size(2)) - 1));
+        }
+        ccomplex_t val = 0.0;
+        for (int c = 0; c < 8; ++c) {
+            const bool a = c & 4, b = c & 2, e = c & 1;
+            val += this->kelem(a ? hi[0] : lo[0], b ? hi[1] : lo[1], e ? hi[2] : lo[2]) * ((a ? x[0] : 1.0 - x[0]) * (b ? x[1] : 1.0 - x[1]) * (e ? x[2] : 1.0 - x[2]));
+        }
+        return val;
+    }
     std::array<size_t, 3> get_k3(size_t i, size_t j, size_t k) const noexcept {   // include/grid_fft.hh:315-318
         return bdistributed ? std::array<size_t, 3>({j, i + size_t(local_1_start_), k}) : std::array<size_t, 3>({i, j, k});
     }
@@ -319,27 +353,75 @@ public:
         throw std::runtime_error("Write_to_HDF5: this host build has no <hdf5.h>");
 #endif
     }
-    //! spherically binned power spectrum of the k-space field (src/grid_fft.cc:1104-1176): mean |f(k)|^2 per |k| bin
+    //! spherically binned power spectrum of the k-space field (src/grid_fft.cc:1133-1209): linear bins of width k_min = the smallest
+    //! fundamental mode up to the largest Nyquist wave number; the vectors are resized here; modes with k_z > 0 count twice
     void Compute_PowerSpectrum(std::vector<double>& bin_k, std::vector<double>& bin_P, std::vector<double>& bin_eP, std::vector<size_t>& bin_count) {
         FourierTransformForward();
         to_host(false);
-        const real_t kmin = kfac_[0], kmax = kfac_[0] * real_t(n_[0] / 2), dklog = std::log(kmax / kmin) / real_t(bin_k.size());
-        std::fill(bin_k.begin(), bin_k.end(), 0.0); std::fill(bin_P.begin(), bin_P.end(), 0.0);
-        std::fill(bin_eP.begin(), bin_eP.end(), 0.0); std::fill(bin_count.begin(), bin_count.end(), size_t(0));
+        const real_t kmax = std::max(std::max(kfac_[0] * nhalf_[0], kfac_[1] * nhalf_[1]), kfac_[2] * nhalf_[2]);
+        const real_t kmin = std::min(std::min(kfac_[0], kfac_[1]), kfac_[2]), dk = kmin;
+        const int nbins = int(kmax / kmin);
+        bin_count.assign(nbins, 0); bin_k.assign(nbins, 0.0); bin_P.assign(nbins, 0.0); bin_eP.assign(nbins, 0.0);
         for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
-            const real_t kk = this->template get_k<real_t>(i, j, k).norm();
+            const double kk = this->template get_k<double>(i, j, k).norm();
             if (!(kk >= kmin && kk < kmax)) continue;
-            const size_t b = std::min(bin_k.size() - 1, size_t(std::log(kk / kmin) / dklog));
-            const double w = (k == 0 || k == n_[2] / 2) ? 1.0 : 2.0, p = std::norm(cdata_[get_idx(i, j, k)]);
-            bin_k[b] += w * kk; bin_P[b] += w * p; bin_eP[b] += w * p * p; bin_count[b] += size_t(w);
+            const int b = int(kk / dk);
+            const double w = (k == 0) ? 1.0 : 2.0, p = std::norm(cdata_[get_idx(i, j, k)]);
+            bin_P[b] += w * p; bin_eP[b] += w * p * p; bin_k[b] += w * kk; bin_count[b] += size_t(w);
         }
-        const real_t volfac = length_[0] * length_[1] * length_[2] / std::pow(2.0 * M_PI, 3.0);
-        for (size_t b = 0; b < bin_k.size(); ++b) {
+        const real_t volfac = length_[0] * length_[1] * length_[2] / std::pow(2.0 * M_PI, 3.0), fftfac = fft_norm_fac_ * fft_norm_fac_;
+        for (int b = 0; b < nbins; ++b) {
             if (!bin_count[b]) continue;
             const double c = double(bin_count[b]);
-            bin_k[b] /= c; bin_P[b] = bin_P[b] / c * volfac;
-            bin_eP[b] = std::sqrt(std::max(0.0, bin_eP[b] / c * volfac * volfac - bin_P[b] * bin_P[b])) / std::sqrt(c);
+            bin_k[b] /= c;
+            bin_P[b] = bin_P[b] / c * volfac * fftfac;
+            bin_eP[b] = std::sqrt(bin_eP[b] / c - bin_P[b] * bin_P[b]) / std::sqrt(c) * volfac * fftfac;
         }
+    }
+    //! the binned spectrum as a four-column text file (src/grid_fft.cc:1104-1131)
+    void Write_PowerSpectrum(std::string ofname) {
+        std::vector<double> bin_k, bin_P, bin_eP;
+        std::vector<size_t> bin_count;
+        Compute_PowerSpectrum(bin_k, bin_P, bin_eP, bin_count);
+        std::ofstream ofs(ofname.c_str());
+        ofs << "# " << std::setw(14) << "k" << std::setw(16) << "P(k)" << std::setw(16) << "err. P(k)" << std::setw(16) << "#modes" << "\n";
+        for (size_t b = 0; b < bin_k.size(); ++b)
+            if (bin_count[b] > 0)
+                ofs << std::setw(16) << bin_k[b] << std::setw(16) << bin_P[b] << std::setw(16) << bin_eP[b] << std::setw(16) << bin_count[b] << std::endl;
+    }
+    //! external constraint field (src/grid_fft.cc:548-668; [random] ConstraintFieldFile): a cubic FP64 dataset replaces this grid
+    //! - the grid takes the dataset's size - and is normalised to unit variance about zero as the reference does
+    void Read_from_HDF5(const std::string Filename, const std::string ObjName) {
+#ifdef MFB_MIRROR_HAVE_HDF5
+        const hid_t file = H5Fopen(Filename.c_str(), H5F_ACC_RDONLY, H5P_DEFAULT);
+        if (file < 0) throw std::runtime_error("Read_from_HDF5: cannot open " + Filename);
+        const hid_t dset = H5Dopen2(file, ObjName.c_str(), H5P_DEFAULT);
+        if (dset < 0) { H5Fclose(file); throw std::runtime_error("Read_from_HDF5: dataset '" + ObjName + "' does not exist in " + Filename); }
+        const hid_t fspace = H5Dget_space(dset);
+        hsize_t dims[3] = {0, 0, 0};
+        if (H5Sget_simple_extent_ndims(fspace) != 3 || H5Sget_simple_extent_dims(fspace, dims, nullptr) < 0 || dims[0] != dims[1] || dims[0] != dims[2]) {
+            H5Sclose(fspace); H5Dclose(dset); H5Fclose(file);
+            throw std::runtime_error("Read_from_HDF5: '" + ObjName + "' is not a cubic three-dimensional dataset");
+        }
+        std::vector<double> buf(size_t(dims[0]) * dims[1] * dims[2]);
+        const herr_t rc = H5Dread(dset, H5T_NATIVE_DOUBLE, H5S_ALL, H5S_ALL, H5P_DEFAULT, buf.data());
+        H5Sclose(fspace); H5Dclose(dset); H5Fclose(file);
+        if (rc < 0) throw std::runtime_error("Read_from_HDF5: reading '" + ObjName + "' failed");
+        reset();
+        for (int d = 0; d < 3; ++d) n_[d] = size_t(dims[d]);
+        space_ = rspace_id;
+        allocate();
+        double s1 = 0, s2 = 0;
+        for (double v : buf) { s1 += v; s2 += v * v; }
+        s1 /= double(buf.size()); s2 /= double(buf.size());
+        const double stdw = std::sqrt(s2 - s1 * s1);
+        to_host(true);
+        for (size_t i = 0; i < n_[0]; ++i) for (size_t j = 0; j < n_[1]; ++j) for (size_t k = 0; k < n_[2]; ++k)
+            data_[(i * n_[1] + j) * npr_ + k] = buf[(i * n_[1] + j) * n_[2] + k] / stdw;
+#else
+        (void)Filename; (void)ObjName;
+        throw std::runtime_error("Read_from_HDF5: this host build has no <hdf5.h>");
+#endif
     }
 
 private:

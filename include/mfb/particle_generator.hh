@@ -23,9 +23,20 @@ struct cfg_reader<C, T, decltype(void(std::declval<C&>().get_value_safe(std::str
 };
 }  // namespace mfb_detail
 
+#if defined(__has_include)
+#if __has_include(<particle_container.hh>)
+#define MFB_MIRROR_REFERENCE_CONTAINER 1
+#endif
+#endif
+#ifdef MFB_MIRROR_REFERENCE_CONTAINER
+#include <particle_container.hh>   // the reference's own container (include/particle_container.hh:30-189): what its output plugins read
+#endif
+
 namespace particle {
 enum lattice { lattice_masked = -2, lattice_glass = -1, lattice_sc = 0, lattice_bcc = 1, lattice_fcc = 2, lattice_rsc = 3 };
 
+#ifndef MFB_MIRROR_REFERENCE_CONTAINER
+// stand-alone hosts (no reference headers on the include path): the same members
 class container {
 public:
     std::vector<float> positions32_, velocities32_, mass32_;
@@ -52,6 +63,7 @@ public:
     size_t get_local_num_particles() const { return ids32_.empty() ? ids64_.size() : ids32_.size(); }
     size_t get_global_num_particles() const { return get_local_num_particles(); }
 };
+#endif
 
 template <typename field_t>
 class lattice_generator {

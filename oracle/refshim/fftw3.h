@@ -18,6 +18,7 @@ fftw_plan fftw_plan_dft_c2r_3d(int n0, int n1, int n2, fftw_complex* in, double*
 fftw_plan fftw_plan_dft_3d(int n0, int n1, int n2, fftw_complex* in, fftw_complex* out, int sign, unsigned flags);
 void fftw_execute(const fftw_plan p);
 void fftw_destroy_plan(fftw_plan p);
+extern const char fftw_version[];   /* printed by src/main.cc:209 */
 int fftw_init_threads(void);
 void fftw_plan_with_nthreads(int);
 void fftw_cleanup_threads(void);

@@ -24,6 +24,7 @@ inline int H5Sget_simple_extent_dims(hid_t, hsize_t*, hsize_t*) { return -1; }
 inline hid_t H5Dcreate2(hid_t, const char*, hid_t, hid_t, hid_t, hid_t, hid_t) { return -1; }
 inline hid_t H5Dopen1(hid_t, const char*) { return -1; }
 inline hid_t H5Dopen(hid_t, const char*) { return -1; }
+inline hid_t H5Dopen2(hid_t, const char*, hid_t) { return -1; }
 inline hid_t H5Dget_space(hid_t) { return -1; }
 inline herr_t H5Dwrite(hid_t, hid_t, hid_t, hid_t, hid_t, const void*) { return -1; }
 inline herr_t H5Dread(hid_t, hid_t, hid_t, hid_t, hid_t, void*) { return -1; }

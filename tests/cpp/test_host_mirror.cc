@@ -150,6 +150,49 @@ int main() {
         });
         CHECK(nwritten == 4 && hbar > 0);
         CHECK(std::fabs(mass_out - mass_in) < 1e-10 * mass_in);      // the drift is unitary: total mass is conserved
+        // the same branch spelled like the reference's host code (src/ic_generator.cc:690-801): Grid_FFT<ccomplex_t> with host
+        // lambdas on the mirror, transforms on the device - density and v_z must equal what the named device operations gave
+        std::vector<double> dens_dev(n * n * n), vz_dev(n * n * n), dens_ref, vz_ref;
+        {
+            Grid_FFT<real_t> r2(N, L), p2(N, L), out(N, L);
+            Fill_Grid(r2, 5); r2 *= 0.05; Fill_Grid(p2, 6); p2 *= 1e-3;
+            r2.FourierTransformForward();
+            const real_t Dp = 0.0257, vfac = 396.69, boxlen = 100.0;
+            ppt::run(r2, p2, nullptr, out, 1, Dp, vfac, boxlen, Csp, 1.0, [&](Grid_FFT<real_t>& g, int comp) {
+                if (comp != 0 && comp != 3) return;
+                auto& dst = comp == 0 ? dens_dev : vz_dev;
+                for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) dst[(i * n + j) * n + k] = g.relem(i, j, k);
+            });
+            Grid_FFT<real_t> rr(N, L), pp(N, L), tt(N, L);
+            Fill_Grid(rr, 5); rr *= 0.05; Fill_Grid(pp, 6); pp *= 1e-3;
+            rr.FourierTransformForward(); rr.zero_DC_mode(); rr.FourierTransformBackward();
+            rr.apply_function_r([&](auto prho) { return std::sqrt(1.0 + Csp * prho); });
+            Grid_FFT<ccomplex_t> psi(N, L);
+            psi.assign_function_of_grids_r([hbar, Dp](real_t pphi, real_t prho) { return prho * std::exp(ccomplex_t(0.0, 1.0 / hbar) * (pphi / Dp)); }, pp, rr);
+            psi.FourierTransformForward();
+            psi.apply_function_k_dep([hbar, Dp](auto epsi, auto k) { return epsi * std::exp(-ccomplex_t(0.0, 0.5) * hbar * k.norm_squared() * Dp); });
+            psi.FourierTransformBackward();
+            rr.assign_function_of_grids_r([&](auto p) { return std::real(p) * std::real(p) + std::imag(p) * std::imag(p) - 1.0; }, psi);
+            Grid_FFT<ccomplex_t> grad_psi(N, L);
+            const real_t vunit = Dp * vfac / boxlen;
+            const int idim = 2;
+            grad_psi.FourierTransformBackward(false);
+            grad_psi.copy_from(psi);
+            grad_psi.FourierTransformForward();
+            grad_psi.apply_function_k_dep([&](auto x, auto k) { return x * ccomplex_t(0.0, k[idim]); });
+            grad_psi.FourierTransformBackward();
+            tt.FourierTransformBackward(false);
+            tt.assign_function_of_grids_r([&](auto ppsi, auto pgrad_psi, auto prho) {
+                return vunit * std::real((std::conj(ppsi) * pgrad_psi - ppsi * std::conj(pgrad_psi)) / ccomplex_t(0.0, 2.0 / hbar) / real_t(1.0 + prho));
+            }, psi, grad_psi, rr);
+            double dmax = 0, vmax = 0, ed = 0, ev = 0;
+            for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) for (size_t k = 0; k < n; ++k) {
+                const size_t q = (i * n + j) * n + k;
+                dmax = std::max(dmax, std::fabs(dens_dev[q])); vmax = std::max(vmax, std::fabs(vz_dev[q]));
+                ed = std::max(ed, std::fabs(rr.relem(i, j, k) - dens_dev[q])); ev = std::max(ev, std::fabs(tt.relem(i, j, k) - vz_dev[q]));
+            }
+            CHECK(dmax > 0 && vmax > 0 && ed < 1e-11 * dmax && ev < 1e-10 * vmax);
+        }
     }
     // particles: ids of a bcc load (include/particle_generator.hh:150-169)
     mock_config cf;

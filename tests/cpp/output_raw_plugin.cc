@@ -1,0 +1,55 @@
+// tests/cpp/output_raw_plugin.cc - TEST INFRASTRUCTURE: an output plugin written against the reference's UNCHANGED plugin API
+// (include/output_plugin.hh:33-123: virtual interface + self-registering output_plugin_creator_concrete), selected by
+// "[output] format = mfb_raw".  It writes what the driver hands it as raw little-endian files next to [output] filename:
+//   <filename>.<SPECIES>_<component>.f64   fields [n0][n1][n2]     (raw_particles = no: species as Lagrangian fields, like "generic")
+//   <filename>.<SPECIES>.{pos,vel}.f64 / .ids.u64 / .mass.f64       (raw_particles = yes: the particle container, like "gadget")
+// so that tests/test_reference_driver.py can read the output of the reference's own executable without HDF5.
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <output_plugin.hh>
+
+class raw_output_plugin : public output_plugin {
+    bool particles_;
+    static std::string species(const cosmo_species& s) { return s == cosmo_species::dm ? "DM" : (s == cosmo_species::baryon ? "BA" : "NU"); }
+    static void dump(const std::string& name, const void* p, size_t bytes) {
+        FILE* f = std::fopen(name.c_str(), "wb");
+        if (!f) throw std::runtime_error("mfb_raw: cannot open " + name);
+        if (bytes && std::fwrite(p, 1, bytes, f) != bytes) { std::fclose(f); throw std::runtime_error("mfb_raw: short write to " + name); }
+        std::fclose(f);
+    }
+
+public:
+    explicit raw_output_plugin(config_file& cf, std::unique_ptr<cosmology::calculator>& pcc) : output_plugin(cf, pcc, "raw dump") {
+        particles_ = cf_.get_value_safe<bool>("output", "raw_particles", false);
+    }
+    output_type write_species_as(const cosmo_species&) const { return particles_ ? output_type::particles : output_type::field_lagrangian; }
+    bool has_64bit_reals() const { return true; }
+    bool has_64bit_ids() const { return true; }
+    real_t position_unit() const { return 1.0; }
+    real_t velocity_unit() const { return 1.0; }
+    real_t mass_unit() const { return 1.0; }
+
+    void write_grid_data(const Grid_FFT<real_t>& g, const cosmo_species& s, const fluid_component& c) {
+        static const char* comp[] = {"delta", "vx", "vy", "vz", "dx", "dy", "dz"};
+        std::vector<double> v(g.n_[0] * g.n_[1] * g.n_[2]);
+        for (size_t i = 0; i < g.size(0); ++i)
+            for (size_t j = 0; j < g.size(1); ++j)
+                for (size_t k = 0; k < g.size(2); ++k) v[(i * g.size(1) + j) * g.size(2) + k] = g.relem(i, j, k);
+        dump(fname_ + "." + species(s) + "_" + comp[int(c)] + ".f64", v.data(), v.size() * sizeof(double));
+    }
+    void write_particle_data(const particle::container& pc, const cosmo_species& s, double) {
+        const std::string base = fname_ + "." + species(s);
+        const size_t np = pc.get_local_num_particles();
+        dump(base + ".pos.f64", pc.get_pos64_ptr(), 3 * np * sizeof(double));
+        dump(base + ".vel.f64", pc.get_vel64_ptr(), 3 * np * sizeof(double));
+        dump(base + ".ids.u64", pc.get_ids64_ptr(), np * sizeof(uint64_t));
+        if (pc.bhas_individual_masses_) dump(base + ".mass.f64", pc.get_mass64_ptr(), np * sizeof(double));
+    }
+};
+
+namespace {
+output_plugin_creator_concrete<raw_output_plugin> creator_raw("mfb_raw");
+}

@@ -60,6 +60,15 @@ namespace mfb_detail {
 inline void check(int rc) {
     if (rc != 0) throw std::runtime_error(mfb_last_error());
 }
+// a host whose main() knows nothing of the library (the reference's src/main.cc as it is) gets the device selected at the first
+// grid allocation: $MFB_DEVICE or device 0.  mfb_init is idempotent, so a host that called it (or mfb_dist_init) itself keeps its choice.
+inline void ensure_init() {
+    static bool done = false;
+    if (done) return;
+    const char* dev = std::getenv("MFB_DEVICE");
+    check(mfb_init(dev ? std::atoi(dev) : 0));
+    done = true;
+}
 }  // namespace mfb_detail
 
 // like the reference (include/grid_fft.hh:31-40): a host built with USE_MPI (one rank per GPU) gets slab grids by default
@@ -109,6 +118,7 @@ public:
 
     void allocate() {  // src/grid_fft.cc:40-112 (non-distributed branch)
         if (ballocated_) return;
+        mfb_detail::ensure_init();
         int n[3] = {int(n_[0]), int(n_[1]), int(n_[2])};
         double L[3] = {length_[0], length_[1], length_[2]};
         mfb_detail::check(mfb_grid_create(&h_, n, L, space_ == kspace_id ? MFB_KSPACE : MFB_RSPACE));

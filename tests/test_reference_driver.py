@@ -1,0 +1,148 @@
+"""The reference's OWN executable on the library: main.cc, ic_generator.cc (the numerical driver, host lambdas and all), the
+cosmology calculator, the plugin factories and the Eisenstein&Hu / NGenIC plugins, every source compiled UNMODIFIED where it
+lies under /root/reference against the drop-in headers (tests/cpp/Makefile), run on the reference's own regression
+configuration (tests/configs/test_*lpt_*.conf: 32^3, L = 100, z = 50, Planck2018EE+BAO+SN, seed 12345) with the output
+plugin swapped for tests/cpp/output_raw_plugin.cc (the reference's plugin API; raw files instead of HDF5, which is not
+installed).  Only src/grid_fft.cc is absent: FFTs, dealiased products, Poisson solves and the particle read-out run in
+libmfb200 (CPU: the thread-emulation build of the same kernels; GPU: the prebuilt executable travels to the box).
+
+Check, as for the reference's goldens (tests/golden_util.py): phi(1) is recovered from the density field of the
+1LPT run, the CPU oracle is run on it, and every displacement / velocity / density field and the particle container of the
+1LPT / 2LPT / 3LPT runs must agree with the oracle to 1e-12 of the field maximum (north_star: 1e-9); ids exact.
+The generator behind the NGenIC plugin here is not GSL's ranlxd1 (tests/cpp/gslmini.cc), so the noise differs from the
+committed goldens; the growth factors do not: vfac of the run equals the goldens' to 1e-9."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import lpt_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "tests", "cpp")
+N, L = 32, 100.0
+FIELDS = ["delta", "dx", "dy", "dz", "vx", "vy", "vz"]
+TOL = 1e-12
+
+CONF = """[setup]
+GridRes         = 32
+BoxLength       = 100
+zstart          = 50.0
+LPTorder        = {order}
+DoBaryons       = {baryons}
+DoBaryonVrel    = no
+DoFixing        = no
+DoInversion     = no
+DoRemoveCornerModes = no
+ParticleLoad    = {lattice}
+[cosmology]
+ParameterSet    = Planck2018EE+BAO+SN
+ZeroRadiation   = false
+transfer        = eisenstein
+[random]
+generator       = NGENIC
+seed            = 12345
+[execution]
+NumThreads      = 1
+[output]
+format          = mfb_raw
+filename        = {name}
+raw_particles   = {particles}
+"""
+
+
+def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False):
+    conf = os.path.join(tmp, name + ".conf")
+    with open(conf, "w") as f:
+        f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
+                            baryons="yes" if baryons else "no"))
+    r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "Have a nice day" in r.stdout
+    return r.stdout
+
+
+def _fields(tmp, name, species="DM"):
+    return {c: np.fromfile(os.path.join(tmp, f"{name}.{species}_{c}.f64")).reshape(N, N, N) for c in FIELDS}
+
+
+def _check(exe, tmp):
+    tmp = str(tmp)
+    g = O.GridSpec(N, L)
+    # ---- 1LPT: recover phi_s = g1 * phi(1) and vfac from the run's own output (golden_util.bootstrap)
+    out = _run(exe, tmp, "o1", 1)
+    assert "eisenstein" in out and "NGENIC" in out.upper()
+    d1 = _fields(tmp, "o1")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        phi_s = g.fwd(d1["delta"]) / g.k2()
+    phi_s[0, 0, 0] = 0.0
+    m = np.abs(d1["dx"]) > 1e-4 * np.abs(d1["dx"]).max()
+    vfac = float(np.median(d1["vx"][m] / d1["dx"][m]))
+    assert abs(vfac / 396.6919511923062 - 1.0) < 1e-9   # the goldens' value: the cosmology calculator ran on the stand-in quadrature / splines
+    assert 0.03 < d1["delta"].std() < 0.12             # sigma of the linear density at z = 50 on this grid (golden: 0.064)
+    prev = None
+    for order in (1, 2, 3):
+        name = f"o{order}"
+        if order > 1:
+            _run(exe, tmp, name, order)
+        d = _fields(tmp, name)
+        pots = O.lpt_potentials(g, phi_s, order, -1.0)
+        f = O.fields(g, pots, order, vfac)
+        for c in FIELDS:
+            err = np.abs(f[c] - d[c]).max() / np.abs(d[c]).max()
+            assert err < TOL, (order, c, err)
+        if prev is not None:   # each order really adds its term
+            assert np.abs(d["dx"] - prev["dx"]).max() > 1e-5 * np.abs(d["dx"]).max()
+        prev = d
+    # ---- particles: 3LPT on a bcc lattice through particle::lattice_generator and the output plugin's container access
+    _run(exe, tmp, "p3", 3, lattice="bcc", particles=True)
+    pots = O.lpt_potentials(g, phi_s, 3, -1.0)
+    lt = O.LATTICE_TYPES["bcc"]
+    pos = np.fromfile(os.path.join(tmp, "p3.DM.pos.f64")).reshape(-1, 3)
+    vel = np.fromfile(os.path.join(tmp, "p3.DM.vel.f64")).reshape(-1, 3)
+    ids = np.fromfile(os.path.join(tmp, "p3.DM.ids.u64"), dtype=np.uint64)
+    assert np.array_equal(ids, O.particle_ids(N, lt, 0, True))
+    for dd in range(3):
+        dr = g.bwd(O.displacement_k(g, pots, 3, dd, 1.0 / L))
+        vr = g.bwd(O.velocity_k(g, pots, 3, dd, vfac, 1.0 / L))
+        assert np.abs(O.set_positions(g, dr, dd, lt, 0, 1.0, True) - pos[:, dd]).max() < 1e-14
+        v = O.set_velocities(g, vr, lt, 0, True)
+        assert np.abs(v - vel[:, dd]).max() < TOL * np.abs(v).max()
+
+    # ---- two species (DoBaryons): dark matter on the primary sc lattice, baryons on the shifted secondary one with id offset
+    # 1 and per-particle masses (src/ic_generator.cc:636-680); E&H has no distinct baryon transfer function, so rho_bc = 0
+    _run(exe, tmp, "b2", 2, lattice="sc", particles=True, baryons=True)
+    pots = O.lpt_potentials(g, phi_s, 2, -1.0)
+    omega_b, omega_m = 0.0488911, 0.3099      # printed by the run ("Cosmological parameters are"); masses checked to 1e-5
+    for species, index, omega in (("DM", 0, omega_m - omega_b), ("BA", 1, omega_b)):
+        pos = np.fromfile(os.path.join(tmp, f"b2.{species}.pos.f64")).reshape(-1, 3)
+        vel = np.fromfile(os.path.join(tmp, f"b2.{species}.vel.f64")).reshape(-1, 3)
+        ids = np.fromfile(os.path.join(tmp, f"b2.{species}.ids.u64"), dtype=np.uint64)
+        mass = np.fromfile(os.path.join(tmp, f"b2.{species}.mass.f64"))
+        assert np.array_equal(ids, O.particle_ids(N, 0, index, True)), species
+        for dd in range(3):
+            dr = g.bwd(O.displacement_k(g, pots, 2, dd, 1.0 / L))
+            vr = g.bwd(O.velocity_k(g, pots, 2, dd, vfac, 1.0 / L))
+            assert np.abs(O.set_positions(g, dr, dd, 0, index, 1.0, True) - pos[:, dd]).max() < 1e-14, species
+            v = O.set_velocities(g, vr, 0, index, True)
+            assert np.abs(v - vel[:, dd]).max() < TOL * np.abs(v).max(), species
+        assert mass.shape == (N ** 3,) and np.allclose(mass, omega / N ** 3, rtol=1e-5), (species, mass[:3], omega / N ** 3)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_reference_executable_on_the_emulated_library(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check(os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp_path)
+
+
+@pytest.mark.gpu
+def test_reference_executable_on_the_gpu(tmp_path):
+    exe = os.path.join(CPP, "_dropin", "monofonIC_mfb")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_dropin/monofonIC_mfb was not built (needs /root/reference at build time; __graft_entry__.build())")
+    _check(exe, tmp_path)

@@ -12,6 +12,7 @@
 
 #include <gsl/gsl_errno.h>
 #include <gsl/gsl_integration.h>
+#include <gsl/gsl_randist.h>
 #include <gsl/gsl_rng.h>
 #include <gsl/gsl_spline.h>
 
@@ -140,6 +141,18 @@ unsigned long int gsl_rng_get(const gsl_rng* r) {
 }
 double gsl_rng_uniform(const gsl_rng* r) { return double(gsl_rng_get(r) >> 11) * (1.0 / 9007199254740992.0); }
 double gsl_rng_uniform_pos(const gsl_rng* r) { double x; do x = gsl_rng_uniform(r); while (x == 0.0); return x; }
+
+// Gaussian deviates (MUSIC1 white-noise generator): Leva's ratio-of-uniforms method
+double gsl_ran_ugaussian_ratio_method(const gsl_rng* r) {
+    for (;;) {
+        const double u = 1.0 - gsl_rng_uniform(r), v = 1.7156 * (gsl_rng_uniform(r) - 0.5);
+        const double x = u - 0.449871, y = std::fabs(v) + 0.386595, q = x * x + y * (0.19600 * y - 0.25472 * x);
+        if (q < 0.27597 || (q <= 0.27846 && v * v <= -4.0 * u * u * std::log(u))) return v / u;
+    }
+}
+double gsl_ran_ugaussian(const gsl_rng* r) { return gsl_ran_ugaussian_ratio_method(r); }
+double gsl_ran_gaussian(const gsl_rng* r, const double sigma) { return sigma * gsl_ran_ugaussian_ratio_method(r); }
+double gsl_ran_flat(const gsl_rng* r, const double a, const double b) { return a + (b - a) * gsl_rng_uniform(r); }
 
 // ------------------------------------------------------------------ error handling
 gsl_error_handler_t* gsl_set_error_handler_off(void) { return nullptr; }

@@ -41,8 +41,7 @@ ParameterSet    = Planck2018EE+BAO+SN
 ZeroRadiation   = false
 transfer        = eisenstein
 [random]
-generator       = NGENIC
-seed            = 12345
+{random}
 [execution]
 NumThreads      = 1
 [output]
@@ -52,11 +51,15 @@ raw_particles   = {particles}
 """
 
 
-def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False):
+RANDOM = {"NGENIC": "generator       = NGENIC\nseed            = 12345",
+          "MUSIC1": "generator       = MUSIC1\nseed[5]         = 12345"}   # MUSIC1: one seed per level, levelmin = log2(32)
+
+
+def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC"):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
-                            baryons="yes" if baryons else "no"))
+                            baryons="yes" if baryons else "no", random=RANDOM[generator]))
     r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "Have a nice day" in r.stdout
@@ -73,6 +76,10 @@ def _check(exe, tmp):
     # ---- 1LPT: recover phi_s = g1 * phi(1) and vfac from the run's own output (golden_util.bootstrap)
     out = _run(exe, tmp, "o1", 1)
     assert "eisenstein" in out and "NGENIC" in out.upper()
+    # the self-registering factories of the reference know every plugin that was linked in (printed when run without arguments)
+    listing = subprocess.run([exe], capture_output=True, text=True).stdout
+    for plugin in ("'CAMB_file'", "'eisenstein'", "'MUSIC1'", "'NGENIC'", "'gadget_hdf5'", "'SWIFT'", "'AREPO'", "'grafic2'", "'generic'", "'mfb_raw'"):
+        assert plugin in listing, plugin
     d1 = _fields(tmp, "o1")
     with np.errstate(divide="ignore", invalid="ignore"):
         phi_s = g.fwd(d1["delta"]) / g.k2()
@@ -128,6 +135,20 @@ def _check(exe, tmp):
             v = O.set_velocities(g, vr, 0, index, True)
             assert np.abs(v - vel[:, dd]).max() < TOL * np.abs(v).max(), species
         assert mass.shape == (N ** 3,) and np.allclose(mass, omega / N ** 3, rtol=1e-5), (species, mass[:3], omega / N ** 3)
+
+    # ---- the MUSIC1 noise plugin (random_music.cc + its white-noise generator, which runs FFTs of its own): real-space noise
+    # with POPULATED Nyquist planes - the case where the pad / unpad semantics of the reference's MPI build matter
+    for order in (1, 2):
+        _run(exe, tmp, f"m{order}", order, generator="MUSIC1")
+    m1, m2 = _fields(tmp, "m1"), _fields(tmp, "m2")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        phi_m = g.fwd(m1["delta"]) / g.k2()
+    phi_m[0, 0, 0] = 0.0
+    assert np.abs(phi_m[N // 2]).max() > 1e-6 * np.abs(phi_m).max()      # Nyquist planes carry power
+    f = O.fields(g, O.lpt_potentials(g, phi_m, 2, -1.0), 2, vfac)
+    for c in FIELDS:
+        err = np.abs(f[c] - m2[c]).max() / np.abs(m2[c]).max()
+        assert err < TOL, ("MUSIC1", c, err)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")

@@ -643,6 +643,10 @@ def run_b200(args):
                 "alg_bytes_per_launch": dom["alg_gb_per_launch"] * 1e9,
                 "frac_of_8000_nominal": dom["gbs"] / 8000.0,
                 "per_kernel_frac": {r["role"]: r["gbs"] / peak for r in fftroles}}
+    if traffic_note and traffic_note.get("pipes_pct_of_peak"):
+        # the dominant kernel is bound inside the SM, not by HBM: its busiest pipe in the committed ncu capture
+        pipe, pct = max(traffic_note["pipes_pct_of_peak"].items(), key=lambda kv: kv[1])
+        roofline["onchip_bound"] = {"pipe": pipe, "frac_of_pipe_peak": pct / 100.0, "source": "ncu capture named in traffic_capture"}
     total_alg = sum(r["alg_gb_per_launch"] * r["launches_per_step"] for r in fftroles)
     sinfo = pl.conv.sources_info() if pl.conv is not None else {"path": 0}
 

@@ -163,7 +163,9 @@ public:
     size_t get_cell_idx_1d(size_t i, size_t j, size_t k) const noexcept { return ((i + local_0_start_) * n_[1] + j) * n_[2] + k; }
     real_t get_dx(int idim) const noexcept { return dx_[idim]; }
     const std::array<real_t, 3>& get_dx() const noexcept { return dx_; }
-    bool is_nyquist_mode(size_t i, size_t j, size_t k) const { return i == n_[0] / 2 || j == n_[1] / 2 || k == n_[2] / 2; }
+    bool is_nyquist_mode(size_t i, size_t j, size_t k) const {   // include/grid_fft.hh:140-147 (first index: local k_y row on slabs)
+        return (i + size_t(local_1_start_) == n_[1] / 2) || (j == n_[0] / 2) || (k == n_[2] / 2);
+    }
     template <typename ft> vec3_t<ft> get_k(size_t i, size_t j, size_t k) const noexcept {   // include/grid_fft.hh:281-296
         if (bdistributed) {   // transposed slab: the first index runs over the local ky rows
             const size_t ip = i + size_t(local_1_start_);

@@ -23,10 +23,14 @@
 #include <complex>
 #include <cstddef>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
 #include "../mfb200.h"
+#ifdef USE_MPI
+#include <mpi.h>
+#endif
 
 #ifndef MFB_HAVE_REFERENCE_GENERAL_HH
 using real_t = double;                   // CODE_PRECISION=DOUBLE (include/general.hh:50-53)
@@ -61,12 +65,45 @@ inline void check(int rc) {
     if (rc != 0) throw std::runtime_error(mfb_last_error());
 }
 // a host whose main() knows nothing of the library (the reference's src/main.cc as it is) gets the device selected at the first
-// grid allocation: $MFB_DEVICE or device 0.  mfb_init is idempotent, so a host that called it (or mfb_dist_init) itself keeps its choice.
-inline void ensure_init() {
+// grid allocation: $MFB_DEVICE, else (MPI rank) % (visible devices) in a USE_MPI build, else device 0.  mfb_init is idempotent, so a host that
+// called it (or mfb_dist_init) itself keeps its choice.
+// USE_MPI build with more than one rank: one rank per GPU, every grid a slab (src/grid_fft.cc:115-192).  The ranks exchange the
+// 64-byte handles of their peer-mapped exchange blocks once (MPI_Allgather) and the slab transposes then run inside the FFT
+// passes over NVLink; with the thread-emulation build of the kernels (CPU tests) or $MFB_STAGED_EXCHANGE the exchange is handed
+// to MPI_Alltoall instead (mfb_dist_init_staged).  `n` is the first grid of the run (GridRes^3 in ic_generator::run): the
+// exchange buffers are sized for it and for its 3/2-padded products.  A host that wants the resident-spectra source stage
+// calls mfb_dist_init_slots itself before its first grid (monofonic_b200/dist.py: pick_nslots).
+#ifdef USE_MPI
+inline void mpi_exchange(const void* send, void* recv, size_t chunk_bytes, void*) {
+    MPI_Alltoall(send, int(chunk_bytes / sizeof(double)), MPI_DOUBLE, recv, int(chunk_bytes / sizeof(double)), MPI_DOUBLE, MPI_COMM_WORLD);
+}
+#endif
+inline void ensure_init(const int n[3]) {
     static bool done = false;
     if (done) return;
     const char* dev = std::getenv("MFB_DEVICE");
-    check(mfb_init(dev ? std::atoi(dev) : 0));
+    int rank = 0, size = 1;
+#ifdef USE_MPI
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &size);
+#endif
+    const int ndev = mfb_device_count();
+    check(mfb_init(dev ? std::atoi(dev) : (ndev > 0 ? rank % ndev : 0)));
+#ifdef USE_MPI
+    if (size > 1 && mfb_dist_nranks() <= 1) {
+        const size_t xbuf = mfb_dist_xbuf_bytes(n, 1, size);
+        if (std::strstr(mfb_build_info(), "emulation") || std::getenv("MFB_STAGED_EXCHANGE")) {
+            check(mfb_dist_init_staged(rank, size, xbuf, mpi_exchange, nullptr));
+        } else {
+            char mine[64];
+            std::vector<char> all(size_t(64) * size);
+            check(mfb_dist_init(rank, size, xbuf, mine));
+            MPI_Allgather(mine, 64, MPI_CHAR, all.data(), 64, MPI_CHAR, MPI_COMM_WORLD);
+            check(mfb_dist_connect(all.data()));
+        }
+    }
+#endif
+    (void)n; (void)size;
     done = true;
 }
 }  // namespace mfb_detail
@@ -118,9 +155,9 @@ public:
 
     void allocate() {  // src/grid_fft.cc:40-112 (non-distributed branch)
         if (ballocated_) return;
-        mfb_detail::ensure_init();
         int n[3] = {int(n_[0]), int(n_[1]), int(n_[2])};
         double L[3] = {length_[0], length_[1], length_[2]};
+        mfb_detail::ensure_init(n);
         mfb_detail::check(mfb_grid_create(&h_, n, L, space_ == kspace_id ? MFB_KSPACE : MFB_RSPACE));
         int loc[4];
         const bool slab = mfb_grid_local(h_, loc) != 0;   // {local_0_start_, local_0_size_, local_1_start_, local_1_size_}

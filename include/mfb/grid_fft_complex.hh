@@ -84,9 +84,9 @@ public:
     }
     void allocate() {
         if (ballocated_) return;
-        mfb_detail::ensure_init();
         int n[3] = {int(n_[0]), int(n_[1]), int(n_[2])};
         double L[3] = {length_[0], length_[1], length_[2]};
+        mfb_detail::ensure_init(n);
         mfb_detail::check(mfb_cgrid_create(&h_, n, L));
         int loc[4];
         if (mfb_cgrid_local(h_, loc) != 0 || bdistributed) {

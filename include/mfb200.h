@@ -39,6 +39,7 @@ enum { MFB_LATTICE_SC = 0, MFB_LATTICE_BCC = 1, MFB_LATTICE_FCC = 2, MFB_LATTICE
 typedef struct mfb_gradient mfb_gradient;
 
 /* ---- library / device ------------------------------------------------------------------ */
+int mfb_device_count(void);          /* CUDA devices visible to this process (0: none) */
 int mfb_init(int device);            /* selects the CUDA device, creates the stream; fails without a GPU */
 int mfb_finalize(void);
 const char* mfb_last_error(void);

@@ -24,6 +24,7 @@ def _declare(lib):
     vpp = C.POINTER(C.c_void_p)
     sig = {
         "mfb_init": (i, [i]),
+        "mfb_device_count": (i, []),
         "mfb_finalize": (i, []),
         "mfb_last_error": (C.c_char_p, []),
         "mfb_build_info": (C.c_char_p, []),

@@ -1288,6 +1288,12 @@ const char* mfb_build_info(void) {
 #endif
 }
 
+/* CUDA devices visible to this process (0 without a GPU or on error): a host with one rank per GPU picks rank % count */
+int mfb_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ndev;
+}
 int mfb_init(int device) {
     MFB_TRY
     if (g_ctx.initialised) return 0;

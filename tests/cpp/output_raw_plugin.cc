@@ -3,6 +3,7 @@
 // "[output] format = mfb_raw".  It writes what the driver hands it as raw little-endian files next to [output] filename:
 //   <filename>.<SPECIES>_<component>.f64   fields [n0][n1][n2]     (raw_particles = no: species as Lagrangian fields, like "generic")
 //   <filename>.<SPECIES>.{pos,vel}.f64 / .ids.u64 / .mass.f64       (raw_particles = yes: the particle container, like "gadget")
+// With more than one MPI rank every rank writes its slab / its particles to <filename>.r<rank>.*
 // so that tests/test_reference_driver.py can read the output of the reference's own executable without HDF5.
 #include <cstdint>
 #include <cstdio>
@@ -24,6 +25,7 @@ class raw_output_plugin : public output_plugin {
 public:
     explicit raw_output_plugin(config_file& cf, std::unique_ptr<cosmology::calculator>& pcc) : output_plugin(cf, pcc, "raw dump") {
         particles_ = cf_.get_value_safe<bool>("output", "raw_particles", false);
+        if (CONFIG::MPI_task_size > 1) fname_ += ".r" + std::to_string(CONFIG::MPI_task_rank);   // one set of files per rank: its slab
     }
     output_type write_species_as(const cosmo_species&) const { return particles_ ? output_type::particles : output_type::field_lagrangian; }
     bool has_64bit_reals() const { return true; }
@@ -34,7 +36,7 @@ public:
 
     void write_grid_data(const Grid_FFT<real_t>& g, const cosmo_species& s, const fluid_component& c) {
         static const char* comp[] = {"delta", "vx", "vy", "vz", "dx", "dy", "dz"};
-        std::vector<double> v(g.n_[0] * g.n_[1] * g.n_[2]);
+        std::vector<double> v(g.size(0) * g.size(1) * g.size(2));   // the local planes (the whole grid on one rank)
         for (size_t i = 0; i < g.size(0); ++i)
             for (size_t j = 0; j < g.size(1); ++j)
                 for (size_t k = 0; k < g.size(2); ++k) v[(i * g.size(1) + j) * g.size(2) + k] = g.relem(i, j, k);

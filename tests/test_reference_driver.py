@@ -10,7 +10,13 @@ Check, as for the reference's goldens (tests/golden_util.py): phi
 1LPT run, the CPU oracle is run on it, and every displacement / velocity / density field and the particle container of the
 1LPT / 2LPT / 3LPT runs must agree with the oracle to 1e-12 of the field maximum (north_star: 1e-9); ids exact.
 The generator behind the NGenIC plugin here is not GSL's ranlxd1 (tests/cpp/gslmini.cc), so the noise differs from the
-committed goldens; the growth factors do not: vfac of the run equals the goldens' to 1e-9."""
+committed goldens; the growth factors do not: vfac of the run equals the goldens' to 1e-9.
+
+The reference's USE_MPI build of the same sources runs too: one process per rank (tests/cpp/minimpi stands in for the MPI
+library), every rank a slab of the library - Grid_FFT<real_t, true> in the transposed layout, MPI_Allreduce in the driver and the
+particle container, the ghost-plane ring shift of grid_interpolate.hh - with the slab transposes inside the library (CPU: staged
+through MPI_Alltoall; GPUs: peer memory after one MPI_Allgather of the IPC handles).  2 and 4 ranks must reproduce the
+single-process run of the same configuration bit for bit (fields) and particle for particle (matched by id)."""
 import os
 import subprocess
 
@@ -167,3 +173,76 @@ def test_reference_executable_on_the_gpu(tmp_path):
     if not os.path.exists(exe):
         pytest.skip("tests/cpp/_dropin/monofonIC_mfb was not built (needs /root/reference at build time; __graft_entry__.build())")
     _check(exe, tmp_path)
+
+
+def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_env=None):
+    conf = os.path.join(tmp, name + ".conf")
+    with open(conf, "w") as f:
+        f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no", baryons="no",
+                            random=RANDOM["NGENIC"]))
+    shm = os.path.join(tmp, name + ".shm")
+    with open(shm, "wb") as f:
+        f.truncate(64 + world * (64 << 20))     # sparse: header + one 64 MiB slot per rank
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, MINIMPI_RANK=str(r), MINIMPI_SIZE=str(world), MINIMPI_SHM=shm, **(extra_env or {}))
+        procs.append(subprocess.Popen([exe, conf], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=900)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, (r, o[-3000:])
+    assert "Have a nice day" in outs[0] and "MPI is enabled                   : yes" in outs[0]
+
+
+def _check_mpi(exe_mpi, exe_single, tmp, worlds):
+    tmp = str(tmp)
+    _run(exe_single, tmp, "s3", 3)
+    _run(exe_single, tmp, "sp", 3, lattice="bcc", particles=True)
+    single = _fields(tmp, "s3")
+    sp = {k: np.fromfile(os.path.join(tmp, "sp.DM." + k), dtype=np.uint64 if k.endswith("u64") else np.float64) for k in ("pos.f64", "vel.f64", "ids.u64")}
+    order = np.argsort(sp["ids.u64"])
+    for world in worlds:
+        name = f"m3w{world}"
+        _run_mpi(exe_mpi, tmp, name, world, 3)
+        for c in FIELDS:   # slabs along axis 0, in rank order
+            got = np.concatenate([np.fromfile(os.path.join(tmp, f"{name}.r{r}.DM_{c}.f64")).reshape(-1, N, N) for r in range(world)])
+            assert got.shape == (N, N, N)
+            assert np.abs(got - single[c]).max() <= 1e-13 * np.abs(single[c]).max(), (world, c)
+        name = f"mpw{world}"
+        _run_mpi(exe_mpi, tmp, name, world, 3, lattice="bcc", particles=True)
+        ids = np.concatenate([np.fromfile(os.path.join(tmp, f"{name}.r{r}.DM.ids.u64"), dtype=np.uint64) for r in range(world)])
+        assert len(ids) == 2 * N ** 3 and len(np.unique(ids)) == len(ids)
+        o2 = np.argsort(ids)
+        assert np.array_equal(ids[o2], sp["ids.u64"][order])
+        for k in ("pos.f64", "vel.f64"):
+            got = np.concatenate([np.fromfile(os.path.join(tmp, f"{name}.r{r}.DM.{k}")).reshape(-1, 3) for r in range(world)])
+            ref = sp[k].reshape(-1, 3)
+            assert np.abs(got[o2] - ref[order]).max() <= 1e-13 * np.abs(ref).max(), (world, k)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_reference_mpi_executable_on_slabs_of_the_emulated_library(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check_mpi(os.path.join(CPP, "_dropin", "monofonIC_mfb_mpi_emu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp_path, (2, 4))
+
+
+@pytest.mark.gpu
+def test_reference_mpi_executable_on_two_gpus(tmp_path):
+    import torch
+
+    exe = os.path.join(CPP, "_dropin", "monofonIC_mfb_mpi")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_dropin/monofonIC_mfb_mpi was not built (needs /root/reference at build time)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (one rank per GPU, exchange over peer memory)")
+    _check_mpi(exe, os.path.join(CPP, "_dropin", "monofonIC_mfb"), tmp_path, (2,))

@@ -13,7 +13,7 @@
 #include <output_plugin.hh>
 
 class raw_output_plugin : public output_plugin {
-    bool particles_;
+    bool particles_, eulerian_;
     static std::string species(const cosmo_species& s) { return s == cosmo_species::dm ? "DM" : (s == cosmo_species::baryon ? "BA" : "NU"); }
     static void dump(const std::string& name, const void* p, size_t bytes) {
         FILE* f = std::fopen(name.c_str(), "wb");
@@ -25,9 +25,12 @@ class raw_output_plugin : public output_plugin {
 public:
     explicit raw_output_plugin(config_file& cf, std::unique_ptr<cosmology::calculator>& pcc) : output_plugin(cf, pcc, "raw dump") {
         particles_ = cf_.get_value_safe<bool>("output", "raw_particles", false);
+        eulerian_ = cf_.get_value_safe<bool>("output", "raw_eulerian", false);   // Eulerian fields: the semiclassical (PPT) branch, like generic_out_eulerian
         if (CONFIG::MPI_task_size > 1) fname_ += ".r" + std::to_string(CONFIG::MPI_task_rank);   // one set of files per rank: its slab
     }
-    output_type write_species_as(const cosmo_species&) const { return particles_ ? output_type::particles : output_type::field_lagrangian; }
+    output_type write_species_as(const cosmo_species&) const {
+        return eulerian_ ? output_type::field_eulerian : (particles_ ? output_type::particles : output_type::field_lagrangian);
+    }
     bool has_64bit_reals() const { return true; }
     bool has_64bit_ids() const { return true; }
     real_t position_unit() const { return 1.0; }

@@ -54,6 +54,7 @@ NumThreads      = 1
 format          = mfb_raw
 filename        = {name}
 raw_particles   = {particles}
+raw_eulerian    = {eulerian}
 """
 
 
@@ -61,11 +62,11 @@ RANDOM = {"NGENIC": "generator       = NGENIC\nseed            = 12345",
           "MUSIC1": "generator       = MUSIC1\nseed[5]         = 12345"}   # MUSIC1: one seed per level, levelmin = log2(32)
 
 
-def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC"):
+def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC", eulerian=False):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
-                            baryons="yes" if baryons else "no", random=RANDOM[generator]))
+                            baryons="yes" if baryons else "no", random=RANDOM[generator], eulerian="yes" if eulerian else "no"))
     r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "Have a nice day" in r.stdout
@@ -142,6 +143,19 @@ def _check(exe, tmp):
             assert np.abs(v - vel[:, dd]).max() < TOL * np.abs(v).max(), species
         assert mass.shape == (N ** 3,) and np.allclose(mass, omega / N ** 3, rtol=1e-5), (species, mass[:3], omega / N ** 3)
 
+    # ---- Eulerian output: the semiclassical (PPT) branch of the driver (src/ic_generator.cc:685-803) as written - host lambdas on
+    # Grid_FFT<ccomplex_t> (the specialisation of include/mfb/grid_fft_complex.hh), c2c transforms on the device.  E&H has no
+    # distinct baryon transfer function, so rho_bc = 0; D+ cancels out of every output (hbar ~ 1/D+).
+    for order in (1, 2):
+        out = _run(exe, tmp, f"e{order}", order, eulerian=True)
+        assert "Semiclassical PT : hbar" in out
+        e = {c: np.fromfile(os.path.join(tmp, f"e{order}.DM_{c}.f64")).reshape(N, N, N) for c in ("delta", "vx", "vy", "vz")}
+        pots = O.lpt_potentials(g, phi_s, order, -1.0)
+        ref, hbar = O.ppt_eulerian(g, np.zeros_like(phi_s), pots, order, 0.0251908, vfac, lambda k: 0.0 * k, 1.0)
+        for c, r in (("delta", ref["density"]), ("vx", ref["vx"]), ("vy", ref["vy"]), ("vz", ref["vz"])):
+            err = np.abs(e[c] - r).max() / np.abs(r).max()
+            assert err < 1e-9, ("PPT", order, c, err)
+
     # ---- the MUSIC1 noise plugin (random_music.cc + its white-noise generator, which runs FFTs of its own): real-space noise
     # with POPULATED Nyquist planes - the case where the pad / unpad semantics of the reference's MPI build matter
     for order in (1, 2):
@@ -179,7 +193,7 @@ def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no", baryons="no",
-                            random=RANDOM["NGENIC"]))
+                            random=RANDOM["NGENIC"], eulerian="no"))
     shm = os.path.join(tmp, name + ".shm")
     with open(shm, "wb") as f:
         f.truncate(64 + world * (64 << 20))     # sparse: header + one 64 MiB slot per rank

@@ -21,6 +21,7 @@ struct fftw_plan_s {
     int kind;  // 0 r2c, 1 c2r, 2 c2c
     int n0, n1, n2, sign;
     void* data;
+    int transposed = 0;   // one-rank FFTW-MPI plans with TRANSPOSED_OUT / _IN: k-space stored [k1][k0][k2]
 };
 
 namespace {
@@ -189,5 +190,41 @@ void fftw_destroy_plan(fftw_plan p) { delete p; }
 int fftw_init_threads(void) { return 1; }
 void fftw_plan_with_nthreads(int) {}
 void fftw_cleanup_threads(void) {}
-void fftw_execute(const fftw_plan p) { execute(p); }
+// [a][b][m] <-> [b][a][m] for the first two axes of a complex array
+static void swap01(cd* c, int a, int b, int m) {
+    std::vector<cd> t(size_t(a) * b * m);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < a; ++i)
+        for (int j = 0; j < b; ++j) std::memcpy(&t[(size_t(j) * a + i) * m], &c[(size_t(i) * b + j) * m], sizeof(cd) * m);
+    std::memcpy(c, t.data(), sizeof(cd) * t.size());
+}
+void fftw_execute(const fftw_plan p) {
+    if (!p->transposed) { execute(p); return; }
+    const int m = (p->kind == 2) ? p->n2 : p->n2 / 2 + 1;
+    cd* c = reinterpret_cast<cd*>(p->data);
+    const bool to_k = (p->kind == 0) || (p->kind == 2 && p->sign == -1);
+    if (to_k) { execute(p); swap01(c, p->n0, p->n1, m); }      // natural in, [k1][k0][k2] out
+    else { swap01(c, p->n1, p->n0, m); execute(p); }           // [k1][k0][k2] in, natural out
+}
+// FFTW-MPI on ONE rank (the reference's USE_MPI build, src/grid_fft.cc:120-140): the whole grid is the local slab; the integer
+// communicator argument is ignored.  Declared in fftw3-mpi.h of this directory.
+void fftw_mpi_init(void) {}
+ptrdiff_t fftw_mpi_local_size_3d_transposed(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int, ptrdiff_t* l0, ptrdiff_t* s0, ptrdiff_t* l1, ptrdiff_t* s1) {
+    *l0 = n0; *s0 = 0; *l1 = n1; *s1 = 0;
+    return n0 * n1 * n2;
+}
+static fftw_plan mkt(int kind, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int sign, void* d, bool transposed) {
+    fftw_plan p = mk(kind, int(n0), int(n1), int(n2), sign, d);
+    p->transposed = transposed ? 1 : 0;
+    return p;
+}
+fftw_plan fftw_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double* in, fftw_complex*, int, unsigned flags) {
+    return mkt(0, n0, n1, n2, -1, in, flags & (1u << 30));
+}
+fftw_plan fftw_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex* in, double*, int, unsigned flags) {
+    return mkt(1, n0, n1, n2, +1, in, flags & (1u << 29));
+}
+fftw_plan fftw_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex* in, fftw_complex*, int, int sign, unsigned flags) {
+    return mkt(2, n0, n1, n2, sign, in, flags & ((1u << 29) | (1u << 30)));
+}
 }   // extern "C"

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -127,9 +128,29 @@ int MPI_Bcast(void* buf, int count, MPI_Datatype t, int root, MPI_Comm) {
     barrier();
     return MPI_SUCCESS;
 }
-int MPI_Isend(const void*, int, MPI_Datatype, int, int, MPI_Comm, MPI_Request*) { die("MPI_Isend is not part of this stand-in"); return 1; }
-int MPI_Send(const void*, int, MPI_Datatype, int, int, MPI_Comm) { die("MPI_Send is not part of this stand-in"); return 1; }
-int MPI_Recv(void*, int, MPI_Datatype, int, int, MPI_Comm, MPI_Status*) { die("MPI_Recv is not part of this stand-in"); return 1; }
+/* point-to-point: only a rank's messages to ITSELF (what src/grid_fft.cc's FourierInterpolateCopyTo and grid_ghosts.hh do on one
+   rank - the pure-CPU reference executable of tests/cpp/Makefile); a send is kept until the matching receive */
+struct Pending { const void* buf; size_t bytes; int tag; bool done; };
+static std::vector<Pending> g_pending;
+int MPI_Isend(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm, MPI_Request* req) {
+    if (dest != g_rank) die("point-to-point between different ranks is not part of this stand-in");
+    g_pending.push_back({buf, size_t(count) * tsize(t), tag, false});
+    *req = int(g_pending.size()) - 1;
+    return MPI_SUCCESS;
+}
+int MPI_Send(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm c) { MPI_Request r; return MPI_Isend(buf, count, t, dest, tag, c, &r); }
+int MPI_Recv(void* buf, int count, MPI_Datatype t, int source, int tag, MPI_Comm, MPI_Status* st) {
+    if (source != g_rank) die("point-to-point between different ranks is not part of this stand-in");
+    for (auto& p : g_pending)
+        if (!p.done && p.tag == tag) {
+            std::memcpy(buf, p.buf, std::min(p.bytes, size_t(count) * tsize(t)));
+            p.done = true;
+            if (st) { st->MPI_SOURCE = g_rank; st->MPI_TAG = tag; st->MPI_ERROR = MPI_SUCCESS; }
+            return MPI_SUCCESS;
+        }
+    die("MPI_Recv without a matching send");
+    return 1;
+}
 /* the one point-to-point pattern of the host code outside grid_fft.cc: a ring shift every rank takes part in (include/grid_interpolate.hh:78-85) */
 int MPI_Sendrecv_replace(void* buf, int count, MPI_Datatype t, int, int, int source, int, MPI_Comm, MPI_Status* st) {
     const size_t bytes = size_t(count) * tsize(t);
@@ -143,10 +164,15 @@ int MPI_Sendrecv_replace(void* buf, int count, MPI_Datatype t, int, int, int sou
     if (st) { st->MPI_SOURCE = source; st->MPI_TAG = 0; st->MPI_ERROR = MPI_SUCCESS; }
     return MPI_SUCCESS;
 }
-int MPI_Test(MPI_Request*, int*, MPI_Status*) { die("MPI_Test is not part of this stand-in"); return 1; }
-int MPI_Wait(MPI_Request*, MPI_Status*) { die("MPI_Wait is not part of this stand-in"); return 1; }
+int MPI_Test(MPI_Request* req, int* flag, MPI_Status*) { *flag = g_pending[*req].done ? 1 : 0; return MPI_SUCCESS; }
+int MPI_Wait(MPI_Request* req, MPI_Status* st) {
+    if (st) st->MPI_ERROR = g_pending[*req].done ? MPI_SUCCESS : 1;
+    bool all = true;
+    for (auto& p : g_pending) all = all && p.done;
+    if (all && *req == int(g_pending.size()) - 1) g_pending.clear();   // last request of a batch
+    return MPI_SUCCESS;
+}
 int MPI_Alltoallv(const void*, const int*, const int*, MPI_Datatype, void*, const int*, const int*, MPI_Datatype, MPI_Comm) { die("MPI_Alltoallv is not part of this stand-in"); return 1; }
 int MPI_Exscan(const void*, void*, int, MPI_Datatype, MPI_Op, MPI_Comm) { die("MPI_Exscan is not part of this stand-in"); return 1; }
 int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int, MPI_Comm c) { return MPI_Allreduce(s, r, n, t, op, c); }   /* every rank gets the result */
-void fftw_mpi_init(void) {}   /* src/main.cc:173 */
 }

@@ -16,7 +16,13 @@ The reference's USE_MPI build of the same sources runs too: one process per rank
 library), every rank a slab of the library - Grid_FFT<real_t, true> in the transposed layout, MPI_Allreduce in the driver and the
 particle container, the ghost-plane ring shift of grid_interpolate.hh - with the slab transposes inside the library (CPU: staged
 through MPI_Alltoall; GPUs: peer memory after one MPI_Allgather of the IPC handles).  2 and 4 ranks must reproduce the
-single-process run of the same configuration bit for bit (fields) and particle for particle (matched by id)."""
+single-process run of the same configuration bit for bit (fields) and particle for particle (matched by id).
+
+And the reference ITSELF is run beside it: tests/cpp/_dropin/monofonIC_ref_cpu is the same set of sources plus the reference's own
+src/grid_fft.cc against its OWN headers - its Grid_FFT, its OrszagConvolver with the pad / unpad of its MPI build, its
+lattice_generator - with no line of this repository's library in it.  Identical configuration files and seeds go through both
+executables and every output is compared directly: north_star's "results must match the reference FFTW path on identical
+configs and noise seeds" (FFTW itself is not installed: its calls are served by the FFT of oracle/refshim/fftw_fast.cc)."""
 import os
 import subprocess
 
@@ -32,7 +38,7 @@ FIELDS = ["delta", "dx", "dy", "dz", "vx", "vy", "vz"]
 TOL = 1e-12
 
 CONF = """[setup]
-GridRes         = 32
+GridRes         = {grid}
 BoxLength       = 100
 zstart          = 50.0
 LPTorder        = {order}
@@ -49,7 +55,7 @@ transfer        = eisenstein
 [random]
 {random}
 [execution]
-NumThreads      = 1
+NumThreads      = {threads}
 [output]
 format          = mfb_raw
 filename        = {name}
@@ -59,22 +65,23 @@ raw_eulerian    = {eulerian}
 
 
 RANDOM = {"NGENIC": "generator       = NGENIC\nseed            = 12345",
-          "MUSIC1": "generator       = MUSIC1\nseed[5]         = 12345"}   # MUSIC1: one seed per level, levelmin = log2(32)
+          "MUSIC1": "generator       = MUSIC1\nseed[{level}]         = 12345"}   # MUSIC1: one seed per level, levelmin = log2(GridRes)
 
 
-def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC", eulerian=False):
+def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC", eulerian=False, grid=32, threads=1):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
-                            baryons="yes" if baryons else "no", random=RANDOM[generator], eulerian="yes" if eulerian else "no"))
+                            baryons="yes" if baryons else "no", random=RANDOM[generator].format(level=grid.bit_length() - 1),
+                            eulerian="yes" if eulerian else "no", grid=grid, threads=threads))
     r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "Have a nice day" in r.stdout
     return r.stdout
 
 
-def _fields(tmp, name, species="DM"):
-    return {c: np.fromfile(os.path.join(tmp, f"{name}.{species}_{c}.f64")).reshape(N, N, N) for c in FIELDS}
+def _fields(tmp, name, species="DM", n=N):
+    return {c: np.fromfile(os.path.join(tmp, f"{name}.{species}_{c}.f64")).reshape(n, n, n) for c in FIELDS}
 
 
 def _check(exe, tmp):
@@ -193,7 +200,7 @@ def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no", baryons="no",
-                            random=RANDOM["NGENIC"], eulerian="no"))
+                            random=RANDOM["NGENIC"], eulerian="no", grid=32, threads=1))
     shm = os.path.join(tmp, name + ".shm")
     with open(shm, "wb") as f:
         f.truncate(64 + world * (64 << 20))     # sparse: header + one 64 MiB slot per rank
@@ -260,3 +267,53 @@ def test_reference_mpi_executable_on_two_gpus(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (one rank per GPU, exchange over peer memory)")
     _check_mpi(exe, os.path.join(CPP, "_dropin", "monofonIC_mfb"), tmp_path, (2,))
+
+
+def _check_against_the_reference_itself(ref_exe, our_exe, tmp, grid, threads):
+    tmp = str(tmp)
+    worst = 0.0
+    for order in (1, 2, 3):
+        _run(ref_exe, tmp, f"r{order}", order, grid=grid, threads=threads)
+        _run(our_exe, tmp, f"d{order}", order, grid=grid, threads=threads)
+        a, b = _fields(tmp, f"r{order}", n=grid), _fields(tmp, f"d{order}", n=grid)
+        for c in FIELDS:
+            err = np.abs(a[c] - b[c]).max() / np.abs(a[c]).max()
+            worst = max(worst, err)
+            assert err < TOL, (order, c, err)
+    # particles of a 3LPT bcc load: ids exact, positions to an ulp of the box, velocities to 1e-12 of their maximum
+    _run(ref_exe, tmp, "rp", 3, lattice="bcc", particles=True, grid=grid, threads=threads)
+    _run(our_exe, tmp, "dp", 3, lattice="bcc", particles=True, grid=grid, threads=threads)
+    ids = [np.fromfile(os.path.join(tmp, f"{t}.DM.ids.u64"), dtype=np.uint64) for t in ("rp", "dp")]
+    assert len(ids[0]) == 2 * grid ** 3 and np.array_equal(ids[0], ids[1])
+    pos = [np.fromfile(os.path.join(tmp, f"{t}.DM.pos.f64")) for t in ("rp", "dp")]
+    vel = [np.fromfile(os.path.join(tmp, f"{t}.DM.vel.f64")) for t in ("rp", "dp")]
+    assert np.abs(pos[0] - pos[1]).max() < 4e-16
+    assert np.abs(vel[0] - vel[1]).max() < TOL * np.abs(vel[0]).max()
+    # MUSIC1 noise (populated Nyquist planes) at 2LPT
+    _run(ref_exe, tmp, "rm", 2, generator="MUSIC1", grid=grid, threads=threads)
+    _run(our_exe, tmp, "dm", 2, generator="MUSIC1", grid=grid, threads=threads)
+    a, b = _fields(tmp, "rm", n=grid), _fields(tmp, "dm", n=grid)
+    for c in FIELDS:
+        err = np.abs(a[c] - b[c]).max() / np.abs(a[c]).max()
+        worst = max(worst, err)
+        assert err < TOL, ("MUSIC1", c, err)
+    print(f"reference itself vs drop-in at {grid}^3: worst field error {worst:.2e} of the field maximum")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_the_reference_itself_and_the_dropin_agree_on_identical_configs(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check_against_the_reference_itself(os.path.join(CPP, "_dropin", "monofonIC_ref_cpu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"),
+                                        tmp_path, 32, 1)
+
+
+@pytest.mark.gpu
+def test_the_reference_itself_on_the_host_and_the_dropin_on_the_gpu_agree_at_128(tmp_path):
+    ref, ours = os.path.join(CPP, "_dropin", "monofonIC_ref_cpu"), os.path.join(CPP, "_dropin", "monofonIC_mfb")
+    if not (os.path.exists(ref) and os.path.exists(ours)):
+        pytest.skip("tests/cpp/_dropin executables were not built (need /root/reference at build time)")
+    _check_against_the_reference_itself(ref, ours, tmp_path, 128, min(16, os.cpu_count() or 1))

@@ -71,8 +71,8 @@ inline void check(int rc) {
 // 64-byte handles of their peer-mapped exchange blocks once (MPI_Allgather) and the slab transposes then run inside the FFT
 // passes over NVLink; with the thread-emulation build of the kernels (CPU tests) or $MFB_STAGED_EXCHANGE the exchange is handed
 // to MPI_Alltoall instead (mfb_dist_init_staged).  `n` is the first grid of the run (GridRes^3 in ic_generator::run): the
-// exchange buffers are sized for it and for its 3/2-padded products.  A host that wants the resident-spectra source stage
-// calls mfb_dist_init_slots itself before its first grid (monofonic_b200/dist.py: pick_nslots).
+// exchange buffers are sized for it and for its 3/2-padded products; their number follows the free device memory
+// ($MFB_EXCHANGE_SLOTS overrides).
 #ifdef USE_MPI
 inline void mpi_exchange(const void* send, void* recv, size_t chunk_bytes, void*) {
     MPI_Alltoall(send, int(chunk_bytes / sizeof(double)), MPI_DOUBLE, recv, int(chunk_bytes / sizeof(double)), MPI_DOUBLE, MPI_COMM_WORLD);
@@ -92,12 +92,29 @@ inline void ensure_init(const int n[3]) {
 #ifdef USE_MPI
     if (size > 1 && mfb_dist_nranks() <= 1) {
         const size_t xbuf = mfb_dist_xbuf_bytes(n, 1, size);
-        if (std::strstr(mfb_build_info(), "emulation") || std::getenv("MFB_STAGED_EXCHANGE")) {
-            check(mfb_dist_init_staged(rank, size, xbuf, mpi_exchange, nullptr));
+        const bool staged = std::strstr(mfb_build_info(), "emulation") || std::getenv("MFB_STAGED_EXCHANGE");
+        // exchange buffers in the peer-mapped block: the transforms need 2; the shared-transform source stage uses all of them as
+        // slots and wants 10 at 3LPT (8, 7, 6, 5: narrower loops).  The largest count that leaves room for the 8 grids and the
+        // particle arrays of an LPT run and a margin is taken - the rule of monofonic_b200/dist.py:pick_nslots - the same on every rank.
+        size_t freeb = 0;
+        check(mfb_device_mem_info(&freeb, nullptr));
+        if (staged) freeb /= 2;   // staged mode keeps a staging copy of every buffer
+        const size_t cells = size_t(n[0]) * n[1] * n[2] / size_t(size);
+        const size_t fixed = 8 * 8 * cells * size_t(n[2] + 2) / size_t(n[2]) + 32 * cells + (size_t(3) << 30);
+        int nslots = 2;
+        const char* want = std::getenv("MFB_EXCHANGE_SLOTS");
+        if (want) nslots = std::atoi(want);
+        else
+            for (int k : {10, 8, 7, 6, 5})
+                if (size_t(k) * xbuf + fixed <= freeb) { nslots = k; break; }
+        int agreed = nslots;
+        MPI_Allreduce(&nslots, &agreed, 1, MPI_INT, MPI_MIN, MPI_COMM_WORLD);
+        if (staged) {
+            check(mfb_dist_init_staged_slots(rank, size, xbuf, agreed, mpi_exchange, nullptr));
         } else {
             char mine[64];
             std::vector<char> all(size_t(64) * size);
-            check(mfb_dist_init(rank, size, xbuf, mine));
+            check(mfb_dist_init_slots(rank, size, xbuf, agreed, mine));
             MPI_Allgather(mine, 64, MPI_CHAR, all.data(), 64, MPI_CHAR, MPI_COMM_WORLD);
             check(mfb_dist_connect(all.data()));
         }

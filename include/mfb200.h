@@ -42,6 +42,7 @@ typedef struct mfb_gradient mfb_gradient;
 int mfb_device_count(void);          /* CUDA devices visible to this process (0: none) */
 int mfb_init(int device);            /* selects the CUDA device, creates the stream; fails without a GPU */
 int mfb_finalize(void);
+int mfb_device_mem_info(size_t* free_bytes, size_t* total_bytes);   /* of the selected device; sizes the exchange block (mfb_dist_init_slots) */
 const char* mfb_last_error(void);
 const char* mfb_build_info(void);    /* "cuda sm_100a" for the product build */
 int mfb_synchronize(void);

@@ -25,6 +25,7 @@ def _declare(lib):
     sig = {
         "mfb_init": (i, [i]),
         "mfb_device_count": (i, []),
+        "mfb_device_mem_info": (i, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "mfb_finalize": (i, []),
         "mfb_last_error": (C.c_char_p, []),
         "mfb_build_info": (C.c_char_p, []),

@@ -1294,6 +1294,16 @@ int mfb_device_count(void) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
     return ndev;
 }
+/* free / total bytes of the selected device (after mfb_init): what a host sizes its exchange block with */
+int mfb_device_mem_info(size_t* free_bytes, size_t* total_bytes) {
+    MFB_TRY
+    require(g_ctx.initialised, "mfb_init has not been called");
+    size_t f = 0, t = 0;
+    cuda_check(cudaMemGetInfo(&f, &t), "cudaMemGetInfo");
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    MFB_CATCH
+}
 int mfb_init(int device) {
     MFB_TRY
     if (g_ctx.initialised) return 0;

@@ -235,6 +235,11 @@ def _check_mpi(exe_mpi, exe_single, tmp, worlds):
             got = np.concatenate([np.fromfile(os.path.join(tmp, f"{name}.r{r}.DM_{c}.f64")).reshape(-1, N, N) for r in range(world)])
             assert got.shape == (N, N, N)
             assert np.abs(got - single[c]).max() <= 1e-13 * np.abs(single[c]).max(), (world, c)
+        if world == 2:   # the ping-pong pair only: the source stage takes its per-product path on the slabs
+            _run_mpi(exe_mpi, tmp, "m3w2s2", world, 3, extra_env={"MFB_EXCHANGE_SLOTS": "2"})
+            for c in FIELDS:
+                got = np.concatenate([np.fromfile(os.path.join(tmp, f"m3w2s2.r{r}.DM_{c}.f64")).reshape(-1, N, N) for r in range(world)])
+                assert np.abs(got - single[c]).max() <= 1e-13 * np.abs(single[c]).max(), (world, c, "2 slots")
         name = f"mpw{world}"
         _run_mpi(exe_mpi, tmp, name, world, 3, lattice="bcc", particles=True)
         ids = np.concatenate([np.fromfile(os.path.join(tmp, f"{name}.r{r}.DM.ids.u64"), dtype=np.uint64) for r in range(world)])

@@ -18,6 +18,7 @@
 //    transposed [ky_loc][kx][kz] exactly like FFTW_MPI_TRANSPOSED_OUT.  Grid_FFT<real_t, false> is the whole grid.
 #pragma once
 #include <array>
+#include <atomic>
 #include <cassert>
 #include <cmath>
 #include <complex>
@@ -56,6 +57,7 @@ template <typename T> struct vec3_t {
 #endif
 #include <fstream>
 #include <iomanip>
+#include <mutex>
 #include <vector>
 
 enum space_t { kspace_id, rspace_id };  // include/grid_fft.hh:29  (kspace_id == MFB_KSPACE == 0)
@@ -492,14 +494,24 @@ public:
 
 private:
     mfb_grid* h_;
-    mutable bool host_dirty_, dev_newer_;
+    // lazy coherence between the host mirror and the device buffer.  Host accessors may be called from inside an OpenMP team (the
+    // reference's own loops are `#pragma omp parallel for` around kelem / relem): the one download a stale mirror needs is taken by
+    // whichever thread comes first, the others wait for it; device operations are issued from serial code.
+    mutable std::atomic<bool> host_dirty_, dev_newer_;
+    mutable std::mutex sync_mu_;
     void set_sizes() {  // src/grid_fft.cc:98-111, 176-189, 230-233, 262-265
         if (space_ == rspace_id) { sizes_ = {size_t(local_0_size_), n_[1], n_[2], npr_}; }
         else { sizes_ = {size_t(local_1_size_), n_[0], npc_, npc_}; }
     }
     void to_host(bool will_write) const {
-        if (dev_newer_) { mfb_detail::check(mfb_grid_download(h_, data_)); dev_newer_ = false; }
-        if (will_write) host_dirty_ = true;
+        if (dev_newer_.load(std::memory_order_acquire)) {
+            std::lock_guard<std::mutex> lk(sync_mu_);
+            if (dev_newer_.load(std::memory_order_relaxed)) {
+                mfb_detail::check(mfb_grid_download(h_, data_));
+                dev_newer_.store(false, std::memory_order_release);
+            }
+        }
+        if (will_write && !host_dirty_.load(std::memory_order_relaxed)) host_dirty_.store(true, std::memory_order_relaxed);
     }
     void to_device() {
         if (host_dirty_) { mfb_detail::check(mfb_grid_upload(h_, data_)); host_dirty_ = false; }

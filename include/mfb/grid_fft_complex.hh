@@ -178,10 +178,17 @@ public:
 private:
     mfb_cgrid* h_ = nullptr;
     std::vector<ccomplex_t> host_;
-    mutable bool host_dirty_ = false, dev_newer_ = false;
+    mutable std::atomic<bool> host_dirty_{false}, dev_newer_{false};   // thread-safe like the real grid's (host lambdas inside OpenMP teams)
+    mutable std::mutex sync_mu_;
     void to_host(bool will_write) const {
-        if (dev_newer_) { mfb_detail::check(mfb_cgrid_download(h_, reinterpret_cast<double*>(const_cast<ccomplex_t*>(host_.data())))); dev_newer_ = false; }
-        if (will_write) host_dirty_ = true;
+        if (dev_newer_.load(std::memory_order_acquire)) {
+            std::lock_guard<std::mutex> lk(sync_mu_);
+            if (dev_newer_.load(std::memory_order_relaxed)) {
+                mfb_detail::check(mfb_cgrid_download(h_, reinterpret_cast<double*>(const_cast<ccomplex_t*>(host_.data()))));
+                dev_newer_.store(false, std::memory_order_release);
+            }
+        }
+        if (will_write && !host_dirty_.load(std::memory_order_relaxed)) host_dirty_.store(true, std::memory_order_relaxed);
     }
     void to_device() const {
         if (host_dirty_) {

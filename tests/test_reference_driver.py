@@ -322,3 +322,27 @@ def test_the_reference_itself_on_the_host_and_the_dropin_on_the_gpu_agree_at_128
     if not (os.path.exists(ref) and os.path.exists(ours)):
         pytest.skip("tests/cpp/_dropin executables were not built (need /root/reference at build time)")
     _check_against_the_reference_itself(ref, ours, tmp_path, 128, min(16, os.cpu_count() or 1))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_dropin_with_the_reference_openmp_loops_on(tmp_path):
+    """-fopenmp build of the same unmodified sources, [execution] NumThreads = 4: the driver's `#pragma omp parallel for` loops
+    call kelem / relem of the drop-in grids from inside OpenMP teams (thread-safe lazy host synchronisation); results equal the
+    serial build bit for bit."""
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    tmp = str(tmp_path)
+    ser, omp = os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_omp_emu")
+    _run(ser, tmp, "s3", 3)
+    out = _run(omp, tmp, "o3", 3, threads=4)
+    assert "(4 used)" in out
+    a, b = _fields(tmp, "s3"), _fields(tmp, "o3")
+    for c in FIELDS:
+        assert np.array_equal(a[c], b[c]), c
+    _run(ser, tmp, "sp", 3, lattice="bcc", particles=True)
+    _run(omp, tmp, "op", 3, lattice="bcc", particles=True, threads=4)
+    for k, dt in (("pos.f64", np.float64), ("vel.f64", np.float64), ("ids.u64", np.uint64)):
+        assert np.array_equal(np.fromfile(os.path.join(tmp, "sp.DM." + k), dtype=dt), np.fromfile(os.path.join(tmp, "op.DM." + k), dtype=dt)), k

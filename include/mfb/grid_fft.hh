@@ -72,7 +72,8 @@ inline void check(int rc) {
 // USE_MPI build with more than one rank: one rank per GPU, every grid a slab (src/grid_fft.cc:115-192).  The ranks exchange the
 // 64-byte handles of their peer-mapped exchange blocks once (MPI_Allgather) and the slab transposes then run inside the FFT
 // passes over NVLink; with the thread-emulation build of the kernels (CPU tests) or $MFB_STAGED_EXCHANGE the exchange is handed
-// to MPI_Alltoall instead (mfb_dist_init_staged).  `n` is the first grid of the run (GridRes^3 in ic_generator::run): the
+// to MPI_Alltoall instead (mfb_dist_init_staged; on GPUs the callback sees device pointers, i.e. that mode wants a CUDA-aware
+// MPI).  `n` is the first grid of the run (GridRes^3 in ic_generator::run): the
 // exchange buffers are sized for it and for its 3/2-padded products; their number follows the free device memory
 // ($MFB_EXCHANGE_SLOTS overrides).
 #ifdef USE_MPI

@@ -4,6 +4,7 @@
 // The AoS arrays are filled on the device and copied once into the std::vectors the output plugins read
 // (get_particles()), instead of a serial host triple loop per component.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <utility>
@@ -137,6 +138,34 @@ public:
             downloaded_ = true;
         }
         return particles_;
+    }
+    // The container chunk by chunk, for particle loads that do not fit the host (3LPT 2048^3: 275 GB): `consume(chunk, first)` is
+    // called with a container holding particles [first, first + chunk.get_local_num_particles()) - the same members an output
+    // plugin reads - while the device -> host copy of the next chunk is in flight; two chunk containers exist at any time.
+    // Extension beyond the reference's interface (its write_particle_data takes the whole container).
+    template <class consumer_t> void for_each_particle_chunk(size_t chunk_particles, consumer_t consume) {
+        container buf[2];
+        const size_t np = global_num_particles_;
+        auto issue = [&](int slot, size_t first) {
+            const size_t cnt = std::min(chunk_particles, np - first);
+            container& c = buf[slot];
+            c.allocate(cnt, b64reals_, b64ids_, bmass_);
+            void* pos = b64reals_ ? (void*)c.positions64_.data() : (void*)c.positions32_.data();
+            void* vel = b64reals_ ? (void*)c.velocities64_.data() : (void*)c.velocities32_.data();
+            void* ids = b64ids_ ? (void*)c.ids64_.data() : (void*)c.ids32_.data();
+            mfb_detail::check(mfb_particles_stream_out_range(p_, MFB_ATTR_POS, first, cnt, pos));
+            mfb_detail::check(mfb_particles_stream_out_range(p_, MFB_ATTR_VEL, first, cnt, vel));
+            mfb_detail::check(mfb_particles_stream_out_range(p_, MFB_ATTR_IDS, first, cnt, ids));
+            if (bmass_) mfb_detail::check(mfb_particles_stream_out_range(p_, MFB_ATTR_MASS, first, cnt, b64reals_ ? (void*)c.mass64_.data() : (void*)c.mass32_.data()));
+        };
+        if (np == 0 || chunk_particles == 0) return;
+        issue(0, 0);
+        int slot = 0;
+        for (size_t first = 0; first < np; first += chunk_particles, slot ^= 1) {
+            mfb_detail::check(mfb_particles_stream_wait(p_));                  // chunk `first` has landed
+            if (first + chunk_particles < np) issue(slot ^ 1, first + chunk_particles);
+            consume(static_cast<const container&>(buf[slot]), first);
+        }
     }
 };
 }  // namespace particle

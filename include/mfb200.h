@@ -269,6 +269,9 @@ int mfb_particles_download(const mfb_particles* p, void* pos, void* vel, void* i
 #define MFB_ATTR_IDS 2
 #define MFB_ATTR_MASS 3
 int mfb_particles_stream_out(mfb_particles* p, int attr, void* host);
+/* particles [first, first + count) of one attribute: for hosts that hand chunks to their consumer through a ring of page-locked
+   buffers instead of holding the whole container (3LPT 2048^3: 275 GB of particles) */
+int mfb_particles_stream_out_range(mfb_particles* p, int attr, size_t first, size_t count, void* host);
 int mfb_particles_stream_wait(mfb_particles* p);
 
 #ifdef __cplusplus

@@ -132,6 +132,7 @@ def _declare(lib):
         "mfb_particles_set_masses": (i, [vp, i, d, vp]),
         "mfb_particles_download": (i, [vp, vp, vp, vp, vp]),
         "mfb_particles_stream_out": (i, [vp, i, vp]),
+        "mfb_particles_stream_out_range": (i, [vp, i, sz, sz, vp]),
         "mfb_particles_stream_wait": (i, [vp]),
     }
     for name, (res, args) in sig.items():

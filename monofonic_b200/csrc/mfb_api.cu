@@ -2425,6 +2425,26 @@ int mfb_particles_stream_out(mfb_particles* p, int attr, void* host) {
     p->copy_pending[attr] = true;
     MFB_CATCH
 }
+/* the same for particles [first, first + count) of one attribute: a host that cannot hold the whole container (3LPT 2048^3:
+   275 GB of particles on a 196 GB host) hands chunks to its consumer through a small ring of page-locked buffers */
+int mfb_particles_stream_out_range(mfb_particles* p, int attr, size_t first, size_t count, void* host) {
+    MFB_TRY
+    require(attr >= 0 && attr < 4 && host != nullptr, "bad particle attribute / host pointer");
+    require(first <= p->np && count <= p->np - first, "particle range outside the container");
+    const size_t rs = p->real64 ? 8 : 4, is = p->ids64 ? 8 : 4;
+    const char* src = static_cast<const char*>(attr == MFB_ATTR_POS ? p->pos : attr == MFB_ATTR_VEL ? p->vel : attr == MFB_ATTR_IDS ? p->ids : p->mass);
+    require(src != nullptr, "particle buffer not allocated");
+    const size_t elem = attr == MFB_ATTR_IDS ? is : (attr == MFB_ATTR_MASS ? rs : 3 * rs);
+    if (count == 0) return 0;
+    if (!g_ctx.copy_stream) cuda_check(cudaStreamCreate(&g_ctx.copy_stream), "cudaStreamCreate(copy)");
+    if (!p->copied[attr]) cuda_check(cudaEventCreateWithFlags(&p->copied[attr], cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventRecord(p->copied[attr], g_ctx.stream), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(g_ctx.copy_stream, p->copied[attr], 0), "cudaStreamWaitEvent");
+    cuda_check(cudaMemcpyAsync(host, src + first * elem, count * elem, cudaMemcpyDeviceToHost, g_ctx.copy_stream), "D2H stream_out_range");
+    cuda_check(cudaEventRecord(p->copied[attr], g_ctx.copy_stream), "cudaEventRecord");
+    p->copy_pending[attr] = true;
+    MFB_CATCH
+}
 int mfb_particles_stream_wait(mfb_particles* p) {
     MFB_TRY
     (void)p;

@@ -205,6 +205,21 @@ int main() {
     CHECK(pc.ids64_.size() == 2 * nc);
     CHECK(pc.ids64_[0] == 2 * nc && pc.ids64_[5] == 2 * nc + 10 && pc.ids64_[nc + 5] == 2 * nc + 11);
     CHECK(pc.positions64_[3 * 5 + 2] == 5.0 / 32 * 2.0 && pc.positions64_[3 * (nc + 5) + 2] == 5.5 / 32 * 2.0);
+    {   // the same container chunk by chunk (ragged last chunk): what a host does whose particle load exceeds its memory
+        size_t seen = 0, calls = 0;
+        bool same = true;
+        lg.for_each_particle_chunk(24571, [&](const particle::container& c, size_t first) {
+            const size_t cnt = c.get_local_num_particles();
+            same = same && first == seen;
+            for (size_t i = 0; i < cnt; ++i) {
+                same = same && c.ids64_[i] == pc.ids64_[first + i];
+                for (int d = 0; d < 3; ++d)
+                    same = same && c.positions64_[3 * i + d] == pc.positions64_[3 * (first + i) + d] && c.velocities64_[3 * i + d] == pc.velocities64_[3 * (first + i) + d];
+            }
+            seen += cnt; ++calls;
+        });
+        CHECK(same && seen == 2 * nc && calls == (2 * nc + 24570) / 24571);
+    }
     {
         // masked sc lattice (include/particle_generator.hh:171-260): a config that says DoBaryons -> CDM on 7 of 8 cells,
         // baryons on the cell centres; ids = IDoffset*N^3 + cell index of the selected cells in (i,j,k) order

@@ -100,6 +100,8 @@ int gsl_integration_qag(const gsl_function* f, double a, double b, double epsabs
     Seg s0 = gk15(f, a, b);
     double val = s0.val, err = s0.err;
     q.push(s0);
+    epsrel = std::min(epsrel, 1e-13);   // converge well past the request: the reference's numbers were made by GSL's 61-point QAG, whose
+                                        // true error is far below its own estimate - only a converged value can agree with it to 1e-12
     for (size_t it = 1; it < std::max<size_t>(limit, 1) && err > std::max(epsabs, epsrel * std::fabs(val)); ++it) {
         const Seg s = q.top(); q.pop();
         const double m = 0.5 * (s.a + s.b);
@@ -115,13 +117,61 @@ int gsl_integration_qags(const gsl_function* f, double a, double b, double epsab
     return gsl_integration_qag(f, a, b, epsabs, epsrel, limit, 1, w, result, abserr);
 }
 
-// ------------------------------------------------------------------ uniform generator (xoshiro256**; NOT ranlxd1)
+// ------------------------------------------------------------------ uniform generators
+// "ranlxd1": Luescher's RANLUX in double precision, luxury level 1 (p = 202) - the published algorithm (M. Luescher, Comput. Phys.
+// Commun. 79 (1994) 100; F. James, ibid. 97 (1996) 357) in the state layout GSL documents for gsl_rng_ranlxd1: twelve 48-bit
+// numbers, subtract-with-borrow x_n = x_{n-7} - x_{n-12} - c, seed bits from a 31-bit shift register.  Whether it reproduces GSL bit
+// for bit is CHECKED, not assumed: tests/test_reference_driver.py compares the phases of the NGenIC white noise it produces
+// through the reference's plugin with the reference's own golden file.  Any other type: xoshiro256**.
 struct gsl_rng_type_s { int id; };
-struct gsl_rng_s { mutable uint64_t s[4]; };
+struct gsl_rng_s {
+    int type;
+    mutable uint64_t s[4];
+    mutable double x[12], carry;
+    mutable unsigned ir, jr, ir_old, pr;
+};
 static const gsl_rng_type k_ranlxd1{0}, k_mt{1};
 const gsl_rng_type* gsl_rng_ranlxd1 = &k_ranlxd1;
 const gsl_rng_type* gsl_rng_mt19937 = &k_mt;
+namespace {
+const double kOneBit = 1.0 / 281474976710656.0;   // 2^-48
+inline unsigned nxt(unsigned i) { return i == 11 ? 0 : i + 1; }
+void lux_step(const gsl_rng* r) {   // one subtract-with-borrow update at (ir, jr)
+    double y = r->x[r->jr] - r->x[r->ir] - r->carry;
+    if (y < 0) { r->carry = kOneBit; y += 1.0; } else r->carry = 0.0;
+    r->x[r->ir] = y;
+    r->ir = nxt(r->ir); r->jr = nxt(r->jr);
+}
+void lux_increment(const gsl_rng* r) {   // p updates between blocks of twelve delivered numbers
+    for (unsigned k = 0; k < r->pr; ++k) lux_step(r);
+    r->ir_old = r->ir;
+}
+void lux_seed(const gsl_rng* r, unsigned long s) {
+    if (s == 0) s = 1;
+    long i = long(s & 0x7FFFFFFFUL);
+    int xbit[31];
+    for (int k = 0; k < 31; ++k) { xbit[k] = int(i % 2); i /= 2; }
+    int ibit = 0, jbit = 18;
+    for (int k = 0; k < 12; ++k) {
+        double x = 0;
+        for (int l = 1; l <= 48; ++l) {
+            const double y = double((xbit[ibit] + 1) % 2);
+            x += x + y;
+            xbit[ibit] = (xbit[ibit] + xbit[jbit]) % 2;
+            ibit = (ibit + 1) % 31; jbit = (jbit + 1) % 31;
+        }
+        r->x[k] = kOneBit * x;
+    }
+    r->carry = 0; r->ir = 11; r->jr = 7; r->ir_old = 0; r->pr = 202;
+}
+double lux_get(const gsl_rng* r) {
+    r->ir = nxt(r->ir);
+    if (r->ir == r->ir_old) lux_increment(r);
+    return r->x[r->ir];
+}
+}  // namespace
 void gsl_rng_set(const gsl_rng* r, unsigned long int seed) {
+    if (r->type == 0) { lux_seed(r, seed); return; }
     uint64_t z = seed + 0x9e3779b97f4a7c15ull;
     for (int i = 0; i < 4; ++i) {   // splitmix64 seeding
         z += 0x9e3779b97f4a7c15ull;
@@ -130,16 +180,20 @@ void gsl_rng_set(const gsl_rng* r, unsigned long int seed) {
         r->s[i] = x ^ (x >> 31);
     }
 }
-gsl_rng* gsl_rng_alloc(const gsl_rng_type*) { auto* r = new gsl_rng_s(); gsl_rng_set(r, 0); return r; }
+gsl_rng* gsl_rng_alloc(const gsl_rng_type* T) { auto* r = new gsl_rng_s(); r->type = T->id; gsl_rng_set(r, 0); return r; }
 void gsl_rng_free(gsl_rng* r) { delete r; }
 unsigned long int gsl_rng_get(const gsl_rng* r) {
+    if (r->type == 0) return (unsigned long)(lux_get(r) * 4294967296.0);   // ranlxd delivers doubles; integers are their top 32 bits
     auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
     uint64_t* s = r->s;
     const uint64_t res = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
     s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
     return res;
 }
-double gsl_rng_uniform(const gsl_rng* r) { return double(gsl_rng_get(r) >> 11) * (1.0 / 9007199254740992.0); }
+double gsl_rng_uniform(const gsl_rng* r) {
+    if (r->type == 0) return lux_get(r);
+    return double(gsl_rng_get(r) >> 11) * (1.0 / 9007199254740992.0);
+}
 double gsl_rng_uniform_pos(const gsl_rng* r) { double x; do x = gsl_rng_uniform(r); while (x == 0.0); return x; }
 
 // Gaussian deviates (MUSIC1 white-noise generator): Leva's ratio-of-uniforms method

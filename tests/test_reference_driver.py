@@ -9,8 +9,8 @@ libmfb200 (CPU: the thread-emulation build of the same kernels; GPU: the prebuil
 Check, as for the reference's goldens (tests/golden_util.py): phi(1) is recovered from the density field of the
 1LPT run, the CPU oracle is run on it, and every displacement / velocity / density field and the particle container of the
 1LPT / 2LPT / 3LPT runs must agree with the oracle to 1e-12 of the field maximum (north_star: 1e-9); ids exact.
-The generator behind the NGenIC plugin here is not GSL's ranlxd1 (tests/cpp/gslmini.cc), so the noise differs from the
-committed goldens; the growth factors do not: vfac of the run equals the goldens' to 1e-9.
+The generator behind the NGenIC plugin is Luescher's RANLUX (tests/cpp/gslmini.cc): the noise is the reference's own, and the
+five golden files themselves are reproduced (last section of this file).
 
 The reference's USE_MPI build of the same sources runs too: one process per rank (tests/cpp/minimpi stands in for the MPI
 library), every rank a slab of the library - Grid_FFT<real_t, true> in the transposed layout, MPI_Allreduce in the driver and the

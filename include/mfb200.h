@@ -110,6 +110,10 @@ int mfb_grid_upload(mfb_grid* g, const double* host);
    NGenIC phases stay with the host plugin (GSL is not available offline); this entry point is for runs that only need
    reproducible Gaussian noise, and removes the host fill + H2D copy from them.  Slabs: every rank fills its own k-slab. */
 int mfb_noise_fill_ngenic(mfb_grid* g, unsigned long long seed);
+/* ... and with the reference's own generator - RANLUX, GSL's gsl_rng_ranlxd1 (:44-45) - one stream per (k_x, k_y) column seeded
+   from the plugin's seed table: the NGenIC white noise of the reference itself for this [random] seed (checked against its golden
+   files), without the host fill and the H2D copy */
+int mfb_noise_fill_ngenic_ranlxd(mfb_grid* g, unsigned long long seed);
 int mfb_grid_stream_in(mfb_grid* g, const double* host);
 int mfb_grid_stream_in_wait(mfb_grid* g);
 int mfb_grid_download(const mfb_grid* g, double* host);

@@ -60,6 +60,7 @@ def _declare(lib):
         "mfb_grid_device_ptr": (vp, [vp]),
         "mfb_grid_upload": (i, [vp, vp]),
         "mfb_noise_fill_ngenic": (i, [vp, C.c_ulonglong]),
+        "mfb_noise_fill_ngenic_ranlxd": (i, [vp, C.c_ulonglong]),
         "mfb_grid_stream_in": (i, [vp, vp]),
         "mfb_grid_stream_in_wait": (i, [vp]),
         "mfb_grid_download": (i, [vp, vp]),

@@ -3,6 +3,7 @@
 // Each kernel names the reference loop it replaces (paths relative to /root/reference).
 #pragma once
 #include "fft_core.cuh"
+#include "ranlux.cuh"
 
 namespace mfb {
 
@@ -514,6 +515,46 @@ __global__ void __launch_bounds__(EW_THREADS) ngenic_fill_kernel(double2* __rest
             }
         }
         w[idx] = z;
+    }
+}
+
+// The same fill with the reference's OWN generator: one RANLUX stream per (k_x, k_y) column, seeded from the plugin's seed table,
+// two draws per k_z (phase, amplitude) in the plugin's order (src/plugins/random_ngenic.cc:96-121) - the reference's NGenIC white
+// noise itself, to the last bit of log / cos / sin.  One thread per stored column walks k_z; its k_z = 0 element is the first draw
+// of its own stream where the column is the primary one of the Hermitian pair (:125-148), else the conjugate of the partner
+// column's first draw (that stream is seeded here a second time instead of writing across columns: no race, slab-local).
+MFB_D double2 ngenic_ranlux_mode(Ranlxd1& r) {   // consumes the two draws of one mode (:110-115)
+    const double phase = r.uniform() * 2 * M_PI;
+    double ampl;
+    do { ampl = r.uniform(); } while (ampl == 0.0 || ampl == 1.0);
+    ampl = sqrt(-log(ampl));
+    return make_double2(ampl * cos(phase), ampl * sin(phase));
+}
+__global__ void __launch_bounds__(128) ngenic_ranlux_fill_kernel(double2* __restrict__ w, KGeom g, const unsigned* __restrict__ seed_table) {
+    const long col = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (col >= long(g.s0) * g.s1) return;
+    const int a = int(col / g.s1), b = int(col - long(a) * g.s1);
+    const int i = g.tr ? b : a, j = g.tr ? a + g.off : b;       // k_x, k_y of this stored column
+    const int n = g.n0, h = n / 2;
+    double2* row = w + col * g.nzc;
+    const bool dead = (i == h || j == h);                        // :117 - Nyquist columns stay zero
+    Ranlxd1 r;
+    r.seed(seed_table[size_t(i) * n + j]);
+    for (int k = 0; k < g.nzc; ++k) {
+        const double2 z = ngenic_ranlux_mode(r);
+        const bool zero = dead || k == h || (i | j | k) == 0;
+        if (k > 0) row[k] = zero ? make_double2(0.0, 0.0) : z;
+        else {
+            const bool primary = (i == 0 && j < h) || (i > 0 && i < h);
+            double2 z0 = z;
+            if (!primary && !zero) {
+                Ranlxd1 p;
+                p.seed(seed_table[size_t((n - i) % n) * n + (n - j) % n]);
+                z0 = ngenic_ranlux_mode(p);
+                z0.y = -z0.y;
+            }
+            row[0] = zero ? make_double2(0.0, 0.0) : z0;
+        }
     }
 }
 

@@ -1887,6 +1887,38 @@ int mfb_noise_fill_ngenic(mfb_grid* g, unsigned long long seed) {
     check_launch("ngenic_fill");
     MFB_CATCH
 }
+/* the same layout from the reference's own generator (RANLUX, gsl_rng_ranlxd1): the seed table of RNG_ngenic's constructor
+   (src/plugins/random_ngenic.cc:42-75) is drawn on the host - N^2 numbers of one stream, in the plugin's ring order - and the
+   column streams run on the device */
+int mfb_noise_fill_ngenic_ranlxd(mfb_grid* g, unsigned long long seed) {
+    MFB_TRY
+    require(g->n[0] == g->n[1] && g->n[1] == g->n[2], "the NGenIC layout needs a cubic grid");
+    const size_t n = size_t(g->n[0]);
+    std::vector<unsigned> table(n * n, 0u);
+    Ranlxd1 r;
+    r.seed((unsigned long)seed);
+    auto draw = [&]() -> unsigned { return unsigned(0x7fffffff * r.uniform()); };
+    for (size_t i = 0; i < n / 2; ++i) {
+        for (size_t j = 0; j < i; ++j) table[i * n + j] = draw();
+        for (size_t j = 0; j < i + 1; ++j) table[j * n + i] = draw();
+        for (size_t j = 0; j < i; ++j) table[(n - 1 - i) * n + j] = draw();
+        for (size_t j = 0; j < i + 1; ++j) table[(n - 1 - j) * n + i] = draw();
+        for (size_t j = 0; j < i; ++j) table[i * n + (n - 1 - j)] = draw();
+        for (size_t j = 0; j < i + 1; ++j) table[j * n + (n - 1 - i)] = draw();
+        for (size_t j = 0; j < i; ++j) table[(n - 1 - i) * n + (n - 1 - j)] = draw();
+        for (size_t j = 0; j < i + 1; ++j) table[(n - 1 - j) * n + (n - 1 - i)] = draw();
+    }
+    unsigned* dtab = (unsigned*)dev_alloc(table.size() * sizeof(unsigned));
+    cuda_check(cudaMemcpyAsync(dtab, table.data(), table.size() * sizeof(unsigned), cudaMemcpyHostToDevice, g_ctx.stream), "seed table upload");
+    g->space = MFB_KSPACE;
+    KGeom k = kgeom(g);
+    const long cols = long(k.s0) * k.s1;
+    MFB_LAUNCH_ROLE(ROLE_ELEMENTWISE, ngenic_ranlux_fill_kernel, unsigned((cols + 127) / 128), 128, reinterpret_cast<double2*>(g->d), k, dtab);
+    check_launch("ngenic_ranlux_fill");
+    cuda_check(cudaStreamSynchronize(g_ctx.stream), "sync");
+    cudaFree(dtab);
+    MFB_CATCH
+}
 int mfb_density_from_phi(mfb_grid* out, const mfb_grid* phi) {
     MFB_TRY
     require(phi->space == MFB_KSPACE, "density_from_phi: phi must be in k-space");

@@ -156,6 +156,11 @@ class Grid_FFT:
         """white noise in k-space with the layout of RNG_ngenic::Fill_Grid, generated on the device (Philox4x32-10)"""
         L.check(self._lib.mfb_noise_fill_ngenic(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), self._lib)
 
+    def fill_noise_ngenic(self, seed: int):
+        """the white noise RNG_ngenic::Fill_Grid gives for this [random] seed - the reference's own generator (RANLUX,
+        gsl_rng_ranlxd1), one stream per column - generated on the device"""
+        L.check(self._lib.mfb_noise_fill_ngenic_ranlxd(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), self._lib)
+
     def stream_in(self, buf: np.ndarray):
         """asynchronous upload_raw on the ingest stream (`buf` should be pinned and must stay alive and unchanged until the
         copy has run); the compute stream continues with work that does not touch this grid.  Pair with stream_in_wait()."""

@@ -854,6 +854,106 @@ def ngenic_layout_noise(n, seed):
     return W
 
 
+class Ranlxd1:
+    """Luescher's RANLUX in double precision at luxury level 1 (p = 202) - what GSL calls gsl_rng_ranlxd1, the generator of the
+    reference's NGenIC plugin (src/plugins/random_ngenic.cc:44-45).  Published algorithm (M. Luescher, Comput. Phys. Commun. 79
+    (1994) 100; F. James, ibid. 97 (1996) 357): twelve 48-bit numbers in a ring, x_n = x_{n-5} - x_{n-12} - c (mod 1), 202 updates
+    per twelve delivered numbers, seed bits from a 31-bit shift register.  PINNED against the reference: the NGenIC noise it gives
+    for the seed of the reference's regression configurations has the phases of the reference's golden density field
+    (tests/test_oracle_golden.py::test_ngenic_noise_is_the_reference_s)."""
+    ONE_BIT = 2.0 ** -48
+
+    def __init__(self, seed):
+        s = int(seed) or 1
+        v = s & 0x7FFFFFFF
+        bit = [(v >> k) & 1 for k in range(31)]
+        ib, jb = 0, 18
+        self.x = []
+        for _ in range(12):
+            acc = 0.0
+            for _ in range(48):
+                acc += acc + float((bit[ib] + 1) % 2)
+                bit[ib] = (bit[ib] + bit[jb]) % 2
+                ib, jb = (ib + 1) % 31, (jb + 1) % 31
+            self.x.append(acc * self.ONE_BIT)
+        self.carry, self.ir, self.jr, self.ir_old = 0.0, 11, 7, 0
+
+    def uniform(self):
+        x = self.x
+        self.ir = (self.ir + 1) % 12
+        if self.ir == self.ir_old:
+            ir, jr, c = self.ir, self.jr, self.carry
+            for _ in range(202):
+                y = x[jr] - x[ir] - c
+                if y < 0.0:
+                    c = self.ONE_BIT
+                    y += 1.0
+                else:
+                    c = 0.0
+                x[ir] = y
+                ir, jr = (ir + 1) % 12, (jr + 1) % 12
+            self.ir, self.jr, self.carry, self.ir_old = ir, jr, c, ir
+        return x[self.ir]
+
+
+def ngenic_seed_table(n, seed):
+    """RNG_ngenic's constructor (src/plugins/random_ngenic.cc:42-75): N^2 column seeds from ONE stream, drawn ring by ring"""
+    r = Ranlxd1(seed)
+    T = np.zeros((n, n), dtype=np.uint32)
+    draw = lambda: np.uint32(int(0x7fffffff * r.uniform()))
+    for i in range(n // 2):
+        for j in range(i):
+            T[i, j] = draw()
+        for j in range(i + 1):
+            T[j, i] = draw()
+        for j in range(i):
+            T[n - 1 - i, j] = draw()
+        for j in range(i + 1):
+            T[n - 1 - j, i] = draw()
+        for j in range(i):
+            T[i, n - 1 - j] = draw()
+        for j in range(i + 1):
+            T[j, n - 1 - i] = draw()
+        for j in range(i):
+            T[n - 1 - i, n - 1 - j] = draw()
+        for j in range(i + 1):
+            T[n - 1 - j, n - 1 - i] = draw()
+    return T
+
+
+def ngenic_noise(n, seed):
+    """RNG_ngenic::Fill_Grid (src/plugins/random_ngenic.cc:84-154, the non-distributed branch; the distributed one fills the same
+    logical modes): the reference's white noise for [random] seed, k-space [kx][ky][kz], before any conditioning."""
+    T = ngenic_seed_table(n, seed)
+    h, nzc = n // 2, n // 2 + 1
+    W = np.zeros((n, n, nzc), dtype=np.complex128)
+    for i in range(n):
+        ii = (n - i) % n
+        for j in range(n):
+            jj = (n - j) % n
+            r = Ranlxd1(int(T[i, j]))
+            for k in range(nzc):
+                phase = r.uniform() * 2 * np.pi
+                while True:
+                    ampl = r.uniform()
+                    if ampl != 0.0 and ampl != 1.0:
+                        break
+                if i == h or j == h or k == h or (i == 0 and j == 0 and k == 0):
+                    continue
+                ampl = np.sqrt(-np.log(ampl))
+                z = complex(ampl * np.cos(phase), ampl * np.sin(phase))
+                if k > 0:
+                    W[i, j, k] = z
+                elif i == 0:
+                    if j < h:
+                        W[i, j, 0] = z
+                        W[i, jj, 0] = np.conj(z)
+                elif i < h:
+                    W[i, j, 0] = z
+                    W[ii, jj, 0] = np.conj(z)
+    return W
+
+
 def make_white_noise_k(n, seed, nyquist_zero=True):
     """Unit-variance complex Gaussian white noise on the half spectrum [kx][ky][kz] that is the
     transform of a real field.  With nyquist_zero (NGenIC behaviour, random_ngenic.cc:117) all

@@ -127,6 +127,8 @@ def main():
     # ---- device noise fill in the NGenIC layout: every rank fills its own k-slab
     P.fill_noise_ngenic_layout(4242)
     assert PC.relerr(MD.gather_kspace(P), O.ngenic_layout_noise(n, 4242)) < 1e-13
+    P.fill_noise_ngenic(12345)          # the reference's own generator: one RANLUX stream per column of the local k-slab
+    assert np.abs(MD.gather_kspace(P) - O.ngenic_noise(n, 12345)).max() < 1e-14
 
     # ---- masked sc lattice on slabs (include/particle_generator.hh:171-260): closed-form particle ranks per slab
     mask = O.particle_type_mask(True, 3)

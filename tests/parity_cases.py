@@ -519,6 +519,16 @@ def check_noise_ingest(M, n=32):
     assert abs(np.mean(np.abs(inner) ** 2) - 1.0) < 5.0 / np.sqrt(inner.size)            # unit variance per complex mode
     pl.wnoise.fill_noise_ngenic_layout(seed + 1)
     assert np.abs(pl.wnoise.get_kspace() - Wref).max() > 1.0                             # another seed, another field
+    # ... and the reference's own NGenIC noise (RANLUX column streams, src/plugins/random_ngenic.cc:42-121), generated on the
+    # device: equal to the plugin's restatement to the last bits of log / cos / sin; Hermitian plane bit for bit
+    Wx = O.ngenic_noise(n, 12345)
+    pl.wnoise.fill_noise_ngenic(12345)
+    assert pl.wnoise.space_ == M.kspace_id
+    gx = pl.wnoise.get_kspace()
+    assert np.abs(gx - Wx).max() < 1e-14, np.abs(gx - Wx).max()
+    assert not gx[h].any() and not gx[:, h].any() and not gx[:, :, h].any() and gx[0, 0, 0] == 0
+    assert np.abs(gx[1:, 1:, 0] - np.conj(gx[1:, 1:, 0][::-1, ::-1])).max() == 0.0
+    assert np.abs(gx[0, 1:, 0] - np.conj(gx[0, 1:, 0][::-1])).max() == 0.0
     pl.wnoise.fill_noise_ngenic_layout(seed)
     out, ref = run(pl), ref_fields(Wref)
     for k in ("dx", "dy", "dz", "vx", "vy", "vz"):
@@ -933,6 +943,37 @@ def close(a, b):
 def check_golden_generic(M, name, order):
     gold = G.load(name)
     pl = _golden_pipeline(M, order, "sc", "generic")
+    for d, c in enumerate("xyz"):
+        assert close(pl.displacement_field(d).get_real(), gold["DM_d" + c]), c
+    for d, c in enumerate("xyz"):
+        assert close(pl.velocity_field(d).get_real(), gold["DM_v" + c]), c
+    assert close(pl.density_field().get_real(), gold["DM_delta"])
+
+
+def check_golden_from_seed(M, name, order):
+    """The golden files from the SEED: the white noise is generated on the device by the reference's own generator
+    (mfb_noise_fill_ngenic_ranlxd, [random] seed = 12345 of the reference's regression configurations); the only thing taken
+    from a golden file is the radial amplitude A(|k|) - delta_k / W_k per |k| shell of the 1LPT run, a function of |n|^2 -,
+    tabulated like a transfer-function plugin would be.  Everything else (noise, phi(1), sources, fields) is the device path."""
+    g = O.GridSpec(G.N, G.L)
+    _, _, vfac = G.bootstrap()
+    W = O.ngenic_noise(G.N, 12345)
+    dk = g.fwd(G.load("test_1lpt_sc_generic")["DM_delta"])
+    m = np.abs(W) > 0
+    shell = np.round(g.k2() / (2.0 * np.pi / G.L) ** 2).astype(np.int64)
+    h = G.N // 2
+    table = np.zeros(3 * h * h + 1)
+    cnt = np.zeros_like(table)
+    np.add.at(table, shell[m], (dk[m] / W[m]).real)
+    np.add.at(cnt, shell[m], 1.0)
+    table = -np.divide(table, cnt, out=np.zeros_like(table), where=cnt > 0)      # phi(1) = -W A / k^2  (D+ := -1, as in bootstrap)
+    cfg = M.lpt_config(GridRes=G.N, BoxLength=G.L, LPTorder=order, ParticleLoad="sc", Dplus0=-1.0, vfac=vfac, lunit=1.0, vunit=1.0,
+                       real64=True, ids64=False)
+    pl = M.LPTPipeline(cfg)
+    pl.wnoise.fill_noise_ngenic(12345)
+    pl.compute_phi1(table)
+    pl.compute_sources()
+    gold = G.load(name)
     for d, c in enumerate("xyz"):
         assert close(pl.displacement_field(d).get_real(), gold["DM_d" + c]), c
     for d, c in enumerate("xyz"):

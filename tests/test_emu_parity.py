@@ -66,6 +66,11 @@ def test_golden_2lpt_generic(M):
     PC.check_golden_generic(M, "test_2lpt_baryons_generic", 2)
 
 
+@pytest.mark.parametrize("name,order", [("test_1lpt_sc_generic", 1), ("test_2lpt_baryons_generic", 2)])
+def test_golden_from_seed(M, name, order):
+    PC.check_golden_from_seed(M, name, order)
+
+
 def test_golden_gadget(M):
     PC.check_golden_gadget(M)
 

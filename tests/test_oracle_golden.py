@@ -112,3 +112,23 @@ def test_convolve2_is_dealiased_product():
     nh = n // 2
     ref[nh], ref[:, nh], ref[:, :, nh] = 0, 0, 0
     assert np.abs(got - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+def test_ngenic_noise_is_the_reference_s():
+    """pins oracle.Ranlxd1 / ngenic_noise (and with them the device fill mfb_noise_fill_ngenic_ranlxd and the GSL stand-in of
+    tests/cpp) against the reference's REAL output: the golden density field of the 1LPT regression run (made with GSL's
+    gsl_rng_ranlxd1, seed 12345) is delta_k = T(|k|) W_k with a real positive T - so delta_k / W_k must be real, positive and
+    the same for all modes of one |k| shell, mode by mode."""
+    g = O.GridSpec(G.N, G.L)
+    W = O.ngenic_noise(G.N, 12345)
+    dk = g.fwd(G.load("test_1lpt_sc_generic")["DM_delta"])
+    m = np.abs(W) > 0
+    assert m.sum() == (G.N - 1) ** 2 * (G.N // 2 - 1) + ((G.N - 1) ** 2 - 1)   # every mode without an index N/2, minus DC
+    ratio = dk[m] / W[m]
+    assert np.abs(ratio.imag).max() < 1e-13 * np.abs(ratio.real).max()
+    assert ratio.real.min() > 0
+    k2 = np.round(g.k2()[m] / g.k2()[1, 0, 0]).astype(np.int64)
+    for shell in np.unique(k2)[:200]:
+        r = ratio.real[k2 == shell]
+        assert r.max() - r.min() < 1e-12 * r.mean(), shell
+    assert not dk[~m].any() or np.abs(dk[~m]).max() < 1e-12 * np.abs(dk).max()

@@ -65,6 +65,7 @@ raw_eulerian    = {eulerian}
 
 
 RANDOM = {"NGENIC": "generator       = NGENIC\nseed            = 12345",
+          "NGENIC_GPU": "generator       = NGENIC_GPU\nseed            = 12345",   # include/mfb/plugins/random_ngenic_device.cc
           "MUSIC1": "generator       = MUSIC1\nseed[{level}]         = 12345"}   # MUSIC1: one seed per level, levelmin = log2(GridRes)
 
 
@@ -196,11 +197,11 @@ def test_reference_executable_on_the_gpu(tmp_path):
     _check(exe, tmp_path)
 
 
-def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_env=None):
+def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_env=None, generator="NGENIC"):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no", baryons="no",
-                            random=RANDOM["NGENIC"], eulerian="no", grid=32, threads=1))
+                            random=RANDOM[generator], eulerian="no", grid=32, threads=1))
     shm = os.path.join(tmp, name + ".shm")
     with open(shm, "wb") as f:
         f.truncate(64 + world * (64 << 20))     # sparse: header + one 64 MiB slot per rank
@@ -467,3 +468,40 @@ def test_reference_goldens_reproduced_by_its_own_executable_on_the_gpu(tmp_path)
     if not os.path.exists(exe):
         pytest.skip("tests/cpp/_dropin/monofonIC_mfb was not built (needs /root/reference at build time)")
     _check_goldens(exe, tmp_path)
+
+
+def _check_device_noise_plugin(exe, exe_mpi, tmp, tol):
+    """[random] generator = NGENIC_GPU - a plugin on the reference's RNG plugin API that fills the grid on the device with the
+    NGENIC plugin's own generator - gives the runs of generator = NGENIC (same seed): `tol` = 0 where host and device share
+    their libm (CPU emulation), a few ulp of log / cos / sin otherwise."""
+    tmp = str(tmp)
+    listing = subprocess.run([exe], capture_output=True, text=True).stdout
+    assert "'NGENIC_GPU'" in listing
+    _run(exe, tmp, "h2", 2)
+    _run(exe, tmp, "g2", 2, generator="NGENIC_GPU")
+    a, b = _fields(tmp, "h2"), _fields(tmp, "g2")
+    for c in FIELDS:
+        assert np.abs(a[c] - b[c]).max() <= tol * np.abs(a[c]).max(), c
+    if exe_mpi is not None:     # every rank fills its own k-slab
+        _run_mpi(exe_mpi, tmp, "g2w2", 2, 2, generator="NGENIC_GPU")
+        for c in FIELDS:
+            got = np.concatenate([np.fromfile(os.path.join(tmp, f"g2w2.r{r}.DM_{c}.f64")).reshape(-1, N, N) for r in range(2)])
+            assert np.abs(got - a[c]).max() <= max(tol, 1e-13) * np.abs(a[c]).max(), c
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_device_noise_plugin_equals_the_ngenic_plugin(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check_device_noise_plugin(os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_mpi_emu"), tmp_path, 0.0)
+
+
+@pytest.mark.gpu
+def test_device_noise_plugin_equals_the_ngenic_plugin_on_the_gpu(tmp_path):
+    exe = os.path.join(CPP, "_dropin", "monofonIC_mfb")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/_dropin/monofonIC_mfb was not built (needs /root/reference at build time)")
+    _check_device_noise_plugin(exe, None, tmp_path, 1e-13)

@@ -53,7 +53,7 @@ public:
 // compiles and runs as written: dense [n0][n1][n2] complex elements in both spaces (src/grid_fft.cc:56-70), the c2c transforms
 // on the device (mfb_cgrid_fft_*), and a lazily synchronised host mirror that the reference's host lambdas
 // (apply_function_k_dep, assign_function_of_grids_r, ... include/grid_fft.hh:698-796) run on - the same coherence rule as the
-// real grid.  The named device operations of namespace ppt below are the fast spelling of the same branch.  Single slab.
+// real grid.  The named device operations of namespace ppt below are the fast spelling of the same branch.  Whole grid or slab.
 template <bool bdistributed>
 class Grid_FFT<ccomplex_t, bdistributed> {
 public:
@@ -89,21 +89,22 @@ public:
         mfb_detail::ensure_init(n);
         mfb_detail::check(mfb_cgrid_create(&h_, n, L));
         int loc[4];
-        if (mfb_cgrid_local(h_, loc) != 0 || bdistributed) {
+        const bool slab = mfb_cgrid_local(h_, loc) != 0;   // {local_0_start_, local_0_size_, local_1_start_, local_1_size_}
+        if (slab != bdistributed) {
             mfb_cgrid_destroy(h_); h_ = nullptr;
-            throw std::runtime_error("Grid_FFT<ccomplex_t>: the host mirror of complex grids is single-slab (use the ppt:: device operations on slabs)");
+            throw std::runtime_error(bdistributed ? "Grid_FFT<ccomplex_t, true>: the library is not slab-decomposed (mfb_dist_init)"
+                                                  : "Grid_FFT<ccomplex_t, false>: the library is slab-decomposed - use Grid_FFT<ccomplex_t, true>");
         }
-        ntot_ = n_[0] * n_[1] * n_[2];
+        local_0_start_ = loc[0]; local_0_size_ = loc[1]; local_1_start_ = loc[2]; local_1_size_ = loc[3];
+        ntot_ = mfb_cgrid_nelem(h_);   // n0 n1 n2, or the larger of the slab's two layouts ([x_loc][n1][n2] / [ky_loc][n0][n2])
         host_.assign(ntot_, ccomplex_t(0.0, 0.0));
         data_ = cdata_ = host_.data();
-        fft_norm_fac_ = 1.0 / std::sqrt(real_t(ntot_));
+        fft_norm_fac_ = 1.0 / std::sqrt(real_t(n_[0]) * real_t(n_[1]) * real_t(n_[2]));
         npr_ = npc_ = n_[2];
         for (int i = 0; i < 3; ++i) {
             nhalf_[i] = n_[i] / 2; kfac_[i] = 2.0 * M_PI / length_[i]; kny_[i] = kfac_[i] * n_[i] / 2; dx_[i] = length_[i] / n_[i];
-            sizes_[i] = n_[i];
         }
-        sizes_[3] = n_[2];
-        local_0_start_ = local_1_start_ = 0; local_0_size_ = ptrdiff_t(n_[0]); local_1_size_ = ptrdiff_t(n_[1]);
+        set_sizes();
         ballocated_ = true;
         host_dirty_ = true; dev_newer_ = false;
         if (space_ == kspace_id) mfb_detail::check(mfb_cgrid_fft_forward(h_, 0));
@@ -114,16 +115,21 @@ public:
     size_t memsize() const noexcept { return ntot_; }
     size_t size(size_t i) const noexcept { return sizes_[i]; }
     size_t rsize(size_t i) const noexcept { return n_[i]; }
-    size_t local_size() const noexcept { return ntot_; }
+    size_t local_size() const noexcept { return size_t(local_0_size_) * n_[1] * n_[2]; }
     const std::array<size_t, 3>& get_global_size() const noexcept { return n_; }
     const std::array<real_t, 3>& get_dx() const noexcept { return dx_; }
-    size_t get_idx(size_t i, size_t j, size_t k) const noexcept { return (i * n_[1] + j) * n_[2] + k; }
+    size_t get_idx(size_t i, size_t j, size_t k) const noexcept { return (i * sizes_[1] + j) * sizes_[2] + k; }
     template <typename ft> vec3_t<ft> get_k(size_t i, size_t j, size_t k) const noexcept {   // include/grid_fft.hh:281-296
+        if (bdistributed) {   // transposed slab: the first index runs over the local ky rows
+            const size_t ip = i + size_t(local_1_start_);
+            return vec3_t<ft>(ft((real_t(j) - real_t(j > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(ip) - real_t(ip > nhalf_[1]) * n_[1]) * kfac_[1]),
+                              ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2]));
+        }
         return vec3_t<ft>(ft((real_t(i) - real_t(i > nhalf_[0]) * n_[0]) * kfac_[0]), ft((real_t(j) - real_t(j > nhalf_[1]) * n_[1]) * kfac_[1]),
                           ft((real_t(k) - real_t(k > nhalf_[2]) * n_[2]) * kfac_[2]));
     }
     template <typename ft> vec3_t<ft> get_r(size_t i, size_t j, size_t k) const noexcept {
-        return vec3_t<ft>(ft(real_t(i) * dx_[0]), ft(real_t(j) * dx_[1]), ft(real_t(k) * dx_[2]));
+        return vec3_t<ft>(ft(real_t(i + local_0_start_) * dx_[0]), ft(real_t(j) * dx_[1]), ft(real_t(k) * dx_[2]));
     }
     // ---- host element access
     ccomplex_t& operator[](size_t i) { to_host(true); return data_[i]; }
@@ -139,38 +145,38 @@ public:
         if (space_ == kspace_id) return;
         if (do_transform) { to_device(); dev_newer_ = true; }
         mfb_detail::check(mfb_cgrid_fft_forward(h_, do_transform ? 1 : 0));
-        space_ = kspace_id;
+        space_ = kspace_id; set_sizes();
     }
     void FourierTransformBackward(bool do_transform = true) {
         if (space_ == rspace_id) return;
         if (do_transform) { to_device(); dev_newer_ = true; }
         mfb_detail::check(mfb_cgrid_fft_backward(h_, do_transform ? 1 : 0));
-        space_ = rspace_id;
+        space_ = rspace_id; set_sizes();
     }
     void zero() noexcept { to_host(true); std::fill(host_.begin(), host_.end(), ccomplex_t(0.0, 0.0)); }
     void copy_from(const Grid_FFT& g) {
         const_cast<Grid_FFT&>(g).to_device();
         mfb_detail::check(mfb_cgrid_copy(h_, g.h_));
-        space_ = g.space_; host_dirty_ = false; dev_newer_ = true;
+        space_ = g.space_; set_sizes(); host_dirty_ = false; dev_newer_ = true;
     }
     // ---- the functor family on the host mirror (include/grid_fft.hh:698-796)
-    template <typename F> void apply_function_k(const F& f) { to_host(true); for (auto& e : host_) e = f(e); }
-    template <typename F> void apply_function_r(const F& f) { to_host(true); for (auto& e : host_) e = f(e); }
+    template <typename F> void apply_function_k(const F& f) { to_host(true); for (size_t q = 0, m = sizes_[0] * sizes_[1] * sizes_[2]; q < m; ++q) data_[q] = f(data_[q]); }
+    template <typename F> void apply_function_r(const F& f) { apply_function_k(f); }
     template <typename F> void apply_function_k_dep(const F& f) {
         to_host(true);
-        for (size_t i = 0; i < n_[0]; ++i) for (size_t j = 0; j < n_[1]; ++j) for (size_t k = 0; k < n_[2]; ++k) {
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
             auto& e = data_[get_idx(i, j, k)]; e = f(e, this->template get_k<real_t>(i, j, k));
         }
     }
     template <typename F> void apply_function_r_dep(const F& f) {
         to_host(true);
-        for (size_t i = 0; i < n_[0]; ++i) for (size_t j = 0; j < n_[1]; ++j) for (size_t k = 0; k < n_[2]; ++k) {
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k) {
             auto& e = data_[get_idx(i, j, k)]; e = f(e, this->template get_r<real_t>(i, j, k));
         }
     }
     template <typename F, typename... Grids> void assign_function_of_grids_r(const F& f, Grids&... grids) {
         to_host(true); (grids.to_host(false), ...);
-        for (size_t i = 0; i < n_[0]; ++i) for (size_t j = 0; j < n_[1]; ++j) for (size_t k = 0; k < n_[2]; ++k)
+        for (size_t i = 0; i < sizes_[0]; ++i) for (size_t j = 0; j < sizes_[1]; ++j) for (size_t k = 0; k < sizes_[2]; ++k)
             data_[get_idx(i, j, k)] = f((grids.data_[grids.get_idx(i, j, k)])...);
     }
     template <typename F, typename... Grids> void assign_function_of_grids_k(const F& f, Grids&... grids) { assign_function_of_grids_r(f, grids...); }
@@ -178,6 +184,10 @@ public:
 private:
     mfb_cgrid* h_ = nullptr;
     std::vector<ccomplex_t> host_;
+    void set_sizes() {   // dense elements: [x_loc][n1][n2] in real space, [ky_loc][n0][n2] (transposed) in k-space on slabs
+        if (space_ == rspace_id) sizes_ = {size_t(local_0_size_), n_[1], n_[2], n_[2]};
+        else sizes_ = {size_t(local_1_size_), n_[0], n_[2], n_[2]};
+    }
     mutable std::atomic<bool> host_dirty_{false}, dev_newer_{false};   // thread-safe like the real grid's (host lambdas inside OpenMP teams)
     mutable std::mutex sync_mu_;
     void to_host(bool will_write) const {

@@ -197,11 +197,11 @@ def test_reference_executable_on_the_gpu(tmp_path):
     _check(exe, tmp_path)
 
 
-def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_env=None, generator="NGENIC"):
+def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_env=None, generator="NGENIC", eulerian=False):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no", baryons="no",
-                            random=RANDOM[generator], eulerian="no", grid=32, threads=1))
+                            random=RANDOM[generator], eulerian="yes" if eulerian else "no", grid=32, threads=1))
     shm = os.path.join(tmp, name + ".shm")
     with open(shm, "wb") as f:
         f.truncate(64 + world * (64 << 20))     # sparse: header + one 64 MiB slot per rank
@@ -224,6 +224,7 @@ def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_
 
 def _check_mpi(exe_mpi, exe_single, tmp, worlds):
     tmp = str(tmp)
+    _run(exe_single, tmp, "s1", 1)
     _run(exe_single, tmp, "s3", 3)
     _run(exe_single, tmp, "sp", 3, lattice="bcc", particles=True)
     single = _fields(tmp, "s3")
@@ -241,6 +242,22 @@ def _check_mpi(exe_mpi, exe_single, tmp, worlds):
             for c in FIELDS:
                 got = np.concatenate([np.fromfile(os.path.join(tmp, f"m3w2s2.r{r}.DM_{c}.f64")).reshape(-1, N, N) for r in range(world)])
                 assert np.abs(got - single[c]).max() <= 1e-13 * np.abs(single[c]).max(), (world, c, "2 slots")
+        if world == 2:
+            # the semiclassical (PPT) branch on slabs: Grid_FFT<ccomplex_t, true> with the reference's host lambdas; hbar follows the
+            # reference's MPI loop (every rank leaves out the x neighbour of its last local plane, then MPI_Allreduce MAX), so it is
+            # compared with the oracle's nranks = 2 statement of that loop, not with the single-process run
+            _run_mpi(exe_mpi, tmp, "e2w2", world, 2, eulerian=True)
+            g = O.GridSpec(N, L)
+            d1 = _fields(tmp, "s1")
+            with np.errstate(divide="ignore", invalid="ignore"):
+                phi_s = g.fwd(d1["delta"]) / g.k2()
+            phi_s[0, 0, 0] = 0.0
+            mk = np.abs(d1["dx"]) > 1e-4 * np.abs(d1["dx"]).max()
+            vfac = float(np.median(d1["vx"][mk] / d1["dx"][mk]))
+            ref, _ = O.ppt_eulerian(g, np.zeros_like(phi_s), O.lpt_potentials(g, phi_s, 2, -1.0), 2, 0.0251908, vfac, lambda k: 0.0 * k, 1.0, 1.0, 2)
+            for c, rname in (("delta", "density"), ("vx", "vx"), ("vy", "vy"), ("vz", "vz")):
+                got = np.concatenate([np.fromfile(os.path.join(tmp, f"e2w2.r{r}.DM_{c}.f64")).reshape(-1, N, N) for r in range(world)])
+                assert np.abs(got - ref[rname]).max() < 1e-9 * np.abs(ref[rname]).max(), ("PPT on slabs", c)
         name = f"mpw{world}"
         _run_mpi(exe_mpi, tmp, name, world, 3, lattice="bcc", particles=True)
         ids = np.concatenate([np.fromfile(os.path.join(tmp, f"{name}.r{r}.DM.ids.u64"), dtype=np.uint64) for r in range(world)])

@@ -7,6 +7,7 @@
 // so that tests/test_reference_driver.py can read the output of the reference's own executable without HDF5.
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,7 @@
 class raw_output_plugin : public output_plugin {
     bool particles_, eulerian_, real64_, ids64_;
     double lunit_, vunit_;
+    std::unique_ptr<output_plugin> units_of_;   // raw_units_of = <plugin>: units, widths and species mode are asked of that plugin
     static std::string species(const cosmo_species& s) { return s == cosmo_species::dm ? "DM" : (s == cosmo_species::baryon ? "BA" : "NU"); }
     static void dump(const std::string& name, const void* p, size_t bytes) {
         FILE* f = std::fopen(name.c_str(), "wb");
@@ -31,7 +33,20 @@ public:
         real64_ = cf_.get_value_safe<bool>("output", "raw_real64", true);
         ids64_ = cf_.get_value_safe<bool>("output", "raw_ids64", true);
         lunit_ = cf_.get_value_safe<double>("output", "raw_position_unit", 1.0);
-        vunit_ = cf_.get_value_safe<double>("output", "raw_velocity_unit", 1.0);   // Eulerian fields: the semiclassical (PPT) branch, like generic_out_eulerian
+        vunit_ = cf_.get_value_safe<double>("output", "raw_velocity_unit", 1.0);
+        // stand in for another output plugin of the reference: everything the driver asks an output plugin for (units, 32 / 64
+        // bit, particles or fields) is answered by an instance of THAT plugin, made by the reference's own factory; only the
+        // bytes go to raw files instead of HDF5
+        const std::string other = cf_.get_value_safe<std::string>("output", "raw_units_of", "");
+        if (!other.empty()) {
+            auto it = get_output_plugin_map().find(other);
+            if (it == get_output_plugin_map().end()) throw std::runtime_error("mfb_raw: unknown output plugin '" + other + "'");
+            units_of_ = it->second->create(cf, pcc);
+            real64_ = units_of_->has_64bit_reals(); ids64_ = units_of_->has_64bit_ids();
+            lunit_ = units_of_->position_unit(); vunit_ = units_of_->velocity_unit();
+            particles_ = units_of_->write_species_as(cosmo_species::dm) == output_type::particles;
+            eulerian_ = units_of_->write_species_as(cosmo_species::dm) == output_type::field_eulerian;
+        }   // Eulerian fields: the semiclassical (PPT) branch, like generic_out_eulerian
         if (CONFIG::MPI_task_size > 1) fname_ += ".r" + std::to_string(CONFIG::MPI_task_rank);   // one set of files per rank: its slab
     }
     output_type write_species_as(const cosmo_species&) const {

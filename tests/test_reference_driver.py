@@ -388,11 +388,12 @@ def _golden_conf(name, tmp):
     import golden_util as G
 
     spec = GOLDEN_RUNS[name]
-    lunit, vunit, real64 = G.units(spec["fmt"])
-    ids64 = spec["fmt"] == "swift"          # UseLongids = true in test_3lpt_bcc_swift.conf; gadget: 32-bit ids
-    out = (f"[output]\nformat = mfb_raw\nfilename = {name}\nraw_particles = {'yes' if spec['particles'] else 'no'}\n"
-           f"raw_real64 = {'yes' if real64 else 'no'}\nraw_ids64 = {'yes' if ids64 else 'no'}\n"
-           f"raw_position_unit = {float(lunit)!r}\nraw_velocity_unit = {float(vunit)!r}\n")
+    # the raw plugin asks the plugin the configuration names - an instance made by the reference's own factory - for its units,
+    # widths and species mode (output_gadget_hdf5.cc:83-84, output_swift.cc:73-74, output_generic.cc:70-78); UseLongids as in the
+    # reference's test_3lpt_bcc_swift.conf
+    plugin = {"generic": "generic", "gadget": "gadget_hdf5", "swift": "SWIFT"}[spec["fmt"]]
+    out = (f"[output]\nformat = mfb_raw\nfilename = {name}\nraw_units_of = {plugin}\n"
+           + ("UseLongids = true\n" if spec["fmt"] == "swift" else ""))
     src = os.path.join("/root/reference/tests/configs", name + ".conf")
     if os.path.exists(src):
         text = open(src).read()

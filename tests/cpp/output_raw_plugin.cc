@@ -15,7 +15,7 @@
 
 class raw_output_plugin : public output_plugin {
     bool particles_, eulerian_, real64_, ids64_;
-    double lunit_, vunit_;
+    double lunit_, vunit_, munit_ = 1.0;
     std::unique_ptr<output_plugin> units_of_;   // raw_units_of = <plugin>: units, widths and species mode are asked of that plugin
     static std::string species(const cosmo_species& s) { return s == cosmo_species::dm ? "DM" : (s == cosmo_species::baryon ? "BA" : "NU"); }
     static void dump(const std::string& name, const void* p, size_t bytes) {
@@ -43,7 +43,7 @@ public:
             if (it == get_output_plugin_map().end()) throw std::runtime_error("mfb_raw: unknown output plugin '" + other + "'");
             units_of_ = it->second->create(cf, pcc);
             real64_ = units_of_->has_64bit_reals(); ids64_ = units_of_->has_64bit_ids();
-            lunit_ = units_of_->position_unit(); vunit_ = units_of_->velocity_unit();
+            lunit_ = units_of_->position_unit(); vunit_ = units_of_->velocity_unit(); munit_ = units_of_->mass_unit();
             particles_ = units_of_->write_species_as(cosmo_species::dm) == output_type::particles;
             eulerian_ = units_of_->write_species_as(cosmo_species::dm) == output_type::field_eulerian;
         }   // Eulerian fields: the semiclassical (PPT) branch, like generic_out_eulerian
@@ -56,7 +56,7 @@ public:
     bool has_64bit_ids() const { return ids64_; }
     real_t position_unit() const { return lunit_; }
     real_t velocity_unit() const { return vunit_; }
-    real_t mass_unit() const { return 1.0; }
+    real_t mass_unit() const { return munit_; }
 
     void write_grid_data(const Grid_FFT<real_t>& g, const cosmo_species& s, const fluid_component& c) {
         static const char* comp[] = {"delta", "vx", "vy", "vz", "dx", "dy", "dz"};

@@ -464,6 +464,9 @@ def _check_goldens(exe, tmp):
             assert close(vel, gold[ptype + "__Velocities"]), (name, species, "vel")
             if rt == np.float64:
                 worst = max(worst, float(np.abs(vel - gold[ptype + "__Velocities"]).max() / np.abs(gold[ptype + "__Velocities"]).max()))
+            if ptype + "__Masses" in gold:
+                mass = np.fromfile(os.path.join(tmp, f"{name}.{species}.mass.{rs}"), dtype=rt)
+                assert close(mass, gold[ptype + "__Masses"]), (name, species, "mass")
             if ptype + "__ParticleIDs" in gold:
                 ids = np.fromfile(os.path.join(tmp, f"{name}.{species}.ids.{it}"), dtype=idt)
                 assert np.array_equal(ids, gold[ptype + "__ParticleIDs"]), (name, species, "ids")

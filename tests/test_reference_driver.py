@@ -15,7 +15,9 @@ five golden files themselves are reproduced (last section of this file).
 The reference's USE_MPI build of the same sources runs too: one process per rank (tests/cpp/minimpi stands in for the MPI
 library), every rank a slab of the library - Grid_FFT<real_t, true> in the transposed layout, MPI_Allreduce in the driver and the
 particle container, the ghost-plane ring shift of grid_interpolate.hh - with the slab transposes inside the library (CPU: staged
-through MPI_Alltoall; GPUs: peer memory after one MPI_Allgather of the IPC handles).  2 and 4 ranks must reproduce the
+through MPI_Alltoall; GPUs: peer memory after one MPI_Allgather of the IPC handles).  This is the reference's own MPI
+consistency test (tests/scripts/test_mpi_consistency.sh:45-138: 1 vs 2 vs 4 tasks of the same configuration, rtol 1e-9) with
+a stricter bar: 2 and 4 ranks must reproduce the
 single-process run of the same configuration bit for bit (fields) and particle for particle (matched by id).
 
 And the reference ITSELF is run beside it: tests/cpp/_dropin/monofonIC_ref_cpu is the same set of sources plus the reference's own

@@ -59,7 +59,8 @@ public:
     real_t mass_unit() const { return munit_; }
 
     void write_grid_data(const Grid_FFT<real_t>& g, const cosmo_species& s, const fluid_component& c) {
-        static const char* comp[] = {"delta", "vx", "vy", "vz", "dx", "dy", "dz"};
+        static const char* comp[] = {"delta", "vx", "vy", "vz", "dx", "dy", "dz", "mass"};   // fluid_component (include/general.hh:60-69)
+        if (int(c) < 0 || int(c) > 7) throw std::runtime_error("mfb_raw: unknown fluid component");
         std::vector<double> v(g.size(0) * g.size(1) * g.size(2));   // the local planes (the whole grid on one rank)
         for (size_t i = 0; i < g.size(0); ++i)
             for (size_t j = 0; j < g.size(1); ++j)

@@ -45,7 +45,7 @@ BoxLength       = 100
 zstart          = 50.0
 LPTorder        = {order}
 DoBaryons       = {baryons}
-DoBaryonVrel    = no
+DoBaryonVrel    = {vrel}
 DoFixing        = no
 DoInversion     = no
 DoRemoveCornerModes = no
@@ -53,7 +53,7 @@ ParticleLoad    = {lattice}
 [cosmology]
 ParameterSet    = Planck2018EE+BAO+SN
 ZeroRadiation   = false
-transfer        = eisenstein
+transfer        = {transfer}
 [random]
 {random}
 [execution]
@@ -71,12 +71,14 @@ RANDOM = {"NGENIC": "generator       = NGENIC\nseed            = 12345",
           "MUSIC1": "generator       = MUSIC1\nseed[{level}]         = 12345"}   # MUSIC1: one seed per level, levelmin = log2(GridRes)
 
 
-def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC", eulerian=False, grid=32, threads=1):
+def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC", eulerian=False, grid=32, threads=1,
+         vrel=False, transfer="eisenstein"):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
                             baryons="yes" if baryons else "no", random=RANDOM[generator].format(level=grid.bit_length() - 1),
-                            eulerian="yes" if eulerian else "no", grid=grid, threads=threads))
+                            eulerian="yes" if eulerian else "no", grid=grid, threads=threads, vrel="yes" if vrel else "no",
+                            transfer=transfer))
     r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "Have a nice day" in r.stdout
@@ -203,7 +205,8 @@ def _run_mpi(exe, tmp, name, world, order, lattice="sc", particles=False, extra_
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
         f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no", baryons="no",
-                            random=RANDOM[generator], eulerian="yes" if eulerian else "no", grid=32, threads=1))
+                            random=RANDOM[generator], eulerian="yes" if eulerian else "no", grid=32, threads=1, vrel="no",
+                            transfer="eisenstein"))
     shm = os.path.join(tmp, name + ".shm")
     with open(shm, "wb") as f:
         f.truncate(64 + world * (64 << 20))     # sparse: header + one 64 MiB slot per rank
@@ -403,9 +406,8 @@ def _golden_conf(name, tmp):
     else:
         order = int(name.split("_")[1][0])
         text = CONF.format(order=order, lattice="bcc" if "bcc" in name else "sc", name=name, particles="no", eulerian="no",
-                           baryons="yes" if "baryons" in name else "no", random=RANDOM["NGENIC"], grid=32, threads=1)
-        if "vrel" in name:
-            text = text.replace("DoBaryonVrel    = no", "DoBaryonVrel    = yes")
+                           baryons="yes" if "baryons" in name else "no", random=RANDOM["NGENIC"], grid=32, threads=1,
+                           vrel="yes" if "vrel" in name else "no", transfer="eisenstein")
         text = text[:text.index("[output]")] + out
     path = os.path.join(tmp, name + ".conf")
     with open(path, "w") as f:
@@ -528,3 +530,70 @@ def test_device_noise_plugin_equals_the_ngenic_plugin_on_the_gpu(tmp_path):
     if not os.path.exists(exe):
         pytest.skip("tests/cpp/_dropin/monofonIC_mfb was not built (needs /root/reference at build time)")
     _check_device_noise_plugin(exe, None, tmp_path, 1e-13)
+
+
+def _camb_table(path):
+    """a synthetic 13-column table in the format of transfer_CAMB_file.cc:66-80 (no CAMB / CLASS output is available offline):
+    smooth, positive, DISTINCT cold-dark-matter and baryon transfer functions and velocity transfer functions, so that the
+    two-fluid terms of the driver are all non-zero: rho_bc (masses), the theta_bc velocity term, distinct species displacements"""
+    k = np.logspace(-4, 3, 512)
+    q = k / 0.14
+    tc = np.log(1.0 + 2.34 * q) / (2.34 * q) * (1 + 3.89 * q + (16.1 * q) ** 2 + (5.46 * q) ** 3 + (6.71 * q) ** 4) ** -0.25
+    tb = tc * (1.0 - 0.02 * k ** 2 / (0.02 + k ** 2)) * (1.0 + 0.005 * np.sin(40.0 * k) * np.exp(-(k / 0.3) ** 2))   # small enough for 1 + C rho_bc > 0 in the PPT branch
+    fb = 0.0488911 / 0.3099
+    tm = (1 - fb) * tc + fb * tb
+    vc, vb = tc * (1.0 + 0.02 * k / (1 + k)), tb * (1.0 - 0.05 * k / (1 + k))
+    cols = [k, tc, tb, 0 * k, 0 * k, tm, tm, tm, tm, tm, vc, vb, vb - vc]
+    np.savetxt(path, np.stack(cols, 1), fmt="%.17e")
+
+
+def _check_two_fluid(ref_exe, our_exe, tmp):
+    """BASELINE config C4 at the reference's regression size: CDM + baryons with two-fluid transfer functions (CAMB_file plugin,
+    the reference's own) and DoBaryonVrel - the reference itself against the drop-in, identical configuration and table"""
+    tmp = str(tmp)
+    table = os.path.join(tmp, "camb_like.dat")
+    _camb_table(table)
+    tf = "CAMB_file\ntransfer_file   = " + table
+    for tag, kw in (("f2", dict(order=2)), ("p2", dict(order=2, particles=True)), ("f3", dict(order=3, lattice="bcc")),
+                    ("e2", dict(order=2, eulerian=True))):
+        _run(ref_exe, tmp, "r" + tag, baryons=True, vrel=True, transfer=tf, **kw)
+        _run(our_exe, tmp, "d" + tag, baryons=True, vrel=True, transfer=tf, **kw)
+        for species in ("DM", "BA"):
+            if kw.get("particles"):
+                for k, dt in (("pos.f64", np.float64), ("vel.f64", np.float64), ("mass.f64", np.float64), ("ids.u64", np.uint64)):
+                    a = np.fromfile(os.path.join(tmp, f"r{tag}.{species}.{k}"), dtype=dt)
+                    b = np.fromfile(os.path.join(tmp, f"d{tag}.{species}.{k}"), dtype=dt)
+                    if dt == np.uint64:
+                        assert np.array_equal(a, b), (tag, species, k)
+                    else:
+                        assert a.size and np.abs(a - b).max() <= (4e-16 if k.startswith("pos") else TOL * np.abs(a).max()), (tag, species, k)
+                mass = np.fromfile(os.path.join(tmp, f"r{tag}.{species}.mass.f64"))
+                assert mass.std() > 1e-7 * mass.mean()          # rho_bc really is non-zero with this table
+            else:
+                comps = ("delta", "vx", "vy", "vz") if kw.get("eulerian") else FIELDS
+                for c in comps:
+                    a = np.fromfile(os.path.join(tmp, f"r{tag}.{species}_{c}.f64"))
+                    b = np.fromfile(os.path.join(tmp, f"d{tag}.{species}_{c}.f64"))
+                    assert np.isfinite(a).all() and np.isfinite(b).all(), (tag, species, c)
+                    assert a.size == N ** 3 and np.abs(a - b).max() <= (1e-9 if kw.get("eulerian") else TOL) * np.abs(a).max(), (tag, species, c)
+        if not kw.get("particles") and not kw.get("eulerian"):   # the species really differ
+            a = np.fromfile(os.path.join(tmp, f"r{tag}.DM_vx.f64")); b = np.fromfile(os.path.join(tmp, f"r{tag}.BA_vx.f64"))
+            assert np.abs(a - b).max() > 1e-7 * np.abs(a).max()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_two_fluid_transfer_table_reference_itself_vs_dropin(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check_two_fluid(os.path.join(CPP, "_dropin", "monofonIC_ref_cpu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp_path)
+
+
+@pytest.mark.gpu
+def test_two_fluid_transfer_table_reference_on_the_host_vs_dropin_on_the_gpu(tmp_path):
+    ref, ours = os.path.join(CPP, "_dropin", "monofonIC_ref_cpu"), os.path.join(CPP, "_dropin", "monofonIC_mfb")
+    if not (os.path.exists(ref) and os.path.exists(ours)):
+        pytest.skip("tests/cpp/_dropin executables were not built (need /root/reference at build time)")
+    _check_two_fluid(ref, ours, tmp_path)

@@ -17,6 +17,8 @@ class BaseConvolver {
         o.g->FourierTransformForward(false);
         return o.g->device_handle();
     }
+    // operands first (transformed to k-space if they are not: include/convolution.hh:142-143), the output grid - which may BE one
+    // of the operands, src/ic_generator.cc:437 - only after that: declaring it k-space must not hide a pending operand transform
     static mfb_grid* in(grid_t& g) { g.FourierTransformForward(); return g.device_handle(); }
 
 protected:
@@ -33,33 +35,40 @@ public:
 
     template <typename opp>
     void convolve_Gradients(grid_t& inl, const std::array<int, 1>& d1l, grid_t& inr, const std::array<int, 1>& d1r, opp o) {
-        mfb_detail::check(mfb_conv_gradients(c_, in(inl), d1l[0], in(inr), d1r[0], out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_gradients(c_, a, d1l[0], b, d1r[0], r, o.code, o.alpha));
     }
     template <typename opp>
     void convolve_Gradient_and_Hessian(grid_t& inl, const std::array<int, 1>& d1l, grid_t& inr, const std::array<int, 2>& d2r, opp o) {
-        mfb_detail::check(mfb_conv_gradient_hessian(c_, in(inl), d1l[0], in(inr), d2r.data(), out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_gradient_hessian(c_, a, d1l[0], b, d2r.data(), r, o.code, o.alpha));
     }
     template <typename opp>
     void convolve_Hessians(grid_t& inl, const std::array<int, 2>& d2l, grid_t& inr, const std::array<int, 2>& d2r, opp o) {
-        mfb_detail::check(mfb_conv_hessians(c_, in(inl), d2l.data(), in(inr), d2r.data(), out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_hessians(c_, a, d2l.data(), b, d2r.data(), r, o.code, o.alpha));
     }
     template <typename opp>
     void convolve_Hessians(grid_t& inl, const std::array<int, 2>& d2l, grid_t& inm, const std::array<int, 2>& d2m, grid_t& inr,
                            const std::array<int, 2>& d2r, opp o) {
-        mfb_detail::check(mfb_conv_hessians3(c_, in(inl), d2l.data(), in(inm), d2m.data(), in(inr), d2r.data(), out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *m = in(inm), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_hessians3(c_, a, d2l.data(), m, d2m.data(), b, d2r.data(), r, o.code, o.alpha));
     }
     template <typename opp>
     void convolve_SumOfHessians(grid_t& inl, const std::array<int, 2>& d2l, grid_t& inr, const std::array<int, 2>& d2r1,
                                 const std::array<int, 2>& d2r2, opp o) {
-        mfb_detail::check(mfb_conv_sum_hessians(c_, in(inl), d2l.data(), in(inr), d2r1.data(), d2r2.data(), out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_sum_hessians(c_, a, d2l.data(), b, d2r1.data(), d2r2.data(), r, o.code, o.alpha));
     }
     template <typename opp>
     void convolve_DifferenceOfHessians(grid_t& inl, const std::array<int, 2>& d2l, grid_t& inr, const std::array<int, 2>& d2r1,
                                        const std::array<int, 2>& d2r2, opp o) {
-        mfb_detail::check(mfb_conv_diff_hessians(c_, in(inl), d2l.data(), in(inr), d2r1.data(), d2r2.data(), out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_diff_hessians(c_, a, d2l.data(), b, d2r1.data(), d2r2.data(), r, o.code, o.alpha));
     }
     template <typename opp> void multiply_field(grid_t& inl, grid_t& inr, opp o) {
-        mfb_detail::check(mfb_conv_multiply(c_, in(inl), in(inr), out(o), o.code, o.alpha));
+        mfb_grid *a = in(inl), *b = in(inr), *r = out(o);
+        mfb_detail::check(mfb_conv_multiply(c_, a, b, r, o.code, o.alpha));
     }
     // convolve2 / convolve3 with the reference's host lambdas kfunc(i,j,k) -> ccomplex_t (include/convolution.hh:512-549): the
     // lambdas are evaluated on the host over the local k-space index range - exactly the loop of the reference's MPI-build

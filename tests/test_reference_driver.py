@@ -72,13 +72,13 @@ RANDOM = {"NGENIC": "generator       = NGENIC\nseed            = 12345",
 
 
 def _run(exe, tmp, name, order, lattice="sc", particles=False, baryons=False, generator="NGENIC", eulerian=False, grid=32, threads=1,
-         vrel=False, transfer="eisenstein"):
+         vrel=False, transfer="eisenstein", edit=None):
     conf = os.path.join(tmp, name + ".conf")
     with open(conf, "w") as f:
-        f.write(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
+        f.write((edit or (lambda t: t))(CONF.format(order=order, lattice=lattice, name=name, particles="yes" if particles else "no",
                             baryons="yes" if baryons else "no", random=RANDOM[generator].format(level=grid.bit_length() - 1),
                             eulerian="yes" if eulerian else "no", grid=grid, threads=threads, vrel="yes" if vrel else "no",
-                            transfer=transfer))
+                            transfer=transfer)))
     r = subprocess.run([exe, conf], cwd=tmp, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "Have a nice day" in r.stdout
@@ -597,3 +597,55 @@ def test_two_fluid_transfer_table_reference_on_the_host_vs_dropin_on_the_gpu(tmp
     if not (os.path.exists(ref) and os.path.exists(ours)):
         pytest.skip("tests/cpp/_dropin executables were not built (need /root/reference at build time)")
     _check_two_fluid(ref, ours, tmp_path)
+
+
+# options of the driver that run through host lambdas on the grids (noise conditioning, the primordial non-Gaussianity branch with
+# its own dealiased products, external tides) or through other lattice branches: identical configurations through the reference
+# itself and through the drop-in
+OPTION_SWEEP = {
+    "fixing": (2, dict(), lambda t: t.replace("DoFixing        = no", "DoFixing        = yes")),
+    "inversion_corners": (2, dict(), lambda t: t.replace("DoInversion     = no", "DoInversion     = yes").replace("DoRemoveCornerModes = no", "DoRemoveCornerModes = yes")),
+    "fnl": (2, dict(), lambda t: t.replace("[cosmology]\n", "[cosmology]\nfnl = 50.0\n")),                       # src/ic_generator.cc:402-455
+    "fnl_running": (1, dict(), lambda t: t.replace("[cosmology]\n", "[cosmology]\nfnl = 50.0\nnf = 0.5\nk0 = 0.05\n")),
+    "gnl": (2, dict(), lambda t: t.replace("[cosmology]\n", "[cosmology]\ngnl = 1.0e4\n")),
+    "tides": (2, dict(), lambda t: t.replace("[cosmology]\n", "[cosmology]\nLSS_aniso_lx = 0.1\nLSS_aniso_ly = 0.05\nLSS_aniso_lz = -0.15\n")),  # :238-242, 492-496, 931-934
+    "fcc_particles": (3, dict(lattice="fcc", particles=True), None),
+    "rsc_particles": (2, dict(lattice="rsc", particles=True), None),
+    "baryons_3lpt_bcc_particles": (3, dict(lattice="bcc", particles=True, baryons=True), None),
+}
+
+
+def _check_option_sweep(ref_exe, our_exe, tmp):
+    tmp = str(tmp)
+    for tag, (order, kw, edit) in OPTION_SWEEP.items():
+        _run(ref_exe, tmp, "r_" + tag, order, edit=edit, **kw)
+        _run(our_exe, tmp, "d_" + tag, order, edit=edit, **kw)
+        species = ("DM", "BA") if kw.get("baryons") else ("DM",)
+        for sp in species:
+            if kw.get("particles"):
+                for k, dt in (("pos.f64", np.float64), ("vel.f64", np.float64), ("ids.u64", np.uint64)):
+                    a = np.fromfile(os.path.join(tmp, f"r_{tag}.{sp}.{k}"), dtype=dt)
+                    b = np.fromfile(os.path.join(tmp, f"d_{tag}.{sp}.{k}"), dtype=dt)
+                    assert a.size and a.size == b.size, (tag, sp, k)
+                    if dt == np.uint64:
+                        assert np.array_equal(a, b), (tag, sp, k)
+                    else:
+                        assert np.abs(a - b).max() <= (4e-16 if k.startswith("pos") else TOL * np.abs(a).max()), (tag, sp, k)
+            else:
+                a, b = _fields(tmp, "r_" + tag, sp), _fields(tmp, "d_" + tag, sp)
+                for c in FIELDS:
+                    assert np.isfinite(a[c]).all() and np.abs(a[c] - b[c]).max() <= TOL * np.abs(a[c]).max(), (tag, sp, c)
+    # the options really change the result
+    base = _fields(tmp, "r_fixing")
+    for tag in ("fnl", "gnl", "tides", "inversion_corners"):
+        assert np.abs(_fields(tmp, "r_" + tag)["vx"] - base["vx"]).max() > 1e-6 * np.abs(base["vx"]).max(), tag
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_driver_options_reference_itself_vs_dropin(tmp_path):
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    _check_option_sweep(os.path.join(CPP, "_dropin", "monofonIC_ref_cpu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp_path)

@@ -612,6 +612,9 @@ OPTION_SWEEP = {
     "fcc_particles": (3, dict(lattice="fcc", particles=True), None),
     "rsc_particles": (2, dict(lattice="rsc", particles=True), None),
     "baryons_3lpt_bcc_particles": (3, dict(lattice="bcc", particles=True, baryons=True), None),
+    # masked sc lattice (include/particle_generator.hh:171-260): both species on one lattice, selected by a 2x2x2 mask
+    "masked_particles": (2, dict(lattice="masked", particles=True, baryons=True), None),
+    "masked_type1_particles": (2, dict(lattice="masked", particles=True, baryons=True), lambda t: t.replace("[setup]\n", "[setup]\nParticleMaskType = 1\n")),
 }
 
 

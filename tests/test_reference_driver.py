@@ -652,3 +652,28 @@ def test_driver_options_reference_itself_vs_dropin(tmp_path):
     r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     _check_option_sweep(os.path.join(CPP, "_dropin", "monofonIC_ref_cpu"), os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp_path)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_naive_convolver_build_reference_itself_vs_dropin(tmp_path):
+    """CONVOLVER_TYPE=NAIVE builds of both executables (include/convolution.hh:296-426: the same named products without padding,
+    aliased, Nyquist planes kept): identical configurations, 2LPT and 3LPT fields and a MUSIC1 run; and the aliased result really
+    differs from the dealiased one"""
+    import emu_util
+
+    emu_util.build_emu()
+    r = subprocess.run(["make", "-s", "-C", CPP, "-j4", "emu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    tmp = str(tmp_path)
+    ref, ours = os.path.join(CPP, "_dropin", "monofonIC_ref_cpu_naive"), os.path.join(CPP, "_dropin", "monofonIC_mfb_naive_emu")
+    for tag, order, gen in (("n2", 2, "NGENIC"), ("n3", 3, "NGENIC"), ("nm", 2, "MUSIC1")):
+        out = _run(ref, tmp, "r" + tag, order, generator=gen)
+        assert "Convolutions : naive" in out
+        out = _run(ours, tmp, "d" + tag, order, generator=gen)
+        assert "Convolutions : naive" in out
+        a, b = _fields(tmp, "r" + tag), _fields(tmp, "d" + tag)
+        for c in FIELDS:
+            assert np.abs(a[c] - b[c]).max() <= TOL * np.abs(a[c]).max(), (tag, c)
+    _run(os.path.join(CPP, "_dropin", "monofonIC_mfb_emu"), tmp, "o3", 3)
+    o3, n3 = _fields(tmp, "o3"), _fields(tmp, "dn3")
+    assert np.abs(o3["vx"] - n3["vx"]).max() > 1e-7 * np.abs(o3["vx"]).max()
